@@ -1,0 +1,145 @@
+/*
+ * lncde_b200.h – C ABI of the B200-native Log-ODE hot path of log-neural-cdes.
+ *
+ * This is the drop-in boundary.  The reference (pure Python/JAX) has no FFI of
+ * its own; each entry point below replaces the XLA-lowered body of the reference
+ * function cited beside it (paths relative to the reference repository root).
+ * A host binding (ctypes here, jax.ffi where JAX exists – see INTEGRATION.md)
+ * passes raw DEVICE pointers, a CUDA stream and integer shapes.
+ *
+ * Conventions
+ *  - all tensors row-major, contiguous, fp32 unless noted; int tables are int32
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream)
+ *  - nothing allocates, synchronises or creates streams; all work is enqueued
+ *    on `stream`; outputs are caller-allocated and fully overwritten
+ *  - return value: 0 OK; <0 argument errors (checked before any launch);
+ *    >0 a cudaError_t from the launch
+ *  - re-entrant and thread-safe; the only process-wide state is an immutable,
+ *    mutex-guarded host cache of Hall tables keyed by (width, depth)
+ */
+#ifndef LNCDE_B200_H_
+#define LNCDE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LNCDE_OK 0
+#define LNCDE_ERR_NULL (-1)        /* required pointer is NULL                 */
+#define LNCDE_ERR_SHAPE (-2)       /* non-positive / inconsistent dimension    */
+#define LNCDE_ERR_UNSUPPORTED (-3) /* depth / width outside the compiled range */
+#define LNCDE_ERR_WORKSPACE (-4)   /* workspace too small                      */
+#define LNCDE_ERR_ALIGN (-5)       /* pointer not 16-byte aligned              */
+
+/* flags */
+#define LNCDE_FLAG_COMPAT 1u /* reproduce reference quirks */
+
+const char* lncde_version(void);
+/* Human-readable text for a status returned by any entry point. */
+const char* lncde_strerror(int status);
+
+/* ------------------------------------------------------------------ K0 ---
+ * Hall basis and tensor->Lie projection tables (host, cached).
+ * Replaces data_dir/hall_set.py:60-119 (HallSet.__init__/grow_up),
+ * :132-161 (product), :191-208 (rbracket), :234-256 (t2l_matrix).           */
+
+/* len(HallSet(width, depth).data), i.e. 1 + dim Lie^{<=depth}; <0 on error. */
+int lncde_hall_size(int width, int depth);
+/* pairs[n][2] = HallSet.data (row 0 = (0,0), letters (0,i)).                */
+int lncde_hall_basis(int width, int depth, int32_t* pairs);
+/* 1 + w + ... + w^depth (hall_set.py:28-33).                                */
+int64_t lncde_tensor_dim(int width, int depth);
+/* Number of non-zeros of t2l_matrix(depth).                                 */
+int lncde_hall_t2l_nnz(int width, int depth);
+/* t2l_matrix(depth) in CSR over its len(data) rows; column = flat tensor
+ * index INCLUDING the scalar slot 0 (so it is exactly hall_set.py's column).
+ * rowptr[n+1], cols[nnz], vals[nnz].                                        */
+int lncde_hall_t2l_csr(int width, int depth, int32_t* rowptr, int32_t* cols, float* vals);
+
+/* ------------------------------------------------------------------ K1 ---
+ * Batched per-interval truncated log-signature in the Hall basis.
+ * Replaces data_dir/generate_paths.py:22-77 (calc_paths) including
+ * hall_basis_logsig (:14-19) and the signax signature/log/flatten it calls.
+ *
+ *   data   [B, L, C]   control path samples
+ *   logsig [B, K, D]   K = lncde_logsig_num_windows(L, stepsize),
+ *                      D = lncde_hall_size(C, depth); column 0 is always 0
+ *   chunk  : with LNCDE_FLAG_COMPAT, the remainder window of sample b gets the
+ *            last point of sample b-1 prepended unless b % chunk == 0
+ *            (generate_paths.py:59; chunk = B for one calc_paths call, 128 for
+ *            datasets.py:43-71 batch_calc_paths).  Ignored without the flag.
+ *   t2l_*  : device CSR from lncde_hall_t2l_csr; may be NULL when depth <= 2
+ *            and C <= 8 (closed-form Levy-area path).
+ * depth in [1, 4].                                                          */
+int lncde_logsig_num_windows(int L, int stepsize);
+int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int L, int C,
+                     int stepsize, int depth, unsigned flags, int chunk,
+                     const int32_t* t2l_rowptr, const int32_t* t2l_cols, const float* t2l_vals);
+
+/* ------------------------------------------------------------------ K3 ---
+ * Log-NCDE: fixed-step Heun solve of the Lie-bracket Log-ODE field.
+ * Replaces models/LogNeuralCDEs.py:107-162 (LogNeuralCDE.__call__, inner func)
+ * and the diffrax Heun/ConstantStepSize loop it drives, batched over samples
+ * (train.py:52-68 jax.vmap).
+ *
+ *   params : flat fp32 buffer [W0|b0|W1|b1|...|Wn|bn] of the vector-field MLP
+ *            (eqx.nn.MLP layout: W_l[out,in] row-major, y = W x + b),
+ *            layer sizes  H -> width (x n_hidden) -> C*H
+ *   logsig [B, K, D]; y0 [B, H]
+ *   stage_row[n_steps*2] int32: logsig row read by each Heun stage
+ *            (searchsorted(intervals, t) - 1, wrapped), stage_scale[n_steps*2]:
+ *            dt / (intervals[idx] - intervals[idx-1])   (LogNeuralCDEs.py:114-138)
+ *   ys [B, n_steps+1, H]: the state after every step (ys[:,0] = y0) – the
+ *            checkpoints the backward sweep and the regression read-out need
+ * depth in {1, 2}.                                                          */
+int lncde_logncde_param_count(int H, int C, int width, int n_hidden);
+size_t lncde_logncde_fwd_smem_bytes(int H, int C, int width, int n_hidden);
+int lncde_logncde_fwd(void* stream, const float* params, const float* logsig, const float* y0,
+                      const int32_t* stage_row, const float* stage_scale, float* ys, int B, int K,
+                      int D, int H, int C, int width, int n_hidden, int depth, int n_steps);
+
+/* Backward sweep (discretise-then-optimise, what diffrax's default adjoint
+ * returns).  g_ys [B, n_steps+1, H] is dLoss/d ys (zero where unused).
+ * Outputs: g_params [P] (summed over the batch), g_y0 [B, H].
+ * workspace: lncde_logncde_bwd_workspace_bytes(...) bytes of device scratch. */
+size_t lncde_logncde_bwd_workspace_bytes(int B, int H, int C, int width, int n_hidden, int depth,
+                                         int n_steps);
+int lncde_logncde_bwd(void* stream, const float* params, const float* logsig,
+                      const int32_t* stage_row, const float* stage_scale, const float* ys,
+                      const float* g_ys, float* g_params, float* g_y0, int B, int K, int D, int H,
+                      int C, int width, int n_hidden, int depth, int n_steps, void* workspace,
+                      size_t workspace_bytes);
+
+/* ------------------------------------------------------------------ K2 ---
+ * Structured linear CDE (D / BD / DE-LNCDE): flows F_k = I + sum_l logsig[k,l] A_l
+ * and the recurrence h_k = F_k h_{k-1}, k = 1..T-1 (flow 0 is never applied).
+ * Replaces models/LinearNeuralCDEs.py:302-316 (diagonal), :318-353 (block),
+ * :355-386 (scanner).
+ *
+ *   lie [nb, bs, bs, n_basis]  bracket matrices from log_ode (:192-232);
+ *        for bs == 1 this is vf_A^T laid out [H, n_coeff]
+ *   logsig [B, T, D]; uses columns 1 .. n_basis
+ *   y0 [B, H];  ys [B, T, H] (ys[:,0] = y0)                                  */
+int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, const float* y0,
+                          float* ys, int B, int T, int D, int nb, int bs, int n_basis);
+/* g_ys [B,T,H] -> g_lie [nb,bs,bs,n_basis] (summed over batch), g_y0 [B,H].
+ * workspace: lncde_linear_scan_bwd_workspace_bytes bytes.                    */
+size_t lncde_linear_scan_bwd_workspace_bytes(int B, int T, int nb, int bs, int n_basis);
+int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, const float* ys,
+                          const float* g_ys, float* g_lie, float* g_y0, int B, int T, int D, int nb,
+                          int bs, int n_basis, void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------ K4 ---
+ * Fused Adam update on a flat parameter buffer (optax.adam defaults,
+ * train.py:134-135,183): m,v moments updated in place, bias-corrected.
+ * grad_scale multiplies the gradient first (1/world after an all-reduce sum). */
+int lncde_adam_step(void* stream, float* params, const float* grads, float* m, float* v, int64_t n,
+                    float lr, float beta1, float beta2, float eps, int step, float grad_scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LNCDE_B200_H_ */

@@ -1,0 +1,451 @@
+// K1 – batched per-interval truncated log-signature in the Hall basis (sm_100a).
+//
+// Replaces data_dir/generate_paths.py:22-77 (calc_paths -> hall_basis_logsig ->
+// signax signature/log/flatten -> t2l projection).  Two kernels:
+//
+//  * logsig_levy_kernel<C, DEPTH2>  (C <= 8, depth <= 2): HBM-bound streaming
+//    kernel.  A CTA stages a contiguous tile of one sample's path
+//    (WT windows x stepsize points x C channels, read once, 128-bit coalesced)
+//    into shared memory with an odd window stride (conflict-free), one thread
+//    then walks one window keeping the C running coordinates and the C(C-1)/2
+//    Levy areas in registers, results are transposed through shared memory and
+//    written back as one contiguous, coalesced block.  The Hall projection at
+//    depth 2 is the identity on the upper triangle (t2l folds to "take L2[i,j],
+//    i<j"), so no table is read.
+//  * logsig_tensor_kernel (any C, depth <= 4): one warp per window; truncated
+//    signature levels live in shared memory, Chen/Horner update per increment,
+//    log and the sparse t2l map (CSR from K0) are folded into the epilogue.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "lncde_b200.h"
+
+namespace lncde {
+
+// ----------------------------------------------------------------------------
+// geometry shared by both kernels.  After the reference's zero-prepend the
+// padded path has n = L+1 points xt[0] = 0, xt[m] = x[m-1].  Full window k
+// (0 <= k < q) holds xt[k*s .. k*s+s-1] with basepoint xt[k*s-1] (0 for k = 0):
+// in ORIGINAL rows that is basepoint row k*s-2 and new rows k*s-1 .. k*s+s-2,
+// rows < 0 reading as 0.  The remainder window (r = n % s != 0) holds original
+// rows L-r-1 .. L-1 (its true predecessor first) and, in compat mode, one more
+// leading point: the last row of the previous sample (generate_paths.py:59).
+// ----------------------------------------------------------------------------
+
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <int C, bool DEPTH2>
+struct LevyState {
+  float base[C];
+  float prev[C];   // previous point minus base
+  float area[DEPTH2 ? (C * (C - 1)) / 2 + 1 : 1];
+
+  __device__ __forceinline__ void init(const float* b) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      base[c] = b[c];
+      prev[c] = 0.f;
+    }
+    if (DEPTH2) {
+#pragma unroll
+      for (int p = 0; p < (C * (C - 1)) / 2; ++p) area[p] = 0.f;
+    }
+  }
+  // advance by one point x (absolute coordinates)
+  __device__ __forceinline__ void step(const float* x) {
+    float cur[C], inc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      cur[c] = x[c] - base[c];
+      inc[c] = cur[c] - prev[c];
+    }
+    if (DEPTH2) {
+      int p = 0;
+#pragma unroll
+      for (int i = 0; i < C; ++i)
+#pragma unroll
+        for (int j = i + 1; j < C; ++j) {
+          // 2*dA_ij = a_i * dx_j - a_j * dx_i, a = position before the increment
+          area[p] = fmaf(prev[i], inc[j], area[p]);
+          area[p] = fmaf(-prev[j], inc[i], area[p]);
+          ++p;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) prev[c] = cur[c];
+  }
+  // write the D-float row [0 | level1 | level2]
+  __device__ __forceinline__ void store(float* out) const {
+    out[0] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[1 + c] = prev[c];
+    if (DEPTH2) {
+#pragma unroll
+      for (int p = 0; p < (C * (C - 1)) / 2; ++p) out[1 + C + p] = 0.5f * area[p];
+    }
+  }
+};
+
+struct LevyParams {
+  const float* data;
+  float* out;
+  int B, L, s, q, r, K, D, WT, tiles, compat, chunk;
+  int stride;         // shared-memory floats per window (s*C, made odd)
+  uint32_t sc_magic;  // ceil(2^32 / (s*C))
+};
+
+template <int C, bool DEPTH2>
+__global__ void __launch_bounds__(128) logsig_levy_kernel(const LevyParams p) {
+  extern __shared__ float smem[];
+  constexpr int D = 1 + C + (DEPTH2 ? (C * (C - 1)) / 2 : 0);
+  const int b = blockIdx.x / p.tiles;
+  const int tile = blockIdx.x - b * p.tiles;
+  const int k0 = tile * p.WT;
+  const int nw = min(p.WT, p.q - k0);  // full windows in this tile (may be 0 for K == remainder only)
+  const int sC = p.s * C;
+  const float* xb = p.data + (size_t)b * p.L * C;
+
+  // ---- stage rows k0*s-2 .. k0*s-2 + nw*s  (nw*s + 1 rows) ------------------
+  // smem: [0,C) tile basepoint row; window w's s rows at C + w*stride.
+  float* tile_base = smem;
+  float* win = smem + C;
+  const long long row0 = (long long)k0 * p.s - 2;  // basepoint row of window k0
+  if (threadIdx.x < C) {
+    tile_base[threadIdx.x] = row0 >= 0 ? ld_stream(xb + row0 * C + threadIdx.x) : 0.f;
+  }
+  {
+    const long long g_begin = (row0 + 1) * C;               // first float wanted (may be < 0)
+    const int n_f = nw * sC;                                 // floats wanted
+    const long long g_lo = g_begin < 0 ? 0 : g_begin;        // clamp: row -1 is the zero point
+    // zero-fill the part that lies before the sample start (only tile 0: C floats)
+    for (int t = threadIdx.x; t < (int)(g_lo - g_begin); t += blockDim.x) win[t] = 0.f;
+    const float* src = xb + g_lo;
+    const int t_off = (int)(g_lo - g_begin);
+    const int n_ld = n_f - t_off;
+    // 128-bit body on the 16 B aligned part, scalar head/tail
+    const int head = min(n_ld, (int)(((16 - ((uintptr_t)src & 15)) & 15) >> 2));
+    const int n_v4 = (n_ld - head) >> 2;
+    const float4* src4 = reinterpret_cast<const float4*>(src + head);
+    auto put = [&](int t, float v) {
+      const uint32_t w = __umulhi((uint32_t)t, p.sc_magic);
+      win[(int)w * p.stride + (t - (int)w * sC)] = v;
+    };
+    if (threadIdx.x < head) put(t_off + threadIdx.x, ld_stream(src + threadIdx.x));
+    for (int i = threadIdx.x; i < n_v4; i += blockDim.x * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * (int)blockDim.x < n_v4) v[u] = ld_stream4(src4 + i + u * blockDim.x);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ii = i + u * (int)blockDim.x;
+        if (ii < n_v4) {
+          const int t = t_off + head + 4 * ii;
+          put(t, v[u].x);
+          put(t + 1, v[u].y);
+          put(t + 2, v[u].z);
+          put(t + 3, v[u].w);
+        }
+      }
+    }
+    const int tail0 = head + 4 * n_v4;
+    if (threadIdx.x < n_ld - tail0) put(t_off + tail0 + threadIdx.x, ld_stream(src + tail0 + threadIdx.x));
+  }
+  __syncthreads();
+
+  // ---- one thread per window ------------------------------------------------
+  LevyState<C, DEPTH2> st;
+  const int w = threadIdx.x;
+  if (w < nw) {
+    const float* bp = (w == 0) ? tile_base : (win + (w - 1) * p.stride + (p.s - 1) * C);
+    float tmp[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) tmp[c] = bp[c];
+    st.init(tmp);
+    const float* rows = win + w * p.stride;
+    for (int l = 0; l < p.s; ++l) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmp[c] = rows[l * C + c];
+      st.step(tmp);
+    }
+  }
+  __syncthreads();
+  // ---- transpose through shared memory, contiguous coalesced store ---------
+  if (w < nw) st.store(smem + w * D);  // D odd or even: row stride D, lanes hit distinct rows
+  __syncthreads();
+  {
+    float* dst = p.out + ((size_t)b * p.K + k0) * D;
+    const int n_o = nw * D;
+    for (int t = threadIdx.x; t < n_o; t += blockDim.x) dst[t] = smem[t];
+  }
+
+  // ---- remainder window: handled by the sample's last tile, one thread -----
+  if (p.r != 0 && tile == p.tiles - 1 && threadIdx.x == 0) {
+    float tmp[C];
+    const bool extra = p.compat != 0;
+    const float* first = xb + (size_t)(p.L - p.r - 1) * C;  // true predecessor row
+    if (extra) {
+      const bool has_prev = (b % p.chunk) != 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmp[c] = has_prev ? xb[-C + c] : 0.f;  // last row of sample b-1
+      st.init(tmp);
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmp[c] = first[c];
+      st.step(tmp);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmp[c] = first[c];
+      st.init(tmp);
+    }
+    for (int l = 1; l <= p.r; ++l) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmp[c] = first[l * C + c];
+      st.step(tmp);
+    }
+    float row[D];
+    st.store(row);
+    float* dst = p.out + ((size_t)b * p.K + p.q) * D;
+#pragma unroll
+    for (int c = 0; c < D; ++c) dst[c] = row[c];
+  }
+}
+
+// ----------------------------------------------------------------------------
+// generic kernel: any width, depth <= 4, one warp per window.
+// ----------------------------------------------------------------------------
+struct TensorParams {
+  const float* data;
+  float* out;
+  const int32_t* rowptr;
+  const int32_t* cols;
+  const float* vals;
+  int B, L, C, s, q, r, K, D, depth, compat, chunk;
+  int tdim;  // C + C^2 + ... + C^depth
+};
+
+// read point m of the (virtual) window `k` of sample b.  Point 0 is the basepoint.
+__device__ __forceinline__ float window_point(const TensorParams& p, const float* xb, int b, int k,
+                                              int m, int c) {
+  if (k < p.q) {
+    const long long row = (long long)k * p.s - 2 + m;
+    return row >= 0 ? xb[row * p.C + c] : 0.f;
+  }
+  // remainder window
+  if (p.compat) {
+    if (m == 0) return (b % p.chunk) != 0 ? xb[-p.C + c] : 0.f;
+    return xb[(size_t)(p.L - p.r - 2 + m) * p.C + c];
+  }
+  return xb[(size_t)(p.L - p.r - 1 + m) * p.C + c];
+}
+
+// entry (word of length n, flat index e within its level) of log(1+S), depth <= 4
+__device__ float log_entry(const float* S, const int* off, int C, int n, int e) {
+  // off[k] = offset of level k (1-based) inside S
+  if (n == 1) return S[off[1] + e];
+  if (n == 2) {
+    const int i = e / C, j = e - i * C;
+    return S[off[2] + e] - 0.5f * S[off[1] + i] * S[off[1] + j];
+  }
+  if (n == 3) {
+    const int i = e / (C * C), jk = e - i * C * C, j = jk / C, k = jk - j * C;
+    const float a = S[off[1] + i], b = S[off[1] + j], c = S[off[1] + k];
+    return S[off[3] + e] - 0.5f * (a * S[off[2] + j * C + k] + S[off[2] + i * C + j] * c) +
+           (1.f / 3.f) * a * b * c;
+  }
+  // n == 4
+  const int C2 = C * C, C3 = C2 * C;
+  const int i = e / C3, r1 = e - i * C3, j = r1 / C2, r2 = r1 - j * C2, k = r2 / C, l = r2 - k * C;
+  const float s1i = S[off[1] + i], s1j = S[off[1] + j], s1k = S[off[1] + k], s1l = S[off[1] + l];
+  const float s2ij = S[off[2] + i * C + j], s2jk = S[off[2] + j * C + k], s2kl = S[off[2] + k * C + l];
+  const float s3ijk = S[off[3] + (i * C + j) * C + k], s3jkl = S[off[3] + (j * C + k) * C + l];
+  return S[off[4] + e] - 0.5f * (s1i * s3jkl + s2ij * s2kl + s3ijk * s1l) +
+         (1.f / 3.f) * (s1i * s1j * s2kl + s1i * s2jk * s1l + s2ij * s1k * s1l) -
+         0.25f * s1i * s1j * s1k * s1l;
+}
+
+__global__ void __launch_bounds__(128) logsig_tensor_kernel(const TensorParams p) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  float* S = smem + (size_t)warp * (p.tdim + 2 * p.C);
+  float* z = S + p.tdim;       // current increment
+  float* prev = z + p.C;       // previous point
+  int off[5];
+  off[1] = 0;
+  for (int k = 2, pw = p.C; k <= 4; ++k, pw *= p.C) off[k] = off[k - 1] + pw;
+  const int C = p.C;
+
+  const long long n_win = (long long)p.B * p.K;
+  for (long long wid = (long long)blockIdx.x * wpb + warp; wid < n_win; wid += (long long)gridDim.x * wpb) {
+    const int b = (int)(wid / p.K), k = (int)(wid - (long long)b * p.K);
+    const float* xb = p.data + (size_t)b * p.L * C;
+    const int n_inc = k < p.q ? p.s : (p.compat ? p.r + 1 : p.r);
+    for (int e = lane; e < p.tdim; e += 32) S[e] = 0.f;
+    for (int c = lane; c < C; c += 32) prev[c] = window_point(p, xb, b, k, 0, c);
+    __syncwarp();
+    for (int m = 1; m <= n_inc; ++m) {
+      for (int c = lane; c < C; c += 32) {
+        const float x = window_point(p, xb, b, k, m, c);
+        z[c] = x - prev[c];
+        prev[c] = x;
+      }
+      __syncwarp();
+      // Chen/Horner, top level first so lower levels are still the old ones
+      int lvl_size = 1;
+      for (int d = 1; d < p.depth; ++d) lvl_size *= C;
+      lvl_size *= C;
+      for (int n = p.depth; n >= 1; --n) {
+        for (int e = lane; e < lvl_size; e += 32) {
+          // decode word digits, most significant first
+          int idx[4];
+          int rem = e;
+          for (int t = n - 1; t >= 0; --t) {
+            idx[t] = rem % C;
+            rem /= C;
+          }
+          float cur = S[off[1] + idx[0]] + z[idx[0]] / (float)n;
+          int pre = idx[0];
+          for (int t = 1; t < n; ++t) {
+            pre = pre * C + idx[t];
+            cur = fmaf(cur, z[idx[t]] / (float)(n - t), S[off[t + 1] + pre]);
+          }
+          // note: for t = n-1 the fma added S_n[e] itself (pre == e)
+          if (n == 1) cur = S[off[1] + e] + z[e];
+          S[off[n] + e] = cur;
+        }
+        __syncwarp();
+        lvl_size /= C;
+      }
+    }
+    // log + Hall projection; row 0 is identically 0
+    float* dst = p.out + (size_t)wid * p.D;
+    for (int h = lane; h < p.D; h += 32) {
+      float acc = 0.f;
+      const int lo = p.rowptr[h], hi = p.rowptr[h + 1];
+      for (int t = lo; t < hi; ++t) {
+        int col = p.cols[t] - 1;  // drop the scalar slot
+        int n = 1, pw = C;
+        while (col >= pw) {
+          col -= pw;
+          pw *= C;
+          ++n;
+        }
+        acc = fmaf(p.vals[t], log_entry(S, off, C, n, col), acc);
+      }
+      dst[h] = acc;
+    }
+    __syncwarp();
+  }
+}
+
+template <int C>
+static int launch_levy(cudaStream_t st, LevyParams p, int depth, size_t smem) {
+  const int grid = p.B * p.tiles;
+  if (depth == 2) {
+    auto k = logsig_levy_kernel<C, true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, 128, smem, st>>>(p);
+  } else {
+    auto k = logsig_levy_kernel<C, false>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, 128, smem, st>>>(p);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace lncde
+
+extern "C" {
+
+int lncde_logsig_num_windows(int L, int stepsize) {
+  if (L < 1 || stepsize < 1) return LNCDE_ERR_SHAPE;
+  const int n = L + 1;
+  const int s = stepsize > n ? n : stepsize;
+  return n / s + (n % s != 0 ? 1 : 0);
+}
+
+int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int L, int C, int stepsize,
+                     int depth, unsigned flags, int chunk, const int32_t* t2l_rowptr,
+                     const int32_t* t2l_cols, const float* t2l_vals) {
+  using namespace lncde;
+  if (!data || !logsig) return LNCDE_ERR_NULL;
+  if (B < 1 || L < 1 || C < 1 || stepsize < 1) return LNCDE_ERR_SHAPE;
+  if (depth < 1 || depth > 4) return LNCDE_ERR_UNSUPPORTED;
+  const int compat = (flags & LNCDE_FLAG_COMPAT) ? 1 : 0;
+  if (compat && chunk < 1) return LNCDE_ERR_SHAPE;
+  const int D = lncde_hall_size(C, depth);
+  if (D < 0) return D;
+  const int n = L + 1;
+  const int s = stepsize > n ? n : stepsize;
+  const int q = n / s, r = n % s;
+  const int K = q + (r ? 1 : 0);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // closed-form streaming kernel: C <= 8, depth <= 2, and a tile of >= 32
+  // windows must fit comfortably in shared memory
+  const long long sC = (long long)s * C;
+  if (C <= 8 && depth <= 2 && sC <= 640) {
+    LevyParams p;
+    p.data = data;
+    p.out = logsig;
+    p.B = B; p.L = L; p.s = s; p.q = q; p.r = r; p.K = K; p.D = D;
+    p.compat = compat;
+    p.chunk = compat ? chunk : 1;
+    p.stride = (int)(sC | 1);
+    p.sc_magic = (uint32_t)((0x100000000ull + sC - 1) / sC);
+    int WT = 128;
+    while (WT > 32 && (size_t)(C + (size_t)WT * p.stride) * 4 > 80 * 1024) WT >>= 1;
+    p.WT = WT;
+    p.tiles = (q + WT - 1) / WT;
+    if (p.tiles < 1) p.tiles = 1;
+    size_t smem = (size_t)(C + (size_t)WT * p.stride) * 4;
+    const size_t smem_out = (size_t)WT * D * 4;
+    if (smem_out > smem) smem = smem_out;
+    switch (C) {
+      case 1: return launch_levy<1>(st, p, depth, smem);
+      case 2: return launch_levy<2>(st, p, depth, smem);
+      case 3: return launch_levy<3>(st, p, depth, smem);
+      case 4: return launch_levy<4>(st, p, depth, smem);
+      case 5: return launch_levy<5>(st, p, depth, smem);
+      case 6: return launch_levy<6>(st, p, depth, smem);
+      case 7: return launch_levy<7>(st, p, depth, smem);
+      case 8: return launch_levy<8>(st, p, depth, smem);
+    }
+  }
+
+  if (!t2l_rowptr || !t2l_cols || !t2l_vals) return LNCDE_ERR_NULL;
+  TensorParams p;
+  p.data = data; p.out = logsig;
+  p.rowptr = t2l_rowptr; p.cols = t2l_cols; p.vals = t2l_vals;
+  p.B = B; p.L = L; p.C = C; p.s = s; p.q = q; p.r = r; p.K = K; p.D = D; p.depth = depth;
+  p.compat = compat;
+  p.chunk = compat ? chunk : 1;
+  const long long tdim = lncde_tensor_dim(C, depth) - 1;
+  p.tdim = (int)tdim;
+  int wpb = 4;
+  size_t per_warp = (size_t)(tdim + 2 * C) * 4;
+  while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+  const size_t smem = per_warp * wpb;
+  if (smem > 227 * 1024) return LNCDE_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(logsig_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  long long n_win = (long long)B * K;
+  long long grid = (n_win + wpb - 1) / wpb;
+  if (grid > 148 * 64) grid = 148 * 64;
+  logsig_tensor_kernel<<<(int)grid, wpb * 32, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+"""ctypes binding of include/lncde_b200.h (the tested host binding; the jax.ffi
+binding a JAX installation would use is shown in INTEGRATION.md)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "liblncde_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+c_fp = C.c_void_p  # device pointers travel as void*
+
+
+class LncdeError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    i, i64, u, f, vp, sz = C.c_int, C.c_int64, C.c_uint, C.c_float, C.c_void_p, C.c_size_t
+    sig = {
+        "lncde_version": (C.c_char_p, []),
+        "lncde_strerror": (C.c_char_p, [i]),
+        "lncde_hall_size": (i, [i, i]),
+        "lncde_hall_basis": (i, [i, i, vp]),
+        "lncde_tensor_dim": (i64, [i, i]),
+        "lncde_hall_t2l_nnz": (i, [i, i]),
+        "lncde_hall_t2l_csr": (i, [i, i, vp, vp, vp]),
+        "lncde_logsig_num_windows": (i, [i, i]),
+        "lncde_logsig_fwd": (i, [vp, vp, vp, i, i, i, i, i, u, i, vp, vp, vp]),
+        "lncde_logncde_param_count": (i, [i, i, i, i]),
+        "lncde_logncde_fwd_smem_bytes": (sz, [i, i, i, i]),
+        "lncde_logncde_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i]),
+        "lncde_logncde_bwd_workspace_bytes": (sz, [i, i, i, i, i, i, i]),
+        "lncde_logncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz]),
+        "lncde_linear_scan_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i]),
+        "lncde_linear_scan_bwd_workspace_bytes": (sz, [i, i, i, i, i]),
+        "lncde_linear_scan_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]),
+        "lncde_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, i, f]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+EXPORTS = None
+
+
+def lib():
+    """The loaded C-ABI library; raises LncdeError if it has not been built."""
+    global _lib, EXPORTS
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise LncdeError(
+                    f"{LIB_PATH} is missing – run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU fallback)")
+            handle = C.CDLL(LIB_PATH)
+            EXPORTS = _declare(handle)
+            _lib = handle
+    return _lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = lib().lncde_strerror(int(status)).decode()
+        raise LncdeError(f"{what or 'lncde call'} failed with status {status}: {msg}")
+
+
+def require_cuda(*tensors):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise LncdeError("lncde needs a CUDA device (sm_100a); there is no CPU fallback")
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise LncdeError("lncde operators take CUDA tensors; got a CPU tensor (no CPU fallback)")
+        if not t.is_contiguous():
+            raise LncdeError("lncde operators take contiguous tensors")
+
+
+def stream_ptr():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())

@@ -1,0 +1,60 @@
+"""``calc_paths`` – mirror of data_dir/generate_paths.py:22-77 over kernel K1."""
+from __future__ import annotations
+
+import functools
+
+import torch
+
+from .. import _lib
+from .hall_set import HallSet
+
+
+@functools.lru_cache(maxsize=None)
+def _device_t2l(width: int, depth: int, device_index: int):
+    rowptr, cols, vals = HallSet(width, depth).t2l_csr()
+    dev = torch.device("cuda", device_index)
+    return (torch.from_numpy(rowptr).to(dev), torch.from_numpy(cols).to(dev), torch.from_numpy(vals).to(dev))
+
+
+def logsig_dim(width: int, depth: int) -> int:
+    return len(HallSet(width, depth))
+
+
+def calc_paths(data: torch.Tensor, stepsize, depth: int, *, compat: bool = True, chunk: int | None = None,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """data[B, L, C] (CUDA fp32) -> logsigs[B, K, D].
+
+    Same argument meaning as the reference: ``stepsize`` is clamped to L+1,
+    column 0 of the result is 0, columns 1..C the increments, then the Hall
+    coordinates of levels 2.. in Hall order.  ``compat`` reproduces the
+    remainder-window quirk of generate_paths.py:59 for a batch processed in
+    chunks of ``chunk`` samples (default: the whole call, as in calc_paths).
+    depth >= 3 (<= 4) extends the reference (which supports 1 and 2 only).
+    """
+    _lib.require_cuda(data)
+    if data.dtype != torch.float32 or data.dim() != 3:
+        raise _lib.LncdeError("calc_paths expects a float32 tensor [B, L, C]")
+    L = _lib.lib()
+    B, Ln, Cn = data.shape
+    stepsize = int(stepsize)
+    K = L.lncde_logsig_num_windows(Ln, stepsize)
+    _lib.check(min(K, 0), "lncde_logsig_num_windows")
+    D = logsig_dim(Cn, depth)
+    if out is None:
+        out = torch.empty((B, K, D), device=data.device, dtype=torch.float32)
+    elif tuple(out.shape) != (B, K, D) or not out.is_contiguous():
+        raise _lib.LncdeError("calc_paths: out has the wrong shape")
+    rowptr, cols, vals = _device_t2l(Cn, depth, data.device.index or 0)
+    with torch.cuda.device(data.device):
+        st = L.lncde_logsig_fwd(_lib.stream_ptr(), _lib.ptr(data), _lib.ptr(out), B, Ln, Cn, stepsize, depth,
+                                1 if compat else 0, int(chunk or B), _lib.ptr(rowptr), _lib.ptr(cols),
+                                _lib.ptr(vals))
+    _lib.check(st, "lncde_logsig_fwd")
+    return out
+
+
+def batch_calc_paths(data: torch.Tensor, stepsize, depth: int, *, compat: bool = True) -> torch.Tensor:
+    """datasets.py:43-71: the reference loops over chunks of 128 samples; here the
+    whole dataset is ONE launch and the chunk boundary only selects which samples
+    have no predecessor for the remainder-window quirk."""
+    return calc_paths(data, stepsize, depth, compat=compat, chunk=128)
