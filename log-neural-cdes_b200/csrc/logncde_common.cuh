@@ -1,0 +1,310 @@
+// Shared device code of the Log-NCDE solve kernels (K3 forward, K3b backward sweep).
+//
+// One CTA integrates one sample.  The Log-ODE field of models/LogNeuralCDEs.py:113-138
+// is evaluated in the restructured but algebraically identical form
+//
+//   G(y) = sum_i l_i f_i(y) + sum_j [ Df(y) . w_j ]_{block j},   w_j = sum_i Lam_ij f_i(y)
+//
+// with f = reshape(MLP(y), (C, H)) and Lam the antisymmetric matrix of the level-2
+// Hall coordinates (pairs (i,j), i<j, lexicographic = HallSet order).  Each of the C
+// tangents therefore needs only block j of the last layer: 1 primal + C "thin" tangent
+// passes instead of the reference's 1 + C full MLP passes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace lncde {
+
+constexpr int kMaxLayers = 5;   // n_hidden <= 4
+constexpr int kSolveThreads = 512;
+
+struct MlpDesc {
+  int H, C, width, n_hidden, n_layers, depth;
+  int in_dim[kMaxLayers], rows[kMaxLayers];
+  int w_off[kMaxLayers], b_off[kMaxLayers];  // offsets in the flat parameter buffer
+  int stride[kMaxLayers];                     // row stride of the weight copy the kernel reads
+  int sm_off[kMaxLayers];                     // offset of the layer in the smem weight region, -1: global
+  int kq_log2[kMaxLayers];                    // lanes cooperating on one output row
+  int n_params;
+  int weights_in_smem;
+  int smem_weight_floats;
+};
+
+// per-stage intermediates in shared memory (floats)
+struct StageLayout {
+  int a, s, z;       // [n_hidden][width]
+  int o, w, ul;      // [C*H]
+  int u, p;          // [n_hidden][C][width]
+  int yin;           // [H]
+  int total;
+};
+
+__host__ __device__ inline StageLayout make_stage_layout(const MlpDesc& d) {
+  StageLayout L;
+  int off = 0;
+  const int hw = d.n_hidden * d.width, ch = d.C * d.H, cw = d.n_hidden * d.C * d.width;
+  L.a = off; off += hw;
+  L.s = off; off += hw;
+  L.z = off; off += hw;
+  L.o = off; off += ch;
+  L.w = off; off += ch;
+  L.ul = off; off += ch;
+  L.u = off; off += cw;
+  L.p = off; off += cw;
+  L.yin = off; off += d.H;
+  L.total = (off + 3) & ~3;
+  return L;
+}
+
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+
+// out[row] for a batch of NB input vectors; KQ = 2^kq_log2 lanes share one row.
+// emit(row, acc[NB]) is called by the lane with q == 0.
+template <int NB, typename Emit>
+__device__ __forceinline__ void matvec_rows(const float* __restrict__ W, int stride, int rows, int in_dim,
+                                            int kq_log2, const float* __restrict__ in, int in_stride,
+                                            Emit&& emit) {
+  const int KQ = 1 << kq_log2;
+  const int items = rows << kq_log2;
+  for (int base = 0; base < items; base += kSolveThreads) {
+    const int item = base + threadIdx.x;
+    const int row = item >> kq_log2, q = item & (KQ - 1);
+    const bool valid = row < rows;
+    float acc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+    if (valid) {
+      const float* wr = W + (size_t)row * stride;
+      for (int c = q; c < in_dim; c += KQ) {
+        const float wv = wr[c];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[j] = fmaf(wv, in[j * in_stride + c], acc[j]);
+      }
+    }
+    for (int m = KQ >> 1; m >= 1; m >>= 1) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], m);
+    }
+    if (valid && q == 0) emit(row, acc);
+  }
+}
+
+// last layer, tangent j uses only block j:  emit(j, h, dot(W[j*H+h,:], in[j]))
+template <typename Emit>
+__device__ __forceinline__ void matvec_rows_blocked(const float* __restrict__ W, int stride, int C, int H,
+                                                    int in_dim, int kq_log2, const float* __restrict__ in,
+                                                    int in_stride, Emit&& emit) {
+  const int KQ = 1 << kq_log2;
+  const int rows = C * H;
+  const int items = rows << kq_log2;
+  for (int base = 0; base < items; base += kSolveThreads) {
+    const int item = base + threadIdx.x;
+    const int row = item >> kq_log2, q = item & (KQ - 1);
+    const bool valid = row < rows;
+    float acc = 0.f;
+    int j = 0;
+    if (valid) {
+      j = row / H;
+      const float* wr = W + (size_t)row * stride;
+      const float* v = in + j * in_stride;
+      for (int c = q; c < in_dim; c += KQ) acc = fmaf(wr[c], v[c], acc);
+    }
+    for (int m = KQ >> 1; m >= 1; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if (valid && q == 0) emit(j, row - j * H, acc);
+  }
+}
+
+// Transposed product.  out[j*out_stride + c] = sum_r W[(row0_j + r)*stride + c] * v[j*v_stride + r]
+// row0_j = j*nrows if BLOCKED else 0.  `scratch` needs kSolveThreads*NB floats.  Ends with the
+// result visible to all threads (contains __syncthreads).
+template <int NB, bool BLOCKED>
+__device__ __forceinline__ void matvec_cols(const float* __restrict__ W, int stride, int nrows, int in_dim,
+                                            const float* __restrict__ v, int v_stride, float* out,
+                                            int out_stride, float* scratch) {
+  // column-parallel: CP = in_dim rounded up to a multiple of 32 lanes, RQ row groups
+  const int CP = (in_dim + 31) & ~31;
+  const int RQ = max(1, kSolveThreads / CP);
+  const int c = threadIdx.x % CP, rq = threadIdx.x / CP;
+  float acc[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+  if (rq < RQ && c < in_dim) {
+    for (int r = rq; r < nrows; r += RQ) {
+      if (BLOCKED) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          acc[j] = fmaf(W[(size_t)(j * nrows + r) * stride + c], v[j * v_stride + r], acc[j]);
+      } else {
+        const float wv = W[(size_t)r * stride + c];
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[j] = fmaf(wv, v[j * v_stride + r], acc[j]);
+      }
+    }
+  }
+  if (rq < RQ && c < in_dim) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) scratch[(rq * NB + j) * in_dim + c] = acc[j];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NB * in_dim; t += kSolveThreads) {
+    const int j = t / in_dim, cc = t - j * in_dim;
+    float sum = 0.f;
+    for (int g = 0; g < RQ; ++g) sum += scratch[(g * NB + j) * in_dim + cc];
+    out[j * out_stride + cc] = sum;
+  }
+  __syncthreads();
+}
+
+struct StageCtx {
+  const MlpDesc* d;
+  const float* params;     // flat parameter buffer in global memory (biases are read from here)
+  const float* wbase[kMaxLayers];  // weight matrix the kernel reads (smem copy or global)
+  float* G;                // [H] field value (without the stage scale)
+  float* lam;              // [C*C] antisymmetric level-2 matrix, [C] level-1 at lam1
+  float* lam1;
+};
+
+// Load level-1 / level-2 coordinates of a logsig row into shared memory.
+template <int C>
+__device__ __forceinline__ void load_logsig_row(const StageCtx& cx, const float* __restrict__ row) {
+  const int depth = cx.d->depth;
+  if (threadIdx.x < C) cx.lam1[threadIdx.x] = row[1 + threadIdx.x];
+  if (depth == 2 && threadIdx.x < C * C) {
+    const int i = threadIdx.x / C, j = threadIdx.x - i * C;
+    float v = 0.f;
+    if (i != j) {
+      const int a = i < j ? i : j, b = i < j ? j : i;
+      // index of pair (a,b), a<b, lexicographic
+      const int p = a * C - (a * (a + 1)) / 2 + (b - a - 1);
+      v = row[1 + C + p];
+      if (i > j) v = -v;
+    }
+    cx.lam[threadIdx.x] = v;
+  }
+}
+
+// Evaluate the field at buf.yin.  On exit G[h] holds the (unscaled) field and all
+// intermediates needed by the reverse sweep are in `buf`.
+template <int C>
+__device__ __forceinline__ void stage_forward(const StageCtx& cx, float* buf, const StageLayout& L,
+                                              const float* __restrict__ ls_row) {
+  const MlpDesc& d = *cx.d;
+  const int H = d.H, Wd = d.width, NL = d.n_hidden;
+  load_logsig_row<C>(cx, ls_row);
+  // ---- primal pass --------------------------------------------------------
+  const float* in = buf + L.yin;
+  for (int l = 0; l < NL; ++l) {
+    const float* bias = cx.params + d.b_off[l];
+    float* a = buf + L.a + l * Wd;
+    float* s = buf + L.s + l * Wd;
+    float* z = buf + L.z + l * Wd;
+    matvec_rows<1>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], in, 0,
+                   [&](int row, const float* acc) {
+                     const float zz = acc[0] + bias[row];
+                     const float sg = sigmoidf_(zz);
+                     z[row] = zz;
+                     a[row] = zz * sg;
+                     s[row] = sg * (1.f + zz * (1.f - sg));
+                   });
+    __syncthreads();
+    in = a;
+  }
+  {
+    const float* bias = cx.params + d.b_off[NL];
+    float* o = buf + L.o;
+    matvec_rows<1>(cx.wbase[NL], d.stride[NL], d.rows[NL], d.in_dim[NL], d.kq_log2[NL], in, 0,
+                   [&](int row, const float* acc) { o[row] = tanhf(acc[0] + bias[row]); });
+  }
+  __syncthreads();
+  // ---- G = sum_i l_i o_i ; w_j = sum_i Lam_ij o_i ---------------------------
+  {
+    const float* o = buf + L.o;
+    float* w = buf + L.w;
+    for (int h = threadIdx.x; h < H; h += kSolveThreads) {
+      float oi[C];
+      float g = 0.f;
+#pragma unroll
+      for (int i = 0; i < C; ++i) {
+        oi[i] = o[i * H + h];
+        g = fmaf(cx.lam1[i], oi[i], g);
+      }
+      cx.G[h] = g;
+      if (d.depth == 2) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < C; ++i) acc = fmaf(cx.lam[i * C + j], oi[i], acc);
+          w[j * H + h] = acc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (d.depth != 2) return;
+  // ---- tangent pass: C tangents through the hidden layers -------------------
+  const float* tin = buf + L.w;
+  int tin_stride = H;
+  for (int l = 0; l < NL; ++l) {
+    const float* s = buf + L.s + l * Wd;
+    float* u = buf + L.u + l * C * Wd;
+    float* p = buf + L.p + l * C * Wd;
+    matvec_rows<C>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], tin, tin_stride,
+                   [&](int row, const float* acc) {
+                     const float sv = s[row];
+#pragma unroll
+                     for (int j = 0; j < C; ++j) {
+                       u[j * Wd + row] = acc[j];
+                       p[j * Wd + row] = sv * acc[j];
+                     }
+                   });
+    __syncthreads();
+    tin = p;
+    tin_stride = Wd;
+  }
+  {
+    float* ul = buf + L.ul;
+    matvec_rows_blocked(cx.wbase[NL], d.stride[NL], C, H, d.in_dim[NL], d.kq_log2[NL], tin, tin_stride,
+                        [&](int j, int h, float acc) { ul[j * H + h] = acc; });
+  }
+  __syncthreads();
+  {
+    const float* o = buf + L.o;
+    const float* ul = buf + L.ul;
+    for (int h = threadIdx.x; h < H; h += kSolveThreads) {
+      float g = cx.G[h];
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float ov = o[j * H + h];
+        g = fmaf(1.f - ov * ov, ul[j * H + h], g);
+      }
+      cx.G[h] = g;
+    }
+  }
+  __syncthreads();
+}
+
+// Copy the MLP weights into shared memory with the padded strides of `d`.
+__device__ __forceinline__ void stage_weights(const MlpDesc& d, const float* __restrict__ params,
+                                              float* smem_w, const float** wbase) {
+  for (int l = 0; l < d.n_layers; ++l) {
+    if (d.sm_off[l] >= 0) {
+      float* dst = smem_w + d.sm_off[l];
+      const float* src = params + d.w_off[l];
+      const int n = d.rows[l] * d.in_dim[l];
+      for (int t = threadIdx.x; t < n; t += kSolveThreads) {
+        const int r = t / d.in_dim[l], c = t - r * d.in_dim[l];
+        dst[r * d.stride[l] + c] = src[t];
+      }
+      wbase[l] = dst;
+    } else {
+      wbase[l] = params + d.w_off[l];
+    }
+  }
+}
+
+// host helper
+int make_mlp_desc(MlpDesc* d, int H, int C, int width, int n_hidden, int depth, size_t other_smem_bytes);
+
+}  // namespace lncde

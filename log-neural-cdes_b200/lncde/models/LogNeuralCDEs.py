@@ -1,0 +1,200 @@
+"""``LogNeuralCDE`` – host-side mirror of models/LogNeuralCDEs.py:37-162 over kernels
+K3 (forward Heun solve) and K3b (exact discrete adjoint).
+
+Attribute names follow the reference pytree (``vf.mlp.layers[i].weight/.bias``,
+``linear1``, ``linear2``, ``pairs``, ``intervals``, ``classification``, ``lip2``,
+``lambd`` ...) so that train.py:79-93,441-458 semantics carry over.  The model is
+called on the whole batch ``X = (ts[B,L], logsig[B,K,D], x0[B,C])`` – the
+reference's per-sample ``__call__`` under ``jax.vmap`` (train.py:66).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..data_dir.hall_set import HallSet
+from .solver_grid import stage_table
+
+
+class _Linear:
+    """View of W[out,in], b[out] inside a flat parameter vector (eqx.nn.Linear layout)."""
+
+    def __init__(self, flat, off, n_in, n_out):
+        self._flat, self._off, self.in_features, self.out_features = flat, off, n_in, n_out
+
+    @property
+    def weight(self):
+        o = self._off
+        return self._flat[o : o + self.out_features * self.in_features].view(self.out_features, self.in_features)
+
+    @property
+    def bias(self):
+        o = self._off + self.out_features * self.in_features
+        return self._flat[o : o + self.out_features]
+
+    def __call__(self, x):
+        return torch.addmm(self.bias, x, self.weight.t())
+
+    @property
+    def numel(self):
+        return self.out_features * (self.in_features + 1)
+
+
+class _MLP:
+    def __init__(self, layers):
+        self.layers = layers
+
+
+class VectorField:
+    """models/NeuralCDEs.py:43-82 – eqx.nn.MLP(H -> width x depth -> H*C), SiLU hidden,
+    tanh final; evaluated inside the solve kernels, never on the host."""
+
+    def __init__(self, layers):
+        self.mlp = _MLP(layers)
+
+
+class _LogNCDESolve(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mlp_flat, logsig, y0, rows, scale, dims):
+        H, C, width, n_hidden, depth = dims
+        _lib.require_cuda(mlp_flat, logsig, y0, rows, scale)
+        L = _lib.lib()
+        B, K, D = logsig.shape
+        n_steps = rows.shape[0]
+        ys = torch.empty((B, n_steps + 1, H), device=y0.device, dtype=torch.float32)
+        mlp_flat = mlp_flat.contiguous()
+        y0c = y0.contiguous()
+        st = L.lncde_logncde_fwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(y0c),
+                                 _lib.ptr(rows), _lib.ptr(scale), _lib.ptr(ys), B, K, D, H, C, width, n_hidden,
+                                 depth, n_steps)
+        _lib.check(st, "lncde_logncde_fwd")
+        ctx.save_for_backward(mlp_flat, logsig, rows, scale, ys)
+        ctx.dims = dims
+        return ys
+
+    @staticmethod
+    def backward(ctx, g_ys):
+        mlp_flat, logsig, rows, scale, ys = ctx.saved_tensors
+        H, C, width, n_hidden, depth = ctx.dims
+        L = _lib.lib()
+        B, K, D = logsig.shape
+        n_steps = rows.shape[0]
+        g_ys = g_ys.contiguous()
+        nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, C, width, n_hidden, depth, n_steps)
+        ws = _workspace(nbytes, ys.device)
+        g_params = torch.empty_like(mlp_flat)
+        g_y0 = torch.empty((B, H), device=ys.device, dtype=torch.float32)
+        st = L.lncde_logncde_bwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(rows),
+                                 _lib.ptr(scale), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_params), _lib.ptr(g_y0),
+                                 B, K, D, H, C, width, n_hidden, depth, n_steps, _lib.ptr(ws), nbytes)
+        _lib.check(st, "lncde_logncde_bwd")
+        return g_params, None, g_y0, None, None, None
+
+
+_WS = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per device (the C ABI never allocates)."""
+    cur = _WS.get(device)
+    if cur is None or cur.numel() < nbytes:
+        cur = torch.empty(max(nbytes, 1), device=device, dtype=torch.uint8)
+        _WS[device] = cur
+    return cur
+
+
+class LogNeuralCDE:
+    stateful = False
+    nondeterministic = False
+    lip2 = True
+
+    def __init__(self, vf_hidden_dim, vf_num_hidden, hidden_dim, data_dim, depth, label_dim, classification,
+                 output_step, intervals, solver, stepsize_controller, dt0, max_steps, scale, lambd, *, key,
+                 device="cuda"):
+        if depth not in (1, 2):
+            raise ValueError("LogNeuralCDE supports logsig depth 1 and 2 (as the reference, LogNeuralCDEs.py:9)")
+        self.data_dim, self.depth, self.hidden_dim = int(data_dim), int(depth), int(hidden_dim)
+        self.vf_width, self.vf_depth = int(vf_hidden_dim), int(vf_num_hidden)
+        self.label_dim = int(label_dim)
+        self.classification, self.output_step = bool(classification), int(output_step)
+        self.solver, self.stepsize_controller = solver, stepsize_controller
+        self.dt0, self.max_steps, self.lambd = float(dt0), int(max_steps), float(lambd)
+        self.device = torch.device(device)
+        H, C, W = self.hidden_dim, self.data_dim, self.vf_width
+        sizes = [H] + [W] * self.vf_depth + [C * H]
+        n_mlp = sum(o * (i + 1) for i, o in zip(sizes[:-1], sizes[1:]))
+        n_tot = n_mlp + H * (C + 1) + self.label_dim * (H + 1)
+        gen = torch.Generator().manual_seed(int(key))
+        flat = torch.empty(n_tot, dtype=torch.float32)
+        off = 0
+        # eqx.nn.Linear: W, b ~ U(-1/sqrt(in), 1/sqrt(in)); the vector field is then divided by `scale`
+        for li, (i, o) in enumerate(list(zip(sizes[:-1], sizes[1:])) + [(C, H), (H, self.label_dim)]):
+            lim = 1.0 / math.sqrt(i)
+            n = o * (i + 1)
+            block = (torch.rand(n, generator=gen, dtype=torch.float64) * 2 - 1) * lim
+            if li < len(sizes) - 1:
+                block = block / scale
+            flat[off : off + n] = block.float()
+            off += n
+        self.params = flat.to(self.device).requires_grad_(True)
+        self.n_mlp = n_mlp
+        layers, off = [], 0
+        for i, o in zip(sizes[:-1], sizes[1:]):
+            layers.append(_Linear(self.params, off, i, o))
+            off += o * (i + 1)
+        self.vf = VectorField(layers)
+        self.linear1 = _Linear(self.params, off, C, H)
+        off += H * (C + 1)
+        self.linear2 = _Linear(self.params, off, H, self.label_dim)
+        hs = HallSet(C, self.depth)
+        self.pairs = None if self.depth == 1 else torch.from_numpy(hs.pairs())
+        self.logsig_dim = len(hs)
+        self.intervals = torch.as_tensor(np.asarray(intervals, np.float32))
+        self._table = None
+
+    # -- parameters -----------------------------------------------------------------
+    def parameters(self):
+        return [self.params]
+
+    def mlp_flat(self):
+        return self.params[: self.n_mlp]
+
+    # -- stage table ----------------------------------------------------------------
+    def _stage_table(self, ts, n_rows):
+        t0, t1 = float(ts[0, 0]), float(ts[0, -1])
+        key = (t0, t1, n_rows)
+        if self._table is None or self._table[0] != key:
+            rows, scale, grid = stage_table(t0, t1, self.intervals.numpy(), self.dt0, n_rows, self.max_steps)
+            interp = None
+            if not self.classification:
+                step = np.float32(self.output_step / ts.shape[1])
+                times = np.arange(step, 1.0, step, dtype=np.float32)  # LogNeuralCDEs.py:143-145
+                idx = np.clip(np.searchsorted(grid, times, side="left"), 1, len(grid) - 1)
+                w = ((times - grid[idx - 1]) / (grid[idx] - grid[idx - 1])).astype(np.float32)
+                interp = (torch.from_numpy(idx).to(self.device), torch.from_numpy(w).to(self.device)[None, :, None])
+            self._table = (key, torch.from_numpy(rows.reshape(-1)).to(self.device).view(-1, 2),
+                           torch.from_numpy(scale.reshape(-1)).to(self.device).view(-1, 2), interp)
+        return self._table[1:]
+
+    # -- forward ---------------------------------------------------------------------
+    def hidden_states(self, X):
+        ts, logsig, x0 = X
+        _lib.require_cuda(logsig, x0)
+        rows, scale, interp = self._stage_table(ts, logsig.shape[1])
+        y0 = self.linear1(x0)
+        dims = (self.hidden_dim, self.data_dim, self.vf_width, self.vf_depth, self.depth)
+        ys = _LogNCDESolve.apply(self.mlp_flat(), logsig.contiguous(), y0, rows, scale, dims)
+        return ys, interp
+
+    def __call__(self, X):
+        ys, interp = self.hidden_states(X)
+        if self.classification:
+            return torch.softmax(self.linear2(ys[:, -1]), dim=-1)  # LogNeuralCDEs.py:159-160
+        idx, w = interp
+        mid = ys[:, idx - 1] * (1 - w) + ys[:, idx] * w  # SaveAt(ts=...) local linear interpolation
+        out = torch.cat([mid, ys[:, -1:]], dim=1)        # ... plus t1
+        B, n, H = out.shape
+        return torch.tanh(self.linear2(out.reshape(B * n, H)).view(B, n, -1))  # :161-162

@@ -1,0 +1,83 @@
+"""Training step – mirror of train.py:52-136 (calc_output, classification_loss,
+regression_loss, make_step) for the hot-path models, plus the batch-sharded
+data-parallel step (one process per GPU, one NCCL all-reduce of the flat gradient).
+
+Loss functions return ``(value, flat_grad)`` like ``eqx.filter_value_and_grad``;
+gradients are taken w.r.t. every inexact leaf except ``intervals`` / ``pairs``
+(train.py:448-452) – here: the model's flat parameter vector.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def calc_output(model, X, state=None, key=None, stateful=False, nondeterministic=False):
+    """train.py:52-68; the hot-path models are neither stateful nor nondeterministic."""
+    if stateful or nondeterministic:
+        raise NotImplementedError("stateful / nondeterministic models are outside the hot path")
+    return model(X), state
+
+
+def _lip2(model):
+    """train.py:79-93."""
+    if not model.lip2:
+        return 0.0
+    norm = 0.0
+    if hasattr(model, "vf"):
+        for layer in model.vf.mlp.layers:
+            norm = norm + torch.mean(torch.linalg.norm(layer.weight, dim=-1) + torch.linalg.norm(layer.bias, dim=-1))
+    elif getattr(model, "vf_A", None) is not None:
+        norm = norm + torch.mean(torch.linalg.norm(model.vf_A, dim=-1))
+    return norm * model.lambd
+
+
+def _value_and_grad(model, loss):
+    (g,) = torch.autograd.grad(loss, model.params)
+    return loss.detach(), g
+
+
+def classification_loss(model, X, y, state=None, key=None):
+    """train.py:71-97: mean(-sum(y * log(pred + 1e-8))) + Lip(2) term."""
+    pred, _ = calc_output(model, X, state, key, model.stateful, model.nondeterministic)
+    loss = torch.mean(-torch.sum(y * torch.log(pred + 1e-8), dim=1)) + _lip2(model)
+    return _value_and_grad(model, loss)
+
+
+def regression_loss(model, X, y, state=None, key=None):
+    """train.py:100-127: mean(mean((pred[:,:,0] - y)^2, axis=1)) + Lip(2) term."""
+    pred, _ = calc_output(model, X, state, key, model.stateful, model.nondeterministic)
+    loss = torch.mean(torch.mean((pred[:, :, 0] - y) ** 2, dim=1)) + _lip2(model)
+    return _value_and_grad(model, loss)
+
+
+class Adam:
+    """optax.adam(lr) (train.py:183) on the flat parameter vector, fused kernel K4."""
+
+    def __init__(self, model, lr, b1=0.9, b2=0.999, eps=1e-8):
+        self.lr, self.b1, self.b2, self.eps = float(lr), b1, b2, eps
+        self.m = torch.zeros_like(model.params)
+        self.v = torch.zeros_like(model.params)
+        self.count = 0
+
+    def update(self, model, grads, grad_scale=1.0):
+        self.count += 1
+        _lib.require_cuda(model.params, grads)
+        p = model.params.detach()
+        st = _lib.lib().lncde_adam_step(_lib.stream_ptr(), _lib.ptr(p), _lib.ptr(grads.contiguous()),
+                                        _lib.ptr(self.m), _lib.ptr(self.v), p.numel(), self.lr, self.b1, self.b2,
+                                        self.eps, self.count, float(grad_scale))
+        _lib.check(st, "lncde_adam_step")
+
+
+def make_step(model, filter_spec, X, y, loss_fn, state, opt, opt_state, key, *, world_size=1):
+    """train.py:130-136.  With world_size > 1 every rank holds a batch shard; the flat
+    gradient is summed with ONE all-reduce and averaged inside the Adam kernel."""
+    value, grads = loss_fn(model, X, y, state, key)
+    if world_size > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+    opt.update(model, grads, grad_scale=1.0 / world_size)
+    return model, state, opt_state, value
