@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the Log-ODE hot path (BASELINE.json metric: train samples/sec, EigenWorms
+Log-NCDE, at 1/2/4/8 B200; logsig HBM GB/s vs peak).
+
+One "step" = one pass of the hot path over one batch of synthetic EigenWorms-shaped input:
+K1 log-signatures of the raw path batch -> Log-NCDE forward (Heun solve) -> CE loss + Lip(2)
+-> exact discrete adjoint -> [all-reduce of the flat gradient, N > 1] -> Adam.
+
+    python bench.py --gpus N --steps K --warmup W          (torchrun for N > 1)
+    python bench.py --impl reference ...                    CPU port of the reference path
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for _p in (REPO, os.path.join(REPO, "log-neural-cdes_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+# EigenWorms Log-NCDE (experiment_configs/repeats/log_ncde/EigenWorms.json), time channel included
+WL = dict(name="EigenWorms", B=32, L=17984, C=7, stepsize=12, depth=2, H=128, vf_width=32, vf_depth=2,
+          dt0=0.00066711140760507, scale=1000.0, lambd=1e-3, lr=1e-3, label_dim=5)
+N_ROT = 16  # distinct input batches rotated through (16 x 16.1 MB = 258 MB > 126 MB L2)
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank, n_rot):
+    """Synthetic EigenWorms-shaped batches: ch 0 = t, ch 1..6 = random walk N(0, 0.05^2)."""
+    from lncde.data_dir.datasets import synthetic_paths
+
+    x = synthetic_paths("EigenWorms", WL["B"] * n_rot, seed=2345 + rank).reshape(n_rot, WL["B"], WL["L"], WL["C"])
+    rng = np.random.default_rng(99 + rank)
+    lab = np.eye(WL["label_dim"], dtype=np.float32)[rng.integers(0, WL["label_dim"], size=(n_rot, WL["B"]))]
+    return x, lab
+
+
+def run_ours(args):
+    from lncde import _build, _lib, train as T
+    from lncde.data_dir.datasets import make_intervals, make_ts
+    from lncde.data_dir.generate_paths import calc_paths
+    from lncde.models.generate_model import create_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        _build.build_library()
+    if world > 1:
+        dist.barrier()
+    _lib.lib()
+
+    B, L, C = WL["B"], WL["L"], WL["C"]
+    x_host, lab_host = make_inputs(rank, N_ROT)
+    x_pin = torch.from_numpy(x_host).pin_memory()
+    lab_pin = torch.from_numpy(lab_host).pin_memory()
+    x_dev = x_pin.to(dev)
+    lab_dev = lab_pin.to(dev)
+    ts0 = make_ts(L)
+    iv = make_intervals(ts0, WL["stepsize"])
+    ts = torch.from_numpy(ts0)[None, :].expand(B, -1)  # host tensor: only ts[0], ts[-1] are read (t0, t1)
+    model, _ = create_model("log_ncde", C, 29, WL["depth"], iv, WL["label_dim"], WL["H"], vf_depth=WL["vf_depth"],
+                            vf_width=WL["vf_width"], dt0=WL["dt0"], scale=WL["scale"], lambd=WL["lambd"], key=2345,
+                            device=dev)
+    if world > 1:
+        dist.broadcast(model.params.data, src=0)
+    opt = T.Adam(model, WL["lr"])
+    K = _lib.lib().lncde_logsig_num_windows(L, WL["stepsize"])
+    ls_buf = torch.empty((B, K, 29), device=dev)
+    stage_buf = torch.empty((B, L, C), device=dev)
+    lab_buf = torch.empty((B, WL["label_dim"]), device=dev)
+
+    def step(raw, lab):
+        ls = calc_paths(raw, WL["stepsize"], WL["depth"], out=ls_buf)
+        X = (ts, ls, raw[:, 0, :])
+        _, _, _, value = T.make_step(model, None, X, lab, T.classification_loss, None, opt, None, None,
+                                     world_size=world)
+        return value
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for i in range(args.warmup):
+        step(x_dev[i % N_ROT], lab_dev[i % N_ROT])
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for i in range(args.steps):
+        step(x_dev[i % N_ROT], lab_dev[i % N_ROT])
+    e1.record()
+    sync()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, every step --------------------
+    def e2e_step(i):
+        stage_buf.copy_(x_pin[i % N_ROT], non_blocking=True)
+        lab_buf.copy_(lab_pin[i % N_ROT], non_blocking=True)
+        return float(step(stage_buf, lab_buf).item())  # D2H read of the loss
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    sync()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        last_loss = e2e_step(i)
+    f1.record()
+    sync()
+    e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 * 0.0)
+
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+
+    out = None
+    if rank == 0:
+        pk, pk_kind = peaks()
+        out = {
+            "metric": "train samples/sec EigenWorms Log-NCDE",
+            "value": world * B * args.steps / (ms * 1e-3),
+            "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "EigenWorms Log-NCDE depth-2 logsig: B=32/GPU, L=17984, C=7 (6+time), stepsize 12, "
+                                   "H=128, vf 2x32, Heun dt0=1/1499 (1499 steps), CE+Lip2, Adam",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": f"rotating {N_ROT} distinct input batches (258 MB) and a 1.5 GB adjoint workspace "
+                             "streamed every step: working set > 126 MB L2"},
+            "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": int(x_pin[0].numel() * 4 + lab_pin[0].numel() * 4),
+                    "d2h_bytes_per_step": 4, "last_loss": last_loss},
+            "gpu_launches": 8 * args.steps * 2,  # K1, K3, K3b, 3 GEMM groups, reduce, Adam per step; both timed loops
+            "clocks": clocks,
+        }
+        out.update(extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms / args.steps))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_per_step):
+    """Roofline of the HBM-bound kernel (K1 logsig at a batch larger than L2), per-kernel
+    breakdown of the step, and the CPU baseline.  Rank 0 only."""
+    from lncde import train as T
+    from lncde.data_dir.datasets import synthetic_paths
+    from lncde.data_dir.generate_paths import calc_paths
+
+    res = {}
+    dev = x_dev.device
+    L, C, s = WL["L"], WL["C"], WL["stepsize"]
+    # ---- K1 roofline leg: B = 2048 EigenWorms paths = 1.03 GB read + 0.36 GB written per launch
+    Bk = 2048
+    big = torch.from_numpy(synthetic_paths("EigenWorms", 64, seed=7)).to(dev).repeat(Bk // 64, 1, 1)
+    big += 0.001 * torch.randn(Bk, 1, 1, device=dev)
+    out = torch.empty((Bk, 1499, 29), device=dev)
+    for _ in range(3):
+        calc_paths(big, s, 2, out=out)
+    torch.cuda.synchronize()
+    n_rep = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_rep):
+        calc_paths(big, s, 2, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    k1_ms = e0.elapsed_time(e1) / n_rep
+    alg_bytes = Bk * (4 * L * C + 4 * 1499 * 29)  # 677 436 B per sample
+    ach = alg_bytes / (k1_ms * 1e-3) / 1e9
+    res["roofline"] = {"kernel": "logsig_levy_kernel<7,depth2> (K1)", "bound": "hbm", "achieved": ach,
+                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                       "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs (burst copy)",
+                       "launch_ms": k1_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                       "shape": f"B={Bk} x EigenWorms (L=17984, C=7, stepsize 12, depth 2): inputs 1.03 GB > L2"}
+    del big, out
+    # ---- per-kernel breakdown of the train step (CUDA events around each phase) -----------------
+    res["step_breakdown_ms"] = breakdown(model, opt, x_dev, lab_dev)
+    res["step_breakdown_ms"]["whole_step"] = ms_per_step
+    # ---- CPU baseline ------------------------------------------------------------------------------
+    if not args.no_cpu_baseline:
+        res["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+    return res
+
+
+def breakdown(model, opt, x_dev, lab_dev):
+    from lncde import train as T
+    from lncde.data_dir.generate_paths import calc_paths
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    names = ["logsig_K1", "forward_solve_K3+readout", "backward_K3b+gemm", "adam_K4"]
+    acc = {n: 0.0 for n in names}
+    reps = 3
+    B, L = WL["B"], WL["L"]
+    ts = torch.zeros(B, L)
+    ts[:, -1] = float(np.float32(1.0 / L) * np.float32(L - 1))
+    for i in range(reps):
+        raw, lab = x_dev[i % N_ROT], lab_dev[i % N_ROT]
+        es = [ev() for _ in range(5)]
+        es[0].record()
+        ls = calc_paths(raw, WL["stepsize"], WL["depth"])
+        es[1].record()
+        pred = model((ts, ls, raw[:, 0, :]))
+        loss = torch.mean(-torch.sum(lab * torch.log(pred + 1e-8), dim=1)) + T._lip2(model)
+        es[2].record()
+        (g,) = torch.autograd.grad(loss, model.params)
+        es[3].record()
+        opt.update(model, g)
+        es[4].record()
+        torch.cuda.synchronize()
+        for n, a, b in zip(names, es[:-1], es[1:]):
+            acc[n] += a.elapsed_time(b) / reps
+    return acc
+
+
+def cpu_baseline(budget_s=20.0):
+    """Oracle port of the reference train step on the host cores, on a bounded sample:
+    the full batch of 32 EigenWorms-shaped paths truncated to the first n_sub Heun steps."""
+    from oracle import log_ncde as O
+    from oracle import paths as OP
+    from oracle.train import LogNCDEStep
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, s, C = WL["B"], WL["stepsize"], WL["C"]
+    n_full = 1499
+    n_sub = 24
+    Ls = (n_sub + 1) * s
+    from lncde.data_dir.datasets import synthetic_paths
+
+    x = synthetic_paths("EigenWorms", B, seed=2345)[:, :Ls]
+    ts_full = OP.make_ts(WL["L"])
+    iv = OP.make_intervals(ts_full, s)
+    t0 = time.perf_counter()
+    ls = OP.calc_paths(x, s, 2, np.float32)
+    t_logsig = time.perf_counter() - t0
+    rows, sc, _ = O.stage_table(ts_full, iv, WL["dt0"], 1499)
+    rows, sc = rows[:n_sub].copy(), sc[:n_sub].copy()
+    rows[rows >= ls.shape[1]] = ls.shape[1] - 1  # quirk B2 row (last row) of the truncated sample
+    stepper = LogNCDEStep(WL["H"], C, WL["vf_width"], WL["vf_depth"], WL["label_dim"], 2, WL["scale"], WL["lambd"],
+                          WL["lr"])
+    lst, x0 = torch.from_numpy(ls), torch.from_numpy(x[:, 0].copy())
+    y = torch.eye(WL["label_dim"])[torch.arange(B) % WL["label_dim"]]
+    stepper.step(lst, x0, y, rows, sc)  # warm-up
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_all < budget_s and len(times) < 20):
+        t0 = time.perf_counter()
+        stepper.step(lst, x0, y, rows, sc)
+        times.append(time.perf_counter() - t0)
+    t_step = float(np.median(times))
+    scale_up = n_full / n_sub
+    t_full = t_step * scale_up + t_logsig * (WL["L"] / Ls)
+    return {"value": B / t_full, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port (torch-CPU fp32, reference formulation 1+C JVPs, autograd adjoint) of the full "
+                      f"B=32 batch truncated to the first {n_sub} of {n_full} Heun steps (L={Ls}); median of "
+                      f"{len(times)} steps = {t_step:.3f} s, scaled x{scale_up:.1f} to the full path; numpy logsig "
+                      f"{t_logsig:.3f} s scaled likewise"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation cannot run offline (jax absent),
+    so this times the oracle port on all host cores (kind 'port').  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    t0 = time.perf_counter()
+    cb = cpu_baseline(budget_s=max(10.0, min(60.0, 6.0 * (args.steps + args.warmup))))
+    out = {"impl": "reference", "metric": "train samples/sec EigenWorms Log-NCDE", "value": cb["value"],
+           "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * WL["B"] / cb["value"], "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "EigenWorms Log-NCDE depth-2 logsig: B=32, L=17984, C=7 (6+time), stepsize 12, "
+                                  "H=128, vf 2x32, Heun dt0=1/1499, CE+Lip2, Adam",
+                      "global_batch": WL["B"], "parallelism": "cpu"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": time.perf_counter() - t0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -164,9 +164,9 @@ class LogNeuralCDE:
 
     # -- stage table ----------------------------------------------------------------
     def _stage_table(self, ts, n_rows):
-        t0, t1 = float(ts[0, 0]), float(ts[0, -1])
-        key = (t0, t1, n_rows)
+        key = (ts.data_ptr(), tuple(ts.shape), n_rows)  # no device read-back on the steady-state path
         if self._table is None or self._table[0] != key:
+            t0, t1 = float(ts[0, 0]), float(ts[0, -1])
             rows, scale, grid = stage_table(t0, t1, self.intervals.numpy(), self.dt0, n_rows, self.max_steps)
             interp = None
             if not self.classification:
