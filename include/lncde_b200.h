@@ -123,11 +123,14 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig,
  *        for bs == 1 this is vf_A^T laid out [H, n_coeff]
  *   logsig [B, T, D]; uses columns 1 .. n_basis
  *   y0 [B, H];  ys [B, T, H] (ys[:,0] = y0)                                  */
+/* Scratch shared by forward and backward: the flows F [B,T,nb,bs,bs] plus split-K partials.
+ * The backward call must receive the SAME workspace the forward call of the same
+ * (lie, logsig) filled, untouched in between (it reads F_t and overwrites it with dF_t).   */
+size_t lncde_linear_scan_workspace_bytes(int B, int T, int nb, int bs, int n_basis);
 int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, const float* y0,
-                          float* ys, int B, int T, int D, int nb, int bs, int n_basis);
-/* g_ys [B,T,H] -> g_lie [nb,bs,bs,n_basis] (summed over batch), g_y0 [B,H].
- * workspace: lncde_linear_scan_bwd_workspace_bytes bytes.                    */
-size_t lncde_linear_scan_bwd_workspace_bytes(int B, int T, int nb, int bs, int n_basis);
+                          float* ys, int B, int T, int D, int nb, int bs, int n_basis,
+                          void* workspace, size_t workspace_bytes);
+/* g_ys [B,T,H] -> g_lie [nb,bs,bs,n_basis] (summed over batch), g_y0 [B,H].               */
 int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, const float* ys,
                           const float* g_ys, float* g_lie, float* g_y0, int B, int T, int D, int nb,
                           int bs, int n_basis, void* workspace, size_t workspace_bytes);

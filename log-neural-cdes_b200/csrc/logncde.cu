@@ -19,6 +19,7 @@
 
 #include "lncde_b200.h"
 #include "logncde_common.cuh"
+#include "outer_gemm.cuh"
 
 namespace lncde {
 
@@ -406,80 +407,6 @@ static size_t bwd_other_floats(int H, int C, int width, int n_hidden) {
          ((n_bias + 3) & ~3) + (size_t)kSolveThreads * C;
 }
 
-// ------------------------------------------------------------------ weight-gradient GEMM
-// out[m][n] = sum over segments, sum_k left[k*ldl + m] * right[k*ldr + n]
-struct GemmSeg {
-  const float* left;
-  const float* right;
-  long long ldl, ldr, count;
-};
-struct GemmTask {
-  GemmSeg seg[2];
-  int M, N;
-  long long part_off;  // float offset of this task's partials: [ksplit][M*N]
-  int out_off;         // offset in g_params
-};
-constexpr int kMaxTasks = 16;
-struct GemmParams {
-  GemmTask task[kMaxTasks];
-  int n_tasks, ksplit;
-  float* part;
-};
-
-template <int TM, int TN>
-__global__ void __launch_bounds__(256) outer_gemm_kernel(const GemmParams p) {
-  constexpr int KT = 16;
-  __shared__ float Ls[KT][16 * TM];
-  __shared__ float Rs[KT][16 * TN];
-  const int task_id = blockIdx.x / p.ksplit, ks = blockIdx.x - task_id * p.ksplit;
-  const GemmTask& t = p.task[task_id];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[TM][TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  for (int sgi = 0; sgi < 2; ++sgi) {
-    const GemmSeg& sg = t.seg[sgi];
-    if (sg.count == 0) continue;
-    const long long per = (sg.count + p.ksplit - 1) / p.ksplit;
-    const long long k_lo = per * ks, k_hi = min(sg.count, k_lo + per);
-    for (long long k0 = k_lo; k0 < k_hi; k0 += KT) {
-      const int kn = (int)min((long long)KT, k_hi - k0);
-      for (int e = threadIdx.x; e < KT * 16 * TM; e += 256) {
-        const int kk = e / (16 * TM), m = e - kk * 16 * TM;
-        Ls[kk][m] = (kk < kn && m < t.M) ? sg.left[(k0 + kk) * sg.ldl + m] : 0.f;
-      }
-      for (int e = threadIdx.x; e < KT * 16 * TN; e += 256) {
-        const int kk = e / (16 * TN), n = e - kk * 16 * TN;
-        Rs[kk][n] = (kk < kn && n < t.N) ? sg.right[(k0 + kk) * sg.ldr + n] : 0.f;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < KT; ++kk) {
-        float a[TM], bb[TN];
-#pragma unroll
-        for (int i = 0; i < TM; ++i) a[i] = Ls[kk][ty + 16 * i];
-#pragma unroll
-        for (int j = 0; j < TN; ++j) bb[j] = Rs[kk][tx + 16 * j];
-#pragma unroll
-        for (int i = 0; i < TM; ++i)
-#pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-      }
-      __syncthreads();
-    }
-  }
-  float* out = p.part + t.part_off + (size_t)ks * t.M * t.N;
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int m = ty + 16 * i, n = tx + 16 * j;
-      if (m < t.M && n < t.N) out[m * t.N + n] = acc[i][j];
-    }
-}
-
 // g_params[out_off + e] = sum_ks part[...]; biases: sum over samples of the per-CTA accumulators
 struct ReduceParams {
   GemmParams g;
@@ -527,36 +454,6 @@ static int launch_bwd(cudaStream_t st, const BwdParams& p, size_t smem) {
   if (e != cudaSuccess) return (int)e;
   k<<<p.B, kSolveThreads, smem, st>>>(p);
   return (int)cudaGetLastError();
-}
-
-static int round_tile(int v) {  // ceil(v/16) rounded up to 1,2,4,8
-  int t = (v + 15) / 16;
-  if (t <= 1) return 1;
-  if (t <= 2) return 2;
-  if (t <= 4) return 4;
-  return 8;
-}
-
-template <int TM>
-static void launch_gemm_tn(int tn, const GemmParams& g, int first, int count, cudaStream_t st) {
-  GemmParams sub = g;
-  sub.n_tasks = count;
-  for (int i = 0; i < count; ++i) sub.task[i] = g.task[first + i];
-  const int grid = count * g.ksplit;
-  switch (tn) {
-    case 1: outer_gemm_kernel<TM, 1><<<grid, 256, 0, st>>>(sub); break;
-    case 2: outer_gemm_kernel<TM, 2><<<grid, 256, 0, st>>>(sub); break;
-    case 4: outer_gemm_kernel<TM, 4><<<grid, 256, 0, st>>>(sub); break;
-    default: outer_gemm_kernel<TM, 8><<<grid, 256, 0, st>>>(sub); break;
-  }
-}
-static void launch_gemm(int tm, int tn, const GemmParams& g, int first, int count, cudaStream_t st) {
-  switch (tm) {
-    case 1: launch_gemm_tn<1>(tn, g, first, count, st); break;
-    case 2: launch_gemm_tn<2>(tn, g, first, count, st); break;
-    case 4: launch_gemm_tn<4>(tn, g, first, count, st); break;
-    default: launch_gemm_tn<8>(tn, g, first, count, st); break;
-  }
 }
 
 constexpr int kKsplit = 48;
@@ -631,7 +528,6 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
   if (st != LNCDE_OK) return st;
   const size_t smem = (size_t)p.d.smem_weight_floats * 4 + other;
   if (smem > 227 * 1024) return LNCDE_ERR_UNSUPPORTED;
-  if (width > 128 || H > 128) return LNCDE_ERR_UNSUPPORTED;  // weight-gradient GEMM tile limit
   p.ws = make_ws_layout(p.d, B, n_steps, kKsplit);
   if (workspace_bytes < p.ws.total * 4) return LNCDE_ERR_WORKSPACE;
   p.params = params; p.logsig = logsig; p.stage_row = stage_row; p.stage_scale = stage_scale;
@@ -685,9 +581,9 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
                   (long long)C * d.width, Kt};
   }
   // group launches by tile shape: layer 0, hidden layers, last-layer blocks
-  launch_gemm(round_tile(d.rows[0]), round_tile(d.in_dim[0]), g, 0, 1, cs);
-  if (NL > 1) launch_gemm(round_tile(d.width), round_tile(d.width), g, 1, NL - 1, cs);
-  launch_gemm(round_tile(H), round_tile(d.width), g, first_last, C, cs);
+  launch_gemm(g, 0, 1, cs);
+  if (NL > 1) launch_gemm(g, 1, NL - 1, cs);
+  launch_gemm(g, first_last, C, cs);
   st = (int)cudaGetLastError();
   if (st != 0) return st;
 

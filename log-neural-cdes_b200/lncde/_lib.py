@@ -36,8 +36,8 @@ def _declare(lib):
         "lncde_logncde_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i]),
         "lncde_logncde_bwd_workspace_bytes": (sz, [i, i, i, i, i, i, i]),
         "lncde_logncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz]),
-        "lncde_linear_scan_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i]),
-        "lncde_linear_scan_bwd_workspace_bytes": (sz, [i, i, i, i, i]),
+        "lncde_linear_scan_workspace_bytes": (sz, [i, i, i, i, i]),
+        "lncde_linear_scan_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]),
         "lncde_linear_scan_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]),
         "lncde_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, i, f]),
     }

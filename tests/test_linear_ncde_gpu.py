@@ -1,0 +1,113 @@
+"""K2 parity: CUDA D / BD / DE-LNCDE (through the C ABI) vs the torch-CPU fp64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import linear_ncde as OL
+from oracle import paths
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _data(B, L, C, s, depth, seed=0):
+    rng = np.random.default_rng(seed)
+    x = np.cumsum(rng.normal(scale=0.1, size=(B, L, C)), axis=1)
+    lo, hi = x.min((0, 1), keepdims=True), x.max((0, 1), keepdims=True)
+    x = (2 * (x - lo) / (hi - lo) - 1).astype(np.float32)  # datasets.py:237-239
+    return x, paths.calc_paths(x, s, depth, np.float32)
+
+
+CASES = [
+    # B, L, C, s, depth, H, bs, classification
+    (3, 64, 3, 4, 2, 16, 1, True),
+    (3, 64, 3, 4, 2, 16, 4, True),
+    (2, 64, 3, 4, 2, 16, 16, True),
+    (2, 64, 3, 4, 1, 16, 4, True),
+    (2, 48, 2, 4, 3, 8, 4, True),      # depth-3 brackets
+    (2, 48, 3, 4, 3, 12, 1, True),     # D-LNCDE ignores levels > 1 (quirk B7)
+    (2, 64, 3, 4, 2, 16, 4, False),    # regression read-out
+    (2, 896, 6, 16, 2, 64, 4, True),   # SCP1 BD-LNCDE shape
+    (2, 240, 7, 12, 2, 128, 4, True),  # EigenWorms BD dims, short
+    (2, 120, 7, 12, 2, 128, 128, True),  # DE dims, short
+    (2, 120, 7, 12, 2, 32, 32, True),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_linear_ncde_loss_and_grads(built_lib, case):
+    from lncde import train as T
+    from lncde.models.generate_model import create_model
+
+    B, L, C, s, depth, H, bs, classification = case
+    x, logsig = _data(B, L, C, s, depth)
+    label_dim = 3 if classification else 1
+    name = {1: "diagonal_linear_ncde", H: "dense_linear_ncde"}.get(bs, "bd_linear_ncde")
+    model, state = create_model(name, C, logsig.shape[-1], depth, None, label_dim, H, block_size=bs,
+                                classification=classification, lambd=0.01, w_init_std=0.25, parallel_steps=128,
+                                key=3)
+    assert state is None
+    X = (None, torch.from_numpy(logsig).cuda(), torch.from_numpy(x[:, 0].copy()).cuda())
+    rng = np.random.default_rng(1)
+    if classification:
+        y = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, 3, B)), 3).float().cuda()
+        loss, grads = T.classification_loss(model, X, y)
+    else:
+        y = torch.from_numpy(rng.normal(size=(B, logsig.shape[1])).astype(np.float32)).cuda()
+        loss, grads = T.regression_loss(model, X, y)
+    # oracle, fp64, same parameters
+    vf_A = model.vf_A.detach().cpu().double().requires_grad_(True)
+    Wi = model.init_layer.weight.detach().cpu().double().requires_grad_(True)
+    bi = model.init_layer.bias.detach().cpu().double().requires_grad_(True)
+    Wo = model.out_layer.weight.detach().cpu().double().requires_grad_(True)
+    bo = model.out_layer.bias.detach().cpu().double().requires_grad_(True)
+    pred = OL.predict(vf_A, Wi, bi, Wo, bo, torch.from_numpy(logsig).double(), torch.from_numpy(x[:, 0]).double(), C,
+                      bs, depth, classification)
+    yo = y.cpu().double()
+    if classification:
+        lo = torch.mean(-torch.sum(yo * torch.log(pred + 1e-8), dim=1))
+    else:
+        lo = torch.mean(torch.mean((pred[:, :, 0] - yo) ** 2, dim=1))
+    lo = lo + OL.lip2_norm(vf_A, 0.01)
+    lo.backward()
+    go = torch.cat([vf_A.grad.reshape(-1), Wi.grad.reshape(-1), bi.grad, Wo.grad.reshape(-1), bo.grad])
+    assert abs(float(loss) - float(lo)) < TOL * max(1.0, abs(float(lo)))
+    g = grads.cpu().numpy()
+    nA = vf_A.numel()
+    assert rel_err(g[:nA], go.numpy()[:nA]) < 5 * TOL
+    assert rel_err(g[nA:], go.numpy()[nA:]) < 5 * TOL
+
+
+def test_hidden_states_match_oracle_and_chunked_scan(built_lib):
+    from lncde.models.generate_model import create_model
+
+    B, L, C, s, depth, H, bs = 2, 600, 3, 4, 2, 16, 4
+    x, logsig = _data(B, L, C, s, depth)
+    model, _ = create_model("bd_linear_ncde", C, logsig.shape[-1], depth, None, 2, H, block_size=bs, key=0)
+    X = (None, torch.from_numpy(logsig).cuda(), torch.from_numpy(x[:, 0].copy()).cuda())
+    ys = model.hidden_states(X).detach().cpu().numpy()
+    vf_A = model.vf_A.detach().cpu().double()
+    for b in range(B):
+        y0 = model.init_layer.weight.detach().cpu().double() @ torch.from_numpy(x[b, 0]).double() \
+            + model.init_layer.bias.detach().cpu().double()
+        seq = OL.forward(vf_A, torch.from_numpy(logsig[b]).double(), y0, C, bs, depth, 1).numpy()
+        par = OL.forward(vf_A, torch.from_numpy(logsig[b]).double(), y0, C, bs, depth, 128).numpy()
+        assert rel_err(par, seq) < 1e-12  # chunk/remainder path == sequential path (quirk B6)
+        assert rel_err(ys[b], seq) < TOL
+
+
+def test_diagonal_equals_1x1_blocks(built_lib):
+    """D-LNCDE == BD with 1x1 blocks at depth 1 (SURVEY 8c identity 3)."""
+    L = built_lib
+    B, T, C, H = 2, 50, 3, 8
+    rng = np.random.default_rng(0)
+    ls = torch.from_numpy(rng.normal(scale=0.1, size=(B, T, 1 + C)).astype(np.float32)).cuda()
+    lie = torch.from_numpy(rng.normal(size=(H, 1, 1, C)).astype(np.float32)).cuda()
+    y0 = torch.from_numpy(rng.normal(size=(B, H)).astype(np.float32)).cuda()
+    from lncde.models.LinearNeuralCDEs import _LinearScan
+
+    ys = _LinearScan.apply(lie, ls, y0, (H, 1, C)).cpu().numpy()
+    flows = 1 + ls.cpu().numpy()[:, :, 1:].astype(np.float64) @ lie.cpu().numpy().reshape(H, C).T.astype(np.float64)
+    want = np.cumprod(np.concatenate([np.ones((B, 1, H)), flows[:, 1:]], 1), axis=1) * y0.cpu().numpy()[:, None, :]
+    assert rel_err(ys, want) < TOL
