@@ -290,7 +290,7 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
   g.part = F + flows;
   g.n_tasks = 1;
   GemmTask& t = g.task[0];
-  t.M = N; t.N = n_basis; t.out_off = 0; t.part_off = 0;
+  t.M = N; t.N = n_basis; t.out_off = 0; t.part_off = 0; t.ksplit = kScanKsplit;
   t.seg[0] = {F, logsig + 1, (long long)N, (long long)D, (long long)B * T};
   t.seg[1] = {nullptr, nullptr, 0, 0, 0};
   launch_gemm(g, 0, 1, cs);

@@ -16,12 +16,16 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "lncde_b200.h"
 #include "logncde_common.cuh"
 #include "outer_gemm.cuh"
 
 namespace lncde {
+
+constexpr int kKsplit = 48;        // last-layer blocks: C tasks x 48 slices
+constexpr int kKsplitSmall = 288;  // single-task launches (layer 0 / hidden layers)
 
 static int ilog2_floor(int v) {
   int l = 0;
@@ -177,7 +181,7 @@ static WsLayout make_ws_layout(const MlpDesc& d, int B, int n_steps, int ksplit)
   w.bias_part = take((size_t)B * n_bias);
   size_t n_w = 0;
   for (int l = 0; l < d.n_layers; ++l) n_w += (size_t)d.rows[l] * d.in_dim[l];
-  w.gemm_part = take(n_w * ksplit);
+  w.gemm_part = take(n_w * kKsplitSmall);
   w.total = off;
   return w;
 }
@@ -195,6 +199,15 @@ struct BwdParams {
   float* wsp;
   int B, K, D, n_steps;
 };
+
+}  // namespace lncde
+#include "logncde_fast.cuh"
+namespace lncde {
+
+static bool use_fast(int H, int C, int width, int n_hidden) {
+  static const bool disabled = getenv("LNCDE_DISABLE_FAST") != nullptr;
+  return !disabled && fast::shape_supported(H, C, width, n_hidden);
+}
 
 struct RevBufs {
   float* g;        // [H] cotangent of G
@@ -424,7 +437,7 @@ __global__ void reduce_grads_kernel(const ReduceParams p) {
     const int mn = t.M * t.N;
     for (int e = tid; e < mn; e += stride) {
       float s = 0.f;
-      for (int ks = 0; ks < p.g.ksplit; ++ks) s += p.g.part[t.part_off + (size_t)ks * mn + e];
+      for (int ks = 0; ks < t.ksplit; ++ks) s += p.g.part[t.part_off + (size_t)ks * mn + e];
       p.g_params[t.out_off + e] = s;
     }
   }
@@ -456,7 +469,6 @@ static int launch_bwd(cudaStream_t st, const BwdParams& p, size_t smem) {
   return (int)cudaGetLastError();
 }
 
-constexpr int kKsplit = 48;
 
 }  // namespace lncde
 
@@ -491,6 +503,13 @@ int lncde_logncde_fwd(void* stream, const float* params, const float* logsig, co
   p.params = params; p.logsig = logsig; p.y0 = y0; p.stage_row = stage_row; p.stage_scale = stage_scale;
   p.ys = ys; p.B = B; p.K = K; p.D = D; p.n_steps = n_steps;
   cudaStream_t cs = (cudaStream_t)stream;
+  if (use_fast(H, C, width, n_hidden)) {
+    switch (C) {
+      case 4: return fast::launch_fwd_fast<4>(cs, p);
+      case 6: return fast::launch_fwd_fast<6>(cs, p);
+      case 7: return fast::launch_fwd_fast<7>(cs, p);
+    }
+  }
   switch (C) {
     case 1: return launch_fwd<1>(cs, p, smem);
     case 2: return launch_fwd<2>(cs, p, smem);
@@ -534,6 +553,13 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
   p.ys = ys; p.g_ys = g_ys; p.g_y0 = g_y0; p.wsp = (float*)workspace;
   p.B = B; p.K = K; p.D = D; p.n_steps = n_steps;
   cudaStream_t cs = (cudaStream_t)stream;
+  if (use_fast(H, C, width, n_hidden)) {
+    switch (C) {
+      case 4: st = fast::launch_bwd_fast<4>(cs, p); break;
+      case 6: st = fast::launch_bwd_fast<6>(cs, p); break;
+      case 7: st = fast::launch_bwd_fast<7>(cs, p); break;
+    }
+  } else
   switch (C) {
     case 1: st = launch_bwd<1>(cs, p, smem); break;
     case 2: st = launch_bwd<2>(cs, p, smem); break;
@@ -559,22 +585,22 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
   g.part = wsp + ws.gemm_part;
   g.n_tasks = 0;
   long long part_off = 0;
-  auto add = [&](int M, int N, int out_off) -> GemmTask& {
+  auto add = [&](int M, int N, int out_off, int ksplit) -> GemmTask& {
     GemmTask& t = g.task[g.n_tasks++];
-    t.M = M; t.N = N; t.out_off = out_off; t.part_off = part_off;
-    part_off += (long long)M * N * kKsplit;
+    t.M = M; t.N = N; t.out_off = out_off; t.part_off = part_off; t.ksplit = ksplit;
+    part_off += (long long)M * N * ksplit;
     t.seg[0].count = t.seg[1].count = 0;
     return t;
   };
   // layer 0 and hidden layers
   for (int l = 0; l < NL; ++l) {
-    GemmTask& t = add(d.rows[l], d.in_dim[l], d.w_off[l]);
+    GemmTask& t = add(d.rows[l], d.in_dim[l], d.w_off[l], kKsplitSmall);
     t.seg[0] = {wsp + ws.Z[l], l == 0 ? wsp + ws.Y : wsp + ws.A[l - 1], d.width, d.in_dim[l], Kt};
     if (tan) t.seg[1] = {wsp + ws.U[l], l == 0 ? wsp + ws.Wt : wsp + ws.P[l - 1], d.width, d.in_dim[l], Kt * C};
   }
   const int first_last = g.n_tasks;
   for (int j = 0; j < C; ++j) {
-    GemmTask& t = add(H, d.width, d.w_off[NL] + j * H * d.width);
+    GemmTask& t = add(H, d.width, d.w_off[NL] + j * H * d.width, kKsplit);
     t.seg[0] = {wsp + ws.ZL + (size_t)j * H, wsp + ws.A[NL - 1], (long long)C * H, d.width, Kt};
     if (tan)
       t.seg[1] = {wsp + ws.UL + (size_t)j * H, wsp + ws.P[NL - 1] + (size_t)j * d.width, (long long)C * H,

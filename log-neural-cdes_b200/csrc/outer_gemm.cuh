@@ -19,6 +19,7 @@ struct GemmSeg {
 struct GemmTask {
   GemmSeg seg[2];
   int M, N;
+  int ksplit;          // k-slices of this task (all tasks of one launch share it)
   long long part_off;  // float offset of this task's partials: [ksplit][M*N]
   int out_off;         // offset in the output buffer
 };
@@ -111,10 +112,11 @@ static inline void launch_gemm(const GemmParams& g, int first, int count, cudaSt
   sub.n_tasks = count;
   for (int i = 0; i < count; ++i) sub.task[i] = g.task[first + i];
   const int M = sub.task[0].M, N = sub.task[0].N;
+  sub.ksplit = sub.task[0].ksplit;
   const int tm = round_tile(M), tn = round_tile(N);
   sub.m_tiles = (M + 16 * tm - 1) / (16 * tm);
   sub.n_tiles = (N + 16 * tn - 1) / (16 * tn);
-  const int grid = count * sub.m_tiles * sub.n_tiles * g.ksplit;
+  const int grid = count * sub.m_tiles * sub.n_tiles * sub.ksplit;
   switch (tm) {
     case 1: launch_gemm_tn<1>(tn, sub, grid, st); break;
     case 2: launch_gemm_tn<2>(tn, sub, grid, st); break;

@@ -54,6 +54,9 @@ CASES = [
     (2, 60, 2, 5, 2, 8, 8, 1, 0.07, 1.0),
     (2, 36, 5, 3, 2, 24, 12, 3, 0.031, 2.0),
     (2, 240, 7, 12, 2, 128, 32, 2, 0.05, 3.0),    # EigenWorms dims, short path
+    (2, 240, 6, 12, 2, 128, 32, 2, 0.05, 3.0),    # EigenWorms dims without time channel (fast path, C=6)
+    (3, 120, 4, 12, 2, 128, 32, 2, 0.07, 3.0),    # fast path, C=4
+    (2, 240, 7, 12, 1, 128, 32, 2, 0.05, 3.0),    # fast path, depth 1
     (2, 60, 6, 4, 2, 64, 128, 3, 0.05, 4.0),      # toy dims: weights stream from global/L2
     (2, 100, 7, 10, 2, 128, 64, 3, 0.1, 4.0),     # PPG depth-2 dims
     (2, 100, 7, 10, 1, 128, 64, 3, 0.1, 4.0),     # PPG reference config (depth 1)
