@@ -1,17 +1,23 @@
 // Specialised Log-NCDE solve kernels for the EigenWorms model shape
 // (hidden H = 128, vector-field width 32, 2 hidden layers; C <= 8 channels).
 //
-// Same algorithm and workspace layout as the generic kernels in logncde.cu, but laid out
-// so that the instruction count per Heun stage is close to the FMA floor:
-//   * the last MLP layer (C*128 x 32, 80 % of the weights) lives in REGISTERS: each of the
-//     C*64 "row threads" owns an 8 x 8 tile (8 consecutive output rows x 8 inputs).  The
-//     same tile serves W a (forward: reduce over the 4 column groups = lane bits 0-1) and
-//     W^T v (adjoint: reduce over the 8 row groups = lane bits 2-4) through shuffle
-//     "transpose-reductions" that halve the live values at every step.
-//   * the small layers (32 x 128, 32 x 32) sit in shared memory in the exact order the
-//     threads read them (one conflict-free 128-bit load per 4 weights), each thread
-//     applying its slice to the primal or to all C tangents.
-//   * all loops are compile-time; one __syncthreads per dependent phase.
+// Same algorithm and workspace layout as the generic kernels in logncde.cu, organised so
+// that the instruction count and the shared-memory wavefronts per Heun stage are close to
+// the floor (ncu of the first version: 3 860 smem wavefronts / 9 300 warp-instructions per
+// stage, LSU-bound; see profiles/):
+//   * last MLP layer (C*128 x 32, 80 % of the weights) in REGISTERS: each of the C*64 "row
+//     threads" owns an 8 x 8 tile (8 consecutive output rows x 8 inputs).  The same tile
+//     serves W a (forward: reduce over the 4 column groups = lane bits 0-1) and W^T v
+//     (adjoint: reduce over the 8 row groups = lane bits 2-4) through shuffle
+//     transpose-reductions that halve the live values at every step.
+//   * hidden layers (32 x 128, 32 x 32): lane = output row, warp = K-slice.  Every lane of
+//     a warp reads the SAME input slice (one broadcast wavefront per 128-bit load), weights
+//     sit in registers, K-slices are combined through shared memory - no shuffles.
+//   * the antisymmetric level-2 mixing w_j = sum_i Lam_ij f_i is moved through the first
+//     layer by linearity:  W1 w_j = sum_i Lam_ij (W1 f_i), so it acts on 32-vectors instead
+//     of 128-vectors (forward) and  Lam^T-mixing of u1-bar gives v_i with
+//     o-bar_i += W1^T v_i,  dW1 += sum_i v_i (x) f_i  (adjoint).
+//   * all loops compile-time; one __syncthreads per dependent phase.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -24,8 +30,7 @@ constexpr int H = 128, W = 32, NT = 512;
 
 __device__ __forceinline__ float sigm(float z) { return 1.f / (1.f + expf(-z)); }
 
-// One halving step of a transpose-reduction across lanes lane^mask: v[0..HALF) keeps the
-// lower half for lanes with upper == false and the upper half otherwise.
+// One halving step of a transpose-reduction across lanes lane^mask.
 template <int HALF>
 __device__ __forceinline__ void xstep(float* v, bool upper, int mask) {
 #pragma unroll
@@ -36,45 +41,41 @@ __device__ __forceinline__ void xstep(float* v, bool upper, int mask) {
   }
 }
 
-__device__ __forceinline__ float dot8(const float4& a0, const float4& a1, const float4& b0, const float4& b1) {
-  float s = a0.x * b0.x;
-  s = fmaf(a0.y, b0.y, s);
-  s = fmaf(a0.z, b0.z, s);
-  s = fmaf(a0.w, b0.w, s);
-  float t = a1.x * b1.x;
-  t = fmaf(a1.y, b1.y, t);
-  t = fmaf(a1.z, b1.z, t);
-  t = fmaf(a1.w, b1.w, t);
-  return s + t;
+__device__ __forceinline__ float dot4(const float* w, const float4& x) {
+  float s = w[0] * x.x;
+  s = fmaf(w[1], x.y, s);
+  s = fmaf(w[2], x.z, s);
+  return fmaf(w[3], x.w, s);
+}
+__device__ __forceinline__ float dot8(const float* w, const float4& x0, const float4& x1) {
+  return dot4(w, x0) + dot4(w + 4, x1);
 }
 
-// shared-memory plan (float offsets)
 template <int C>
 struct Smem {
   static constexpr int CH = C * H, CW = C * W;
-  // weights
-  static constexpr int W1 = 0;               // [32][128] row-major
-  static constexpr int W2 = W1 + W * H;      // [32][32]
-  static constexpr int W1T = W2 + W * W;     // [128][32]   (backward only)
-  static constexpr int W2T = W1T + H * W;    // [32][32]    (backward only)
-  static constexpr int WEND_FWD = W1T;
+  // weight region (backward only): transposed small layers in per-thread order
+  static constexpr int W1T = 0;              // [16 warps][2 halves][32 lanes][4]
+  static constexpr int W2T = W1T + H * W;    // [8 slices][32 lanes][4]
+  static constexpr int WEND_FWD = 0;
   static constexpr int WEND_BWD = W2T + W * W;
   // stage buffer (relative)
   static constexpr int yin = 0, z1 = yin + H, a1 = z1 + W, s1 = a1 + W, z2 = s1 + W, a2 = z2 + W, s2 = a2 + W;
-  static constexpr int o = s2 + W, w = o + CH, u1 = w + CH, p1 = u1 + CW, u2 = p1 + CW, p2 = u2 + CW;
+  static constexpr int o = s2 + W, u1 = o + CH, p1 = u1 + CW, u2 = p1 + CW, p2 = u2 + CW;
   static constexpr int STAGE = p2 + CW;
   // common (relative to the common base)
   static constexpr int lam = 0;              // [8][8]
   static constexpr int lam1 = lam + 64;      // [8]
   static constexpr int dbuf = lam1 + 8;      // [CH]  last-layer tangent outputs / row staging
-  static constexpr int ycur = dbuf + CH, k1 = ycur + H;
+  static constexpr int part = dbuf + CH;     // [4096] K-slice partials
+  static constexpr int qv = part + 4096;     // [C][32]
+  static constexpr int ycur = qv + CW, k1 = ycur + H;
   static constexpr int COMMON_FWD = k1 + H;
   // backward extras
-  static constexpr int g = COMMON_FWD, ybar = g + H, ab = ybar + H, yout = ab + H;
-  static constexpr int red = yout + H;       // [16][32]
-  static constexpr int wbar = red + 16 * W;  // [C][128]
-  static constexpr int ub2 = wbar + CH, ub1 = ub2 + CW, sp2 = ub1 + CW, sp1 = sp2 + CW;  // [C][32] each
-  static constexpr int sb2 = sp1 + CW, sb1 = sb2 + W, zb2 = sb1 + W, zb1 = zb2 + W;
+  static constexpr int g = COMMON_FWD, ybar = g + H, ab = ybar + H;
+  static constexpr int red = ab + H;         // [16][32]
+  static constexpr int ub2 = red + 16 * W, ub1 = ub2 + CW, sp2 = ub1 + CW, sp1 = sp2 + CW, vb = sp1 + CW;
+  static constexpr int sb2 = vb + CW, sb1 = sb2 + W, zb2 = sb1 + W, zb1 = zb2 + W;
   static constexpr int bacc = zb1 + W;       // [64] bias accumulators of the two hidden layers
   static constexpr int COMMON_BWD = bacc + 2 * W;
 };
@@ -82,22 +83,25 @@ struct Smem {
 struct Regs {
   float Wt[8][8];  // last-layer tile: rows r0..r0+7, inputs cg*8..cg*8+7
   float b3[2];     // bias of the two rows this lane finishes
-  float b1, b2;    // hidden-layer biases of output o = tid / 16
+  float w1[8];     // W1[lane][warp*8 .. +7]
+  float w2[4];     // W2[lane][(warp&7)*4 .. +3]
+  float b1, b2;    // hidden-layer biases of output row = lane
 };
 
-// rows finished by this lane after the forward transpose-reduce
 __device__ __forceinline__ int lane_row0(int tid) {
   const int lane = tid & 31, warp = tid >> 5;
-  const int rg = lane >> 2;
-  return (warp * 8 + rg) * 8 + (lane & 1) * 4 + ((lane >> 1) & 1) * 2;
+  return (warp * 8 + (lane >> 2)) * 8 + (lane & 1) * 4 + ((lane >> 1) & 1) * 2;
 }
 
 template <int C>
 __device__ __forceinline__ void load_regs(Regs& R, const float* __restrict__ params, const MlpDesc& d) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int o = tid >> 4;
-  R.b1 = params[d.b_off[0] + o];
-  R.b2 = params[d.b_off[1] + o];
+  R.b1 = params[d.b_off[0] + lane];
+  R.b2 = params[d.b_off[1] + lane];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) R.w1[e] = params[d.w_off[0] + lane * H + warp * 8 + e];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) R.w2[e] = params[d.w_off[1] + lane * W + (warp & 7) * 4 + e];
   if (tid < C * 64) {
     const int r0 = (warp * 8 + (lane >> 2)) * 8, cg = lane & 3;
 #pragma unroll
@@ -110,33 +114,19 @@ __device__ __forceinline__ void load_regs(Regs& R, const float* __restrict__ par
   }
 }
 
-// y[r0+e] = sum_k Wt[e][k] * x[cg*8+k], reduced over the 4 column groups; the lane ends
-// with the two complete sums of rows lane_row0, lane_row0+1.
 __device__ __forceinline__ void tile_rows(const Regs& R, const float* __restrict__ x8, int lane, float& r_a,
                                           float& r_b) {
   const float4 x0 = *reinterpret_cast<const float4*>(x8);
   const float4 x1 = *reinterpret_cast<const float4*>(x8 + 4);
   float v[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    float s = R.Wt[e][0] * x0.x;
-    s = fmaf(R.Wt[e][1], x0.y, s);
-    s = fmaf(R.Wt[e][2], x0.z, s);
-    s = fmaf(R.Wt[e][3], x0.w, s);
-    s = fmaf(R.Wt[e][4], x1.x, s);
-    s = fmaf(R.Wt[e][5], x1.y, s);
-    s = fmaf(R.Wt[e][6], x1.z, s);
-    s = fmaf(R.Wt[e][7], x1.w, s);
-    v[e] = s;
-  }
+  for (int e = 0; e < 8; ++e) v[e] = dot8(R.Wt[e], x0, x1);
   xstep<4>(v, lane & 1, 1);
   xstep<2>(v, lane & 2, 2);
   r_a = v[0];
   r_b = v[1];
 }
 
-// col[cg*8+k] = sum_e Wt[e][k] * x[r0+e], reduced over the 8 row groups of the warp; the lane
-// ends with the warp-partial of column cg*8 + (bit2*4 + bit3*2 + bit4).
 __device__ __forceinline__ float tile_cols(const Regs& R, const float* __restrict__ x8, int lane) {
   const float4 x0 = *reinterpret_cast<const float4*>(x8);
   const float4 x1 = *reinterpret_cast<const float4*>(x8 + 4);
@@ -162,16 +152,6 @@ __device__ __forceinline__ int lane_col(int lane) {
   return (lane & 3) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 4) & 1);
 }
 
-// C vectors reduced over 16 lanes (bits 0-3): on exit lanes with even q hold the total of
-// vector q >> 1 in v[0].
-__device__ __forceinline__ void reduce16_vec8(float* v, int q) {
-  xstep<4>(v, q & 8, 8);
-  xstep<2>(v, q & 4, 4);
-  xstep<1>(v, q & 2, 2);
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-__device__ __forceinline__ int vec_of_q(int q) { return ((q >> 3) & 1) * 4 + ((q >> 2) & 1) * 2 + ((q >> 1) & 1); }
-
 template <int C>
 __device__ __forceinline__ void load_lambda(float* cm, const float* __restrict__ row, bool d2) {
   using S = Smem<C>;
@@ -191,52 +171,47 @@ __device__ __forceinline__ void load_lambda(float* cm, const float* __restrict__
   }
 }
 
+// z = b + sum_q part[q*32 + lane] over NQ K-slices, then SiLU and its derivative.
+template <int NQ>
+__device__ __forceinline__ void hidden_finish(const float* part, float bias, int lane, float* z_out, float* a_out,
+                                              float* s_out) {
+  float acc[4] = {bias, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int qq = 0; qq < NQ; ++qq) acc[qq & 3] += part[qq * 32 + lane];
+  const float z = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  const float sg = sigm(z);
+  z_out[lane] = z;
+  a_out[lane] = z * sg;
+  s_out[lane] = sg * (1.f + z * (1.f - sg));
+}
+
 // Forward evaluation of the field at sb[yin].  Leaves every intermediate in `sb`, the
-// last-layer outputs of this lane in o_r / u3_r and, after the trailing barrier, the
-// per-row tangent contributions in cm[dbuf].  The caller finishes
+// last-layer outputs of this lane in o_r / u3_r and, after the trailing barrier, the per-row
+// tangent contributions in cm[dbuf].  The caller finishes
 //   G[h] = sum_i lam1[i] o[i][h] + sum_j dbuf[j][h].
 template <int C, bool D2>
-__device__ __forceinline__ void stage_forward(const float* __restrict__ sw, float* sb, float* cm, const Regs& R,
-                                              const float* __restrict__ ls_row, float (&o_r)[2], float (&u3_r)[2]) {
+__device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& R, const float* __restrict__ ls_row,
+                                              float (&o_r)[2], float (&u3_r)[2]) {
   using S = Smem<C>;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int o = tid >> 4, q = tid & 15;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* part = cm + S::part;
   load_lambda<C>(cm, ls_row, D2);
-  // P1: z1 = W1 y + b1
-  const float4 w1a = *reinterpret_cast<const float4*>(sw + S::W1 + tid * 8);
-  const float4 w1b = *reinterpret_cast<const float4*>(sw + S::W1 + tid * 8 + 4);
+  // P1: K-slice partials of z1 = W1 y
   {
-    const float4 ya = *reinterpret_cast<const float4*>(sb + S::yin + q * 8);
-    const float4 yb = *reinterpret_cast<const float4*>(sb + S::yin + q * 8 + 4);
-    float acc = dot8(w1a, w1b, ya, yb);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (q == 0) {
-      const float z = acc + R.b1, sg = sigm(z);
-      sb[S::z1 + o] = z;
-      sb[S::a1 + o] = z * sg;
-      sb[S::s1 + o] = sg * (1.f + z * (1.f - sg));
-    }
+    const float4 ya = *reinterpret_cast<const float4*>(sb + S::yin + warp * 8);
+    const float4 yb = *reinterpret_cast<const float4*>(sb + S::yin + warp * 8 + 4);
+    part[warp * 32 + lane] = dot8(R.w1, ya, yb);
   }
   __syncthreads();
-  // P2: z2 = W2 a1 + b2
-  const float2 w2 = *reinterpret_cast<const float2*>(sw + S::W2 + tid * 2);
-  {
-    const float2 a = *reinterpret_cast<const float2*>(sb + S::a1 + q * 2);
-    float acc = fmaf(w2.y, a.y, w2.x * a.x);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (q == 0) {
-      const float z = acc + R.b2, sg = sigm(z);
-      sb[S::z2 + o] = z;
-      sb[S::a2 + o] = z * sg;
-      sb[S::s2 + o] = sg * (1.f + z * (1.f - sg));
-    }
+  if (warp == 0) hidden_finish<16>(part, R.b1, lane, sb + S::z1, sb + S::a1, sb + S::s1);
+  __syncthreads();
+  // P2: z2 = W2 a1
+  if (warp < 8) {
+    const float4 a = *reinterpret_cast<const float4*>(sb + S::a1 + warp * 4);
+    part[warp * 32 + lane] = dot4(R.w2, a);
   }
+  __syncthreads();
+  if (warp == 0) hidden_finish<8>(part, R.b2, lane, sb + S::z2, sb + S::a2, sb + S::s2);
   __syncthreads();
   // P3: o = tanh(W3 a2 + b3)
   const int row0 = lane_row0(tid);
@@ -249,59 +224,50 @@ __device__ __forceinline__ void stage_forward(const float* __restrict__ sw, floa
   }
   __syncthreads();
   if (!D2) return;
-  // P4: w_j = sum_i Lam_ij o_i
-  if (tid < C * 64) {
-    const int j = tid >> 6, hh = tid & 63;
-    float wa = 0.f, wb = 0.f;
+  // P5: q_i = W1 o_i, K-slice partials
 #pragma unroll
-    for (int i = 0; i < C; ++i) {
-      const float l = cm[S::lam + i * 8 + j];
-      wa = fmaf(l, sb[S::o + i * H + hh], wa);
-      wb = fmaf(l, sb[S::o + i * H + hh + 64], wb);
-    }
-    sb[S::w + j * H + hh] = wa;
-    sb[S::w + j * H + hh + 64] = wb;
+  for (int i = 0; i < C; ++i) {
+    const float4 xa = *reinterpret_cast<const float4*>(sb + S::o + i * H + warp * 8);
+    const float4 xb = *reinterpret_cast<const float4*>(sb + S::o + i * H + warp * 8 + 4);
+    part[(warp * 8 + i) * 32 + lane] = dot8(R.w1, xa, xb);
   }
   __syncthreads();
-  // P5: u1_j = W1 w_j, p1_j = s1 * u1_j
-  {
-    float v[8];
+  if (warp < C) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int qq = 0; qq < 16; ++qq) acc[qq & 3] += part[(qq * 8 + warp) * 32 + lane];
+    cm[S::qv + warp * W + lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+  __syncthreads();
+  // u1_j = sum_i Lam_ij q_i ; p1_j = s1 * u1_j
+  if (warp < C) {
+    float u = 0.f;
+#pragma unroll
+    for (int i = 0; i < C; ++i) u = fmaf(cm[S::lam + i * 8 + warp], cm[S::qv + i * W + lane], u);
+    sb[S::u1 + warp * W + lane] = u;
+    sb[S::p1 + warp * W + lane] = sb[S::s1 + lane] * u;
+  }
+  __syncthreads();
+  // P6: u2_j = W2 p1_j (8 K-slices x 2 vector halves)
+  {
+    const int q = warp & 7, j0 = (warp >> 3) * 4;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
       if (j < C) {
-        const float4 xa = *reinterpret_cast<const float4*>(sb + S::w + j * H + q * 8);
-        const float4 xb = *reinterpret_cast<const float4*>(sb + S::w + j * H + q * 8 + 4);
-        v[j] = dot8(w1a, w1b, xa, xb);
-      } else {
-        v[j] = 0.f;
+        const float4 x = *reinterpret_cast<const float4*>(sb + S::p1 + j * W + q * 4);
+        part[(q * 8 + j) * 32 + lane] = dot4(R.w2, x);
       }
-    }
-    reduce16_vec8(v, q);
-    const int jv = vec_of_q(q);
-    if (!(q & 1) && jv < C) {
-      sb[S::u1 + jv * W + o] = v[0];
-      sb[S::p1 + jv * W + o] = sb[S::s1 + o] * v[0];
     }
   }
   __syncthreads();
-  // P6: u2_j = W2 p1_j, p2_j = s2 * u2_j
-  {
-    float v[8];
+  if (warp < C) {
+    float acc[2] = {0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < C) {
-        const float2 x = *reinterpret_cast<const float2*>(sb + S::p1 + j * W + q * 2);
-        v[j] = fmaf(w2.y, x.y, w2.x * x.x);
-      } else {
-        v[j] = 0.f;
-      }
-    }
-    reduce16_vec8(v, q);
-    const int jv = vec_of_q(q);
-    if (!(q & 1) && jv < C) {
-      sb[S::u2 + jv * W + o] = v[0];
-      sb[S::p2 + jv * W + o] = sb[S::s2 + o] * v[0];
-    }
+    for (int qq = 0; qq < 8; ++qq) acc[qq & 1] += part[(qq * 8 + warp) * 32 + lane];
+    const float u = acc[0] + acc[1];
+    sb[S::u2 + warp * W + lane] = u;
+    sb[S::p2 + warp * W + lane] = sb[S::s2 + lane] * u;
   }
   __syncthreads();
   // P7: u3 = W3[block j] p2_j ; d = (1 - o^2) u3
@@ -327,25 +293,20 @@ __device__ __forceinline__ float field_value(const float* sb, const float* cm, i
   return gsum;
 }
 
+// transposed small layers, stored in the order the backward threads read them
 template <int C>
-__device__ __forceinline__ void stage_weights_fast(const MlpDesc& d, const float* __restrict__ params, float* sw,
-                                                   bool bwd) {
+__device__ __forceinline__ void stage_weights_bwd(const MlpDesc& d, const float* __restrict__ params, float* sw) {
   using S = Smem<C>;
+  // W1T: thread (lane, hq = warp&3, ks = warp>>2) handles h = hq*32 + lane, inputs c = ks*8 + half*4 + e
   for (int t = threadIdx.x; t < W * H; t += NT) {
-    const float v = params[d.w_off[0] + t];
-    sw[S::W1 + t] = v;
-    if (bwd) {
-      const int c = t / H, h = t - c * H;
-      sw[S::W1T + h * W + c] = v;
-    }
+    const int e = t & 3, lane = (t >> 2) & 31, half = (t >> 7) & 1, warp = t >> 8;
+    const int h = (warp & 3) * 32 + lane, c = (warp >> 2) * 8 + half * 4 + e;
+    sw[S::W1T + t] = params[d.w_off[0] + c * H + h];
   }
+  // W2T: thread (lane = c', q) : inputs c = q*4 + e
   for (int t = threadIdx.x; t < W * W; t += NT) {
-    const float v = params[d.w_off[1] + t];
-    sw[S::W2 + t] = v;
-    if (bwd) {
-      const int c = t / W, c2 = t - c * W;
-      sw[S::W2T + c2 * W + c] = v;
-    }
+    const int e = t & 3, lane = (t >> 2) & 31, q = t >> 7;
+    sw[S::W2T + t] = params[d.w_off[1] + (q * 4 + e) * W + lane];
   }
 }
 
@@ -354,13 +315,11 @@ template <int C, bool D2>
 __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams p) {
   using S = Smem<C>;
   extern __shared__ __align__(16) float smem[];
-  float* sw = smem;
   float* sb = smem + S::WEND_FWD;
   float* cm = sb + S::STAGE;
   const int tid = threadIdx.x;
   Regs R;
   load_regs<C>(R, p.params, p.d);
-  stage_weights_fast<C>(p.d, p.params, sw, false);
   const int b = blockIdx.x;
   const float* ls = p.logsig + (size_t)b * p.K * p.D;
   float* ys = p.ys + (size_t)b * (p.n_steps + 1) * H;
@@ -375,14 +334,14 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
   for (int n = 0; n < p.n_steps; ++n) {
     const int r1 = p.stage_row[2 * n], r2 = p.stage_row[2 * n + 1];
     const float s1 = p.stage_scale[2 * n], s2 = p.stage_scale[2 * n + 1];
-    stage_forward<C, D2>(sw, sb, cm, R, ls + (size_t)r1 * p.D, o_r, u3_r);
+    stage_forward<C, D2>(sb, cm, R, ls + (size_t)r1 * p.D, o_r, u3_r);
     if (tid < H) {
       const float kk = s1 * field_value<C, D2>(sb, cm, tid);
       cm[S::k1 + tid] = kk;
       sb[S::yin + tid] = cm[S::ycur + tid] + kk;
     }
     __syncthreads();
-    stage_forward<C, D2>(sw, sb, cm, R, ls + (size_t)r2 * p.D, o_r, u3_r);
+    stage_forward<C, D2>(sb, cm, R, ls + (size_t)r2 * p.D, o_r, u3_r);
     if (tid < H) {
       const float yn = cm[S::ycur + tid] + 0.5f * (cm[S::k1 + tid] + s2 * field_value<C, D2>(sb, cm, tid));
       cm[S::ycur + tid] = yn;
@@ -394,8 +353,9 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
 }
 
 // ------------------------------------------------------------------------------ backward
-// Reverse sweep of one stage.  cm[g] holds dLoss/dG times the stage scale; on exit (after the
-// trailing barrier) cm[yout] holds dLoss/d(stage input).
+// Reverse sweep of one stage.  cm[g] holds dLoss/dG times the stage scale.  On exit (after the
+// trailing barrier) cm[part + ks*128 + h], ks < 4, hold the K-slice partials of
+// dLoss/d(stage input); the caller sums them.
 template <int C, bool D2>
 __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, float* sb, float* cm, const Regs& R,
                                               const float (&o_r)[2], const float (&u3_r)[2], float (&b3acc)[2],
@@ -403,8 +363,8 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
   using S = Smem<C>;
   constexpr int CH = C * H, CW = C * W;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int o = tid >> 4, q = tid & 15;
   const int row0 = lane_row0(tid);
+  float* part = cm + S::part;
   // right-hand vectors of the weight-gradient outer products
   if (tid < H) wsp[ws.Y + slot * H + tid] = sb[S::yin + tid];
   if (tid < W) {
@@ -412,7 +372,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     wsp[ws.A[1] + slot * W + tid] = sb[S::a2 + tid];
   }
   if (D2) {
-    for (int t = tid; t < CH; t += NT) wsp[ws.Wt + slot * CH + t] = sb[S::w + t];
+    for (int t = tid; t < CH; t += NT) wsp[ws.Wt + slot * CH + t] = sb[S::o + t];  // pairs with v_i (see header)
     if (tid < CW) {
       wsp[ws.P[0] + slot * CW + tid] = sb[S::p1 + tid];
       wsp[ws.P[1] + slot * CW + tid] = sb[S::p2 + tid];
@@ -435,91 +395,90 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
       *reinterpret_cast<float2*>(wsp + ws.UL + slot * CH + row0) = ub;
       *reinterpret_cast<float2*>(cm + S::dbuf + row0) = ub;
       __syncwarp();
-      const float part = tile_cols(R, cm + S::dbuf + (warp * 8 + (lane >> 2)) * 8, lane);
-      cm[S::red + warp * W + lane_col(lane)] = part;
+      const float pr = tile_cols(R, cm + S::dbuf + (warp * 8 + (lane >> 2)) * 8, lane);
+      cm[S::red + warp * W + lane_col(lane)] = pr;
     }
   }
   if (D2) {
     __syncthreads();
     // Q2: u2-bar = s2 * p2-bar ; s2-bar partials
-    if (tid < CW) {
-      const int j = tid >> 5, c = tid & 31;
-      const float pb = cm[S::red + (2 * j) * W + c] + cm[S::red + (2 * j + 1) * W + c];
-      const float ub = sb[S::s2 + c] * pb;
+    if (warp < C) {
+      const float pb = cm[S::red + (2 * warp) * W + lane] + cm[S::red + (2 * warp + 1) * W + lane];
+      const float ub = sb[S::s2 + lane] * pb;
       cm[S::ub2 + tid] = ub;
       cm[S::sp2 + tid] = sb[S::u2 + tid] * pb;
       wsp[ws.U[1] + slot * CW + tid] = ub;
     }
     __syncthreads();
-    // Q3: p1-bar_j = W2^T u2-bar_j ; u1-bar = s1 * p1-bar ; s1-bar partials ; s2-bar
+    // Q3: p1-bar_j = W2^T u2-bar_j  (8 K-slices x 2 vector halves) ; s2-bar
     {
-      const float2 w2t = *reinterpret_cast<const float2*>(sw + S::W2T + tid * 2);
-      float v[8];
+      const int q = warp & 7, j0 = (warp >> 3) * 4;
+      const float4 wt = *reinterpret_cast<const float4*>(sw + S::W2T + (q * 32 + lane) * 4);
+      const float w4[4] = {wt.x, wt.y, wt.z, wt.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = j0 + jj;
         if (j < C) {
-          const float2 x = *reinterpret_cast<const float2*>(cm + S::ub2 + j * W + q * 2);
-          v[j] = fmaf(w2t.y, x.y, w2t.x * x.x);
-        } else {
-          v[j] = 0.f;
+          const float4 x = *reinterpret_cast<const float4*>(cm + S::ub2 + j * W + q * 4);
+          part[(q * 8 + j) * 32 + lane] = dot4(w4, x);
         }
       }
-      reduce16_vec8(v, q);
-      const int jv = vec_of_q(q);
-      if (!(q & 1) && jv < C) {
-        const float ub = sb[S::s1 + o] * v[0];
-        cm[S::ub1 + jv * W + o] = ub;
-        cm[S::sp1 + jv * W + o] = sb[S::u1 + jv * W + o] * v[0];
-        wsp[ws.U[0] + slot * CW + jv * W + o] = ub;
-      }
-      if (tid < W) {
+      if (warp == 15) {
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < C; ++j) s += cm[S::sp2 + j * W + tid];
-        cm[S::sb2 + tid] = s;
+        for (int j = 0; j < C; ++j) s += cm[S::sp2 + j * W + lane];
+        cm[S::sb2 + lane] = s;
       }
     }
     __syncthreads();
-    // Q4: w-bar_j = W1^T u1-bar_j ; s1-bar
+    // u1-bar = s1 * p1-bar ; s1-bar partials
+    if (warp < C) {
+      float acc[2] = {0.f, 0.f};
+#pragma unroll
+      for (int qq = 0; qq < 8; ++qq) acc[qq & 1] += part[(qq * 8 + warp) * 32 + lane];
+      const float pb = acc[0] + acc[1];
+      cm[S::ub1 + tid] = sb[S::s1 + lane] * pb;
+      cm[S::sp1 + tid] = sb[S::u1 + tid] * pb;
+    }
+    __syncthreads();
+    // v_i = sum_j Lam_ij u1-bar_j ; s1-bar
+    if (warp < C) {
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) v = fmaf(cm[S::lam + warp * 8 + j], cm[S::ub1 + j * W + lane], v);
+      cm[S::vb + tid] = v;
+      wsp[ws.U[0] + slot * CW + tid] = v;
+    } else if (warp == 15) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < C; ++j) s += cm[S::sp1 + j * W + lane];
+      cm[S::sb1 + lane] = s;
+    }
+    __syncthreads();
+    // Q4: o-bar_i[h] += sum_c W1[c][h] v_i[c]   (4 K-slices x 4 h-quarters)
     {
-      const int h = tid >> 2, q4 = tid & 3;
-      const float4 wa = *reinterpret_cast<const float4*>(sw + S::W1T + tid * 8);
-      const float4 wb = *reinterpret_cast<const float4*>(sw + S::W1T + tid * 8 + 4);
-      float v[8];
+      const int ks = warp >> 2, h = (warp & 3) * 32 + lane;
+      const float4 wa = *reinterpret_cast<const float4*>(sw + S::W1T + ((warp * 2 + 0) * 32 + lane) * 4);
+      const float4 wb = *reinterpret_cast<const float4*>(sw + S::W1T + ((warp * 2 + 1) * 32 + lane) * 4);
+      const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < C) {
-          const float4 xa = *reinterpret_cast<const float4*>(cm + S::ub1 + j * W + q4 * 8);
-          const float4 xb = *reinterpret_cast<const float4*>(cm + S::ub1 + j * W + q4 * 8 + 4);
-          v[j] = dot8(wa, wb, xa, xb);
-        } else {
-          v[j] = 0.f;
-        }
-      }
-      xstep<4>(v, q4 & 1, 1);
-      xstep<2>(v, q4 & 2, 2);
-      const int jv = (q4 & 1) * 4 + ((q4 >> 1) & 1) * 2;
-      if (jv < C) cm[S::wbar + jv * H + h] = v[0];
-      if (jv + 1 < C) cm[S::wbar + (jv + 1) * H + h] = v[1];
-      if (tid < W) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < C; ++j) s += cm[S::sp1 + j * W + tid];
-        cm[S::sb1 + tid] = s;
+      for (int i = 0; i < C; ++i) {
+        const float4 xa = *reinterpret_cast<const float4*>(cm + S::vb + i * W + ks * 8);
+        const float4 xb = *reinterpret_cast<const float4*>(cm + S::vb + i * W + ks * 8 + 4);
+        part[(ks * 8 + i) * H + h] = dot8(w8, xa, xb);
       }
     }
     __syncthreads();
   }
-  // Q5: o-bar += Lam w-bar ; z3-bar = (1 - o^2) o-bar ; a2-bar partials
+  // Q5: o-bar complete ; z3-bar = (1 - o^2) o-bar ; a2-bar partials
   if (tid < C * 64) {
     const int j = tid >> 6, h0 = row0 & (H - 1);
     if (D2) {
 #pragma unroll
-      for (int jj = 0; jj < C; ++jj) {
-        const float l = cm[S::lam + j * 8 + jj];
-        const float2 wv = *reinterpret_cast<const float2*>(cm + S::wbar + jj * H + h0);
-        ob[0] = fmaf(l, wv.x, ob[0]);
-        ob[1] = fmaf(l, wv.y, ob[1]);
+      for (int ks = 0; ks < 4; ++ks) {
+        const float2 pv = *reinterpret_cast<const float2*>(part + (ks * 8 + j) * H + h0);
+        ob[0] += pv.x;
+        ob[1] += pv.y;
       }
     }
     const float2 zb = make_float2(tp[0] * ob[0], tp[1] * ob[1]);
@@ -528,59 +487,65 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     *reinterpret_cast<float2*>(wsp + ws.ZL + slot * CH + row0) = zb;
     *reinterpret_cast<float2*>(cm + S::dbuf + row0) = zb;
     __syncwarp();
-    const float part = tile_cols(R, cm + S::dbuf + (warp * 8 + (lane >> 2)) * 8, lane);
-    cm[S::red + warp * W + lane_col(lane)] = part;
+    const float pr = tile_cols(R, cm + S::dbuf + (warp * 8 + (lane >> 2)) * 8, lane);
+    cm[S::red + warp * W + lane_col(lane)] = pr;
   }
   __syncthreads();
   // Q6: a2-bar ; z2-bar
-  if (tid < W) {
-    float ab2 = 0.f;
+  if (warp == 0) {
+    float acc[2] = {0.f, 0.f};
 #pragma unroll
-    for (int wq = 0; wq < 2 * C; ++wq) ab2 += cm[S::red + wq * W + tid];
-    float zb = sb[S::s2 + tid] * ab2;
+    for (int wq = 0; wq < 2 * C; ++wq) acc[wq & 1] += cm[S::red + wq * W + lane];
+    float zb = sb[S::s2 + lane] * (acc[0] + acc[1]);
     if (D2) {
-      const float z = sb[S::z2 + tid], sg = sigm(z);
-      zb = fmaf(sg * (1.f - sg) * (2.f + z * (1.f - 2.f * sg)), cm[S::sb2 + tid], zb);
+      const float z = sb[S::z2 + lane], sg = sigm(z);
+      zb = fmaf(sg * (1.f - sg) * (2.f + z * (1.f - 2.f * sg)), cm[S::sb2 + lane], zb);
     }
-    cm[S::zb2 + tid] = zb;
-    cm[S::bacc + W + tid] += zb;
-    wsp[ws.Z[1] + slot * W + tid] = zb;
+    cm[S::zb2 + lane] = zb;
+    cm[S::bacc + W + lane] += zb;
+    wsp[ws.Z[1] + slot * W + lane] = zb;
   }
   __syncthreads();
-  // Q7: a1-bar = W2^T z2-bar ; z1-bar
-  {
-    const float2 w2t = *reinterpret_cast<const float2*>(sw + S::W2T + tid * 2);
-    const float2 x = *reinterpret_cast<const float2*>(cm + S::zb2 + q * 2);
-    float acc = fmaf(w2t.y, x.y, w2t.x * x.x);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (q == 0) {
-      float zb = sb[S::s1 + o] * acc;
-      if (D2) {
-        const float z = sb[S::z1 + o], sg = sigm(z);
-        zb = fmaf(sg * (1.f - sg) * (2.f + z * (1.f - 2.f * sg)), cm[S::sb1 + o], zb);
-      }
-      cm[S::zb1 + o] = zb;
-      cm[S::bacc + o] += zb;
-      wsp[ws.Z[0] + slot * W + o] = zb;
+  // Q7: a1-bar = W2^T z2-bar (8 K-slices)
+  if (warp < 8) {
+    const float4 wt = *reinterpret_cast<const float4*>(sw + S::W2T + (warp * 32 + lane) * 4);
+    const float w4[4] = {wt.x, wt.y, wt.z, wt.w};
+    const float4 x = *reinterpret_cast<const float4*>(cm + S::zb2 + warp * 4);
+    part[warp * 32 + lane] = dot4(w4, x);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float acc[2] = {0.f, 0.f};
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) acc[qq & 1] += part[qq * 32 + lane];
+    float zb = sb[S::s1 + lane] * (acc[0] + acc[1]);
+    if (D2) {
+      const float z = sb[S::z1 + lane], sg = sigm(z);
+      zb = fmaf(sg * (1.f - sg) * (2.f + z * (1.f - 2.f * sg)), cm[S::sb1 + lane], zb);
     }
+    cm[S::zb1 + lane] = zb;
+    cm[S::bacc + lane] += zb;
+    wsp[ws.Z[0] + slot * W + lane] = zb;
   }
   __syncthreads();
-  // Q8: y-bar = W1^T z1-bar
+  // Q8: y-bar = W1^T z1-bar, K-slice partials (summed by the caller)
   {
-    const int h = tid >> 2, q4 = tid & 3;
-    const float4 wa = *reinterpret_cast<const float4*>(sw + S::W1T + tid * 8);
-    const float4 wb = *reinterpret_cast<const float4*>(sw + S::W1T + tid * 8 + 4);
-    const float4 xa = *reinterpret_cast<const float4*>(cm + S::zb1 + q4 * 8);
-    const float4 xb = *reinterpret_cast<const float4*>(cm + S::zb1 + q4 * 8 + 4);
-    float acc = dot8(wa, wb, xa, xb);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    if (q4 == 0) cm[S::yout + h] = acc;
+    const int ks = warp >> 2, h = (warp & 3) * 32 + lane;
+    const float4 wa = *reinterpret_cast<const float4*>(sw + S::W1T + ((warp * 2 + 0) * 32 + lane) * 4);
+    const float4 wb = *reinterpret_cast<const float4*>(sw + S::W1T + ((warp * 2 + 1) * 32 + lane) * 4);
+    const float w8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+    const float4 xa = *reinterpret_cast<const float4*>(cm + S::zb1 + ks * 8);
+    const float4 xb = *reinterpret_cast<const float4*>(cm + S::zb1 + ks * 8 + 4);
+    part[ks * H + h] = dot8(w8, xa, xb);
   }
   __syncthreads();
+}
+
+template <int C>
+__device__ __forceinline__ float yout_value(const float* cm, int h) {
+  using S = Smem<C>;
+  const float* part = cm + S::part;
+  return (part[h] + part[H + h]) + (part[2 * H + h] + part[3 * H + h]);
 }
 
 template <int C, bool D2>
@@ -594,7 +559,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
   const int tid = threadIdx.x;
   Regs R;
   load_regs<C>(R, p.params, p.d);
-  stage_weights_fast<C>(p.d, p.params, sw, true);
+  stage_weights_bwd<C>(p.d, p.params, sw);
   const int b = blockIdx.x;
   const float* ls = p.logsig + (size_t)b * p.K * p.D;
   const float* ys = p.ys + (size_t)b * (p.n_steps + 1) * H;
@@ -610,22 +575,22 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
     const size_t slot = ((size_t)b * p.n_steps + n) * 2;
     if (tid < H) sbA[S::yin + tid] = ys[(size_t)n * H + tid];
     __syncthreads();
-    stage_forward<C, D2>(sw, sbA, cm, R, ls + (size_t)r1 * p.D, oA, uA);
+    stage_forward<C, D2>(sbA, cm, R, ls + (size_t)r1 * p.D, oA, uA);
     if (tid < H) sbB[S::yin + tid] = sbA[S::yin + tid] + s1 * field_value<C, D2>(sbA, cm, tid);
     __syncthreads();
-    stage_forward<C, D2>(sw, sbB, cm, R, ls + (size_t)r2 * p.D, oB, uB);  // leaves Lambda of row r2
+    stage_forward<C, D2>(sbB, cm, R, ls + (size_t)r2 * p.D, oB, uB);  // leaves Lambda of row r2
     if (tid < H) cm[S::g + tid] = 0.5f * s2 * cm[S::ybar + tid];
     __syncthreads();
     stage_reverse<C, D2>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1);
     if (tid < H) {
-      const float a = cm[S::yout + tid];
+      const float a = yout_value<C>(cm, tid);
       cm[S::ab + tid] = a;
       cm[S::g + tid] = s1 * (0.5f * cm[S::ybar + tid] + a);
     }
     load_lambda<C>(cm, ls + (size_t)r1 * p.D, D2);
     __syncthreads();
     stage_reverse<C, D2>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot);
-    if (tid < H) cm[S::ybar + tid] += cm[S::ab + tid] + cm[S::yout + tid] + gys[(size_t)n * H + tid];
+    if (tid < H) cm[S::ybar + tid] += cm[S::ab + tid] + yout_value<C>(cm, tid) + gys[(size_t)n * H + tid];
     __syncthreads();
   }
   if (tid < H) p.g_y0[(size_t)b * H + tid] = cm[S::ybar + tid];
