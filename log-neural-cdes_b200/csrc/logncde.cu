@@ -630,3 +630,4 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
 }
 
 }  // extern "C"
+

@@ -4,7 +4,10 @@
 // Same algorithm and workspace layout as the generic kernels in logncde.cu, organised so
 // that the instruction count and the shared-memory wavefronts per Heun stage are close to
 // the floor (ncu of the first version: 3 860 smem wavefronts / 9 300 warp-instructions per
-// stage, LSU-bound; see profiles/):
+// stage, LSU-bound; see profiles/).  A warp-specialised variant (hidden layers on single
+// warps, 5 barriers per stage instead of 12) was measured SLOWER (10.5 vs 7.2 ms forward):
+// with 64+ registers pinned by the last-layer tile a lone warp cannot keep enough loads in
+// flight, so the K-sliced all-warp form below is kept:
 //   * last MLP layer (C*128 x 32, 80 % of the weights) in REGISTERS: each of the C*64 "row
 //     threads" owns an 8 x 8 tile (8 consecutive output rows x 8 inputs).  The same tile
 //     serves W a (forward: reduce over the 4 column groups = lane bits 0-1) and W^T v
@@ -152,23 +155,30 @@ __device__ __forceinline__ int lane_col(int lane) {
   return (lane & 3) * 8 + ((lane >> 2) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 4) & 1);
 }
 
+// Level-1 / level-2 coordinates of one logsig row.  Threads 0..63 own one entry of the
+// antisymmetric matrix Lam, threads 64..71 one level-1 coefficient.  The global load is
+// issued one stage AHEAD (lambda_fetch) so its latency is off the dependent chain.
 template <int C>
-__device__ __forceinline__ void load_lambda(float* cm, const float* __restrict__ row, bool d2) {
-  using S = Smem<C>;
+__device__ __forceinline__ float lambda_fetch(const float* __restrict__ row, bool d2) {
   const int tid = threadIdx.x;
+  float v = 0.f;
   if (tid < 64) {
     const int i = tid >> 3, j = tid & 7;
-    float v = 0.f;
     if (d2 && i < C && j < C && i != j) {
       const int a = i < j ? i : j, b = i < j ? j : i;
-      v = row[1 + C + a * C - (a * (a + 1)) / 2 + (b - a - 1)];
-      if (i > j) v = -v;
+      v = __ldg(row + 1 + C + a * C - (a * (a + 1)) / 2 + (b - a - 1));  // sign applied at store time
     }
-    cm[S::lam + tid] = v;
   } else if (tid < 72) {
     const int i = tid - 64;
-    cm[S::lam1 + i] = i < C ? row[1 + i] : 0.f;
+    if (i < C) v = __ldg(row + 1 + i);
   }
+  return v;
+}
+template <int C>
+__device__ __forceinline__ void lambda_store(float* cm, float v) {
+  using S = Smem<C>;
+  const int tid = threadIdx.x;
+  if (tid < 72) cm[S::lam + tid] = (tid < 64 && (tid >> 3) > (tid & 7)) ? -v : v;  // lam1 follows lam
 }
 
 // z = b + sum_q part[q*32 + lane] over NQ K-slices, then SiLU and its derivative.
@@ -190,12 +200,12 @@ __device__ __forceinline__ void hidden_finish(const float* part, float bias, int
 // tangent contributions in cm[dbuf].  The caller finishes
 //   G[h] = sum_i lam1[i] o[i][h] + sum_j dbuf[j][h].
 template <int C, bool D2>
-__device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& R, const float* __restrict__ ls_row,
+__device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& R, float lam_v,
                                               float (&o_r)[2], float (&u3_r)[2]) {
   using S = Smem<C>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* part = cm + S::part;
-  load_lambda<C>(cm, ls_row, D2);
+  lambda_store<C>(cm, lam_v);
   // P1: K-slice partials of z1 = W1 y
   {
     const float4 ya = *reinterpret_cast<const float4*>(sb + S::yin + warp * 8);
@@ -331,17 +341,24 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
   }
   __syncthreads();
   float o_r[2], u3_r[2];
+  // software pipeline: stage table entries one step ahead, logsig rows one stage ahead
+  int r2 = p.stage_row[1];
+  float s1 = p.stage_scale[0], s2 = p.stage_scale[1];
+  float lam_a = lambda_fetch<C>(ls + (size_t)p.stage_row[0] * p.D, D2);
   for (int n = 0; n < p.n_steps; ++n) {
-    const int r1 = p.stage_row[2 * n], r2 = p.stage_row[2 * n + 1];
-    const float s1 = p.stage_scale[2 * n], s2 = p.stage_scale[2 * n + 1];
-    stage_forward<C, D2>(sb, cm, R, ls + (size_t)r1 * p.D, o_r, u3_r);
+    const int nn = n + 1 < p.n_steps ? n + 1 : n;
+    const int r1n = p.stage_row[2 * nn], r2n = p.stage_row[2 * nn + 1];
+    const float s1n = p.stage_scale[2 * nn], s2n = p.stage_scale[2 * nn + 1];
+    const float lam_b = lambda_fetch<C>(ls + (size_t)r2 * p.D, D2);
+    stage_forward<C, D2>(sb, cm, R, lam_a, o_r, u3_r);
     if (tid < H) {
       const float kk = s1 * field_value<C, D2>(sb, cm, tid);
       cm[S::k1 + tid] = kk;
       sb[S::yin + tid] = cm[S::ycur + tid] + kk;
     }
     __syncthreads();
-    stage_forward<C, D2>(sb, cm, R, ls + (size_t)r2 * p.D, o_r, u3_r);
+    lam_a = lambda_fetch<C>(ls + (size_t)r1n * p.D, D2);
+    stage_forward<C, D2>(sb, cm, R, lam_b, o_r, u3_r);
     if (tid < H) {
       const float yn = cm[S::ycur + tid] + 0.5f * (cm[S::k1 + tid] + s2 * field_value<C, D2>(sb, cm, tid));
       cm[S::ycur + tid] = yn;
@@ -349,6 +366,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
       ys[(size_t)(n + 1) * H + tid] = yn;
     }
     __syncthreads();
+    r2 = r2n; s1 = s1n; s2 = s2n;
   }
 }
 
@@ -568,17 +586,28 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
   if (tid < H) cm[S::ybar + tid] = gys[(size_t)p.n_steps * H + tid];
   float b3acc[2] = {0.f, 0.f};
   float oA[2], uA[2], oB[2], uB[2];
+  // software pipeline: everything the next step reads from global memory is fetched one
+  // step ahead (stage table, checkpoint y_n, output cotangent, the two logsig rows)
+  const int n0 = p.n_steps - 1;
+  float s1 = p.stage_scale[2 * n0], s2 = p.stage_scale[2 * n0 + 1];
+  float lam_a = lambda_fetch<C>(ls + (size_t)p.stage_row[2 * n0] * p.D, D2);
+  float lam_b = lambda_fetch<C>(ls + (size_t)p.stage_row[2 * n0 + 1] * p.D, D2);
+  float y_n = tid < H ? ys[(size_t)n0 * H + tid] : 0.f;
+  float g_n = tid < H ? gys[(size_t)n0 * H + tid] : 0.f;
   __syncthreads();
   for (int n = p.n_steps - 1; n >= 0; --n) {
-    const int r1 = p.stage_row[2 * n], r2 = p.stage_row[2 * n + 1];
-    const float s1 = p.stage_scale[2 * n], s2 = p.stage_scale[2 * n + 1];
     const size_t slot = ((size_t)b * p.n_steps + n) * 2;
-    if (tid < H) sbA[S::yin + tid] = ys[(size_t)n * H + tid];
+    const int nn = n > 0 ? n - 1 : 0;
+    const int r1n = p.stage_row[2 * nn], r2n = p.stage_row[2 * nn + 1];
+    const float s1n = p.stage_scale[2 * nn], s2n = p.stage_scale[2 * nn + 1];
+    const float y_nn = tid < H ? ys[(size_t)nn * H + tid] : 0.f;
+    const float g_nn = tid < H ? gys[(size_t)nn * H + tid] : 0.f;
+    if (tid < H) sbA[S::yin + tid] = y_n;
     __syncthreads();
-    stage_forward<C, D2>(sbA, cm, R, ls + (size_t)r1 * p.D, oA, uA);
+    stage_forward<C, D2>(sbA, cm, R, lam_a, oA, uA);
     if (tid < H) sbB[S::yin + tid] = sbA[S::yin + tid] + s1 * field_value<C, D2>(sbA, cm, tid);
     __syncthreads();
-    stage_forward<C, D2>(sbB, cm, R, ls + (size_t)r2 * p.D, oB, uB);  // leaves Lambda of row r2
+    stage_forward<C, D2>(sbB, cm, R, lam_b, oB, uB);  // leaves Lambda of row r2
     if (tid < H) cm[S::g + tid] = 0.5f * s2 * cm[S::ybar + tid];
     __syncthreads();
     stage_reverse<C, D2>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1);
@@ -587,11 +616,15 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
       cm[S::ab + tid] = a;
       cm[S::g + tid] = s1 * (0.5f * cm[S::ybar + tid] + a);
     }
-    load_lambda<C>(cm, ls + (size_t)r1 * p.D, D2);
+    lambda_store<C>(cm, lam_a);
+    const float lam_an = lambda_fetch<C>(ls + (size_t)r1n * p.D, D2);
+    const float lam_bn = lambda_fetch<C>(ls + (size_t)r2n * p.D, D2);
     __syncthreads();
     stage_reverse<C, D2>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot);
-    if (tid < H) cm[S::ybar + tid] += cm[S::ab + tid] + yout_value<C>(cm, tid) + gys[(size_t)n * H + tid];
+    if (tid < H) cm[S::ybar + tid] += cm[S::ab + tid] + yout_value<C>(cm, tid) + g_n;
     __syncthreads();
+    s1 = s1n; s2 = s2n;
+    lam_a = lam_an; lam_b = lam_bn; y_n = y_nn; g_n = g_nn;
   }
   if (tid < H) p.g_y0[(size_t)b * H + tid] = cm[S::ybar + tid];
   const int n_bias = 2 * W + C * H;
