@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "lncde_b200.h"
 
@@ -138,26 +139,36 @@ __global__ void __launch_bounds__(128) logsig_levy_kernel(const LevyParams p) {
     const int head = min(n_ld, (int)(((16 - ((uintptr_t)src & 15)) & 15) >> 2));
     const int n_v4 = (n_ld - head) >> 2;
     const float4* src4 = reinterpret_cast<const float4*>(src + head);
+    // window index once per 128-bit load; the +1 pad per window boundary is branch-free
+    const int pad = p.stride - sC;  // 0 or 1
     auto put = [&](int t, float v) {
       const uint32_t w = __umulhi((uint32_t)t, p.sc_magic);
-      win[(int)w * p.stride + (t - (int)w * sC)] = v;
+      win[t + (int)w * pad] = v;
+    };
+    auto put4 = [&](int t, const float4& v) {
+      if (sC < 4) {  // a 128-bit load may span several windows: scalar placement
+        put(t, v.x); put(t + 1, v.y); put(t + 2, v.z); put(t + 3, v.w);
+        return;
+      }
+      const int w = (int)__umulhi((uint32_t)t, p.sc_magic);
+      const int r = t - w * sC;          // position inside window w
+      float* dst = win + t + w * pad;
+      const int lim = sC - r;            // elements e >= lim belong to window w+1
+      dst[0] = v.x;
+      dst[1 + (1 >= lim ? pad : 0)] = v.y;
+      dst[2 + (2 >= lim ? pad : 0)] = v.z;
+      dst[3 + (3 >= lim ? pad : 0)] = v.w;
     };
     if (threadIdx.x < head) put(t_off + threadIdx.x, ld_stream(src + threadIdx.x));
-    for (int i = threadIdx.x; i < n_v4; i += blockDim.x * 4) {
-      float4 v[4];
+    for (int i = threadIdx.x; i < n_v4; i += blockDim.x * 6) {
+      float4 v[6];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 6; ++u)
         if (i + u * (int)blockDim.x < n_v4) v[u] = ld_stream4(src4 + i + u * blockDim.x);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 6; ++u) {
         const int ii = i + u * (int)blockDim.x;
-        if (ii < n_v4) {
-          const int t = t_off + head + 4 * ii;
-          put(t, v[u].x);
-          put(t + 1, v[u].y);
-          put(t + 2, v[u].z);
-          put(t + 3, v[u].w);
-        }
+        if (ii < n_v4) put4(t_off + head + 4 * ii, v[u]);
       }
     }
     const int tail0 = head + 4 * n_v4;
@@ -175,20 +186,32 @@ __global__ void __launch_bounds__(128) logsig_levy_kernel(const LevyParams p) {
     for (int c = 0; c < C; ++c) tmp[c] = bp[c];
     st.init(tmp);
     const float* rows = win + w * p.stride;
+#pragma unroll 4
     for (int l = 0; l < p.s; ++l) {
+      float xs[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) tmp[c] = rows[l * C + c];
-      st.step(tmp);
+      for (int c = 0; c < C; ++c) xs[c] = rows[l * C + c];
+      st.step(xs);
     }
   }
   __syncthreads();
   // ---- transpose through shared memory, contiguous coalesced store ---------
-  if (w < nw) st.store(smem + w * D);  // D odd or even: row stride D, lanes hit distinct rows
+  // staged at an offset that makes shared source and global destination 16 B aligned together
+  float* dst = p.out + ((size_t)b * p.K + k0) * D;
+  const int OUT_SHIFT = (int)(((uintptr_t)dst >> 2) & 3);
+  if (w < nw) st.store(smem + OUT_SHIFT + w * D);
   __syncthreads();
   {
-    float* dst = p.out + ((size_t)b * p.K + k0) * D;
     const int n_o = nw * D;
-    for (int t = threadIdx.x; t < n_o; t += blockDim.x) dst[t] = smem[t];
+    // 128-bit body: smem offset `oh` floats makes source and destination 16 B aligned together
+    const int oh = min(n_o, (int)(((16 - ((uintptr_t)dst & 15)) & 15) >> 2));
+    const int n4 = (n_o - oh) >> 2;
+    if (threadIdx.x < oh) dst[threadIdx.x] = smem[OUT_SHIFT + threadIdx.x];
+    const float4* s4 = reinterpret_cast<const float4*>(smem + OUT_SHIFT + oh);
+    float4* d4 = reinterpret_cast<float4*>(dst + oh);
+    for (int t = threadIdx.x; t < n4; t += blockDim.x) d4[t] = s4[t];
+    const int ot = oh + 4 * n4;
+    if (threadIdx.x < n_o - ot) dst[ot + threadIdx.x] = smem[OUT_SHIFT + ot + threadIdx.x];
   }
 
   // ---- remainder window: handled by the sample's last tile, one thread -----
@@ -356,11 +379,11 @@ static int launch_levy(cudaStream_t st, LevyParams p, int depth, size_t smem) {
   if (depth == 2) {
     auto k = logsig_levy_kernel<C, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, 128, smem, st>>>(p);
+    k<<<grid, p.WT, smem, st>>>(p);
   } else {
     auto k = logsig_levy_kernel<C, false>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, 128, smem, st>>>(p);
+    k<<<grid, p.WT, smem, st>>>(p);
   }
   return (int)cudaGetLastError();
 }
@@ -405,13 +428,17 @@ int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int 
     p.chunk = compat ? chunk : 1;
     p.stride = (int)(sC | 1);
     p.sc_magic = (uint32_t)((0x100000000ull + sC - 1) / sC);
-    int WT = 128;
+    static const int wt_env = getenv("LNCDE_LEVY_WT") ? atoi(getenv("LNCDE_LEVY_WT")) : 0;
+    // measured on B200 (scripts/k1_sweep.py): 32-window, single-warp CTAs give the best overlap of
+    // the load / walk / store phases across the ~21 CTAs resident per SM (63.8 % vs 59.7 % at 128)
+    int WT = wt_env > 0 ? wt_env : 32;
     while (WT > 32 && (size_t)(C + (size_t)WT * p.stride) * 4 > 80 * 1024) WT >>= 1;
+    if (WT > 128) WT = 128;
     p.WT = WT;
     p.tiles = (q + WT - 1) / WT;
     if (p.tiles < 1) p.tiles = 1;
     size_t smem = (size_t)(C + (size_t)WT * p.stride) * 4;
-    const size_t smem_out = (size_t)WT * D * 4;
+    const size_t smem_out = ((size_t)WT * D + 4) * 4;
     if (smem_out > smem) smem = smem_out;
     switch (C) {
       case 1: return launch_levy<1>(st, p, depth, smem);

@@ -71,13 +71,31 @@ class Adam:
         _lib.check(st, "lncde_adam_step")
 
 
+def shard_slice(global_batch: int, rank: int, world_size: int) -> slice:
+    """Contiguous batch shard of one rank (samples are independent through K1/K2/K3, so the
+    batch axis is the only axis that is split; parameters are replicated)."""
+    if global_batch % world_size:
+        raise ValueError("global batch must be divisible by the number of ranks")
+    per = global_batch // world_size
+    return slice(rank * per, (rank + 1) * per)
+
+
+def allreduce_sum_(flat_grads: torch.Tensor, world_size: int) -> torch.Tensor:
+    """The ONE collective of a data-parallel step: in-place sum of the flat gradient over ranks
+    (NCCL over NVLink on GPUs, gloo in the CPU tests).  The 1/world factor that turns the sum of
+    per-shard mean-loss gradients into the global-batch gradient is applied by the consumer
+    (Adam kernel ``grad_scale``)."""
+    if world_size > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)
+    return flat_grads
+
+
 def make_step(model, filter_spec, X, y, loss_fn, state, opt, opt_state, key, *, world_size=1):
     """train.py:130-136.  With world_size > 1 every rank holds a batch shard; the flat
     gradient is summed with ONE all-reduce and averaged inside the Adam kernel."""
     value, grads = loss_fn(model, X, y, state, key)
-    if world_size > 1:
-        import torch.distributed as dist
-
-        dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+    allreduce_sum_(grads, world_size)
     opt.update(model, grads, grad_scale=1.0 / world_size)
     return model, state, opt_state, value
