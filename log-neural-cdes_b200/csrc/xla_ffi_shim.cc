@@ -13,6 +13,8 @@
 #ifdef LNCDE_HAVE_XLA_FFI
 #include <cuda_runtime_api.h>
 
+#include <string>
+
 #include "lncde_b200.h"
 #include "xla/ffi/api/ffi.h"
 
