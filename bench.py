@@ -27,9 +27,45 @@ for _p in (REPO, os.path.join(REPO, "log-neural-cdes_b200")):
 import numpy as np
 import torch
 
-# EigenWorms Log-NCDE (experiment_configs/repeats/log_ncde/EigenWorms.json), time channel included
-WL = dict(name="EigenWorms", B=32, L=17984, C=7, stepsize=12, depth=2, H=128, vf_width=32, vf_depth=2,
-          dt0=0.00066711140760507, scale=1000.0, lambd=1e-3, lr=1e-3, label_dim=5)
+# Default = BASELINE.json configs[1]: EigenWorms Log-NCDE (experiment_configs/repeats/log_ncde/EigenWorms.json),
+# time channel included.  The other entries are the remaining BASELINE configs, selectable with --workload
+# (their numbers go to BASELINE.md; the driver only runs the default).
+WORKLOADS = {
+    "eigenworms_logncde": dict(name="EigenWorms", model="log_ncde", B=32, L=17984, C=7, stepsize=12, depth=2, H=128,
+                               vf_width=32, vf_depth=2, dt0=0.00066711140760507, scale=1000.0, lambd=1e-3, lr=1e-3,
+                               label_dim=5, classification=True,
+                               desc="EigenWorms Log-NCDE depth-2 logsig: B=32/GPU, L=17984, C=7 (6+time), stepsize 12, "
+                                    "H=128, vf 2x32, Heun dt0=1/1499 (1499 steps), CE+Lip2, Adam"),
+    "eigenworms_logncde_c6": dict(name="EigenWorms", model="log_ncde", B=32, L=17984, C=6, stepsize=12, depth=2, H=128,
+                                  vf_width=32, vf_depth=2, dt0=0.00066711140760507, scale=1000.0, lambd=1e-3, lr=1e-3,
+                                  label_dim=5, classification=True,
+                                  desc="EigenWorms Log-NCDE, 6 channels (no time channel), otherwise as the default"),
+    "toy_logncde": dict(name="toy", model="log_ncde", B=32, L=100, C=6, stepsize=4, depth=2, H=64, vf_width=128,
+                        vf_depth=3, dt0=0.01, scale=1.0, lambd=0.0, lr=3e-4, label_dim=2, classification=True,
+                        desc="toy Log-NCDE depth 2, stepsize 4: B=32, L=100, C=6, H=64, vf 3x128, dt0=0.01 (99 steps)"),
+    "ppg_logncde_d1": dict(name="ppg", model="log_ncde", B=32, L=49920, C=7, stepsize=10, depth=1, H=128, vf_width=64,
+                           vf_depth=3, dt0=0.0002002803925495694, scale=1000.0, lambd=0.0, lr=1e-3, label_dim=1,
+                           classification=False, output_step=128,
+                           desc="PPG-DaLiA Log-NCDE depth 1 (reference config): B=32, L=49920, C=7, stepsize 10, H=128, "
+                                "vf 3x64, 4994 steps, regression (390 outputs), MSE"),
+    "ppg_logncde_d2": dict(name="ppg", model="log_ncde", B=32, L=49920, C=7, stepsize=10, depth=2, H=128, vf_width=64,
+                           vf_depth=3, dt0=0.0002002803925495694, scale=1000.0, lambd=0.0, lr=1e-3, label_dim=1,
+                           classification=False, output_step=128,
+                           desc="PPG-DaLiA Log-NCDE depth 2 (BASELINE variant), otherwise as ppg_logncde_d1"),
+    "scp1_bd": dict(name="SelfRegulationSCP1", model="bd_linear_ncde", B=32, L=896, C=6, stepsize=16, depth=2, H=64,
+                    block_size=4, lambd=0.0, lr=1e-4, label_dim=2, classification=True,
+                    desc="SelfRegulationSCP1 BD-LNCDE: B=32, L=896, C=6, stepsize 16, depth 2, H=64, block 4"),
+    "eigenworms_bd": dict(name="EigenWorms", model="bd_linear_ncde", B=32, L=17984, C=7, stepsize=12, depth=2, H=128,
+                          block_size=4, lambd=1e-3, lr=1e-3, label_dim=5, classification=True,
+                          desc="EigenWorms BD-LNCDE: B=32, L=17984, C=7, stepsize 12, depth 2, H=128, block 4"),
+    "eigenworms_d": dict(name="EigenWorms", model="diagonal_linear_ncde", B=32, L=17984, C=7, stepsize=12, depth=1,
+                         H=128, block_size=1, lambd=1e-3, lr=1e-3, label_dim=5, classification=True,
+                         desc="EigenWorms D-LNCDE: depth 1, H=128, block 1"),
+    "eigenworms_de": dict(name="EigenWorms", model="dense_linear_ncde", B=32, L=17984, C=7, stepsize=12, depth=2,
+                          H=128, block_size=128, lambd=1e-3, lr=1e-3, label_dim=5, classification=True,
+                          desc="EigenWorms DE-LNCDE: depth 2, H=128, block 128 (dense)"),
+}
+WL = dict(WORKLOADS["eigenworms_logncde"])
 N_ROT = 16  # distinct input batches rotated through (16 x 16.1 MB = 258 MB > 126 MB L2)
 
 
@@ -115,9 +151,18 @@ def make_inputs(rank, n_rot):
     """Synthetic EigenWorms-shaped batches: ch 0 = t, ch 1..6 = random walk N(0, 0.05^2)."""
     from lncde.data_dir.datasets import synthetic_paths
 
-    x = synthetic_paths("EigenWorms", WL["B"] * n_rot, seed=2345 + rank).reshape(n_rot, WL["B"], WL["L"], WL["C"])
+    linear = WL["model"].endswith("linear_ncde")
+    x = synthetic_paths(WL["name"], WL["B"] * n_rot, seed=2345 + rank, scale_to_unit=linear)
+    if x.shape[2] != WL["C"]:  # e.g. EigenWorms without its time channel
+        x = np.ascontiguousarray(x[:, :, x.shape[2] - WL["C"]:])
+    x = x.reshape(n_rot, WL["B"], WL["L"], WL["C"])
     rng = np.random.default_rng(99 + rank)
-    lab = np.eye(WL["label_dim"], dtype=np.float32)[rng.integers(0, WL["label_dim"], size=(n_rot, WL["B"]))]
+    if WL["classification"]:
+        lab = np.eye(WL["label_dim"], dtype=np.float32)[rng.integers(0, WL["label_dim"], size=(n_rot, WL["B"]))]
+    else:
+        n_out = len(np.arange(np.float32(WL["output_step"] / WL["L"]), 1.0, np.float32(WL["output_step"] / WL["L"]),
+                              dtype=np.float32)) + 1
+        lab = rng.uniform(-1, 1, size=(n_rot, WL["B"], n_out)).astype(np.float32)
     return x, lab
 
 
@@ -153,23 +198,33 @@ def run_ours(args):
     ts0 = make_ts(L)
     iv = make_intervals(ts0, WL["stepsize"])
     ts = torch.from_numpy(ts0)[None, :].expand(B, -1)  # host tensor: only ts[0], ts[-1] are read (t0, t1)
-    model, _ = create_model("log_ncde", C, 29, WL["depth"], iv, WL["label_dim"], WL["H"], vf_depth=WL["vf_depth"],
-                            vf_width=WL["vf_width"], dt0=WL["dt0"], scale=WL["scale"], lambd=WL["lambd"], key=2345,
-                            device=dev)
+    from lncde.data_dir.generate_paths import logsig_dim
+
+    D = logsig_dim(C, WL["depth"])
+    model, _ = create_model(WL["model"], C, D, WL["depth"], iv, WL["label_dim"], WL["H"],
+                            block_size=WL.get("block_size"), vf_depth=WL.get("vf_depth"), vf_width=WL.get("vf_width"),
+                            classification=WL["classification"], output_step=WL.get("output_step", 1),
+                            dt0=WL.get("dt0", 1), scale=WL.get("scale", 1.0), lambd=WL["lambd"], parallel_steps=128,
+                            key=2345, device=dev)
+    loss_fn = T.classification_loss if WL["classification"] else T.regression_loss
     if world > 1:
         dist.broadcast(model.params.data, src=0)
     opt = T.Adam(model, WL["lr"])
     K = _lib.lib().lncde_logsig_num_windows(L, WL["stepsize"])
-    ls_buf = torch.empty((B, K, 29), device=dev)
+    ls_buf = torch.empty((B, K, D), device=dev)
     stage_buf = torch.empty((B, L, C), device=dev)
-    lab_buf = torch.empty((B, WL["label_dim"]), device=dev)
+    lab_buf = torch.empty(tuple(lab_dev.shape[1:]), device=dev)
 
     def step(raw, lab):
         ls = calc_paths(raw, WL["stepsize"], WL["depth"], out=ls_buf)
         X = (ts, ls, raw[:, 0, :])
-        _, _, _, value = T.make_step(model, None, X, lab, T.classification_loss, None, opt, None, None,
-                                     world_size=world)
+        _, _, _, value = T.make_step(model, None, X, lab, loss_fn, None, opt, None, None, world_size=world)
         return value
+
+    # workloads whose per-step working set is smaller than L2 get an explicit L2 flush between steps
+    flush = None
+    if N_ROT * B * L * C * 4 < 200e6 and args.workload != "eigenworms_logncde":
+        flush = torch.empty(64 * 1024 * 1024, device=dev)
 
     def sync():
         torch.cuda.synchronize()
@@ -187,13 +242,23 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     sampler.mark_start()
-    e0.record()
-    for i in range(args.steps):
-        step(x_dev[i % N_ROT], lab_dev[i % N_ROT])
-    e1.record()
-    sync()
+    if flush is None:
+        e0.record()
+        for i in range(args.steps):
+            step(x_dev[i % N_ROT], lab_dev[i % N_ROT])
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+    else:  # time each step on its own, flushing L2 in between (not timed)
+        ms = 0.0
+        for i in range(args.steps):
+            flush.zero_()
+            e0.record()
+            step(x_dev[i % N_ROT], lab_dev[i % N_ROT])
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
     sampler.mark_stop()
-    ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, every step --------------------
@@ -220,21 +285,24 @@ def run_ours(args):
     ms, e2e_ms = float(t[0]), float(t[1])
 
     out = None
+    in_mb = N_ROT * x_pin[0].numel() * 4 / 1e6
+    l2_note = (f"rotating {N_ROT} distinct input batches ({in_mb:.0f} MB)"
+               + (" and a 1.5 GB adjoint workspace streamed every step: working set > 126 MB L2"
+                  if args.workload == "eigenworms_logncde" else
+                  "; L2 additionally flushed by a 256 MB write between timed steps" if flush is not None else ""))
     if rank == 0:
         pk, pk_kind = peaks()
         out = {
-            "metric": "train samples/sec EigenWorms Log-NCDE",
+            "metric": "train samples/sec EigenWorms Log-NCDE" if args.workload == "eigenworms_logncde"
+            else f"train samples/sec {args.workload}",
             "value": world * B * args.steps / (ms * 1e-3),
             "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "EigenWorms Log-NCDE depth-2 logsig: B=32/GPU, L=17984, C=7 (6+time), stepsize 12, "
-                                   "H=128, vf 2x32, Heun dt0=1/1499 (1499 steps), CE+Lip2, Adam",
-                       "global_batch": world * B, "parallelism": f"dp{world}",
-                       "l2": f"rotating {N_ROT} distinct input batches (258 MB) and a 1.5 GB adjoint workspace "
-                             "streamed every step: working set > 126 MB L2"},
+            "config": {"workload": WL["desc"], "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": l2_note},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": int(x_pin[0].numel() * 4 + lab_pin[0].numel() * 4),
                     "d2h_bytes_per_step": 4, "last_loss": last_loss},
@@ -242,7 +310,8 @@ def run_ours(args):
             "gpu_launches": 8 * args.steps,
             "clocks": clocks,
         }
-        out.update(extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms / args.steps))
+        if args.workload == "eigenworms_logncde":
+            out.update(extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms / args.steps))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -397,7 +466,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--workload", default="eigenworms_logncde", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    WL.clear()
+    WL.update(WORKLOADS[args.workload])
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -194,6 +194,123 @@ __global__ void scan_bwd_kernel(float* __restrict__ F, const float* __restrict__
   for (int h = threadIdx.x; h < H; h += blockDim.x) g_y0[(size_t)b * H + h] = sh[cur * H + h];
 }
 
+
+// ---------------------------------------------------------------- 2b/3b. warp-shuffle scans
+// Block sizes that divide 32: the bs threads of one block sit in one warp, the state lives in
+// registers and is exchanged with shuffles - no shared memory, no barriers; flows are
+// prefetched PF steps ahead so the dependent chain per step is bs x (SHFL + FMA).
+template <int BS, int PF>
+__global__ void __launch_bounds__(256) scan_fwd_warp_kernel(const float* __restrict__ F, const float* __restrict__ y0,
+                                                            float* __restrict__ ys, int B, int T, int H) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = gid < (long long)B * H;
+  const int b = live ? (int)(gid / H) : 0, h = live ? (int)(gid - (long long)b * H) : 0;
+  const int lane = threadIdx.x & 31, base = lane & ~(BS - 1);
+  const float* Fb = F + ((size_t)b * T) * H * BS + (size_t)h * BS;  // row h of step 0
+  float* yb = ys + (size_t)b * T * H + h;
+  float y = live ? y0[(size_t)b * H + h] : 0.f;
+  if (live) yb[0] = y;
+  float row[PF][BS];
+  const size_t step = (size_t)H * BS;
+#pragma unroll
+  for (int u = 0; u < PF; ++u)
+#pragma unroll
+    for (int j = 0; j < BS; ++j) row[u][j] = (live && 1 + u < T) ? __ldg(Fb + (size_t)(1 + u) * step + j) : 0.f;
+  for (int t0 = 1; t0 < T; t0 += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int t = t0 + u;
+      if (t < T) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < BS; ++j) acc = fmaf(row[u][j], __shfl_sync(0xffffffffu, y, base + j), acc);
+        y = acc;
+        if (live) yb[(size_t)t * H] = y;
+        // refill this slot with the flow PF steps ahead
+        const int tn = t + PF;
+#pragma unroll
+        for (int j = 0; j < BS; ++j) row[u][j] = (live && tn < T) ? __ldg(Fb + (size_t)tn * step + j) : 0.f;
+      }
+    }
+  }
+}
+
+// thread (b, h = blk*BS + j) owns COLUMN j of its block:
+// lam_{t-1}[j] = g_{t-1}[j] + sum_i F_t[i][j] lam_t[i];  dF_t[i][j] = lam_t[i] * y_{t-1}[j]
+template <int BS, int PF>
+__global__ void __launch_bounds__(256) scan_bwd_warp_kernel(float* __restrict__ F, const float* __restrict__ ys,
+                                                            const float* __restrict__ g_ys, float* __restrict__ g_y0,
+                                                            int B, int T, int H) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = gid < (long long)B * H;
+  const int b = live ? (int)(gid / H) : 0, h = live ? (int)(gid - (long long)b * H) : 0;
+  const int lane = threadIdx.x & 31, base = lane & ~(BS - 1), j = lane & (BS - 1);
+  const size_t step = (size_t)H * BS;
+  float* Fb = F + ((size_t)b * T) * H * BS + (size_t)(h - j) * BS + j;  // F[blk][0][j] of step 0
+  const float* yb = ys + (size_t)b * T * H + h;
+  const float* gb = g_ys + (size_t)b * T * H + h;
+  float lam = live ? gb[(size_t)(T - 1) * H] : 0.f;
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < BS; ++i) Fb[i * BS] = 0.f;  // flow 0 is never applied
+  }
+  float col[PF][BS], yp[PF], gp[PF];
+#pragma unroll
+  for (int u = 0; u < PF; ++u) {
+    const int t = T - 1 - u;
+#pragma unroll
+    for (int i = 0; i < BS; ++i) col[u][i] = (live && t >= 1) ? Fb[(size_t)t * step + i * BS] : 0.f;
+    yp[u] = (live && t >= 1) ? yb[(size_t)(t - 1) * H] : 0.f;
+    gp[u] = (live && t >= 1) ? gb[(size_t)(t - 1) * H] : 0.f;
+  }
+  for (int t0 = T - 1; t0 >= 1; t0 -= PF) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int t = t0 - u;
+      if (t >= 1) {
+        float acc = gp[u];
+        float* Ft = Fb + (size_t)t * step;
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+          const float li = __shfl_sync(0xffffffffu, lam, base + i);
+          acc = fmaf(col[u][i], li, acc);
+          if (live) Ft[i * BS] = li * yp[u];
+        }
+        lam = acc;
+        const int tn = t - PF;
+#pragma unroll
+        for (int i = 0; i < BS; ++i) col[u][i] = (live && tn >= 1) ? Fb[(size_t)tn * step + i * BS] : 0.f;
+        yp[u] = (live && tn >= 1) ? yb[(size_t)(tn - 1) * H] : 0.f;
+        gp[u] = (live && tn >= 1) ? gb[(size_t)(tn - 1) * H] : 0.f;
+      }
+    }
+  }
+  if (live) g_y0[(size_t)b * H + h] = lam;
+}
+
+template <int BS, int PF>
+static void launch_scan_warp(bool bwd, cudaStream_t cs, float* F, const float* y0, float* ys, const float* g_ys,
+                             float* g_y0, int B, int T, int H) {
+  const long long n = (long long)B * H;
+  const int threads = 256, grid = (int)((n + threads - 1) / threads);
+  if (!bwd)
+    scan_fwd_warp_kernel<BS, PF><<<grid, threads, 0, cs>>>(F, y0, ys, B, T, H);
+  else
+    scan_bwd_warp_kernel<BS, PF><<<grid, threads, 0, cs>>>(F, ys, g_ys, g_y0, B, T, H);
+}
+static bool scan_warp_dispatch(bool bwd, cudaStream_t cs, float* F, const float* y0, float* ys, const float* g_ys,
+                               float* g_y0, int B, int T, int H, int bs) {
+  switch (bs) {
+    case 1: launch_scan_warp<1, 8>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H); return true;
+    case 2: launch_scan_warp<2, 8>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H); return true;
+    case 4: launch_scan_warp<4, 6>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H); return true;
+    case 8: launch_scan_warp<8, 4>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H); return true;
+    case 16: launch_scan_warp<16, 2>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H); return true;
+    case 32: launch_scan_warp<32, 2>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H); return true;
+  }
+  return false;
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int ksplit) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -256,7 +373,8 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   st = (int)cudaGetLastError();
   if (st != 0) return st;
   // 2. scan
-  if (bs <= 16) {
+  if (scan_warp_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
+  } else if (bs <= 16) {
     int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));
     scan_fwd_small_kernel<<<B, threads, 2 * H * sizeof(float), cs>>>(F, y0, ys, T, H, bs);
   } else {
@@ -279,8 +397,10 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
   cudaStream_t cs = (cudaStream_t)stream;
   float* F = (float*)workspace;  // still holds the forward flows of the SAME (lie, logsig)
   const int H = nb * bs, N = H * bs;
-  int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));
-  scan_bwd_kernel<<<B, threads, 3 * H * sizeof(float), cs>>>(F, ys, g_ys, g_y0, T, H, bs);
+  if (!scan_warp_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs)) {
+    int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));
+    scan_bwd_kernel<<<B, threads, 3 * H * sizeof(float), cs>>>(F, ys, g_ys, g_y0, T, H, bs);
+  }
   st = (int)cudaGetLastError();
   if (st != 0) return st;
   // dLie[n][l] = sum_m dF[m][n] * logsig[m][1+l]

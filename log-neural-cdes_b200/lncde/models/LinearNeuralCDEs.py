@@ -76,6 +76,7 @@ class LogLinearCDE:
         hs = HallSet(self.data_dim, self.logsig_depth)
         self.basis_list = hs.basis_list()  # what roughpy's lie_basis enumerates (:111-116)
         self._basis_pairs = hs.data
+        self._levels = None
         C, H, bs, nb = self.data_dim, self.hidden_dim, self.block_size, self.num_blocks
         n_A = C * nb * bs * bs
         n_tot = n_A + H * (C + 1) + self.label_dim * (H + 1)
@@ -100,12 +101,27 @@ class LogLinearCDE:
         return [self.params]
 
     def log_ode(self, vfs):
-        """vfs [C, nb, bs, bs] -> bracket matrices [nb, bs, bs, n_basis] (:192-232), batched over blocks."""
-        A = [None] * len(self._basis_pairs)
-        for k in range(1, len(self._basis_pairs)):
-            l, r = self._basis_pairs[k]
-            A[k] = vfs[r - 1] if l == 0 else torch.matmul(A[r], A[l]) - torch.matmul(A[l], A[r])
-        return torch.stack(A[1:], dim=-1)
+        """vfs [C, nb, bs, bs] -> bracket matrices [nb, bs, bs, n_basis] (:192-232), batched over blocks.
+        Level by level, every bracket of a level in ONE batched matmul pair:
+        A_[u,v] = A_v A_u - A_u A_v  (:225-227)."""
+        if self._levels is None:
+            n = len(self._basis_pairs)
+            deg = [0] * n
+            for k in range(1, n):
+                l, r = self._basis_pairs[k]
+                deg[k] = 1 if l == 0 else deg[l] + deg[r]
+            levels = []
+            for d in range(2, max(deg[1:]) + 1):
+                ks = [k for k in range(1, n) if deg[k] == d]
+                li = torch.tensor([self._basis_pairs[k][0] - 1 for k in ks], device=self.device)
+                ri = torch.tensor([self._basis_pairs[k][1] - 1 for k in ks], device=self.device)
+                levels.append((li, ri))
+            self._levels = levels
+        A = vfs  # index k-1 <-> basis element k; the first C entries are the letters in order
+        for li, ri in self._levels:
+            Al, Ar = A.index_select(0, li), A.index_select(0, ri)
+            A = torch.cat([A, torch.matmul(Ar, Al) - torch.matmul(Al, Ar)], dim=0)
+        return A.permute(1, 2, 3, 0)
 
     def hidden_states(self, X):
         ts, logsigs, x0 = X
