@@ -35,7 +35,8 @@ extern "C" {
 #define LNCDE_ERR_ALIGN (-5)       /* pointer not 16-byte aligned              */
 
 /* flags */
-#define LNCDE_FLAG_COMPAT 1u /* reproduce reference quirks */
+#define LNCDE_FLAG_COMPAT 1u    /* reproduce reference quirks */
+#define LNCDE_FLAG_SAVED_FWD 2u /* lncde_logncde_bwd: workspace was filled by lncde_logncde_fwd */
 
 const char* lncde_version(void);
 /* Human-readable text for a status returned by any entry point. */
@@ -97,9 +98,13 @@ int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int 
  * depth in {1, 2}.                                                          */
 int lncde_logncde_param_count(int H, int C, int width, int n_hidden);
 size_t lncde_logncde_fwd_smem_bytes(int H, int C, int width, int n_hidden);
+/* workspace: NULL for inference.  In training pass lncde_logncde_bwd_workspace_bytes(...) bytes;
+ * the forward may keep per-stage intermediates there so that the adjoint sweep need not
+ * recompute them (then call lncde_logncde_bwd with the same buffer and LNCDE_FLAG_SAVED_FWD). */
 int lncde_logncde_fwd(void* stream, const float* params, const float* logsig, const float* y0,
                       const int32_t* stage_row, const float* stage_scale, float* ys, int B, int K,
-                      int D, int H, int C, int width, int n_hidden, int depth, int n_steps);
+                      int D, int H, int C, int width, int n_hidden, int depth, int n_steps,
+                      void* workspace, size_t workspace_bytes);
 
 /* Backward sweep (discretise-then-optimise, what diffrax's default adjoint
  * returns).  g_ys [B, n_steps+1, H] is dLoss/d ys (zero where unused).
@@ -111,7 +116,7 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig,
                       const int32_t* stage_row, const float* stage_scale, const float* ys,
                       const float* g_ys, float* g_params, float* g_y0, int B, int K, int D, int H,
                       int C, int width, int n_hidden, int depth, int n_steps, void* workspace,
-                      size_t workspace_bytes);
+                      size_t workspace_bytes, unsigned flags);
 
 /* ------------------------------------------------------------------ K2 ---
  * Structured linear CDE (D / BD / DE-LNCDE): flows F_k = I + sum_l logsig[k,l] A_l
@@ -141,6 +146,11 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
  * grad_scale multiplies the gradient first (1/world after an all-reduce sum). */
 int lncde_adam_step(void* stream, float* params, const float* grads, float* m, float* v, int64_t n,
                     float lr, float beta1, float beta2, float eps, int step, float grad_scale);
+
+/* Same update with the step count held in device memory (*step_counter = steps done so far, incremented
+ * by the call): a launch captured in a CUDA graph stays valid across replays.                          */
+int lncde_adam_step_dev(void* stream, float* params, const float* grads, float* m, float* v, int64_t n,
+                        float lr, float beta1, float beta2, float eps, int* step_counter, float grad_scale);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,49 @@ int make_mlp_desc(MlpDesc* d, int H, int C, int width, int n_hidden, int depth, 
   return LNCDE_OK;
 }
 
+// ------------------------------------------------------------------ workspace
+struct WsLayout {  // float offsets into the workspace; arrays are [Ktot][dim]
+  size_t Y, Wt, A[kMaxLayers], P[kMaxLayers];
+  size_t ZL, UL, Z[kMaxLayers], U[kMaxLayers];
+  size_t ZS, US, U3;  // forward intermediates saved in training mode: [z|s] per hidden layer, u per layer, last-layer u
+  size_t bias_part;  // [B][n_bias]
+  size_t gemm_part;  // split-K partials
+  size_t total;
+};
+
+static WsLayout make_ws_layout(const MlpDesc& d, int B, int n_steps, int ksplit) {
+  WsLayout w;
+  const size_t Kt = (size_t)B * 2 * n_steps;
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    size_t o = off;
+    off += (n + 3) & ~(size_t)3;
+    return o;
+  };
+  const bool tan = d.depth == 2;
+  w.Y = take(Kt * d.H);
+  w.Wt = take(Kt * d.C * d.H);  // depth 1 too: the saved-forward adjoint reads the field outputs from here
+  for (int l = 0; l < d.n_hidden; ++l) {
+    w.A[l] = take(Kt * d.width);
+    w.P[l] = tan ? take(Kt * d.C * d.width) : 0;
+    w.Z[l] = take(Kt * d.width);
+    w.U[l] = tan ? take(Kt * d.C * d.width) : 0;
+  }
+  w.ZL = take(Kt * d.C * d.H);
+  w.UL = tan ? take(Kt * d.C * d.H) : 0;
+  w.ZS = take(Kt * 2 * d.n_hidden * d.width);
+  w.US = tan ? take(Kt * d.n_hidden * d.C * d.width) : 0;
+  w.U3 = tan ? take(Kt * d.C * d.H) : 0;
+  int n_bias = 0;
+  for (int l = 0; l < d.n_layers; ++l) n_bias += d.rows[l];
+  w.bias_part = take((size_t)B * n_bias);
+  size_t n_w = 0;
+  for (int l = 0; l < d.n_layers; ++l) n_w += (size_t)d.rows[l] * d.in_dim[l];
+  w.gemm_part = take(n_w * kKsplitSmall);
+  w.total = off;
+  return w;
+}
+
 // ------------------------------------------------------------------ forward
 struct FwdParams {
   MlpDesc d;
@@ -81,6 +124,9 @@ struct FwdParams {
   const float* stage_scale;
   float* ys;
   int B, K, D, n_steps;
+  WsLayout ws;  // used when save != 0 (training-mode forward of the specialised kernels)
+  float* wsp;
+  int save;
 };
 
 template <int C>
@@ -148,44 +194,6 @@ static size_t fwd_other_bytes(int H, int C, int width, int n_hidden) {
 }
 
 // ------------------------------------------------------------------ backward sweep
-struct WsLayout {  // float offsets into the workspace; arrays are [Ktot][dim]
-  size_t Y, Wt, A[kMaxLayers], P[kMaxLayers];
-  size_t ZL, UL, Z[kMaxLayers], U[kMaxLayers];
-  size_t bias_part;  // [B][n_bias]
-  size_t gemm_part;  // split-K partials
-  size_t total;
-};
-
-static WsLayout make_ws_layout(const MlpDesc& d, int B, int n_steps, int ksplit) {
-  WsLayout w;
-  const size_t Kt = (size_t)B * 2 * n_steps;
-  size_t off = 0;
-  auto take = [&](size_t n) {
-    size_t o = off;
-    off += (n + 3) & ~(size_t)3;
-    return o;
-  };
-  const bool tan = d.depth == 2;
-  w.Y = take(Kt * d.H);
-  w.Wt = tan ? take(Kt * d.C * d.H) : 0;
-  for (int l = 0; l < d.n_hidden; ++l) {
-    w.A[l] = take(Kt * d.width);
-    w.P[l] = tan ? take(Kt * d.C * d.width) : 0;
-    w.Z[l] = take(Kt * d.width);
-    w.U[l] = tan ? take(Kt * d.C * d.width) : 0;
-  }
-  w.ZL = take(Kt * d.C * d.H);
-  w.UL = tan ? take(Kt * d.C * d.H) : 0;
-  int n_bias = 0;
-  for (int l = 0; l < d.n_layers; ++l) n_bias += d.rows[l];
-  w.bias_part = take((size_t)B * n_bias);
-  size_t n_w = 0;
-  for (int l = 0; l < d.n_layers; ++l) n_w += (size_t)d.rows[l] * d.in_dim[l];
-  w.gemm_part = take(n_w * kKsplitSmall);
-  w.total = off;
-  return w;
-}
-
 struct BwdParams {
   MlpDesc d;
   WsLayout ws;
@@ -198,6 +206,7 @@ struct BwdParams {
   float* g_y0;
   float* wsp;
   int B, K, D, n_steps;
+  int saved;  // workspace already holds the forward intermediates (written by the forward kernel)
 };
 
 }  // namespace lncde
@@ -489,7 +498,8 @@ size_t lncde_logncde_fwd_smem_bytes(int H, int C, int width, int n_hidden) {
 
 int lncde_logncde_fwd(void* stream, const float* params, const float* logsig, const float* y0,
                       const int32_t* stage_row, const float* stage_scale, float* ys, int B, int K, int D,
-                      int H, int C, int width, int n_hidden, int depth, int n_steps) {
+                      int H, int C, int width, int n_hidden, int depth, int n_steps, void* workspace,
+                      size_t workspace_bytes) {
   using namespace lncde;
   if (!params || !logsig || !y0 || !stage_row || !stage_scale || !ys) return LNCDE_ERR_NULL;
   if (B < 1 || K < 1 || n_steps < 1) return LNCDE_ERR_SHAPE;
@@ -502,8 +512,16 @@ int lncde_logncde_fwd(void* stream, const float* params, const float* logsig, co
   if (smem > 227 * 1024) return LNCDE_ERR_UNSUPPORTED;
   p.params = params; p.logsig = logsig; p.y0 = y0; p.stage_row = stage_row; p.stage_scale = stage_scale;
   p.ys = ys; p.B = B; p.K = K; p.D = D; p.n_steps = n_steps;
+  p.wsp = nullptr; p.save = 0;
   cudaStream_t cs = (cudaStream_t)stream;
   if (use_fast(H, C, width, n_hidden)) {
+    if (workspace) {  // training mode: keep the per-stage intermediates for the adjoint sweep
+      if (((uintptr_t)workspace & 15) != 0) return LNCDE_ERR_ALIGN;
+      p.ws = make_ws_layout(p.d, B, n_steps, kKsplit);
+      if (workspace_bytes < p.ws.total * 4) return LNCDE_ERR_WORKSPACE;
+      p.wsp = (float*)workspace;
+      p.save = 1;
+    }
     switch (C) {
       case 4: return fast::launch_fwd_fast<4>(cs, p);
       case 6: return fast::launch_fwd_fast<6>(cs, p);
@@ -533,7 +551,7 @@ size_t lncde_logncde_bwd_workspace_bytes(int B, int H, int C, int width, int n_h
 int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, const int32_t* stage_row,
                       const float* stage_scale, const float* ys, const float* g_ys, float* g_params,
                       float* g_y0, int B, int K, int D, int H, int C, int width, int n_hidden, int depth,
-                      int n_steps, void* workspace, size_t workspace_bytes) {
+                      int n_steps, void* workspace, size_t workspace_bytes, unsigned flags) {
   using namespace lncde;
   if (!params || !logsig || !stage_row || !stage_scale || !ys || !g_ys || !g_params || !g_y0 || !workspace)
     return LNCDE_ERR_NULL;
@@ -552,6 +570,7 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
   p.params = params; p.logsig = logsig; p.stage_row = stage_row; p.stage_scale = stage_scale;
   p.ys = ys; p.g_ys = g_ys; p.g_y0 = g_y0; p.wsp = (float*)workspace;
   p.B = B; p.K = K; p.D = D; p.n_steps = n_steps;
+  p.saved = (flags & LNCDE_FLAG_SAVED_FWD) ? 1 : 0;
   cudaStream_t cs = (cudaStream_t)stream;
   if (use_fast(H, C, width, n_hidden)) {
     switch (C) {

@@ -321,7 +321,41 @@ __device__ __forceinline__ void stage_weights_bwd(const MlpDesc& d, const float*
 }
 
 // ------------------------------------------------------------------------------ forward
+// Training-mode forward: keep what the adjoint sweep needs of one stage in the workspace slot
+// (the right-hand vectors of the weight-gradient pairs in their final place, plus z/s of the
+// hidden layers and the tangent pre-activations).  Must run before sb[yin] is overwritten.
 template <int C, bool D2>
+__device__ __forceinline__ void save_stage(const float* sb, const float (&u3_r)[2], const WsLayout& ws,
+                                           float* __restrict__ wsp, size_t slot) {
+  using S = Smem<C>;
+  constexpr int CH = C * H, CW = C * W;
+  const int tid = threadIdx.x;
+  if (tid < H) {
+    wsp[ws.Y + slot * H + tid] = sb[S::yin + tid];
+    const int l = tid >> 5, c = tid & 31;  // ZS = [z1 | s1 | z2 | s2]
+    const int src = (l == 0) ? S::z1 : (l == 1) ? S::s1 : (l == 2) ? S::z2 : S::s2;
+    wsp[ws.ZS + slot * 4 * W + tid] = sb[src + c];
+  }
+  if (tid < W) {
+    wsp[ws.A[0] + slot * W + tid] = sb[S::a1 + tid];
+    wsp[ws.A[1] + slot * W + tid] = sb[S::a2 + tid];
+  }
+  if (D2) {
+    for (int t = tid; t < CH; t += NT) wsp[ws.Wt + slot * CH + t] = sb[S::o + t];
+    if (tid < CW) {
+      wsp[ws.P[0] + slot * CW + tid] = sb[S::p1 + tid];
+      wsp[ws.P[1] + slot * CW + tid] = sb[S::p2 + tid];
+      wsp[ws.US + slot * 2 * CW + tid] = sb[S::u1 + tid];
+      wsp[ws.US + slot * 2 * CW + CW + tid] = sb[S::u2 + tid];
+    }
+    if (tid < C * 64)
+      *reinterpret_cast<float2*>(wsp + ws.U3 + slot * CH + lane_row0(tid)) = make_float2(u3_r[0], u3_r[1]);
+  } else {
+    for (int t = tid; t < CH; t += NT) wsp[ws.Wt + slot * CH + t] = sb[S::o + t];
+  }
+}
+
+template <int C, bool D2, bool SAVE>
 __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams p) {
   using S = Smem<C>;
   extern __shared__ __align__(16) float smem[];
@@ -351,6 +385,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
     const float s1n = p.stage_scale[2 * nn], s2n = p.stage_scale[2 * nn + 1];
     const float lam_b = lambda_fetch<C>(ls + (size_t)r2 * p.D, D2);
     stage_forward<C, D2>(sb, cm, R, lam_a, o_r, u3_r);
+    if (SAVE) save_stage<C, D2>(sb, u3_r, p.ws, p.wsp, ((size_t)b * p.n_steps + n) * 2);
     if (tid < H) {
       const float kk = s1 * field_value<C, D2>(sb, cm, tid);
       cm[S::k1 + tid] = kk;
@@ -359,6 +394,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
     __syncthreads();
     lam_a = lambda_fetch<C>(ls + (size_t)r1n * p.D, D2);
     stage_forward<C, D2>(sb, cm, R, lam_b, o_r, u3_r);
+    if (SAVE) save_stage<C, D2>(sb, u3_r, p.ws, p.wsp, ((size_t)b * p.n_steps + n) * 2 + 1);
     if (tid < H) {
       const float yn = cm[S::ycur + tid] + 0.5f * (cm[S::k1 + tid] + s2 * field_value<C, D2>(sb, cm, tid));
       cm[S::ycur + tid] = yn;
@@ -374,7 +410,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
 // Reverse sweep of one stage.  cm[g] holds dLoss/dG times the stage scale.  On exit (after the
 // trailing barrier) cm[part + ks*128 + h], ks < 4, hold the K-slice partials of
 // dLoss/d(stage input); the caller sums them.
-template <int C, bool D2>
+template <int C, bool D2, bool RIGHTS>
 __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, float* sb, float* cm, const Regs& R,
                                               const float (&o_r)[2], const float (&u3_r)[2], float (&b3acc)[2],
                                               const WsLayout& ws, float* __restrict__ wsp, size_t slot) {
@@ -383,13 +419,13 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = lane_row0(tid);
   float* part = cm + S::part;
-  // right-hand vectors of the weight-gradient outer products
-  if (tid < H) wsp[ws.Y + slot * H + tid] = sb[S::yin + tid];
-  if (tid < W) {
+  // right-hand vectors of the weight-gradient outer products (already in place when the forward saved them)
+  if (RIGHTS && tid < H) wsp[ws.Y + slot * H + tid] = sb[S::yin + tid];
+  if (RIGHTS && tid < W) {
     wsp[ws.A[0] + slot * W + tid] = sb[S::a1 + tid];
     wsp[ws.A[1] + slot * W + tid] = sb[S::a2 + tid];
   }
-  if (D2) {
+  if (RIGHTS && D2) {
     for (int t = tid; t < CH; t += NT) wsp[ws.Wt + slot * CH + t] = sb[S::o + t];  // pairs with v_i (see header)
     if (tid < CW) {
       wsp[ws.P[0] + slot * CW + tid] = sb[S::p1 + tid];
@@ -610,7 +646,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
     stage_forward<C, D2>(sbB, cm, R, lam_b, oB, uB);  // leaves Lambda of row r2
     if (tid < H) cm[S::g + tid] = 0.5f * s2 * cm[S::ybar + tid];
     __syncthreads();
-    stage_reverse<C, D2>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1);
+    stage_reverse<C, D2, true>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1);
     if (tid < H) {
       const float a = yout_value<C>(cm, tid);
       cm[S::ab + tid] = a;
@@ -620,7 +656,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
     const float lam_an = lambda_fetch<C>(ls + (size_t)r1n * p.D, D2);
     const float lam_bn = lambda_fetch<C>(ls + (size_t)r2n * p.D, D2);
     __syncthreads();
-    stage_reverse<C, D2>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot);
+    stage_reverse<C, D2, true>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot);
     if (tid < H) cm[S::ybar + tid] += cm[S::ab + tid] + yout_value<C>(cm, tid) + g_n;
     __syncthreads();
     s1 = s1n; s2 = s2n;
@@ -632,6 +668,112 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
   if (tid < 2 * W) bp[tid] = cm[S::bacc + tid];
   if (tid < C * 64) {
     const int row0 = lane_row0(tid);
+    bp[2 * W + row0] = b3acc[0];
+    bp[2 * W + row0 + 1] = b3acc[1];
+  }
+}
+
+
+// Adjoint sweep over SAVED forward intermediates (training-mode forward ran with a workspace):
+// no recomputation - one reverse stage per Heun stage, walking the slots backwards.  The z/s/u
+// vectors of the next slot are staged with cp.async into the other half of a double buffer and
+// the per-lane o / u3 values are prefetched into registers while the current stage runs.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int C, bool D2>
+__device__ __forceinline__ void fetch_saved(float* sb, const WsLayout& ws, const float* __restrict__ wsp,
+                                            size_t slot) {
+  using S = Smem<C>;
+  constexpr int CW = C * W;
+  const int tid = threadIdx.x;
+  if (tid < H) {
+    const int l = tid >> 5, c = tid & 31;
+    const int dst = (l == 0) ? S::z1 : (l == 1) ? S::s1 : (l == 2) ? S::z2 : S::s2;
+    cp_async4(sb + dst + c, wsp + ws.ZS + slot * 4 * W + tid);
+  }
+  if (D2 && tid < CW) {
+    cp_async4(sb + S::u1 + tid, wsp + ws.US + slot * 2 * CW + tid);
+    cp_async4(sb + S::u2 + tid, wsp + ws.US + slot * 2 * CW + CW + tid);
+  }
+  cp_async_commit();
+}
+
+template <int C, bool D2>
+__global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParams p) {
+  using S = Smem<C>;
+  constexpr int CH = C * H;
+  extern __shared__ __align__(16) float smem[];
+  float* sw = smem;
+  float* sbuf[2] = {smem + S::WEND_BWD, smem + S::WEND_BWD + S::STAGE};
+  float* cm = sbuf[1] + S::STAGE;
+  const int tid = threadIdx.x;
+  Regs R;
+  load_regs<C>(R, p.params, p.d);
+  stage_weights_bwd<C>(p.d, p.params, sw);
+  const int b = blockIdx.x;
+  const float* ls = p.logsig + (size_t)b * p.K * p.D;
+  const float* gys = p.g_ys + (size_t)b * (p.n_steps + 1) * H;
+  const float* wsp = p.wsp;
+  if (tid < 2 * W) cm[S::bacc + tid] = 0.f;
+  if (tid < H) cm[S::ybar + tid] = gys[(size_t)p.n_steps * H + tid];
+  float b3acc[2] = {0.f, 0.f};
+  const int n_stage = 2 * p.n_steps;
+  const size_t slot0 = (size_t)b * n_stage;
+  const int row0 = lane_row0(tid);
+  const bool rowt = tid < C * 64;
+  // prologue: everything of the last stage
+  int sidx = n_stage - 1;
+  float lam_c = lambda_fetch<C>(ls + (size_t)p.stage_row[sidx] * p.D, D2);
+  float sc_c = p.stage_scale[sidx];
+  float2 o_c = make_float2(0.f, 0.f), u_c = o_c;
+  if (rowt) {
+    o_c = *reinterpret_cast<const float2*>(wsp + p.ws.Wt + (slot0 + sidx) * CH + row0);
+    if (D2) u_c = *reinterpret_cast<const float2*>(wsp + p.ws.U3 + (slot0 + sidx) * CH + row0);
+  }
+  float g_c = tid < H ? gys[(size_t)(p.n_steps - 1) * H + tid] : 0.f;  // cotangent of y_n, n = sidx / 2
+  fetch_saved<C, D2>(sbuf[sidx & 1], p.ws, wsp, slot0 + sidx);
+  cp_async_wait_all();
+  __syncthreads();
+  for (; sidx >= 0; --sidx) {
+    const int nx = sidx > 0 ? sidx - 1 : 0;
+    // prefetch the next (earlier) stage
+    const float lam_n = lambda_fetch<C>(ls + (size_t)p.stage_row[nx] * p.D, D2);
+    const float sc_n = p.stage_scale[nx];
+    float2 o_n = make_float2(0.f, 0.f), u_n = o_n;
+    if (rowt) {
+      o_n = *reinterpret_cast<const float2*>(wsp + p.ws.Wt + (slot0 + nx) * CH + row0);
+      if (D2) u_n = *reinterpret_cast<const float2*>(wsp + p.ws.U3 + (slot0 + nx) * CH + row0);
+    }
+    const float g_n = tid < H ? gys[(size_t)(nx >> 1) * H + tid] : 0.f;
+    fetch_saved<C, D2>(sbuf[nx & 1], p.ws, wsp, slot0 + nx);
+    // cotangent of this stage's field value
+    const bool second = sidx & 1;  // stage 2 of its Heun step
+    if (tid < H)
+      cm[S::g + tid] = second ? 0.5f * sc_c * cm[S::ybar + tid] : sc_c * (0.5f * cm[S::ybar + tid] + cm[S::ab + tid]);
+    lambda_store<C>(cm, lam_c);
+    __syncthreads();
+    const float oc[2] = {o_c.x, o_c.y}, uc[2] = {u_c.x, u_c.y};
+    stage_reverse<C, D2, false>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx);
+    if (tid < H) {
+      const float yo = yout_value<C>(cm, tid);
+      if (second) cm[S::ab + tid] = yo;
+      else cm[S::ybar + tid] += cm[S::ab + tid] + yo + g_c;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    lam_c = lam_n; sc_c = sc_n; o_c = o_n; u_c = u_n;
+    if (!second) g_c = g_n;  // g_n was fetched for step (nx >> 1); it changes only when the step changes
+  }
+  if (tid < H) p.g_y0[(size_t)b * H + tid] = cm[S::ybar + tid];
+  const int n_bias = 2 * W + C * H;
+  float* bp = p.wsp + p.ws.bias_part + (size_t)b * n_bias;
+  if (tid < 2 * W) bp[tid] = cm[S::bacc + tid];
+  if (rowt) {
     bp[2 * W + row0] = b3acc[0];
     bp[2 * W + row0 + 1] = b3acc[1];
   }
@@ -649,28 +791,32 @@ constexpr size_t bwd_smem_bytes() {
 template <int C>
 static int launch_fwd_fast(cudaStream_t st, const FwdParams& p) {
   const size_t smem = fwd_smem_bytes<C>();
+  auto go = [&](auto k) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<p.B, NT, smem, st>>>(p);
+  };
   if (p.d.depth == 2) {
-    auto k = logncde_fwd_fast_kernel<C, true>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<p.B, NT, smem, st>>>(p);
+    if (p.save) go(logncde_fwd_fast_kernel<C, true, true>);
+    else go(logncde_fwd_fast_kernel<C, true, false>);
   } else {
-    auto k = logncde_fwd_fast_kernel<C, false>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<p.B, NT, smem, st>>>(p);
+    if (p.save) go(logncde_fwd_fast_kernel<C, false, true>);
+    else go(logncde_fwd_fast_kernel<C, false, false>);
   }
   return (int)cudaGetLastError();
 }
 template <int C>
 static int launch_bwd_fast(cudaStream_t st, const BwdParams& p) {
   const size_t smem = bwd_smem_bytes<C>();
+  auto go = [&](auto k) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<p.B, NT, smem, st>>>(p);
+  };
   if (p.d.depth == 2) {
-    auto k = logncde_bwd_fast_kernel<C, true>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<p.B, NT, smem, st>>>(p);
+    if (p.saved) go(logncde_bwd_saved_kernel<C, true>);
+    else go(logncde_bwd_fast_kernel<C, true>);
   } else {
-    auto k = logncde_bwd_fast_kernel<C, false>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<p.B, NT, smem, st>>>(p);
+    if (p.saved) go(logncde_bwd_saved_kernel<C, false>);
+    else go(logncde_bwd_fast_kernel<C, false>);
   }
   return (int)cudaGetLastError();
 }

@@ -60,7 +60,7 @@ static ffi::Error SolveFwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params
   return status_to_error(
       lncde_logncde_fwd(stream, params.typed_data(), logsig.typed_data(), y0.typed_data(), rows.typed_data(),
                         scale.typed_data(), ys->typed_data(), (int)l[0], (int)l[1], (int)l[2], (int)y[1], C, width,
-                        n_hidden, depth, n_steps),
+                        n_hidden, depth, n_steps, nullptr, 0),
       "lncde_logncde_fwd");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_logncde_fwd, SolveFwdImpl,
@@ -89,7 +89,7 @@ static ffi::Error SolveBwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params
       lncde_logncde_bwd(stream, params.typed_data(), logsig.typed_data(), rows.typed_data(), scale.typed_data(),
                         ys.typed_data(), g_ys.typed_data(), g_params->typed_data(), g_y0->typed_data(), (int)l[0],
                         (int)l[1], (int)l[2], (int)y[2], C, width, n_hidden, depth, (int)y[1] - 1,
-                        scratch->typed_data(), scratch->size_bytes()),
+                        scratch->typed_data(), scratch->size_bytes(), 0u),
       "lncde_logncde_bwd");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_logncde_bwd, SolveBwdImpl,

@@ -33,13 +33,14 @@ def _declare(lib):
         "lncde_logsig_fwd": (i, [vp, vp, vp, i, i, i, i, i, u, i, vp, vp, vp]),
         "lncde_logncde_param_count": (i, [i, i, i, i]),
         "lncde_logncde_fwd_smem_bytes": (sz, [i, i, i, i]),
-        "lncde_logncde_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i]),
+        "lncde_logncde_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz]),
         "lncde_logncde_bwd_workspace_bytes": (sz, [i, i, i, i, i, i, i]),
-        "lncde_logncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz]),
+        "lncde_logncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz, u]),
         "lncde_linear_scan_workspace_bytes": (sz, [i, i, i, i, i]),
         "lncde_linear_scan_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]),
         "lncde_linear_scan_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]),
         "lncde_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, i, f]),
+        "lncde_adam_step_dev": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, vp, f]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it

@@ -67,12 +67,21 @@ class _LogNCDESolve(torch.autograd.Function):
         ys = torch.empty((B, n_steps + 1, H), device=y0.device, dtype=torch.float32)
         mlp_flat = mlp_flat.contiguous()
         y0c = y0.contiguous()
+        # training mode: hand the adjoint workspace to the forward so it can keep its intermediates
+        train = any(ctx.needs_input_grad)
+        nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, C, width, n_hidden, depth, n_steps) if train else 0
+        ws = _workspace(nbytes, ys.device) if train else None
         st = L.lncde_logncde_fwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(y0c),
                                  _lib.ptr(rows), _lib.ptr(scale), _lib.ptr(ys), B, K, D, H, C, width, n_hidden,
-                                 depth, n_steps)
+                                 depth, n_steps, _lib.ptr(ws), nbytes)
         _lib.check(st, "lncde_logncde_fwd")
         ctx.save_for_backward(mlp_flat, logsig, rows, scale, ys)
         ctx.dims = dims
+        # shared grow-only scratch: its contents are valid until the next training-mode forward on this device
+        ctx.ws = ws
+        if train:
+            _WS_GEN[ys.device] = _WS_GEN.get(ys.device, 0) + 1
+        ctx.ws_gen = _WS_GEN.get(ys.device, 0)
         return ys
 
     @staticmethod
@@ -84,17 +93,22 @@ class _LogNCDESolve(torch.autograd.Function):
         n_steps = rows.shape[0]
         g_ys = g_ys.contiguous()
         nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, C, width, n_hidden, depth, n_steps)
-        ws = _workspace(nbytes, ys.device)
+        ws = ctx.ws
+        # LNCDE_FLAG_SAVED_FWD only if nobody has reused the scratch since our forward wrote it
+        saved = 2 if (ws is not None and _WS.get(ys.device) is ws and _WS_GEN.get(ys.device) == ctx.ws_gen) else 0
+        if ws is None or saved == 0:
+            ws = _workspace(nbytes, ys.device)
         g_params = torch.empty_like(mlp_flat)
         g_y0 = torch.empty((B, H), device=ys.device, dtype=torch.float32)
         st = L.lncde_logncde_bwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(rows),
                                  _lib.ptr(scale), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_params), _lib.ptr(g_y0),
-                                 B, K, D, H, C, width, n_hidden, depth, n_steps, _lib.ptr(ws), nbytes)
+                                 B, K, D, H, C, width, n_hidden, depth, n_steps, _lib.ptr(ws), nbytes, saved)
         _lib.check(st, "lncde_logncde_bwd")
         return g_params, None, g_y0, None, None, None
 
 
 _WS = {}
+_WS_GEN = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:

@@ -59,16 +59,16 @@ class Adam:
         self.lr, self.b1, self.b2, self.eps = float(lr), b1, b2, eps
         self.m = torch.zeros_like(model.params)
         self.v = torch.zeros_like(model.params)
-        self.count = 0
+        # the step count lives on the device so that an update captured in a CUDA graph stays valid
+        self.count = torch.zeros(1, dtype=torch.int32, device=model.params.device)
 
     def update(self, model, grads, grad_scale=1.0):
-        self.count += 1
         _lib.require_cuda(model.params, grads)
         p = model.params.detach()
-        st = _lib.lib().lncde_adam_step(_lib.stream_ptr(), _lib.ptr(p), _lib.ptr(grads.contiguous()),
-                                        _lib.ptr(self.m), _lib.ptr(self.v), p.numel(), self.lr, self.b1, self.b2,
-                                        self.eps, self.count, float(grad_scale))
-        _lib.check(st, "lncde_adam_step")
+        st = _lib.lib().lncde_adam_step_dev(_lib.stream_ptr(), _lib.ptr(p), _lib.ptr(grads.contiguous()),
+                                            _lib.ptr(self.m), _lib.ptr(self.v), p.numel(), self.lr, self.b1, self.b2,
+                                            self.eps, _lib.ptr(self.count), float(grad_scale))
+        _lib.check(st, "lncde_adam_step_dev")
 
 
 def shard_slice(global_batch: int, rank: int, world_size: int) -> slice:
@@ -99,3 +99,29 @@ def make_step(model, filter_spec, X, y, loss_fn, state, opt, opt_state, key, *, 
     allreduce_sum_(grads, world_size)
     opt.update(model, grads, grad_scale=1.0 / world_size)
     return model, state, opt_state, value
+
+
+class GraphedStep:
+    """One training step captured in a CUDA graph (streams and graphs instead of a tracing compiler):
+    the ~100 small launches of a step (K1, solve / scan kernels, read-out + loss autograd, gradient GEMMs,
+    [NCCL all-reduce], Adam) replay as ONE graph launch.  Inputs are copied into static buffers."""
+
+    def __init__(self, step_fn, example_inputs, warmup=3):
+        self.static_in = [t.clone() for t in example_inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step_fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_out = step_fn(*self.static_in)
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_out
