@@ -31,7 +31,8 @@ namespace fast {
 
 constexpr int H = 128, W = 32, NT = 512;
 
-__device__ __forceinline__ float sigm(float z) { return 1.f / (1.f + expf(-z)); }
+// logistic function with the fast exp / reciprocal units (no cancellation here: |error| ~ 2 ulp)
+__device__ __forceinline__ float sigm(float z) { return __frcp_rn(1.f + __expf(-z)); }
 
 // One halving step of a transpose-reduction across lanes lane^mask.
 template <int HALF>
@@ -325,8 +326,8 @@ __device__ __forceinline__ void stage_weights_bwd(const MlpDesc& d, const float*
 // (the right-hand vectors of the weight-gradient pairs in their final place, plus z/s of the
 // hidden layers and the tangent pre-activations).  Must run before sb[yin] is overwritten.
 template <int C, bool D2>
-__device__ __forceinline__ void save_stage(const float* sb, const float (&u3_r)[2], const WsLayout& ws,
-                                           float* __restrict__ wsp, size_t slot) {
+__device__ __forceinline__ void save_stage(const float* sb, const float (&o_r)[2], const float (&u3_r)[2],
+                                           const WsLayout& ws, float* __restrict__ wsp, size_t slot) {
   using S = Smem<C>;
   constexpr int CH = C * H, CW = C * W;
   const int tid = threadIdx.x;
@@ -340,18 +341,16 @@ __device__ __forceinline__ void save_stage(const float* sb, const float (&u3_r)[
     wsp[ws.A[0] + slot * W + tid] = sb[S::a1 + tid];
     wsp[ws.A[1] + slot * W + tid] = sb[S::a2 + tid];
   }
-  if (D2) {
-    for (int t = tid; t < CH; t += NT) wsp[ws.Wt + slot * CH + t] = sb[S::o + t];
-    if (tid < CW) {
-      wsp[ws.P[0] + slot * CW + tid] = sb[S::p1 + tid];
-      wsp[ws.P[1] + slot * CW + tid] = sb[S::p2 + tid];
-      wsp[ws.US + slot * 2 * CW + tid] = sb[S::u1 + tid];
-      wsp[ws.US + slot * 2 * CW + CW + tid] = sb[S::u2 + tid];
-    }
-    if (tid < C * 64)
-      *reinterpret_cast<float2*>(wsp + ws.U3 + slot * CH + lane_row0(tid)) = make_float2(u3_r[0], u3_r[1]);
-  } else {
-    for (int t = tid; t < CH; t += NT) wsp[ws.Wt + slot * CH + t] = sb[S::o + t];
+  if (tid < C * 64) {
+    const int row0 = lane_row0(tid);
+    *reinterpret_cast<float2*>(wsp + ws.Wt + slot * CH + row0) = make_float2(o_r[0], o_r[1]);
+    if (D2) *reinterpret_cast<float2*>(wsp + ws.U3 + slot * CH + row0) = make_float2(u3_r[0], u3_r[1]);
+  }
+  if (D2 && tid < CW) {
+    wsp[ws.P[0] + slot * CW + tid] = sb[S::p1 + tid];
+    wsp[ws.P[1] + slot * CW + tid] = sb[S::p2 + tid];
+    wsp[ws.US + slot * 2 * CW + tid] = sb[S::u1 + tid];
+    wsp[ws.US + slot * 2 * CW + CW + tid] = sb[S::u2 + tid];
   }
 }
 
@@ -385,7 +384,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
     const float s1n = p.stage_scale[2 * nn], s2n = p.stage_scale[2 * nn + 1];
     const float lam_b = lambda_fetch<C>(ls + (size_t)r2 * p.D, D2);
     stage_forward<C, D2>(sb, cm, R, lam_a, o_r, u3_r);
-    if (SAVE) save_stage<C, D2>(sb, u3_r, p.ws, p.wsp, ((size_t)b * p.n_steps + n) * 2);
+    if (SAVE) save_stage<C, D2>(sb, o_r, u3_r, p.ws, p.wsp, ((size_t)b * p.n_steps + n) * 2);
     if (tid < H) {
       const float kk = s1 * field_value<C, D2>(sb, cm, tid);
       cm[S::k1 + tid] = kk;
@@ -394,7 +393,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
     __syncthreads();
     lam_a = lambda_fetch<C>(ls + (size_t)r1n * p.D, D2);
     stage_forward<C, D2>(sb, cm, R, lam_b, o_r, u3_r);
-    if (SAVE) save_stage<C, D2>(sb, u3_r, p.ws, p.wsp, ((size_t)b * p.n_steps + n) * 2 + 1);
+    if (SAVE) save_stage<C, D2>(sb, o_r, u3_r, p.ws, p.wsp, ((size_t)b * p.n_steps + n) * 2 + 1);
     if (tid < H) {
       const float yn = cm[S::ycur + tid] + 0.5f * (cm[S::k1 + tid] + s2 * field_value<C, D2>(sb, cm, tid));
       cm[S::ycur + tid] = yn;

@@ -9,6 +9,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 namespace lncde {
 
 struct GemmSeg {
@@ -31,46 +33,97 @@ struct GemmParams {
   float* part;
 };
 
-template <int TM, int TN>
+// index of the i-th row (column) owned by thread coordinate t: contiguous groups of 4 so that the
+// operand reads from shared memory are conflict-free 128-bit (64-bit for T = 2) loads
+template <int T>
+__device__ __forceinline__ int own_index(int t, int i) {
+  return T >= 4 ? (i >> 2) * 64 + t * 4 + (i & 3) : t * T + i;
+}
+
+template <int TM, int TN, bool VEC>
 __global__ void __launch_bounds__(256) outer_gemm_kernel(const GemmParams p) {
-  constexpr int KT = 16;
-  __shared__ float Ls[KT][16 * TM];
-  __shared__ float Rs[KT][16 * TN];
+  constexpr int KT = 32, MT = 16 * TM, NT_ = 16 * TN;
+  __shared__ __align__(16) float Ls[KT][MT];
+  __shared__ __align__(16) float Rs[KT][NT_];
   int bid = blockIdx.x;
   const int ks = bid % p.ksplit; bid /= p.ksplit;
   const int nt = bid % p.n_tiles; bid /= p.n_tiles;
   const int mt = bid % p.m_tiles; bid /= p.m_tiles;
   const GemmTask& t = p.task[bid];
-  const int m0 = mt * 16 * TM, n0 = nt * 16 * TN;
+  const int m0 = mt * MT, n0 = nt * NT_;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  // global -> register staging: LV (RV) 128-bit loads per thread cover one K-tile
+  constexpr int LV = (KT * MT / 4 + 255) / 256, RV = (KT * NT_ / 4 + 255) / 256;
+  float4 lreg[LV], rreg[RV];
   for (int sgi = 0; sgi < 2; ++sgi) {
     const GemmSeg& sg = t.seg[sgi];
     if (sg.count == 0) continue;
     const long long per = (sg.count + p.ksplit - 1) / p.ksplit;
     const long long k_lo = per * ks, k_hi = min(sg.count, k_lo + per);
-    for (long long k0 = k_lo; k0 < k_hi; k0 += KT) {
-      const int kn = (int)min((long long)KT, k_hi - k0);
-      for (int e = threadIdx.x; e < KT * 16 * TM; e += 256) {
-        const int kk = e / (16 * TM), m = e - kk * 16 * TM;
-        Ls[kk][m] = (kk < kn && m0 + m < t.M) ? sg.left[(k0 + kk) * sg.ldl + m0 + m] : 0.f;
+    auto fetch = [&](long long k0) {
+#pragma unroll
+      for (int u = 0; u < LV; ++u) {
+        const int e = threadIdx.x + u * 256;
+        const int kk = e / (MT / 4), m = (e - kk * (MT / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < KT * MT / 4 && k0 + kk < k_hi) {
+          const float* src = sg.left + (k0 + kk) * sg.ldl + m0 + m;
+          if (VEC) {
+            if (m0 + m < t.M) v = *reinterpret_cast<const float4*>(src);
+          } else {
+            if (m0 + m + 0 < t.M) v.x = src[0];
+            if (m0 + m + 1 < t.M) v.y = src[1];
+            if (m0 + m + 2 < t.M) v.z = src[2];
+            if (m0 + m + 3 < t.M) v.w = src[3];
+          }
+        }
+        lreg[u] = v;
       }
-      for (int e = threadIdx.x; e < KT * 16 * TN; e += 256) {
-        const int kk = e / (16 * TN), n = e - kk * 16 * TN;
-        Rs[kk][n] = (kk < kn && n0 + n < t.N) ? sg.right[(k0 + kk) * sg.ldr + n0 + n] : 0.f;
+#pragma unroll
+      for (int u = 0; u < RV; ++u) {
+        const int e = threadIdx.x + u * 256;
+        const int kk = e / (NT_ / 4), n = (e - kk * (NT_ / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < KT * NT_ / 4 && k0 + kk < k_hi) {
+          const float* src = sg.right + (k0 + kk) * sg.ldr + n0 + n;
+          if (VEC) {
+            if (n0 + n < t.N) v = *reinterpret_cast<const float4*>(src);
+          } else {
+            if (n0 + n + 0 < t.N) v.x = src[0];
+            if (n0 + n + 1 < t.N) v.y = src[1];
+            if (n0 + n + 2 < t.N) v.z = src[2];
+            if (n0 + n + 3 < t.N) v.w = src[3];
+          }
+        }
+        rreg[u] = v;
+      }
+    };
+    if (k_lo < k_hi) fetch(k_lo);
+    for (long long k0 = k_lo; k0 < k_hi; k0 += KT) {
+#pragma unroll
+      for (int u = 0; u < LV; ++u) {
+        const int e = threadIdx.x + u * 256;
+        if (e < KT * MT / 4) *reinterpret_cast<float4*>(&Ls[0][0] + e * 4) = lreg[u];
+      }
+#pragma unroll
+      for (int u = 0; u < RV; ++u) {
+        const int e = threadIdx.x + u * 256;
+        if (e < KT * NT_ / 4) *reinterpret_cast<float4*>(&Rs[0][0] + e * 4) = rreg[u];
       }
       __syncthreads();
-#pragma unroll
+      if (k0 + KT < k_hi) fetch(k0 + KT);  // next tile in flight while this one is consumed
+#pragma unroll 8
       for (int kk = 0; kk < KT; ++kk) {
         float a[TM], bb[TN];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) a[i] = Ls[kk][ty + 16 * i];
+        for (int i = 0; i < TM; ++i) a[i] = Ls[kk][own_index<TM>(ty, i)];
 #pragma unroll
-        for (int j = 0; j < TN; ++j) bb[j] = Rs[kk][tx + 16 * j];
+        for (int j = 0; j < TN; ++j) bb[j] = Rs[kk][own_index<TN>(tx, j)];
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -84,7 +137,7 @@ __global__ void __launch_bounds__(256) outer_gemm_kernel(const GemmParams p) {
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
-      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+      const int m = m0 + own_index<TM>(ty, i), n = n0 + own_index<TN>(tx, j);
       if (m < t.M && n < t.N) out[(size_t)m * t.N + n] = acc[i][j];
     }
 }
@@ -97,13 +150,22 @@ static inline int round_tile(int v) {  // ceil(v/16) rounded up to 1,2,4,8
   return 8;
 }
 
-template <int TM>
+template <int TM, bool VEC>
 static inline void launch_gemm_tn(int tn, const GemmParams& sub, int grid, cudaStream_t st) {
   switch (tn) {
-    case 1: outer_gemm_kernel<TM, 1><<<grid, 256, 0, st>>>(sub); break;
-    case 2: outer_gemm_kernel<TM, 2><<<grid, 256, 0, st>>>(sub); break;
-    case 4: outer_gemm_kernel<TM, 4><<<grid, 256, 0, st>>>(sub); break;
-    default: outer_gemm_kernel<TM, 8><<<grid, 256, 0, st>>>(sub); break;
+    case 1: outer_gemm_kernel<TM, 1, VEC><<<grid, 256, 0, st>>>(sub); break;
+    case 2: outer_gemm_kernel<TM, 2, VEC><<<grid, 256, 0, st>>>(sub); break;
+    case 4: outer_gemm_kernel<TM, 4, VEC><<<grid, 256, 0, st>>>(sub); break;
+    default: outer_gemm_kernel<TM, 8, VEC><<<grid, 256, 0, st>>>(sub); break;
+  }
+}
+template <bool VEC>
+static inline void launch_gemm_tm(int tm, int tn, const GemmParams& sub, int grid, cudaStream_t st) {
+  switch (tm) {
+    case 1: launch_gemm_tn<1, VEC>(tn, sub, grid, st); break;
+    case 2: launch_gemm_tn<2, VEC>(tn, sub, grid, st); break;
+    case 4: launch_gemm_tn<4, VEC>(tn, sub, grid, st); break;
+    default: launch_gemm_tn<8, VEC>(tn, sub, grid, st); break;
   }
 }
 // Launch tasks [first, first+count) of g; all must share M, N.
@@ -117,12 +179,17 @@ static inline void launch_gemm(const GemmParams& g, int first, int count, cudaSt
   sub.m_tiles = (M + 16 * tm - 1) / (16 * tm);
   sub.n_tiles = (N + 16 * tn - 1) / (16 * tn);
   const int grid = count * sub.m_tiles * sub.n_tiles * sub.ksplit;
-  switch (tm) {
-    case 1: launch_gemm_tn<1>(tn, sub, grid, st); break;
-    case 2: launch_gemm_tn<2>(tn, sub, grid, st); break;
-    case 4: launch_gemm_tn<4>(tn, sub, grid, st); break;
-    default: launch_gemm_tn<8>(tn, sub, grid, st); break;
-  }
+  // 128-bit global loads when every operand row is 16 B aligned and M, N are multiples of 4
+  bool vec = (M % 4 == 0) && (N % 4 == 0);
+  for (int i = 0; i < count && vec; ++i)
+    for (int sg = 0; sg < 2; ++sg) {
+      const GemmSeg& g2 = sub.task[i].seg[sg];
+      if (g2.count == 0) continue;
+      vec = vec && ((uintptr_t)g2.left % 16 == 0) && ((uintptr_t)g2.right % 16 == 0) && (g2.ldl % 4 == 0) &&
+            (g2.ldr % 4 == 0);
+    }
+  if (vec) launch_gemm_tm<true>(tm, tn, sub, grid, st);
+  else launch_gemm_tm<false>(tm, tn, sub, grid, st);
 }
 
 }  // namespace lncde
