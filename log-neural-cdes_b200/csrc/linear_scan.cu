@@ -311,6 +311,238 @@ static bool scan_warp_dispatch(bool bwd, cudaStream_t cs, float* F, const float*
   return false;
 }
 
+// ---------------------------------------------------------------- 2c/3c. big-block scans (DE-LNCDE)
+// One CTA per sample.  The flows do not depend on the state, so they are streamed through a ring
+// of shared-memory stages by 1-D TMA bulk copies (cp.async.bulk + mbarrier, issued NS-1 steps
+// ahead by one thread); only the H-vector recurrence is on the dependent chain.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kBigThreads = 512;
+
+template <int NS>
+__global__ void __launch_bounds__(kBigThreads, 1) scan_fwd_tma_kernel(const float* __restrict__ F,
+                                                                       const float* __restrict__ y0,
+                                                                       float* __restrict__ ys, int T, int H, int bs) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int N = H * bs;
+  const unsigned step_bytes = (unsigned)N * 4;
+  float* tiles = reinterpret_cast<float*>(smraw);                 // [NS][N]
+  float* ybuf = tiles + (size_t)NS * N;                           // [2][H]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ybuf + 2 * H);
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = kBigThreads / 32;
+  const float* Fb = F + (size_t)b * T * N;
+  float* yb = ys + (size_t)b * T * H;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int h = tid; h < H; h += kBigThreads) {
+    const float v = y0[(size_t)b * H + h];
+    ybuf[h] = v;
+    yb[h] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int u = 0; u < NS - 1 && 1 + u < T; ++u) {
+      mbar_expect_tx(bars + (u % NS), step_bytes);
+      tma_load_1d(tiles + (size_t)(u % NS) * N, Fb + (size_t)(1 + u) * N, step_bytes, bars + (u % NS));
+    }
+  }
+  int cur = 0;
+  for (int t = 1; t < T; ++t) {
+    const int it = t - 1, s = it % NS;
+    // keep NS-1 steps in flight: the stage freed at the end of the previous step is refilled now
+    if (tid == 0) {
+      const int tn = t + NS - 1;
+      if (tn < T) {
+        const int sn = (it + NS - 1) % NS;
+        fence_async_proxy();
+        mbar_expect_tx(bars + sn, step_bytes);
+        tma_load_1d(tiles + (size_t)sn * N, Fb + (size_t)tn * N, step_bytes, bars + sn);
+      }
+    }
+    mbar_wait(bars + s, (unsigned)((it / NS) & 1));
+    const float* Ft = tiles + (size_t)s * N;
+    const float* yc = ybuf + cur * H;
+    float* yn = ybuf + (cur ^ 1) * H;
+    // warp per group of 4 rows, lanes across the columns
+    for (int h0 = warp * 4; h0 < H; h0 += nw * 4) {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const int blk = h0 / bs;
+      const float* yv = yc + blk * bs;
+      for (int j4 = lane; j4 < bs / 4; j4 += 32) {
+        const float4 y4 = *reinterpret_cast<const float4*>(yv + j4 * 4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float4 f4 = *reinterpret_cast<const float4*>(Ft + (size_t)(h0 + r) * bs + j4 * 4);
+          v[r] = fmaf(f4.x, y4.x, v[r]);
+          v[r] = fmaf(f4.y, y4.y, v[r]);
+          v[r] = fmaf(f4.z, y4.z, v[r]);
+          v[r] = fmaf(f4.w, y4.w, v[r]);
+        }
+      }
+      // transpose-reduce 4 rows over 32 lanes
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const bool up = lane & 16;
+        const float send = up ? v[k] : v[k + 2], keep = up ? v[k + 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+      {
+        const bool up = lane & 8;
+        const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 4);
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+      if ((lane & 7) == 0) {
+        const int r = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+        yn[h0 + r] = v[0];
+        yb[(size_t)t * H + h0 + r] = v[0];
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kBigThreads, 1) scan_bwd_tma_kernel(float* __restrict__ F,
+                                                                       const float* __restrict__ ys,
+                                                                       const float* __restrict__ g_ys,
+                                                                       float* __restrict__ g_y0, int T, int H, int bs) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int N = H * bs;
+  const unsigned step_bytes = (unsigned)N * 4;
+  float* tiles = reinterpret_cast<float*>(smraw);      // [NS][N]
+  float* lamb = tiles + (size_t)NS * N;                // [2][H]
+  float* yprev = lamb + 2 * H;                         // [2][H]  (double buffered prefetch)
+  float* red = yprev + 2 * H;                          // [RQ][H]
+  const int RQ = kBigThreads / H;                      // row groups (H <= 512)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(red + (size_t)RQ * H);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float* Fb = F + (size_t)b * T * N;
+  const float* yb = ys + (size_t)b * T * H;
+  const float* gb = g_ys + (size_t)b * T * H;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int h = tid; h < H; h += kBigThreads) {
+    lamb[h] = gb[(size_t)(T - 1) * H + h];
+    if (T >= 2) yprev[h] = yb[(size_t)(T - 2) * H + h];
+  }
+  for (int e = tid; e < N; e += kBigThreads) Fb[e] = 0.f;  // flow 0 is never applied: zero gradient
+  __syncthreads();
+  if (tid == 0) {
+    for (int u = 0; u < NS - 1 && T - 1 - u >= 1; ++u) {
+      mbar_expect_tx(bars + (u % NS), step_bytes);
+      tma_load_1d(tiles + (size_t)(u % NS) * N, Fb + (size_t)(T - 1 - u) * N, step_bytes, bars + (u % NS));
+    }
+  }
+  const int h = tid % H, rq = tid / H;
+  const bool act = rq < RQ;
+  const int blk = h / bs, jj = h - blk * bs;
+  int cur = 0;
+  for (int t = T - 1; t >= 1; --t) {
+    const int it = T - 1 - t, s = it % NS;
+    if (tid == 0) {
+      const int tn = t - (NS - 1);
+      if (tn >= 1) {
+        const int sn = (it + NS - 1) % NS;
+        fence_async_proxy();
+        mbar_expect_tx(bars + sn, step_bytes);
+        tma_load_1d(tiles + (size_t)sn * N, Fb + (size_t)tn * N, step_bytes, bars + sn);
+      }
+    }
+    // prefetch y_{t-2} and g for the next step into the other halves
+    float y_next = 0.f;
+    if (tid < H && t >= 2) y_next = yb[(size_t)(t - 2) * H + tid];
+    const float g_prev = tid < H ? gb[(size_t)(t - 1) * H + tid] : 0.f;
+    mbar_wait(bars + s, (unsigned)((it / NS) & 1));
+    const float* Ft = tiles + (size_t)s * N;
+    const float* lam = lamb + cur * H;
+    const float* yp = yprev + cur * H;
+    float* Fg = Fb + (size_t)t * N;
+    float acc = 0.f;
+    if (act) {
+      const float ypj = yp[h];
+      const float* col = Ft + (size_t)blk * bs * bs + jj;
+      float* gcol = Fg + (size_t)blk * bs * bs + jj;
+      const float* lv = lam + blk * bs;
+      for (int i = rq; i < bs; i += RQ) {
+        const float li = lv[i];
+        acc = fmaf(col[(size_t)i * bs], li, acc);
+        gcol[(size_t)i * bs] = li * ypj;  // dF_t[i][j] = lam_t[i] * y_{t-1}[j], in place
+      }
+      red[rq * H + h] = acc;
+    }
+    __syncthreads();
+    if (tid < H) {
+      float sum = g_prev;
+      for (int q = 0; q < RQ; ++q) sum += red[q * H + tid];
+      lamb[(cur ^ 1) * H + tid] = sum;
+      yprev[(cur ^ 1) * H + tid] = y_next;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  for (int hh = tid; hh < H; hh += kBigThreads) g_y0[(size_t)b * H + hh] = lamb[cur * H + hh];
+}
+
+static bool scan_tma_dispatch(bool bwd, cudaStream_t cs, float* F, const float* y0, float* ys, const float* g_ys,
+                              float* g_y0, int B, int T, int H, int bs) {
+  if (bs % 4 != 0 || H > kBigThreads || kBigThreads % H != 0 || H % 4 != 0) return false;
+  const size_t step_bytes = (size_t)H * bs * 4;
+  if (step_bytes % 16 != 0) return false;
+  const size_t extra = (size_t)(4 * H + (kBigThreads / H) * H) * 4 + 64;
+  int ns = 0;
+  for (int cand = 4; cand >= 2; --cand)
+    if (cand * step_bytes + extra <= 220 * 1024) { ns = cand; break; }
+  if (ns == 0) return false;
+  const size_t smem = ns * step_bytes + extra;
+  auto launch = [&](auto kf, auto kb) {
+    if (!bwd) {
+      cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kf<<<B, kBigThreads, smem, cs>>>(F, y0, ys, T, H, bs);
+    } else {
+      cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kb<<<B, kBigThreads, smem, cs>>>(F, ys, g_ys, g_y0, T, H, bs);
+    }
+  };
+  if (ns == 4) launch(scan_fwd_tma_kernel<4>, scan_bwd_tma_kernel<4>);
+  else if (ns == 3) launch(scan_fwd_tma_kernel<3>, scan_bwd_tma_kernel<3>);
+  else launch(scan_fwd_tma_kernel<2>, scan_bwd_tma_kernel<2>);
+  return true;
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int ksplit) {
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -374,6 +606,7 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   if (st != 0) return st;
   // 2. scan
   if (scan_warp_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
+  } else if (scan_tma_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
   } else if (bs <= 16) {
     int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));
     scan_fwd_small_kernel<<<B, threads, 2 * H * sizeof(float), cs>>>(F, y0, ys, T, H, bs);
@@ -397,7 +630,8 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
   cudaStream_t cs = (cudaStream_t)stream;
   float* F = (float*)workspace;  // still holds the forward flows of the SAME (lie, logsig)
   const int H = nb * bs, N = H * bs;
-  if (!scan_warp_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs)) {
+  if (!scan_warp_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs) &&
+      !scan_tma_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs)) {
     int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));
     scan_bwd_kernel<<<B, threads, 3 * H * sizeof(float), cs>>>(F, ys, g_ys, g_y0, T, H, bs);
   }
