@@ -456,9 +456,7 @@ def run_reference(args):
            "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": 1e3 * WL["B"] / cb["value"], "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "EigenWorms Log-NCDE depth-2 logsig: B=32, L=17984, C=7 (6+time), stepsize 12, "
-                                  "H=128, vf 2x32, Heun dt0=1/1499, CE+Lip2, Adam",
-                      "global_batch": WL["B"], "parallelism": "cpu"},
+           "config": {"workload": WL["desc"], "global_batch": WL["B"], "parallelism": "cpu"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.perf_counter() - t0}
