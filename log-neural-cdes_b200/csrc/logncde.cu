@@ -59,15 +59,44 @@ int make_mlp_desc(MlpDesc* d, int H, int C, int width, int n_hidden, int depth, 
     sm = (sm + 3) & ~3;
   }
   d->n_params = off;
-  d->smem_weight_floats = sm;
-  d->weights_in_smem = ((size_t)sm * 4 + other_smem_bytes <= (size_t)220 * 1024) ? 1 : 0;
-  if (!d->weights_in_smem) {
-    for (int l = 0; l <= n_hidden; ++l) {
+  // Shared-memory residency per layer: keep as many layers as fit (smallest first - the hidden
+  // layers are reused by all C tangents); the rest is streamed from global / L2 with coalesced
+  // 128-bit row reads.
+  const size_t budget = (size_t)218 * 1024;
+  size_t used = other_smem_bytes;
+  int order[kMaxLayers];
+  for (int l = 0; l <= n_hidden; ++l) order[l] = l;
+  for (int a = 0; a <= n_hidden; ++a)
+    for (int b = a + 1; b <= n_hidden; ++b)
+      if (d->rows[order[b]] * d->stride[order[b]] < d->rows[order[a]] * d->stride[order[a]]) {
+        const int t = order[a]; order[a] = order[b]; order[b] = t;
+      }
+  bool resident[kMaxLayers] = {false, false, false, false, false};
+  for (int k = 0; k <= n_hidden; ++k) {
+    const int l = order[k];
+    const size_t bytes = ((size_t)d->rows[l] * d->stride[l] + 3) / 4 * 16;
+    if (used + bytes <= budget) {
+      resident[l] = true;
+      used += bytes;
+    }
+  }
+  sm = 0;
+  d->weights_in_smem = 1;
+  for (int l = 0; l <= n_hidden; ++l) {
+    d->gvec[l] = 0;
+    if (resident[l]) {
+      d->sm_off[l] = sm;
+      sm += d->rows[l] * d->stride[l];
+      sm = (sm + 3) & ~3;
+    } else {
+      d->weights_in_smem = 0;
       d->sm_off[l] = -1;
       d->stride[l] = d->in_dim[l];
+      // coalesced 128-bit path needs 16 B aligned rows (the parameter buffer itself is 16 B aligned)
+      d->gvec[l] = (d->in_dim[l] % 4 == 0 && d->w_off[l] % 4 == 0 && (l < n_hidden || H % 4 == 0)) ? 1 : 0;
     }
-    d->smem_weight_floats = 0;
   }
+  d->smem_weight_floats = sm;
   return LNCDE_OK;
 }
 

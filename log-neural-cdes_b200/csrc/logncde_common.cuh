@@ -26,6 +26,7 @@ struct MlpDesc {
   int stride[kMaxLayers];                     // row stride of the weight copy the kernel reads
   int sm_off[kMaxLayers];                     // offset of the layer in the smem weight region, -1: global
   int kq_log2[kMaxLayers];                    // lanes cooperating on one output row
+  int gvec[kMaxLayers];                       // layer read from global memory with coalesced 128-bit rows
   int n_params;
   int weights_in_smem;
   int smem_weight_floats;
@@ -115,6 +116,105 @@ __device__ __forceinline__ void matvec_rows_blocked(const float* __restrict__ W,
   }
 }
 
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Global-memory weights (layer not resident in shared memory): one warp per output row, lanes
+// across the columns with coalesced 128-bit loads, butterfly reduction.  Requires in_dim % 4 == 0
+// and 16-byte aligned rows (checked by the host when it picks this path).
+template <int NB, typename Emit>
+__device__ __forceinline__ void matvec_rows_global(const float* __restrict__ W, int rows, int in_dim,
+                                                   const float* __restrict__ in, int in_stride, Emit&& emit) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kSolveThreads >> 5;
+  const int nq = in_dim >> 2;
+  for (int row = warp; row < rows; row += nw) {
+    float acc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+    const float* wr = W + (size_t)row * in_dim;
+    for (int q = lane; q < nq; q += 32) {
+      const float4 w4 = ldg4(wr + 4 * q);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float4 x4 = *reinterpret_cast<const float4*>(in + j * in_stride + 4 * q);
+        acc[j] = fmaf(w4.x, x4.x, acc[j]);
+        acc[j] = fmaf(w4.y, x4.y, acc[j]);
+        acc[j] = fmaf(w4.z, x4.z, acc[j]);
+        acc[j] = fmaf(w4.w, x4.w, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], m);
+    }
+    if (lane == 0) emit(row, acc);
+  }
+}
+
+// 4 rows per warp at a time, each row against its own block's input vector
+template <typename Emit>
+__device__ __forceinline__ void matvec_rows_blocked_global(const float* __restrict__ W, int C, int H, int in_dim,
+                                                           const float* __restrict__ in, int in_stride, Emit&& emit) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kSolveThreads >> 5;
+  const int nq = in_dim >> 2, rows = C * H;
+  for (int r0 = warp * 4; r0 < rows; r0 += nw * 4) {  // H % 4 == 0: the 4 rows share one block
+    const int j = r0 / H;
+    const float* v = in + j * in_stride;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = lane; q < nq; q += 32) {
+      const float4 x4 = *reinterpret_cast<const float4*>(v + 4 * q);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float4 w4 = ldg4(W + (size_t)(r0 + r) * in_dim + 4 * q);
+        acc[r] = fmaf(w4.x, x4.x, acc[r]);
+        acc[r] = fmaf(w4.y, x4.y, acc[r]);
+        acc[r] = fmaf(w4.z, x4.z, acc[r]);
+        acc[r] = fmaf(w4.w, x4.w, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], m);
+    }
+    if (lane < 4) emit(j, r0 + lane - j * H, lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]);
+  }
+}
+
+// primal last layer from global memory: 4 rows per warp at a time, one shared input vector
+template <typename Emit>
+__device__ __forceinline__ void matvec_rows4_global(const float* __restrict__ W, int rows, int in_dim,
+                                                    const float* __restrict__ in, Emit&& emit) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kSolveThreads >> 5;
+  const int nq = in_dim >> 2;
+  for (int r0 = warp * 4; r0 < rows; r0 += nw * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = lane; q < nq; q += 32) {
+      const float4 x4 = *reinterpret_cast<const float4*>(in + 4 * q);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (r0 + r < rows) {
+          const float4 w4 = ldg4(W + (size_t)(r0 + r) * in_dim + 4 * q);
+          acc[r] = fmaf(w4.x, x4.x, acc[r]);
+          acc[r] = fmaf(w4.y, x4.y, acc[r]);
+          acc[r] = fmaf(w4.z, x4.z, acc[r]);
+          acc[r] = fmaf(w4.w, x4.w, acc[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], m);
+    }
+    if (lane < 4 && r0 + lane < rows) {
+      float one[1] = {lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]};
+      emit(r0 + lane, one);
+    }
+  }
+}
+
 // Transposed product.  out[j*out_stride + c] = sum_r W[(row0_j + r)*stride + c] * v[j*v_stride + r]
 // row0_j = j*nrows if BLOCKED else 0.  `scratch` needs kSolveThreads*NB floats.  Ends with the
 // result visible to all threads (contains __syncthreads).
@@ -199,22 +299,24 @@ __device__ __forceinline__ void stage_forward(const StageCtx& cx, float* buf, co
     float* a = buf + L.a + l * Wd;
     float* s = buf + L.s + l * Wd;
     float* z = buf + L.z + l * Wd;
-    matvec_rows<1>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], in, 0,
-                   [&](int row, const float* acc) {
-                     const float zz = acc[0] + bias[row];
-                     const float sg = sigmoidf_(zz);
-                     z[row] = zz;
-                     a[row] = zz * sg;
-                     s[row] = sg * (1.f + zz * (1.f - sg));
-                   });
+    auto fin = [&](int row, const float* acc) {
+      const float zz = acc[0] + bias[row];
+      const float sg = sigmoidf_(zz);
+      z[row] = zz;
+      a[row] = zz * sg;
+      s[row] = sg * (1.f + zz * (1.f - sg));
+    };
+    if (d.gvec[l]) matvec_rows4_global(cx.wbase[l], d.rows[l], d.in_dim[l], in, fin);
+    else matvec_rows<1>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], in, 0, fin);
     __syncthreads();
     in = a;
   }
   {
     const float* bias = cx.params + d.b_off[NL];
     float* o = buf + L.o;
-    matvec_rows<1>(cx.wbase[NL], d.stride[NL], d.rows[NL], d.in_dim[NL], d.kq_log2[NL], in, 0,
-                   [&](int row, const float* acc) { o[row] = tanhf(acc[0] + bias[row]); });
+    auto fin = [&](int row, const float* acc) { o[row] = tanhf(acc[0] + bias[row]); };
+    if (d.gvec[NL]) matvec_rows4_global(cx.wbase[NL], d.rows[NL], d.in_dim[NL], in, fin);
+    else matvec_rows<1>(cx.wbase[NL], d.stride[NL], d.rows[NL], d.in_dim[NL], d.kq_log2[NL], in, 0, fin);
   }
   __syncthreads();
   // ---- G = sum_i l_i o_i ; w_j = sum_i Lam_ij o_i ---------------------------
@@ -250,23 +352,25 @@ __device__ __forceinline__ void stage_forward(const StageCtx& cx, float* buf, co
     const float* s = buf + L.s + l * Wd;
     float* u = buf + L.u + l * C * Wd;
     float* p = buf + L.p + l * C * Wd;
-    matvec_rows<C>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], tin, tin_stride,
-                   [&](int row, const float* acc) {
-                     const float sv = s[row];
+    auto fin = [&](int row, const float* acc) {
+      const float sv = s[row];
 #pragma unroll
-                     for (int j = 0; j < C; ++j) {
-                       u[j * Wd + row] = acc[j];
-                       p[j * Wd + row] = sv * acc[j];
-                     }
-                   });
+      for (int j = 0; j < C; ++j) {
+        u[j * Wd + row] = acc[j];
+        p[j * Wd + row] = sv * acc[j];
+      }
+    };
+    if (d.gvec[l]) matvec_rows_global<C>(cx.wbase[l], d.rows[l], d.in_dim[l], tin, tin_stride, fin);
+    else matvec_rows<C>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], tin, tin_stride, fin);
     __syncthreads();
     tin = p;
     tin_stride = Wd;
   }
   {
     float* ul = buf + L.ul;
-    matvec_rows_blocked(cx.wbase[NL], d.stride[NL], C, H, d.in_dim[NL], d.kq_log2[NL], tin, tin_stride,
-                        [&](int j, int h, float acc) { ul[j * H + h] = acc; });
+    auto fin = [&](int j, int h, float acc) { ul[j * H + h] = acc; };
+    if (d.gvec[NL]) matvec_rows_blocked_global(cx.wbase[NL], C, H, d.in_dim[NL], tin, tin_stride, fin);
+    else matvec_rows_blocked(cx.wbase[NL], d.stride[NL], C, H, d.in_dim[NL], d.kq_log2[NL], tin, tin_stride, fin);
   }
   __syncthreads();
   {
