@@ -107,21 +107,13 @@ struct LevyParams {
   uint32_t sc_magic;  // ceil(2^32 / (s*C))
 };
 
-template <int C, bool DEPTH2>
-__global__ void __launch_bounds__(128) logsig_levy_kernel(const LevyParams p) {
-  extern __shared__ float smem[];
-  constexpr int D = 1 + C + (DEPTH2 ? (C * (C - 1)) / 2 : 0);
-  const int b = blockIdx.x / p.tiles;
-  const int tile = blockIdx.x - b * p.tiles;
-  const int k0 = tile * p.WT;
-  const int nw = min(p.WT, p.q - k0);  // full windows in this tile (may be 0 for K == remainder only)
+// Stage rows k0*s-2 .. k0*s-2 + nw*s of one sample (nw*s + 1 rows) into shared memory:
+// tile_base[0,C) = basepoint row of window k0; window w's s rows at win + w*stride (odd stride).
+__device__ __forceinline__ void stage_windows(const LevyParams& p, const int C, const float* __restrict__ xb,
+                                              const int k0, const int nw, float* tile_base, float* win) {
   const int sC = p.s * C;
-  const float* xb = p.data + (size_t)b * p.L * C;
-
   // ---- stage rows k0*s-2 .. k0*s-2 + nw*s  (nw*s + 1 rows) ------------------
   // smem: [0,C) tile basepoint row; window w's s rows at C + w*stride.
-  float* tile_base = smem;
-  float* win = smem + C;
   const long long row0 = (long long)k0 * p.s - 2;  // basepoint row of window k0
   if (threadIdx.x < C) {
     tile_base[threadIdx.x] = row0 >= 0 ? ld_stream(xb + row0 * C + threadIdx.x) : 0.f;
@@ -174,6 +166,22 @@ __global__ void __launch_bounds__(128) logsig_levy_kernel(const LevyParams p) {
     const int tail0 = head + 4 * n_v4;
     if (threadIdx.x < n_ld - tail0) put(t_off + tail0 + threadIdx.x, ld_stream(src + tail0 + threadIdx.x));
   }
+}
+
+template <int C, bool DEPTH2>
+__global__ void __launch_bounds__(128) logsig_levy_kernel(const LevyParams p) {
+  extern __shared__ float smem[];
+  constexpr int D = 1 + C + (DEPTH2 ? (C * (C - 1)) / 2 : 0);
+  const int b = blockIdx.x / p.tiles;
+  const int tile = blockIdx.x - b * p.tiles;
+  const int k0 = tile * p.WT;
+  const int nw = min(p.WT, p.q - k0);  // full windows in this tile (may be 0 for K == remainder only)
+  const int sC = p.s * C;
+  const float* xb = p.data + (size_t)b * p.L * C;
+
+  float* tile_base = smem;
+  float* win = smem + C;
+  stage_windows(p, C, xb, k0, nw, tile_base, win);
   __syncthreads();
 
   // ---- one thread per window ------------------------------------------------
@@ -245,6 +253,140 @@ __global__ void __launch_bounds__(128) logsig_levy_kernel(const LevyParams p) {
   }
 }
 
+
+// ----------------------------------------------------------------------------
+// depth 3, C <= 8: thread (window, i) keeps "row i" of the truncated signature in registers
+// (S1[i], S2[i][.], S3[i][.][.]): the Chen/Horner update of row i needs only the increment, so
+// the sweep over the window is communication-free.  log() and the sparse Hall projection (CSR
+// from K0) run once per window out of shared memory.
+// ----------------------------------------------------------------------------
+struct D3Params {
+  LevyParams lv;
+  const int32_t* rowptr;
+  const int32_t* cols;
+  const float* vals;
+};
+
+template <int C>
+__global__ void __launch_bounds__(32 * C) logsig_d3_kernel(const D3Params pp) {
+  extern __shared__ float smem[];
+  const LevyParams& p = pp.lv;
+  constexpr int WT = 32, C2 = C * C, C3 = C * C * C, E = C + C2 + C3;
+  const int b = blockIdx.x / p.tiles, tile = blockIdx.x - b * p.tiles;
+  const int k0 = tile * WT;
+  const int nw = min(WT, p.q - k0);
+  const float* xb = p.data + (size_t)b * p.L * C;
+  float* ex = smem;                       // [WT][E] : S1 | S2 | L3 per window
+  float* tile_base = smem + WT * E;
+  float* win = tile_base + C;
+  stage_windows(p, C, xb, k0, nw, tile_base, win);
+  __syncthreads();
+  const int w = threadIdx.x / C, i = threadIdx.x - w * C;
+  float s1 = 0.f, S2r[C], S3r[C][C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    S2r[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < C; ++k) S3r[j][k] = 0.f;
+  }
+  if (w < nw) {
+    const float* bp = (w == 0) ? tile_base : (win + (w - 1) * p.stride + (p.s - 1) * C);
+    float base[C], prev[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      base[c] = bp[c];
+      prev[c] = 0.f;
+    }
+    const float base_i = bp[i];
+    float prev_i = 0.f;
+    const float* rows = win + w * p.stride;
+#pragma unroll 2
+    for (int l = 0; l < p.s; ++l) {
+      float z[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float cur = rows[l * C + c] - base[c];
+        z[c] = cur - prev[c];
+        prev[c] = cur;
+      }
+      const float cur_i = rows[l * C + i] - base_i;
+      const float zi = cur_i - prev_i;
+      prev_i = cur_i;
+      const float a3 = fmaf(zi, 1.f / 3.f, s1);
+#pragma unroll
+      for (int j = 0; j < C; ++j) {
+        const float bj = fmaf(a3 * 0.5f, z[j], S2r[j]);
+#pragma unroll
+        for (int k = 0; k < C; ++k) S3r[j][k] = fmaf(bj, z[k], S3r[j][k]);
+      }
+      const float a2 = fmaf(zi, 0.5f, s1);
+#pragma unroll
+      for (int j = 0; j < C; ++j) S2r[j] = fmaf(a2, z[j], S2r[j]);
+      s1 += zi;
+    }
+    float* e = ex + w * E;
+    e[i] = s1;
+#pragma unroll
+    for (int j = 0; j < C; ++j) e[C + i * C + j] = S2r[j];
+  }
+  __syncthreads();
+  if (w < nw) {
+    // log(1+S) level 3, row i:  S3 - (S1 (x) S2 + S2 (x) S1)/2 + S1^3/3
+    float* e = ex + w * E;
+    float S1v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) S1v[c] = e[c];
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+#pragma unroll
+      for (int k = 0; k < C; ++k) {
+        const float s2jk = e[C + j * C + k];
+        float v = S3r[j][k] - 0.5f * (s1 * s2jk + S2r[j] * S1v[k]);
+        v = fmaf((1.f / 3.f) * s1 * S1v[j], S1v[k], v);
+        e[C + C2 + (i * C + j) * C + k] = v;
+      }
+  }
+  __syncthreads();
+  if (w < nw) {  // level 2 of the log in place: S2 - S1 (x) S1 / 2 (all readers of S2 are done)
+    float* e = ex + w * E;
+    const float s1i = e[i];
+#pragma unroll
+    for (int j = 0; j < C; ++j) e[C + i * C + j] -= 0.5f * s1i * e[j];
+  }
+  // sparse t2l (CSR, a few KB) into shared memory: it is re-read for every window of the tile
+  const int D = p.D;
+  int* s_rowptr = reinterpret_cast<int*>(win + WT * p.stride);
+  const int nnz = pp.rowptr[D];
+  int* s_cols = s_rowptr + D + 1;
+  float* s_vals = reinterpret_cast<float*>(s_cols + nnz);
+  for (int t = threadIdx.x; t <= D; t += blockDim.x) s_rowptr[t] = pp.rowptr[t];
+  for (int t = threadIdx.x; t < nnz; t += blockDim.x) {
+    s_cols[t] = pp.cols[t] - 1;  // flat tensor index without the scalar slot
+    s_vals[t] = pp.vals[t];
+  }
+  __syncthreads();
+  // Hall projection: one thread per Hall row, looping over the windows of the tile; for a fixed
+  // window consecutive threads write consecutive floats
+  {
+    float* dst = p.out + ((size_t)b * p.K + k0) * D;
+    for (int h = threadIdx.x; h < D; h += blockDim.x) {
+      const int lo = s_rowptr[h], hi = s_rowptr[h + 1];
+      for (int w0 = 0; w0 < nw; w0 += 8) {  // 8 windows at a time: independent accumulators
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = lo; t < hi; ++t) {
+          const float v = s_vals[t];
+          const float* e = ex + w0 * E + s_cols[t];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = fmaf(v, e[u * E], acc[u]);  // windows beyond nw hold stale but finite data
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (w0 + u < nw) dst[(size_t)(w0 + u) * D + h] = acc[u];
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------
 // generic kernel: any width, depth <= 4, one warp per window.
 // ----------------------------------------------------------------------------
@@ -256,6 +398,7 @@ struct TensorParams {
   const float* vals;
   int B, L, C, s, q, r, K, D, depth, compat, chunk;
   int tdim;  // C + C^2 + ... + C^depth
+  int k_begin;  // only windows k >= k_begin are processed (the depth-3 kernel leaves the remainder here)
 };
 
 // read point m of the (virtual) window `k` of sample b.  Point 0 is the basepoint.
@@ -310,9 +453,11 @@ __global__ void __launch_bounds__(128) logsig_tensor_kernel(const TensorParams p
   for (int k = 2, pw = p.C; k <= 4; ++k, pw *= p.C) off[k] = off[k - 1] + pw;
   const int C = p.C;
 
-  const long long n_win = (long long)p.B * p.K;
-  for (long long wid = (long long)blockIdx.x * wpb + warp; wid < n_win; wid += (long long)gridDim.x * wpb) {
-    const int b = (int)(wid / p.K), k = (int)(wid - (long long)b * p.K);
+  const int nk = p.K - p.k_begin;
+  const long long n_win = (long long)p.B * nk;
+  for (long long wi = (long long)blockIdx.x * wpb + warp; wi < n_win; wi += (long long)gridDim.x * wpb) {
+    const int b = (int)(wi / nk), k = p.k_begin + (int)(wi - (long long)b * nk);
+    const long long wid = (long long)b * p.K + k;
     const float* xb = p.data + (size_t)b * p.L * C;
     const int n_inc = k < p.q ? p.s : (p.compat ? p.r + 1 : p.r);
     for (int e = lane; e < p.tdim; e += 32) S[e] = 0.f;
@@ -453,10 +598,45 @@ int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int 
   }
 
   if (!t2l_rowptr || !t2l_cols || !t2l_vals) return LNCDE_ERR_NULL;
+  bool d3_done = false;
+  if (depth == 3 && C >= 2 && C <= 8 && sC <= 640) {
+    D3Params dp;
+    LevyParams& lp = dp.lv;
+    lp.data = data; lp.out = logsig;
+    lp.B = B; lp.L = L; lp.s = s; lp.q = q; lp.r = r; lp.K = K; lp.D = D;
+    lp.compat = compat; lp.chunk = compat ? chunk : 1;
+    lp.stride = (int)(sC | 1);
+    lp.sc_magic = (uint32_t)((0x100000000ull + sC - 1) / sC);
+    lp.WT = 32;
+    lp.tiles = (q + 31) / 32;
+    dp.rowptr = t2l_rowptr; dp.cols = t2l_cols; dp.vals = t2l_vals;
+    const size_t E = (size_t)C + C * C + C * C * C;
+    const int nnz_h = lncde_hall_t2l_nnz(C, 3);
+    const size_t smem = (32 * E + C + (size_t)32 * lp.stride + (size_t)(D + 1) + 2 * (size_t)nnz_h + 4) * 4;
+    const int grid = B * lp.tiles;
+    auto go = [&](auto k) {
+      if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k<<<grid, 32 * C, smem, st>>>(dp);
+    };
+    switch (C) {
+      case 2: go(logsig_d3_kernel<2>); break;
+      case 3: go(logsig_d3_kernel<3>); break;
+      case 4: go(logsig_d3_kernel<4>); break;
+      case 5: go(logsig_d3_kernel<5>); break;
+      case 6: go(logsig_d3_kernel<6>); break;
+      case 7: go(logsig_d3_kernel<7>); break;
+      case 8: go(logsig_d3_kernel<8>); break;
+    }
+    const int e = (int)cudaGetLastError();
+    if (e != 0) return e;
+    if (r == 0) return 0;
+    d3_done = true;  // the remainder windows (one per sample) go through the generic kernel below
+  }
   TensorParams p;
   p.data = data; p.out = logsig;
   p.rowptr = t2l_rowptr; p.cols = t2l_cols; p.vals = t2l_vals;
   p.B = B; p.L = L; p.C = C; p.s = s; p.q = q; p.r = r; p.K = K; p.D = D; p.depth = depth;
+  p.k_begin = d3_done ? q : 0;
   p.compat = compat;
   p.chunk = compat ? chunk : 1;
   const long long tdim = lncde_tensor_dim(C, depth) - 1;
@@ -468,7 +648,7 @@ int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int 
   if (smem > 227 * 1024) return LNCDE_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(logsig_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  long long n_win = (long long)B * K;
+  long long n_win = (long long)B * (K - p.k_begin);
   long long grid = (n_win + wpb - 1) / wpb;
   if (grid > 148 * 64) grid = 148 * 64;
   logsig_tensor_kernel<<<(int)grid, wpb * 32, smem, st>>>(p);
