@@ -374,34 +374,32 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
   }
   __syncthreads();
   float o_r[2], u3_r[2];
-  // software pipeline: stage table entries one step ahead, logsig rows one stage ahead
-  int r2 = p.stage_row[1];
-  float s1 = p.stage_scale[0], s2 = p.stage_scale[1];
-  float lam_a = lambda_fetch<C>(ls + (size_t)p.stage_row[0] * p.D, D2);
-  for (int n = 0; n < p.n_steps; ++n) {
-    const int nn = n + 1 < p.n_steps ? n + 1 : n;
-    const int r1n = p.stage_row[2 * nn], r2n = p.stage_row[2 * nn + 1];
-    const float s1n = p.stage_scale[2 * nn], s2n = p.stage_scale[2 * nn + 1];
-    const float lam_b = lambda_fetch<C>(ls + (size_t)r2 * p.D, D2);
-    stage_forward<C, D2>(sb, cm, R, lam_a, o_r, u3_r);
-    if (SAVE) save_stage<C, D2>(sb, o_r, u3_r, p.ws, p.wsp, ((size_t)b * p.n_steps + n) * 2);
+  // ONE inlined stage body, looped over the 2*n_steps stages (keeps the loop inside the 32 KB
+  // instruction cache); stage table entries and logsig rows are fetched one stage ahead
+  const int n_stage = 2 * p.n_steps;
+  float sc = p.stage_scale[0];
+  float lam_c = lambda_fetch<C>(ls + (size_t)p.stage_row[0] * p.D, D2);
+  for (int sidx = 0; sidx < n_stage; ++sidx) {
+    const int nx = sidx + 1 < n_stage ? sidx + 1 : sidx;
+    const float sc_n = p.stage_scale[nx];
+    const float lam_n = lambda_fetch<C>(ls + (size_t)p.stage_row[nx] * p.D, D2);
+    stage_forward<C, D2>(sb, cm, R, lam_c, o_r, u3_r);
+    if (SAVE) save_stage<C, D2>(sb, o_r, u3_r, p.ws, p.wsp, (size_t)b * n_stage + sidx);
     if (tid < H) {
-      const float kk = s1 * field_value<C, D2>(sb, cm, tid);
-      cm[S::k1 + tid] = kk;
-      sb[S::yin + tid] = cm[S::ycur + tid] + kk;
+      const float gk = sc * field_value<C, D2>(sb, cm, tid);
+      if (!(sidx & 1)) {  // first Heun stage: k1, then evaluate at y + k1
+        cm[S::k1 + tid] = gk;
+        sb[S::yin + tid] = cm[S::ycur + tid] + gk;
+      } else {            // second stage: y_{n+1} = y_n + (k1 + k2) / 2
+        const float yn = cm[S::ycur + tid] + 0.5f * (cm[S::k1 + tid] + gk);
+        cm[S::ycur + tid] = yn;
+        sb[S::yin + tid] = yn;
+        ys[(size_t)((sidx >> 1) + 1) * H + tid] = yn;
+      }
     }
     __syncthreads();
-    lam_a = lambda_fetch<C>(ls + (size_t)r1n * p.D, D2);
-    stage_forward<C, D2>(sb, cm, R, lam_b, o_r, u3_r);
-    if (SAVE) save_stage<C, D2>(sb, o_r, u3_r, p.ws, p.wsp, ((size_t)b * p.n_steps + n) * 2 + 1);
-    if (tid < H) {
-      const float yn = cm[S::ycur + tid] + 0.5f * (cm[S::k1 + tid] + s2 * field_value<C, D2>(sb, cm, tid));
-      cm[S::ycur + tid] = yn;
-      sb[S::yin + tid] = yn;
-      ys[(size_t)(n + 1) * H + tid] = yn;
-    }
-    __syncthreads();
-    r2 = r2n; s1 = s1n; s2 = s2n;
+    sc = sc_n;
+    lam_c = lam_n;
   }
 }
 
