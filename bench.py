@@ -355,7 +355,10 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     alg_bytes = Bk * (4 * L * C + 4 * 1499 * 29)  # 677 436 B per sample
     ach = alg_bytes / (k1_ms * 1e-3) / 1e9
     res["roofline"] = {"kernel": "logsig_levy_kernel<7,depth2> (K1)", "bound": "hbm", "achieved": ach,
-                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                       # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed
+                       # ncu --set full capture profiles/r01_full_logsig_final.md (1.0525 GB + 0.2990 GB)
+                       "traffic": 1.3515e9,
                        "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs (burst copy)",
                        "launch_ms": k1_ms, "algorithmic_bytes_per_launch": alg_bytes,
                        "shape": f"B={Bk} x EigenWorms (L=17984, C=7, stepsize 12, depth 2): inputs 1.03 GB > L2"}
