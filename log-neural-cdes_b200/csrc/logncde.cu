@@ -263,7 +263,7 @@ struct RevBufs {
 // scale).  On exit rb.yout holds dLoss/d(stage input).  Vector pairs for the weight
 // gradient go to the workspace slot `slot`.
 template <int C>
-__device__ __forceinline__ void stage_reverse(const StageCtx& cx, float* buf, const StageLayout& L,
+__device__ __noinline__ void stage_reverse(const StageCtx& cx, float* buf, const StageLayout& L,
                                               const RevBufs& rb, const WsLayout& ws, float* wsp, size_t slot) {
   const MlpDesc& d = *cx.d;
   const int H = d.H, Wd = d.width, NL = d.n_hidden;

@@ -287,7 +287,7 @@ __device__ __forceinline__ void load_logsig_row(const StageCtx& cx, const float*
 // Evaluate the field at buf.yin.  On exit G[h] holds the (unscaled) field and all
 // intermediates needed by the reverse sweep are in `buf`.
 template <int C>
-__device__ __forceinline__ void stage_forward(const StageCtx& cx, float* buf, const StageLayout& L,
+__device__ __noinline__ void stage_forward(const StageCtx& cx, float* buf, const StageLayout& L,
                                               const float* __restrict__ ls_row) {
   const MlpDesc& d = *cx.d;
   const int H = d.H, Wd = d.width, NL = d.n_hidden;
