@@ -494,7 +494,8 @@ def main():
     args = ap.parse_args()
     WL.clear()
     WL.update(WORKLOADS[args.workload])
-    _watchdog(float(os.environ.get("LNCDE_BENCH_TIMEOUT", "900")))
+    # the default run finishes in ~40 s; never let a stuck collective hold N GPUs for long
+    _watchdog(float(os.environ.get("LNCDE_BENCH_TIMEOUT", "600" if args.impl == "reference" else "420")))
     if args.impl == "reference":
         run_reference(args)
     else:

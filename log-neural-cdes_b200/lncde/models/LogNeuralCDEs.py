@@ -109,12 +109,15 @@ class _LogNCDESolve(torch.autograd.Function):
 
 _WS = {}
 _WS_GEN = {}
+_RETIRED = []
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
     """Grow-only scratch buffer per device (the C ABI never allocates)."""
     cur = _WS.get(device)
     if cur is None or cur.numel() < nbytes:
+        if cur is not None:
+            _RETIRED.append(cur)  # a captured CUDA graph may still hold its address: never hand it back
         cur = torch.empty(max(nbytes, 1), device=device, dtype=torch.uint8)
         _WS[device] = cur
     return cur
