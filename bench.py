@@ -369,6 +369,21 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     # ---- per-kernel breakdown of the train step (CUDA events around each phase) -----------------
     res["step_breakdown_ms"] = breakdown(model, opt, x_dev, lab_dev)
     res["step_breakdown_ms"]["whole_step"] = ms_per_step
+    # The kernel that dominates the STEP is the adjoint sweep (+ its deferred gradient GEMMs).  It is bound
+    # by the latency of ~12 dependent phases per Heun stage, not by HBM or the tensor pipe:
+    # its FP32 rate is quoted against the NOMINAL FFMA peak (148 SM x 128 lanes x 2 x 1.965 GHz) for scale.
+    macs_stage = 98304                                  # restructured field, SURVEY.md 8d (C = 7)
+    n_stage = 2 * 1499
+    flop = 2.0 * (2 * macs_stage) * n_stage * WL["B"]   # transposed mat-vecs + weight-gradient outer products
+    t_ms = res["step_breakdown_ms"]["backward_K3b+gemm"]
+    ach = flop / (t_ms * 1e-3) / 1e12
+    res["roofline_dominant"] = {"kernel": "logncde_bwd_saved_kernel<7,depth2> + outer_gemm_kernel (K3b)",
+                                "bound": "latency (dependent phases), fp32 issue", "achieved": ach,
+                                "peak": 74.4, "unit": "TFLOP/s", "frac": ach / 74.4,
+                                "peak_source": "nominal FP32 FFMA peak (not in MEASURED_PEAKS.json)",
+                                "share_of_step": t_ms / ms_per_step,
+                                "us_per_stage": 1e3 * t_ms / n_stage,
+                                "algorithmic_flop_per_step": flop}
     # ---- CPU baseline ------------------------------------------------------------------------------
     if not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
