@@ -20,4 +20,11 @@ Pinning status
   0.7.0, equinox 0.12.2, optax 0.2.4, roughpy 0.2.0 semantics – all absent
   offline): PARITY UNPINNED by reference outputs; restated from the call sites
   cited in each function.
+
+Because those oracles cannot be pinned on reference outputs, each of them is
+cross-checked against a second, structurally different derivation of the same
+mathematics in ``tests/test_oracle_independent_checks.py`` (brute-force iterated
+integrals vs Chen/Horner, exp(log S) = S, BCH, Lie-element round trip, Lie
+brackets from explicit Jacobians vs the JVP formulation, hand-rolled Heun
+recurrence, bracket definition / commuting-field / chunked-scan identities).
 """
