@@ -460,7 +460,18 @@ def cpu_baseline(budget_s=20.0):
     t_step = float(np.median(times))
     scale_up = n_full / n_sub
     t_full = t_step * scale_up + t_logsig * (WL["L"] / Ls)
+    # logsig half of the metric on the CPU: the numpy oracle of calc_paths over the full-size batch
+    xf = synthetic_paths("EigenWorms", B, seed=2345)
+    OP.calc_paths(xf[:2], s, 2, np.float32)
+    t0 = time.perf_counter()
+    lsf = OP.calc_paths(xf, s, 2, np.float32)
+    t_ls = time.perf_counter() - t0
+    ls_gbs = (xf.nbytes + lsf.nbytes) / t_ls / 1e9
     return {"value": B / t_full, "unit": "samples/s", "cores": cores, "kind": "port",
+            "logsig": {"value": ls_gbs, "unit": "GB/s", "kind": "port",
+                       "sample": f"numpy oracle calc_paths (signax-style Chen/Horner, log, t2l) on the full B=32 x "
+                                 f"L=17984 x C=7 batch: {t_ls:.3f} s, same algorithmic bytes as the GPU roofline leg "
+                                 f"per sample"},
             "sample": f"oracle port (torch-CPU fp32, reference formulation 1+C JVPs, autograd adjoint) of the full "
                       f"B=32 batch truncated to the first {n_sub} of {n_full} Heun steps (L={Ls}); median of "
                       f"{len(times)} steps = {t_step:.3f} s, scaled x{scale_up:.1f} to the full path; numpy logsig "
