@@ -1,5 +1,5 @@
 """K1 roofline sweep (dev tool): GB/s of calc_paths at B=2048 x EigenWorms for a few shapes."""
-import os, sys, time
+import os, sys
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, R); sys.path.insert(0, os.path.join(R, "log-neural-cdes_b200"))
 import torch
