@@ -19,6 +19,7 @@
 
 #include "lncde_b200.h"
 #include "outer_gemm.cuh"
+#include "ptx.cuh"
 
 namespace lncde {
 
@@ -315,34 +316,6 @@ static bool scan_warp_dispatch(bool bwd, cudaStream_t cs, float* F, const float*
 // One CTA per sample.  The flows do not depend on the state, so they are streamed through a ring
 // of shared-memory stages by 1-D TMA bulk copies (cp.async.bulk + mbarrier, issued NS-1 steps
 // ahead by one thread); only the H-vector recurrence is on the dependent chain.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni WAIT_DONE;\n"
-      "bra.uni WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 constexpr int kBigThreads = 512;
 
 template <int NS>
@@ -360,7 +333,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) scan_fwd_tma_kernel(const floa
   float* yb = ys + (size_t)b * T * H;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbar_init();
   }
   for (int h = tid; h < H; h += kBigThreads) {
     const float v = y0[(size_t)b * H + h];
@@ -453,7 +426,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) scan_bwd_tma_kernel(float* __r
   const float* gb = g_ys + (size_t)b * T * H;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbar_init();
   }
   for (int h = tid; h < H; h += kBigThreads) {
     lamb[h] = gb[(size_t)(T - 1) * H + h];

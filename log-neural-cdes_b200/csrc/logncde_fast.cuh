@@ -26,6 +26,8 @@
 
 #include <cstdint>
 
+#include "ptx.cuh"
+
 namespace lncde {
 namespace fast {
 
@@ -675,13 +677,6 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
 // no recomputation - one reverse stage per Heun stage, walking the slots backwards.  The z/s/u
 // vectors of the next slot are staged with cp.async into the other half of a double buffer and
 // the per-lane o / u3 values are prefetched into registers while the current stage runs.
-__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 template <int C, bool D2>
 __device__ __forceinline__ void fetch_saved(float* sb, const WsLayout& ws, const float* __restrict__ wsp,
                                             size_t slot) {

@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "lncde_b200.h"
+#include "ptx.cuh"
 
 namespace lncde {
 
@@ -33,19 +34,6 @@ namespace lncde {
 // rows L-r-1 .. L-1 (its true predecessor first) and, in compat mode, one more
 // leading point: the last row of the previous sample (generate_paths.py:59).
 // ----------------------------------------------------------------------------
-
-__device__ __forceinline__ float ld_stream(const float* p) {
-  float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ float4 ld_stream4(const float4* p) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p));
-  return v;
-}
 
 template <int C, bool DEPTH2>
 struct LevyState {

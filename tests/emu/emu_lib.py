@@ -1,0 +1,142 @@
+"""numpy/ctypes binding of the HOST-EMULATED kernel library (tests only, see cuda_emu.h).
+
+"Device pointers" are plain host pointers here; every wrapper mirrors the call the product
+binding (lncde/*.py over liblncde_b200.so) makes, so the same kernel source is exercised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import build_emu  # noqa: E402
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build_emu.build())
+        i, u, vp, sz = C.c_int, C.c_uint, C.c_void_p, C.c_size_t
+        _lib.lncde_logsig_fwd.argtypes = [vp, vp, vp, i, i, i, i, i, u, i, vp, vp, vp]
+        _lib.lncde_hall_size.argtypes = [i, i]
+        _lib.lncde_hall_t2l_nnz.argtypes = [i, i]
+        _lib.lncde_hall_t2l_csr.argtypes = [i, i, vp, vp, vp]
+        _lib.lncde_logsig_num_windows.argtypes = [i, i]
+        _lib.lncde_logncde_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz]
+        _lib.lncde_logncde_bwd_workspace_bytes.argtypes = [i, i, i, i, i, i, i]
+        _lib.lncde_logncde_bwd_workspace_bytes.restype = sz
+        _lib.lncde_logncde_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz, u]
+        _lib.lncde_linear_scan_workspace_bytes.argtypes = [i, i, i, i, i]
+        _lib.lncde_linear_scan_workspace_bytes.restype = sz
+        _lib.lncde_linear_scan_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]
+        _lib.lncde_linear_scan_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]
+        _lib.lncde_adam_step.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, i,
+                                         C.c_float]
+    return _lib
+
+
+def _p(a):
+    return C.c_void_p(0 if a is None else a.ctypes.data)
+
+
+def _aligned(nbytes, align=256):
+    raw = np.zeros(nbytes + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off : off + nbytes]
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def calc_paths(x, stepsize, depth, compat=True, chunk=None):
+    L = lib()
+    x = f32(x)
+    B, Ln, Cn = x.shape
+    K = L.lncde_logsig_num_windows(Ln, int(stepsize))
+    D = L.lncde_hall_size(Cn, depth)
+    nnz = L.lncde_hall_t2l_nnz(Cn, depth)
+    rowptr = np.zeros(D + 1, np.int32)
+    cols = np.zeros(nnz, np.int32)
+    vals = np.zeros(nnz, np.float32)
+    assert L.lncde_hall_t2l_csr(Cn, depth, _p(rowptr), _p(cols), _p(vals)) == 0
+    # canary rows either side of the output catch out-of-bounds global writes
+    buf = np.full((B * K * D + 64,), np.float32(12345.0))
+    out = buf[32 : 32 + B * K * D].reshape(B, K, D)
+    out[...] = np.nan
+    st = L.lncde_logsig_fwd(None, _p(x), _p(out), B, Ln, Cn, int(stepsize), depth, 1 if compat else 0,
+                            int(chunk or B), _p(rowptr), _p(cols), _p(vals))
+    assert st == 0, st
+    assert np.all(buf[:32] == 12345.0) and np.all(buf[32 + B * K * D :] == 12345.0), "global write out of bounds"
+    return out.copy()
+
+
+def logncde_fwd_bwd(flat, logsig, y0, rows, scale, dims, g_ys, train=True):
+    """lncde_logncde_fwd (+ bwd with the saved-forward workspace when train)."""
+    L = lib()
+    H, Cn, width, n_hidden, depth = dims
+    flat, logsig, y0, scale = f32(flat), f32(logsig), f32(y0), f32(scale)
+    rows = np.ascontiguousarray(rows, np.int32)
+    B, K, D = logsig.shape
+    n_steps = rows.shape[0]  # rows / scale are [n_steps, 2]
+    ys = np.full((B, n_steps + 1, H), np.nan, np.float32)
+    nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, Cn, width, n_hidden, depth, n_steps) if train else 0
+    ws = _aligned(nbytes) if train else None
+    st = L.lncde_logncde_fwd(None, _p(flat), _p(logsig), _p(y0), _p(rows), _p(scale), _p(ys), B, K, D, H, Cn, width,
+                             n_hidden, depth, n_steps, _p(ws), nbytes)
+    assert st == 0, st
+    if not train:
+        return ys, None, None
+    g_ys = f32(g_ys)
+    g_params = np.full(flat.shape, np.nan, np.float32)
+    g_y0 = np.full((B, H), np.nan, np.float32)
+    st = L.lncde_logncde_bwd(None, _p(flat), _p(logsig), _p(rows), _p(scale), _p(ys), _p(g_ys), _p(g_params),
+                             _p(g_y0), B, K, D, H, Cn, width, n_hidden, depth, n_steps, _p(ws), nbytes, 2)
+    assert st == 0, st
+    return ys, g_params, g_y0
+
+
+def logncde_bwd_recompute(flat, logsig, ys, rows, scale, dims, g_ys):
+    """lncde_logncde_bwd without LNCDE_FLAG_SAVED_FWD (recomputing adjoint)."""
+    L = lib()
+    H, Cn, width, n_hidden, depth = dims
+    flat, logsig, ys, scale, g_ys = f32(flat), f32(logsig), f32(ys), f32(scale), f32(g_ys)
+    rows = np.ascontiguousarray(rows, np.int32)
+    B, K, D = logsig.shape
+    n_steps = rows.shape[0]
+    nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, Cn, width, n_hidden, depth, n_steps)
+    ws = _aligned(nbytes)
+    g_params = np.full(flat.shape, np.nan, np.float32)
+    g_y0 = np.full((B, H), np.nan, np.float32)
+    st = L.lncde_logncde_bwd(None, _p(flat), _p(logsig), _p(rows), _p(scale), _p(ys), _p(g_ys), _p(g_params),
+                             _p(g_y0), B, K, D, H, Cn, width, n_hidden, depth, n_steps, _p(ws), nbytes, 0)
+    assert st == 0, st
+    return g_params, g_y0
+
+
+def linear_scan(lie, logsig, y0, nb, bs, g_ys=None):
+    """lncde_linear_scan_fwd (+ bwd).  lie [nb,bs,bs,n_basis]."""
+    L = lib()
+    lie, logsig, y0 = f32(lie), f32(logsig), f32(y0)
+    B, T, D = logsig.shape
+    n_basis = lie.shape[-1]
+    H = nb * bs
+    nbytes = L.lncde_linear_scan_workspace_bytes(B, T, nb, bs, n_basis)
+    ws = _aligned(nbytes)
+    ys = np.full((B, T, H), np.nan, np.float32)
+    st = L.lncde_linear_scan_fwd(None, _p(lie), _p(logsig), _p(y0), _p(ys), B, T, D, nb, bs, n_basis, _p(ws), nbytes)
+    assert st == 0, st
+    if g_ys is None:
+        return ys, None, None
+    g_ys = f32(g_ys)
+    g_lie = np.full(lie.shape, np.nan, np.float32)
+    g_y0 = np.full((B, H), np.nan, np.float32)
+    st = L.lncde_linear_scan_bwd(None, _p(lie), _p(logsig), _p(ys), _p(g_ys), _p(g_lie), _p(g_y0), B, T, D, nb, bs,
+                                 n_basis, _p(ws), nbytes)
+    assert st == 0, st
+    return ys, g_lie, g_y0

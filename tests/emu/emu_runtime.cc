@@ -1,0 +1,364 @@
+// Runtime of the host CUDA emulator (see cuda_emu.h): fibers, barriers, warp collectives,
+// mbarrier / bulk-copy bookkeeping and the few cudart entry points the host wrappers call.
+#include <sys/mman.h>
+
+#include <map>
+#include <vector>
+
+#include "cuda_emu.h"
+
+// Minimal cooperative context switch (callee-saved registers + stack pointer).  glibc's
+// swapcontext makes a signal-mask system call per switch, which dominated the run time.
+#if !defined(__x86_64__)
+#error "the CUDA host emulator's context switch is written for x86-64"
+#endif
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
+
+namespace emu {
+
+Idx g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+
+namespace {
+
+constexpr size_t kStack = 512 * 1024;
+constexpr size_t kCanary = 256;  // bytes either side of dynamic shared memory
+constexpr unsigned char kCanaryByte = 0xA5;
+
+enum Wait { RUN = 0, BAR, WARP, MBAR, DONE };
+
+struct Fiber {
+  void* sp = nullptr;
+  Wait wait = RUN;
+  long gen = 0;        // generation being waited for (BAR / WARP)
+  void* mbar = nullptr;
+  unsigned parity = 0;
+};
+
+struct Warp {
+  unsigned arrived = 0, mask = 0;
+  long gen = 0;
+  uint64_t slot[32];
+  uint64_t snap[2][32];
+};
+
+struct MBar {
+  unsigned count = 0;   // arrivals per phase
+  int pending = 0;      // arrivals still missing in the current phase
+  long long tx = 0;     // outstanding transaction bytes
+  unsigned phase = 0;
+};
+
+struct Block {
+  int n = 0, live = 0, cur = 0;
+  std::vector<Fiber> fib;
+  std::vector<Warp> warps;
+  void* sched_sp = nullptr;
+  int bar_arrived = 0;
+  long bar_gen = 0;
+  std::map<void*, MBar> mbars;
+  unsigned char* smem_raw = nullptr;
+  size_t smem_bytes = 0;
+  const std::function<void()>* body = nullptr;
+  dim3 bdim;
+};
+
+Block* g_blk = nullptr;
+char* g_stacks = nullptr;
+size_t g_stack_cap = 0;
+std::map<const void*, int> g_max_dyn_smem;
+int g_last_error = 0;
+
+[[noreturn]] void die(const char* msg) {
+  std::fprintf(stderr, "cuda-emu: %s (block %u,%u,%u thread %u)\n", msg, g_blockIdx.x, g_blockIdx.y, g_blockIdx.z,
+               g_blk ? (unsigned)g_blk->cur : 0u);
+  std::abort();
+}
+
+void set_thread(Block& b, int t) {
+  b.cur = t;
+  g_threadIdx.x = t % b.bdim.x;
+  g_threadIdx.y = (t / b.bdim.x) % b.bdim.y;
+  g_threadIdx.z = t / (b.bdim.x * b.bdim.y);
+}
+
+void yield() {
+  Block& b = *g_blk;
+  emu_switch(&b.fib[b.cur].sp, b.sched_sp);
+}
+
+void trampoline() {
+  Block& b = *g_blk;
+  (*b.body)();
+  b.fib[b.cur].wait = DONE;
+  emu_switch(&b.fib[b.cur].sp, b.sched_sp);
+  std::abort();  // a finished fiber is never resumed
+}
+
+bool runnable(Block& b, int t) {
+  Fiber& f = b.fib[t];
+  switch (f.wait) {
+    case RUN: return true;
+    case BAR: return b.bar_gen > f.gen;
+    case WARP: return b.warps[t >> 5].gen > f.gen;
+    case MBAR: return b.mbars[f.mbar].phase != f.parity;
+    case DONE: return false;
+  }
+  return false;
+}
+
+unsigned live_mask(Block& b, int warp) {
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) {
+    const int t = warp * 32 + l;
+    if (t < b.n && b.fib[t].wait != DONE) m |= 1u << l;
+  }
+  return m;
+}
+
+void complete_warp(Warp& w) {
+  std::memcpy(w.snap[w.gen & 1], w.slot, sizeof(w.slot));
+  w.arrived = 0;
+  w.gen++;
+}
+
+void run_block(Block& b) {
+  for (int t = 0; t < b.n; ++t) {
+    Fiber& f = b.fib[t];
+    f.wait = RUN;
+    // initial frame: six callee-saved registers, then `ret` into trampoline with the stack
+    // 8 mod 16 as after a call
+    uintptr_t top = ((uintptr_t)(g_stacks + (size_t)(t + 1) * kStack)) & ~(uintptr_t)15;
+    void** sp = (void**)top;
+    *--sp = nullptr;                 // fake return address of trampoline
+    *--sp = (void*)&trampoline;
+    for (int r = 0; r < 6; ++r) *--sp = nullptr;
+    f.sp = sp;
+  }
+  b.live = b.n;
+  while (b.live > 0) {
+    bool progress = false;
+    for (int t = 0; t < b.n; ++t) {
+      if (!runnable(b, t)) continue;
+      b.fib[t].wait = RUN;
+      set_thread(b, t);
+      emu_switch(&b.sched_sp, b.fib[t].sp);
+      progress = true;
+      if (b.fib[t].wait == DONE) {
+        b.live--;
+        // exited threads no longer count towards barriers / warp collectives
+        if (b.bar_arrived > 0 && b.bar_arrived == b.live) {
+          b.bar_arrived = 0;
+          b.bar_gen++;
+        }
+        Warp& w = b.warps[t >> 5];
+        const unsigned need = w.mask & live_mask(b, t >> 5);
+        if (w.arrived != 0 && (w.arrived & need) == need) complete_warp(w);
+      }
+    }
+    if (!progress) die("deadlock: no runnable thread (mismatched __syncthreads / collective / mbarrier wait)");
+  }
+}
+
+}  // namespace
+
+void* dyn_smem() { return g_blk->smem_raw + kCanary; }
+
+bool in_dyn_smem(const void* p, size_t bytes) {
+  const unsigned char* q = (const unsigned char*)p;
+  const unsigned char* lo = g_blk->smem_raw + kCanary;
+  return q >= lo && q + bytes <= lo + g_blk->smem_bytes;
+}
+
+void sync_threads() {
+  Block& b = *g_blk;
+  Fiber& f = b.fib[b.cur];
+  const long my = b.bar_gen;
+  if (++b.bar_arrived == b.live) {
+    b.bar_arrived = 0;
+    b.bar_gen++;
+    return;
+  }
+  f.wait = BAR;
+  f.gen = my;
+  yield();
+}
+
+const uint64_t* warp_exchange(unsigned mask, uint64_t v) {
+  Block& b = *g_blk;
+  const int t = b.cur, wi = t >> 5, lane = t & 31;
+  Warp& w = b.warps[wi];
+  if (!((mask >> lane) & 1u)) die("warp collective: calling lane is not in its own mask");
+  if (w.arrived == 0) w.mask = mask;
+  else if (w.mask != mask) die("warp collective: lanes of one warp passed different masks");
+  if ((w.arrived >> lane) & 1u) die("warp collective: lane arrived twice");
+  w.slot[lane] = v;
+  w.arrived |= 1u << lane;
+  const long my = w.gen;
+  const unsigned need = mask & live_mask(b, wi);
+  if ((w.arrived & need) == need) {
+    complete_warp(w);
+  } else {
+    Fiber& f = b.fib[t];
+    f.wait = WARP;
+    f.gen = my;
+    yield();
+  }
+  return w.snap[my & 1];
+}
+
+void mbar_init(void* bar, unsigned count) {
+  if (!in_dyn_smem(bar, 8) || ((uintptr_t)bar & 7)) die("mbarrier.init: not an 8-byte aligned shared-memory address");
+  MBar& m = g_blk->mbars[bar];
+  m.count = count;
+  m.pending = (int)count;
+  m.tx = 0;
+  m.phase = 0;
+}
+static void mbar_maybe_complete(MBar& m) {
+  if (m.pending == 0 && m.tx == 0) {
+    m.phase ^= 1u;
+    m.pending = (int)m.count;
+  }
+}
+void mbar_expect_tx(void* bar, unsigned bytes) {
+  auto it = g_blk->mbars.find(bar);
+  if (it == g_blk->mbars.end()) die("mbarrier.arrive.expect_tx on an uninitialised barrier");
+  MBar& m = it->second;
+  if (m.pending <= 0) die("mbarrier: more arrivals than the initialised count");
+  m.tx += bytes;
+  m.pending--;
+  mbar_maybe_complete(m);
+}
+void mbar_complete_tx(void* bar, unsigned bytes) {
+  auto it = g_blk->mbars.find(bar);
+  if (it == g_blk->mbars.end()) die("bulk copy signals an uninitialised mbarrier");
+  MBar& m = it->second;
+  m.tx -= bytes;
+  mbar_maybe_complete(m);
+}
+void mbar_wait(void* bar, unsigned parity) {
+  Block& b = *g_blk;
+  auto it = b.mbars.find(bar);
+  if (it == b.mbars.end()) die("mbarrier.try_wait on an uninitialised barrier");
+  if (it->second.phase != (parity & 1u)) return;
+  Fiber& f = b.fib[b.cur];
+  f.wait = MBAR;
+  f.mbar = bar;
+  f.parity = parity & 1u;
+  yield();
+}
+void check_bulk(const void* smem_ptr, const void* gptr, unsigned bytes, const char* what) {
+  if (bytes == 0 || (bytes & 15u)) die((std::string(what) + ": size is not a positive multiple of 16 bytes").c_str());
+  if ((uintptr_t)smem_ptr & 15u) die((std::string(what) + ": shared-memory address not 16-byte aligned").c_str());
+  if ((uintptr_t)gptr & 15u) die((std::string(what) + ": global address not 16-byte aligned").c_str());
+  if (!in_dyn_smem(smem_ptr, bytes)) die((std::string(what) + ": shared-memory range outside the CTA's allocation").c_str());
+}
+
+void launch(const void* func, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
+  const size_t n = (size_t)block.x * block.y * block.z;
+  if (n == 0 || n > 1024 || (size_t)grid.x * grid.y * grid.z == 0) {
+    g_last_error = (int)cudaErrorInvalidConfiguration;
+    return;
+  }
+  int allowed = 48 * 1024;
+  auto it = g_max_dyn_smem.find(func);
+  if (it != g_max_dyn_smem.end()) allowed = it->second;
+  if (smem > (size_t)allowed || smem > 227 * 1024) {
+    std::fprintf(stderr, "cuda-emu: launch with %zu B dynamic shared memory (allowed %d)\n", smem, allowed);
+    g_last_error = (int)cudaErrorInvalidValue;
+    return;
+  }
+  if (g_stack_cap < n) {
+    if (g_stacks) munmap(g_stacks, g_stack_cap * kStack);
+    g_stacks = (char*)mmap(nullptr, n * kStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (g_stacks == MAP_FAILED) {
+      std::perror("cuda-emu mmap");
+      std::abort();
+    }
+    g_stack_cap = n;
+  }
+  Block b;
+  b.n = (int)n;
+  b.bdim = block;
+  b.fib.resize(n);
+  b.warps.resize((n + 31) / 32);
+  b.body = &body;
+  b.smem_bytes = smem;
+  std::vector<unsigned char> raw(smem + 2 * kCanary + 128);
+  // 128-byte aligned start like the hardware window
+  unsigned char* base = raw.data();
+  base += (128 - ((uintptr_t)(base + kCanary) & 127)) & 127;
+  b.smem_raw = base;
+  g_blockDim = {block.x, block.y, block.z};
+  g_gridDim = {grid.x, grid.y, grid.z};
+  Block* saved = g_blk;
+  g_blk = &b;
+  for (unsigned z = 0; z < grid.z; ++z)
+    for (unsigned y = 0; y < grid.y; ++y)
+      for (unsigned x = 0; x < grid.x; ++x) {
+        g_blockIdx = {x, y, z};
+        std::memset(base, kCanaryByte, kCanary);
+        std::memset(base + kCanary, 0xFF, smem);  // uninitialised shared memory reads as NaN
+        std::memset(base + kCanary + smem, kCanaryByte, kCanary);
+        b.bar_arrived = 0;
+        b.mbars.clear();
+        for (auto& w : b.warps) w = Warp();
+        run_block(b);
+        for (size_t i = 0; i < kCanary; ++i)
+          if (base[i] != kCanaryByte || base[kCanary + smem + i] != kCanaryByte)
+            die("dynamic shared memory written out of bounds");
+      }
+  g_blk = saved;
+}
+
+}  // namespace emu
+
+// ---- the cudart entry points used by the host wrappers ----------------------------------------
+extern "C" {
+cudaError_t cudaFuncSetAttribute(const void* func, cudaFuncAttribute attr, int value) {
+  if (attr == cudaFuncAttributeMaxDynamicSharedMemorySize) {
+    if (value > 227 * 1024) return cudaErrorInvalidValue;
+    emu::g_max_dyn_smem[func] = value;
+  }
+  return cudaSuccess;
+}
+cudaError_t cudaGetLastError(void) {
+  const int e = emu::g_last_error;
+  emu::g_last_error = 0;
+  return (cudaError_t)e;
+}
+cudaError_t cudaPeekAtLastError(void) { return (cudaError_t)emu::g_last_error; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cuda-emu error"; }
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+  std::memset(p, v, n);
+  return cudaSuccess;
+}
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) {
+  std::memmove(d, s, n);
+  return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+}

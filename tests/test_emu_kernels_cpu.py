@@ -1,0 +1,158 @@
+"""The CUDA kernel SOURCES executed on the CPU by the host emulator (tests/emu) and compared with the
+oracle - so that `-m "not gpu"` checks the real kernel code, not only the host logic.  The GPU
+parity tests (`-m gpu`, through liblncde_b200.so) remain the gate for the compiled product; this
+file catches indexing / barrier / alignment mistakes before GPU time is spent on them."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import linear_ncde as OL
+from oracle import log_ncde as O
+from oracle import paths
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu_lib as E  # noqa: E402
+
+TOL = 1e-5
+
+
+def _toy(B, L, C, seed=1234):
+    rng = np.random.default_rng(seed)
+    return np.cumsum(np.round(rng.normal(size=(B, L, C))), axis=1).astype(np.float32)
+
+
+def _walk(B, L, C, seed=2345):
+    rng = np.random.default_rng(seed)
+    return np.cumsum(rng.normal(scale=0.05, size=(B, L, C)), axis=1).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("C", [1, 2, 3, 6, 7, 8])
+@pytest.mark.parametrize("depth", [1, 2])
+def test_emu_logsig_integer_kat_bit_exact(C, depth):
+    x = _toy(5, 100, C)
+    for s in (1, 4, 7, 12, 100, 101, 500):
+        want = paths.calc_paths(x, s, depth, np.float64)
+        got = E.calc_paths(x, s, depth)
+        assert got.shape == want.shape
+        assert np.array_equal(got.astype(np.float64), want), (C, depth, s)
+
+
+@pytest.mark.parametrize("compat", [True, False])
+def test_emu_logsig_compat_and_chunk(compat):
+    x = _toy(140, 30, 3)
+    want = paths.batch_calc_paths(x, 4, 2, np.float64, compat=compat)
+    got = E.calc_paths(x, 4, 2, compat=compat, chunk=128)
+    assert np.array_equal(got.astype(np.float64), want)
+
+
+@pytest.mark.parametrize("C,s,L", [(7, 12, 1200), (6, 12, 1190), (6, 16, 896), (7, 10, 999), (4, 10, 503), (5, 3, 1000)])
+def test_emu_logsig_float_paths_depth2(C, s, L):
+    x = _walk(3, L, C)
+    want = paths.calc_paths(x, s, 2, np.float64)
+    got = E.calc_paths(x, s, 2)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < TOL
+
+
+@pytest.mark.parametrize("C,depth", [(2, 3), (3, 3), (7, 3), (2, 4), (3, 4), (10, 2), (9, 1)])
+def test_emu_logsig_tensor_kernels(C, depth):
+    x = _toy(3, 50, C)
+    for s in (4, 12, 51):
+        want = paths.calc_paths(x, s, depth, np.float64)
+        assert rel_err(E.calc_paths(x, s, depth), want) < TOL, (C, depth, s)
+    xf = _walk(2, 200, C)
+    assert rel_err(E.calc_paths(xf, 12, depth), paths.calc_paths(xf, 12, depth, np.float64)) < TOL
+
+
+# ------------------------------------------------------------------------------------------ K3 / K3b
+def _setup(B, L, C, s, depth, H, width, n_hidden, dt0, scale, seed=0):
+    rng = np.random.default_rng(seed)
+    x = np.cumsum(rng.normal(scale=0.3, size=(B, L, C)), axis=1).astype(np.float32)
+    logsig = paths.calc_paths(x, s, depth, np.float64)
+    ts = paths.make_ts(L)
+    iv = paths.make_intervals(ts, s)
+    rows, sc, grid = O.stage_table(ts, iv, dt0, logsig.shape[1])
+    layers = O.init_params(H, C, width, n_hidden, scale=scale, seed=seed, dtype=torch.float64)
+    y0 = torch.from_numpy(rng.normal(size=(B, H)) * 0.5)
+    return logsig, rows, sc, grid, layers, y0
+
+
+def _oracle(layers, logsig, y0, rows, sc, dims, g_ys):
+    H, C, width, n_hidden, depth = dims
+    lay = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in layers]
+    y0o = y0.clone().requires_grad_(True)
+    ys = O.solve(lay, torch.from_numpy(logsig), y0o, rows, sc, C, H, depth)
+    (ys * g_ys).sum().backward()
+    gflat = torch.cat([t.grad.reshape(-1) for W, b in lay for t in (W, b)])
+    return ys.detach().numpy(), gflat.numpy(), y0o.grad.numpy()
+
+
+SOLVE_CASES = [
+    # B, L,  C, s, depth, H, width, n_hidden, dt0, scale
+    (2, 40, 3, 4, 2, 16, 8, 2, 0.05, 1.0),        # generic kernels
+    (2, 40, 3, 4, 1, 16, 8, 2, 0.05, 1.0),
+    (1, 36, 5, 3, 2, 24, 12, 3, 0.031, 2.0),
+    (2, 96, 7, 12, 2, 128, 32, 2, 0.11, 3.0),     # EigenWorms dims: specialised register-tile kernels
+    (1, 96, 6, 12, 2, 128, 32, 2, 0.11, 3.0),
+    (1, 96, 4, 12, 2, 128, 32, 2, 0.11, 3.0),
+    (1, 96, 7, 12, 1, 128, 32, 2, 0.11, 3.0),
+    (1, 40, 6, 4, 2, 64, 128, 3, 0.1, 4.0),       # toy dims: weights partly streamed from global
+    (1, 50, 7, 10, 2, 128, 64, 3, 0.2, 4.0),      # PPG dims
+]
+
+
+@pytest.mark.parametrize("case", SOLVE_CASES)
+def test_emu_logncde_forward_and_adjoint(case):
+    B, L, C, s, depth, H, width, n_hidden, dt0, scale = case
+    logsig, rows, sc, grid, layers, y0 = _setup(B, L, C, s, depth, H, width, n_hidden, dt0, scale)
+    dims = (H, C, width, n_hidden, depth)
+    g_ys = torch.from_numpy(np.random.default_rng(1).normal(size=(B, len(grid), H)))
+    flat = O.flatten_params(layers).numpy()
+    ys_o, gp_o, gy_o = _oracle(layers, logsig, y0, rows, sc, dims, g_ys)
+    # training-mode forward (saves its intermediates) + saved-mode adjoint
+    ys_e, gp_e, gy_e = E.logncde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, dims, g_ys.numpy())
+    assert rel_err(ys_e, ys_o) < TOL
+    assert rel_err(gy_e, gy_o) < 5 * TOL
+    off = 0
+    sizes = O.mlp_sizes(H, C, width, n_hidden)
+    for i, o in zip(sizes[:-1], sizes[1:]):
+        for n in (o * i, o):
+            assert rel_err(gp_e[off : off + n], gp_o[off : off + n]) < 5 * TOL, (case, off)
+            off += n
+    # inference-mode forward and the recomputing adjoint agree with the saved-mode pair
+    ys_i, _, _ = E.logncde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, dims, None, train=False)
+    assert np.array_equal(ys_i, ys_e)
+    gp_r, gy_r = E.logncde_bwd_recompute(flat, logsig, ys_e, rows, sc, dims, g_ys.numpy())
+    assert rel_err(gy_r, gy_o) < 5 * TOL
+    assert rel_err(gp_r, gp_o) < 5 * TOL
+
+
+# ------------------------------------------------------------------------------------------ K2
+@pytest.mark.parametrize("nb,bs,T,n_basis", [(16, 1, 40, 3), (8, 4, 33, 6), (4, 8, 20, 6), (2, 32, 12, 3),
+                                             (1, 64, 9, 6), (3, 5, 14, 3)])
+def test_emu_linear_scan_forward_and_adjoint(nb, bs, T, n_basis):
+    rng = np.random.default_rng(3)
+    B, H = 2, nb * bs
+    D = n_basis + 1
+    lie = rng.normal(size=(nb, bs, bs, n_basis)) * 0.3
+    ls = rng.normal(size=(B, T, D)) * 0.2
+    ls[..., 0] = 0
+    y0 = rng.normal(size=(B, H))
+    g_ys = rng.normal(size=(B, T, H))
+    lie_t = torch.from_numpy(lie).requires_grad_(True)
+    y0_t = torch.from_numpy(y0).requires_grad_(True)
+    flows = torch.einsum("nijl,btl->btnij", lie_t, torch.from_numpy(ls[..., 1:])) + torch.eye(bs, dtype=torch.float64)
+    ys = [y0_t]
+    for t in range(1, T):  # flow 0 is never applied (quirk B4)
+        ys.append(torch.einsum("bnij,bnj->bni", flows[:, t], ys[-1].view(B, nb, bs)).reshape(B, H))
+    ys_o = torch.stack(ys, 1)
+    (ys_o * torch.from_numpy(g_ys)).sum().backward()
+    ys_e, gl_e, gy_e = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
+    assert rel_err(ys_e, ys_o.detach().numpy()) < TOL
+    assert rel_err(gy_e, y0_t.grad.numpy()) < 5 * TOL
+    assert rel_err(gl_e, lie_t.grad.numpy()) < 5 * TOL
