@@ -384,10 +384,30 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
                                 "share_of_step": t_ms / ms_per_step,
                                 "us_per_stage": 1e3 * t_ms / n_stage,
                                 "algorithmic_flop_per_step": flop}
+    # ---- K1 variants (not the default path): parity + timing in a subprocess, so that a variant which
+    # has not been on hardware yet cannot take this process down; errors are reported, not raised
+    if not args.no_variants and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        res["k1_variants"] = k1_variants(pk)
     # ---- CPU baseline ------------------------------------------------------------------------------
     if not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     return res
+
+
+def k1_variants(pk):
+    """scripts/k1_variant_check.py: logsig_levy_tma_kernel (bulk-copy staging) vs the classic kernel."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "k1_variant_check.py")],
+                           capture_output=True, text=True, timeout=150)
+        if r.returncode != 0:
+            return {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+        for k in ("classic", "tma"):
+            if k in out.get("timing", {}):
+                out["timing"][k]["frac_of_hbm_peak"] = out["timing"][k]["GB/s"] / pk["hbm_gbs"]
+        return out
+    except Exception as e:  # timeout, unparsable output
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def breakdown(model, opt, x_dev, lab_dev):
@@ -519,6 +539,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--workload", default="eigenworms_logncde", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
+    ap.add_argument("--no-variants", action="store_true", help="skip the K1 kernel-variant leg (subprocess)")
     args = ap.parse_args()
     WL.clear()
     WL.update(WORKLOADS[args.workload])

@@ -37,6 +37,7 @@ extern "C" {
 /* flags */
 #define LNCDE_FLAG_COMPAT 1u    /* reproduce reference quirks */
 #define LNCDE_FLAG_SAVED_FWD 2u /* lncde_logncde_bwd: workspace was filled by lncde_logncde_fwd */
+#define LNCDE_FLAG_K1_TMA 4u    /* lncde_logsig_fwd: closed-form kernel variant that moves its tiles with TMA bulk copies */
 
 const char* lncde_version(void);
 /* Human-readable text for a status returned by any entry point. */

@@ -243,6 +243,174 @@ __global__ void __launch_bounds__(128) logsig_levy_kernel(const LevyParams p) {
 
 
 // ----------------------------------------------------------------------------
+// logsig_levy_tma_kernel<C, DEPTH2>: same closed form and the same LevyState arithmetic as
+// logsig_levy_kernel (bit-identical results), with the data movement handed to the TMA unit:
+//   * the tile's input slab (32 windows of one sample, contiguous in global memory) arrives in
+//     shared memory with ONE 1-D bulk copy (cp.async.bulk + mbarrier) issued by lane 0, instead of
+//     ~85 scalar shared-memory stores per window plus their index arithmetic (40 % of the
+//     instructions of the kernel above; ncu: issue slots were the co-limiter at 64 % of HBM);
+//   * when s*C is a multiple of 4 every window of the tile has the same 16-byte phase SH, so a
+//     thread walks its window with 128-bit shared loads at compile-time register offsets
+//     (template on SH); window stride s*C/4 chunks: conflict-free when odd, at most 2-/4-way
+//     otherwise, which still leaves the shared-memory pipe far below the HBM time of a tile;
+//     other strides walk with scalar loads on the same unpadded tile;
+//   * the 32 x D result rows leave through one bulk store of the 16-byte aligned body
+//     (cp.async.bulk.global.shared::cta) plus <= 3 head / tail floats.
+// Single-warp CTAs: the only synchronisation is __syncwarp and the mbarrier wait.
+// ----------------------------------------------------------------------------
+constexpr int kLevyPad = 16;  // floats in front of the bulk-copied slab: room for the two zero rows of tile 0
+
+template <int C, bool DEPTH2, int SH>
+__device__ __forceinline__ void levy_walk_vec(LevyState<C, DEPTH2>& st, const float* slot, int s) {
+  // stream position i of this window (basepoint row, then the s rows) is element SH + i of the
+  // 16-byte chunks starting at `slot`
+  constexpr int NB = (SH + C + 3) / 4;
+  float b[4 * NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const float4 v = reinterpret_cast<const float4*>(slot)[j];
+    b[4 * j] = v.x; b[4 * j + 1] = v.y; b[4 * j + 2] = v.z; b[4 * j + 3] = v.w;
+  }
+  st.init(&b[SH]);
+  constexpr int R = (C % 4 == 0) ? 1 : (C % 2 == 0) ? 2 : 4;  // rows per group: R*C floats = G whole chunks
+  constexpr int G = R * C / 4;
+  constexpr int O = (SH + C) % 4, Q0 = (SH + C) / 4;
+  constexpr int NV = G + (O ? 1 : 0);
+  const float4* q = reinterpret_cast<const float4*>(slot) + Q0;
+  const int groups = s / R;  // s*C % 4 == 0 implies s % R == 0
+  for (int g = 0; g < groups; ++g, q += G) {
+    float v[4 * NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 t = q[j];
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) st.step(&v[O + r * C]);
+  }
+}
+
+template <int C, bool DEPTH2>
+__global__ void __launch_bounds__(32) logsig_levy_tma_kernel(const LevyParams p) {
+  extern __shared__ __align__(128) float smem[];
+  constexpr int D = 1 + C + (DEPTH2 ? (C * (C - 1)) / 2 : 0);
+  const int lane = threadIdx.x;
+  const int b = blockIdx.x / p.tiles;
+  const int tile = blockIdx.x - b * p.tiles;
+  const int k0 = tile * 32;
+  const int nw = min(32, p.q - k0);
+  const int sC = p.s * C;
+  const float* xb = p.data + (size_t)b * p.L * C;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem);
+  float* buf = smem + 4;  // 16 bytes in: [kLevyPad floats | bulk-copied slab | tail floats]
+
+  LevyState<C, DEPTH2> st;
+  if (nw > 0) {
+    // floats [start_f, end_f) of the sample: basepoint row k0*s-2 .. last row (k0+nw)*s-2; rows < 0 read as 0
+    const long long start_f = ((long long)k0 * p.s - 2) * C;
+    const long long end_f = ((long long)(k0 + nw) * p.s - 1) * C;
+    const long long lo_f = start_f < 0 ? 0 : start_f;
+    const float* g_lo = xb + lo_f;
+    const float* g_end = xb + end_f;
+    const float* a0 = reinterpret_cast<const float*>((uintptr_t)g_lo & ~(uintptr_t)15);
+    const float* a1 = reinterpret_cast<const float*>((uintptr_t)g_end & ~(uintptr_t)15);
+    const int sh0 = (int)(g_lo - a0);
+    const unsigned bytes = a1 > a0 ? (unsigned)((a1 - a0) * 4) : 0u;
+    float* slab = buf + kLevyPad;  // smem image of a0[...]
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+      if (bytes) {
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(slab, a0, bytes, bar);
+      }
+    }
+    // <= 3 floats between the 16-byte floor of the end and the end itself
+    const float* t_lo = a1 > g_lo ? a1 : g_lo;
+    if (lane < (int)(g_end - t_lo)) slab[(t_lo - a0) + lane] = ld_stream(t_lo + lane);
+    __syncwarp();
+    if (bytes) mbar_wait(bar, 0);
+    const int lead = (int)(lo_f - start_f);  // 2C zero floats in front of tile 0, else 0
+    if (lane < lead) slab[sh0 - lead + lane] = 0.f;
+    __syncwarp();
+    if (lane < nw) {
+      const int base_idx = kLevyPad + sh0 - lead + lane * sC;  // basepoint row of this lane's window
+      if ((sC & 3) == 0) {
+        const float* slot = buf + (base_idx & ~3);
+        switch (base_idx & 3) {  // warp-uniform: kLevyPad, lane*sC are multiples of 4
+          case 0: levy_walk_vec<C, DEPTH2, 0>(st, slot, p.s); break;
+          case 1: levy_walk_vec<C, DEPTH2, 1>(st, slot, p.s); break;
+          case 2: levy_walk_vec<C, DEPTH2, 2>(st, slot, p.s); break;
+          default: levy_walk_vec<C, DEPTH2, 3>(st, slot, p.s); break;
+        }
+      } else {
+        const float* rows = buf + base_idx;
+        float tmp[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) tmp[c] = rows[c];
+        st.init(tmp);
+        rows += C;
+#pragma unroll 2
+        for (int l = 0; l < p.s; ++l) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) tmp[c] = rows[l * C + c];
+          st.step(tmp);
+        }
+      }
+    }
+    __syncwarp();  // every lane is done reading the slab: reuse it for the result rows
+    float* dst = p.out + ((size_t)b * p.K + k0) * D;
+    const int os = (int)(((uintptr_t)dst >> 2) & 3);  // smem phase = global phase: body 16 B aligned in both
+    float* stage = buf + os;
+    if (lane < nw) st.store(stage + lane * D);
+    fence_async_proxy();  // generic-proxy writes above -> visible to the bulk store below
+    __syncwarp();
+    const int n_o = nw * D;
+    const int head = min(n_o, (4 - os) & 3);
+    const int body = (n_o - head) & ~3;
+    if (lane == 0 && body > 0) {
+      tma_store_1d(dst + head, stage + head, (unsigned)body * 4);
+      tma_store_commit();
+    }
+    if (lane < head) dst[lane] = stage[lane];
+    const int tail0 = head + body;
+    if (lane < n_o - tail0) dst[tail0 + lane] = stage[tail0 + lane];
+    if (lane == 0 && body > 0) tma_store_wait_read();  // shared memory must outlive the bulk read
+  }
+
+  // ---- remainder window: handled by the sample's last tile, one thread -----
+  if (p.r != 0 && tile == p.tiles - 1 && lane == 0) {
+    float tmp[C];
+    const bool extra = p.compat != 0;
+    const float* first = xb + (size_t)(p.L - p.r - 1) * C;  // true predecessor row
+    if (extra) {
+      const bool has_prev = (b % p.chunk) != 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmp[c] = has_prev ? xb[-C + c] : 0.f;  // last row of sample b-1
+      st.init(tmp);
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmp[c] = first[c];
+      st.step(tmp);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmp[c] = first[c];
+      st.init(tmp);
+    }
+    for (int l = 1; l <= p.r; ++l) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmp[c] = first[l * C + c];
+      st.step(tmp);
+    }
+    float row[D];
+    st.store(row);
+    float* dst = p.out + ((size_t)b * p.K + p.q) * D;
+#pragma unroll
+    for (int c = 0; c < D; ++c) dst[c] = row[c];
+  }
+}
+
+
+// ----------------------------------------------------------------------------
 // depth 3, C <= 8: thread (window, i) keeps "row i" of the truncated signature in registers
 // (S1[i], S2[i][.], S3[i][.][.]): the Chen/Horner update of row i needs only the increment, so
 // the sweep over the window is communication-free.  log() and the sparse Hall projection (CSR
@@ -507,6 +675,26 @@ __global__ void __launch_bounds__(128) logsig_tensor_kernel(const TensorParams p
 }
 
 template <int C>
+static int launch_levy_tma(cudaStream_t st, LevyParams p, int depth) {
+  const int D = 1 + C + (depth == 2 ? (C * (C - 1)) / 2 : 0);
+  p.WT = 32;
+  p.tiles = (p.q + 31) / 32;
+  if (p.tiles < 1) p.tiles = 1;
+  // [mbarrier 16 B | kLevyPad | 32 windows + basepoint row + <= 3 alignment floats | 4 floats of over-read slack]
+  const size_t in_f = 4 + kLevyPad + (size_t)32 * p.s * C + C + 3 + 4;
+  const size_t out_f = 4 + 3 + (size_t)32 * D + 4;
+  const size_t smem = (in_f > out_f ? in_f : out_f) * 4;
+  const int grid = p.B * p.tiles;
+  auto go = [&](auto k) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, 32, smem, st>>>(p);
+  };
+  if (depth == 2) go(logsig_levy_tma_kernel<C, true>);
+  else go(logsig_levy_tma_kernel<C, false>);
+  return (int)cudaGetLastError();
+}
+
+template <int C>
 static int launch_levy(cudaStream_t st, LevyParams p, int depth, size_t smem) {
   const int grid = p.B * p.tiles;
   if (depth == 2) {
@@ -561,6 +749,23 @@ int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int 
     p.chunk = compat ? chunk : 1;
     p.stride = (int)(sC | 1);
     p.sc_magic = (uint32_t)((0x100000000ull + sC - 1) / sC);
+    // LNCDE_FLAG_K1_TMA (or LNCDE_LEVY_KERNEL=tma in the environment) selects the bulk-copy kernel; it
+    // needs a 16-byte aligned `data` so that the 16-byte floor of a tile's first float never precedes
+    // the buffer.  Default: the classic kernel (the one measured on B200 so far).
+    static const bool env_tma = getenv("LNCDE_LEVY_KERNEL") && getenv("LNCDE_LEVY_KERNEL")[0] == 't';
+    const bool use_tma = env_tma || (flags & LNCDE_FLAG_K1_TMA);
+    if (use_tma && ((uintptr_t)data & 15) == 0) {
+      switch (C) {
+        case 1: return launch_levy_tma<1>(st, p, depth);
+        case 2: return launch_levy_tma<2>(st, p, depth);
+        case 3: return launch_levy_tma<3>(st, p, depth);
+        case 4: return launch_levy_tma<4>(st, p, depth);
+        case 5: return launch_levy_tma<5>(st, p, depth);
+        case 6: return launch_levy_tma<6>(st, p, depth);
+        case 7: return launch_levy_tma<7>(st, p, depth);
+        case 8: return launch_levy_tma<8>(st, p, depth);
+      }
+    }
     static const int wt_env = getenv("LNCDE_LEVY_WT") ? atoi(getenv("LNCDE_LEVY_WT")) : 0;
     // measured on B200 (scripts/k1_sweep.py): 32-window, single-warp CTAs give the best overlap of
     // the load / walk / store phases across the ~21 CTAs resident per SM (63.8 % vs 59.7 % at 128)

@@ -21,7 +21,7 @@ def logsig_dim(width: int, depth: int) -> int:
 
 
 def calc_paths(data: torch.Tensor, stepsize, depth: int, *, compat: bool = True, chunk: int | None = None,
-               out: torch.Tensor | None = None) -> torch.Tensor:
+               out: torch.Tensor | None = None, kernel: str | None = None) -> torch.Tensor:
     """data[B, L, C] (CUDA fp32) -> logsigs[B, K, D].
 
     Same argument meaning as the reference: ``stepsize`` is clamped to L+1,
@@ -30,6 +30,8 @@ def calc_paths(data: torch.Tensor, stepsize, depth: int, *, compat: bool = True,
     remainder-window quirk of generate_paths.py:59 for a batch processed in
     chunks of ``chunk`` samples (default: the whole call, as in calc_paths).
     depth >= 3 (<= 4) extends the reference (which supports 1 and 2 only).
+    ``kernel="tma"`` selects the bulk-copy variant of the closed-form kernel (LNCDE_FLAG_K1_TMA;
+    C <= 8, depth <= 2), ``None`` / ``"classic"`` the default one.
     """
     _lib.require_cuda(data)
     if data.dtype != torch.float32 or data.dim() != 3:
@@ -44,10 +46,13 @@ def calc_paths(data: torch.Tensor, stepsize, depth: int, *, compat: bool = True,
         out = torch.empty((B, K, D), device=data.device, dtype=torch.float32)
     elif tuple(out.shape) != (B, K, D) or not out.is_contiguous():
         raise _lib.LncdeError("calc_paths: out has the wrong shape")
+    if kernel not in (None, "classic", "tma"):
+        raise _lib.LncdeError(f"calc_paths: unknown kernel {kernel!r}")
+    flags = (1 if compat else 0) | (4 if kernel == "tma" else 0)
     rowptr, cols, vals = _device_t2l(Cn, depth, data.device.index or 0)
     with torch.cuda.device(data.device):
         st = L.lncde_logsig_fwd(_lib.stream_ptr(), _lib.ptr(data), _lib.ptr(out), B, Ln, Cn, stepsize, depth,
-                                1 if compat else 0, int(chunk or B), _lib.ptr(rowptr), _lib.ptr(cols),
+                                flags, int(chunk or B), _lib.ptr(rowptr), _lib.ptr(cols),
                                 _lib.ptr(vals))
     _lib.check(st, "lncde_logsig_fwd")
     return out

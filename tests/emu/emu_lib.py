@@ -37,7 +37,24 @@ def lib():
         _lib.lncde_linear_scan_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]
         _lib.lncde_adam_step.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, i,
                                          C.c_float]
+        _lib.emu_bulk_copies.restype = C.c_long
+        _lib.emu_guarded_alloc.restype = C.c_void_p
+        _lib.emu_guarded_alloc.argtypes = [C.c_size_t, C.c_int, C.c_int]
     return _lib
+
+
+def bulk_copies():
+    """Bulk (TMA) copies issued by the emulated kernels since the last call."""
+    return lib().emu_bulk_copies()
+
+
+def guarded(shape, dtype=np.float32, tight_end=True, start_mod16=0):
+    """numpy array over a "device" allocation bounded by guard pages (never freed: tests are short)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib().emu_guarded_alloc(max(n, 1), 1 if tight_end else 0, start_mod16)
+    assert ptr
+    buf = (C.c_char * max(n, 1)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 def _p(a):
@@ -54,7 +71,7 @@ def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
-def calc_paths(x, stepsize, depth, compat=True, chunk=None):
+def calc_paths(x, stepsize, depth, compat=True, chunk=None, tma=False, misalign=0, tight_end=True):
     L = lib()
     x = f32(x)
     B, Ln, Cn = x.shape
@@ -65,14 +82,14 @@ def calc_paths(x, stepsize, depth, compat=True, chunk=None):
     cols = np.zeros(nnz, np.int32)
     vals = np.zeros(nnz, np.float32)
     assert L.lncde_hall_t2l_csr(Cn, depth, _p(rowptr), _p(cols), _p(vals)) == 0
-    # canary rows either side of the output catch out-of-bounds global writes
-    buf = np.full((B * K * D + 64,), np.float32(12345.0))
-    out = buf[32 : 32 + B * K * D].reshape(B, K, D)
+    # input and output live in guard-page bounded allocations: out-of-bounds global accesses fault
+    out = guarded((B, K, D), tight_end=tight_end, start_mod16=0 if tight_end else 4 * (misalign % 4))
     out[...] = np.nan
-    st = L.lncde_logsig_fwd(None, _p(x), _p(out), B, Ln, Cn, int(stepsize), depth, 1 if compat else 0,
-                            int(chunk or B), _p(rowptr), _p(cols), _p(vals))
+    xin = guarded(x.shape, tight_end=tight_end, start_mod16=4 * (misalign % 4))
+    xin[...] = x
+    st = L.lncde_logsig_fwd(None, _p(xin), _p(out), B, Ln, Cn, int(stepsize), depth,
+                            (1 if compat else 0) | (4 if tma else 0), int(chunk or B), _p(rowptr), _p(cols), _p(vals))
     assert st == 0, st
-    assert np.all(buf[:32] == 12345.0) and np.all(buf[32 + B * K * D :] == 12345.0), "global write out of bounds"
     return out.copy()
 
 

@@ -1,6 +1,8 @@
 // Runtime of the host CUDA emulator (see cuda_emu.h): fibers, barriers, warp collectives,
 // mbarrier / bulk-copy bookkeeping and the few cudart entry points the host wrappers call.
+#include <signal.h>
 #include <sys/mman.h>
+#include <unistd.h>
 
 #include <map>
 #include <vector>
@@ -269,7 +271,9 @@ void mbar_wait(void* bar, unsigned parity) {
   f.parity = parity & 1u;
   yield();
 }
+long g_bulk_copies = 0;
 void check_bulk(const void* smem_ptr, const void* gptr, unsigned bytes, const char* what) {
+  ++g_bulk_copies;
   if (bytes == 0 || (bytes & 15u)) die((std::string(what) + ": size is not a positive multiple of 16 bytes").c_str());
   if ((uintptr_t)smem_ptr & 15u) die((std::string(what) + ": shared-memory address not 16-byte aligned").c_str());
   if ((uintptr_t)gptr & 15u) die((std::string(what) + ": global address not 16-byte aligned").c_str());
@@ -306,10 +310,18 @@ void launch(const void* func, dim3 grid, dim3 block, size_t smem, const std::fun
   b.warps.resize((n + 31) / 32);
   b.body = &body;
   b.smem_bytes = smem;
-  std::vector<unsigned char> raw(smem + 2 * kCanary + 128);
-  // 128-byte aligned start like the hardware window
-  unsigned char* base = raw.data();
-  base += (128 - ((uintptr_t)(base + kCanary) & 127)) & 127;
+  // Shared-memory window: its END sits against an inaccessible guard page (reads or writes past the
+  // allocation fault, to within the 128-byte alignment of the start), a canary guards the front.
+  const size_t page = 4096;
+  const size_t span = ((kCanary + smem + 127) / 128 * 128 + page - 1) / page * page;
+  unsigned char* region = (unsigned char*)mmap(nullptr, span + page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (region == MAP_FAILED) {
+    std::perror("cuda-emu mmap");
+    std::abort();
+  }
+  mprotect(region + span, page, PROT_NONE);
+  unsigned char* win = region + span - (smem + 127) / 128 * 128;  // 128-byte aligned start like the hardware window
+  unsigned char* base = win - kCanary;
   b.smem_raw = base;
   g_blockDim = {block.x, block.y, block.z};
   g_gridDim = {grid.x, grid.y, grid.z};
@@ -320,23 +332,63 @@ void launch(const void* func, dim3 grid, dim3 block, size_t smem, const std::fun
       for (unsigned x = 0; x < grid.x; ++x) {
         g_blockIdx = {x, y, z};
         std::memset(base, kCanaryByte, kCanary);
-        std::memset(base + kCanary, 0xFF, smem);  // uninitialised shared memory reads as NaN
-        std::memset(base + kCanary + smem, kCanaryByte, kCanary);
+        std::memset(win, 0xFF, region + span - win);  // uninitialised shared memory reads as NaN
         b.bar_arrived = 0;
         b.mbars.clear();
         for (auto& w : b.warps) w = Warp();
         run_block(b);
         for (size_t i = 0; i < kCanary; ++i)
-          if (base[i] != kCanaryByte || base[kCanary + smem + i] != kCanaryByte)
-            die("dynamic shared memory written out of bounds");
+          if (base[i] != kCanaryByte) die("dynamic shared memory written out of bounds (before the window)");
       }
+  munmap(region, span + page);
   g_blk = saved;
 }
 
 }  // namespace emu
 
 // ---- the cudart entry points used by the host wrappers ----------------------------------------
+namespace {
+void on_segv(int) {
+  static const char msg[] = "cuda-emu: memory access outside a guarded allocation (out-of-bounds global or shared access)\n";
+  ssize_t r = write(2, msg, sizeof(msg) - 1);
+  (void)r;
+  _exit(134);
+}
+}  // namespace
+
 extern "C" {
+// Test hook: "device" allocation whose end (tight_end != 0) or start (tight_end == 0) touches an
+// inaccessible guard page, so that out-of-bounds global reads and writes of the kernels fault.
+// start_mod16: byte offset of the returned pointer modulo 16 (0 = 16-byte aligned).
+void* emu_guarded_alloc(size_t bytes, int tight_end, int start_mod16) {
+  static bool handler = false;
+  if (!handler) {
+    signal(SIGSEGV, on_segv);
+    handler = true;
+  }
+  const size_t page = 4096;
+  const size_t span = (bytes + 16 + page - 1) / page * page;
+  unsigned char* region = (unsigned char*)mmap(nullptr, span + 2 * page, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (region == MAP_FAILED) return nullptr;
+  mprotect(region, page, PROT_NONE);
+  mprotect(region + page + span, page, PROT_NONE);
+  unsigned char* lo = region + page;
+  unsigned char* p;
+  if (tight_end) {
+    p = lo + span - bytes;
+    p -= ((uintptr_t)p - (uintptr_t)start_mod16) & 15;  // largest address <= with the requested phase
+  } else {
+    p = lo + (start_mod16 & 15);
+  }
+  std::memset(lo, 0xFF, span);
+  return p;
+}
+// test hook: number of bulk (TMA) copies issued since the last call
+long emu_bulk_copies(void) {
+  const long n = emu::g_bulk_copies;
+  emu::g_bulk_copies = 0;
+  return n;
+}
 cudaError_t cudaFuncSetAttribute(const void* func, cudaFuncAttribute attr, int value) {
   if (attr == cudaFuncAttributeMaxDynamicSharedMemorySize) {
     if (value > 227 * 1024) return cudaErrorInvalidValue;

@@ -31,32 +31,65 @@ def _walk(B, L, C, seed=2345):
 
 
 # ------------------------------------------------------------------------------------------ K1
+# tma=False: logsig_levy_kernel (classic staging); tma=True: logsig_levy_tma_kernel (bulk copies).
+# Inputs and outputs sit in guard-page bounded allocations (tight at the end or at the start), so an
+# out-of-bounds global access of either kernel faults instead of passing silently.
+@pytest.mark.parametrize("tma", [False, True])
 @pytest.mark.parametrize("C", [1, 2, 3, 6, 7, 8])
 @pytest.mark.parametrize("depth", [1, 2])
-def test_emu_logsig_integer_kat_bit_exact(C, depth):
+def test_emu_logsig_integer_kat_bit_exact(C, depth, tma):
     x = _toy(5, 100, C)
     for s in (1, 4, 7, 12, 100, 101, 500):
         want = paths.calc_paths(x, s, depth, np.float64)
-        got = E.calc_paths(x, s, depth)
-        assert got.shape == want.shape
-        assert np.array_equal(got.astype(np.float64), want), (C, depth, s)
+        for tight_end in (True, False):
+            got = E.calc_paths(x, s, depth, tma=tma, tight_end=tight_end)
+            assert got.shape == want.shape
+            assert np.array_equal(got.astype(np.float64), want), (C, depth, s)
 
 
+@pytest.mark.parametrize("tma", [False, True])
 @pytest.mark.parametrize("compat", [True, False])
-def test_emu_logsig_compat_and_chunk(compat):
+def test_emu_logsig_compat_and_chunk(compat, tma):
     x = _toy(140, 30, 3)
     want = paths.batch_calc_paths(x, 4, 2, np.float64, compat=compat)
-    got = E.calc_paths(x, 4, 2, compat=compat, chunk=128)
+    got = E.calc_paths(x, 4, 2, compat=compat, chunk=128, tma=tma)
     assert np.array_equal(got.astype(np.float64), want)
 
 
-@pytest.mark.parametrize("C,s,L", [(7, 12, 1200), (6, 12, 1190), (6, 16, 896), (7, 10, 999), (4, 10, 503), (5, 3, 1000)])
-def test_emu_logsig_float_paths_depth2(C, s, L):
+@pytest.mark.parametrize("tma", [False, True])
+@pytest.mark.parametrize("C,s,L", [(7, 12, 1200), (6, 12, 1190), (6, 16, 896), (7, 10, 999), (4, 10, 503), (5, 3, 1000),
+                                   (3, 7, 333), (8, 16, 700)])
+def test_emu_logsig_float_paths_depth2(C, s, L, tma):
     x = _walk(3, L, C)
     want = paths.calc_paths(x, s, 2, np.float64)
-    got = E.calc_paths(x, s, 2)
+    E.bulk_copies()
+    got = E.calc_paths(x, s, 2, tma=tma)
+    assert (E.bulk_copies() > 0) == tma  # the requested kernel is the one that ran
     assert got.shape == want.shape
     assert rel_err(got, want) < TOL
+
+
+def test_emu_logsig_tma_equals_classic_every_alignment():
+    """Same LevyState arithmetic: bit-identical results for every 16-byte phase of the tiles (odd L*C moves
+    the phase from sample to sample), every remainder length and tile counts around 32 windows."""
+    rng = np.random.default_rng(11)
+    for C, L, s in [(7, 12 * 33 + 5, 12), (3, 97, 4), (5, 131, 4), (1, 70, 4), (7, 389, 12), (6, 150, 2), (8, 64, 1)]:
+        x = np.cumsum(rng.normal(size=(5, L, C)), axis=1).astype(np.float32)
+        for depth in (1, 2):
+            a = E.calc_paths(x, s, depth, tma=False)
+            b = E.calc_paths(x, s, depth, tma=True)
+            assert np.array_equal(a, b), (C, L, s, depth)
+
+
+def test_emu_logsig_tma_eigenworms_length():
+    """One EigenWorms-length sample (47 tiles of 32 windows) through the bulk-copy kernel."""
+    x = _walk(1, 17984, 7, seed=5)
+    x[..., 0] = np.arange(17984) / 17984
+    want = paths.calc_paths(x, 12, 2, np.float64)
+    got = E.calc_paths(x, 12, 2, tma=True)
+    assert got.shape == (1, 1499, 29)
+    assert rel_err(got, want) < TOL
+    assert np.array_equal(got, E.calc_paths(x, 12, 2, tma=False))
 
 
 @pytest.mark.parametrize("C,depth", [(2, 3), (3, 3), (7, 3), (2, 4), (3, 4), (10, 2), (9, 1)])
