@@ -189,6 +189,18 @@ def run_ours(args):
         dist.barrier()
     _lib.lib()
 
+    # ---- kernel-variant autotune (rank 0 decides, everybody applies the same choice) -------------------
+    tuning, tune_report = {"k1_tma": 0, "k3_fused": 0}, None
+    if not args.no_autotune and args.workload == "eigenworms_logncde":
+        if rank == 0:
+            tuning, tune_report = autotune()
+        if world > 1:
+            box = [tuning]
+            dist.broadcast_object_list(box, src=0)
+            tuning = box[0]
+        for k, v in tuning.items():
+            _lib.set_tuning(k, v)
+
     B, L, C = WL["B"], WL["L"], WL["C"]
     x_host, lab_host = make_inputs(rank, N_ROT)
     x_pin = torch.from_numpy(x_host).pin_memory()
@@ -312,7 +324,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WL["desc"], "global_batch": world * B, "parallelism": f"dp{world}",
                        "launch": "one CUDA graph per step" if use_graph else "eager",
-                       "l2": l2_note},
+                       "tuning": tuning, "l2": l2_note},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": int(x_pin[0].numel() * 4 + lab_pin[0].numel() * 4),
                     "d2h_bytes_per_step": 4, "last_loss": last_loss},
@@ -320,8 +332,10 @@ def run_ours(args):
             "gpu_launches": 8 * args.steps,
             "clocks": clocks,
         }
+        if tune_report is not None:
+            out["autotune"] = tune_report
         if args.workload == "eigenworms_logncde":
-            out.update(extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms / args.steps))
+            out.update(extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms / args.steps, tuning))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -329,7 +343,7 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_per_step):
+def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_per_step, tuning):
     """Roofline of the HBM-bound kernel (K1 logsig at a batch larger than L2), per-kernel
     breakdown of the step, and the CPU baseline.  Rank 0 only."""
     from lncde import train as T
@@ -357,11 +371,15 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     k1_ms = e0.elapsed_time(e1) / n_rep
     alg_bytes = Bk * (4 * L * C + 4 * 1499 * 29)  # 677 436 B per sample
     ach = alg_bytes / (k1_ms * 1e-3) / 1e9
-    res["roofline"] = {"kernel": "logsig_levy_kernel<7,depth2> (K1)", "bound": "hbm", "achieved": ach,
+    k1_tma = bool(tuning.get("k1_tma"))
+    res["roofline"] = {"kernel": ("logsig_levy_tma_kernel<7,depth2> (K1, TMA staging)" if k1_tma
+                                  else "logsig_levy_kernel<7,depth2> (K1)"),
+                       "bound": "hbm", "achieved": ach,
                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                        # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed
-                       # ncu --set full capture profiles/r01_full_logsig_final.md (1.0525 GB + 0.2990 GB)
-                       "traffic": 1.3515e9,
+                       # ncu --set full capture profiles/r01_full_logsig_final.md (1.0525 GB + 0.2990 GB);
+                       # no capture of the TMA variant exists yet
+                       "traffic": None if k1_tma else 1.3515e9,
                        "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs (burst copy)",
                        "launch_ms": k1_ms, "algorithmic_bytes_per_launch": alg_bytes,
                        "shape": f"B={Bk} x EigenWorms (L=17984, C=7, stepsize 12, depth 2): inputs 1.03 GB > L2"}
@@ -377,37 +395,50 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     flop = 2.0 * (2 * macs_stage) * n_stage * WL["B"]   # transposed mat-vecs + weight-gradient outer products
     t_ms = res["step_breakdown_ms"]["backward_K3b+gemm"]
     ach = flop / (t_ms * 1e-3) / 1e12
-    res["roofline_dominant"] = {"kernel": "logncde_bwd_saved_kernel<7,depth2> + outer_gemm_kernel (K3b)",
+    res["roofline_dominant"] = {"kernel": "logncde_bwd_saved_kernel<7,depth2%s> + outer_gemm_kernel (K3b)"
+                                          % (",fused" if tuning.get("k3_fused") else ""),
                                 "bound": "latency (dependent phases), fp32 issue", "achieved": ach,
                                 "peak": 74.4, "unit": "TFLOP/s", "frac": ach / 74.4,
                                 "peak_source": "nominal FP32 FFMA peak (not in MEASURED_PEAKS.json)",
                                 "share_of_step": t_ms / ms_per_step,
                                 "us_per_stage": 1e3 * t_ms / n_stage,
                                 "algorithmic_flop_per_step": flop}
-    # ---- K1 variants (not the default path): parity + timing in a subprocess, so that a variant which
-    # has not been on hardware yet cannot take this process down; errors are reported, not raised
-    if not args.no_variants and int(os.environ.get("WORLD_SIZE", "1")) == 1:
-        res["k1_variants"] = k1_variants(pk)
     # ---- CPU baseline ------------------------------------------------------------------------------
     if not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     return res
 
 
-def k1_variants(pk):
-    """scripts/k1_variant_check.py: logsig_levy_tma_kernel (bulk-copy staging) vs the classic kernel."""
+def decide_tuning(rep, margin=0.98):
+    """A variant is used only if ITS parity check passed and it beat the default by the margin."""
+    choice = {"k1_tma": 0, "k3_fused": 0}
+    k1, k3 = rep.get("k1", {}), rep.get("k3", {})
     try:
-        r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "k1_variant_check.py")],
-                           capture_output=True, text=True, timeout=150)
+        if k1.get("parity", {}).get("ok") and "error" not in k1:
+            choice["k1_tma"] = int(k1["timing"]["tma"]["ms"] < margin * k1["timing"]["classic"]["ms"])
+        if k3.get("parity", {}).get("ok") and "error" not in k3:
+            choice["k3_fused"] = int(k3["timing"]["fused"]["ms"] < margin * k3["timing"]["default"]["ms"])
+    except (KeyError, TypeError):
+        pass
+    return choice
+
+
+def autotune():
+    """Pick among kernel variants that compute the same result (lncde.set_tuning): scripts/variant_check.py runs
+    each variant in a SUBPROCESS (a variant that has never been on this hardware cannot take the bench down),
+    checks it against the default kernels and times both; a variant is switched on only if its parity check
+    passed there and it was measurably faster.  Returns (choices, raw report)."""
+    choice = {"k1_tma": 0, "k3_fused": 0}
+    try:
+        r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "variant_check.py")],
+                           capture_output=True, text=True, timeout=200)
         if r.returncode != 0:
-            return {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
-        out = json.loads(r.stdout.strip().splitlines()[-1])
-        for k in ("classic", "tma"):
-            if k in out.get("timing", {}):
-                out["timing"][k]["frac_of_hbm_peak"] = out["timing"][k]["GB/s"] / pk["hbm_gbs"]
-        return out
+            return choice, {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
+        rep = json.loads(r.stdout.strip().splitlines()[-1])
     except Exception as e:  # timeout, unparsable output
-        return {"error": f"{type(e).__name__}: {e}"[:300]}
+        return choice, {"error": f"{type(e).__name__}: {e}"[:300]}
+    choice = decide_tuning(rep)
+    return choice, rep
 
 
 def breakdown(model, opt, x_dev, lab_dev):
@@ -539,12 +570,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--workload", default="eigenworms_logncde", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
-    ap.add_argument("--no-variants", action="store_true", help="skip the K1 kernel-variant leg (subprocess)")
+    ap.add_argument("--no-autotune", action="store_true",
+                    help="keep the default kernels (skip the subprocess that checks and times the variants)")
     args = ap.parse_args()
     WL.clear()
     WL.update(WORKLOADS[args.workload])
     # the default run finishes in ~40 s; never let a stuck collective hold N GPUs for long
-    _watchdog(float(os.environ.get("LNCDE_BENCH_TIMEOUT", "600" if args.impl == "reference" else "420")))
+    _watchdog(float(os.environ.get("LNCDE_BENCH_TIMEOUT", "600")))
     if args.impl == "reference":
         run_reference(args)
     else:

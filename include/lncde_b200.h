@@ -43,6 +43,15 @@ const char* lncde_version(void);
 /* Human-readable text for a status returned by any entry point. */
 const char* lncde_strerror(int status);
 
+/* Kernel-variant switches.  Every variant computes the same result; the default is the variant measured
+ * fastest on B200 so far.  Keys: "k1_tma" (lncde_logsig_fwd: TMA bulk-copy staging, same as passing
+ * LNCDE_FLAG_K1_TMA), "k3_fused" (lncde_logncde_fwd/bwd, specialised H=128 / width 32 kernels: the 32 x 32
+ * layer phases fused on single warps).  Process-wide, thread-safe; initial values come from the
+ * environment (LNCDE_TUNE_K1_TMA, LNCDE_TUNE_K3_FUSED).  A forward/backward pair must run under the same
+ * setting only in the sense that each call reads the value once at entry; results are interchangeable. */
+int lncde_set_tuning(const char* key, int value);
+int lncde_get_tuning(const char* key); /* value, or <0 for an unknown key */
+
 /* ------------------------------------------------------------------ K0 ---
  * Hall basis and tensor->Lie projection tables (host, cached).
  * Replaces data_dir/hall_set.py:60-119 (HallSet.__init__/grow_up),

@@ -84,6 +84,8 @@ struct Smem {
   static constexpr int sb2 = vb + CW, sb1 = sb2 + W, zb2 = sb1 + W, zb1 = zb2 + W;
   static constexpr int bacc = zb1 + W;       // [64] bias accumulators of the two hidden layers
   static constexpr int COMMON_BWD = bacc + 2 * W;
+  // FUSED variant only: W2 in per-thread order [8 K-slices][32 rows][4], appended after the common area
+  static constexpr int W2R_FLOATS = W * W;
 };
 
 struct Regs {
@@ -198,13 +200,48 @@ __device__ __forceinline__ void hidden_finish(const float* part, float bias, int
   s_out[lane] = sg * (1.f + z * (1.f - sg));
 }
 
+// SiLU and its derivative from the four running sums of hidden_finish (same order of additions).
+__device__ __forceinline__ void hidden_finish_acc(const float (&acc)[4], int lane, float* z_out, float* a_out,
+                                                  float* s_out) {
+  const float z = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  const float sg = sigm(z);
+  z_out[lane] = z;
+  a_out[lane] = z * sg;
+  s_out[lane] = sg * (1.f + z * (1.f - sg));
+}
+
+// acc[q % NACC] += dot(Wq[(q*32 + lane)*4 .. +3], x[4q .. 4q+3]), q = 0..7 in order: one 32 x 32 mat-vec (or its
+// transpose, depending on the layout of Wq) done by ONE warp, lane = output index, x read as broadcast
+// 128-bit loads.  The partial products and the order they are summed in are those of the K-sliced path.
+template <int NACC>
+__device__ __forceinline__ void warp_matvec32(const float* __restrict__ Wq, const float* __restrict__ x, int lane,
+                                              float (&acc)[NACC]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 wt = *reinterpret_cast<const float4*>(Wq + (q * 32 + lane) * 4);
+    const float w4[4] = {wt.x, wt.y, wt.z, wt.w};
+    acc[q % NACC] += dot4(w4, *reinterpret_cast<const float4*>(x + q * 4));
+  }
+}
+
+// W2 in the order warp_matvec32 reads it for the FORWARD product: Wq[(q*32 + row)*4 + e] = W2[row][4q + e]
+__device__ __forceinline__ void stage_w2r(const MlpDesc& d, const float* __restrict__ params, float* w2r) {
+  for (int t = threadIdx.x; t < W * W; t += NT) {
+    const int e = t & 3, row = (t >> 2) & 31, q = t >> 7;
+    w2r[t] = params[d.w_off[1] + row * W + q * 4 + e];
+  }
+}
+
 // Forward evaluation of the field at sb[yin].  Leaves every intermediate in `sb`, the
 // last-layer outputs of this lane in o_r / u3_r and, after the trailing barrier, the per-row
 // tangent contributions in cm[dbuf].  The caller finishes
 //   G[h] = sum_i lam1[i] o[i][h] + sum_j dbuf[j][h].
-template <int C, bool D2>
+// FUSED (kernel variant, see lncde_set_tuning "k3_fused"): the 32 x 32 layer and the steps around it run on
+// single warps straight out of shared memory (warp_matvec32) instead of being K-sliced over all warps
+// with a reduce phase each: 8 block barriers per stage instead of 12, same sums in the same order.
+template <int C, bool D2, bool FUSED = false>
 __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& R, float lam_v,
-                                              float (&o_r)[2], float (&u3_r)[2]) {
+                                              float (&o_r)[2], float (&u3_r)[2], const float* w2r = nullptr) {
   using S = Smem<C>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* part = cm + S::part;
@@ -216,16 +253,28 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     part[warp * 32 + lane] = dot8(R.w1, ya, yb);
   }
   __syncthreads();
-  if (warp == 0) hidden_finish<16>(part, R.b1, lane, sb + S::z1, sb + S::a1, sb + S::s1);
-  __syncthreads();
-  // P2: z2 = W2 a1
-  if (warp < 8) {
-    const float4 a = *reinterpret_cast<const float4*>(sb + S::a1 + warp * 4);
-    part[warp * 32 + lane] = dot4(R.w2, a);
+  if (FUSED) {
+    // F1: warp 0 finishes z1 / a1 / s1 and goes straight on to z2 = W2 a1
+    if (warp == 0) {
+      hidden_finish<16>(part, R.b1, lane, sb + S::z1, sb + S::a1, sb + S::s1);
+      __syncwarp();
+      float acc[4] = {R.b2, 0.f, 0.f, 0.f};
+      warp_matvec32<4>(w2r, sb + S::a1, lane, acc);
+      hidden_finish_acc(acc, lane, sb + S::z2, sb + S::a2, sb + S::s2);
+    }
+    __syncthreads();
+  } else {
+    if (warp == 0) hidden_finish<16>(part, R.b1, lane, sb + S::z1, sb + S::a1, sb + S::s1);
+    __syncthreads();
+    // P2: z2 = W2 a1
+    if (warp < 8) {
+      const float4 a = *reinterpret_cast<const float4*>(sb + S::a1 + warp * 4);
+      part[warp * 32 + lane] = dot4(R.w2, a);
+    }
+    __syncthreads();
+    if (warp == 0) hidden_finish<8>(part, R.b2, lane, sb + S::z2, sb + S::a2, sb + S::s2);
+    __syncthreads();
   }
-  __syncthreads();
-  if (warp == 0) hidden_finish<8>(part, R.b2, lane, sb + S::z2, sb + S::a2, sb + S::s2);
-  __syncthreads();
   // P3: o = tanh(W3 a2 + b3)
   const int row0 = lane_row0(tid);
   if (tid < C * 64) {
@@ -259,8 +308,18 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     for (int i = 0; i < C; ++i) u = fmaf(cm[S::lam + i * 8 + warp], cm[S::qv + i * W + lane], u);
     sb[S::u1 + warp * W + lane] = u;
     sb[S::p1 + warp * W + lane] = sb[S::s1 + lane] * u;
+    if (FUSED) {
+      // F2: warp j carries tangent j through the 32 x 32 layer on its own: u2_j = W2 p1_j ; p2_j = s2 * u2_j
+      __syncwarp();
+      float acc[2] = {0.f, 0.f};
+      warp_matvec32<2>(w2r, sb + S::p1 + warp * W, lane, acc);
+      const float u2v = acc[0] + acc[1];
+      sb[S::u2 + warp * W + lane] = u2v;
+      sb[S::p2 + warp * W + lane] = sb[S::s2 + lane] * u2v;
+    }
   }
   __syncthreads();
+  if (!FUSED) {
   // P6: u2_j = W2 p1_j (8 K-slices x 2 vector halves)
   {
     const int q = warp & 7, j0 = (warp >> 3) * 4;
@@ -283,6 +342,7 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     sb[S::p2 + warp * W + lane] = sb[S::s2 + lane] * u;
   }
   __syncthreads();
+  }  // !FUSED
   // P7: u3 = W3[block j] p2_j ; d = (1 - o^2) u3
   if (tid < C * 64) {
     const int j = tid >> 6;
@@ -356,15 +416,17 @@ __device__ __forceinline__ void save_stage(const float* sb, const float (&o_r)[2
   }
 }
 
-template <int C, bool D2, bool SAVE>
+template <int C, bool D2, bool SAVE, bool FUSED>
 __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams p) {
   using S = Smem<C>;
   extern __shared__ __align__(16) float smem[];
   float* sb = smem + S::WEND_FWD;
   float* cm = sb + S::STAGE;
+  float* w2r = cm + S::COMMON_FWD;  // FUSED only
   const int tid = threadIdx.x;
   Regs R;
   load_regs<C>(R, p.params, p.d);
+  if (FUSED) stage_w2r(p.d, p.params, w2r);
   const int b = blockIdx.x;
   const float* ls = p.logsig + (size_t)b * p.K * p.D;
   float* ys = p.ys + (size_t)b * (p.n_steps + 1) * H;
@@ -385,7 +447,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
     const int nx = sidx + 1 < n_stage ? sidx + 1 : sidx;
     const float sc_n = p.stage_scale[nx];
     const float lam_n = lambda_fetch<C>(ls + (size_t)p.stage_row[nx] * p.D, D2);
-    stage_forward<C, D2>(sb, cm, R, lam_c, o_r, u3_r);
+    stage_forward<C, D2, FUSED>(sb, cm, R, lam_c, o_r, u3_r, w2r);
     if (SAVE) save_stage<C, D2>(sb, o_r, u3_r, p.ws, p.wsp, (size_t)b * n_stage + sidx);
     if (tid < H) {
       const float gk = sc * field_value<C, D2>(sb, cm, tid);
@@ -409,7 +471,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
 // Reverse sweep of one stage.  cm[g] holds dLoss/dG times the stage scale.  On exit (after the
 // trailing barrier) cm[part + ks*128 + h], ks < 4, hold the K-slice partials of
 // dLoss/d(stage input); the caller sums them.
-template <int C, bool D2, bool RIGHTS>
+template <int C, bool D2, bool RIGHTS, bool FUSED = false>
 __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, float* sb, float* cm, const Regs& R,
                                               const float (&o_r)[2], const float (&u3_r)[2], float (&b3acc)[2],
                                               const WsLayout& ws, float* __restrict__ wsp, size_t slot) {
@@ -454,6 +516,23 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
   }
   if (D2) {
     __syncthreads();
+    if (FUSED) {
+      // FQ2: warp j takes tangent j through Q2 (u2-bar), Q3 (p1-bar_j = W2^T u2-bar_j) and Q3r (u1-bar) alone
+      if (warp < C) {
+        const float pb = cm[S::red + (2 * warp) * W + lane] + cm[S::red + (2 * warp + 1) * W + lane];
+        const float ub = sb[S::s2 + lane] * pb;
+        cm[S::ub2 + tid] = ub;
+        cm[S::sp2 + tid] = sb[S::u2 + tid] * pb;
+        wsp[ws.U[1] + slot * CW + tid] = ub;
+        __syncwarp();
+        float acc[2] = {0.f, 0.f};
+        warp_matvec32<2>(sw + S::W2T, cm + S::ub2 + warp * W, lane, acc);
+        const float pb1 = acc[0] + acc[1];
+        cm[S::ub1 + tid] = sb[S::s1 + lane] * pb1;
+        cm[S::sp1 + tid] = sb[S::u1 + tid] * pb1;
+      }
+      __syncthreads();
+    } else {
     // Q2: u2-bar = s2 * p2-bar ; s2-bar partials
     if (warp < C) {
       const float pb = cm[S::red + (2 * warp) * W + lane] + cm[S::red + (2 * warp + 1) * W + lane];
@@ -494,6 +573,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
       cm[S::sp1 + tid] = sb[S::u1 + tid] * pb;
     }
     __syncthreads();
+    }  // !FUSED
     // v_i = sum_j Lam_ij u1-bar_j ; s1-bar
     if (warp < C) {
       float v = 0.f;
@@ -506,6 +586,12 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
 #pragma unroll
       for (int j = 0; j < C; ++j) s += cm[S::sp1 + j * W + lane];
       cm[S::sb1 + lane] = s;
+      if (FUSED) {  // s2-bar (the unfused path sums it in Q3)
+        float s2s = 0.f;
+#pragma unroll
+        for (int j = 0; j < C; ++j) s2s += cm[S::sp2 + j * W + lane];
+        cm[S::sb2 + lane] = s2s;
+      }
     }
     __syncthreads();
     // Q4: o-bar_i[h] += sum_c W1[c][h] v_i[c]   (4 K-slices x 4 h-quarters)
@@ -544,6 +630,34 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     cm[S::red + warp * W + lane_col(lane)] = pr;
   }
   __syncthreads();
+  if (FUSED) {
+    // FQ6: warp 0 does Q6 (z2-bar), Q7 (a1-bar = W2^T z2-bar) and Q7r (z1-bar) back to back
+    if (warp == 0) {
+      float acc[2] = {0.f, 0.f};
+#pragma unroll
+      for (int wq = 0; wq < 2 * C; ++wq) acc[wq & 1] += cm[S::red + wq * W + lane];
+      float zb = sb[S::s2 + lane] * (acc[0] + acc[1]);
+      if (D2) {
+        const float z = sb[S::z2 + lane], sg = sigm(z);
+        zb = fmaf(sg * (1.f - sg) * (2.f + z * (1.f - 2.f * sg)), cm[S::sb2 + lane], zb);
+      }
+      cm[S::zb2 + lane] = zb;
+      cm[S::bacc + W + lane] += zb;
+      wsp[ws.Z[1] + slot * W + lane] = zb;
+      __syncwarp();
+      float ac2[2] = {0.f, 0.f};
+      warp_matvec32<2>(sw + S::W2T, cm + S::zb2, lane, ac2);
+      float zb1v = sb[S::s1 + lane] * (ac2[0] + ac2[1]);
+      if (D2) {
+        const float z = sb[S::z1 + lane], sg = sigm(z);
+        zb1v = fmaf(sg * (1.f - sg) * (2.f + z * (1.f - 2.f * sg)), cm[S::sb1 + lane], zb1v);
+      }
+      cm[S::zb1 + lane] = zb1v;
+      cm[S::bacc + lane] += zb1v;
+      wsp[ws.Z[0] + slot * W + lane] = zb1v;
+    }
+    __syncthreads();
+  } else {
   // Q6: a2-bar ; z2-bar
   if (warp == 0) {
     float acc[2] = {0.f, 0.f};
@@ -581,6 +695,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     wsp[ws.Z[0] + slot * W + lane] = zb;
   }
   __syncthreads();
+  }  // !FUSED
   // Q8: y-bar = W1^T z1-bar, K-slice partials (summed by the caller)
   {
     const int ks = warp >> 2, h = (warp & 3) * 32 + lane;
@@ -601,7 +716,7 @@ __device__ __forceinline__ float yout_value(const float* cm, int h) {
   return (part[h] + part[H + h]) + (part[2 * H + h] + part[3 * H + h]);
 }
 
-template <int C, bool D2>
+template <int C, bool D2, bool FUSED>
 __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams p) {
   using S = Smem<C>;
   extern __shared__ __align__(16) float smem[];
@@ -609,10 +724,12 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
   float* sbA = smem + S::WEND_BWD;
   float* sbB = sbA + S::STAGE;
   float* cm = sbB + S::STAGE;
+  float* w2r = cm + S::COMMON_BWD;  // FUSED only
   const int tid = threadIdx.x;
   Regs R;
   load_regs<C>(R, p.params, p.d);
   stage_weights_bwd<C>(p.d, p.params, sw);
+  if (FUSED) stage_w2r(p.d, p.params, w2r);
   const int b = blockIdx.x;
   const float* ls = p.logsig + (size_t)b * p.K * p.D;
   const float* ys = p.ys + (size_t)b * (p.n_steps + 1) * H;
@@ -639,13 +756,13 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
     const float g_nn = tid < H ? gys[(size_t)nn * H + tid] : 0.f;
     if (tid < H) sbA[S::yin + tid] = y_n;
     __syncthreads();
-    stage_forward<C, D2>(sbA, cm, R, lam_a, oA, uA);
+    stage_forward<C, D2, FUSED>(sbA, cm, R, lam_a, oA, uA, w2r);
     if (tid < H) sbB[S::yin + tid] = sbA[S::yin + tid] + s1 * field_value<C, D2>(sbA, cm, tid);
     __syncthreads();
-    stage_forward<C, D2>(sbB, cm, R, lam_b, oB, uB);  // leaves Lambda of row r2
+    stage_forward<C, D2, FUSED>(sbB, cm, R, lam_b, oB, uB, w2r);  // leaves Lambda of row r2
     if (tid < H) cm[S::g + tid] = 0.5f * s2 * cm[S::ybar + tid];
     __syncthreads();
-    stage_reverse<C, D2, true>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1);
+    stage_reverse<C, D2, true, FUSED>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1);
     if (tid < H) {
       const float a = yout_value<C>(cm, tid);
       cm[S::ab + tid] = a;
@@ -655,7 +772,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
     const float lam_an = lambda_fetch<C>(ls + (size_t)r1n * p.D, D2);
     const float lam_bn = lambda_fetch<C>(ls + (size_t)r2n * p.D, D2);
     __syncthreads();
-    stage_reverse<C, D2, true>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot);
+    stage_reverse<C, D2, true, FUSED>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot);
     if (tid < H) cm[S::ybar + tid] += cm[S::ab + tid] + yout_value<C>(cm, tid) + g_n;
     __syncthreads();
     s1 = s1n; s2 = s2n;
@@ -695,7 +812,7 @@ __device__ __forceinline__ void fetch_saved(float* sb, const WsLayout& ws, const
   cp_async_commit();
 }
 
-template <int C, bool D2>
+template <int C, bool D2, bool FUSED>
 __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParams p) {
   using S = Smem<C>;
   constexpr int CH = C * H;
@@ -750,7 +867,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
     lambda_store<C>(cm, lam_c);
     __syncthreads();
     const float oc[2] = {o_c.x, o_c.y}, uc[2] = {u_c.x, u_c.y};
-    stage_reverse<C, D2, false>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx);
+    stage_reverse<C, D2, false, FUSED>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx);
     if (tid < H) {
       const float yo = yout_value<C>(cm, tid);
       if (second) cm[S::ab + tid] = yo;
@@ -772,45 +889,53 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
 }
 
 template <int C>
-constexpr size_t fwd_smem_bytes() {
-  return (size_t)(Smem<C>::WEND_FWD + Smem<C>::STAGE + Smem<C>::COMMON_FWD) * 4;
+constexpr size_t fwd_smem_bytes(bool fused) {
+  return (size_t)(Smem<C>::WEND_FWD + Smem<C>::STAGE + Smem<C>::COMMON_FWD + (fused ? Smem<C>::W2R_FLOATS : 0)) * 4;
 }
 template <int C>
-constexpr size_t bwd_smem_bytes() {
-  return (size_t)(Smem<C>::WEND_BWD + 2 * Smem<C>::STAGE + Smem<C>::COMMON_BWD) * 4;
+constexpr size_t bwd_smem_bytes(bool fused) {
+  return (size_t)(Smem<C>::WEND_BWD + 2 * Smem<C>::STAGE + Smem<C>::COMMON_BWD + (fused ? Smem<C>::W2R_FLOATS : 0)) * 4;
 }
 
-template <int C>
-static int launch_fwd_fast(cudaStream_t st, const FwdParams& p) {
-  const size_t smem = fwd_smem_bytes<C>();
+template <int C, bool FUSED>
+static int launch_fwd_fast_v(cudaStream_t st, const FwdParams& p) {
+  const size_t smem = fwd_smem_bytes<C>(FUSED);
   auto go = [&](auto k) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<p.B, NT, smem, st>>>(p);
   };
   if (p.d.depth == 2) {
-    if (p.save) go(logncde_fwd_fast_kernel<C, true, true>);
-    else go(logncde_fwd_fast_kernel<C, true, false>);
+    if (p.save) go(logncde_fwd_fast_kernel<C, true, true, FUSED>);
+    else go(logncde_fwd_fast_kernel<C, true, false, FUSED>);
   } else {
-    if (p.save) go(logncde_fwd_fast_kernel<C, false, true>);
-    else go(logncde_fwd_fast_kernel<C, false, false>);
+    if (p.save) go(logncde_fwd_fast_kernel<C, false, true, FUSED>);
+    else go(logncde_fwd_fast_kernel<C, false, false, FUSED>);
   }
   return (int)cudaGetLastError();
 }
 template <int C>
-static int launch_bwd_fast(cudaStream_t st, const BwdParams& p) {
-  const size_t smem = bwd_smem_bytes<C>();
+static int launch_fwd_fast(cudaStream_t st, const FwdParams& p, bool fused) {
+  return fused ? launch_fwd_fast_v<C, true>(st, p) : launch_fwd_fast_v<C, false>(st, p);
+}
+template <int C, bool FUSED>
+static int launch_bwd_fast_v(cudaStream_t st, const BwdParams& p) {
+  const size_t smem = bwd_smem_bytes<C>(FUSED && !p.saved);  // only the recomputing kernel runs stage_forward
   auto go = [&](auto k) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<p.B, NT, smem, st>>>(p);
   };
   if (p.d.depth == 2) {
-    if (p.saved) go(logncde_bwd_saved_kernel<C, true>);
-    else go(logncde_bwd_fast_kernel<C, true>);
+    if (p.saved) go(logncde_bwd_saved_kernel<C, true, FUSED>);
+    else go(logncde_bwd_fast_kernel<C, true, FUSED>);
   } else {
-    if (p.saved) go(logncde_bwd_saved_kernel<C, false>);
-    else go(logncde_bwd_fast_kernel<C, false>);
+    if (p.saved) go(logncde_bwd_saved_kernel<C, false, FUSED>);
+    else go(logncde_bwd_fast_kernel<C, false, FUSED>);
   }
   return (int)cudaGetLastError();
+}
+template <int C>
+static int launch_bwd_fast(cudaStream_t st, const BwdParams& p, bool fused) {
+  return fused ? launch_bwd_fast_v<C, true>(st, p) : launch_bwd_fast_v<C, false>(st, p);
 }
 
 inline bool shape_supported(int Hh, int C, int width, int n_hidden) {

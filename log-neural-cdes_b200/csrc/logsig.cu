@@ -22,6 +22,7 @@
 
 #include "lncde_b200.h"
 #include "ptx.cuh"
+#include "tuning.h"
 
 namespace lncde {
 
@@ -749,11 +750,10 @@ int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int 
     p.chunk = compat ? chunk : 1;
     p.stride = (int)(sC | 1);
     p.sc_magic = (uint32_t)((0x100000000ull + sC - 1) / sC);
-    // LNCDE_FLAG_K1_TMA (or LNCDE_LEVY_KERNEL=tma in the environment) selects the bulk-copy kernel; it
+    // LNCDE_FLAG_K1_TMA (or the "k1_tma" tuning value, tuning.h) selects the bulk-copy kernel; it
     // needs a 16-byte aligned `data` so that the 16-byte floor of a tile's first float never precedes
     // the buffer.  Default: the classic kernel (the one measured on B200 so far).
-    static const bool env_tma = getenv("LNCDE_LEVY_KERNEL") && getenv("LNCDE_LEVY_KERNEL")[0] == 't';
-    const bool use_tma = env_tma || (flags & LNCDE_FLAG_K1_TMA);
+    const bool use_tma = (flags & LNCDE_FLAG_K1_TMA) || tuning_value(kTuneK1Tma);
     if (use_tma && ((uintptr_t)data & 15) == 0) {
       switch (C) {
         case 1: return launch_levy_tma<1>(st, p, depth);

@@ -1,0 +1,16 @@
+// Kernel-variant switches (internal).  Every variant computes the same result; which one is faster is a
+// hardware question answered by measurement, so the choice is a process-wide tuning value settable through
+// lncde_set_tuning() (include/lncde_b200.h) or the environment (LNCDE_TUNE_<KEY>=0/1 read at first use).
+#pragma once
+
+namespace lncde {
+
+enum TuneKey {
+  kTuneK1Tma = 0,    // "k1_tma":   closed-form logsig kernel with TMA bulk-copy staging (logsig_levy_tma_kernel)
+  kTuneK3Fused = 1,  // "k3_fused": specialised Log-NCDE kernels with the 32 x 32 layer phases fused on single warps
+  kTuneCount
+};
+
+int tuning_value(int key);
+
+}  // namespace lncde

@@ -24,6 +24,8 @@ def _declare(lib):
     sig = {
         "lncde_version": (C.c_char_p, []),
         "lncde_strerror": (C.c_char_p, [i]),
+        "lncde_set_tuning": (i, [C.c_char_p, i]),
+        "lncde_get_tuning": (i, [C.c_char_p]),
         "lncde_hall_size": (i, [i, i]),
         "lncde_hall_basis": (i, [i, i, vp]),
         "lncde_tensor_dim": (i64, [i, i]),
@@ -65,6 +67,18 @@ def lib():
             EXPORTS = _declare(handle)
             _lib = handle
     return _lib
+
+
+def set_tuning(key: str, value: int) -> None:
+    """Select a kernel variant ("k1_tma", "k3_fused"); every variant computes the same result."""
+    check(lib().lncde_set_tuning(key.encode(), int(value)), f"lncde_set_tuning({key!r})")
+
+
+def get_tuning(key: str) -> int:
+    v = lib().lncde_get_tuning(key.encode())
+    if v < 0:
+        check(v, f"lncde_get_tuning({key!r})")
+    return v
 
 
 def check(status: int, what: str = ""):

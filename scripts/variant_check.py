@@ -1,0 +1,167 @@
+"""Kernel variants on the GPU, in a process of their own.  Prints ONE JSON line:
+
+  k1: ``calc_paths(kernel="tma")`` (logsig_levy_tma_kernel) - parity against the fp64 oracle and the classic
+      kernel (bit-identical), CUDA-event timings of both at the roofline shape (B=2048 x EigenWorms);
+  k3: ``set_tuning("k3_fused", 1)`` (specialised Log-NCDE kernels with the 32 x 32 layer phases fused on single
+      warps) - loss, gradient and solver states against the default kernels, CUDA-event timings of the
+      EigenWorms train step (forward + adjoint) under both settings.
+
+Used by tests/test_zz_variants_gpu.py and by the autotune leg of bench.py, which run it as a subprocess so that
+a fault or hang in a variant that has not been on hardware yet cannot take the caller's CUDA context with it.
+
+    python scripts/variant_check.py [--no-timing] [--no-parity] [--only k1|k3]
+"""
+import json
+import os
+import sys
+
+R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, R)
+sys.path.insert(0, os.path.join(R, "log-neural-cdes_b200"))
+
+import numpy as np
+import torch
+
+
+def parity():
+    from lncde.data_dir.generate_paths import calc_paths
+    from oracle import paths
+
+    res = {"cases": 0, "bit_identical_to_classic": True, "max_rel_err_vs_fp64_oracle": 0.0, "integer_kat_exact": True}
+    rng = np.random.default_rng(3)
+    # integer KATs (bit-exact), all widths / odd sizes / every tile phase
+    for C in range(1, 9):
+        for depth in (1, 2):
+            x = np.cumsum(np.round(rng.normal(size=(5, 101, C))), axis=1).astype(np.float32)
+            xd = torch.from_numpy(x).cuda()
+            for s in (1, 4, 7, 12, 16, 100, 102, 500):
+                if s * C > 640:
+                    continue
+                want = paths.calc_paths(x, s, depth, np.float64)
+                a = calc_paths(xd, s, depth, kernel="tma").cpu().numpy()
+                b = calc_paths(xd, s, depth, kernel="classic").cpu().numpy()
+                res["cases"] += 1
+                res["integer_kat_exact"] &= bool(np.array_equal(a.astype(np.float64), want))
+                res["bit_identical_to_classic"] &= bool(np.array_equal(a, b))
+    # float paths at the BASELINE shapes (short batch)
+    for C, s, L in [(7, 12, 17984), (6, 12, 17984), (6, 16, 896), (7, 10, 4992), (4, 10, 4992), (7, 16, 896)]:
+        x = np.cumsum(rng.normal(scale=0.05, size=(3, L, C)), axis=1).astype(np.float32)
+        xd = torch.from_numpy(x).cuda()
+        want = paths.calc_paths(x, s, 2, np.float64)
+        a = calc_paths(xd, s, 2, kernel="tma").cpu().numpy()
+        b = calc_paths(xd, s, 2, kernel="classic").cpu().numpy()
+        res["cases"] += 1
+        res["bit_identical_to_classic"] &= bool(np.array_equal(a, b))
+        err = float(np.abs(a - want).max() / np.abs(want).max())
+        res["max_rel_err_vs_fp64_oracle"] = max(res["max_rel_err_vs_fp64_oracle"], err)
+    res["ok"] = bool(res["integer_kat_exact"] and res["bit_identical_to_classic"]
+                     and res["max_rel_err_vs_fp64_oracle"] < 1e-5)
+    return res
+
+
+def timing(B=2048, L=17984, C=7, s=12, reps=10):
+    from lncde.data_dir.generate_paths import calc_paths
+
+    x = (torch.randn(64, L, C, device="cuda") * 0.05).cumsum(1).repeat(B // 64, 1, 1)
+    x += 0.001 * torch.randn(B, 1, 1, device="cuda")
+    out = torch.empty((B, (L + 1 + s - 1) // s, 1 + C + C * (C - 1) // 2), device="cuda")
+    byts = x.numel() * 4 + out.numel() * 4
+    res = {"shape": f"B={B} x L={L} x C={C}, stepsize {s}, depth 2", "algorithmic_bytes": byts}
+    for k in ("classic", "tma"):
+        for _ in range(3):
+            calc_paths(x, s, 2, out=out, kernel=k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            calc_paths(x, s, 2, out=out, kernel=k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        res[k] = {"ms": ms, "GB/s": byts / ms / 1e6}
+    return res
+
+
+def _eigenworms_step(B, n_windows, seed=0):
+    """Model, inputs and a closure running loss + flat gradient of the EigenWorms Log-NCDE config on a path of
+    n_windows * 12 - 1 samples (n_windows = 1499 is the full BASELINE length)."""
+    from lncde import train as T
+    from lncde.data_dir.datasets import make_intervals, make_ts
+    from lncde.data_dir.generate_paths import calc_paths, logsig_dim
+    from lncde.models.generate_model import create_model
+
+    C, s, H = 7, 12, 128
+    L = n_windows * s - 1
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(B, L, C, device="cuda", generator=g) * 0.05).cumsum(1)
+    x[..., 0] = torch.arange(L, device="cuda") / L
+    ts0 = make_ts(L)
+    iv = make_intervals(ts0, s)
+    model, _ = create_model("log_ncde", C, logsig_dim(C, 2), 2, iv, 5, H, vf_depth=2, vf_width=32, dt0=1.0 / n_windows,
+                            scale=1000.0, lambd=1e-3, key=2345, device=torch.device("cuda"))
+    ts = torch.from_numpy(ts0)[None, :].expand(B, -1)
+    y = torch.eye(5, device="cuda")[torch.arange(B, device="cuda") % 5]
+    ls = calc_paths(x, s, 2)
+
+    def step():
+        return T.classification_loss(model, (ts, ls, x[:, 0, :]), y)
+
+    return model, step
+
+
+def k3_parity():
+    from lncde import _lib
+
+    res = {"cases": 0, "max_rel_diff_grad": 0.0, "max_rel_diff_loss": 0.0}
+    for B, nwin in ((3, 40), (32, 200)):
+        model, step = _eigenworms_step(B, nwin, seed=B)
+        _lib.set_tuning("k3_fused", 0)
+        l0, g0 = step()
+        _lib.set_tuning("k3_fused", 1)
+        l1, g1 = step()
+        _lib.set_tuning("k3_fused", 0)
+        torch.cuda.synchronize()
+        res["cases"] += 1
+        res["max_rel_diff_loss"] = max(res["max_rel_diff_loss"], abs(float(l1) - float(l0)) / max(abs(float(l0)), 1e-30))
+        res["max_rel_diff_grad"] = max(res["max_rel_diff_grad"],
+                                       float((g1 - g0).abs().max() / g0.abs().max().clamp_min(1e-30)))
+    res["ok"] = bool(res["max_rel_diff_loss"] < 1e-6 and res["max_rel_diff_grad"] < 1e-5)
+    return res
+
+
+def k3_timing(reps=5):
+    from lncde import _lib
+
+    model, step = _eigenworms_step(32, 1499)
+    res = {"shape": "EigenWorms Log-NCDE train step (loss + adjoint), B=32, 1499 Heun steps, eager launches"}
+    for name, v in (("default", 0), ("fused", 1)):
+        _lib.set_tuning("k3_fused", v)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = {"ms": e0.elapsed_time(e1) / reps}
+    _lib.set_tuning("k3_fused", 0)
+    return res
+
+
+if __name__ == "__main__":
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    out = {}
+    for name, par, tim in (("k1", parity, timing), ("k3", k3_parity, k3_timing)):
+        if only not in (None, name):
+            continue
+        out[name] = {}
+        try:
+            if "--no-parity" not in sys.argv:
+                out[name]["parity"] = par()
+            if "--no-timing" not in sys.argv:
+                out[name]["timing"] = tim()
+        except Exception as e:  # report, keep going with the other variant
+            out[name]["error"] = f"{type(e).__name__}: {e}"[:300]
+    print(json.dumps(out))

@@ -43,6 +43,10 @@ def lib():
     return _lib
 
 
+def set_tuning(key, value):
+    assert lib().lncde_set_tuning(key.encode(), int(value)) == 0
+
+
 def bulk_copies():
     """Bulk (TMA) copies issued by the emulated kernels since the last call."""
     return lib().emu_bulk_copies()

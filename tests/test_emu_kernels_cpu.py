@@ -165,6 +165,31 @@ def test_emu_logncde_forward_and_adjoint(case):
     assert rel_err(gp_r, gp_o) < 5 * TOL
 
 
+@pytest.mark.parametrize("case", [c for c in SOLVE_CASES if c[5:8] == (128, 32, 2)])
+def test_emu_logncde_fused_variant_bit_identical(case):
+    """lncde_set_tuning("k3_fused", 1): the single-warp 32 x 32 phases form the same sums in the same order as
+    the K-sliced default, so forward states, saved-mode and recomputing adjoints agree bit for bit."""
+    B, L, C, s, depth, H, width, n_hidden, dt0, scale = case
+    logsig, rows, sc, grid, layers, y0 = _setup(B, L, C, s, depth, H, width, n_hidden, dt0, scale)
+    dims = (H, C, width, n_hidden, depth)
+    g_ys = np.random.default_rng(1).normal(size=(B, len(grid), H))
+    flat = O.flatten_params(layers).numpy()
+    ref = E.logncde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, dims, g_ys)
+    ref_r = E.logncde_bwd_recompute(flat, logsig, ref[0], rows, sc, dims, g_ys)
+    E.set_tuning("k3_fused", 1)
+    try:
+        got = E.logncde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, dims, g_ys)
+        got_i = E.logncde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, dims, None, train=False)
+        got_r = E.logncde_bwd_recompute(flat, logsig, got[0], rows, sc, dims, g_ys)
+    finally:
+        E.set_tuning("k3_fused", 0)
+    for a, b in zip(ref + ref_r, got + got_r):
+        assert np.array_equal(a, b)
+    assert np.array_equal(got_i[0], ref[0])
+    ys_o, gp_o, gy_o = _oracle(layers, logsig, y0, rows, sc, dims, torch.from_numpy(g_ys))
+    assert rel_err(got[0], ys_o) < TOL and rel_err(got[1], gp_o) < 5 * TOL and rel_err(got[2], gy_o) < 5 * TOL
+
+
 # ------------------------------------------------------------------------------------------ K2
 @pytest.mark.parametrize("nb,bs,T,n_basis", [(16, 1, 40, 3), (8, 4, 33, 6), (4, 8, 20, 6), (2, 32, 12, 3),
                                              (1, 64, 9, 6), (3, 5, 14, 3)])

@@ -86,3 +86,39 @@ def test_lncde_error_without_gpu_paths():
         pytest.skip("GPU present")
     with pytest.raises(_lib.LncdeError):
         _lib.require_cuda(torch.zeros(1))
+
+
+def test_bench_autotune_decision():
+    """bench.py switches a kernel variant on only if its own parity check passed AND it was measurably faster."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ok, bad = {"ok": True}, {"ok": False}
+    t = lambda a, b, ka, kb: {ka: {"ms": a}, kb: {"ms": b}}
+    rep = {"k1": {"parity": ok, "timing": t(0.33, 0.25, "classic", "tma")},
+           "k3": {"parity": ok, "timing": t(19.0, 18.9, "default", "fused")}}
+    assert bench.decide_tuning(rep) == {"k1_tma": 1, "k3_fused": 0}       # 0.5 % is inside the noise margin
+    rep["k1"]["parity"] = bad
+    rep["k3"]["timing"] = t(19.0, 15.0, "default", "fused")
+    assert bench.decide_tuning(rep) == {"k1_tma": 0, "k3_fused": 1}       # faster but wrong is never used
+    assert bench.decide_tuning({"k1": {"error": "x"}, "k3": {"parity": ok}}) == {"k1_tma": 0, "k3_fused": 0}
+    assert bench.decide_tuning({}) == {"k1_tma": 0, "k3_fused": 0}
+
+
+def test_tuning_api_roundtrip(built_lib):
+    from lncde import _lib
+
+    for key in ("k1_tma", "k3_fused"):
+        old = _lib.get_tuning(key)
+        _lib.set_tuning(key, 1)
+        assert _lib.get_tuning(key) == 1
+        _lib.set_tuning(key, old)
+        assert _lib.get_tuning(key) == old
+    import pytest
+
+    with pytest.raises(_lib.LncdeError):
+        _lib.set_tuning("no_such_key", 1)
