@@ -4,8 +4,9 @@ Restates ``models/LinearNeuralCDEs.py``: ``log_ode`` (:192-232), the diagonal br
 (:302-316), the block branch (:318-353), the scanner incl. the parallel_steps chunk /
 remainder logic (:355-386) and the read-outs (:389-394).  The basis list comes from the
 Hall set (roughpy 0.2.0, un-vendored, enumerates the same Hall basis – equal by inspection
-at depth <= 2, assumed at depth 3: UNPINNED).
-PARITY UNPINNED by reference outputs."""
+at depth <= 2, assumed at depth 3: that ORDER is unpinned).
+PINNED to the reference's own LogLinearCDE.__call__ / log_ode / losses, executed from /root/reference
+under library stand-ins (tests/golden/ref_linear.npz, tests/test_oracle_reference_pinned.py)."""
 from __future__ import annotations
 
 import torch

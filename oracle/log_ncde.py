@@ -9,7 +9,9 @@ tableau c=[1], a=[[1]], b=[1/2,1/2]; ``tnext = tprev + dt``, clipped to t1 when
 within 1e-6 in fp32; default adjoint = exact gradient of the discrete
 recurrences, which torch autograd of this loop reproduces) and the read-outs.
 
-PARITY UNPINNED by reference outputs (jax/diffrax/equinox absent offline).
+PINNED to the reference's own LogNeuralCDE.__call__ / create_model / losses, executed from
+/root/reference under library stand-ins (tests/golden/ref_logncde.npz,
+tests/test_oracle_reference_pinned.py); the diffrax / equinox semantics are restated.
 """
 from __future__ import annotations
 

@@ -8,7 +8,9 @@ Restates ``data_dir/generate_paths.py:14-77`` and ``data_dir/datasets.py:43-71,
 * B3 – the time axis is zero-prepended first (generate_paths.py:30-32), so
   window k covers original points k*s-1 .. k*s+s-2.
 
-PARITY UNPINNED by reference outputs (signax absent offline).
+PINNED to the reference's own calc_paths / batch_calc_paths, executed from /root/reference under
+library stand-ins (tests/golden/ref_paths.npz, tests/test_oracle_reference_pinned.py); the
+signax semantics underneath (oracle.tensor_algebra) are restated, see oracle/__init__.py.
 """
 from __future__ import annotations
 

@@ -10,8 +10,10 @@ README.md:98; NOT vendored in /root/reference, not installed offline) as used at
 * ``log``: truncated series ``log(1+x) = sum_n (-1)^(n+1) x^n / n``.
 * ``flatten``: concatenation of the C-order ravelled levels 1..depth (no scalar).
 
-PARITY UNPINNED by reference outputs (no signax offline, no reference test
-vectors); anchored by identities in tests/test_oracle_logsig.py.
+PARITY UNPINNED against signax itself (not installable offline, no reference test vectors);
+anchored by identities in tests/test_oracle_logsig.py and by agreement (1e-14) with the independent
+implementation in tests/golden/refshim/signax that the reference's calc_paths runs on when the
+golden fixtures are generated.
 
 All functions broadcast over leading batch axes; levels are arrays of shape
 ``batch + (C,)*k``.

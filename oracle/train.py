@@ -3,7 +3,8 @@
 Restates train.py:71-136 (loss, value_and_grad, optax.adam update) around
 oracle.log_ncde.solve.  Used by tests and as the timed CPU baseline of bench.py
 (kind "port": the reference's JAX-CPU path cannot run offline).
-PARITY UNPINNED by reference outputs."""
+The loss formulas are pinned through oracle.log_ncde / oracle.linear_ncde (tests/golden/ref_*.npz);
+the optax.adam update is restated (optax absent offline): unpinned."""
 from __future__ import annotations
 
 import numpy as np

@@ -1,0 +1,175 @@
+"""Generate tests/golden/ref_*.npz by EXECUTING THE REFERENCE'S OWN SOURCE FILES from /root/reference under the
+library stand-ins of tests/golden/refshim (jax / equinox / diffrax / signax / roughpy are not installable offline;
+see refshim/README.md for what this pins and what it cannot).
+
+    python tests/golden/make_golden_ref.py          (needs /root/reference; fixtures are committed)
+
+Files executed unmodified: data_dir/generate_paths.py (calc_paths), data_dir/datasets.py (batch_calc_paths),
+data_dir/hall_set.py, models/generate_model.py (create_model), models/LogNeuralCDEs.py, models/NeuralCDEs.py
+(VectorField), models/LinearNeuralCDEs.py, train.py (calc_output, classification_loss, regression_loss).
+All arithmetic is float64 except what the reference keeps in float32 by construction (time grids).
+"""
+import os
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("LNCDE_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+sys.path.insert(0, REF)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+
+
+# model families / preprocessing outside the hot path: imported by generate_model.py and
+# datasets.py at module level, never called here
+_out = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("outside the hot path"))  # noqa: E731
+_stub("models.LRU", LRU=_out)
+_stub("models.S5", S5=_out)
+_stub("models.RNN", GRUCell=_out, LinearCell=_out, LSTMCell=_out, MLPCell=_out, RNN=_out)
+_stub("data_dir.generate_coeffs", calc_coeffs=_out)
+
+import diffrax  # noqa: E402  (refshim)
+import train as ref_train  # noqa: E402
+from data_dir.datasets import batch_calc_paths as ref_batch_calc_paths  # noqa: E402
+from data_dir.generate_paths import calc_paths as ref_calc_paths  # noqa: E402
+from models.generate_model import create_model as ref_create_model  # noqa: E402
+
+
+def T(a, dtype=torch.float64):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+
+
+def make_ts(L):  # datasets.py:143-156 with T = 1: fp32 (T / L) * arange(L)
+    return (np.float32(1.0 / L) * np.arange(L, dtype=np.float32)).astype(np.float32)
+
+
+def make_intervals(ts, s):  # datasets.py:161-163
+    idx = np.arange(0, len(ts), s)
+    return np.concatenate([ts[idx], np.array([1.0], np.float32)]).astype(np.float32)
+
+
+def paths_cases():
+    rng = np.random.default_rng(20261020)
+    out = {}
+    cases = [(3, 30, 3, 4, 2), (5, 25, 2, 7, 2), (4, 17, 3, 4, 1), (2, 12, 4, 12, 2), (2, 13, 3, 20, 2), (3, 11, 2, 1, 2),
+             (3, 8, 2, 9, 2), (2, 47, 7, 12, 2), (2, 36, 6, 12, 2), (3, 21, 1, 5, 2)]
+    for i, (B, L, C, s, d) in enumerate(cases):
+        x = np.cumsum(rng.normal(size=(B, L, C)), axis=1)
+        out[f"x{i}"] = x
+        out[f"cfg{i}"] = np.array([B, L, C, s, d])
+        out[f"logsig{i}"] = ref_calc_paths(T(x), s, d).numpy()
+    out["n"] = np.array(len(cases))
+    # datasets.py:43-71: chunks of 128 samples (the remainder-window quirk restarts at every chunk)
+    x = np.cumsum(np.round(rng.normal(size=(131, 10, 2))), axis=1)
+    out["xb"] = x
+    out["cfgb"] = np.array([4, 2])
+    out["logsigb"] = ref_batch_calc_paths(T(x), 4, 2).numpy()
+    np.savez_compressed(os.path.join(HERE, "ref_paths.npz"), **out)
+    print("ref_paths.npz:", len(cases) + 1, "cases")
+
+
+def _flat_mlp(model):
+    return np.concatenate([np.concatenate([l.weight.detach().numpy().ravel(), l.bias.detach().numpy().ravel()])
+                           for l in model.vf.mlp.layers])
+
+
+def logncde_cases():
+    rng = np.random.default_rng(7)
+    out = {}
+    #        B, L,  C, s, depth, H, width, n_hidden, dt0, scale, lambd, classification, output_step, label_dim
+    cases = [(3, 40, 3, 4, 2, 16, 8, 2, 0.05, 1.0, 0.01, True, 1, 3),
+             (2, 40, 3, 4, 1, 16, 8, 2, 0.05, 1.0, 0.0, True, 1, 2),
+             (2, 64, 3, 4, 2, 16, 8, 2, 0.04, 1.0, 0.01, False, 8, 1),
+             (2, 36, 5, 3, 2, 24, 12, 3, 0.031, 2.0, 0.001, True, 1, 4),
+             (2, 96, 7, 12, 2, 128, 32, 2, 0.11, 3.0, 0.001, True, 1, 5),
+             (2, 50, 4, 5, 1, 12, 8, 1, 0.013, 1.0, 0.0, False, 7, 1)]
+    for i, (B, L, C, s, depth, H, width, nh, dt0, scale, lambd, cls, ostep, ld) in enumerate(cases):
+        x = np.cumsum(rng.normal(scale=0.3, size=(B, L, C)), axis=1)
+        ts = make_ts(L)
+        iv = make_intervals(ts, s)
+        logsig = ref_calc_paths(T(x), s, depth)
+        model, state = ref_create_model("log_ncde", C, logsig.shape[-1], depth, T(iv, torch.float32), ld, H,
+                                        vf_depth=nh, vf_width=width, classification=cls, output_step=ostep,
+                                        solver=diffrax.Heun(), stepsize_controller=diffrax.ConstantStepSize(), dt0=dt0,
+                                        scale=scale, lambd=lambd, key=100 + i)
+        assert state is None
+        X = (T(np.tile(ts, (B, 1)), torch.float32), logsig, T(x[:, 0, :]))
+        pred, _ = ref_train.calc_output(model, X, None, None, model.stateful, model.nondeterministic)
+        if cls:
+            y = np.eye(ld)[rng.integers(0, ld, size=B)]
+            (loss, _), _ = ref_train.classification_loss(model, None, X, T(y), None, None)
+        else:
+            y = rng.normal(size=(B, pred.shape[1]))
+            (loss, _), _ = ref_train.regression_loss(model, None, X, T(y), None, None)
+        out[f"cfg{i}"] = np.array([B, L, C, s, depth, H, width, nh, int(cls), ostep, ld])
+        out[f"hyper{i}"] = np.array([dt0, scale, lambd])
+        out[f"x{i}"], out[f"logsig{i}"], out[f"y{i}"] = x, logsig.numpy(), y
+        out[f"mlp{i}"] = _flat_mlp(model)
+        out[f"lin1_{i}"] = np.concatenate([model.linear1.weight.numpy().ravel(), model.linear1.bias.numpy()])
+        out[f"lin2_{i}"] = np.concatenate([model.linear2.weight.numpy().ravel(), model.linear2.bias.numpy()])
+        out[f"pairs{i}"] = np.zeros((0, 2), np.int64) if model.pairs is None else np.asarray(model.pairs)
+        out[f"pred{i}"], out[f"loss{i}"] = pred.numpy(), np.array(float(loss))
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "ref_logncde.npz"), **out)
+    print("ref_logncde.npz:", len(cases), "cases")
+
+
+def linear_cases():
+    rng = np.random.default_rng(11)
+    out = {}
+    #        name, B, L, C, s, depth, H, bs, P, lambd, classification, label_dim
+    cases = [("diagonal_linear_ncde", 3, 40, 3, 4, 1, 8, 1, 1, 0.1, True, 3),
+             ("diagonal_linear_ncde", 2, 45, 3, 4, 2, 8, 1, 4, 0.1, True, 2),     # depth-2 rows, level 1 used (quirk B7)
+             ("bd_linear_ncde", 2, 61, 3, 4, 2, 8, 4, 5, 0.05, True, 3),          # 3 chunks of 5 + remainder
+             ("bd_linear_ncde", 2, 41, 2, 4, 2, 6, 2, 128, 0.0, True, 2),         # T - 1 < parallel_steps
+             ("dense_linear_ncde", 2, 40, 3, 4, 2, 8, 8, 1, 0.1, False, 2),
+             ("bd_linear_ncde", 1, 40, 3, 4, 3, 8, 4, 3, 0.1, True, 3)]           # depth 3 (basis order: Hall set)
+    from data_dir.hall_set import HallSet
+
+    for i, (name, B, L, C, s, depth, H, bs, P, lambd, cls, ld) in enumerate(cases):
+        x = np.cumsum(rng.normal(scale=0.3, size=(B, L, C)), axis=1)
+        ts = make_ts(L)
+        if depth <= 2:
+            logsig = ref_calc_paths(T(x), s, depth)
+        else:  # the reference's calc_paths stops at depth 2: any Hall-ordered rows serve as INPUT of the LNCDE forward
+            D = len(HallSet(C, depth).data)
+            logsig = T(rng.normal(scale=0.1, size=(B, (L + 1 + s - 1) // s, D)))
+            logsig[..., 0] = 0
+        model, state = ref_create_model(name, C, logsig.shape[-1], depth, None, ld, H, block_size=bs, classification=cls,
+                                        lambd=lambd, parallel_steps=P, key=200 + i)
+        assert state is None
+        X = (T(np.tile(ts, (B, 1)), torch.float32), logsig, T(x[:, 0, :]))
+        pred, _ = ref_train.calc_output(model, X, None, None, model.stateful, model.nondeterministic)
+        if cls:
+            y = np.eye(ld)[rng.integers(0, ld, size=B)]
+            (loss, _), _ = ref_train.classification_loss(model, None, X, T(y), None, None)
+        else:
+            y = rng.normal(size=(B, pred.shape[1]))
+            (loss, _), _ = ref_train.regression_loss(model, None, X, T(y), None, None)
+        out[f"name{i}"] = np.array(name)
+        out[f"cfg{i}"] = np.array([B, L, C, s, depth, H, bs, P, int(cls), ld])
+        out[f"lambd{i}"] = np.array(lambd)
+        out[f"x{i}"], out[f"logsig{i}"], out[f"y{i}"] = x, logsig.numpy(), y
+        out[f"vfA{i}"] = model.vf_A.numpy()
+        out[f"init{i}"] = np.concatenate([model.init_layer.weight.numpy().ravel(), model.init_layer.bias.numpy()])
+        out[f"out{i}"] = np.concatenate([model.out_layer.weight.numpy().ravel(), model.out_layer.bias.numpy()])
+        out[f"basis{i}"] = np.array(str(model.basis_list))
+        out[f"pred{i}"], out[f"loss{i}"] = pred.numpy(), np.array(float(loss))
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "ref_linear.npz"), **out)
+    print("ref_linear.npz:", len(cases), "cases")
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, HERE)
+    paths_cases()
+    logncde_cases()
+    linear_cases()

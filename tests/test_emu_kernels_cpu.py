@@ -214,3 +214,71 @@ def test_emu_linear_scan_forward_and_adjoint(nb, bs, T, n_basis):
     assert rel_err(ys_e, ys_o.detach().numpy()) < TOL
     assert rel_err(gy_e, y0_t.grad.numpy()) < 5 * TOL
     assert rel_err(gl_e, lie_t.grad.numpy()) < 5 * TOL
+
+
+# ------------------------------------------------------------------------------------------ reference-executed fixtures
+# tests/golden/ref_*.npz hold outputs of the reference's OWN code (tests/golden/make_golden_ref.py): the emulated
+# kernels are compared with them directly, the oracle only supplies the glue the reference does in its host code.
+from conftest import GOLDEN  # noqa: E402
+
+_P = np.load(os.path.join(GOLDEN, "ref_paths.npz"))
+_N = np.load(os.path.join(GOLDEN, "ref_logncde.npz"))
+_LN = np.load(os.path.join(GOLDEN, "ref_linear.npz"))
+
+
+@pytest.mark.parametrize("tma", [False, True])
+@pytest.mark.parametrize("i", range(int(_P["n"])))
+def test_emu_logsig_vs_reference_code(i, tma):
+    B, L, C, s, d = (int(v) for v in _P[f"cfg{i}"])
+    got = E.calc_paths(_P[f"x{i}"], s, d, tma=tma)
+    assert got.shape == _P[f"logsig{i}"].shape
+    assert rel_err(got, _P[f"logsig{i}"]) < TOL
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("i", range(int(_N["n"])))
+def test_emu_logncde_vs_reference_code(i, fused):
+    B, L, C, s, depth, H, width, nh, cls, ostep, ld = (int(v) for v in _N[f"cfg{i}"])
+    dt0 = float(_N[f"hyper{i}"][0])
+    ts = paths.make_ts(L)
+    iv = paths.make_intervals(ts, s)
+    rows, sc, grid = O.stage_table(ts, iv, dt0, _N[f"logsig{i}"].shape[1])
+    l1, l2 = _N[f"lin1_{i}"], _N[f"lin2_{i}"]
+    W1, b1, W2, b2 = l1[: H * C].reshape(H, C), l1[H * C :], l2[: ld * H].reshape(ld, H), l2[ld * H :]
+    y0 = _N[f"x{i}"][:, 0] @ W1.T + b1
+    E.set_tuning("k3_fused", fused)
+    try:
+        ys, _, _ = E.logncde_fwd_bwd(_N[f"mlp{i}"], _N[f"logsig{i}"], y0, rows, sc, (H, C, width, nh, depth), None,
+                                     train=False)
+    finally:
+        E.set_tuning("k3_fused", 0)
+    ys = torch.from_numpy(ys).double()
+    if cls:
+        pred = torch.softmax(ys[:, -1] @ torch.from_numpy(W2).T + torch.from_numpy(b2), -1)
+    else:
+        out = torch.cat([O.interp_outputs(ys, grid, O.regression_times(L, ostep)), ys[:, -1:]], 1)
+        pred = torch.tanh(out @ torch.from_numpy(W2).T + torch.from_numpy(b2))
+    assert rel_err(pred.numpy(), _N[f"pred{i}"]) < TOL
+
+
+@pytest.mark.parametrize("i", range(int(_LN["n"])))
+def test_emu_linear_scan_vs_reference_code(i):
+    B, L, C, s, depth, H, bs, Psteps, cls, ld = (int(v) for v in _LN[f"cfg{i}"])
+    vfA = torch.from_numpy(_LN[f"vfA{i}"])
+    ini, out = _LN[f"init{i}"], _LN[f"out{i}"]
+    Wi, bi, Wo, bo = ini[: H * C].reshape(H, C), ini[H * C :], out[: ld * H].reshape(ld, H), out[ld * H :]
+    nb = H // bs
+    if bs == 1:
+        lie = vfA.T.reshape(nb, 1, 1, C).numpy()
+    else:
+        from oracle.hall import Hall
+
+        hall = Hall(C, depth)
+        vfs = vfA.reshape(C, nb, bs, bs)
+        lie = torch.stack([OL.log_ode(vfs[:, b], hall) for b in range(nb)]).numpy()
+    y0 = _LN[f"x{i}"][:, 0] @ Wi.T + bi
+    ys, _, _ = E.linear_scan(lie, _LN[f"logsig{i}"], y0, nb, bs)
+    ys = torch.from_numpy(ys).double()
+    Wo_t, bo_t = torch.from_numpy(Wo), torch.from_numpy(bo)
+    pred = torch.softmax(ys.mean(1) @ Wo_t.T + bo_t, -1) if cls else torch.tanh(ys @ Wo_t.T + bo_t)
+    assert rel_err(pred.numpy(), _LN[f"pred{i}"]) < TOL

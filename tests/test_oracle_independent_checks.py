@@ -1,4 +1,4 @@
-"""Independent cross-checks of the (reference-output-unpinned) oracles: every restatement of a
+"""Independent cross-checks of the third-party semantics the oracles restate (signax, diffrax; see oracle/__init__.py): every restatement of a
 third-party algorithm is compared with a second, structurally different derivation of the
 same mathematics, so an error in the restatement cannot hide."""
 import itertools

@@ -1,4 +1,4 @@
-"""Identities that anchor the (reference-output-unpinned) signature/log/calc_paths oracle."""
+"""Identities that anchor the signature/log restatement (signax itself is absent offline) and calc_paths."""
 import numpy as np
 import pytest
 
