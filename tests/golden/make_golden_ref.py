@@ -101,14 +101,25 @@ def logncde_cases():
                                         solver=diffrax.Heun(), stepsize_controller=diffrax.ConstantStepSize(), dt0=dt0,
                                         scale=scale, lambd=lambd, key=100 + i)
         assert state is None
+        leaves = [t for l in model.vf.mlp.layers for t in (l.weight, l.bias)] + [
+            model.linear1.weight, model.linear1.bias, model.linear2.weight, model.linear2.bias]
+        for t in leaves:
+            t.requires_grad_(True)
         X = (T(np.tile(ts, (B, 1)), torch.float32), logsig, T(x[:, 0, :]))
         pred, _ = ref_train.calc_output(model, X, None, None, model.stateful, model.nondeterministic)
+        pred = pred.detach()
         if cls:
             y = np.eye(ld)[rng.integers(0, ld, size=B)]
             (loss, _), _ = ref_train.classification_loss(model, None, X, T(y), None, None)
         else:
             y = rng.normal(size=(B, pred.shape[1]))
             (loss, _), _ = ref_train.regression_loss(model, None, X, T(y), None, None)
+        # gradient of the reference's own loss function (reverse mode through its code, incl. its jax.jvp calls)
+        grads = torch.autograd.grad(loss, leaves)
+        out[f"grad{i}"] = np.concatenate([g.numpy().ravel() for g in grads])
+        loss = loss.detach()
+        for t in leaves:
+            t.requires_grad_(False)
         out[f"cfg{i}"] = np.array([B, L, C, s, depth, H, width, nh, int(cls), ostep, ld])
         out[f"hyper{i}"] = np.array([dt0, scale, lambd])
         out[f"x{i}"], out[f"logsig{i}"], out[f"y{i}"] = x, logsig.numpy(), y
@@ -146,14 +157,23 @@ def linear_cases():
         model, state = ref_create_model(name, C, logsig.shape[-1], depth, None, ld, H, block_size=bs, classification=cls,
                                         lambd=lambd, parallel_steps=P, key=200 + i)
         assert state is None
+        leaves = [model.vf_A, model.init_layer.weight, model.init_layer.bias, model.out_layer.weight, model.out_layer.bias]
+        for t in leaves:
+            t.requires_grad_(True)
         X = (T(np.tile(ts, (B, 1)), torch.float32), logsig, T(x[:, 0, :]))
         pred, _ = ref_train.calc_output(model, X, None, None, model.stateful, model.nondeterministic)
+        pred = pred.detach()
         if cls:
             y = np.eye(ld)[rng.integers(0, ld, size=B)]
             (loss, _), _ = ref_train.classification_loss(model, None, X, T(y), None, None)
         else:
             y = rng.normal(size=(B, pred.shape[1]))
             (loss, _), _ = ref_train.regression_loss(model, None, X, T(y), None, None)
+        grads = torch.autograd.grad(loss, leaves)  # gradient of the reference's own loss function
+        out[f"grad{i}"] = np.concatenate([g.numpy().ravel() for g in grads])
+        loss = loss.detach()
+        for t in leaves:
+            t.requires_grad_(False)
         out[f"name{i}"] = np.array(name)
         out[f"cfg{i}"] = np.array([B, L, C, s, depth, H, bs, P, int(cls), ld])
         out[f"lambd{i}"] = np.array(lambd)

@@ -41,15 +41,18 @@ def test_batch_calc_paths_chunking_matches_reference_code():
 
 
 def logncde_oracle(i, dtype=torch.float64):
+    """(pred, loss, flat gradient in the layout [mlp | linear1 | linear2])."""
     B, L, C, s, depth, H, width, nh, cls, ostep, ld = (int(v) for v in N[f"cfg{i}"])
     dt0, scale, lambd = (float(v) for v in N[f"hyper{i}"])
     sizes = O.mlp_sizes(H, C, width, nh)
     flat, off, lay = torch.from_numpy(N[f"mlp{i}"]), 0, []
     for a, b in zip(sizes[:-1], sizes[1:]):
-        lay.append((flat[off : off + a * b].view(b, a), flat[off + a * b : off + a * b + b]))
+        lay.append((flat[off : off + a * b].view(b, a).clone().requires_grad_(True),
+                    flat[off + a * b : off + a * b + b].clone().requires_grad_(True)))
         off += b * (a + 1)
     l1, l2 = torch.from_numpy(N[f"lin1_{i}"]), torch.from_numpy(N[f"lin2_{i}"])
-    W1, b1, W2, b2 = l1[: H * C].view(H, C), l1[H * C :], l2[: ld * H].view(ld, H), l2[ld * H :]
+    W1, b1, W2, b2 = (t.clone().requires_grad_(True) for t in
+                      (l1[: H * C].view(H, C), l1[H * C :], l2[: ld * H].view(ld, H), l2[ld * H :]))
     ts = paths.make_ts(L)
     iv = paths.make_intervals(ts, s)
     logsig = torch.from_numpy(N[f"logsig{i}"])
@@ -64,7 +67,9 @@ def logncde_oracle(i, dtype=torch.float64):
         out = torch.cat([O.interp_outputs(ys, grid, O.regression_times(L, ostep)), ys[:, -1:]], 1)
         pred = torch.tanh(out @ W2.T + b2)
         loss = O.regression_loss(pred, y)
-    return pred, loss + O.lip2_norm(lay, lambd)
+    loss = loss + O.lip2_norm(lay, lambd)
+    grads = torch.autograd.grad(loss, [t for Wb in lay for t in Wb] + [W1, b1, W2, b2])
+    return pred.detach(), loss.detach(), torch.cat([g.reshape(-1) for g in grads])
 
 
 @pytest.mark.parametrize("i", range(int(N["n"])))
@@ -74,30 +79,36 @@ def test_logncde_matches_reference_code(i):
     assert rel_err(paths.calc_paths(N[f"x{i}"], s, depth, np.float64), N[f"logsig{i}"]) < 1e-12
     if depth == 2:
         assert np.array_equal(np.asarray(OH.Hall(C, 2).basis[1:]), N[f"pairs{i}"])
-    pred, loss = logncde_oracle(i)
+    pred, loss, grad = logncde_oracle(i)
     # the oracle folds dt / (interval length) into ONE fp32 factor, the reference divides then multiplies: 1e-7
     assert rel_err(pred.numpy(), N[f"pred{i}"]) < 5e-7
     assert abs(float(loss) - float(N[f"loss{i}"])) < 5e-7 * max(1.0, abs(float(N[f"loss{i}"])))
+    # gradient of the reference's own loss function (torch reverse mode THROUGH the reference's code)
+    assert rel_err(grad.numpy(), N[f"grad{i}"]) < 2e-6
 
 
 def linear_oracle(i):
     B, L, C, s, depth, H, bs, Psteps, cls, ld = (int(v) for v in LN[f"cfg{i}"])
     lambd = float(LN[f"lambd{i}"])
-    vfA = torch.from_numpy(LN[f"vfA{i}"])
+    vfA = torch.from_numpy(LN[f"vfA{i}"]).clone().requires_grad_(True)
     ini, out = torch.from_numpy(LN[f"init{i}"]), torch.from_numpy(LN[f"out{i}"])
-    Wi, bi, Wo, bo = ini[: H * C].view(H, C), ini[H * C :], out[: ld * H].view(ld, H), out[ld * H :]
+    Wi, bi, Wo, bo = (t.clone().requires_grad_(True) for t in
+                      (ini[: H * C].view(H, C), ini[H * C :], out[: ld * H].view(ld, H), out[ld * H :]))
     pred = OL.predict(vfA, Wi, bi, Wo, bo, torch.from_numpy(LN[f"logsig{i}"]), torch.from_numpy(LN[f"x{i}"][:, 0]), C, bs,
                       depth, bool(cls), Psteps)
     y = torch.from_numpy(LN[f"y{i}"])
     loss = O.classification_loss(pred, y) if cls else O.regression_loss(pred, y)
-    return pred, loss + OL.lip2_norm(vfA, lambd)
+    loss = loss + OL.lip2_norm(vfA, lambd)
+    grads = torch.autograd.grad(loss, [vfA, Wi, bi, Wo, bo])
+    return pred.detach(), loss.detach(), torch.cat([g.reshape(-1) for g in grads])
 
 
 @pytest.mark.parametrize("i", range(int(LN["n"])))
 def test_linear_ncde_matches_reference_code(i):
-    pred, loss = linear_oracle(i)
+    pred, loss, grad = linear_oracle(i)
     assert rel_err(pred.numpy(), LN[f"pred{i}"]) < 1e-12
     assert abs(float(loss) - float(LN[f"loss{i}"])) < 1e-12 * max(1.0, abs(float(LN[f"loss{i}"])))
+    assert rel_err(grad.numpy(), LN[f"grad{i}"]) < 1e-11
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference not mounted")

@@ -67,9 +67,11 @@ def test_log_ncde_vs_reference_code(built_lib, i):
     pred = model(X)
     assert rel_err(pred.detach().cpu().numpy(), N[f"pred{i}"]) < TOL
     y = torch.from_numpy(N[f"y{i}"]).float().cuda()
-    loss, _ = (T.classification_loss if cls else T.regression_loss)(model, X, y)
+    loss, grads = (T.classification_loss if cls else T.regression_loss)(model, X, y)
     want = float(N[f"loss{i}"])
     assert abs(float(loss) - want) < TOL * max(1.0, abs(want))
+    # gradient of the reference's own loss function, same flat layout [mlp | linear1 | linear2]
+    assert rel_err(grads.cpu().numpy(), N[f"grad{i}"]) < 5 * TOL
 
 
 @pytest.mark.parametrize("i", range(int(LN["n"])))
@@ -92,6 +94,7 @@ def test_linear_ncde_vs_reference_code(built_lib, i):
     pred = model(X)
     assert rel_err(pred.detach().cpu().numpy(), LN[f"pred{i}"]) < TOL
     y = torch.from_numpy(LN[f"y{i}"]).float().cuda()
-    loss, _ = (T.classification_loss if cls else T.regression_loss)(model, X, y)
+    loss, grads = (T.classification_loss if cls else T.regression_loss)(model, X, y)
     want = float(LN[f"loss{i}"])
     assert abs(float(loss) - want) < TOL * max(1.0, abs(want))
+    assert rel_err(grads.cpu().numpy(), LN[f"grad{i}"]) < 5 * TOL  # layout [vf_A | init_layer | out_layer]
