@@ -3,8 +3,12 @@ models/LinearNeuralCDEs.py:55-396 over kernels K2 (flow build, scan, reverse sca
 gradient GEMM).  ``log_ode`` (:192-232) is a polynomial in the parameters only and stays in
 the host autograd; the kernel boundary is (lie, logsig, y0) -> ys.
 
-The diagonal+dense, Walsh-Hadamard, DPLR and sparse variants are outside the hot path
-(SURVEY.md §8 row f3)."""
+The remaining SLiCE structures of the reference are parameterisations of the same
+two scans and reuse the same kernels: Walsh-Hadamard (:319-329), diagonal-plus-low-rank (:322-325) and sparse
+(:319-321) build dense H x H vector fields and run the DE path; diagonal+dense (:273-300) runs a diagonal scan
+on the first H - bs state components and one dense bs x bs block on the rest.  The reference's two
+special-cased recurrent steps (:243-268, depth 1 and parallel_steps 1) are the same linear maps
+y -> (I + sum_c a_c A_c) y written without forming A_c; they take the DE path here."""
 from __future__ import annotations
 
 import math
@@ -64,25 +68,61 @@ class LogLinearCDE:
                  diagonal_dense=False, rank=0, sparsity=1.0, key, device="cuda"):
         if hidden_dim % block_size != 0:
             raise ValueError("hidden_dim must be divisible by block_size.")
-        if walsh_hadamard or diagonal_dense or rank > 0 or sparsity < 1.0:
-            raise NotImplementedError("only the D / BD / DE structures are on the B200 hot path")
         self.hidden_dim, self.block_size = int(hidden_dim), int(block_size)
         self.num_blocks = self.hidden_dim // self.block_size
         self.parallel_steps, self.logsig_depth = int(parallel_steps), int(logsig_depth)
         self.data_dim, self.label_dim = int(data_dim), int(label_dim)
         self.lambd, self.w_init_std, self.classification = float(lambd), float(w_init_std), bool(classification)
+        self.walsh_hadamard, self.diagonal_dense = bool(walsh_hadamard), bool(diagonal_dense)
+        self.rank, self.sparsity = int(rank), float(sparsity)
+        self.dense_size = 0
         self.device = torch.device(device)
         hs = HallSet(self.data_dim, self.logsig_depth)
         self.basis_list = hs.basis_list()  # what roughpy's lie_basis enumerates (:111-116)
         self._basis_pairs = hs.data
         self._levels = None
         C, H, bs, nb = self.data_dim, self.hidden_dim, self.block_size, self.num_blocks
-        n_A = C * nb * bs * bs
-        n_tot = n_A + H * (C + 1) + self.label_dim * (H + 1)
         gen = torch.Generator().manual_seed(int(key))
+        randn = lambda n: torch.randn(n, generator=gen)
+        # flat parameter vector: [structure-specific vector-field blocks | init_layer | out_layer]
+        self._sparse_idx = None
+        if self.diagonal_dense:  # (:124-136): vf_A_diag [C, H - bs], vf_A_dense [C, bs, bs]; vf_A stays None
+            blocks = [("vf_A_diag", (C, H - bs), randn(C * (H - bs)) * self.w_init_std),
+                      ("vf_A_dense", (C, bs, bs), randn(C * bs * bs) * self.w_init_std / math.sqrt(bs))]
+            self.dense_size = bs
+        elif self.sparsity < 1.0:  # (:137-153): nnz values at fixed random positions of [C, H, H]
+            total = C * H * H
+            nnz = int(round(total * self.sparsity))
+            if nnz == 0:
+                raise ValueError("sparsity too low, no weights left!")
+            self._sparse_idx = torch.randperm(total, generator=gen)[:nnz].sort().values.to(self.device)
+            blocks = [("_sparse_values", (nnz,), randn(nnz) * self.w_init_std / math.sqrt(H))]
+            self.block_size, self.num_blocks = H, 1
+        else:  # (:154-177)
+            blocks = [("vf_A", (C, nb * bs * bs), randn(C * nb * bs * bs) * self.w_init_std / math.sqrt(bs))]
+            if self.rank > 0:
+                if nb * bs * bs != H:
+                    raise ValueError("the low-rank structure needs block_size 1 (vf_A holds the diagonals, :324)")
+                r = self.rank
+                blocks += [("vf_A_u", (C, H, r), randn(C * H * r) * self.w_init_std / math.sqrt(r)),
+                           ("vf_A_v", (C, H, r), randn(C * H * r) * self.w_init_std / math.sqrt(r))]
+                self.block_size, self.num_blocks = H, 1
+        self.hadamard_matrix = None
+        if self.walsh_hadamard:  # (:181-188)
+            if self.diagonal_dense or self.rank > 0 or self.sparsity < 1.0 or nb * bs * bs != H:
+                raise ValueError("walsh_hadamard needs block_size 1 and no other structure (:326-328)")
+            from scipy.linalg import hadamard
+
+            self.hadamard_matrix = (torch.from_numpy(hadamard(H)).float() / math.sqrt(H)).to(self.device)
+            self.block_size, self.num_blocks = H, 1
+        n_A = sum(v.numel() for _, _, v in blocks)
+        n_tot = n_A + H * (C + 1) + self.label_dim * (H + 1)
         flat = torch.empty(n_tot, dtype=torch.float32)
-        flat[:n_A] = torch.randn(n_A, generator=gen) * self.w_init_std / math.sqrt(bs)  # (:156-160)
-        off = n_A
+        self._blocks, off = {}, 0
+        for name, shape, v in blocks:
+            flat[off : off + v.numel()] = v
+            self._blocks[name] = (off, shape)
+            off += v.numel()
         for i, o in ((C, H), (H, self.label_dim)):
             n = o * (i + 1)
             flat[off : off + n] = ((torch.rand(n, generator=gen, dtype=torch.float64) * 2 - 1) / math.sqrt(i)).float()
@@ -92,9 +132,36 @@ class LogLinearCDE:
         self.init_layer = _Linear(self.params, n_A, C, H)
         self.out_layer = _Linear(self.params, n_A + H * (C + 1), H, self.label_dim)
 
+    def _block(self, name):
+        if name not in self._blocks:
+            return None
+        off, shape = self._blocks[name]
+        n = 1
+        for d in shape:
+            n *= d
+        return self.params[off : off + n].view(*shape)
+
+    vf_A = property(lambda self: self._block("vf_A"))
+    vf_A_diag = property(lambda self: self._block("vf_A_diag"))
+    vf_A_dense = property(lambda self: self._block("vf_A_dense"))
+    vf_A_u = property(lambda self: self._block("vf_A_u"))
+    vf_A_v = property(lambda self: self._block("vf_A_v"))
+
     @property
-    def vf_A(self):
-        return self.params[: self.n_A].view(self.data_dim, self.num_blocks * self.block_size * self.block_size)
+    def vf_A_sparse(self):
+        """Object with ``.todense()`` -> [C, H, H] (what train.py:89-90 reads), or None."""
+        if self._sparse_idx is None:
+            return None
+        model = self
+
+        class _View:
+            @staticmethod
+            def todense():
+                C, H = model.data_dim, model.hidden_dim
+                dense = torch.zeros(C * H * H, device=model.device, dtype=torch.float32)
+                return dense.index_put((model._sparse_idx,), model._block("_sparse_values")).view(C, H, H)
+
+        return _View()
 
     def parameters(self):
         return [self.params]
@@ -126,14 +193,27 @@ class LogLinearCDE:
         ts, logsigs, x0 = X
         _lib.require_cuda(logsigs)
         y0 = self.init_layer(x0)
-        C, nb, bs = self.data_dim, self.num_blocks, self.block_size
-        if bs == 1:
-            lie = self.vf_A.t()                 # [H, C]: flows = 1 + logsig[:, 1:C+1] @ vf_A  (:303-305)
-            n_basis = C
+        C, H, nb, bs = self.data_dim, self.hidden_dim, self.num_blocks, self.block_size
+        logsigs = logsigs.contiguous()
+        if self.diagonal_dense:  # (:273-300): diagonal scan on the first H - bs components, one dense block on the rest
+            nd = H - self.dense_size
+            ys_d = _LinearScan.apply(self.vf_A_diag.t(), logsigs, y0[:, :nd], (nd, 1, C))
+            lie = self.log_ode(self.vf_A_dense.unsqueeze(1))
+            ys_e = _LinearScan.apply(lie, logsigs, y0[:, nd:], (1, self.dense_size, lie.shape[-1]))
+            return torch.cat([ys_d, ys_e], dim=-1)
+        if self._sparse_idx is not None:    # (:319-321)
+            vfs = self.vf_A_sparse.todense().view(C, 1, H, H)
+        elif self.rank > 0:                 # (:322-325): U_c V_c^T + diag(vf_A[c])
+            vfs = (torch.einsum("cir,cjr->cij", self.vf_A_u, self.vf_A_v) + torch.diag_embed(self.vf_A)).unsqueeze(1)
+        elif self.walsh_hadamard:           # (:326-328): vf_A[c, j] * Hm[i, j]
+            vfs = (self.vf_A[:, None, :] * self.hadamard_matrix[None, :, :]).view(C, 1, H, H)
+        elif bs == 1:
+            # [H, C]: flows = 1 + logsig[:, 1:C+1] @ vf_A  (:303-305)
+            return _LinearScan.apply(self.vf_A.t(), logsigs, y0, (nb, 1, C))
         else:
-            lie = self.log_ode(self.vf_A.view(C, nb, bs, bs))
-            n_basis = lie.shape[-1]
-        return _LinearScan.apply(lie, logsigs.contiguous(), y0, (nb, bs, n_basis))
+            vfs = self.vf_A.view(C, nb, bs, bs)
+        lie = self.log_ode(vfs)
+        return _LinearScan.apply(lie, logsigs, y0, (nb, bs, lie.shape[-1]))
 
     def __call__(self, X):
         ys = self.hidden_states(X)

@@ -20,15 +20,13 @@ def create_model(model_name, data_dim, logsig_dim, logsig_depth, intervals, labe
                              output_step, intervals, solver, stepsize_controller, dt0, max_steps, scale, lambd,
                              key=key, device=device), None)
     if model_name.endswith("_linear_ncde"):
-        if walsh_hadamard or diagonal_dense or sparsity < 1.0 or rank > 0:
-            raise NotImplementedError(
-                "walsh_hadamard / diagonal_dense / sparse / low-rank SLiCE variants are outside the B200 hot "
-                "path (SURVEY.md §8 row f3); D, BD and DE-LNCDE are supported")
         from .LinearNeuralCDEs import LogLinearCDE
 
         return (LogLinearCDE(data_dim=data_dim, hidden_dim=hidden_dim, label_dim=label_dim, block_size=block_size,
                              logsig_depth=logsig_depth, lambd=lambd, w_init_std=w_init_std,
-                             classification=classification, parallel_steps=parallel_steps, key=key, device=device),
+                             classification=classification, parallel_steps=parallel_steps,
+                             walsh_hadamard=walsh_hadamard, diagonal_dense=diagonal_dense, sparsity=sparsity, rank=rank,
+                             key=key, device=device),
                 None)
     if model_name in ("ncde", "nrde", "lru", "S5", "rnn_linear", "rnn_gru", "rnn_lstm", "rnn_mlp"):
         raise NotImplementedError(f"{model_name} is a comparison baseline outside the Log-ODE hot path (SURVEY.md §2)")

@@ -30,6 +30,8 @@ def _lip2(model):
             norm = norm + torch.mean(torch.linalg.norm(layer.weight, dim=-1) + torch.linalg.norm(layer.bias, dim=-1))
     elif getattr(model, "vf_A", None) is not None:
         norm = norm + torch.mean(torch.linalg.norm(model.vf_A, dim=-1))
+    elif getattr(model, "vf_A_sparse", None) is not None:  # train.py:89-91
+        norm = norm + torch.mean(torch.linalg.norm(model.vf_A_sparse.todense(), dim=-1))
     return norm * model.lambd
 
 

@@ -188,8 +188,63 @@ def linear_cases():
     print("ref_linear.npz:", len(cases), "cases")
 
 
+def slice_cases():
+    """The remaining SLiCE structures of LogLinearCDE (LinearNeuralCDEs.py:124-177, :243-300, :319-329)."""
+    rng = np.random.default_rng(13)
+    out = {}
+    #        kind, B, L, C, s, depth, H, bs, P, extra kwargs, classification, label_dim
+    cases = [("wh", 2, 40, 3, 4, 2, 8, 1, 4, dict(walsh_hadamard=True), True, 3),
+             ("wh", 2, 40, 3, 4, 1, 8, 1, 1, dict(walsh_hadamard=True), True, 2),      # special recurrent step :243-253
+             ("dplr", 2, 41, 3, 4, 2, 8, 1, 3, dict(rank=2), True, 3),
+             ("dplr", 2, 40, 3, 4, 1, 8, 1, 1, dict(rank=2), False, 1),                # special recurrent step :255-268
+             ("sparse", 2, 40, 2, 4, 2, 6, 1, 4, dict(sparsity=0.3), True, 2),
+             ("diagdense", 2, 45, 3, 4, 2, 12, 4, 5, dict(diagonal_dense=True), True, 3),
+             ("diagdense", 2, 40, 3, 4, 1, 12, 4, 1, dict(diagonal_dense=True), False, 2)]
+    for i, (kind, B, L, C, s, depth, H, bs, P, kw, cls, ld) in enumerate(cases):
+        x = np.cumsum(rng.normal(scale=0.3, size=(B, L, C)), axis=1)
+        ts = make_ts(L)
+        logsig = ref_calc_paths(T(x), s, depth)
+        model_name = {"wh": "wh", "dplr": "dplr", "sparse": "sparse", "diagdense": "diagonal_dense"}[kind] + "_linear_ncde"
+        model, state = ref_create_model(model_name, C, logsig.shape[-1], depth, None, ld, H, block_size=bs,
+                                        classification=cls, lambd=0.1, parallel_steps=P, key=300 + i, **kw)
+        names = {"wh": ["vf_A"], "dplr": ["vf_A", "vf_A_u", "vf_A_v"], "sparse": [], "diagdense": ["vf_A_diag", "vf_A_dense"]}[kind]
+        leaves = [getattr(model, n) for n in names]
+        if kind == "sparse":
+            dense = model.vf_A_sparse.todense()
+            leaves = [dense]
+        leaves += [model.init_layer.weight, model.init_layer.bias, model.out_layer.weight, model.out_layer.bias]
+        for t in leaves:
+            t.requires_grad_(True)
+        X = (T(np.tile(ts, (B, 1)), torch.float32), logsig, T(x[:, 0, :]))
+        pred, _ = ref_train.calc_output(model, X, None, None, model.stateful, model.nondeterministic)
+        pred = pred.detach()
+        if cls:
+            y = np.eye(ld)[rng.integers(0, ld, size=B)]
+            (loss, _), _ = ref_train.classification_loss(model, None, X, T(y), None, None)
+        else:
+            y = rng.normal(size=(B, pred.shape[1]))
+            (loss, _), _ = ref_train.regression_loss(model, None, X, T(y), None, None)
+        grads = torch.autograd.grad(loss, leaves)
+        for t in leaves:
+            t.requires_grad_(False)
+        out[f"kind{i}"] = np.array(kind)
+        out[f"cfg{i}"] = np.array([B, L, C, s, depth, H, bs, P, int(cls), ld])
+        out[f"kw{i}"] = np.array(str(kw))
+        out[f"x{i}"], out[f"logsig{i}"], out[f"y{i}"] = x, logsig.numpy(), y
+        out[f"vf{i}"] = np.concatenate([t.detach().numpy().ravel() for t in leaves[: len(leaves) - 4]])
+        out[f"vfgrad{i}"] = np.concatenate([g.numpy().ravel() for g in grads[: len(leaves) - 4]])
+        out[f"init{i}"] = np.concatenate([model.init_layer.weight.numpy().ravel(), model.init_layer.bias.numpy()])
+        out[f"out{i}"] = np.concatenate([model.out_layer.weight.numpy().ravel(), model.out_layer.bias.numpy()])
+        out[f"iograd{i}"] = np.concatenate([g.numpy().ravel() for g in grads[len(leaves) - 4 :]])
+        out[f"pred{i}"], out[f"loss{i}"] = pred.numpy(), np.array(float(loss.detach()))
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "ref_slice.npz"), **out)
+    print("ref_slice.npz:", len(cases), "cases")
+
+
 if __name__ == "__main__":
     sys.path.insert(0, HERE)
     paths_cases()
     logncde_cases()
     linear_cases()
+    slice_cases()

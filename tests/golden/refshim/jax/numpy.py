@@ -11,6 +11,8 @@ pi = _np.pi
 
 
 def asarray(x, dtype=None):
+    if dtype is torch.float32:
+        dtype = torch.float64  # value arrays run in the arbiter's precision (time grids never pass through here)
     if isinstance(x, torch.Tensor):
         return x if dtype is None else x.to(dtype)
     if isinstance(x, _np.ndarray):

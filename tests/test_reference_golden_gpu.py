@@ -98,3 +98,12 @@ def test_linear_ncde_vs_reference_code(built_lib, i):
     want = float(LN[f"loss{i}"])
     assert abs(float(loss) - want) < TOL * max(1.0, abs(want))
     assert rel_err(grads.cpu().numpy(), LN[f"grad{i}"]) < 5 * TOL  # layout [vf_A | init_layer | out_layer]
+
+
+@pytest.mark.parametrize("i", range(7))
+def test_slice_variants_vs_reference_code(built_lib, monkeypatch, i):
+    """Walsh-Hadamard / DPLR / sparse / diagonal + dense LogLinearCDE (tests/golden/ref_slice.npz) on the K2 kernels."""
+    import test_slice_variants_cpu as V
+
+    model, X, y, cls, kind = V.build(i, monkeypatch, device="cuda")
+    V.check(i, model, X, y, cls, kind, 2e-5)
