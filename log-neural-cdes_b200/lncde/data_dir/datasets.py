@@ -12,6 +12,7 @@ import dataclasses
 import numpy as np
 import torch
 
+from .dataloaders import Dataloader
 from .generate_paths import batch_calc_paths
 
 # name: (L, raw channels, time channel, stepsize, depth, n_classes / None for regression)
@@ -55,36 +56,89 @@ def make_intervals(ts0: np.ndarray, stepsize: int, T: float = 1.0) -> np.ndarray
 
 @dataclasses.dataclass
 class Dataset:
+    """data_dir/datasets.py:31-40."""
     name: str
-    data: torch.Tensor        # [N, L, C] on device
-    labels: torch.Tensor      # one-hot [N, n_classes] or [N, n_out]
-    ts: torch.Tensor          # [L]
-    paths: torch.Tensor       # logsig [N, K, D]
+    raw_dataloaders: dict
+    coeff_dataloaders: dict | None   # NCDE interpolation coefficients: outside the Log-ODE hot path (always None)
+    path_dataloaders: dict
     data_dim: int
     logsig_dim: int
     intervals: np.ndarray
     label_dim: int
 
-    def batch(self, idx):
-        """(X, y) with X = (ts, logsig, x0) as in datasets.py:185-200."""
-        ts = self.ts[None, :].expand(len(idx), -1)
-        return (ts, self.paths[idx], self.data[idx, 0, :]), self.labels[idx]
+
+def dataset_generator(name, data, labels, stepsize, depth, include_time, T, inmemory=True, idxs=None,
+                      use_presplit=False, *, key, device="cuda", paths_fn=None):
+    """Mirror of data_dir/datasets.py:105-232 for the raw and path (log-signature) dataloaders: 70 / 15 / 15
+    split by a random permutation (or ``idxs`` / pre-split tuples), ``ts`` (:143-156), log-signatures of every
+    split through K1 - ONE launch per split instead of the reference's loop over chunks of 128, same chunk
+    semantics (``batch_calc_paths``) - ``intervals`` (:161-163) and the ``(ts, logsig, x0)`` triples (:185-200).
+    Everything stays on ``device``; with ``inmemory=False`` the loaders keep pinned host copies instead.
+    As in the reference, ``idxs`` leaves the test split empty (:138-141)."""
+    paths_fn = paths_fn or batch_calc_paths
+    as_t = lambda a: a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
+    if idxs is None:
+        if use_presplit:
+            (train_data, val_data, test_data), (train_labels, val_labels, test_labels) = data, labels
+        else:
+            N = len(data)
+            gen = key if isinstance(key, torch.Generator) else torch.Generator().manual_seed(int(key))
+            perm = torch.randperm(N, generator=gen)
+            b1, b2 = int(N * 0.7), int(N * 0.85)
+            data, labels = as_t(data), as_t(labels)
+            pick = lambda a, i: a.index_select(0, i.to(a.device))
+            train_data, train_labels = pick(data, perm[:b1]), pick(labels, perm[:b1])
+            val_data, val_labels = pick(data, perm[b1:b2]), pick(labels, perm[b1:b2])
+            test_data, test_labels = pick(data, perm[b2:]), pick(labels, perm[b2:])
+    else:
+        data, labels = as_t(data), as_t(labels)
+        i0, i1 = (torch.as_tensor(np.asarray(i)).long() for i in idxs[:2])
+        train_data, train_labels = data[i0.to(data.device)], labels[i0.to(labels.device)]
+        val_data, val_labels = data[i1.to(data.device)], labels[i1.to(labels.device)]
+        test_data, test_labels = None, None
+    dev = torch.device(device)
+    splits = {}
+    for split, d, l in (("train", train_data, train_labels), ("val", val_data, val_labels),
+                        ("test", test_data, test_labels)):
+        if d is None:
+            splits[split] = None
+            continue
+        d = as_t(d).to(dev, torch.float32).contiguous()
+        l = as_t(l).to(dev)
+        if include_time:
+            ts = d[:, :, 0]
+        else:
+            ts = torch.from_numpy(make_ts(d.shape[1], T)).to(dev)[None, :].expand(d.shape[0], -1)
+        splits[split] = (d, l, ts, paths_fn(d, stepsize, depth))
+    tr = splits["train"]
+    idx = np.unique(np.r_[0 : tr[0].shape[1] : int(stepsize)])
+    intervals = np.concatenate([tr[2][0].detach().cpu().numpy()[idx], np.array([T], np.float32)]).astype(np.float32)
+    keep = (lambda t: t) if inmemory else (lambda t: t.cpu().pin_memory() if dev.type == "cuda" else t.cpu())
+    raw, path = {}, {}
+    for split, v in splits.items():
+        if v is None:
+            raw[split], path[split] = Dataloader(None, None, inmemory, device), Dataloader(None, None, inmemory, device)
+            continue
+        d, l, ts, p = v
+        raw[split] = Dataloader(keep(d), keep(l), inmemory, device)
+        path[split] = Dataloader((keep(ts.contiguous()), keep(p), keep(d[:, 0, :].contiguous())), keep(l), inmemory, device)
+    label_dim = 1 if (tr[1].dim() == 1 or name == "ppg") else int(tr[1].shape[-1])
+    return Dataset(name, raw, None, path, int(tr[0].shape[-1]), int(tr[3].shape[-1]), intervals, label_dim)
 
 
 def create_dataset(name: str, n: int, *, seed: int = 2345, stepsize=None, depth=None, T: float = 1.0,
-                   scale: bool = False, device="cuda", L: int | None = None, n_out: int | None = None) -> Dataset:
+                   scale: bool = False, device="cuda", L: int | None = None, n_out: int | None = None,
+                   inmemory: bool = True) -> Dataset:
+    """Synthetic stand-in for data_dir/datasets.py:create_dataset (the real datasets are not available offline):
+    synthetic paths of the named dataset's shape, then ``dataset_generator`` exactly as the reference calls it."""
     cfg = SHAPES[name]
     stepsize = cfg["stepsize"] if stepsize is None else int(stepsize)
     depth = cfg["depth"] if depth is None else int(depth)
     x = synthetic_paths(name, n, seed, T, scale_to_unit=scale, L=L)
-    Ln = x.shape[1]
     rng = np.random.default_rng(seed + 1)
     if cfg["classification"]:
         lab = np.eye(cfg["label_dim"], dtype=np.float32)[rng.integers(0, cfg["label_dim"], size=n)]
     else:
         lab = rng.uniform(-1, 1, size=(n, n_out or 1)).astype(np.float32)
-    data = torch.from_numpy(x).to(device)
-    paths = batch_calc_paths(data, stepsize, depth)
-    ts0 = make_ts(Ln, T)
-    return Dataset(name, data, torch.from_numpy(lab).to(device), torch.from_numpy(ts0).to(device), paths,
-                   x.shape[2], paths.shape[-1], make_intervals(ts0, stepsize, T), cfg["label_dim"])
+    return dataset_generator(name, torch.from_numpy(x), torch.from_numpy(lab), stepsize, depth, cfg["time"], T,
+                             inmemory=inmemory, key=seed, device=device)

@@ -34,7 +34,9 @@ _out = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("outside the ho
 _stub("models.LRU", LRU=_out)
 _stub("models.S5", S5=_out)
 _stub("models.RNN", GRUCell=_out, LinearCell=_out, LSTMCell=_out, MLPCell=_out, RNN=_out)
-_stub("data_dir.generate_coeffs", calc_coeffs=_out)
+# NCDE interpolation coefficients (outside the hot path): dataset_generator only needs something tuple-shaped
+_stub("data_dir.generate_coeffs",
+      calc_coeffs=lambda data, include_time, T: (torch.zeros(data.shape[0], data.shape[1] - 1, data.shape[2]),))
 
 import diffrax  # noqa: E402  (refshim)
 import train as ref_train  # noqa: E402
@@ -242,8 +244,67 @@ def slice_cases():
     print("ref_slice.npz:", len(cases), "cases")
 
 
+def data_cases():
+    """datasets.py:dataset_generator (pre-split, so no jax.random permutation is involved) and the batching
+    protocol of dataloaders.py:Dataloader."""
+    import jax.random as jr
+    from data_dir.dataloaders import Dataloader as RefDataloader
+    from data_dir.datasets import dataset_generator as ref_dataset_generator
+
+    rng = np.random.default_rng(17)
+    out = {}
+    cases = [("toy", 11, 5, 4, 18, 3, 4, 2, False, 1.0, True), ("ppg", 9, 4, 5, 23, 3, 5, 1, True, 1.0, False)]
+    for i, (name, ntr, nva, nte, L, C, s, depth, include_time, Tend, onehot) in enumerate(cases):
+        mk = lambda n: np.cumsum(rng.normal(scale=0.3, size=(n, L, C)), axis=1)
+        data = [mk(ntr), mk(nva), mk(nte)]
+        if include_time:
+            for d in data:
+                d[:, :, 0] = (Tend / L) * np.arange(L)
+        if onehot:
+            labels = [np.eye(3)[rng.integers(0, 3, size=n)] for n in (ntr, nva, nte)]
+        else:
+            labels = [rng.normal(size=(n, 6)) for n in (ntr, nva, nte)]
+        ds = ref_dataset_generator(name, tuple(T(d) for d in data), tuple(T(l) for l in labels), s, depth, include_time,
+                                   Tend, use_presplit=True, key=0)
+        out[f"cfg{i}"] = np.array([ntr, nva, nte, L, C, s, depth, int(include_time), int(onehot)])
+        out[f"name{i}"] = np.array(name)
+        out[f"dims{i}"] = np.array([ds.data_dim, ds.logsig_dim, ds.label_dim])
+        out[f"intervals{i}"] = np.asarray(ds.intervals, dtype=np.float64)
+        for k, split in enumerate(("train", "val", "test")):
+            out[f"x{i}_{k}"], out[f"y{i}_{k}"] = data[k], labels[k]
+            batches = list(ds.path_dataloaders[split].loop_epoch(4))
+            out[f"nb{i}_{k}"] = np.array([len(b[1]) for b in batches])
+            out[f"ts{i}_{k}"] = torch.cat([b[0][0] for b in batches]).double().numpy()
+            out[f"ls{i}_{k}"] = torch.cat([b[0][1] for b in batches]).numpy()
+            out[f"x0{i}_{k}"] = torch.cat([b[0][2] for b in batches]).numpy()
+            out[f"lab{i}_{k}"] = torch.cat([b[1] for b in batches]).numpy()
+    out["n"] = np.array(len(cases))
+    # Dataloader.loop: how many permutations are drawn while K batches are yielded (the last batch of every
+    # permutation is dropped, even a full one: `while end < self.size`)
+    calls = [0]
+    orig = jr.permutation
+
+    def counting(key, n):
+        calls[0] += 1
+        return orig(key, n)
+
+    jr.permutation = counting
+    rows = []
+    for size, bs, K in ((10, 3, 7), (10, 5, 4), (12, 4, 5), (7, 6, 3)):
+        dl = RefDataloader(T(rng.normal(size=(size, 4, 2))), T(rng.normal(size=(size,))))
+        calls[0] = 0
+        it = dl.loop(bs, key=5)
+        sizes = [len(next(it)[1]) for _ in range(K)]
+        rows.append([size, bs, K, calls[0], min(sizes), max(sizes)])
+    jr.permutation = orig
+    out["loop_protocol"] = np.array(rows)
+    np.savez_compressed(os.path.join(HERE, "ref_data.npz"), **out)
+    print("ref_data.npz:", len(cases), "datasets +", len(rows), "loop protocols")
+
+
 if __name__ == "__main__":
     sys.path.insert(0, HERE)
+    data_cases()
     paths_cases()
     logncde_cases()
     linear_cases()

@@ -27,4 +27,6 @@ def uniform(key, shape=(), dtype=None, minval=0.0, maxval=1.0):
 
 
 def permutation(key, n):
+    if isinstance(n, torch.Tensor) and n.dim() >= 1:  # permute the entries of an array
+        return n[torch.randperm(n.shape[0], generator=_gen(key))]
     return torch.randperm(int(n), generator=_gen(key))

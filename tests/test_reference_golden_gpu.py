@@ -107,3 +107,16 @@ def test_slice_variants_vs_reference_code(built_lib, monkeypatch, i):
 
     model, X, y, cls, kind = V.build(i, monkeypatch, device="cuda")
     V.check(i, model, X, y, cls, kind, 2e-5)
+
+
+@pytest.mark.parametrize("inmemory", [True, False])
+@pytest.mark.parametrize("i", range(2))
+def test_data_pipeline_vs_reference_code(built_lib, i, inmemory):
+    """dataset_generator + Dataloader on the device (log-signatures from K1, one launch per split) against the
+    reference's own dataset_generator (tests/golden/ref_data.npz); inmemory=False keeps pinned host copies."""
+    import test_data_pipeline_cpu as DP
+
+    ds = DP.build(i, device="cuda", paths_fn=None, inmemory=inmemory)
+    (ts, ls, x0), y = next(ds.path_dataloaders["train"].loop_epoch(4))
+    assert ls.is_cuda and x0.is_cuda and y.is_cuda
+    DP.check(i, ds)
