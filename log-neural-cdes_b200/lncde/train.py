@@ -103,6 +103,101 @@ def make_step(model, filter_spec, X, y, loss_fn, state, opt, opt_state, key, *, 
     return model, state, opt_state, value
 
 
+def _scaled_inputs(model_name, dataset_name, X):
+    """train.py:212-216: log-signature rescaling the reference applies to two datasets."""
+    if model_name == "dplr_linear_ncde":
+        if dataset_name in ("Heartbeat", "MotorImagery"):
+            return (X[0], X[1] / 100, X[2])
+    elif model_name.endswith("linear_ncde") and dataset_name == "Heartbeat":
+        return (X[0], X[1] / 10, X[2])
+    return X
+
+
+def evaluate(model_name, dataset_name, model, dataloader, batch_size, state=None):
+    """Metric of one ordered pass (train.py:224-250): accuracy, or mean over samples of the per-sample MSE."""
+    preds, labels = [], []
+    with torch.no_grad():
+        for X, y in dataloader.loop_epoch(batch_size):
+            pred, _ = calc_output(model, _scaled_inputs(model_name, dataset_name, X), state, None, model.stateful,
+                                  model.nondeterministic)
+            preds.append(pred)
+            labels.append(y)
+    pred, y = torch.cat(preds), torch.cat(labels)
+    if model.classification:
+        return float((pred.argmax(dim=1) == y.argmax(dim=1)).float().mean())
+    return float(((pred[:, :, 0] - y) ** 2).mean(dim=1).mean(dim=0))
+
+
+def train_model(model_name, dataset_name, model, metric, filter_spec, state, dataloaders, num_steps, print_steps,
+                early_stopping_steps, lr, lr_scheduler, batch_size, key, output_dir, *, world_size=1, overwrite=False,
+                log=print):
+    """train.py:139-349: the training loop with periodic train / validation metrics, early stopping on the
+    validation metric, a test pass whenever validation improves, and the .npy curves the reference writes.
+    Differences: an existing ``output_dir`` raises unless ``overwrite`` (no interactive prompt); ``lr_scheduler(lr)``
+    may return a float or a step -> lr callable; ``key`` seeds the batch shuffling."""
+    import os
+    import shutil
+    import time
+
+    import numpy as np
+
+    if metric == "accuracy":
+        best_val, improv, no_improv, first = max, (lambda x, y: x >= y), (lambda x, y: x <= y), 0.0
+    elif metric == "mse":
+        best_val, improv, no_improv, first = min, (lambda x, y: x <= y), (lambda x, y: x >= y), 100.0
+    else:
+        raise ValueError(f"Unknown metric: {metric}")
+    if os.path.isdir(output_dir):
+        if not overwrite:
+            raise ValueError(f"Directory {output_dir} already exists. Exiting.")
+        shutil.rmtree(output_dir)
+    os.makedirs(output_dir)
+    sched = lr_scheduler(lr) if lr_scheduler is not None else lr
+    opt = Adam(model, sched(0) if callable(sched) else sched)
+    loss_fn = classification_loss if model.classification else regression_loss
+    running_loss = 0.0
+    all_val, all_train, val_for_best, all_time = [first], [first], [first], []
+    no_val_improvement, test_metric = 0, None
+    start = time.time()
+    for step, (X, y) in zip(range(num_steps), dataloaders["train"].loop(batch_size, key=key)):
+        if callable(sched):
+            opt.lr = float(sched(step))
+        X = _scaled_inputs(model_name, dataset_name, X)
+        model, state, _, value = make_step(model, filter_spec, X, y, loss_fn, state, opt, None, None,
+                                           world_size=world_size)
+        running_loss += float(value)
+        if (step + 1) % print_steps == 0:
+            end = time.time()
+            train_metric = evaluate(model_name, dataset_name, model, dataloaders["train"], batch_size, state)
+            val_metric = evaluate(model_name, dataset_name, model, dataloaders["val"], batch_size, state)
+            total_time = end - start
+            log(f"Step: {step + 1}, Loss: {running_loss / print_steps}, Train metric: {train_metric}, "
+                f"Validation metric: {val_metric}, Time: {total_time}")
+            start = time.time()
+            if step > 0:
+                if no_improv(val_metric, best_val(val_for_best)):
+                    no_val_improvement += 1
+                    if no_val_improvement > early_stopping_steps:
+                        break
+                else:
+                    no_val_improvement = 0
+                if improv(val_metric, best_val(val_for_best)):
+                    val_for_best.append(val_metric)
+                    test_metric = evaluate(model_name, dataset_name, model, dataloaders["test"], batch_size, state)
+                    log(f"Test metric: {test_metric}")
+                running_loss = 0.0
+                all_train.append(train_metric)
+                all_val.append(val_metric)
+                all_time.append(total_time)
+                np.save(output_dir + "/steps.npy", np.arange(0, step + 1, print_steps))
+                np.save(output_dir + "/all_train_metric.npy", np.array(all_train))
+                np.save(output_dir + "/all_val_metric.npy", np.array(all_val))
+                np.save(output_dir + "/all_time.npy", np.array(all_time))
+                np.save(output_dir + "/test_metric.npy", np.array(test_metric if test_metric is not None else np.nan))
+    log(f"Test metric: {test_metric}")
+    return model
+
+
 class GraphedStep:
     """One training step captured in a CUDA graph (streams and graphs instead of a tracing compiler):
     the ~100 small launches of a step (K1, solve / scan kernels, read-out + loss autograd, gradient GEMMs,
