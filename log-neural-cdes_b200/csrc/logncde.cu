@@ -512,6 +512,22 @@ static int launch_bwd(cudaStream_t st, const BwdParams& p, size_t smem) {
 
 }  // namespace lncde
 
+#ifdef LNCDE_PHASE_TIMING
+// dev tool only (scripts/phase_timing.py); not part of include/lncde_b200.h
+extern "C" int lncde_debug_phase_clocks(long long* host, size_t n, int reset) {
+  using namespace lncde::fast;
+  const size_t total = (size_t)kPtStages * kPtLines * kPtWarps;
+  if (n < total) return LNCDE_ERR_WORKSPACE;
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_phase_clock, total * sizeof(long long));
+  if (e == cudaSuccess && reset) {
+    void* dev = nullptr;
+    e = cudaGetSymbolAddress(&dev, g_phase_clock);
+    if (e == cudaSuccess) e = cudaMemset(dev, 0, total * sizeof(long long));
+  }
+  return (int)e;
+}
+#endif
+
 extern "C" {
 
 int lncde_logncde_param_count(int H, int C, int width, int n_hidden) {

@@ -33,6 +33,26 @@ namespace fast {
 
 constexpr int H = 128, W = 32, NT = 512;
 
+// Block barrier of the solve kernels.  A -DLNCDE_PHASE_TIMING build (dev tool, scripts/phase_timing.py) records
+// the clock at which every warp of CTA 0 ARRIVES at every barrier of a few stages, keyed by source line, so
+// that the time between consecutive barriers (= one dependent phase) can be read off per phase.
+#ifdef LNCDE_PHASE_TIMING
+constexpr int kPtStages = 4, kPtLines = 1280, kPtWarps = NT / 32, kPtStage0 = 200;
+__device__ long long g_phase_clock[kPtStages * kPtLines * kPtWarps];
+__device__ __forceinline__ void pt_sync(int slot, int line) {
+  if (slot >= 0 && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && line < kPtLines)
+    g_phase_clock[(slot * kPtLines + line) * kPtWarps + (threadIdx.x >> 5)] = clock64();
+  __syncthreads();
+}
+__device__ __forceinline__ int pt_slot_of(int stage) {
+  return (stage >= kPtStage0 && stage < kPtStage0 + kPtStages) ? stage - kPtStage0 : -1;
+}
+#define LNCDE_SYNC() pt_sync(pt_slot, __LINE__)
+#else
+__device__ __forceinline__ int pt_slot_of(int) { return -1; }
+#define LNCDE_SYNC() __syncthreads()
+#endif
+
 // logistic function with the fast exp / reciprocal units (no cancellation here: |error| ~ 2 ulp)
 __device__ __forceinline__ float sigm(float z) { return __frcp_rn(1.f + __expf(-z)); }
 
@@ -241,7 +261,8 @@ __device__ __forceinline__ void stage_w2r(const MlpDesc& d, const float* __restr
 // with a reduce phase each: 8 block barriers per stage instead of 12, same sums in the same order.
 template <int C, bool D2, bool FUSED = false>
 __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& R, float lam_v,
-                                              float (&o_r)[2], float (&u3_r)[2], const float* w2r = nullptr) {
+                                              float (&o_r)[2], float (&u3_r)[2], const float* w2r = nullptr,
+                                              int pt_slot = -1) {
   using S = Smem<C>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* part = cm + S::part;
@@ -252,7 +273,7 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     const float4 yb = *reinterpret_cast<const float4*>(sb + S::yin + warp * 8 + 4);
     part[warp * 32 + lane] = dot8(R.w1, ya, yb);
   }
-  __syncthreads();
+  LNCDE_SYNC();
   if (FUSED) {
     // F1: warp 0 finishes z1 / a1 / s1 and goes straight on to z2 = W2 a1
     if (warp == 0) {
@@ -262,18 +283,18 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
       warp_matvec32<4>(w2r, sb + S::a1, lane, acc);
       hidden_finish_acc(acc, lane, sb + S::z2, sb + S::a2, sb + S::s2);
     }
-    __syncthreads();
+    LNCDE_SYNC();
   } else {
     if (warp == 0) hidden_finish<16>(part, R.b1, lane, sb + S::z1, sb + S::a1, sb + S::s1);
-    __syncthreads();
+    LNCDE_SYNC();
     // P2: z2 = W2 a1
     if (warp < 8) {
       const float4 a = *reinterpret_cast<const float4*>(sb + S::a1 + warp * 4);
       part[warp * 32 + lane] = dot4(R.w2, a);
     }
-    __syncthreads();
+    LNCDE_SYNC();
     if (warp == 0) hidden_finish<8>(part, R.b2, lane, sb + S::z2, sb + S::a2, sb + S::s2);
-    __syncthreads();
+    LNCDE_SYNC();
   }
   // P3: o = tanh(W3 a2 + b3)
   const int row0 = lane_row0(tid);
@@ -284,7 +305,7 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     o_r[1] = tanhf(rb + R.b3[1]);
     *reinterpret_cast<float2*>(sb + S::o + row0) = make_float2(o_r[0], o_r[1]);
   }
-  __syncthreads();
+  LNCDE_SYNC();
   if (!D2) return;
   // P5: q_i = W1 o_i, K-slice partials
 #pragma unroll
@@ -293,14 +314,14 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     const float4 xb = *reinterpret_cast<const float4*>(sb + S::o + i * H + warp * 8 + 4);
     part[(warp * 8 + i) * 32 + lane] = dot8(R.w1, xa, xb);
   }
-  __syncthreads();
+  LNCDE_SYNC();
   if (warp < C) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int qq = 0; qq < 16; ++qq) acc[qq & 3] += part[(qq * 8 + warp) * 32 + lane];
     cm[S::qv + warp * W + lane] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
   }
-  __syncthreads();
+  LNCDE_SYNC();
   // u1_j = sum_i Lam_ij q_i ; p1_j = s1 * u1_j
   if (warp < C) {
     float u = 0.f;
@@ -318,7 +339,7 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
       sb[S::p2 + warp * W + lane] = sb[S::s2 + lane] * u2v;
     }
   }
-  __syncthreads();
+  LNCDE_SYNC();
   if (!FUSED) {
   // P6: u2_j = W2 p1_j (8 K-slices x 2 vector halves)
   {
@@ -332,7 +353,7 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
       }
     }
   }
-  __syncthreads();
+  LNCDE_SYNC();
   if (warp < C) {
     float acc[2] = {0.f, 0.f};
 #pragma unroll
@@ -341,7 +362,7 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     sb[S::u2 + warp * W + lane] = u;
     sb[S::p2 + warp * W + lane] = sb[S::s2 + lane] * u;
   }
-  __syncthreads();
+  LNCDE_SYNC();
   }  // !FUSED
   // P7: u3 = W3[block j] p2_j ; d = (1 - o^2) u3
   if (tid < C * 64) {
@@ -350,7 +371,7 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     *reinterpret_cast<float2*>(cm + S::dbuf + row0) =
         make_float2((1.f - o_r[0] * o_r[0]) * u3_r[0], (1.f - o_r[1] * o_r[1]) * u3_r[1]);
   }
-  __syncthreads();
+  LNCDE_SYNC();
 }
 
 template <int C, bool D2>
@@ -447,7 +468,8 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
     const int nx = sidx + 1 < n_stage ? sidx + 1 : sidx;
     const float sc_n = p.stage_scale[nx];
     const float lam_n = lambda_fetch<C>(ls + (size_t)p.stage_row[nx] * p.D, D2);
-    stage_forward<C, D2, FUSED>(sb, cm, R, lam_c, o_r, u3_r, w2r);
+    const int pt_slot = pt_slot_of(sidx);
+    stage_forward<C, D2, FUSED>(sb, cm, R, lam_c, o_r, u3_r, w2r, pt_slot);
     if (SAVE) save_stage<C, D2>(sb, o_r, u3_r, p.ws, p.wsp, (size_t)b * n_stage + sidx);
     if (tid < H) {
       const float gk = sc * field_value<C, D2>(sb, cm, tid);
@@ -461,7 +483,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
         ys[(size_t)((sidx >> 1) + 1) * H + tid] = yn;
       }
     }
-    __syncthreads();
+    LNCDE_SYNC();
     sc = sc_n;
     lam_c = lam_n;
   }
@@ -474,7 +496,8 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
 template <int C, bool D2, bool RIGHTS, bool FUSED = false>
 __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, float* sb, float* cm, const Regs& R,
                                               const float (&o_r)[2], const float (&u3_r)[2], float (&b3acc)[2],
-                                              const WsLayout& ws, float* __restrict__ wsp, size_t slot) {
+                                              const WsLayout& ws, float* __restrict__ wsp, size_t slot,
+                                              int pt_slot = -1) {
   using S = Smem<C>;
   constexpr int CH = C * H, CW = C * W;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -515,7 +538,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     }
   }
   if (D2) {
-    __syncthreads();
+    LNCDE_SYNC();
     if (FUSED) {
       // FQ2: warp j takes tangent j through Q2 (u2-bar), Q3 (p1-bar_j = W2^T u2-bar_j) and Q3r (u1-bar) alone
       if (warp < C) {
@@ -531,7 +554,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
         cm[S::ub1 + tid] = sb[S::s1 + lane] * pb1;
         cm[S::sp1 + tid] = sb[S::u1 + tid] * pb1;
       }
-      __syncthreads();
+      LNCDE_SYNC();
     } else {
     // Q2: u2-bar = s2 * p2-bar ; s2-bar partials
     if (warp < C) {
@@ -541,7 +564,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
       cm[S::sp2 + tid] = sb[S::u2 + tid] * pb;
       wsp[ws.U[1] + slot * CW + tid] = ub;
     }
-    __syncthreads();
+    LNCDE_SYNC();
     // Q3: p1-bar_j = W2^T u2-bar_j  (8 K-slices x 2 vector halves) ; s2-bar
     {
       const int q = warp & 7, j0 = (warp >> 3) * 4;
@@ -562,7 +585,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
         cm[S::sb2 + lane] = s;
       }
     }
-    __syncthreads();
+    LNCDE_SYNC();
     // u1-bar = s1 * p1-bar ; s1-bar partials
     if (warp < C) {
       float acc[2] = {0.f, 0.f};
@@ -572,7 +595,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
       cm[S::ub1 + tid] = sb[S::s1 + lane] * pb;
       cm[S::sp1 + tid] = sb[S::u1 + tid] * pb;
     }
-    __syncthreads();
+    LNCDE_SYNC();
     }  // !FUSED
     // v_i = sum_j Lam_ij u1-bar_j ; s1-bar
     if (warp < C) {
@@ -593,7 +616,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
         cm[S::sb2 + lane] = s2s;
       }
     }
-    __syncthreads();
+    LNCDE_SYNC();
     // Q4: o-bar_i[h] += sum_c W1[c][h] v_i[c]   (4 K-slices x 4 h-quarters)
     {
       const int ks = warp >> 2, h = (warp & 3) * 32 + lane;
@@ -607,7 +630,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
         part[(ks * 8 + i) * H + h] = dot8(w8, xa, xb);
       }
     }
-    __syncthreads();
+    LNCDE_SYNC();
   }
   // Q5: o-bar complete ; z3-bar = (1 - o^2) o-bar ; a2-bar partials
   if (tid < C * 64) {
@@ -629,7 +652,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     const float pr = tile_cols(R, cm + S::dbuf + (warp * 8 + (lane >> 2)) * 8, lane);
     cm[S::red + warp * W + lane_col(lane)] = pr;
   }
-  __syncthreads();
+  LNCDE_SYNC();
   if (FUSED) {
     // FQ6: warp 0 does Q6 (z2-bar), Q7 (a1-bar = W2^T z2-bar) and Q7r (z1-bar) back to back
     if (warp == 0) {
@@ -656,7 +679,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
       cm[S::bacc + lane] += zb1v;
       wsp[ws.Z[0] + slot * W + lane] = zb1v;
     }
-    __syncthreads();
+    LNCDE_SYNC();
   } else {
   // Q6: a2-bar ; z2-bar
   if (warp == 0) {
@@ -672,7 +695,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     cm[S::bacc + W + lane] += zb;
     wsp[ws.Z[1] + slot * W + lane] = zb;
   }
-  __syncthreads();
+  LNCDE_SYNC();
   // Q7: a1-bar = W2^T z2-bar (8 K-slices)
   if (warp < 8) {
     const float4 wt = *reinterpret_cast<const float4*>(sw + S::W2T + (warp * 32 + lane) * 4);
@@ -680,7 +703,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     const float4 x = *reinterpret_cast<const float4*>(cm + S::zb2 + warp * 4);
     part[warp * 32 + lane] = dot4(w4, x);
   }
-  __syncthreads();
+  LNCDE_SYNC();
   if (warp == 0) {
     float acc[2] = {0.f, 0.f};
 #pragma unroll
@@ -694,7 +717,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     cm[S::bacc + lane] += zb;
     wsp[ws.Z[0] + slot * W + lane] = zb;
   }
-  __syncthreads();
+  LNCDE_SYNC();
   }  // !FUSED
   // Q8: y-bar = W1^T z1-bar, K-slice partials (summed by the caller)
   {
@@ -706,7 +729,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     const float4 xb = *reinterpret_cast<const float4*>(cm + S::zb1 + ks * 8 + 4);
     part[ks * H + h] = dot8(w8, xa, xb);
   }
-  __syncthreads();
+  LNCDE_SYNC();
 }
 
 template <int C>
@@ -865,16 +888,17 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
     if (tid < H)
       cm[S::g + tid] = second ? 0.5f * sc_c * cm[S::ybar + tid] : sc_c * (0.5f * cm[S::ybar + tid] + cm[S::ab + tid]);
     lambda_store<C>(cm, lam_c);
-    __syncthreads();
+    const int pt_slot = pt_slot_of(n_stage - 1 - sidx);  // slots count stages in sweep order
+    LNCDE_SYNC();
     const float oc[2] = {o_c.x, o_c.y}, uc[2] = {u_c.x, u_c.y};
-    stage_reverse<C, D2, false, FUSED>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx);
+    stage_reverse<C, D2, false, FUSED>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx, pt_slot);
     if (tid < H) {
       const float yo = yout_value<C>(cm, tid);
       if (second) cm[S::ab + tid] = yo;
       else cm[S::ybar + tid] += cm[S::ab + tid] + yo + g_c;
     }
     cp_async_wait_all();
-    __syncthreads();
+    LNCDE_SYNC();
     lam_c = lam_n; sc_c = sc_n; o_c = o_n; u_c = u_n;
     if (!second) g_c = g_n;  // g_n was fetched for step (nx >> 1); it changes only when the step changes
   }

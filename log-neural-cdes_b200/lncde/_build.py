@@ -38,8 +38,11 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every source under csrc/ into one shared library (idempotent)."""
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), lib_path: str | None = None) -> str:
+    """Compile every source under csrc/ into one shared library (idempotent).  ``extra_flags`` / ``lib_path``
+    build a differently configured copy (dev tools, e.g. -DLNCDE_PHASE_TIMING) next to the product library."""
+    if extra_flags or lib_path:
+        return _build_variant(list(extra_flags), lib_path or LIB_PATH.replace(".so", "_variant.so"), verbose)
     digest = _digest()
     if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
         with open(STAMP) as fh:
@@ -70,6 +73,28 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     with open(STAMP, "w") as fh:
         fh.write(digest)
     return LIB_PATH
+
+
+def _build_variant(extra_flags, lib_path, verbose=False) -> str:
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    build_dir = os.path.join(PKG_DIR, "build", os.path.basename(lib_path) + ".d")
+    os.makedirs(build_dir, exist_ok=True)
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(build_dir, os.path.basename(src) + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", os.path.join(REPO, "include"), "-I", CSRC, "-x", "cu", "-c", src,
+               "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    r = subprocess.run([nvcc, "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -7,7 +7,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "liblncde_b200.so")
+# LNCDE_LIB: load a differently configured build of the same library (dev tools such as scripts/phase_timing.py)
+LIB_PATH = os.environ.get("LNCDE_LIB") or os.path.join(_PKG, "liblncde_b200.so")
 
 _lock = threading.Lock()
 _lib = None

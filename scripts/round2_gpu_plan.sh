@@ -1,0 +1,28 @@
+#!/bin/bash
+# First GPU call of round 2 (one gpurun, ~6-8 GPU-minutes): everything that was written blind at the end of
+# round 1 gets its hardware verdict, and the captures that profiles/README.md lists as gaps are taken.
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash scripts/round2_gpu_plan.sh'
+set -u
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/r2_smoke.log 2>&1
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest.log
+timeout 300 python scripts/variant_check.py > gpurun_out/r2_variants.json 2> gpurun_out/r2_variants.err
+timeout 300 python scripts/phase_timing.py > gpurun_out/r2_phases.txt 2>&1
+python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
+for w in eigenworms_bd eigenworms_d eigenworms_de scp1_bd; do
+  python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline >> gpurun_out/r2_bench_others.json 2>> gpurun_out/r2_bench.err
+done
+python scripts/k1_sweep.py > gpurun_out/r2_k1_sweep.txt 2>&1
+LNCDE_TUNE_K1_TMA=1 python scripts/k1_sweep.py > gpurun_out/r2_k1_sweep_tma.txt 2>&1
+# launch list of the default step (shares only), then one full capture of the K1 TMA kernel and of the K2 kernels
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-autotune > gpurun_out/r2_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-autotune --no-graph > gpurun_out/r2_ncu1.log 2>&1
+LNCDE_TUNE_K1_TMA=1 python scripts/k1_sweep.py > gpurun_out/r2_plain2.log 2>&1 &&
+LNCDE_TUNE_K1_TMA=1 ncu --set full --clock-control none --import-source on -k regex:logsig_levy -c 2 \
+    -o gpurun_out/r2_prof_k1_tma python scripts/k1_sweep.py > gpurun_out/r2_ncu2.log 2>&1
+python bench.py --workload eigenworms_de --steps 2 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r2_plain3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'scan_|flow_build' -s 6 -c 4 \
+    -o gpurun_out/r2_prof_k2 python bench.py --workload eigenworms_de --steps 2 --warmup 3 --no-cpu-baseline --no-graph \
+    > gpurun_out/r2_ncu3.log 2>&1
+tail -3 gpurun_out/r2_pytest.log; head -c 1500 gpurun_out/r2_variants.json; echo; head -c 600 gpurun_out/r2_bench.json
