@@ -46,8 +46,9 @@ const char* lncde_strerror(int status);
 /* Kernel-variant switches.  Every variant computes the same result; the default is the variant measured
  * fastest on B200 so far.  Keys: "k1_tma" (lncde_logsig_fwd: TMA bulk-copy staging, same as passing
  * LNCDE_FLAG_K1_TMA), "k3_fused" (lncde_logncde_fwd/bwd, specialised H=128 / width 32 kernels: the 32 x 32
- * layer phases fused on single warps).  Process-wide, thread-safe; initial values come from the
- * environment (LNCDE_TUNE_K1_TMA, LNCDE_TUNE_K3_FUSED).  A forward/backward pair must run under the same
+ * layer phases fused on single warps), "k2_fused_d" (host mirror: diagonal LNCDE through lncde_dlncde_* instead
+ * of flow build + scan).  Process-wide, thread-safe; initial values come from the environment
+ * (LNCDE_TUNE_K1_TMA, LNCDE_TUNE_K3_FUSED, LNCDE_TUNE_K2_FUSED_D).  A forward/backward pair must run under the same
  * setting only in the sense that each call reads the value once at entry; results are interchangeable. */
 int lncde_set_tuning(const char* key, int value);
 int lncde_get_tuning(const char* key); /* value, or <0 for an unknown key */
@@ -149,6 +150,21 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
 int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, const float* ys,
                           const float* g_ys, float* g_lie, float* g_y0, int B, int T, int D, int nb,
                           int bs, int n_basis, void* workspace, size_t workspace_bytes);
+
+/* ----------------------------------------------------------------- K2d ---
+ * Fused diagonal LNCDE (block size 1): f_t = 1 + sum_c logsig[t, 1 + c] vf_A[c, :], y_t = f_t * y_{t-1},
+ * t = 1..T-1, WITHOUT materialising the flows (models/LinearNeuralCDEs.py:302-316 + scanner :355-386).
+ * Same results as lncde_linear_scan_fwd/bwd with bs = 1, n_basis = C; a third of their HBM traffic.
+ *   vf_At [H, C] (= vf_A transposed, the `lie` layout of the generic call for bs = 1); C <= 8
+ *   logsig [B, T, D] with D >= 1 + C; y0 [B, H]; ys [B, T, H] (ys[:,0] = y0)
+ *   g_ys [B, T, H] -> g_vf_At [H, C] (summed over the batch), g_y0 [B, H]
+ * workspace (backward only): lncde_dlncde_bwd_workspace_bytes(B, H, C) bytes.                              */
+size_t lncde_dlncde_bwd_workspace_bytes(int B, int H, int C);
+int lncde_dlncde_fwd(void* stream, const float* vf_At, const float* logsig, const float* y0, float* ys,
+                     int B, int T, int D, int H, int C);
+int lncde_dlncde_bwd(void* stream, const float* vf_At, const float* logsig, const float* ys,
+                     const float* g_ys, float* g_vf_At, float* g_y0, int B, int T, int D, int H, int C,
+                     void* workspace, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------ K4 ---
  * Fused Adam update on a flat parameter buffer (optax.adam defaults,

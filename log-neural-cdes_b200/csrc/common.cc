@@ -10,9 +10,9 @@
 
 namespace lncde {
 namespace {
-const char* const kTuneNames[kTuneCount] = {"k1_tma", "k3_fused"};
-const char* const kTuneEnv[kTuneCount] = {"LNCDE_TUNE_K1_TMA", "LNCDE_TUNE_K3_FUSED"};
-std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}};  // -1: not set yet -> environment, else 0
+const char* const kTuneNames[kTuneCount] = {"k1_tma", "k3_fused", "k2_fused_d"};
+const char* const kTuneEnv[kTuneCount] = {"LNCDE_TUNE_K1_TMA", "LNCDE_TUNE_K3_FUSED", "LNCDE_TUNE_K2_FUSED_D"};
+std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}};  // -1: not set yet -> environment, else 0
 }  // namespace
 
 int tuning_value(int key) {

@@ -42,6 +42,9 @@ def _declare(lib):
         "lncde_linear_scan_workspace_bytes": (sz, [i, i, i, i, i]),
         "lncde_linear_scan_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]),
         "lncde_linear_scan_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]),
+        "lncde_dlncde_bwd_workspace_bytes": (sz, [i, i, i]),
+        "lncde_dlncde_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i]),
+        "lncde_dlncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]),
         "lncde_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, i, f]),
         "lncde_adam_step_dev": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, vp, f]),
     }

@@ -56,6 +56,48 @@ class _LinearScan(torch.autograd.Function):
         return g_lie, None, g_y0, None
 
 
+class _DiagScan(torch.autograd.Function):
+    """Fused diagonal LNCDE (K2d, lncde_dlncde_*): no flows in HBM.  vf_At is [H, C]."""
+
+    @staticmethod
+    def forward(ctx, vf_At, logsig, y0):
+        _lib.require_cuda(logsig)
+        L = _lib.lib()
+        B, T, D = logsig.shape
+        H, C = vf_At.shape
+        vf_At, y0 = vf_At.contiguous(), y0.contiguous()
+        ys = torch.empty((B, T, H), device=logsig.device, dtype=torch.float32)
+        st = L.lncde_dlncde_fwd(_lib.stream_ptr(), _lib.ptr(vf_At), _lib.ptr(logsig), _lib.ptr(y0), _lib.ptr(ys), B, T, D,
+                                H, C)
+        _lib.check(st, "lncde_dlncde_fwd")
+        ctx.save_for_backward(vf_At, logsig, ys)
+        return ys
+
+    @staticmethod
+    def backward(ctx, g_ys):
+        vf_At, logsig, ys = ctx.saved_tensors
+        L = _lib.lib()
+        B, T, D = logsig.shape
+        H, C = vf_At.shape
+        g_ys = g_ys.contiguous()
+        nbytes = L.lncde_dlncde_bwd_workspace_bytes(B, H, C)
+        ws = torch.empty(nbytes, device=ys.device, dtype=torch.uint8)
+        g_A = torch.empty_like(vf_At)
+        g_y0 = torch.empty((B, H), device=ys.device, dtype=torch.float32)
+        st = L.lncde_dlncde_bwd(_lib.stream_ptr(), _lib.ptr(vf_At), _lib.ptr(logsig), _lib.ptr(ys), _lib.ptr(g_ys),
+                                _lib.ptr(g_A), _lib.ptr(g_y0), B, T, D, H, C, _lib.ptr(ws), nbytes)
+        _lib.check(st, "lncde_dlncde_bwd")
+        return g_A, None, g_y0
+
+
+def _diag_scan(vf_At, logsigs, y0):
+    """Diagonal scan: the fused K2d kernels when the "k2_fused_d" tuning value is set, else flow build + scan."""
+    H, C = vf_At.shape
+    if C <= 8 and _lib.get_tuning("k2_fused_d"):
+        return _DiagScan.apply(vf_At, logsigs, y0)
+    return _LinearScan.apply(vf_At, logsigs, y0, (H, 1, C))
+
+
 class LogLinearCDE:
     lip2 = True
     nondeterministic = False
@@ -197,7 +239,7 @@ class LogLinearCDE:
         logsigs = logsigs.contiguous()
         if self.diagonal_dense:  # (:273-300): diagonal scan on the first H - bs components, one dense block on the rest
             nd = H - self.dense_size
-            ys_d = _LinearScan.apply(self.vf_A_diag.t(), logsigs, y0[:, :nd], (nd, 1, C))
+            ys_d = _diag_scan(self.vf_A_diag.t(), logsigs, y0[:, :nd])
             lie = self.log_ode(self.vf_A_dense.unsqueeze(1))
             ys_e = _LinearScan.apply(lie, logsigs, y0[:, nd:], (1, self.dense_size, lie.shape[-1]))
             return torch.cat([ys_d, ys_e], dim=-1)
@@ -209,7 +251,7 @@ class LogLinearCDE:
             vfs = (self.vf_A[:, None, :] * self.hadamard_matrix[None, :, :]).view(C, 1, H, H)
         elif bs == 1:
             # [H, C]: flows = 1 + logsig[:, 1:C+1] @ vf_A  (:303-305)
-            return _LinearScan.apply(self.vf_A.t(), logsigs, y0, (nb, 1, C))
+            return _diag_scan(self.vf_A.t(), logsigs, y0)
         else:
             vfs = self.vf_A.view(C, nb, bs, bs)
         lie = self.log_ode(vfs)

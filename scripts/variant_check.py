@@ -9,7 +9,10 @@
 Used by tests/test_zz_variants_gpu.py and by the autotune leg of bench.py, which run it as a subprocess so that
 a fault or hang in a variant that has not been on hardware yet cannot take the caller's CUDA context with it.
 
-    python scripts/variant_check.py [--no-timing] [--no-parity] [--only k1|k3]
+  k2: ``set_tuning("k2_fused_d", 1)`` (fused diagonal LNCDE kernels, dlncde.cu) - loss and gradients against flow
+      build + scan, timings of the EigenWorms D-LNCDE train step at B = 32 and B = 2048.
+
+    python scripts/variant_check.py [--no-timing] [--no-parity] [--only k1|k2|k3]
 """
 import json
 import os
@@ -150,11 +153,82 @@ def k3_timing(reps=5):
     return res
 
 
+def _dlncde_step(B, n_windows, seed=0):
+    """EigenWorms D-LNCDE config (diagonal_linear_ncde, depth-1 rows, H = 128): loss + flat gradient closure."""
+    from lncde import train as T
+    from lncde.data_dir.generate_paths import calc_paths, logsig_dim
+    from lncde.models.generate_model import create_model
+
+    C, s, H = 7, 12, 128
+    L = n_windows * s - 1
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(B, L, C, device="cuda", generator=g) * 0.05).cumsum(1)
+    x = 2 * (x - x.amin((0, 1))) / (x.amax((0, 1)) - x.amin((0, 1))) - 1
+    model, _ = create_model("diagonal_linear_ncde", C, logsig_dim(C, 1), 1, None, 5, H, block_size=1, lambd=1e-3, key=2345,
+                            device=torch.device("cuda"))
+    ts = torch.zeros(B, L)
+    y = torch.eye(5, device="cuda")[torch.arange(B, device="cuda") % 5]
+    ls = calc_paths(x, s, 1)
+
+    def step():
+        return T.classification_loss(model, (ts, ls, x[:, 0, :]), y)
+
+    return model, step
+
+
+def k2_parity():
+    from lncde import _lib
+
+    res = {"cases": 0, "max_rel_diff_grad": 0.0, "max_rel_diff_loss": 0.0}
+    for B, nwin in ((3, 40), (32, 1499), (5, 130)):
+        model, step = _dlncde_step(B, nwin, seed=B)
+        _lib.set_tuning("k2_fused_d", 0)
+        l0, g0 = step()
+        _lib.set_tuning("k2_fused_d", 1)
+        l1, g1 = step()
+        _lib.set_tuning("k2_fused_d", 0)
+        torch.cuda.synchronize()
+        res["cases"] += 1
+        res["max_rel_diff_loss"] = max(res["max_rel_diff_loss"], abs(float(l1) - float(l0)) / max(abs(float(l0)), 1e-30))
+        res["max_rel_diff_grad"] = max(res["max_rel_diff_grad"],
+                                       float((g1 - g0).abs().max() / g0.abs().max().clamp_min(1e-30)))
+    res["ok"] = bool(res["max_rel_diff_loss"] < 1e-5 and res["max_rel_diff_grad"] < 5e-5)
+    return res
+
+
+def k2_timing(reps=10):
+    from lncde import _lib
+
+    res = {"shape": "EigenWorms D-LNCDE train step (loss + gradient), eager launches; B=32 and B=2048 (HBM-sized)"}
+    for B in (32, 2048):
+        model, step = _dlncde_step(B, 1499)
+        for name, v in (("default", 0), ("fused", 1)):
+            _lib.set_tuning("k2_fused_d", v)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            res[f"{name}_B{B}"] = {"ms": e0.elapsed_time(e1) / reps}
+        del model, step
+        torch.cuda.empty_cache()
+    _lib.set_tuning("k2_fused_d", 0)
+    # algorithmic bytes of the fused pair per step at B = 2048: ys written once, ys + g_ys read once, logsig twice
+    T, H, D = 1499, 128, 8
+    res["fused_algorithmic_bytes_B2048"] = 2048 * T * (3 * H * 4 + 2 * D * 4)
+    return res
+
+
 if __name__ == "__main__":
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    skip = sys.argv[sys.argv.index("--skip") + 1].split(",") if "--skip" in sys.argv else []
     out = {}
-    for name, par, tim in (("k1", parity, timing), ("k3", k3_parity, k3_timing)):
-        if only not in (None, name):
+    for name, par, tim in (("k1", parity, timing), ("k3", k3_parity, k3_timing), ("k2", k2_parity, k2_timing)):
+        if only not in (None, name) or name in skip:
             continue
         out[name] = {}
         try:

@@ -37,6 +37,10 @@ def lib():
         _lib.lncde_linear_scan_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]
         _lib.lncde_adam_step.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, i,
                                          C.c_float]
+        _lib.lncde_dlncde_bwd_workspace_bytes.argtypes = [i, i, i]
+        _lib.lncde_dlncde_bwd_workspace_bytes.restype = sz
+        _lib.lncde_dlncde_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i]
+        _lib.lncde_dlncde_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]
         _lib.emu_bulk_copies.restype = C.c_long
         _lib.emu_guarded_alloc.restype = C.c_void_p
         _lib.emu_guarded_alloc.argtypes = [C.c_size_t, C.c_int, C.c_int]
@@ -161,3 +165,32 @@ def linear_scan(lie, logsig, y0, nb, bs, g_ys=None):
                                  n_basis, _p(ws), nbytes)
     assert st == 0, st
     return ys, g_lie, g_y0
+
+
+def dlncde(vf_At, logsig, y0, g_ys=None):
+    """lncde_dlncde_fwd (+ bwd): fused diagonal LNCDE.  vf_At [H, C]; buffers end at guard pages."""
+    L = lib()
+    H, Cn = vf_At.shape
+    B, T, D = logsig.shape
+
+    def dev(a):
+        g = guarded(a.shape)
+        g[...] = a
+        return g
+
+    A, ls, y0d = dev(f32(vf_At)), dev(f32(logsig)), dev(f32(y0))
+    ys = guarded((B, T, H))
+    ys[...] = np.nan
+    st = L.lncde_dlncde_fwd(None, _p(A), _p(ls), _p(y0d), _p(ys), B, T, D, H, Cn)
+    assert st == 0, st
+    if g_ys is None:
+        return ys.copy(), None, None
+    g = dev(f32(g_ys))
+    nbytes = L.lncde_dlncde_bwd_workspace_bytes(B, H, Cn)
+    ws = guarded((nbytes // 4,))
+    g_A, g_y0 = guarded((H, Cn)), guarded((B, H))
+    g_A[...] = np.nan
+    g_y0[...] = np.nan
+    st = L.lncde_dlncde_bwd(None, _p(A), _p(ls), _p(ys), _p(g), _p(g_A), _p(g_y0), B, T, D, H, Cn, _p(ws), nbytes)
+    assert st == 0, st
+    return ys.copy(), g_A.copy(), g_y0.copy()

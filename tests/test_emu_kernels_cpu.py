@@ -216,6 +216,35 @@ def test_emu_linear_scan_forward_and_adjoint(nb, bs, T, n_basis):
     assert rel_err(gl_e, lie_t.grad.numpy()) < 5 * TOL
 
 
+# ------------------------------------------------------------------------------------------ K2d
+@pytest.mark.parametrize("B,T,H,C,D", [(2, 40, 16, 3, 4), (3, 131, 128, 7, 29), (1, 2, 5, 1, 2), (2, 1, 8, 2, 4),
+                                       (2, 65, 200, 8, 37), (1, 64, 130, 6, 22), (2, 129, 7, 4, 11)])
+def test_emu_fused_diagonal_scan(B, T, H, C, D):
+    """lncde_dlncde_fwd/bwd (no flows in HBM) against torch autograd of the recurrence and against the generic
+    flow-build + scan kernels with bs = 1."""
+    rng = np.random.default_rng(B * 1000 + T)
+    A = rng.normal(size=(H, C)) * 0.3
+    ls = rng.normal(size=(B, T, D)) * 0.2
+    ls[..., 0] = 0
+    y0 = rng.normal(size=(B, H))
+    g_ys = rng.normal(size=(B, T, H))
+    A_t = torch.from_numpy(A).requires_grad_(True)
+    y0_t = torch.from_numpy(y0).requires_grad_(True)
+    flows = 1 + torch.from_numpy(ls[..., 1 : 1 + C]) @ A_t.T
+    ys = [y0_t]
+    for t in range(1, T):
+        ys.append(flows[:, t] * ys[-1])
+    ys_o = torch.stack(ys, 1)
+    (ys_o * torch.from_numpy(g_ys)).sum().backward()
+    ys_e, gA_e, gy_e = E.dlncde(A, ls, y0, g_ys)
+    assert rel_err(ys_e, ys_o.detach().numpy()) < TOL
+    assert rel_err(gy_e, y0_t.grad.numpy()) < 5 * TOL
+    gA_o = np.zeros((H, C)) if A_t.grad is None else A_t.grad.numpy()  # T = 1: no flow is ever applied
+    assert rel_err(gA_e, gA_o) < 5 * TOL
+    ys_g, gl_g, gy_g = E.linear_scan(A.reshape(H, 1, 1, C), ls, y0, H, 1, g_ys)
+    assert rel_err(ys_e, ys_g) < 1e-5 and rel_err(gy_e, gy_g) < 5e-5 and rel_err(gA_e, gl_g.reshape(H, C)) < 5e-5
+
+
 # ------------------------------------------------------------------------------------------ reference-executed fixtures
 # tests/golden/ref_*.npz hold outputs of the reference's OWN code (tests/golden/make_golden_ref.py): the emulated
 # kernels are compared with them directly, the oracle only supplies the glue the reference does in its host code.
@@ -278,6 +307,9 @@ def test_emu_linear_scan_vs_reference_code(i):
         lie = torch.stack([OL.log_ode(vfs[:, b], hall) for b in range(nb)]).numpy()
     y0 = _LN[f"x{i}"][:, 0] @ Wi.T + bi
     ys, _, _ = E.linear_scan(lie, _LN[f"logsig{i}"], y0, nb, bs)
+    if bs == 1:  # the fused diagonal kernels give the same states
+        ys_f, _, _ = E.dlncde(vfA.T.numpy(), _LN[f"logsig{i}"], y0)
+        assert rel_err(ys_f, ys) < 1e-5
     ys = torch.from_numpy(ys).double()
     Wo_t, bo_t = torch.from_numpy(Wo), torch.from_numpy(bo)
     pred = torch.softmax(ys.mean(1) @ Wo_t.T + bo_t, -1) if cls else torch.tanh(ys @ Wo_t.T + bo_t)
