@@ -1,6 +1,5 @@
 """train_model (train.py:139-349 mirror): loop, metrics, early stopping and the files it writes, on the CPU with the
 K2 scan replaced by the plain-torch statement of its contract (tests/test_slice_variants_cpu.TorchScan)."""
-import os
 
 import numpy as np
 import pytest
