@@ -416,8 +416,13 @@ def decide_tuning(rep, margin=0.98):
     try:
         if k1.get("parity", {}).get("ok") and "error" not in k1:
             choice["k1_tma"] = int(k1["timing"]["tma"]["ms"] < margin * k1["timing"]["classic"]["ms"])
-        if k3.get("parity", {}).get("ok") and "error" not in k3:
-            choice["k3_fused"] = int(k3["timing"]["fused"]["ms"] < margin * k3["timing"]["default"]["ms"])
+        if "error" not in k3 and "timing" in k3:
+            ok = k3.get("parity", {}).get("ok_by_variant", {})
+            best, best_ms = 0, margin * k3["timing"]["default"]["ms"]
+            for v, name in ((1, "fused"), (2, "fused2")):
+                if ok.get(str(v)) and name in k3["timing"] and k3["timing"][name]["ms"] < best_ms:
+                    best, best_ms = v, k3["timing"][name]["ms"]
+            choice["k3_fused"] = best
     except (KeyError, TypeError):
         pass
     return choice

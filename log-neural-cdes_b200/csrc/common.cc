@@ -20,7 +20,7 @@ int tuning_value(int key) {
   int v = g_tune[key].load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = std::getenv(kTuneEnv[key]);
-    v = (e && e[0] != '\0' && e[0] != '0') ? 1 : 0;
+    v = (e && e[0] >= '0' && e[0] <= '9') ? (e[0] - '0') : 0;
     int expected = -1;
     g_tune[key].compare_exchange_strong(expected, v);  // a concurrent lncde_set_tuning wins
     v = g_tune[key].load(std::memory_order_relaxed);
@@ -35,7 +35,7 @@ int lncde_set_tuning(const char* key, int value) {
   if (!key) return LNCDE_ERR_NULL;
   for (int k = 0; k < lncde::kTuneCount; ++k)
     if (std::strcmp(key, lncde::kTuneNames[k]) == 0) {
-      lncde::g_tune[k].store(value ? 1 : 0);
+      lncde::g_tune[k].store(value < 0 ? 0 : value);
       return LNCDE_OK;
     }
   return LNCDE_ERR_UNSUPPORTED;

@@ -247,7 +247,7 @@ static bool use_fast(int H, int C, int width, int n_hidden) {
   static const bool disabled = getenv("LNCDE_DISABLE_FAST") != nullptr;
   return !disabled && fast::shape_supported(H, C, width, n_hidden);
 }
-static bool use_fused() { return tuning_value(kTuneK3Fused) != 0; }
+static int fused_variant() { return tuning_value(kTuneK3Fused); }
 
 struct RevBufs {
   float* g;        // [H] cotangent of G
@@ -570,9 +570,9 @@ int lncde_logncde_fwd(void* stream, const float* params, const float* logsig, co
       p.save = 1;
     }
     switch (C) {
-      case 4: return fast::launch_fwd_fast<4>(cs, p, use_fused());
-      case 6: return fast::launch_fwd_fast<6>(cs, p, use_fused());
-      case 7: return fast::launch_fwd_fast<7>(cs, p, use_fused());
+      case 4: return fast::launch_fwd_fast<4>(cs, p, fused_variant() != 0);
+      case 6: return fast::launch_fwd_fast<6>(cs, p, fused_variant() != 0);
+      case 7: return fast::launch_fwd_fast<7>(cs, p, fused_variant() != 0);
     }
   }
   switch (C) {
@@ -621,9 +621,9 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
   cudaStream_t cs = (cudaStream_t)stream;
   if (use_fast(H, C, width, n_hidden)) {
     switch (C) {
-      case 4: st = fast::launch_bwd_fast<4>(cs, p, use_fused()); break;
-      case 6: st = fast::launch_bwd_fast<6>(cs, p, use_fused()); break;
-      case 7: st = fast::launch_bwd_fast<7>(cs, p, use_fused()); break;
+      case 4: st = fast::launch_bwd_fast<4>(cs, p, fused_variant()); break;
+      case 6: st = fast::launch_bwd_fast<6>(cs, p, fused_variant()); break;
+      case 7: st = fast::launch_bwd_fast<7>(cs, p, fused_variant()); break;
     }
   } else
   switch (C) {

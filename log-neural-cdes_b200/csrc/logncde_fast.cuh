@@ -106,6 +106,8 @@ struct Smem {
   static constexpr int COMMON_BWD = bacc + 2 * W;
   // FUSED variant only: W2 in per-thread order [8 K-slices][32 rows][4], appended after the common area
   static constexpr int W2R_FLOATS = W * W;
+  // M45 variant only (backward): plain copy of W1 [32][128] behind it
+  static constexpr int W1C_FLOATS = W * H;
 };
 
 struct Regs {
@@ -493,11 +495,15 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
 // Reverse sweep of one stage.  cm[g] holds dLoss/dG times the stage scale.  On exit (after the
 // trailing barrier) cm[part + ks*128 + h], ks < 4, hold the K-slice partials of
 // dLoss/d(stage input); the caller sums them.
-template <int C, bool D2, bool RIGHTS, bool FUSED = false>
+// M45 (kernel variant, tuning "k3_fused" = 2): phase Q4 (o-bar partials over 4 K-slices, all warps) is folded into
+// Q5 - every row thread forms the full K = 32 sums of ITS two rows from a plain copy of W1 in shared memory
+// (32 conflict-free 64-bit loads + 8 broadcast 128-bit loads), so one block barrier and the partial-sum round
+// trip through shared memory disappear.
+template <int C, bool D2, bool RIGHTS, bool FUSED = false, bool M45 = false>
 __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, float* sb, float* cm, const Regs& R,
                                               const float (&o_r)[2], const float (&u3_r)[2], float (&b3acc)[2],
                                               const WsLayout& ws, float* __restrict__ wsp, size_t slot,
-                                              int pt_slot = -1) {
+                                              int pt_slot = -1, const float* w1c = nullptr) {
   using S = Smem<C>;
   constexpr int CH = C * H, CW = C * W;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -618,7 +624,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     }
     LNCDE_SYNC();
     // Q4: o-bar_i[h] += sum_c W1[c][h] v_i[c]   (4 K-slices x 4 h-quarters)
-    {
+    if (!M45) {
       const int ks = warp >> 2, h = (warp & 3) * 32 + lane;
       const float4 wa = *reinterpret_cast<const float4*>(sw + S::W1T + ((warp * 2 + 0) * 32 + lane) * 4);
       const float4 wb = *reinterpret_cast<const float4*>(sw + S::W1T + ((warp * 2 + 1) * 32 + lane) * 4);
@@ -629,13 +635,30 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
         const float4 xb = *reinterpret_cast<const float4*>(cm + S::vb + i * W + ks * 8 + 4);
         part[(ks * 8 + i) * H + h] = dot8(w8, xa, xb);
       }
+      LNCDE_SYNC();
     }
-    LNCDE_SYNC();
   }
   // Q5: o-bar complete ; z3-bar = (1 - o^2) o-bar ; a2-bar partials
   if (tid < C * 64) {
     const int j = tid >> 6, h0 = row0 & (H - 1);
-    if (D2) {
+    if (D2 && M45) {
+      const float* wc = w1c + h0;  // W1[c][h0], W1[c][h0 + 1]
+      const float* vj = cm + S::vb + j * W;
+      float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v4 = *reinterpret_cast<const float4*>(vj + 4 * q);
+        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 w2 = *reinterpret_cast<const float2*>(wc + (4 * q + e) * H);
+          a0[e & 1] = fmaf(w2.x, vv[e], a0[e & 1]);
+          a1[e & 1] = fmaf(w2.y, vv[e], a1[e & 1]);
+        }
+      }
+      ob[0] += a0[0] + a0[1];
+      ob[1] += a1[0] + a1[1];
+    } else if (D2) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const float2 pv = *reinterpret_cast<const float2*>(part + (ks * 8 + j) * H + h0);
@@ -739,7 +762,7 @@ __device__ __forceinline__ float yout_value(const float* cm, int h) {
   return (part[h] + part[H + h]) + (part[2 * H + h] + part[3 * H + h]);
 }
 
-template <int C, bool D2, bool FUSED>
+template <int C, bool D2, bool FUSED, bool M45 = false>
 __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams p) {
   using S = Smem<C>;
   extern __shared__ __align__(16) float smem[];
@@ -748,11 +771,14 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
   float* sbB = sbA + S::STAGE;
   float* cm = sbB + S::STAGE;
   float* w2r = cm + S::COMMON_BWD;  // FUSED only
+  float* w1c = w2r + S::W2R_FLOATS; // M45 only
   const int tid = threadIdx.x;
   Regs R;
   load_regs<C>(R, p.params, p.d);
   stage_weights_bwd<C>(p.d, p.params, sw);
   if (FUSED) stage_w2r(p.d, p.params, w2r);
+  if (M45)
+    for (int t = tid; t < W * H; t += NT) w1c[t] = p.params[p.d.w_off[0] + t];
   const int b = blockIdx.x;
   const float* ls = p.logsig + (size_t)b * p.K * p.D;
   const float* ys = p.ys + (size_t)b * (p.n_steps + 1) * H;
@@ -785,7 +811,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
     stage_forward<C, D2, FUSED>(sbB, cm, R, lam_b, oB, uB, w2r);  // leaves Lambda of row r2
     if (tid < H) cm[S::g + tid] = 0.5f * s2 * cm[S::ybar + tid];
     __syncthreads();
-    stage_reverse<C, D2, true, FUSED>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1);
+    stage_reverse<C, D2, true, FUSED, M45>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1, -1, w1c);
     if (tid < H) {
       const float a = yout_value<C>(cm, tid);
       cm[S::ab + tid] = a;
@@ -795,7 +821,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
     const float lam_an = lambda_fetch<C>(ls + (size_t)r1n * p.D, D2);
     const float lam_bn = lambda_fetch<C>(ls + (size_t)r2n * p.D, D2);
     __syncthreads();
-    stage_reverse<C, D2, true, FUSED>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot);
+    stage_reverse<C, D2, true, FUSED, M45>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot, -1, w1c);
     if (tid < H) cm[S::ybar + tid] += cm[S::ab + tid] + yout_value<C>(cm, tid) + g_n;
     __syncthreads();
     s1 = s1n; s2 = s2n;
@@ -835,7 +861,7 @@ __device__ __forceinline__ void fetch_saved(float* sb, const WsLayout& ws, const
   cp_async_commit();
 }
 
-template <int C, bool D2, bool FUSED>
+template <int C, bool D2, bool FUSED, bool M45 = false>
 __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParams p) {
   using S = Smem<C>;
   constexpr int CH = C * H;
@@ -843,10 +869,13 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
   float* sw = smem;
   float* sbuf[2] = {smem + S::WEND_BWD, smem + S::WEND_BWD + S::STAGE};
   float* cm = sbuf[1] + S::STAGE;
+  float* w1c = cm + S::COMMON_BWD + S::W2R_FLOATS;  // M45 only (same offset as in the recomputing kernel)
   const int tid = threadIdx.x;
   Regs R;
   load_regs<C>(R, p.params, p.d);
   stage_weights_bwd<C>(p.d, p.params, sw);
+  if (M45)
+    for (int t = tid; t < W * H; t += NT) w1c[t] = p.params[p.d.w_off[0] + t];
   const int b = blockIdx.x;
   const float* ls = p.logsig + (size_t)b * p.K * p.D;
   const float* gys = p.g_ys + (size_t)b * (p.n_steps + 1) * H;
@@ -891,7 +920,8 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
     const int pt_slot = pt_slot_of(n_stage - 1 - sidx);  // slots count stages in sweep order
     LNCDE_SYNC();
     const float oc[2] = {o_c.x, o_c.y}, uc[2] = {u_c.x, u_c.y};
-    stage_reverse<C, D2, false, FUSED>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx, pt_slot);
+    stage_reverse<C, D2, false, FUSED, M45>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx, pt_slot,
+                                            w1c);
     if (tid < H) {
       const float yo = yout_value<C>(cm, tid);
       if (second) cm[S::ab + tid] = yo;
@@ -917,8 +947,9 @@ constexpr size_t fwd_smem_bytes(bool fused) {
   return (size_t)(Smem<C>::WEND_FWD + Smem<C>::STAGE + Smem<C>::COMMON_FWD + (fused ? Smem<C>::W2R_FLOATS : 0)) * 4;
 }
 template <int C>
-constexpr size_t bwd_smem_bytes(bool fused) {
-  return (size_t)(Smem<C>::WEND_BWD + 2 * Smem<C>::STAGE + Smem<C>::COMMON_BWD + (fused ? Smem<C>::W2R_FLOATS : 0)) * 4;
+constexpr size_t bwd_smem_bytes(bool fused, bool m45) {
+  return (size_t)(Smem<C>::WEND_BWD + 2 * Smem<C>::STAGE + Smem<C>::COMMON_BWD +
+                  (fused || m45 ? Smem<C>::W2R_FLOATS : 0) + (m45 ? Smem<C>::W1C_FLOATS : 0)) * 4;
 }
 
 template <int C, bool FUSED>
@@ -941,25 +972,27 @@ template <int C>
 static int launch_fwd_fast(cudaStream_t st, const FwdParams& p, bool fused) {
   return fused ? launch_fwd_fast_v<C, true>(st, p) : launch_fwd_fast_v<C, false>(st, p);
 }
-template <int C, bool FUSED>
+template <int C, bool FUSED, bool M45>
 static int launch_bwd_fast_v(cudaStream_t st, const BwdParams& p) {
-  const size_t smem = bwd_smem_bytes<C>(FUSED && !p.saved);  // only the recomputing kernel runs stage_forward
+  const size_t smem = bwd_smem_bytes<C>(FUSED, M45);
   auto go = [&](auto k) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<p.B, NT, smem, st>>>(p);
   };
   if (p.d.depth == 2) {
-    if (p.saved) go(logncde_bwd_saved_kernel<C, true, FUSED>);
-    else go(logncde_bwd_fast_kernel<C, true, FUSED>);
-  } else {
-    if (p.saved) go(logncde_bwd_saved_kernel<C, false, FUSED>);
-    else go(logncde_bwd_fast_kernel<C, false, FUSED>);
+    if (p.saved) go(logncde_bwd_saved_kernel<C, true, FUSED, M45>);
+    else go(logncde_bwd_fast_kernel<C, true, FUSED, M45>);
+  } else {  // depth 1 has no Q4: M45 is the same kernel as FUSED
+    if (p.saved) go(logncde_bwd_saved_kernel<C, false, FUSED, false>);
+    else go(logncde_bwd_fast_kernel<C, false, FUSED, false>);
   }
   return (int)cudaGetLastError();
 }
+// variant: 0 default, 1 fused 32 x 32 phases, 2 fused + Q4 folded into Q5
 template <int C>
-static int launch_bwd_fast(cudaStream_t st, const BwdParams& p, bool fused) {
-  return fused ? launch_bwd_fast_v<C, true>(st, p) : launch_bwd_fast_v<C, false>(st, p);
+static int launch_bwd_fast(cudaStream_t st, const BwdParams& p, int variant) {
+  if (variant >= 2) return launch_bwd_fast_v<C, true, true>(st, p);
+  return variant == 1 ? launch_bwd_fast_v<C, true, false>(st, p) : launch_bwd_fast_v<C, false, false>(st, p);
 }
 
 inline bool shape_supported(int Hh, int C, int width, int n_hidden) {

@@ -47,9 +47,10 @@ def norm(name):
     m = re.match(r"void (logncde_fwd_fast_kernel)<(\d), (\w+), (\w+), (\w+)>", name)
     if m:
         return None if m.group(5) == "true" else f"void {m.group(1)}<{m.group(2)}, {m.group(3)}, {m.group(4)}>(FwdParams)"
-    m = re.match(r"void (logncde_bwd_(?:fast|saved)_kernel)<(\d), (\w+), (\w+)>", name)
+    m = re.match(r"void (logncde_bwd_(?:fast|saved)_kernel)<(\d), (\w+), (\w+)(?:, (\w+))?>", name)
     if m:
-        return None if m.group(4) == "true" else f"void {m.group(1)}<{m.group(2)}, {m.group(3)}>(BwdParams)"
+        variant = m.group(4) == "true" or m.group(5) == "true"
+        return None if variant else f"void {m.group(1)}<{m.group(2)}, {m.group(3)}>(BwdParams)"
     return name
 
 

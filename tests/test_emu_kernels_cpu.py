@@ -190,6 +190,31 @@ def test_emu_logncde_fused_variant_bit_identical(case):
     assert rel_err(got[0], ys_o) < TOL and rel_err(got[1], gp_o) < 5 * TOL and rel_err(got[2], gy_o) < 5 * TOL
 
 
+@pytest.mark.parametrize("case", [c for c in SOLVE_CASES if c[5:8] == (128, 32, 2)])
+def test_emu_logncde_fused_level2_variant(case):
+    """lncde_set_tuning("k3_fused", 2): level 1 plus phase Q4 folded into Q5 in the adjoint sweep (different order
+    of the K = 32 sums: agreement to rounding, not bit for bit).  Forward kernels are those of level 1."""
+    B, L, C, s, depth, H, width, n_hidden, dt0, scale = case
+    logsig, rows, sc, grid, layers, y0 = _setup(B, L, C, s, depth, H, width, n_hidden, dt0, scale)
+    dims = (H, C, width, n_hidden, depth)
+    g_ys = np.random.default_rng(1).normal(size=(B, len(grid), H))
+    flat = O.flatten_params(layers).numpy()
+    ref = E.logncde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, dims, g_ys)
+    E.set_tuning("k3_fused", 2)
+    try:
+        got = E.logncde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, dims, g_ys)
+        got_r = E.logncde_bwd_recompute(flat, logsig, got[0], rows, sc, dims, g_ys)
+    finally:
+        E.set_tuning("k3_fused", 0)
+    assert np.array_equal(got[0], ref[0])
+    ys_o, gp_o, gy_o = _oracle(layers, logsig, y0, rows, sc, dims, torch.from_numpy(g_ys))
+    for gp, gy in ((got[1], got[2]), got_r):
+        assert rel_err(gp, gp_o) < 5 * TOL and rel_err(gy, gy_o) < 5 * TOL
+        assert rel_err(gp, ref[1]) < 1e-5 and rel_err(gy, ref[2]) < 1e-5
+    if depth == 1:  # no Q4 at depth 1: identical kernels
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
 # ------------------------------------------------------------------------------------------ K2
 @pytest.mark.parametrize("nb,bs,T,n_basis", [(16, 1, 40, 3), (8, 4, 33, 6), (4, 8, 20, 6), (2, 32, 12, 3),
                                              (1, 64, 9, 6), (3, 5, 14, 3)])

@@ -98,14 +98,17 @@ def test_bench_autotune_decision():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     ok, bad = {"ok": True}, {"ok": False}
-    t = lambda a, b, ka, kb: {ka: {"ms": a}, kb: {"ms": b}}
-    rep = {"k1": {"parity": ok, "timing": t(0.33, 0.25, "classic", "tma")},
-           "k3": {"parity": ok, "timing": t(19.0, 18.9, "default", "fused")}}
-    assert bench.decide_tuning(rep) == {"k1_tma": 1, "k3_fused": 0}       # 0.5 % is inside the noise margin
+    t = lambda **kw: {k: {"ms": v} for k, v in kw.items()}
+    k3ok = {"ok": True, "ok_by_variant": {"1": True, "2": True}}
+    rep = {"k1": {"parity": ok, "timing": t(classic=0.33, tma=0.25)},
+           "k3": {"parity": k3ok, "timing": t(default=19.0, fused=18.9, fused2=18.8)}}
+    assert bench.decide_tuning(rep) == {"k1_tma": 1, "k3_fused": 0}       # 1 % is inside the noise margin
     rep["k1"]["parity"] = bad
-    rep["k3"]["timing"] = t(19.0, 15.0, "default", "fused")
-    assert bench.decide_tuning(rep) == {"k1_tma": 0, "k3_fused": 1}       # faster but wrong is never used
-    assert bench.decide_tuning({"k1": {"error": "x"}, "k3": {"parity": ok}}) == {"k1_tma": 0, "k3_fused": 0}
+    rep["k3"]["timing"] = t(default=19.0, fused=15.0, fused2=14.0)
+    assert bench.decide_tuning(rep) == {"k1_tma": 0, "k3_fused": 2}       # faster but wrong is never used; best variant wins
+    rep["k3"]["parity"] = {"ok": False, "ok_by_variant": {"1": True, "2": False}}
+    assert bench.decide_tuning(rep) == {"k1_tma": 0, "k3_fused": 1}       # level 2 failed its check: fall back to level 1
+    assert bench.decide_tuning({"k1": {"error": "x"}, "k3": {"parity": k3ok}}) == {"k1_tma": 0, "k3_fused": 0}
     assert bench.decide_tuning({}) == {"k1_tma": 0, "k3_fused": 0}
 
 
@@ -114,8 +117,8 @@ def test_tuning_api_roundtrip(built_lib):
 
     for key in ("k1_tma", "k3_fused"):
         old = _lib.get_tuning(key)
-        _lib.set_tuning(key, 1)
-        assert _lib.get_tuning(key) == 1
+        _lib.set_tuning(key, 2)
+        assert _lib.get_tuning(key) == 2
         _lib.set_tuning(key, old)
         assert _lib.get_tuning(key) == old
     import pytest
