@@ -898,6 +898,13 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
   }
   float g_c = tid < H ? gys[(size_t)(p.n_steps - 1) * H + tid] : 0.f;  // cotangent of y_n, n = sidx / 2
   fetch_saved<C, D2>(sbuf[sidx & 1], p.ws, wsp, slot0 + sidx);
+  if (M45) {
+    // M45 also drops one barrier per stage: the cotangent of the NEXT stage's field value and its Lambda are
+    // written at the end of a stage by the threads that just produced their inputs (cm[g] is last read in Q1,
+    // Lambda in Q3m), so the stage starts straight after the closing barrier.  The last stage is a second one.
+    if (tid < H) cm[S::g + tid] = 0.5f * sc_c * cm[S::ybar + tid];
+    lambda_store<C>(cm, lam_c);
+  }
   cp_async_wait_all();
   __syncthreads();
   for (; sidx >= 0; --sidx) {
@@ -914,11 +921,13 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
     fetch_saved<C, D2>(sbuf[nx & 1], p.ws, wsp, slot0 + nx);
     // cotangent of this stage's field value
     const bool second = sidx & 1;  // stage 2 of its Heun step
-    if (tid < H)
-      cm[S::g + tid] = second ? 0.5f * sc_c * cm[S::ybar + tid] : sc_c * (0.5f * cm[S::ybar + tid] + cm[S::ab + tid]);
-    lambda_store<C>(cm, lam_c);
     const int pt_slot = pt_slot_of(n_stage - 1 - sidx);  // slots count stages in sweep order
-    LNCDE_SYNC();
+    if (!M45) {
+      if (tid < H)
+        cm[S::g + tid] = second ? 0.5f * sc_c * cm[S::ybar + tid] : sc_c * (0.5f * cm[S::ybar + tid] + cm[S::ab + tid]);
+      lambda_store<C>(cm, lam_c);
+      LNCDE_SYNC();
+    }
     const float oc[2] = {o_c.x, o_c.y}, uc[2] = {u_c.x, u_c.y};
     stage_reverse<C, D2, false, FUSED, M45>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx, pt_slot,
                                             w1c);
@@ -926,7 +935,10 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
       const float yo = yout_value<C>(cm, tid);
       if (second) cm[S::ab + tid] = yo;
       else cm[S::ybar + tid] += cm[S::ab + tid] + yo + g_c;
+      if (M45 && sidx > 0)  // next stage: second iff this one is a first stage
+        cm[S::g + tid] = !second ? 0.5f * sc_n * cm[S::ybar + tid] : sc_n * (0.5f * cm[S::ybar + tid] + cm[S::ab + tid]);
     }
+    if (M45 && sidx > 0) lambda_store<C>(cm, lam_n);
     cp_async_wait_all();
     LNCDE_SYNC();
     lam_c = lam_n; sc_c = sc_n; o_c = o_n; u_c = u_n;
