@@ -371,9 +371,9 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     k1_ms = e0.elapsed_time(e1) / n_rep
     alg_bytes = Bk * (4 * L * C + 4 * 1499 * 29)  # 677 436 B per sample
     ach = alg_bytes / (k1_ms * 1e-3) / 1e9
-    k1_tma = bool(tuning.get("k1_tma"))
-    res["roofline"] = {"kernel": ("logsig_levy_tma_kernel<7,depth2> (K1, TMA staging)" if k1_tma
-                                  else "logsig_levy_kernel<7,depth2> (K1)"),
+    k1_tma = int(tuning.get("k1_tma", 0))
+    res["roofline"] = {"kernel": ("logsig_levy_tma_kernel<7,depth2%s> (K1, TMA staging)" % (",persistent" if k1_tma > 1 else "")
+                                  if k1_tma else "logsig_levy_kernel<7,depth2> (K1)"),
                        "bound": "hbm", "achieved": ach,
                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                        # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed
@@ -414,8 +414,13 @@ def decide_tuning(rep, margin=0.98):
     choice = {"k1_tma": 0, "k3_fused": 0}
     k1, k3 = rep.get("k1", {}), rep.get("k3", {})
     try:
-        if k1.get("parity", {}).get("ok") and "error" not in k1:
-            choice["k1_tma"] = int(k1["timing"]["tma"]["ms"] < margin * k1["timing"]["classic"]["ms"])
+        if "error" not in k1 and "timing" in k1:
+            ok = k1.get("parity", {}).get("ok_by_variant", {})
+            best, best_ms = 0, margin * k1["timing"]["classic"]["ms"]
+            for v, name in ((1, "tma"), (2, "tma_persistent")):
+                if ok.get(str(v)) and name in k1["timing"] and k1["timing"][name]["ms"] < best_ms:
+                    best, best_ms = v, k1["timing"][name]["ms"]
+            choice["k1_tma"] = best
         if "error" not in k3 and "timing" in k3:
             ok = k3.get("parity", {}).get("ok_by_variant", {})
             best, best_ms = 0, margin * k3["timing"]["default"]["ms"]

@@ -44,8 +44,8 @@ const char* lncde_version(void);
 const char* lncde_strerror(int status);
 
 /* Kernel-variant switches.  Every variant computes the same result; the default is the variant measured
- * fastest on B200 so far.  Keys: "k1_tma" (lncde_logsig_fwd: TMA bulk-copy staging, same as passing
- * LNCDE_FLAG_K1_TMA), "k3_fused" (lncde_logncde_fwd/bwd, specialised H=128 / width 32 kernels: 1 = the 32 x 32
+ * fastest on B200 so far.  Keys: "k1_tma" (lncde_logsig_fwd: 1 = TMA bulk-copy staging, same as passing
+ * LNCDE_FLAG_K1_TMA; 2 = the same kernel persistent, two-buffer ring, grid sized to the machine), "k3_fused" (lncde_logncde_fwd/bwd, specialised H=128 / width 32 kernels: 1 = the 32 x 32
  * layer phases fused on single warps, 2 = additionally phase Q4 of the adjoint folded into Q5), "k2_fused_d" (host mirror: diagonal LNCDE through lncde_dlncde_* instead
  * of flow build + scan).  Process-wide, thread-safe; initial values come from the environment
  * (LNCDE_TUNE_K1_TMA, LNCDE_TUNE_K3_FUSED, LNCDE_TUNE_K2_FUSED_D).  A forward/backward pair must run under the same

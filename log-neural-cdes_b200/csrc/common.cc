@@ -10,9 +10,10 @@
 
 namespace lncde {
 namespace {
-const char* const kTuneNames[kTuneCount] = {"k1_tma", "k3_fused", "k2_fused_d"};
-const char* const kTuneEnv[kTuneCount] = {"LNCDE_TUNE_K1_TMA", "LNCDE_TUNE_K3_FUSED", "LNCDE_TUNE_K2_FUSED_D"};
-std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}};  // -1: not set yet -> environment, else 0
+const char* const kTuneNames[kTuneCount] = {"k1_tma", "k3_fused", "k2_fused_d", "k1_grid_cap"};
+const char* const kTuneEnv[kTuneCount] = {"LNCDE_TUNE_K1_TMA", "LNCDE_TUNE_K3_FUSED", "LNCDE_TUNE_K2_FUSED_D",
+                                          "LNCDE_TUNE_K1_GRID_CAP"};
+std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}, {-1}};  // -1: not set yet -> environment, else 0
 }  // namespace
 
 int tuning_value(int key) {
@@ -20,7 +21,7 @@ int tuning_value(int key) {
   int v = g_tune[key].load(std::memory_order_relaxed);
   if (v < 0) {
     const char* e = std::getenv(kTuneEnv[key]);
-    v = (e && e[0] >= '0' && e[0] <= '9') ? (e[0] - '0') : 0;
+    v = (e && e[0] >= '0' && e[0] <= '9') ? std::atoi(e) : 0;
     int expected = -1;
     g_tune[key].compare_exchange_strong(expected, v);  // a concurrent lncde_set_tuning wins
     v = g_tune[key].load(std::memory_order_relaxed);

@@ -291,125 +291,166 @@ __device__ __forceinline__ void levy_walk_vec(LevyState<C, DEPTH2>& st, const fl
   }
 }
 
-template <int C, bool DEPTH2>
-__global__ void __launch_bounds__(32) logsig_levy_tma_kernel(const LevyParams p) {
+// Geometry of tile t = (sample b, windows k0 .. k0 + nw - 1): floats [start_f, end_f) of the sample - basepoint row
+// k0*s - 2 .. last row (k0 + nw)*s - 2, rows < 0 read as 0 - and the 16-byte aligned range [a0, a1) inside it.
+struct LevyTile {
+  int b, tile, k0, nw, sh0, lead;
+  unsigned bytes;
+  const float *xb, *a0, *t_lo;
+  int n_tail;
+};
+__device__ __forceinline__ LevyTile levy_tile(const LevyParams& p, int C, long long t) {
+  LevyTile g;
+  g.b = (int)(t / p.tiles);
+  g.tile = (int)(t - (long long)g.b * p.tiles);
+  g.k0 = g.tile * 32;
+  g.nw = min(32, p.q - g.k0);
+  g.xb = p.data + (size_t)g.b * p.L * C;
+  const long long start_f = ((long long)g.k0 * p.s - 2) * C;
+  const long long end_f = ((long long)(g.k0 + g.nw) * p.s - 1) * C;
+  const long long lo_f = start_f < 0 ? 0 : start_f;
+  const float* g_lo = g.xb + lo_f;
+  const float* g_end = g.xb + end_f;
+  g.a0 = reinterpret_cast<const float*>((uintptr_t)g_lo & ~(uintptr_t)15);
+  const float* a1 = reinterpret_cast<const float*>((uintptr_t)g_end & ~(uintptr_t)15);
+  g.sh0 = (int)(g_lo - g.a0);
+  g.bytes = (g.nw > 0 && a1 > g.a0) ? (unsigned)((a1 - g.a0) * 4) : 0u;
+  g.t_lo = a1 > g_lo ? a1 : g_lo;                       // <= 3 floats between the 16-byte floor of the end and the end
+  g.n_tail = g.nw > 0 ? (int)(g_end - g.t_lo) : 0;
+  g.lead = (int)(lo_f - start_f);                       // 2C zero floats in front of tile 0, else 0
+  return g;
+}
+// start the load of a tile into `buf`: one bulk copy (lane 0) + the tail floats
+__device__ __forceinline__ void levy_issue(const LevyTile& g, float* buf, unsigned long long* bar, int lane) {
+  float* slab = buf + kLevyPad;  // smem image of a0[...]
+  if (lane == 0 && g.bytes) {
+    mbar_expect_tx(bar, g.bytes);
+    tma_load_1d(slab, g.a0, g.bytes, bar);
+  }
+  if (lane < g.n_tail) slab[(g.t_lo - g.a0) + lane] = ld_stream(g.t_lo + lane);
+}
+
+// PERSISTENT = false: one CTA per tile.  PERSISTENT = true (tuning "k1_tma" = 2): the grid is sized to the machine,
+// a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... through a two-buffer ring - the bulk copy of the NEXT
+// tile is in flight while the current one is walked and stored - so barrier set-up and CTA launch are paid once.
+template <int C, bool DEPTH2, bool PERSISTENT>
+__global__ void __launch_bounds__(32) logsig_levy_tma_kernel(const LevyParams p, int buf_floats) {
   extern __shared__ __align__(128) float smem[];
   constexpr int D = 1 + C + (DEPTH2 ? (C * (C - 1)) / 2 : 0);
   const int lane = threadIdx.x;
-  const int b = blockIdx.x / p.tiles;
-  const int tile = blockIdx.x - b * p.tiles;
-  const int k0 = tile * 32;
-  const int nw = min(32, p.q - k0);
   const int sC = p.s * C;
-  const float* xb = p.data + (size_t)b * p.L * C;
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem);
-  float* buf = smem + 4;  // 16 bytes in: [kLevyPad floats | bulk-copied slab | tail floats]
-
-  LevyState<C, DEPTH2> st;
-  if (nw > 0) {
-    // floats [start_f, end_f) of the sample: basepoint row k0*s-2 .. last row (k0+nw)*s-2; rows < 0 read as 0
-    const long long start_f = ((long long)k0 * p.s - 2) * C;
-    const long long end_f = ((long long)(k0 + nw) * p.s - 1) * C;
-    const long long lo_f = start_f < 0 ? 0 : start_f;
-    const float* g_lo = xb + lo_f;
-    const float* g_end = xb + end_f;
-    const float* a0 = reinterpret_cast<const float*>((uintptr_t)g_lo & ~(uintptr_t)15);
-    const float* a1 = reinterpret_cast<const float*>((uintptr_t)g_end & ~(uintptr_t)15);
-    const int sh0 = (int)(g_lo - a0);
-    const unsigned bytes = a1 > a0 ? (unsigned)((a1 - a0) * 4) : 0u;
-    float* slab = buf + kLevyPad;  // smem image of a0[...]
-    if (lane == 0) {
-      mbar_init(bar, 1);
-      fence_mbar_init();
-      if (bytes) {
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d(slab, a0, bytes, bar);
-      }
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
+  float* bufs = smem + 4;  // 16 bytes in; per buffer: [kLevyPad floats | bulk-copied slab | tail floats]
+  const long long n_tiles = (long long)p.B * p.tiles;
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    if (PERSISTENT) mbar_init(bars + 1, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  long long t = blockIdx.x;
+  if (t >= n_tiles) return;
+  unsigned phase = 0;  // bit s: parity the next wait on buffer s uses
+  bool store_pending = false;
+  levy_issue(levy_tile(p, C, t), bufs, bars, lane);
+  for (int k = 0; t < n_tiles; t += gridDim.x, ++k) {
+    const int sb = PERSISTENT ? (k & 1) : 0;
+    float* buf = bufs + (size_t)sb * buf_floats;
+    if (PERSISTENT && t + gridDim.x < n_tiles) {
+      // the other buffer was the source of the previous tile's bulk store: let that finish reading first
+      if (lane == 0 && store_pending) tma_store_wait_read();
+      __syncwarp();
+      levy_issue(levy_tile(p, C, t + gridDim.x), bufs + (size_t)(sb ^ 1) * buf_floats, bars + (sb ^ 1), lane);
     }
-    // <= 3 floats between the 16-byte floor of the end and the end itself
-    const float* t_lo = a1 > g_lo ? a1 : g_lo;
-    if (lane < (int)(g_end - t_lo)) slab[(t_lo - a0) + lane] = ld_stream(t_lo + lane);
-    __syncwarp();
-    if (bytes) mbar_wait(bar, 0);
-    const int lead = (int)(lo_f - start_f);  // 2C zero floats in front of tile 0, else 0
-    if (lane < lead) slab[sh0 - lead + lane] = 0.f;
-    __syncwarp();
-    if (lane < nw) {
-      const int base_idx = kLevyPad + sh0 - lead + lane * sC;  // basepoint row of this lane's window
-      if ((sC & 3) == 0) {
-        const float* slot = buf + (base_idx & ~3);
-        switch (base_idx & 3) {  // warp-uniform: kLevyPad, lane*sC are multiples of 4
-          case 0: levy_walk_vec<C, DEPTH2, 0>(st, slot, p.s); break;
-          case 1: levy_walk_vec<C, DEPTH2, 1>(st, slot, p.s); break;
-          case 2: levy_walk_vec<C, DEPTH2, 2>(st, slot, p.s); break;
-          default: levy_walk_vec<C, DEPTH2, 3>(st, slot, p.s); break;
-        }
-      } else {
-        const float* rows = buf + base_idx;
-        float tmp[C];
+    const LevyTile g = levy_tile(p, C, t);
+    LevyState<C, DEPTH2> st;
+    if (g.nw > 0) {
+      float* slab = buf + kLevyPad;
+      __syncwarp();
+      if (g.bytes) {
+        mbar_wait(bars + sb, (phase >> sb) & 1u);
+        phase ^= 1u << sb;
+      }
+      if (lane < g.lead) slab[g.sh0 - g.lead + lane] = 0.f;
+      __syncwarp();
+      if (lane < g.nw) {
+        const int base_idx = kLevyPad + g.sh0 - g.lead + lane * sC;  // basepoint row of this lane's window
+        if ((sC & 3) == 0) {
+          const float* slot = buf + (base_idx & ~3);
+          switch (base_idx & 3) {  // warp-uniform: kLevyPad, lane*sC are multiples of 4
+            case 0: levy_walk_vec<C, DEPTH2, 0>(st, slot, p.s); break;
+            case 1: levy_walk_vec<C, DEPTH2, 1>(st, slot, p.s); break;
+            case 2: levy_walk_vec<C, DEPTH2, 2>(st, slot, p.s); break;
+            default: levy_walk_vec<C, DEPTH2, 3>(st, slot, p.s); break;
+          }
+        } else {
+          const float* rows = buf + base_idx;
+          float tmp[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) tmp[c] = rows[c];
-        st.init(tmp);
-        rows += C;
+          for (int c = 0; c < C; ++c) tmp[c] = rows[c];
+          st.init(tmp);
+          rows += C;
 #pragma unroll 2
-        for (int l = 0; l < p.s; ++l) {
+          for (int l = 0; l < p.s; ++l) {
 #pragma unroll
-          for (int c = 0; c < C; ++c) tmp[c] = rows[l * C + c];
-          st.step(tmp);
+            for (int c = 0; c < C; ++c) tmp[c] = rows[l * C + c];
+            st.step(tmp);
+          }
         }
       }
+      __syncwarp();  // every lane is done reading the slab: reuse it for the result rows
+      float* dst = p.out + ((size_t)g.b * p.K + g.k0) * D;
+      const int os = (int)(((uintptr_t)dst >> 2) & 3);  // smem phase = global phase: body 16 B aligned in both
+      float* stage = buf + os;
+      if (lane < g.nw) st.store(stage + lane * D);
+      fence_async_proxy();  // generic-proxy writes above -> visible to the bulk store below
+      __syncwarp();
+      const int n_o = g.nw * D;
+      const int head = min(n_o, (4 - os) & 3);
+      const int body = (n_o - head) & ~3;
+      if (lane == 0 && body > 0) {
+        tma_store_1d(dst + head, stage + head, (unsigned)body * 4);
+        tma_store_commit();
+      }
+      store_pending = body > 0;
+      if (lane < head) dst[lane] = stage[lane];
+      const int tail0 = head + body;
+      if (lane < n_o - tail0) dst[tail0 + lane] = stage[tail0 + lane];
     }
-    __syncwarp();  // every lane is done reading the slab: reuse it for the result rows
-    float* dst = p.out + ((size_t)b * p.K + k0) * D;
-    const int os = (int)(((uintptr_t)dst >> 2) & 3);  // smem phase = global phase: body 16 B aligned in both
-    float* stage = buf + os;
-    if (lane < nw) st.store(stage + lane * D);
-    fence_async_proxy();  // generic-proxy writes above -> visible to the bulk store below
-    __syncwarp();
-    const int n_o = nw * D;
-    const int head = min(n_o, (4 - os) & 3);
-    const int body = (n_o - head) & ~3;
-    if (lane == 0 && body > 0) {
-      tma_store_1d(dst + head, stage + head, (unsigned)body * 4);
-      tma_store_commit();
-    }
-    if (lane < head) dst[lane] = stage[lane];
-    const int tail0 = head + body;
-    if (lane < n_o - tail0) dst[tail0 + lane] = stage[tail0 + lane];
-    if (lane == 0 && body > 0) tma_store_wait_read();  // shared memory must outlive the bulk read
-  }
 
-  // ---- remainder window: handled by the sample's last tile, one thread -----
-  if (p.r != 0 && tile == p.tiles - 1 && lane == 0) {
-    float tmp[C];
-    const bool extra = p.compat != 0;
-    const float* first = xb + (size_t)(p.L - p.r - 1) * C;  // true predecessor row
-    if (extra) {
-      const bool has_prev = (b % p.chunk) != 0;
+    // ---- remainder window: handled with the sample's last tile, one thread -----
+    if (p.r != 0 && g.tile == p.tiles - 1 && lane == 0) {
+      float tmp[C];
+      const float* xb = g.xb;
+      const bool extra = p.compat != 0;
+      const float* first = xb + (size_t)(p.L - p.r - 1) * C;  // true predecessor row
+      if (extra) {
+        const bool has_prev = (g.b % p.chunk) != 0;
 #pragma unroll
-      for (int c = 0; c < C; ++c) tmp[c] = has_prev ? xb[-C + c] : 0.f;  // last row of sample b-1
-      st.init(tmp);
+        for (int c = 0; c < C; ++c) tmp[c] = has_prev ? xb[-C + c] : 0.f;  // last row of sample b-1
+        st.init(tmp);
 #pragma unroll
-      for (int c = 0; c < C; ++c) tmp[c] = first[c];
-      st.step(tmp);
-    } else {
+        for (int c = 0; c < C; ++c) tmp[c] = first[c];
+        st.step(tmp);
+      } else {
 #pragma unroll
-      for (int c = 0; c < C; ++c) tmp[c] = first[c];
-      st.init(tmp);
+        for (int c = 0; c < C; ++c) tmp[c] = first[c];
+        st.init(tmp);
+      }
+      for (int l = 1; l <= p.r; ++l) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) tmp[c] = first[l * C + c];
+        st.step(tmp);
+      }
+      float row[D];
+      st.store(row);
+      float* dst = p.out + ((size_t)g.b * p.K + p.q) * D;
+#pragma unroll
+      for (int c = 0; c < D; ++c) dst[c] = row[c];
     }
-    for (int l = 1; l <= p.r; ++l) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) tmp[c] = first[l * C + c];
-      st.step(tmp);
-    }
-    float row[D];
-    st.store(row);
-    float* dst = p.out + ((size_t)b * p.K + p.q) * D;
-#pragma unroll
-    for (int c = 0; c < D; ++c) dst[c] = row[c];
   }
+  if (lane == 0 && store_pending) tma_store_wait_read();  // shared memory must outlive the bulk read
 }
-
 
 // ----------------------------------------------------------------------------
 // depth 3, C <= 8: thread (window, i) keeps "row i" of the truncated signature in registers
@@ -676,22 +717,38 @@ __global__ void __launch_bounds__(128) logsig_tensor_kernel(const TensorParams p
 }
 
 template <int C>
-static int launch_levy_tma(cudaStream_t st, LevyParams p, int depth) {
+static int launch_levy_tma(cudaStream_t st, LevyParams p, int depth, bool persistent) {
   const int D = 1 + C + (depth == 2 ? (C * (C - 1)) / 2 : 0);
   p.WT = 32;
   p.tiles = (p.q + 31) / 32;
   if (p.tiles < 1) p.tiles = 1;
-  // [mbarrier 16 B | kLevyPad | 32 windows + basepoint row + <= 3 alignment floats | 4 floats of over-read slack]
-  const size_t in_f = 4 + kLevyPad + (size_t)32 * p.s * C + C + 3 + 4;
-  const size_t out_f = 4 + 3 + (size_t)32 * D + 4;
-  const size_t smem = (in_f > out_f ? in_f : out_f) * 4;
-  const int grid = p.B * p.tiles;
+  // per buffer: [kLevyPad | 32 windows + basepoint row + <= 3 alignment floats | 4 floats of over-read slack], or the
+  // 32 x D result rows staged in the same place
+  const size_t in_f = kLevyPad + (size_t)32 * p.s * C + C + 3 + 4;
+  const size_t out_f = 3 + (size_t)32 * D + 4;
+  const size_t buf_f = ((in_f > out_f ? in_f : out_f) + 3) & ~(size_t)3;
+  const size_t smem = (4 + buf_f * (persistent ? 2 : 1)) * 4;  // 16 bytes of mbarriers in front
+  const long long n_tiles = (long long)p.B * p.tiles;
+  long long grid = n_tiles;
+  if (persistent) {
+    long long occ = (long long)(220 * 1024) / (long long)smem;  // CTAs per SM that fit in shared memory
+    if (occ > 16) occ = 16;
+    if (occ < 1) occ = 1;
+    if (grid > 148 * occ) grid = 148 * occ;                      // B200: 148 SMs
+    const int cap = tuning_value(kTuneK1GridCap);
+    if (cap > 0 && grid > cap) grid = cap;
+  }
   auto go = [&](auto k) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, 32, smem, st>>>(p);
+    k<<<(int)grid, 32, smem, st>>>(p, (int)buf_f);
   };
-  if (depth == 2) go(logsig_levy_tma_kernel<C, true>);
-  else go(logsig_levy_tma_kernel<C, false>);
+  if (persistent) {
+    if (depth == 2) go(logsig_levy_tma_kernel<C, true, true>);
+    else go(logsig_levy_tma_kernel<C, false, true>);
+  } else {
+    if (depth == 2) go(logsig_levy_tma_kernel<C, true, false>);
+    else go(logsig_levy_tma_kernel<C, false, false>);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -753,17 +810,18 @@ int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int 
     // LNCDE_FLAG_K1_TMA (or the "k1_tma" tuning value, tuning.h) selects the bulk-copy kernel; it
     // needs a 16-byte aligned `data` so that the 16-byte floor of a tile's first float never precedes
     // the buffer.  Default: the classic kernel (the one measured on B200 so far).
-    const bool use_tma = (flags & LNCDE_FLAG_K1_TMA) || tuning_value(kTuneK1Tma);
-    if (use_tma && ((uintptr_t)data & 15) == 0) {
+    const int tma_mode = tuning_value(kTuneK1Tma) ? tuning_value(kTuneK1Tma) : ((flags & LNCDE_FLAG_K1_TMA) ? 1 : 0);
+    if (tma_mode && ((uintptr_t)data & 15) == 0) {
+      const bool persistent = tma_mode >= 2 && sC <= 1024;
       switch (C) {
-        case 1: return launch_levy_tma<1>(st, p, depth);
-        case 2: return launch_levy_tma<2>(st, p, depth);
-        case 3: return launch_levy_tma<3>(st, p, depth);
-        case 4: return launch_levy_tma<4>(st, p, depth);
-        case 5: return launch_levy_tma<5>(st, p, depth);
-        case 6: return launch_levy_tma<6>(st, p, depth);
-        case 7: return launch_levy_tma<7>(st, p, depth);
-        case 8: return launch_levy_tma<8>(st, p, depth);
+        case 1: return launch_levy_tma<1>(st, p, depth, persistent);
+        case 2: return launch_levy_tma<2>(st, p, depth, persistent);
+        case 3: return launch_levy_tma<3>(st, p, depth, persistent);
+        case 4: return launch_levy_tma<4>(st, p, depth, persistent);
+        case 5: return launch_levy_tma<5>(st, p, depth, persistent);
+        case 6: return launch_levy_tma<6>(st, p, depth, persistent);
+        case 7: return launch_levy_tma<7>(st, p, depth, persistent);
+        case 8: return launch_levy_tma<8>(st, p, depth, persistent);
       }
     }
     static const int wt_env = getenv("LNCDE_LEVY_WT") ? atoi(getenv("LNCDE_LEVY_WT")) : 0;

@@ -9,6 +9,7 @@ enum TuneKey {
   kTuneK1Tma = 0,    // "k1_tma":   closed-form logsig kernel with TMA bulk-copy staging (logsig_levy_tma_kernel)
   kTuneK3Fused = 1,  // "k3_fused": specialised Log-NCDE kernels with the 32 x 32 layer phases fused on single warps
   kTuneK2FusedD = 2, // "k2_fused_d": read by the host mirror - diagonal LNCDE through the fused K2d kernels (dlncde.cu)
+  kTuneK1GridCap = 3, // "k1_grid_cap": upper bound on the grid of the persistent K1 kernel (0 = machine-sized); experiments, tests
   kTuneCount
 };
 

@@ -26,11 +26,25 @@ import numpy as np
 import torch
 
 
+def _persistent(fn):
+    """Run fn() with the persistent bulk-copy K1 kernel (tuning k1_tma = 2)."""
+    from lncde import _lib
+
+    _lib.set_tuning("k1_tma", 2)
+    try:
+        out = fn()
+        torch.cuda.synchronize()
+        return out
+    finally:
+        _lib.set_tuning("k1_tma", 0)
+
+
 def parity():
     from lncde.data_dir.generate_paths import calc_paths
     from oracle import paths
 
-    res = {"cases": 0, "bit_identical_to_classic": True, "max_rel_err_vs_fp64_oracle": 0.0, "integer_kat_exact": True}
+    res = {"cases": 0, "bit_identical_to_classic": True, "persistent_bit_identical": True,
+           "max_rel_err_vs_fp64_oracle": 0.0, "integer_kat_exact": True}
     rng = np.random.default_rng(3)
     # integer KATs (bit-exact), all widths / odd sizes / every tile phase
     for C in range(1, 9):
@@ -43,9 +57,11 @@ def parity():
                 want = paths.calc_paths(x, s, depth, np.float64)
                 a = calc_paths(xd, s, depth, kernel="tma").cpu().numpy()
                 b = calc_paths(xd, s, depth, kernel="classic").cpu().numpy()
+                a2 = _persistent(lambda: calc_paths(xd, s, depth)).cpu().numpy()
                 res["cases"] += 1
                 res["integer_kat_exact"] &= bool(np.array_equal(a.astype(np.float64), want))
                 res["bit_identical_to_classic"] &= bool(np.array_equal(a, b))
+                res["persistent_bit_identical"] &= bool(np.array_equal(a2, b))
     # float paths at the BASELINE shapes (short batch)
     for C, s, L in [(7, 12, 17984), (6, 12, 17984), (6, 16, 896), (7, 10, 4992), (4, 10, 4992), (7, 16, 896)]:
         x = np.cumsum(rng.normal(scale=0.05, size=(3, L, C)), axis=1).astype(np.float32)
@@ -53,12 +69,15 @@ def parity():
         want = paths.calc_paths(x, s, 2, np.float64)
         a = calc_paths(xd, s, 2, kernel="tma").cpu().numpy()
         b = calc_paths(xd, s, 2, kernel="classic").cpu().numpy()
+        a2 = _persistent(lambda: calc_paths(xd, s, 2)).cpu().numpy()
         res["cases"] += 1
         res["bit_identical_to_classic"] &= bool(np.array_equal(a, b))
+        res["persistent_bit_identical"] &= bool(np.array_equal(a2, b))
         err = float(np.abs(a - want).max() / np.abs(want).max())
         res["max_rel_err_vs_fp64_oracle"] = max(res["max_rel_err_vs_fp64_oracle"], err)
     res["ok"] = bool(res["integer_kat_exact"] and res["bit_identical_to_classic"]
                      and res["max_rel_err_vs_fp64_oracle"] < 1e-5)
+    res["ok_by_variant"] = {"1": res["ok"], "2": bool(res["ok"] and res["persistent_bit_identical"])}
     return res
 
 
@@ -70,18 +89,22 @@ def timing(B=2048, L=17984, C=7, s=12, reps=10):
     out = torch.empty((B, (L + 1 + s - 1) // s, 1 + C + C * (C - 1) // 2), device="cuda")
     byts = x.numel() * 4 + out.numel() * 4
     res = {"shape": f"B={B} x L={L} x C={C}, stepsize {s}, depth 2", "algorithmic_bytes": byts}
-    for k in ("classic", "tma"):
+    from lncde import _lib
+
+    for k, mode in (("classic", 0), ("tma", 1), ("tma_persistent", 2)):
+        _lib.set_tuning("k1_tma", mode)
         for _ in range(3):
-            calc_paths(x, s, 2, out=out, kernel=k)
+            calc_paths(x, s, 2, out=out)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            calc_paths(x, s, 2, out=out, kernel=k)
+            calc_paths(x, s, 2, out=out)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         res[k] = {"ms": ms, "GB/s": byts / ms / 1e6}
+    _lib.set_tuning("k1_tma", 0)
     return res
 
 

@@ -51,6 +51,14 @@ def set_tuning(key, value):
     assert lib().lncde_set_tuning(key.encode(), int(value)) == 0
 
 
+def _with_tuning(key, value, fn):
+    set_tuning(key, value)
+    try:
+        return fn()
+    finally:
+        set_tuning(key, 0)
+
+
 def bulk_copies():
     """Bulk (TMA) copies issued by the emulated kernels since the last call."""
     return lib().emu_bulk_copies()
@@ -80,6 +88,7 @@ def f32(a):
 
 
 def calc_paths(x, stepsize, depth, compat=True, chunk=None, tma=False, misalign=0, tight_end=True):
+    """tma: False (classic kernel), True / 1 (bulk-copy kernel, one CTA per tile), 2 (persistent bulk-copy kernel)."""
     L = lib()
     x = f32(x)
     B, Ln, Cn = x.shape
@@ -96,7 +105,10 @@ def calc_paths(x, stepsize, depth, compat=True, chunk=None, tma=False, misalign=
     xin = guarded(x.shape, tight_end=tight_end, start_mod16=4 * (misalign % 4))
     xin[...] = x
     st = L.lncde_logsig_fwd(None, _p(xin), _p(out), B, Ln, Cn, int(stepsize), depth,
-                            (1 if compat else 0) | (4 if tma else 0), int(chunk or B), _p(rowptr), _p(cols), _p(vals))
+                            (1 if compat else 0) | (4 if tma else 0), int(chunk or B), _p(rowptr), _p(cols), _p(vals)) \
+        if int(tma) < 2 else _with_tuning("k1_tma", 2, lambda: L.lncde_logsig_fwd(
+            None, _p(xin), _p(out), B, Ln, Cn, int(stepsize), depth, 1 if compat else 0, int(chunk or B), _p(rowptr),
+            _p(cols), _p(vals)))
     assert st == 0, st
     return out.copy()
 

@@ -31,13 +31,22 @@ def _walk(B, L, C, seed=2345):
 
 
 # ------------------------------------------------------------------------------------------ K1
-# tma=False: logsig_levy_kernel (classic staging); tma=True: logsig_levy_tma_kernel (bulk copies).
+# tma=False: logsig_levy_kernel (classic staging); tma=True / 1: logsig_levy_tma_kernel (bulk copies, one CTA per
+# tile); tma=2: the same kernel persistent (two-buffer ring; the grid is capped at 3 CTAs here so that every CTA
+# walks many tiles and both buffers / both mbarrier parities are exercised).
 # Inputs and outputs sit in guard-page bounded allocations (tight at the end or at the start), so an
 # out-of-bounds global access of either kernel faults instead of passing silently.
-@pytest.mark.parametrize("tma", [False, True])
+@pytest.fixture
+def small_grid():
+    E.set_tuning("k1_grid_cap", 3)
+    yield
+    E.set_tuning("k1_grid_cap", 0)
+
+
+@pytest.mark.parametrize("tma", [False, True, 2])
 @pytest.mark.parametrize("C", [1, 2, 3, 6, 7, 8])
 @pytest.mark.parametrize("depth", [1, 2])
-def test_emu_logsig_integer_kat_bit_exact(C, depth, tma):
+def test_emu_logsig_integer_kat_bit_exact(C, depth, tma, small_grid):
     x = _toy(5, 100, C)
     for s in (1, 4, 7, 12, 100, 101, 500):
         want = paths.calc_paths(x, s, depth, np.float64)
@@ -47,24 +56,24 @@ def test_emu_logsig_integer_kat_bit_exact(C, depth, tma):
             assert np.array_equal(got.astype(np.float64), want), (C, depth, s)
 
 
-@pytest.mark.parametrize("tma", [False, True])
+@pytest.mark.parametrize("tma", [False, True, 2])
 @pytest.mark.parametrize("compat", [True, False])
-def test_emu_logsig_compat_and_chunk(compat, tma):
+def test_emu_logsig_compat_and_chunk(compat, tma, small_grid):
     x = _toy(140, 30, 3)
     want = paths.batch_calc_paths(x, 4, 2, np.float64, compat=compat)
     got = E.calc_paths(x, 4, 2, compat=compat, chunk=128, tma=tma)
     assert np.array_equal(got.astype(np.float64), want)
 
 
-@pytest.mark.parametrize("tma", [False, True])
+@pytest.mark.parametrize("tma", [False, True, 2])
 @pytest.mark.parametrize("C,s,L", [(7, 12, 1200), (6, 12, 1190), (6, 16, 896), (7, 10, 999), (4, 10, 503), (5, 3, 1000),
                                    (3, 7, 333), (8, 16, 700)])
-def test_emu_logsig_float_paths_depth2(C, s, L, tma):
+def test_emu_logsig_float_paths_depth2(C, s, L, tma, small_grid):
     x = _walk(3, L, C)
     want = paths.calc_paths(x, s, 2, np.float64)
     E.bulk_copies()
     got = E.calc_paths(x, s, 2, tma=tma)
-    assert (E.bulk_copies() > 0) == tma  # the requested kernel is the one that ran
+    assert (E.bulk_copies() > 0) == bool(tma)  # the requested kernel is the one that ran
     assert got.shape == want.shape
     assert rel_err(got, want) < TOL
 
@@ -79,6 +88,12 @@ def test_emu_logsig_tma_equals_classic_every_alignment():
             a = E.calc_paths(x, s, depth, tma=False)
             b = E.calc_paths(x, s, depth, tma=True)
             assert np.array_equal(a, b), (C, L, s, depth)
+            for cap in (1, 2, 5):
+                E.set_tuning("k1_grid_cap", cap)
+                try:
+                    assert np.array_equal(a, E.calc_paths(x, s, depth, tma=2)), (C, L, s, depth, cap)
+                finally:
+                    E.set_tuning("k1_grid_cap", 0)
 
 
 def test_emu_logsig_tma_eigenworms_length():
@@ -90,6 +105,11 @@ def test_emu_logsig_tma_eigenworms_length():
     assert got.shape == (1, 1499, 29)
     assert rel_err(got, want) < TOL
     assert np.array_equal(got, E.calc_paths(x, 12, 2, tma=False))
+    E.set_tuning("k1_grid_cap", 4)  # 47 tiles on 4 persistent CTAs
+    try:
+        assert np.array_equal(got, E.calc_paths(x, 12, 2, tma=2))
+    finally:
+        E.set_tuning("k1_grid_cap", 0)
 
 
 @pytest.mark.parametrize("C,depth", [(2, 3), (3, 3), (7, 3), (2, 4), (3, 4), (10, 2), (9, 1)])
@@ -280,7 +300,7 @@ _N = np.load(os.path.join(GOLDEN, "ref_logncde.npz"))
 _LN = np.load(os.path.join(GOLDEN, "ref_linear.npz"))
 
 
-@pytest.mark.parametrize("tma", [False, True])
+@pytest.mark.parametrize("tma", [False, True, 2])
 @pytest.mark.parametrize("i", range(int(_P["n"])))
 def test_emu_logsig_vs_reference_code(i, tma):
     B, L, C, s, d = (int(v) for v in _P[f"cfg{i}"])

@@ -100,10 +100,13 @@ def test_bench_autotune_decision():
     ok, bad = {"ok": True}, {"ok": False}
     t = lambda **kw: {k: {"ms": v} for k, v in kw.items()}
     k3ok = {"ok": True, "ok_by_variant": {"1": True, "2": True}}
-    rep = {"k1": {"parity": ok, "timing": t(classic=0.33, tma=0.25)},
+    k1ok = {"ok": True, "ok_by_variant": {"1": True, "2": True}}
+    rep = {"k1": {"parity": k1ok, "timing": t(classic=0.33, tma=0.25, tma_persistent=0.26)},
            "k3": {"parity": k3ok, "timing": t(default=19.0, fused=18.9, fused2=18.8)}}
     assert bench.decide_tuning(rep) == {"k1_tma": 1, "k3_fused": 0}       # 1 % is inside the noise margin
-    rep["k1"]["parity"] = bad
+    rep["k1"]["timing"] = t(classic=0.33, tma=0.25, tma_persistent=0.22)
+    assert bench.decide_tuning(rep)["k1_tma"] == 2
+    rep["k1"]["parity"] = {"ok": False, "ok_by_variant": {"1": False, "2": False}}
     rep["k3"]["timing"] = t(default=19.0, fused=15.0, fused2=14.0)
     assert bench.decide_tuning(rep) == {"k1_tma": 0, "k3_fused": 2}       # faster but wrong is never used; best variant wins
     rep["k3"]["parity"] = {"ok": False, "ok_by_variant": {"1": True, "2": False}}
