@@ -438,17 +438,18 @@ def autotune():
     each variant in a SUBPROCESS (a variant that has never been on this hardware cannot take the bench down),
     checks it against the default kernels and times both; a variant is switched on only if its parity check
     passed there and it was measurably faster.  Returns (choices, raw report)."""
-    choice = {"k1_tma": 0, "k3_fused": 0}
-    try:
-        r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "variant_check.py"), "--skip", "k2"],
-                           capture_output=True, text=True, timeout=200)
-        if r.returncode != 0:
-            return choice, {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
-        rep = json.loads(r.stdout.strip().splitlines()[-1])
-    except Exception as e:  # timeout, unparsable output
-        return choice, {"error": f"{type(e).__name__}: {e}"[:300]}
-    choice = decide_tuning(rep)
-    return choice, rep
+    rep = {}
+    for which in ("k1", "k3"):  # one process each: a fault or hang in one family does not lose the other
+        try:
+            r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "variant_check.py"), "--only", which],
+                               capture_output=True, text=True, timeout=150)
+            if r.returncode != 0:
+                rep[which] = {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
+            else:
+                rep[which] = json.loads(r.stdout.strip().splitlines()[-1]).get(which, {"error": "no result"})
+        except Exception as e:  # timeout, unparsable output
+            rep[which] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return decide_tuning(rep), rep
 
 
 def breakdown(model, opt, x_dev, lab_dev):
