@@ -191,9 +191,11 @@ def run_ours(args):
 
     # ---- kernel-variant autotune (rank 0 decides, everybody applies the same choice) -------------------
     tuning, tune_report = {"k1_tma": 0, "k3_fused": 0}, None
-    if not args.no_autotune and args.workload == "eigenworms_logncde":
+    families = {"log_ncde": ("k1", "k3"), "diagonal_linear_ncde": ("k1", "k2"), "dense_linear_ncde": ("k1", "k2de")}
+    if not args.no_autotune and (args.workload == "eigenworms_logncde" or WL["model"] in ("diagonal_linear_ncde",
+                                                                                           "dense_linear_ncde")):
         if rank == 0:
-            tuning, tune_report = autotune()
+            tuning, tune_report = autotune(families[WL["model"]])
         if world > 1:
             box = [tuning]
             dist.broadcast_object_list(box, src=0)
@@ -413,6 +415,16 @@ def decide_tuning(rep, margin=0.98):
     """A variant is used only if ITS parity check passed and it beat the default by the margin."""
     choice = {"k1_tma": 0, "k3_fused": 0}
     k1, k3 = rep.get("k1", {}), rep.get("k3", {})
+    for fam, key, base, var in (("k2", "k2_fused_d", "default_B32", "fused_B32"), ("k2de", "k2_de_v2", "default", "v2")):
+        r = rep.get(fam)
+        if r is None:
+            continue
+        choice[key] = 0
+        try:
+            if "error" not in r and r.get("parity", {}).get("ok") and r["timing"][var]["ms"] < margin * r["timing"][base]["ms"]:
+                choice[key] = 1
+        except (KeyError, TypeError):
+            pass
     try:
         if "error" not in k1 and "timing" in k1:
             ok = k1.get("parity", {}).get("ok_by_variant", {})
@@ -433,13 +445,13 @@ def decide_tuning(rep, margin=0.98):
     return choice
 
 
-def autotune():
+def autotune(families=("k1", "k3")):
     """Pick among kernel variants that compute the same result (lncde.set_tuning): scripts/variant_check.py runs
     each variant in a SUBPROCESS (a variant that has never been on this hardware cannot take the bench down),
     checks it against the default kernels and times both; a variant is switched on only if its parity check
     passed there and it was measurably faster.  Returns (choices, raw report)."""
     rep = {}
-    for which in ("k1", "k3"):  # one process each: a fault or hang in one family does not lose the other
+    for which in families:  # one process each: a fault or hang in one family does not lose the other
         try:
             r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "variant_check.py"), "--only", which],
                                capture_output=True, text=True, timeout=150)

@@ -47,8 +47,11 @@ const char* lncde_strerror(int status);
  * fastest on B200 so far.  Keys: "k1_tma" (lncde_logsig_fwd: 1 = TMA bulk-copy staging, same as passing
  * LNCDE_FLAG_K1_TMA; 2 = the same kernel persistent, two-buffer ring, grid sized to the machine), "k3_fused" (lncde_logncde_fwd/bwd, specialised H=128 / width 32 kernels: 1 = the 32 x 32
  * layer phases fused on single warps, 2 = additionally phase Q4 of the adjoint folded into Q5), "k2_fused_d" (host mirror: diagonal LNCDE through lncde_dlncde_* instead
- * of flow build + scan).  Process-wide, thread-safe; initial values come from the environment
- * (LNCDE_TUNE_K1_TMA, LNCDE_TUNE_K3_FUSED, LNCDE_TUNE_K2_FUSED_D).  A forward/backward pair must run under the same
+ * of flow build + scan), "k2_de_v2" (lncde_linear_scan_fwd/bwd with block size >= 64: 128 x 128 flow-build tiles with
+ * 8 x 8 register tiles; the reverse sweep stores lam_t instead of dF_t and the bracket gradient is the triple product
+ * sum lam_t (x) y_{t-1} (x) logsig_t - the flows in the workspace are then left intact by the backward call).
+ * Process-wide, thread-safe; initial values come from the environment
+ * (LNCDE_TUNE_K1_TMA, LNCDE_TUNE_K3_FUSED, LNCDE_TUNE_K2_FUSED_D, LNCDE_TUNE_K2_DE_V2).  A forward/backward pair must run under the same
  * setting only in the sense that each call reads the value once at entry; results are interchangeable. */
 int lncde_set_tuning(const char* key, int value);
 int lncde_get_tuning(const char* key); /* value, or <0 for an unknown key */
@@ -139,7 +142,8 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig,
  *        for bs == 1 this is vf_A^T laid out [H, n_coeff]
  *   logsig [B, T, D]; uses columns 1 .. n_basis
  *   y0 [B, H];  ys [B, T, H] (ys[:,0] = y0)                                  */
-/* Scratch shared by forward and backward: the flows F [B,T,nb,bs,bs] plus split-K partials.
+/* Scratch shared by forward and backward: the flows F [B,T,nb,bs,bs] plus split-K partials (plus lam [B,T,H] for
+ * block sizes >= 64, used by the "k2_de_v2" kernels).
  * The backward call must receive the SAME workspace the forward call of the same
  * (lie, logsig) filled, untouched in between (it reads F_t and overwrites it with dF_t).   */
 size_t lncde_linear_scan_workspace_bytes(int B, int T, int nb, int bs, int n_basis);

@@ -1,0 +1,310 @@
+// K2 "dense v2" (tuning "k2_de_v2"): the two kernels that dominate the DE-LNCDE step besides the scans.
+//
+// ncu launch list of round 1 (EigenWorms DE, 32 x 1499 x 128 x 128, n_basis 28): flow build 3.8 ms for 44 GFLOP
+// and 3.1 GB of output (16 % of the FP32 peak - its 4 x 4 register tile issues one shared-memory load per two
+// FMAs), bracket-gradient GEMM 1.7 ms reading 3.1 GB of dF that the reverse scan had to write first.
+//
+//  * flow_build8_kernel: same contraction F[m][n] = eye + sum_l ls[m][1+l] lie[n][l] with a 128 x 128 CTA tile and
+//    an 8 x 8 register tile per thread: per k-step 4 conflict-free 128-bit shared loads feed 64 FMAs, every
+//    thread stores rows of 2 x 128 bits (256-byte segments per half-warp).  K = n_basis is 21..36 at depth 2:
+//    one or two k-tiles, so the kernel is FP32-issue bound with the 3.1 GB of output streaming out underneath.
+//  * dlie_triple_kernel: dLie[(i,j)][l] = sum_{b,t>=1} lam_t[i] * y_{t-1}[j] * ls[t][1+l] straight from the small
+//    operands (lam, y: 24 MB each, ls: 5 MB) - the reverse scan then only has to store lam_t (512 B per step)
+//    instead of the outer product dF_t (64 KB per step), and nothing reads 3.1 GB back.  Same FLOPs as the GEMM it
+//    replaces (the rank-1 factor costs 2 extra multiplies per 56 FMAs), split-K with a deterministic reduce.
+//  * scan_bwd_tma_lam_kernel: the reverse sweep of scan_bwd_tma_kernel (linear_scan.cu) with the in-place dF_t store
+//    replaced by a 512-byte store of lam_t - same ring of TMA bulk copies, same order of the sums, so lam, g_y0 are
+//    bit-identical to the default kernel; the flows in the workspace stay intact.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "ptx.cuh"
+
+namespace lncde {
+
+// ---------------------------------------------------------------- flow build, 8 x 8 register tile
+// thread (tx, ty) of 16 x 16 owns rows ty*4 + {0..3} and 64 + ty*4 + {0..3}, columns tx*4 + {0..3} and
+// 64 + tx*4 + {0..3} of the 128 x 128 tile: every 128-bit operand load of a half-warp covers 256 contiguous bytes.
+__global__ void __launch_bounds__(256) flow_build8_kernel(const float* __restrict__ lie,
+                                                          const float* __restrict__ logsig, float* __restrict__ F,
+                                                          long long Mtot, int N, int D, int n_basis, int bs) {
+  constexpr int KT = 32, TS = 128;
+  __shared__ __align__(16) float As[KT][TS];  // logsig tile, k-major
+  __shared__ __align__(16) float Bs[KT][TS];  // lie tile, k-major
+  const long long m0 = (long long)blockIdx.y * TS;
+  const int n0 = blockIdx.x * TS;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < n_basis; k0 += KT) {
+    // consecutive threads walk the rows (columns) of the tile: conflict-free shared stores
+    for (int e = threadIdx.x; e < KT * TS; e += 256) {
+      const int kk = e >> 7, m = e & (TS - 1);
+      As[kk][m] = (m0 + m < Mtot && k0 + kk < n_basis) ? __ldg(logsig + (m0 + m) * D + 1 + k0 + kk) : 0.f;
+      Bs[kk][m] = (n0 + m < N && k0 + kk < n_basis) ? __ldg(lie + (size_t)(n0 + m) * n_basis + k0 + kk) : 0.f;
+    }
+    __syncthreads();
+    const int kmax = min(KT, n_basis - k0);
+#pragma unroll 4
+    for (int kk = 0; kk < kmax; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  const int bs2 = bs * bs;
+  const bool vec = (N & 3) == 0;  // rows of F are 16-byte aligned (workspace is, N % 4 == 0)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
+    if (m >= Mtot) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + jh * 64 + tx * 4;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = (n + j) % bs2;
+        v[j] = acc[i][jh * 4 + j] + ((r / bs == r % bs) ? 1.f : 0.f);
+      }
+      float* dst = F + m * N + n;
+      if (vec && n + 3 < N) {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < N) dst[j] = v[j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- bracket gradient without dF
+// out[ks][((blk*bs + i)*bs + j)*n_basis + l] = sum over the k-slice of lam[b,t,blk*bs+i] * y[b,t-1,blk*bs+j] * ls[b,t,1+l]
+// with k = b*(T-1) + (t-1), t = 1..T-1.  CTA tile: 16 (i) x 32 (j) x all l; thread (ty = i, tx) owns j = tx and tx + 16.
+template <int NBP>  // n_basis rounded up to a multiple of 4 (<= 36)
+__global__ void __launch_bounds__(256) dlie_triple_kernel(const float* __restrict__ lam, const float* __restrict__ ys,
+                                                          const float* __restrict__ logsig, float* __restrict__ part,
+                                                          int B, int T, int D, int H, int bs, int n_basis, int ksplit,
+                                                          int i_tiles, int j_tiles) {
+  constexpr int KC = 32, TI = 16, TJ = 32;
+  __shared__ __align__(16) float lam_s[KC][TI];
+  __shared__ __align__(16) float y_s[KC][TJ];
+  __shared__ __align__(16) float ls_s[KC][NBP];
+  int bid = blockIdx.x;
+  const int ks = bid % ksplit; bid /= ksplit;
+  const int jt = bid % j_tiles; bid /= j_tiles;
+  const int it = bid % i_tiles; bid /= i_tiles;
+  const int blk = bid;
+  const int i0 = it * TI, j0 = jt * TJ;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const unsigned Tm1 = (unsigned)(T - 1);
+  const unsigned Ktot = (unsigned)B * Tm1;  // < 2^31 (checked by the dispatcher): 32-bit index arithmetic
+  const unsigned per = (Ktot + ksplit - 1) / ksplit;
+  const unsigned k_lo = min(Ktot, per * ks), k_hi = min(Ktot, k_lo + per);
+  float acc0[NBP], acc1[NBP];
+#pragma unroll
+  for (int l = 0; l < NBP; ++l) acc0[l] = acc1[l] = 0.f;
+  for (unsigned kc = k_lo; kc < k_hi; kc += KC) {
+    for (int e = threadIdx.x; e < KC * TI; e += 256) {
+      const int kk = e / TI, i = e - kk * TI;
+      const unsigned k = kc + kk;
+      float v = 0.f;
+      if (k < k_hi && i0 + i < bs) {
+        const unsigned b = k / Tm1, t = 1 + (k - b * Tm1);
+        v = __ldg(lam + ((size_t)b * T + t) * H + blk * bs + i0 + i);
+      }
+      lam_s[kk][i] = v;
+    }
+    for (int e = threadIdx.x; e < KC * TJ; e += 256) {
+      const int kk = e / TJ, j = e - kk * TJ;
+      const unsigned k = kc + kk;
+      float v = 0.f;
+      if (k < k_hi && j0 + j < bs) {
+        const unsigned b = k / Tm1, t = 1 + (k - b * Tm1);
+        v = __ldg(ys + ((size_t)b * T + t - 1) * H + blk * bs + j0 + j);
+      }
+      y_s[kk][j] = v;
+    }
+    for (int e = threadIdx.x; e < KC * NBP; e += 256) {
+      const int kk = e / NBP, l = e - kk * NBP;
+      const unsigned k = kc + kk;
+      float v = 0.f;
+      if (k < k_hi && l < n_basis) {
+        const unsigned b = k / Tm1, t = 1 + (k - b * Tm1);
+        v = __ldg(logsig + ((size_t)b * T + t) * D + 1 + l);
+      }
+      ls_s[kk][l] = v;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int kk = 0; kk < KC; ++kk) {
+      const float li = lam_s[kk][ty];
+      const float w0 = li * y_s[kk][tx], w1 = li * y_s[kk][tx + 16];
+#pragma unroll
+      for (int q = 0; q < NBP / 4; ++q) {
+        const float4 s4 = *reinterpret_cast<const float4*>(&ls_s[kk][4 * q]);
+        acc0[4 * q + 0] = fmaf(w0, s4.x, acc0[4 * q + 0]);
+        acc0[4 * q + 1] = fmaf(w0, s4.y, acc0[4 * q + 1]);
+        acc0[4 * q + 2] = fmaf(w0, s4.z, acc0[4 * q + 2]);
+        acc0[4 * q + 3] = fmaf(w0, s4.w, acc0[4 * q + 3]);
+        acc1[4 * q + 0] = fmaf(w1, s4.x, acc1[4 * q + 0]);
+        acc1[4 * q + 1] = fmaf(w1, s4.y, acc1[4 * q + 1]);
+        acc1[4 * q + 2] = fmaf(w1, s4.z, acc1[4 * q + 2]);
+        acc1[4 * q + 3] = fmaf(w1, s4.w, acc1[4 * q + 3]);
+      }
+    }
+    __syncthreads();
+  }
+  const size_t n_out = (size_t)(H / bs) * bs * bs * n_basis;
+  float* out = part + (size_t)ks * n_out;
+  const int i = i0 + ty;
+  if (i < bs) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j = j0 + tx + 16 * half;
+      if (j >= bs) continue;
+      float* o = out + (((size_t)blk * bs + i) * bs + j) * n_basis;
+#pragma unroll
+      for (int l = 0; l < NBP; ++l)
+        if (l < n_basis) o[l] = half ? acc1[l] : acc0[l];
+    }
+  }
+}
+
+template <int NBP>
+static inline void launch_dlie_triple(cudaStream_t st, int grid, const float* lam, const float* ys, const float* ls,
+                                      float* part, int B, int T, int D, int H, int bs, int n_basis, int ksplit, int it,
+                                      int jt) {
+  dlie_triple_kernel<NBP><<<grid, 256, 0, st>>>(lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt);
+}
+
+// returns false if n_basis is outside the compiled range
+static inline bool dlie_triple_dispatch(cudaStream_t st, const float* lam, const float* ys, const float* ls, float* part,
+                                        int B, int T, int D, int H, int bs, int n_basis, int ksplit) {
+  if (T < 2 || (long long)B * (T - 1) >= (1ll << 31) - 64) return false;
+  const int nb = H / bs, it = (bs + 15) / 16, jt = (bs + 31) / 32;
+  const int grid = nb * it * jt * ksplit;
+  const int nbp = (n_basis + 3) & ~3;
+  switch (nbp) {
+    case 4: launch_dlie_triple<4>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;
+    case 8: launch_dlie_triple<8>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;
+    case 12: launch_dlie_triple<12>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;
+    case 16: launch_dlie_triple<16>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;
+    case 20: launch_dlie_triple<20>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;
+    case 24: launch_dlie_triple<24>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;
+    case 28: launch_dlie_triple<28>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;
+    case 32: launch_dlie_triple<32>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;
+    case 36: launch_dlie_triple<36>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------- reverse scan that stores lam_t only
+// lam_{T-1} = g_{T-1};  for t = T-1 .. 1:  lam_out[b,t,:] = lam_t;  lam_{t-1} = F_t^T lam_t + g_{t-1};  g_y0 = lam_0.
+constexpr int kLamThreads = 512;
+
+template <int NS>
+__global__ void __launch_bounds__(kLamThreads, 1) scan_bwd_tma_lam_kernel(const float* __restrict__ F,
+                                                                           const float* __restrict__ g_ys,
+                                                                           float* __restrict__ lam_out,
+                                                                           float* __restrict__ g_y0, int T, int H, int bs) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int N = H * bs;
+  const unsigned step_bytes = (unsigned)N * 4;
+  float* tiles = reinterpret_cast<float*>(smraw);  // [NS][N]
+  float* lamb = tiles + (size_t)NS * N;            // [2][H]
+  float* red = lamb + 2 * H;                       // [RQ][H]
+  const int RQ = kLamThreads / H;                  // row groups (H <= 512, H | 512)
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(red + (size_t)RQ * H);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* Fb = F + (size_t)b * T * N;
+  const float* gb = g_ys + (size_t)b * T * H;
+  float* lo = lam_out + (size_t)b * T * H;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+    fence_mbar_init();
+  }
+  for (int h = tid; h < H; h += kLamThreads) lamb[h] = gb[(size_t)(T - 1) * H + h];
+  __syncthreads();
+  if (tid == 0) {
+    for (int u = 0; u < NS - 1 && T - 1 - u >= 1; ++u) {
+      mbar_expect_tx(bars + (u % NS), step_bytes);
+      tma_load_1d(tiles + (size_t)(u % NS) * N, Fb + (size_t)(T - 1 - u) * N, step_bytes, bars + (u % NS));
+    }
+  }
+  const int h = tid % H, rq = tid / H;
+  const int blk = h / bs, jj = h - blk * bs;
+  int cur = 0;
+  for (int t = T - 1; t >= 1; --t) {
+    const int it = T - 1 - t, s = it % NS;
+    if (tid == 0) {
+      const int tn = t - (NS - 1);
+      if (tn >= 1) {
+        // the stage being refilled was last read (generic proxy) before the barrier that closed the previous step
+        const int sn = (it + NS - 1) % NS;
+        fence_async_proxy();
+        mbar_expect_tx(bars + sn, step_bytes);
+        tma_load_1d(tiles + (size_t)sn * N, Fb + (size_t)tn * N, step_bytes, bars + sn);
+      }
+    }
+    const float g_prev = tid < H ? gb[(size_t)(t - 1) * H + tid] : 0.f;
+    const float* lam = lamb + cur * H;
+    if (tid < H) lo[(size_t)t * H + tid] = lam[tid];
+    mbar_wait(bars + s, (unsigned)((it / NS) & 1));
+    const float* col = tiles + (size_t)s * N + (size_t)blk * bs * bs + jj;
+    const float* lv = lam + blk * bs;
+    float acc = 0.f;
+    for (int i = rq; i < bs; i += RQ) acc = fmaf(col[(size_t)i * bs], lv[i], acc);
+    red[rq * H + h] = acc;
+    __syncthreads();
+    if (tid < H) {
+      float sum = g_prev;
+      for (int q = 0; q < RQ; ++q) sum += red[q * H + tid];
+      lamb[(cur ^ 1) * H + tid] = sum;
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  for (int hh = tid; hh < H; hh += kLamThreads) g_y0[(size_t)b * H + hh] = lamb[cur * H + hh];
+}
+
+// false if the shape is outside what the kernel handles (same conditions as scan_tma_dispatch in linear_scan.cu)
+static inline bool scan_bwd_lam_dispatch(cudaStream_t cs, const float* F, const float* g_ys, float* lam_out, float* g_y0,
+                                         int B, int T, int H, int bs) {
+  if (bs % 4 != 0 || H > kLamThreads || kLamThreads % H != 0 || H % 4 != 0) return false;
+  const size_t step_bytes = (size_t)H * bs * 4;
+  if (step_bytes % 16 != 0) return false;
+  const size_t extra = (size_t)(2 * H + (kLamThreads / H) * H) * 4 + 64;
+  int ns = 0;
+  for (int cand = 4; cand >= 2; --cand)
+    if (cand * step_bytes + extra <= 220 * 1024) { ns = cand; break; }
+  if (ns == 0) return false;
+  const size_t smem = ns * step_bytes + extra;
+  if (ns == 4) {
+    cudaFuncSetAttribute(scan_bwd_tma_lam_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_bwd_tma_lam_kernel<4><<<B, kLamThreads, smem, cs>>>(F, g_ys, lam_out, g_y0, T, H, bs);
+  } else if (ns == 3) {
+    cudaFuncSetAttribute(scan_bwd_tma_lam_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_bwd_tma_lam_kernel<3><<<B, kLamThreads, smem, cs>>>(F, g_ys, lam_out, g_y0, T, H, bs);
+  } else {
+    cudaFuncSetAttribute(scan_bwd_tma_lam_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_bwd_tma_lam_kernel<2><<<B, kLamThreads, smem, cs>>>(F, g_ys, lam_out, g_y0, T, H, bs);
+  }
+  return true;
+}
+
+}  // namespace lncde

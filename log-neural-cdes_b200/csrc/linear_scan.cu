@@ -18,8 +18,10 @@
 #include <cstdint>
 
 #include "lncde_b200.h"
+#include "linear_de.cuh"
 #include "outer_gemm.cuh"
 #include "ptx.cuh"
+#include "tuning.h"
 
 namespace lncde {
 
@@ -539,6 +541,9 @@ constexpr int kScanKsplit = 64;
 
 static size_t flows_floats(int B, int T, int nb, int bs) { return (size_t)B * T * nb * bs * bs; }
 
+// "k2_de_v2" applies to big blocks only (the warp-shuffle scans of bs | 32 keep their kernels)
+static bool de_v2_shape(int bs, int n_basis) { return bs >= 64 && bs % 4 == 0 && ((n_basis + 3) & ~3) <= 36; }
+
 }  // namespace lncde
 
 extern "C" {
@@ -547,8 +552,9 @@ size_t lncde_linear_scan_workspace_bytes(int B, int T, int nb, int bs, int n_bas
   using namespace lncde;
   if (B < 1 || T < 1 || nb < 1 || bs < 1 || n_basis < 1) return 0;
   const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
-  const size_t part = (size_t)nb * bs * bs * n_basis * kScanKsplit;
-  return (flows + part) * 4;
+  const size_t part = ((size_t)nb * bs * bs * n_basis * kScanKsplit + 3) & ~(size_t)3;
+  const size_t lam = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;  // lam_t of the "k2_de_v2" reverse sweep
+  return (flows + part + lam) * 4;
 }
 
 static int check_scan_args(int B, int T, int D, int nb, int bs, int n_basis) {
@@ -572,9 +578,14 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   const int H = nb * bs, N = H * bs;
   const long long Mtot = (long long)B * T;
   // 1. flows
-  const int tm = 4, tn = round_tile(N) > 4 ? 4 : round_tile(N);
-  dim3 grid((N + 16 * tn - 1) / (16 * tn), (unsigned)((Mtot + 16 * tm - 1) / (16 * tm)));
-  launch_build_tn<4>(tn, grid, cs, lie, logsig, F, Mtot, N, D, n_basis, bs);
+  if (tuning_value(kTuneK2DeV2) && de_v2_shape(bs, n_basis)) {
+    dim3 grid((N + 127) / 128, (unsigned)((Mtot + 127) / 128));
+    flow_build8_kernel<<<grid, 256, 0, cs>>>(lie, logsig, F, Mtot, N, D, n_basis, bs);
+  } else {
+    const int tm = 4, tn = round_tile(N) > 4 ? 4 : round_tile(N);
+    dim3 grid((N + 16 * tn - 1) / (16 * tn), (unsigned)((Mtot + 16 * tm - 1) / (16 * tm)));
+    launch_build_tn<4>(tn, grid, cs, lie, logsig, F, Mtot, N, D, n_basis, bs);
+  }
   st = (int)cudaGetLastError();
   if (st != 0) return st;
   // 2. scan
@@ -603,6 +614,22 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
   cudaStream_t cs = (cudaStream_t)stream;
   float* F = (float*)workspace;  // still holds the forward flows of the SAME (lie, logsig)
   const int H = nb * bs, N = H * bs;
+  if (tuning_value(kTuneK2DeV2) && de_v2_shape(bs, n_basis) && T >= 2) {
+    // reverse sweep stores lam_t only; dLie = sum lam_t (x) y_{t-1} (x) logsig_t from the small operands
+    const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
+    const size_t part_n = ((size_t)N * n_basis * kScanKsplit + 3) & ~(size_t)3;
+    float* part = F + flows;
+    float* lam = part + part_n;
+    if (scan_bwd_lam_dispatch(cs, F, g_ys, lam, g_y0, B, T, H, bs)) {
+      st = (int)cudaGetLastError();
+      if (st != 0) return st;
+      if (!dlie_triple_dispatch(cs, lam, ys, logsig, part, B, T, D, H, bs, n_basis, kScanKsplit)) return LNCDE_ERR_UNSUPPORTED;
+      st = (int)cudaGetLastError();
+      if (st != 0) return st;
+      reduce_partials_kernel<<<148 * 2, 256, 0, cs>>>(part, g_lie, N * n_basis, kScanKsplit);
+      return (int)cudaGetLastError();
+    }
+  }
   if (!scan_warp_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs) &&
       !scan_tma_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs)) {
     int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));

@@ -10,6 +10,8 @@ enum TuneKey {
   kTuneK3Fused = 1,  // "k3_fused": specialised Log-NCDE kernels with the 32 x 32 layer phases fused on single warps
   kTuneK2FusedD = 2, // "k2_fused_d": read by the host mirror - diagonal LNCDE through the fused K2d kernels (dlncde.cu)
   kTuneK1GridCap = 3, // "k1_grid_cap": upper bound on the grid of the persistent K1 kernel (0 = machine-sized); experiments, tests
+  kTuneK2DeV2 = 4,   // "k2_de_v2": big-block (DE) LNCDE - 8 x 8 register-tile flow build, reverse scan stores lam_t only and the
+                     //             bracket gradient is a triple product of the small operands (linear_de.cuh)
   kTuneCount
 };
 

@@ -12,7 +12,10 @@ a fault or hang in a variant that has not been on hardware yet cannot take the c
   k2: ``set_tuning("k2_fused_d", 1)`` (fused diagonal LNCDE kernels, dlncde.cu) - loss and gradients against flow
       build + scan, timings of the EigenWorms D-LNCDE train step at B = 32 and B = 2048.
 
-    python scripts/variant_check.py [--no-timing] [--no-parity] [--only k1|k2|k3]
+  k2de: ``set_tuning("k2_de_v2", 1)`` (dense LNCDE: 8 x 8 flow build, lam-only reverse sweep, triple-product bracket
+      gradient, linear_de.cuh) - loss and gradients against the default kernels, timings of the EigenWorms DE step.
+
+    python scripts/variant_check.py [--no-timing] [--no-parity] [--only k1|k2|k3|k2de]
 """
 import json
 import os
@@ -251,11 +254,78 @@ def k2_timing(reps=10):
     return res
 
 
+def _de_step(B, n_windows, seed=0):
+    """EigenWorms DE-LNCDE config (dense_linear_ncde, depth 2, H = 128, one 128 x 128 block): loss + flat gradient."""
+    from lncde import train as T
+    from lncde.data_dir.generate_paths import calc_paths, logsig_dim
+    from lncde.models.generate_model import create_model
+
+    C, s, H = 7, 12, 128
+    L = n_windows * s - 1
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(B, L, C, device="cuda", generator=g) * 0.05).cumsum(1)
+    x = 2 * (x - x.amin((0, 1))) / (x.amax((0, 1)) - x.amin((0, 1))) - 1
+    model, _ = create_model("dense_linear_ncde", C, logsig_dim(C, 2), 2, None, 5, H, block_size=H, lambd=1e-3, key=2345,
+                            device=torch.device("cuda"))
+    ts = torch.zeros(B, L)
+    y = torch.eye(5, device="cuda")[torch.arange(B, device="cuda") % 5]
+    ls = calc_paths(x, s, 2)
+
+    def step():
+        return T.classification_loss(model, (ts, ls, x[:, 0, :]), y)
+
+    return model, step
+
+
+def k2de_parity():
+    from lncde import _lib
+
+    res = {"cases": 0, "max_rel_diff_grad": 0.0, "max_rel_diff_loss": 0.0}
+    for B, nwin in ((3, 40), (8, 1499), (5, 130)):
+        model, step = _de_step(B, nwin, seed=B)
+        _lib.set_tuning("k2_de_v2", 0)
+        l0, g0 = step()
+        _lib.set_tuning("k2_de_v2", 1)
+        l1, g1 = step()
+        _lib.set_tuning("k2_de_v2", 0)
+        torch.cuda.synchronize()
+        res["cases"] += 1
+        res["max_rel_diff_loss"] = max(res["max_rel_diff_loss"], abs(float(l1) - float(l0)) / max(abs(float(l0)), 1e-30))
+        res["max_rel_diff_grad"] = max(res["max_rel_diff_grad"],
+                                       float((g1 - g0).abs().max() / g0.abs().max().clamp_min(1e-30)))
+        del model, step
+        torch.cuda.empty_cache()
+    res["ok"] = bool(res["max_rel_diff_loss"] < 1e-5 and res["max_rel_diff_grad"] < 5e-5)
+    return res
+
+
+def k2de_timing(reps=5):
+    from lncde import _lib
+
+    res = {"shape": "EigenWorms DE-LNCDE train step (loss + gradient), eager launches, B=32 (flows 3.1 GB)"}
+    model, step = _de_step(32, 1499)
+    for name, v in (("default", 0), ("v2", 1)):
+        _lib.set_tuning("k2_de_v2", v)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = {"ms": e0.elapsed_time(e1) / reps}
+    _lib.set_tuning("k2_de_v2", 0)
+    return res
+
+
 if __name__ == "__main__":
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     skip = sys.argv[sys.argv.index("--skip") + 1].split(",") if "--skip" in sys.argv else []
     out = {}
-    for name, par, tim in (("k1", parity, timing), ("k3", k3_parity, k3_timing), ("k2", k2_parity, k2_timing)):
+    for name, par, tim in (("k1", parity, timing), ("k3", k3_parity, k3_timing), ("k2", k2_parity, k2_timing),
+                           ("k2de", k2de_parity, k2de_timing)):
         if only not in (None, name) or name in skip:
             continue
         out[name] = {}

@@ -261,6 +261,39 @@ def test_emu_linear_scan_forward_and_adjoint(nb, bs, T, n_basis):
     assert rel_err(gl_e, lie_t.grad.numpy()) < 5 * TOL
 
 
+@pytest.mark.parametrize("nb,bs,T,n_basis,B", [(1, 64, 9, 6, 2), (1, 128, 7, 28, 2), (2, 64, 5, 21, 3), (1, 64, 2, 3, 1),
+                                               (1, 68, 6, 10, 2), (1, 128, 40, 36, 1)])
+def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B):
+    """tuning "k2_de_v2" (linear_de.cuh): 8 x 8 flow build, lam-only reverse sweep, triple-product bracket gradient.
+    ys and g_y0 are bit-identical to the default kernels (same sums in the same order); g_lie to rounding."""
+    rng = np.random.default_rng(11)
+    H, D = nb * bs, n_basis + 2  # one unused trailing logsig column
+    lie = rng.normal(size=(nb, bs, bs, n_basis)) * (0.5 / np.sqrt(bs))
+    ls = rng.normal(size=(B, T, D)) * 0.2
+    ls[..., 0] = 0
+    y0 = rng.normal(size=(B, H))
+    g_ys = rng.normal(size=(B, T, H))
+    ys0, gl0, gy0 = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
+    E.set_tuning("k2_de_v2", 1)
+    try:
+        ys1, gl1, gy1 = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
+    finally:
+        E.set_tuning("k2_de_v2", 0)
+    assert np.array_equal(ys0, ys1)
+    assert np.array_equal(gy0, gy1)
+    assert rel_err(gl1, gl0) < 1e-5
+    # and against fp64 autograd
+    lie_t = torch.from_numpy(lie).requires_grad_(True)
+    flows = torch.einsum("nijl,btl->btnij", lie_t, torch.from_numpy(ls[..., 1:1 + n_basis])) + torch.eye(bs, dtype=torch.float64)
+    y = torch.from_numpy(y0)
+    out = [y]
+    for t in range(1, T):
+        y = torch.einsum("bnij,bnj->bni", flows[:, t], y.view(B, nb, bs)).reshape(B, H)
+        out.append(y)
+    (torch.stack(out, 1) * torch.from_numpy(g_ys)).sum().backward()
+    assert rel_err(gl1, lie_t.grad.numpy()) < 5 * TOL
+
+
 # ------------------------------------------------------------------------------------------ K2d
 @pytest.mark.parametrize("B,T,H,C,D", [(2, 40, 16, 3, 4), (3, 131, 128, 7, 29), (1, 2, 5, 1, 2), (2, 1, 8, 2, 4),
                                        (2, 65, 200, 8, 37), (1, 64, 130, 6, 22), (2, 129, 7, 4, 11)])

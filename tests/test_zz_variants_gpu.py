@@ -41,3 +41,8 @@ def test_k3_fused_variant_parity(built_lib):
 @pytest.mark.xfail(strict=False, reason=REASON)
 def test_k2_fused_diagonal_variant_parity(built_lib):
     _check("k2")
+
+
+@pytest.mark.xfail(strict=False, reason=REASON)
+def test_k2_dense_v2_variant_parity(built_lib):
+    _check("k2de")
