@@ -40,6 +40,12 @@ WORKLOADS = {
                                   vf_width=32, vf_depth=2, dt0=0.00066711140760507, scale=1000.0, lambd=1e-3, lr=1e-3,
                                   label_dim=5, classification=True,
                                   desc="EigenWorms Log-NCDE, 6 channels (no time channel), otherwise as the default"),
+    # the reference's own comparison baseline on the same input (experiment_configs/repeats/nrde/EigenWorms.json)
+    "eigenworms_nrde": dict(name="EigenWorms", model="nrde", B=32, L=17984, C=6, stepsize=4, depth=2, H=64, vf_width=64,
+                            vf_depth=3, dt0=0.00022237046920169, scale=1.0, lambd=0.0, lr=1e-3, label_dim=5,
+                            classification=True,
+                            desc="EigenWorms NRDE (reference config): B=32, L=17984, C=6 (no time channel), stepsize 4, "
+                                 "depth 2, H=64, vf 3x64, Heun dt0=1/4497 (4497 steps), CE, Adam"),
     "toy_logncde": dict(name="toy", model="log_ncde", B=32, L=100, C=6, stepsize=4, depth=2, H=64, vf_width=128,
                         vf_depth=3, dt0=0.01, scale=1.0, lambd=0.0, lr=3e-4, label_dim=2, classification=True,
                         desc="toy Log-NCDE depth 2, stepsize 4: B=32, L=100, C=6, H=64, vf 3x128, dt0=0.01 (99 steps)"),

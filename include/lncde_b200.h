@@ -132,6 +132,25 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig,
                       int C, int width, int n_hidden, int depth, int n_steps, void* workspace,
                       size_t workspace_bytes, unsigned flags);
 
+/* ----------------------------------------------------------------- K3n ---
+ * Neural RDE solve (Heun, constant step) and its exact discrete adjoint.
+ * Replaces NeuralRDE.__call__ + func, models/NeuralCDEs.py:227-266 (the reference's comparison
+ * baseline on the same (ts, logsig, x0) input):
+ *   field = reshape(mlp_linear(vf(y)), (H, D-1)) @ logsig[row][1:] * stage_scale
+ *   vf = n_vf linear layers H -> width -> ... -> width, relu between, tanh after the last (NeuralCDEs.py:209-216,
+ *        n_vf = the reference's vf_depth); mlp_linear: width -> H*(D-1) (:217-219).
+ * params: flat fp32 [W0|b0|...|W_{n_vf-1}|b_{n_vf-1}|Wm|bm], eqx layout W[out,in]; 16-byte aligned.
+ * width % 4 == 0, H <= 512, width <= 512, n_vf <= 4.  stage_row / stage_scale / ys / g_ys as for K3.       */
+int lncde_nrde_param_count(int H, int Dm, int width, int n_vf); /* Dm = D - 1; < 0 if unsupported */
+int lncde_nrde_fwd(void* stream, const float* params, const float* logsig, const float* y0,
+                   const int32_t* stage_row, const float* stage_scale, float* ys, int B, int K, int D,
+                   int H, int width, int n_vf, int n_steps);
+size_t lncde_nrde_bwd_workspace_bytes(int B, int H, int Dm, int width, int n_vf, int n_steps);
+int lncde_nrde_bwd(void* stream, const float* params, const float* logsig, const int32_t* stage_row,
+                   const float* stage_scale, const float* ys, const float* g_ys, float* g_params,
+                   float* g_y0, int B, int K, int D, int H, int width, int n_vf, int n_steps,
+                   void* workspace, size_t workspace_bytes);
+
 /* ------------------------------------------------------------------ K2 ---
  * Structured linear CDE (D / BD / DE-LNCDE): flows F_k = I + sum_l logsig[k,l] A_l
  * and the recurrence h_k = F_k h_{k-1}, k = 1..T-1 (flow 0 is never applied).

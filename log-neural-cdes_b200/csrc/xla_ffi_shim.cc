@@ -108,4 +108,56 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_logncde_bwd, SolveBwdImpl,
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::U8>>());
+
+// ---- K3n: Neural RDE (NeuralCDEs.py:227-266).  params = [vf layers | mlp_linear]; attrs: width, n_vf.
+static ffi::Error NrdeFwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params, ffi::Buffer<ffi::F32> logsig,
+                              ffi::Buffer<ffi::F32> y0, ffi::Buffer<ffi::S32> rows, ffi::Buffer<ffi::F32> scale,
+                              int32_t width, int32_t n_vf, ffi::ResultBuffer<ffi::F32> ys) {
+  auto l = logsig.dimensions();
+  auto y = y0.dimensions();
+  const int n_steps = (int)rows.dimensions()[0];
+  return status_to_error(
+      lncde_nrde_fwd(stream, params.typed_data(), logsig.typed_data(), y0.typed_data(), rows.typed_data(),
+                     scale.typed_data(), ys->typed_data(), (int)l[0], (int)l[1], (int)l[2], (int)y[1], width, n_vf, n_steps),
+      "lncde_nrde_fwd");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_nrde_fwd, NrdeFwdImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("width")
+                                  .Attr<int32_t>("n_vf")
+                                  .Ret<ffi::Buffer<ffi::F32>>());
+
+static ffi::Error NrdeBwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params, ffi::Buffer<ffi::F32> logsig,
+                              ffi::Buffer<ffi::S32> rows, ffi::Buffer<ffi::F32> scale, ffi::Buffer<ffi::F32> ys,
+                              ffi::Buffer<ffi::F32> g_ys, int32_t width, int32_t n_vf,
+                              ffi::ResultBuffer<ffi::F32> g_params, ffi::ResultBuffer<ffi::F32> g_y0,
+                              ffi::ResultBuffer<ffi::U8> scratch) {
+  auto l = logsig.dimensions();
+  auto y = ys.dimensions();
+  return status_to_error(
+      lncde_nrde_bwd(stream, params.typed_data(), logsig.typed_data(), rows.typed_data(), scale.typed_data(),
+                     ys.typed_data(), g_ys.typed_data(), g_params->typed_data(), g_y0->typed_data(), (int)l[0], (int)l[1],
+                     (int)l[2], (int)y[2], width, n_vf, (int)y[1] - 1, scratch->typed_data(), scratch->size_bytes()),
+      "lncde_nrde_bwd");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_nrde_bwd, NrdeBwdImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("width")
+                                  .Attr<int32_t>("n_vf")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>());
 #endif  // LNCDE_HAVE_XLA_FFI

@@ -45,6 +45,10 @@ def _declare(lib):
         "lncde_dlncde_bwd_workspace_bytes": (sz, [i, i, i]),
         "lncde_dlncde_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i]),
         "lncde_dlncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]),
+        "lncde_nrde_param_count": (i, [i, i, i, i]),
+        "lncde_nrde_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i]),
+        "lncde_nrde_bwd_workspace_bytes": (sz, [i, i, i, i, i, i]),
+        "lncde_nrde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, sz]),
         "lncde_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, i, f]),
         "lncde_adam_step_dev": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, vp, f]),
     }
@@ -103,6 +107,13 @@ def require_cuda(*tensors):
             raise LncdeError("lncde operators take CUDA tensors; got a CPU tensor (no CPU fallback)")
         if not t.is_contiguous():
             raise LncdeError("lncde operators take contiguous tensors")
+
+
+def require_cuda_device(*tensors):
+    """Like require_cuda without the contiguity requirement (inputs of host-side torch ops, e.g. x0 = data[:, 0, :])."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise LncdeError("lncde operators take CUDA tensors; got a CPU tensor (no CPU fallback)")
 
 
 def stream_ptr():

@@ -200,8 +200,7 @@ class LogNeuralCDE:
     def hidden_states(self, X):
         ts, logsig, x0 = X
         _lib.require_cuda(logsig)
-        if not x0.is_cuda:
-            raise _lib.LncdeError("x0 must be a CUDA tensor (no CPU fallback)")
+        _lib.require_cuda_device(x0)
         rows, scale, interp = self._stage_table(ts, logsig.shape[1])
         y0 = self.linear1(x0)
         dims = (self.hidden_dim, self.data_dim, self.vf_width, self.vf_depth, self.depth)

@@ -1,5 +1,6 @@
 """``create_model`` – mirror of models/generate_model.py:53-229 for the models on the
-Log-ODE hot path (``log_ncde`` :86-109 and ``*_linear_ncde`` :110-129).  Same
+Log-ODE hot path (``log_ncde`` :86-109 and ``*_linear_ncde`` :110-129) and the ``nrde`` comparison model on the
+same input (:151-172).  Same
 signature, defaults and error behaviour; ``solver`` / ``stepsize_controller`` are
 accepted for signature compatibility – the kernels implement Heun with a constant
 step (the reference defaults, run_experiment.py:196-197)."""
@@ -28,6 +29,13 @@ def create_model(model_name, data_dim, logsig_dim, logsig_depth, intervals, labe
                              walsh_hadamard=walsh_hadamard, diagonal_dense=diagonal_dense, sparsity=sparsity, rank=rank,
                              key=key, device=device),
                 None)
-    if model_name in ("ncde", "nrde", "lru", "S5", "rnn_linear", "rnn_gru", "rnn_lstm", "rnn_mlp"):
+    if model_name == "nrde":
+        if vf_width is None or vf_depth is None:
+            raise ValueError("Must specify vf_width and vf_depth for a NRDE.")
+        from .NeuralCDEs import NeuralRDE
+
+        return (NeuralRDE(vf_width, vf_depth, hidden_dim, data_dim, logsig_dim, label_dim, classification, output_step,
+                          intervals, solver, stepsize_controller, dt0, max_steps, scale, key=key, device=device), None)
+    if model_name in ("ncde", "lru", "S5", "rnn_linear", "rnn_gru", "rnn_lstm", "rnn_mlp"):
         raise NotImplementedError(f"{model_name} is a comparison baseline outside the Log-ODE hot path (SURVEY.md §2)")
     raise ValueError(f"Unknown model name: {model_name}")

@@ -41,6 +41,11 @@ def lib():
         _lib.lncde_dlncde_bwd_workspace_bytes.restype = sz
         _lib.lncde_dlncde_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i]
         _lib.lncde_dlncde_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]
+        _lib.lncde_nrde_param_count.argtypes = [i, i, i, i]
+        _lib.lncde_nrde_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i]
+        _lib.lncde_nrde_bwd_workspace_bytes.argtypes = [i, i, i, i, i, i]
+        _lib.lncde_nrde_bwd_workspace_bytes.restype = sz
+        _lib.lncde_nrde_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, sz]
         _lib.emu_bulk_copies.restype = C.c_long
         _lib.emu_guarded_alloc.restype = C.c_void_p
         _lib.emu_guarded_alloc.argtypes = [C.c_size_t, C.c_int, C.c_int]
@@ -154,6 +159,41 @@ def logncde_bwd_recompute(flat, logsig, ys, rows, scale, dims, g_ys):
                              _p(g_y0), B, K, D, H, Cn, width, n_hidden, depth, n_steps, _p(ws), nbytes, 0)
     assert st == 0, st
     return g_params, g_y0
+
+
+def nrde_fwd_bwd(flat, logsig, y0, rows, scale, dims, g_ys=None):
+    """lncde_nrde_fwd (+ bwd).  dims = (H, width, n_vf); parameter, output and gradient buffers end at guard pages."""
+    L = lib()
+    H, width, n_vf = dims
+    logsig, scale = f32(logsig), f32(scale)
+    rows = np.ascontiguousarray(rows, np.int32)
+    B, K, D = logsig.shape
+    n_steps = rows.shape[0]
+    assert L.lncde_nrde_param_count(H, D - 1, width, n_vf) == np.asarray(flat).size
+    fl = guarded(np.asarray(flat).shape)
+    fl[...] = flat
+    y0g = guarded((B, H))
+    y0g[...] = y0
+    ys = guarded((B, n_steps + 1, H))
+    ys[...] = np.nan
+    st = L.lncde_nrde_fwd(None, _p(fl), _p(logsig), _p(y0g), _p(rows), _p(scale), _p(ys), B, K, D, H, width, n_vf, n_steps)
+    assert st == 0, st
+    if g_ys is None:
+        return ys.copy(), None, None
+    gy = guarded((B, n_steps + 1, H))
+    gy[...] = g_ys
+    nbytes = L.lncde_nrde_bwd_workspace_bytes(B, H, D - 1, width, n_vf, n_steps)
+    assert nbytes > 0
+    ws = guarded((nbytes,), np.uint8)
+    ws[...] = 0xFF  # NaN pattern: anything read before it is written shows up
+    g_params = guarded(fl.shape)
+    g_params[...] = np.nan
+    g_y0 = guarded((B, H))
+    g_y0[...] = np.nan
+    st = L.lncde_nrde_bwd(None, _p(fl), _p(logsig), _p(rows), _p(scale), _p(ys), _p(gy), _p(g_params), _p(g_y0), B, K, D, H,
+                          width, n_vf, n_steps, _p(ws), nbytes)
+    assert st == 0, st
+    return ys.copy(), g_params.copy(), g_y0.copy()
 
 
 def linear_scan(lie, logsig, y0, nb, bs, g_ys=None):

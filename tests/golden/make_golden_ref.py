@@ -6,7 +6,7 @@ see refshim/README.md for what this pins and what it cannot).
 
 Files executed unmodified: data_dir/generate_paths.py (calc_paths), data_dir/datasets.py (batch_calc_paths),
 data_dir/hall_set.py, models/generate_model.py (create_model), models/LogNeuralCDEs.py, models/NeuralCDEs.py
-(VectorField), models/LinearNeuralCDEs.py, train.py (calc_output, classification_loss, regression_loss).
+(VectorField, NeuralRDE), models/LinearNeuralCDEs.py, train.py (calc_output, classification_loss, regression_loss).
 All arithmetic is float64 except what the reference keeps in float32 by construction (time grids).
 """
 import os
@@ -133,6 +133,57 @@ def logncde_cases():
     out["n"] = np.array(len(cases))
     np.savez_compressed(os.path.join(HERE, "ref_logncde.npz"), **out)
     print("ref_logncde.npz:", len(cases), "cases")
+
+
+def nrde_cases():
+    """create_model("nrde") -> NeuralRDE (models/NeuralCDEs.py:168-266) run unmodified: predictions, the reference's
+    own losses and their gradients w.r.t. every parameter leaf."""
+    rng = np.random.default_rng(17)
+    out = {}
+    #        B, L,  C, s, depth, H, width, n_vf, dt0, scale, classification, output_step, label_dim
+    cases = [(3, 40, 3, 4, 2, 16, 8, 2, 0.05, 1.0, True, 1, 3),
+             (2, 40, 3, 4, 1, 12, 8, 1, 0.05, 1.0, True, 1, 2),
+             (2, 64, 3, 4, 2, 16, 8, 3, 0.04, 2.0, False, 8, 1),
+             (2, 48, 6, 4, 2, 64, 32, 3, 0.07, 1.0, True, 1, 5),
+             (1, 30, 7, 6, 2, 128, 16, 4, 0.15, 1.5, True, 1, 5)]
+    for i, (B, L, C, s, depth, H, width, nvf, dt0, scale, cls, ostep, ld) in enumerate(cases):
+        x = np.cumsum(rng.normal(scale=0.3, size=(B, L, C)), axis=1)
+        ts = make_ts(L)
+        iv = make_intervals(ts, s)
+        logsig = ref_calc_paths(T(x), s, depth)
+        model, state = ref_create_model("nrde", C, logsig.shape[-1], depth, T(iv, torch.float32), ld, H,
+                                        vf_depth=nvf, vf_width=width, classification=cls, output_step=ostep,
+                                        solver=diffrax.Heun(), stepsize_controller=diffrax.ConstantStepSize(), dt0=dt0,
+                                        scale=scale, key=300 + i)
+        assert state is None and len(model.vf.mlp.layers) == nvf and model.logsig_dim == logsig.shape[-1] - 1
+        lin = list(model.vf.mlp.layers) + [model.mlp_linear, model.linear1, model.linear2]
+        leaves = [t for l in lin for t in (l.weight, l.bias)]
+        for t in leaves:
+            t.data = t.data.float().double()  # fp32-representable parameters: the fixture stores them losslessly as fp32
+            t.requires_grad_(True)
+        X = (T(np.tile(ts, (B, 1)), torch.float32), logsig, T(x[:, 0, :]))
+        pred, _ = ref_train.calc_output(model, X, None, None, model.stateful, model.nondeterministic)
+        pred = pred.detach()
+        if cls:
+            y = np.eye(ld)[rng.integers(0, ld, size=B)]
+            (loss, _), _ = ref_train.classification_loss(model, None, X, T(y), None, None)
+        else:
+            y = rng.normal(size=(B, pred.shape[1]))
+            (loss, _), _ = ref_train.regression_loss(model, None, X, T(y), None, None)
+        grads = torch.autograd.grad(loss, leaves)
+        out[f"grad{i}"] = np.concatenate([g.numpy().ravel() for g in grads]).astype(np.float32)
+        loss = loss.detach()
+        for t in leaves:
+            t.requires_grad_(False)
+        out[f"cfg{i}"] = np.array([B, L, C, s, depth, H, width, nvf, int(cls), ostep, ld])
+        out[f"hyper{i}"] = np.array([dt0, scale])
+        out[f"x{i}"], out[f"logsig{i}"], out[f"y{i}"] = x, logsig.numpy(), y
+        # flat parameters in the order [vf layers | mlp_linear | linear1 | linear2], each W then b
+        out[f"params{i}"] = np.concatenate([t.detach().numpy().ravel() for t in leaves]).astype(np.float32)
+        out[f"pred{i}"], out[f"loss{i}"] = pred.numpy(), np.array(float(loss))
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "ref_nrde.npz"), **out)
+    print("ref_nrde.npz:", len(cases), "cases")
 
 
 def linear_cases():
@@ -304,8 +355,7 @@ def data_cases():
 
 if __name__ == "__main__":
     sys.path.insert(0, HERE)
-    data_cases()
-    paths_cases()
-    logncde_cases()
-    linear_cases()
-    slice_cases()
+    makers = {"data": data_cases, "paths": paths_cases, "logncde": logncde_cases, "nrde": nrde_cases,
+              "linear": linear_cases, "slice": slice_cases}
+    for name in (sys.argv[1:] or list(makers)):  # e.g. `make_golden_ref.py nrde` regenerates one fixture file
+        makers[name]()

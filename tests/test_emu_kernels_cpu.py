@@ -235,6 +235,49 @@ def test_emu_logncde_fused_level2_variant(case):
         assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
 
 
+# ------------------------------------------------------------------------------------------ K3n (NRDE)
+NRDE_CASES = [
+    # B, L,  C, s, depth, H, width, n_vf, dt0, scale
+    (2, 40, 3, 4, 2, 16, 8, 2, 0.05, 1.0),
+    (2, 40, 3, 4, 1, 12, 8, 1, 0.05, 1.0),     # single vf layer, H not a multiple of 4 rows per warp group
+    (1, 36, 5, 3, 2, 22, 12, 3, 0.031, 2.0),   # H % 4 != 0
+    (1, 48, 6, 4, 2, 64, 64, 3, 0.07, 1.0),    # EigenWorms NRDE config dims (Dm = 21): Wm fully resident
+    (1, 30, 7, 6, 2, 128, 64, 4, 0.15, 1.5),   # Wm (917 KB) mostly streamed from global memory
+    (1, 24, 3, 4, 3, 32, 16, 2, 0.1, 1.0),     # depth-3 rows (Dm = 13)
+]
+
+
+@pytest.mark.parametrize("case", NRDE_CASES)
+def test_emu_nrde_forward_and_adjoint(case):
+    from oracle import nrde as ON
+
+    B, L, C, s, depth, H, width, n_vf, dt0, scale = case
+    rng = np.random.default_rng(5)
+    x = np.cumsum(rng.normal(scale=0.3, size=(B, L, C)), axis=1).astype(np.float32)
+    logsig = paths.calc_paths(x, s, depth, np.float64)
+    ts = paths.make_ts(L)
+    rows, sc, grid = O.stage_table(ts, paths.make_intervals(ts, s), dt0, logsig.shape[1])
+    Dm = logsig.shape[2] - 1
+    layers = ON.init_params(H, Dm, width, n_vf, scale=scale, seed=3, dtype=torch.float64)
+    y0 = torch.from_numpy(rng.normal(size=(B, H)) * 0.5)
+    g_ys = torch.from_numpy(rng.normal(size=(B, len(grid), H)))
+    lay = [(W.clone().requires_grad_(True), b.clone().requires_grad_(True)) for W, b in layers]
+    y0o = y0.clone().requires_grad_(True)
+    ys_o = ON.solve(lay, torch.from_numpy(logsig), y0o, rows, sc, H)
+    (ys_o * g_ys).sum().backward()
+    flat = ON.flatten_params(layers).numpy()
+    ys_e, gp_e, gy_e = E.nrde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, (H, width, n_vf), g_ys.numpy())
+    assert rel_err(ys_e, ys_o.detach().numpy()) < TOL
+    assert rel_err(gy_e, y0o.grad.numpy()) < 5 * TOL
+    off = 0
+    for (W, b) in lay:
+        for t in (W, b):
+            n = t.numel()
+            assert rel_err(gp_e[off : off + n], t.grad.reshape(-1).numpy()) < 5 * TOL, (case, off)
+            off += n
+    assert off == gp_e.size
+
+
 # ------------------------------------------------------------------------------------------ K2
 @pytest.mark.parametrize("nb,bs,T,n_basis", [(16, 1, 40, 3), (8, 4, 33, 6), (4, 8, 20, 6), (2, 32, 12, 3),
                                              (1, 64, 9, 6), (3, 5, 14, 3)])
@@ -331,6 +374,7 @@ from conftest import GOLDEN  # noqa: E402
 _P = np.load(os.path.join(GOLDEN, "ref_paths.npz"))
 _N = np.load(os.path.join(GOLDEN, "ref_logncde.npz"))
 _LN = np.load(os.path.join(GOLDEN, "ref_linear.npz"))
+_NR = np.load(os.path.join(GOLDEN, "ref_nrde.npz"))
 
 
 @pytest.mark.parametrize("tma", [False, True, 2])
@@ -366,6 +410,43 @@ def test_emu_logncde_vs_reference_code(i, fused):
         out = torch.cat([O.interp_outputs(ys, grid, O.regression_times(L, ostep)), ys[:, -1:]], 1)
         pred = torch.tanh(out @ torch.from_numpy(W2).T + torch.from_numpy(b2))
     assert rel_err(pred.numpy(), _N[f"pred{i}"]) < TOL
+
+
+@pytest.mark.parametrize("i", range(int(_NR["n"])))
+def test_emu_nrde_vs_reference_code(i):
+    """K3n kernels against predictions and parameter gradients of the reference's own NeuralRDE / loss code."""
+    from oracle import nrde as ON
+
+    B, L, C, s, depth, H, width, nvf, cls, ostep, ld = (int(v) for v in _NR[f"cfg{i}"])
+    dt0 = float(_NR[f"hyper{i}"][0])
+    logsig = _NR[f"logsig{i}"]
+    Dm = logsig.shape[2] - 1
+    flat = _NR[f"params{i}"].astype(np.float64)
+    n_field = sum(o * (a + 1) for a, o in ON.layer_sizes(H, Dm, width, nvf))
+    rest = torch.from_numpy(flat[n_field:])
+    W1, b1, W2, b2 = (t.clone().requires_grad_(True) for t in
+                      (rest[: H * C].view(H, C), rest[H * C : H * C + H], rest[H * C + H : H * C + H + ld * H].view(ld, H),
+                       rest[H * C + H + ld * H :]))
+    ts = paths.make_ts(L)
+    rows, sc, grid = O.stage_table(ts, paths.make_intervals(ts, s), dt0, logsig.shape[1])
+    y0 = torch.from_numpy(_NR[f"x{i}"][:, 0]) @ W1.T + b1
+    ys_np, _, _ = E.nrde_fwd_bwd(flat[:n_field], logsig, y0.detach().numpy(), rows, sc, (H, width, nvf))
+    ys = torch.from_numpy(ys_np).double().requires_grad_(True)
+    y = torch.from_numpy(_NR[f"y{i}"])
+    if cls:
+        pred = torch.softmax(ys[:, -1] @ W2.T + b2, -1)
+        loss = O.classification_loss(pred, y)
+    else:
+        out = torch.cat([O.interp_outputs(ys, grid, O.regression_times(L, ostep)), ys[:, -1:]], 1)
+        pred = torch.tanh(out @ W2.T + b2)
+        loss = O.regression_loss(pred, y)
+    assert rel_err(pred.detach().numpy(), _NR[f"pred{i}"]) < TOL
+    assert abs(float(loss.detach()) - float(_NR[f"loss{i}"])) < TOL * max(1.0, abs(float(_NR[f"loss{i}"])))
+    loss.backward()  # read-out in host autograd, as the product does; the solve's cotangent goes through the kernels
+    _, gp, gy0 = E.nrde_fwd_bwd(flat[:n_field], logsig, y0.detach().numpy(), rows, sc, (H, width, nvf), ys.grad.numpy())
+    assert rel_err(gp, _NR[f"grad{i}"][:n_field]) < 5 * TOL
+    gW1 = gy0.astype(np.float64).T @ _NR[f"x{i}"][:, 0]
+    assert rel_err(gW1.ravel(), _NR[f"grad{i}"][n_field : n_field + H * C]) < 5 * TOL
 
 
 @pytest.mark.parametrize("i", range(int(_LN["n"])))

@@ -113,12 +113,18 @@ def test_bench_autotune_decision():
     assert bench.decide_tuning(rep) == {"k1_tma": 0, "k3_fused": 1}       # level 2 failed its check: fall back to level 1
     assert bench.decide_tuning({"k1": {"error": "x"}, "k3": {"parity": k3ok}}) == {"k1_tma": 0, "k3_fused": 0}
     assert bench.decide_tuning({}) == {"k1_tma": 0, "k3_fused": 0}
+    # K2 workloads: one variant per family, same rule
+    de = {"k2de": {"parity": ok, "timing": t(default=10.9, v2=8.0)}}
+    assert bench.decide_tuning(de)["k2_de_v2"] == 1
+    de["k2de"]["parity"] = bad
+    assert bench.decide_tuning(de)["k2_de_v2"] == 0
+    assert bench.decide_tuning({"k2": {"parity": ok, "timing": t(default_B32=1.0, fused_B32=0.99)}})["k2_fused_d"] == 0
 
 
 def test_tuning_api_roundtrip(built_lib):
     from lncde import _lib
 
-    for key in ("k1_tma", "k3_fused"):
+    for key in ("k1_tma", "k3_fused", "k2_fused_d", "k2_de_v2"):
         old = _lib.get_tuning(key)
         _lib.set_tuning(key, 2)
         assert _lib.get_tuning(key) == 2
@@ -128,3 +134,32 @@ def test_tuning_api_roundtrip(built_lib):
 
     with pytest.raises(_lib.LncdeError):
         _lib.set_tuning("no_such_key", 1)
+
+
+def test_nrde_mirror_layout_and_errors(built_lib):
+    """create_model("nrde"): same errors as generate_model.py:151-153, reference pytree names, parameter count of
+    the C ABI (lncde_nrde_param_count) = [vf | mlp_linear] of the host layout; no CPU fallback."""
+    import numpy as np
+    import torch
+
+    from lncde import _lib
+    from lncde.models.generate_model import create_model
+
+    with pytest.raises(ValueError, match="vf_width and vf_depth for a NRDE"):
+        create_model("nrde", 6, 22, 2, None, 5, 64, key=0, device="cpu")
+    iv = np.linspace(0, 1, 12).astype(np.float32)
+    model, state = create_model("nrde", 6, 22, 2, iv, 5, 64, vf_depth=3, vf_width=64, scale=10.0, key=0, device="cpu")
+    assert state is None and not model.lip2 and not model.stateful and not model.nondeterministic
+    assert model.logsig_dim == 21 and len(model.vf.mlp.layers) == 3
+    assert model.vf.mlp.layers[0].weight.shape == (64, 64) and model.mlp_linear.weight.shape == (64 * 21, 64)
+    assert model.linear1.weight.shape == (64, 6) and model.linear2.weight.shape == (5, 64)
+    assert built_lib.lncde_nrde_param_count(64, 21, 64, 3) == model.n_field
+    assert model.params.numel() == model.n_field + 64 * 7 + 5 * 65
+    # only the vector field is divided by `scale` (NeuralCDEs.py:209-219)
+    assert float(model.vf.mlp.layers[0].weight.detach().abs().max()) <= 1 / 8 / 10 + 1e-6
+    assert float(model.mlp_linear.weight.detach().abs().max()) > 1 / 8 / 2
+    assert built_lib.lncde_nrde_param_count(64, 21, 30, 3) < 0          # width % 4 != 0: outside the compiled range
+    assert built_lib.lncde_nrde_bwd_workspace_bytes(32, 64, 21, 64, 3, 4497) > 0
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.LncdeError):
+            model((torch.zeros(2, 44), torch.zeros(2, 11, 22), torch.zeros(2, 6)))

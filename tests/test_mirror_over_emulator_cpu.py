@@ -1,0 +1,91 @@
+"""The PRODUCT host mirrors (lncde.models.*, lncde.train) executed on the CPU over the host-emulated kernel library
+(tests/emu): same Python code, same ctypes signatures and argument order as on the GPU box, with the three
+device-specific hooks of lncde._lib swapped for the test (library handle, stream, CUDA check).  Test
+infrastructure only - the product has no CPU path.  Results are compared with the reference-executed fixtures."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+TOL = 1e-5
+NR = np.load(os.path.join(GOLDEN, "ref_nrde.npz"))
+N = np.load(os.path.join(GOLDEN, "ref_logncde.npz"))
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    import build_emu
+    from lncde import _lib
+
+    handle = C.CDLL(build_emu.build())
+    _lib._declare(handle)  # the product's own signature table: a symbol or arity mismatch fails here
+    monkeypatch.setattr(_lib, "lib", lambda: handle)
+    monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "require_cuda_device", lambda *a: None)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: C.c_void_p(0))
+    return handle
+
+
+def _ts(L):
+    return (np.float32(1.0 / L) * np.arange(L, dtype=np.float32)).astype(np.float32)
+
+
+def _intervals(ts, s):
+    return np.concatenate([ts[np.arange(0, len(ts), s)], np.array([1.0], np.float32)]).astype(np.float32)
+
+
+@pytest.mark.parametrize("i", range(int(NR["n"])))
+def test_nrde_mirror_vs_reference_code(emulated, i):
+    from lncde import train as T
+    from lncde.models.generate_model import create_model
+
+    B, L, C_, s, depth, H, width, nvf, cls, ostep, ld = (int(v) for v in NR[f"cfg{i}"])
+    dt0, scale = (float(v) for v in NR[f"hyper{i}"])
+    ts = _ts(L)
+    model, state = create_model("nrde", C_, NR[f"logsig{i}"].shape[-1], depth, _intervals(ts, s), ld, H, vf_depth=nvf,
+                                vf_width=width, classification=bool(cls), output_step=ostep, dt0=dt0, scale=scale, key=1,
+                                device="cpu")
+    assert NR[f"params{i}"].size == model.params.numel()
+    with torch.no_grad():
+        model.params.copy_(torch.from_numpy(NR[f"params{i}"]).float())
+    X = (torch.from_numpy(np.tile(ts, (B, 1))), torch.from_numpy(NR[f"logsig{i}"]).float(),
+         torch.from_numpy(NR[f"x{i}"][:, 0, :].copy()).float())
+    pred = model(X)
+    assert rel_err(pred.detach().numpy(), NR[f"pred{i}"]) < TOL
+    y = torch.from_numpy(NR[f"y{i}"]).float()
+    loss, grads = (T.classification_loss if cls else T.regression_loss)(model, X, y)
+    want = float(NR[f"loss{i}"])
+    assert abs(float(loss) - want) < TOL * max(1.0, abs(want))
+    assert rel_err(grads.numpy(), NR[f"grad{i}"]) < 5 * TOL
+
+
+@pytest.mark.parametrize("i", [0, 2, 5])
+def test_log_ncde_mirror_vs_reference_code(emulated, i):
+    """Same check for the hot-path model (the GPU twin is tests/test_reference_golden_gpu.py)."""
+    from lncde import train as T
+    from lncde.models.generate_model import create_model
+
+    B, L, C_, s, depth, H, width, nh, cls, ostep, ld = (int(v) for v in N[f"cfg{i}"])
+    dt0, scale, lambd = (float(v) for v in N[f"hyper{i}"])
+    ts = _ts(L)
+    model, _ = create_model("log_ncde", C_, N[f"logsig{i}"].shape[-1], depth, _intervals(ts, s), ld, H, vf_depth=nh,
+                            vf_width=width, classification=bool(cls), output_step=ostep, dt0=dt0, scale=scale, lambd=lambd,
+                            key=1, device="cpu")
+    flat = np.concatenate([N[f"mlp{i}"], N[f"lin1_{i}"], N[f"lin2_{i}"]])
+    with torch.no_grad():
+        model.params.copy_(torch.from_numpy(flat).float())
+    X = (torch.from_numpy(np.tile(ts, (B, 1))), torch.from_numpy(N[f"logsig{i}"]).float(),
+         torch.from_numpy(N[f"x{i}"][:, 0, :].copy()).float())
+    y = torch.from_numpy(N[f"y{i}"]).float()
+    loss, grads = (T.classification_loss if cls else T.regression_loss)(model, X, y)
+    want = float(N[f"loss{i}"])
+    assert abs(float(loss) - want) < TOL * max(1.0, abs(want))
+    assert rel_err(grads.numpy(), N[f"grad{i}"]) < 5 * TOL
