@@ -89,3 +89,66 @@ def test_log_ncde_mirror_vs_reference_code(emulated, i):
     want = float(N[f"loss{i}"])
     assert abs(float(loss) - want) < TOL * max(1.0, abs(want))
     assert rel_err(grads.numpy(), N[f"grad{i}"]) < 5 * TOL
+
+
+LN = np.load(os.path.join(GOLDEN, "ref_linear.npz"))
+
+
+@pytest.mark.parametrize("fused_d", [0, 1])
+@pytest.mark.parametrize("i", range(int(LN["n"])))
+def test_linear_ncde_mirror_vs_reference_code(emulated, i, fused_d):
+    """LogLinearCDE (D / BD / DE, chunked scanner configs) through the product mirror on the emulated K2 kernels;
+    fused_d = 1 routes the diagonal configs through the K2d kernels (tuning "k2_fused_d")."""
+    from lncde import _lib, train as T
+    from lncde.models.generate_model import create_model
+
+    B, L, C_, s, depth, H, bs, Psteps, cls, ld = (int(v) for v in LN[f"cfg{i}"])
+    if fused_d and bs != 1:
+        pytest.skip("k2_fused_d only changes the diagonal model")
+    model, _ = create_model(str(LN[f"name{i}"]), C_, LN[f"logsig{i}"].shape[-1], depth, None, ld, H, block_size=bs,
+                            classification=bool(cls), lambd=float(LN[f"lambd{i}"]), parallel_steps=Psteps, key=1,
+                            device="cpu")
+    flat = np.concatenate([LN[f"vfA{i}"].ravel(), LN[f"init{i}"], LN[f"out{i}"]])
+    with torch.no_grad():
+        model.params.copy_(torch.from_numpy(flat).float())
+    X = (torch.from_numpy(np.tile(_ts(L), (B, 1))), torch.from_numpy(LN[f"logsig{i}"]).float(),
+         torch.from_numpy(LN[f"x{i}"][:, 0, :].copy()).float())
+    y = torch.from_numpy(LN[f"y{i}"]).float()
+    _lib.set_tuning("k2_fused_d", fused_d)
+    try:
+        loss, grads = (T.classification_loss if cls else T.regression_loss)(model, X, y)
+    finally:
+        _lib.set_tuning("k2_fused_d", 0)
+    want = float(LN[f"loss{i}"])
+    assert abs(float(loss) - want) < TOL * max(1.0, abs(want))
+    assert rel_err(grads.numpy(), LN[f"grad{i}"]) < 5 * TOL
+
+
+def test_make_step_with_emulated_adam_kernel(emulated):
+    """train.make_step end to end (loss, adjoint, fused Adam kernel K4 with its device-side step counter) against
+    the oracle's optax-style update."""
+    from lncde import train as T
+    from lncde.models.generate_model import create_model
+
+    i = 1
+    B, L, C_, s, depth, H, width, nh, cls, ostep, ld = (int(v) for v in N[f"cfg{i}"])
+    dt0, scale, lambd = (float(v) for v in N[f"hyper{i}"])
+    ts = _ts(L)
+    model, _ = create_model("log_ncde", C_, N[f"logsig{i}"].shape[-1], depth, _intervals(ts, s), ld, H, vf_depth=nh,
+                            vf_width=width, classification=True, dt0=dt0, scale=scale, lambd=lambd, key=1, device="cpu")
+    flat = np.concatenate([N[f"mlp{i}"], N[f"lin1_{i}"], N[f"lin2_{i}"]])
+    with torch.no_grad():
+        model.params.copy_(torch.from_numpy(flat).float())
+    X = (torch.from_numpy(np.tile(ts, (B, 1))), torch.from_numpy(N[f"logsig{i}"]).float(),
+         torch.from_numpy(N[f"x{i}"][:, 0, :].copy()).float())
+    y = torch.from_numpy(N[f"y{i}"]).float()
+    opt = T.Adam(model, 1e-2)
+    p0 = model.params.detach().clone().double()
+    _, _, _, value = T.make_step(model, None, X, y, T.classification_loss, None, opt, None, None)
+    assert abs(float(value) - float(N[f"loss{i}"])) < TOL
+    g = torch.from_numpy(N[f"grad{i}"])
+    # first Adam step (optax.adam, bias-corrected): p - lr * g / (|g| + eps)
+    want = p0 - 1e-2 * g / (g.abs() + 1e-8)
+    big = g.abs() > 1e-6  # elements whose update is not dominated by eps / fp32 rounding of g
+    assert rel_err(model.params.detach().double()[big].numpy(), want[big].numpy()) < 1e-4
+    assert int(opt.count) == 1
