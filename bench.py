@@ -198,8 +198,10 @@ def run_ours(args):
     # ---- kernel-variant autotune (rank 0 decides, everybody applies the same choice) -------------------
     tuning, tune_report = {"k1_tma": 0, "k3_fused": 0}, None
     families = {"log_ncde": ("k1", "k3"), "diagonal_linear_ncde": ("k1", "k2"), "dense_linear_ncde": ("k1", "k2de")}
-    if not args.no_autotune and (args.workload == "eigenworms_logncde" or WL["model"] in ("diagonal_linear_ncde",
-                                                                                           "dense_linear_ncde")):
+    generic = WL["model"] == "log_ncde" and (WL["H"], WL["vf_width"], WL["vf_depth"]) != (128, 32, 2)
+    if generic:
+        families["log_ncde"] = ("k1", "k3g")  # shapes outside the specialised kernels: the generic solve kernels
+    if not args.no_autotune and (WL["model"] in families):
         if rank == 0:
             tuning, tune_report = autotune(families[WL["model"]])
         if world > 1:
@@ -421,7 +423,8 @@ def decide_tuning(rep, margin=0.98):
     """A variant is used only if ITS parity check passed and it beat the default by the margin."""
     choice = {"k1_tma": 0, "k3_fused": 0}
     k1, k3 = rep.get("k1", {}), rep.get("k3", {})
-    for fam, key, base, var in (("k2", "k2_fused_d", "default_B32", "fused_B32"), ("k2de", "k2_de_v2", "default", "v2")):
+    for fam, key, base, var in (("k2", "k2_fused_d", "default_B32", "fused_B32"), ("k2de", "k2_de_v2", "default", "v2"),
+                                ("k3g", "k3_stream", "default_ppg", "stream_ppg")):
         r = rep.get(fam)
         if r is None:
             continue

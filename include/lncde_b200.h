@@ -50,8 +50,10 @@ const char* lncde_strerror(int status);
  * of flow build + scan), "k2_de_v2" (lncde_linear_scan_fwd/bwd with block size >= 64: 128 x 128 flow-build tiles with
  * 8 x 8 register tiles; the reverse sweep stores lam_t instead of dF_t and the bracket gradient is the triple product
  * sum lam_t (x) y_{t-1} (x) logsig_t - the flows in the workspace are then left intact by the backward call).
+ * "k3_stream" (lncde_logncde_fwd/bwd, generic kernels - shapes other than H = 128 / width 32 / 2 hidden layers: layers that
+ * do not fit in shared memory are read with prefetching all-lane mat-vecs; forward states bit-identical).
  * Process-wide, thread-safe; initial values come from the environment
- * (LNCDE_TUNE_K1_TMA, LNCDE_TUNE_K3_FUSED, LNCDE_TUNE_K2_FUSED_D, LNCDE_TUNE_K2_DE_V2).  A forward/backward pair must run under the same
+ * (LNCDE_TUNE_K1_TMA, LNCDE_TUNE_K3_FUSED, LNCDE_TUNE_K2_FUSED_D, LNCDE_TUNE_K2_DE_V2, LNCDE_TUNE_K3_STREAM).  A forward/backward pair must run under the same
  * setting only in the sense that each call reads the value once at entry; results are interchangeable. */
 int lncde_set_tuning(const char* key, int value);
 int lncde_get_tuning(const char* key); /* value, or <0 for an unknown key */

@@ -159,7 +159,7 @@ struct FwdParams {
   int save;
 };
 
-template <int C>
+template <int C, bool PF = false>
 __global__ void __launch_bounds__(kSolveThreads, 1) logncde_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(16) float smem[];
   const MlpDesc& d = p.d;
@@ -195,14 +195,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) logncde_fwd_kernel(const Fwd
     const float s1 = p.stage_scale[2 * n], s2 = p.stage_scale[2 * n + 1];
     for (int h = threadIdx.x; h < H; h += kSolveThreads) buf[L.yin + h] = ycur[h];
     __syncthreads();
-    stage_forward<C>(cx, buf, L, ls + (size_t)r1 * p.D);
+    stage_forward<C, PF>(cx, buf, L, ls + (size_t)r1 * p.D);
     for (int h = threadIdx.x; h < H; h += kSolveThreads) {
       const float kk = s1 * G[h];
       k1[h] = kk;
       buf[L.yin + h] = ycur[h] + kk;
     }
     __syncthreads();
-    stage_forward<C>(cx, buf, L, ls + (size_t)r2 * p.D);
+    stage_forward<C, PF>(cx, buf, L, ls + (size_t)r2 * p.D);
     for (int h = threadIdx.x; h < H; h += kSolveThreads) {
       const float yn = ycur[h] + 0.5f * (k1[h] + s2 * G[h]);
       ycur[h] = yn;
@@ -264,7 +264,21 @@ struct RevBufs {
 // Reverse sweep of one stage.  On entry rb.g holds dLoss/dG (already times the stage
 // scale).  On exit rb.yout holds dLoss/d(stage input).  Vector pairs for the weight
 // gradient go to the workspace slot `slot`.
-template <int C>
+// transposed product of layer l: the streamed form when PF and the layer is read from global memory
+template <int NB, bool BLOCKED, bool PF>
+__device__ __forceinline__ void layer_cols(const StageCtx& cx, int l, int nrows, const float* v, int v_stride, float* out,
+                                           int out_stride, float* scratch) {
+  const MlpDesc& d = *cx.d;
+  if constexpr (PF) {
+    if (d.gvec[l]) {
+      matvec_cols_stream<NB, BLOCKED>(cx.wbase[l], nrows, d.in_dim[l], v, v_stride, out, out_stride, scratch);
+      return;
+    }
+  }
+  matvec_cols<NB, BLOCKED>(cx.wbase[l], d.stride[l], nrows, d.in_dim[l], v, v_stride, out, out_stride, scratch);
+}
+
+template <int C, bool PF = false>
 __device__ __noinline__ void stage_reverse(const StageCtx& cx, float* buf, const StageLayout& L,
                                               const RevBufs& rb, const WsLayout& ws, float* wsp, size_t slot) {
   const MlpDesc& d = *cx.d;
@@ -301,7 +315,8 @@ __device__ __noinline__ void stage_reverse(const StageCtx& cx, float* buf, const
   __syncthreads();
   if (tan) {
     // R2: p-bar of the last hidden layer, block j of the last weight matrix
-    matvec_cols<C, true>(cx.wbase[NL], d.stride[NL], H, Wd, buf + L.ul, H, rb.pbar, PW, rb.scratch);
+    if constexpr (PF) layer_cols<C, true, PF>(cx, NL, H, buf + L.ul, H, rb.pbar, PW, rb.scratch);
+    else matvec_cols<C, true>(cx.wbase[NL], d.stride[NL], H, Wd, buf + L.ul, H, rb.pbar, PW, rb.scratch);
     // R3: down the hidden layers
     for (int l = NL - 1; l >= 0; --l) {
       const float* s = buf + L.s + l * Wd;
@@ -320,7 +335,8 @@ __device__ __noinline__ void stage_reverse(const StageCtx& cx, float* buf, const
         rb.sbar[l * Wd + c] = sb;
       }
       __syncthreads();
-      matvec_cols<C, false>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], u, Wd, rb.pbar, PW, rb.scratch);
+      if constexpr (PF) layer_cols<C, false, PF>(cx, l, d.rows[l], u, Wd, rb.pbar, PW, rb.scratch);
+      else matvec_cols<C, false>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], u, Wd, rb.pbar, PW, rb.scratch);
     }
     // R4: rb.pbar now holds w-bar [C][H];  o-bar_i += sum_j Lam_ij w-bar_j
     for (int h = threadIdx.x; h < H; h += kSolveThreads) {
@@ -351,7 +367,8 @@ __device__ __noinline__ void stage_reverse(const StageCtx& cx, float* buf, const
   }
   __syncthreads();
   // R6: a-bar of the last hidden layer
-  matvec_cols<1, false>(cx.wbase[NL], d.stride[NL], d.rows[NL], d.in_dim[NL], rb.obar, 0, rb.abar, 0, rb.scratch);
+  if constexpr (PF) layer_cols<1, false, PF>(cx, NL, d.rows[NL], rb.obar, 0, rb.abar, 0, rb.scratch);
+  else matvec_cols<1, false>(cx.wbase[NL], d.stride[NL], d.rows[NL], d.in_dim[NL], rb.obar, 0, rb.abar, 0, rb.scratch);
   // R7: down the hidden layers
   for (int l = NL - 1; l >= 0; --l) {
     const float* s = buf + L.s + l * Wd;
@@ -369,12 +386,13 @@ __device__ __noinline__ void stage_reverse(const StageCtx& cx, float* buf, const
       rb.bias_acc[l * Wd + c] += zb;
     }
     __syncthreads();
-    matvec_cols<1, false>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], rb.zbar, 0,
-                          l == 0 ? rb.yout : rb.abar, 0, rb.scratch);
+    if constexpr (PF) layer_cols<1, false, PF>(cx, l, d.rows[l], rb.zbar, 0, l == 0 ? rb.yout : rb.abar, 0, rb.scratch);
+    else matvec_cols<1, false>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], rb.zbar, 0,
+                               l == 0 ? rb.yout : rb.abar, 0, rb.scratch);
   }
 }
 
-template <int C>
+template <int C, bool PF = false>
 __global__ void __launch_bounds__(kSolveThreads, 1) logncde_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(16) float smem[];
   const MlpDesc& d = p.d;
@@ -425,14 +443,14 @@ __global__ void __launch_bounds__(kSolveThreads, 1) logncde_bwd_kernel(const Bwd
     // recompute both stages of the step
     for (int h = threadIdx.x; h < H; h += kSolveThreads) bufA[L.yin + h] = ys[(size_t)n * H + h];
     __syncthreads();
-    stage_forward<C>(cx, bufA, L, ls + (size_t)r1 * p.D);
+    stage_forward<C, PF>(cx, bufA, L, ls + (size_t)r1 * p.D);
     for (int h = threadIdx.x; h < H; h += kSolveThreads) bufB[L.yin + h] = bufA[L.yin + h] + s1 * G[h];
     __syncthreads();
-    stage_forward<C>(cx, bufB, L, ls + (size_t)r2 * p.D);  // leaves lam/lam1 of row r2
+    stage_forward<C, PF>(cx, bufB, L, ls + (size_t)r2 * p.D);  // leaves lam/lam1 of row r2
     // stage 2 reverse: k2-bar = ybar/2
     for (int h = threadIdx.x; h < H; h += kSolveThreads) rb.g[h] = 0.5f * s2 * ybar[h];
     __syncthreads();
-    stage_reverse<C>(cx, bufB, L, rb, p.ws, p.wsp, slot + 1);
+    stage_reverse<C, PF>(cx, bufB, L, rb, p.ws, p.wsp, slot + 1);
     for (int h = threadIdx.x; h < H; h += kSolveThreads) {
       const float a = rb.yout[h];
       ab[h] = a;
@@ -440,7 +458,7 @@ __global__ void __launch_bounds__(kSolveThreads, 1) logncde_bwd_kernel(const Bwd
     }
     load_logsig_row<C>(cx, ls + (size_t)r1 * p.D);
     __syncthreads();
-    stage_reverse<C>(cx, bufA, L, rb, p.ws, p.wsp, slot);
+    stage_reverse<C, PF>(cx, bufA, L, rb, p.ws, p.wsp, slot);
     for (int h = threadIdx.x; h < H; h += kSolveThreads)
       ybar[h] = ybar[h] + ab[h] + rb.yout[h] + gys[(size_t)n * H + h];
     __syncthreads();
@@ -450,14 +468,17 @@ __global__ void __launch_bounds__(kSolveThreads, 1) logncde_bwd_kernel(const Bwd
     p.wsp[p.ws.bias_part + (size_t)b * n_bias + t] = rb.bias_acc[t];
 }
 
-static size_t bwd_other_floats(int H, int C, int width, int n_hidden) {
+static size_t bwd_other_floats(int H, int C, int width, int n_hidden, bool stream = false) {
   MlpDesc t;
   t.H = H; t.C = C; t.width = width; t.n_hidden = n_hidden;
   const StageLayout L = make_stage_layout(t);
   const int PW = width > H ? width : H;
   int n_bias = n_hidden * width + C * H;
+  // scratch of the transposed products: matvec_cols threads x C, matvec_cols_stream warps x C x in_dim
+  size_t scratch = (size_t)kSolveThreads * C;
+  if (stream && (size_t)(kSolveThreads / 32) * C * PW > scratch) scratch = (size_t)(kSolveThreads / 32) * C * PW;
   return (size_t)2 * L.total + H + C * C + 8 + 5 * H + C * H + C * PW + n_hidden * width + PW + width +
-         ((n_bias + 3) & ~3) + (size_t)kSolveThreads * C;
+         ((n_bias + 3) & ~3) + scratch;
 }
 
 // g_params[out_off + e] = sum_ks part[...]; biases: sum over samples of the per-CTA accumulators
@@ -492,20 +513,31 @@ __global__ void reduce_grads_kernel(const ReduceParams p) {
   }
 }
 
+static bool any_global_layer(const MlpDesc& d) {
+  for (int l = 0; l < d.n_layers; ++l)
+    if (d.gvec[l]) return true;
+  return false;
+}
+// tuning "k3_stream": streamed global-weight mat-vecs; only matters when some layer is not resident in shared memory
+static bool stream_variant() { return tuning_value(kTuneK3Stream) != 0; }
+
 template <int C>
 static int launch_fwd(cudaStream_t st, const FwdParams& p, size_t smem) {
-  auto k = logncde_fwd_kernel<C>;
+  const bool pf = stream_variant() && any_global_layer(p.d);
+  auto k = pf ? logncde_fwd_kernel<C, true> : logncde_fwd_kernel<C, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k<<<p.B, kSolveThreads, smem, st>>>(p);
+  if (pf) logncde_fwd_kernel<C, true><<<p.B, kSolveThreads, smem, st>>>(p);
+  else logncde_fwd_kernel<C, false><<<p.B, kSolveThreads, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 template <int C>
-static int launch_bwd(cudaStream_t st, const BwdParams& p, size_t smem) {
-  auto k = logncde_bwd_kernel<C>;
+static int launch_bwd(cudaStream_t st, const BwdParams& p, size_t smem, bool pf) {
+  auto k = pf ? logncde_bwd_kernel<C, true> : logncde_bwd_kernel<C, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  k<<<p.B, kSolveThreads, smem, st>>>(p);
+  if (pf) logncde_bwd_kernel<C, true><<<p.B, kSolveThreads, smem, st>>>(p);
+  else logncde_bwd_kernel<C, false><<<p.B, kSolveThreads, smem, st>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -607,9 +639,18 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
   if (D != lncde_hall_size(C, depth)) return LNCDE_ERR_SHAPE;
   if (((uintptr_t)workspace & 15) != 0) return LNCDE_ERR_ALIGN;
   BwdParams p;
-  const size_t other = bwd_other_floats(H, C, width, n_hidden) * 4;
+  size_t other = bwd_other_floats(H, C, width, n_hidden) * 4;
   int st = make_mlp_desc(&p.d, H, C, width, n_hidden, depth, other);
   if (st != LNCDE_OK) return st;
+  // "k3_stream": if some layer stays in global memory, lay the kernel out again with the larger scratch of the
+  // streamed transposed products (which may push another layer out of shared memory: decided on that layout)
+  bool pf = false;
+  if (stream_variant() && any_global_layer(p.d) && !use_fast(H, C, width, n_hidden)) {
+    other = bwd_other_floats(H, C, width, n_hidden, true) * 4;
+    st = make_mlp_desc(&p.d, H, C, width, n_hidden, depth, other);
+    if (st != LNCDE_OK) return st;
+    pf = true;
+  }
   const size_t smem = (size_t)p.d.smem_weight_floats * 4 + other;
   if (smem > 227 * 1024) return LNCDE_ERR_UNSUPPORTED;
   p.ws = make_ws_layout(p.d, B, n_steps, kKsplit);
@@ -627,14 +668,14 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
     }
   } else
   switch (C) {
-    case 1: st = launch_bwd<1>(cs, p, smem); break;
-    case 2: st = launch_bwd<2>(cs, p, smem); break;
-    case 3: st = launch_bwd<3>(cs, p, smem); break;
-    case 4: st = launch_bwd<4>(cs, p, smem); break;
-    case 5: st = launch_bwd<5>(cs, p, smem); break;
-    case 6: st = launch_bwd<6>(cs, p, smem); break;
-    case 7: st = launch_bwd<7>(cs, p, smem); break;
-    case 8: st = launch_bwd<8>(cs, p, smem); break;
+    case 1: st = launch_bwd<1>(cs, p, smem, pf); break;
+    case 2: st = launch_bwd<2>(cs, p, smem, pf); break;
+    case 3: st = launch_bwd<3>(cs, p, smem, pf); break;
+    case 4: st = launch_bwd<4>(cs, p, smem, pf); break;
+    case 5: st = launch_bwd<5>(cs, p, smem, pf); break;
+    case 6: st = launch_bwd<6>(cs, p, smem, pf); break;
+    case 7: st = launch_bwd<7>(cs, p, smem, pf); break;
+    case 8: st = launch_bwd<8>(cs, p, smem, pf); break;
     default: return LNCDE_ERR_UNSUPPORTED;
   }
   if (st != 0) return st;

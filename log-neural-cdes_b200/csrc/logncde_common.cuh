@@ -215,6 +215,191 @@ __device__ __forceinline__ void matvec_rows4_global(const float* __restrict__ W,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// "Streamed" forms of the global-weight mat-vecs (template flag PF of the generic kernels, tuning "k3_stream").
+// The functions above wait for every group of weight rows before they ask for the next one: per warp one round
+// trip to L2 per 4 rows (and with in_dim <= 64 half of the lanes issue nothing), so a 896 x 64 layer costs 14
+// dependent L2 latencies.  Here a warp covers 32 / LPR groups of 4 rows per pass (LPR = lanes a row needs) and
+// the loads of pass k + 1 are issued before pass k is reduced.  Same partial sums in the same order (idle lanes
+// contributed exact zeros to the butterflies above): bit-identical results.
+__device__ __forceinline__ int lanes_per_row(int nq) {
+  int l = 1;
+  while (l < nq && l < 32) l <<= 1;
+  return l;
+}
+
+// rows of W [rows][in_dim] against one vector (BLOCKED: the 4-row group of block j = r0 / H against in + j*in_stride).
+// emit(row, value) is called by one lane per row.
+template <bool BLOCKED, typename Emit>
+__device__ __forceinline__ void matvec_rows4_stream(const float* __restrict__ W, int rows, int H, int in_dim,
+                                                    const float* __restrict__ in, int in_stride, Emit&& emit) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kSolveThreads >> 5;
+  const int nq = in_dim >> 2, nch = (nq + 31) >> 5;
+  const int LPR = lanes_per_row(nq), GPW = 32 / LPR;  // groups of 4 rows a warp covers per pass
+  const int sub = lane / LPR, ql = lane - sub * LPR;
+  const int ngroups = (rows + 3) >> 2, stride_g = nw * GPW;
+  auto load = [&](int g, int ch, float4 (&w)[4]) {
+    const int q = ql + 32 * ch, r0 = 4 * g;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      w[r] = (g < ngroups && q < nq && r0 + r < rows) ? ldg4(W + (size_t)(r0 + r) * in_dim + 4 * q)
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 cur[4], nxt[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) nxt[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int g = warp * GPW + sub, ch = 0;  // g0 = the warp's first group of the pass: loop control is warp-uniform
+  load(g, 0, cur);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int g0 = warp * GPW; g0 < ngroups; ) {
+    int g2 = g, ch2 = ch + 1, g02 = g0;
+    if (ch2 == nch) { ch2 = 0; g2 = g + stride_g; g02 = g0 + stride_g; }
+    if (g02 < ngroups) load(g2, ch2, nxt);
+    const int q = ql + 32 * ch;
+    if (g < ngroups && q < nq) {
+      const float* v = BLOCKED ? in + ((4 * g) / H) * in_stride : in;
+      const float4 x4 = *reinterpret_cast<const float4*>(v + 4 * q);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[r] = fmaf(cur[r].x, x4.x, acc[r]);
+        acc[r] = fmaf(cur[r].y, x4.y, acc[r]);
+        acc[r] = fmaf(cur[r].z, x4.z, acc[r]);
+        acc[r] = fmaf(cur[r].w, x4.w, acc[r]);
+      }
+    }
+    if (ch == nch - 1) {
+      for (int m = LPR >> 1; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], m);
+      }
+      if (g < ngroups && ql < 4 && 4 * g + ql < rows)
+        emit(4 * g + ql, ql == 0 ? acc[0] : ql == 1 ? acc[1] : ql == 2 ? acc[2] : acc[3]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = 0.f;
+    }
+    g = g2; ch = ch2; g0 = g02;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) cur[r] = nxt[r];
+  }
+}
+
+// one row per LPR lanes against NB vectors (tangent passes through a hidden layer held in global memory)
+template <int NB, typename Emit>
+__device__ __forceinline__ void matvec_rows_stream(const float* __restrict__ W, int rows, int in_dim,
+                                                   const float* __restrict__ in, int in_stride, Emit&& emit) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kSolveThreads >> 5;
+  const int nq = in_dim >> 2, nch = (nq + 31) >> 5;
+  const int LPR = lanes_per_row(nq), RPW = 32 / LPR;
+  const int sub = lane / LPR, ql = lane - sub * LPR;
+  const int stride_r = nw * RPW;
+  auto load = [&](int row, int ch) {
+    const int q = ql + 32 * ch;
+    return (row < rows && q < nq) ? ldg4(W + (size_t)row * in_dim + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  int row = warp * RPW + sub, ch = 0;
+  float4 cur = load(row, 0), nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+  for (int r0 = warp * RPW; r0 < rows; ) {
+    int row2 = row, ch2 = ch + 1, r02 = r0;
+    if (ch2 == nch) { ch2 = 0; row2 = row + stride_r; r02 = r0 + stride_r; }
+    if (r02 < rows) nxt = load(row2, ch2);
+    const int q = ql + 32 * ch;
+    if (row < rows && q < nq) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float4 x4 = *reinterpret_cast<const float4*>(in + j * in_stride + 4 * q);
+        acc[j] = fmaf(cur.x, x4.x, acc[j]);
+        acc[j] = fmaf(cur.y, x4.y, acc[j]);
+        acc[j] = fmaf(cur.z, x4.z, acc[j]);
+        acc[j] = fmaf(cur.w, x4.w, acc[j]);
+      }
+    }
+    if (ch == nch - 1) {
+      for (int m = LPR >> 1; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], m);
+      }
+      if (row < rows && ql == 0) emit(row, acc);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+    }
+    row = row2; ch = ch2; r0 = r02;
+    cur = nxt;
+  }
+}
+
+// Transposed product with W in global memory (row-major [*][in_dim], in_dim % 4 == 0, 16-byte aligned rows):
+// out[j*out_stride + c] = sum_r W[(row0_j + r)*in_dim + c] * v[j*v_stride + r], row0_j = j*nrows if BLOCKED else 0.
+// Lanes own 4 columns (128-bit loads, a warp reads 32 / LPR whole rows per pass, several passes in flight); the rows
+// of a warp are combined by shuffles, the warps through `scratch` ((kSolveThreads / 32) * NB * in_dim floats).
+// Ends with the result visible to all threads.  Same mathematics as matvec_cols, different association order.
+template <int NB, bool BLOCKED>
+__device__ __forceinline__ void matvec_cols_stream(const float* __restrict__ W, int nrows, int in_dim,
+                                                   const float* __restrict__ v, int v_stride, float* out,
+                                                   int out_stride, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kSolveThreads >> 5;
+  const int nq = in_dim >> 2, nch = (nq + 31) >> 5;
+  const int LPR = lanes_per_row(nq), RPW = 32 / LPR;
+  const int sub = lane / LPR, ql = lane - sub * LPR;
+  for (int ch = 0; ch < nch; ++ch) {
+    const int q = ql + 32 * ch;
+    float4 acc[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < nq) {
+      if (BLOCKED) {
+#pragma unroll 2
+        for (int r = warp * RPW + sub; r < nrows; r += nw * RPW) {
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const float4 w4 = ldg4(W + (size_t)(j * nrows + r) * in_dim + 4 * q);
+            const float vv = v[j * v_stride + r];
+            acc[j].x = fmaf(w4.x, vv, acc[j].x); acc[j].y = fmaf(w4.y, vv, acc[j].y);
+            acc[j].z = fmaf(w4.z, vv, acc[j].z); acc[j].w = fmaf(w4.w, vv, acc[j].w);
+          }
+        }
+      } else {
+#pragma unroll 8
+        for (int r = warp * RPW + sub; r < nrows; r += nw * RPW) {
+          const float4 w4 = ldg4(W + (size_t)r * in_dim + 4 * q);
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            const float vv = v[j * v_stride + r];
+            acc[j].x = fmaf(w4.x, vv, acc[j].x); acc[j].y = fmaf(w4.y, vv, acc[j].y);
+            acc[j].z = fmaf(w4.z, vv, acc[j].z); acc[j].w = fmaf(w4.w, vv, acc[j].w);
+          }
+        }
+      }
+    }
+    for (int m = LPR; m < 32; m <<= 1) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        acc[j].x += __shfl_xor_sync(0xffffffffu, acc[j].x, m);
+        acc[j].y += __shfl_xor_sync(0xffffffffu, acc[j].y, m);
+        acc[j].z += __shfl_xor_sync(0xffffffffu, acc[j].z, m);
+        acc[j].w += __shfl_xor_sync(0xffffffffu, acc[j].w, m);
+      }
+    }
+    if (sub == 0 && q < nq) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        float* dst = scratch + (size_t)(warp * NB + j) * in_dim + 4 * q;
+        dst[0] = acc[j].x; dst[1] = acc[j].y; dst[2] = acc[j].z; dst[3] = acc[j].w;
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < NB * in_dim; t += kSolveThreads) {
+    const int j = t / in_dim, cc = t - j * in_dim;
+    float sum = 0.f;
+    for (int w = 0; w < nw; ++w) sum += scratch[(size_t)(w * NB + j) * in_dim + cc];
+    out[j * out_stride + cc] = sum;
+  }
+  __syncthreads();
+}
+
 // Transposed product.  out[j*out_stride + c] = sum_r W[(row0_j + r)*stride + c] * v[j*v_stride + r]
 // row0_j = j*nrows if BLOCKED else 0.  `scratch` needs kSolveThreads*NB floats.  Ends with the
 // result visible to all threads (contains __syncthreads).
@@ -286,7 +471,7 @@ __device__ __forceinline__ void load_logsig_row(const StageCtx& cx, const float*
 
 // Evaluate the field at buf.yin.  On exit G[h] holds the (unscaled) field and all
 // intermediates needed by the reverse sweep are in `buf`.
-template <int C>
+template <int C, bool PF = false>
 __device__ __noinline__ void stage_forward(const StageCtx& cx, float* buf, const StageLayout& L,
                                               const float* __restrict__ ls_row) {
   const MlpDesc& d = *cx.d;
@@ -306,8 +491,12 @@ __device__ __noinline__ void stage_forward(const StageCtx& cx, float* buf, const
       a[row] = zz * sg;
       s[row] = sg * (1.f + zz * (1.f - sg));
     };
-    if (d.gvec[l]) matvec_rows4_global(cx.wbase[l], d.rows[l], d.in_dim[l], in, fin);
-    else matvec_rows<1>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], in, 0, fin);
+    if (d.gvec[l]) {
+      if constexpr (PF)
+        matvec_rows4_stream<false>(cx.wbase[l], d.rows[l], 1, d.in_dim[l], in, 0, [&](int row, float v) { fin(row, &v); });
+      else
+        matvec_rows4_global(cx.wbase[l], d.rows[l], d.in_dim[l], in, fin);
+    } else matvec_rows<1>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], in, 0, fin);
     __syncthreads();
     in = a;
   }
@@ -315,8 +504,12 @@ __device__ __noinline__ void stage_forward(const StageCtx& cx, float* buf, const
     const float* bias = cx.params + d.b_off[NL];
     float* o = buf + L.o;
     auto fin = [&](int row, const float* acc) { o[row] = tanhf(acc[0] + bias[row]); };
-    if (d.gvec[NL]) matvec_rows4_global(cx.wbase[NL], d.rows[NL], d.in_dim[NL], in, fin);
-    else matvec_rows<1>(cx.wbase[NL], d.stride[NL], d.rows[NL], d.in_dim[NL], d.kq_log2[NL], in, 0, fin);
+    if (d.gvec[NL]) {
+      if constexpr (PF)
+        matvec_rows4_stream<false>(cx.wbase[NL], d.rows[NL], 1, d.in_dim[NL], in, 0, [&](int row, float v) { fin(row, &v); });
+      else
+        matvec_rows4_global(cx.wbase[NL], d.rows[NL], d.in_dim[NL], in, fin);
+    } else matvec_rows<1>(cx.wbase[NL], d.stride[NL], d.rows[NL], d.in_dim[NL], d.kq_log2[NL], in, 0, fin);
   }
   __syncthreads();
   // ---- G = sum_i l_i o_i ; w_j = sum_i Lam_ij o_i ---------------------------
@@ -360,8 +553,10 @@ __device__ __noinline__ void stage_forward(const StageCtx& cx, float* buf, const
         p[j * Wd + row] = sv * acc[j];
       }
     };
-    if (d.gvec[l]) matvec_rows_global<C>(cx.wbase[l], d.rows[l], d.in_dim[l], tin, tin_stride, fin);
-    else matvec_rows<C>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], tin, tin_stride, fin);
+    if (d.gvec[l]) {
+      if constexpr (PF) matvec_rows_stream<C>(cx.wbase[l], d.rows[l], d.in_dim[l], tin, tin_stride, fin);
+      else matvec_rows_global<C>(cx.wbase[l], d.rows[l], d.in_dim[l], tin, tin_stride, fin);
+    } else matvec_rows<C>(cx.wbase[l], d.stride[l], d.rows[l], d.in_dim[l], d.kq_log2[l], tin, tin_stride, fin);
     __syncthreads();
     tin = p;
     tin_stride = Wd;
@@ -369,8 +564,15 @@ __device__ __noinline__ void stage_forward(const StageCtx& cx, float* buf, const
   {
     float* ul = buf + L.ul;
     auto fin = [&](int j, int h, float acc) { ul[j * H + h] = acc; };
-    if (d.gvec[NL]) matvec_rows_blocked_global(cx.wbase[NL], C, H, d.in_dim[NL], tin, tin_stride, fin);
-    else matvec_rows_blocked(cx.wbase[NL], d.stride[NL], C, H, d.in_dim[NL], d.kq_log2[NL], tin, tin_stride, fin);
+    if (d.gvec[NL]) {
+      if constexpr (PF)
+        matvec_rows4_stream<true>(cx.wbase[NL], C * H, H, d.in_dim[NL], tin, tin_stride, [&](int row, float v) {
+          const int j = row / H;
+          fin(j, row - j * H, v);
+        });
+      else
+        matvec_rows_blocked_global(cx.wbase[NL], C, H, d.in_dim[NL], tin, tin_stride, fin);
+    } else matvec_rows_blocked(cx.wbase[NL], d.stride[NL], C, H, d.in_dim[NL], d.kq_log2[NL], tin, tin_stride, fin);
   }
   __syncthreads();
   {

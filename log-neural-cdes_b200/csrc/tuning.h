@@ -12,6 +12,8 @@ enum TuneKey {
   kTuneK1GridCap = 3, // "k1_grid_cap": upper bound on the grid of the persistent K1 kernel (0 = machine-sized); experiments, tests
   kTuneK2DeV2 = 4,   // "k2_de_v2": big-block (DE) LNCDE - 8 x 8 register-tile flow build, reverse scan stores lam_t only and the
                      //             bracket gradient is a triple product of the small operands (linear_de.cuh)
+  kTuneK3Stream = 5, // "k3_stream": generic Log-NCDE kernels - layers that do not fit in shared memory are read with the streamed
+                     //              (prefetching, all-lanes) mat-vecs of logncde_common.cuh
   kTuneCount
 };
 

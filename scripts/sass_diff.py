@@ -51,6 +51,9 @@ def norm(name):
     if m:
         variant = m.group(4) == "true" or m.group(5) == "true"
         return None if variant else f"void {m.group(1)}<{m.group(2)}, {m.group(3)}>(BwdParams)"
+    m = re.match(r"void (logncde_(?:fwd|bwd)_kernel)<(\d), (\w+)>\((\w+)\)", name)
+    if m:  # generic kernels: trailing PF = false of the streamed-weights variant ("k3_stream")
+        return None if m.group(3) == "true" else f"void {m.group(1)}<{m.group(2)}>({m.group(4)})"
     return name
 
 

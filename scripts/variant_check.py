@@ -15,7 +15,10 @@ a fault or hang in a variant that has not been on hardware yet cannot take the c
   k2de: ``set_tuning("k2_de_v2", 1)`` (dense LNCDE: 8 x 8 flow build, lam-only reverse sweep, triple-product bracket
       gradient, linear_de.cuh) - loss and gradients against the default kernels, timings of the EigenWorms DE step.
 
-    python scripts/variant_check.py [--no-timing] [--no-parity] [--only k1|k2|k3|k2de]
+  k3g: ``set_tuning("k3_stream", 1)`` (generic Log-NCDE kernels with streamed global-weight mat-vecs) - loss and
+      gradients against the default generic kernels on PPG / toy dims, timings of both.
+
+    python scripts/variant_check.py [--no-timing] [--no-parity] [--only k1|k2|k3|k2de|k3g]
 """
 import json
 import os
@@ -320,12 +323,81 @@ def k2de_timing(reps=5):
     return res
 
 
+def _generic_step(kind, B, n_windows, seed=0):
+    """Log-NCDE configurations that run the GENERIC solve kernels with a layer in global memory: "ppg" (H 128,
+    vf 3 x 64, C 7, depth 2, regression read-out replaced by classification for the check) and "toy" (H 64, vf 3 x 128,
+    C 6, depth 2)."""
+    from lncde import train as T
+    from lncde.data_dir.datasets import make_intervals, make_ts
+    from lncde.data_dir.generate_paths import calc_paths, logsig_dim
+    from lncde.models.generate_model import create_model
+
+    C, s, H, width, scale = (7, 10, 128, 64, 1000.0) if kind == "ppg" else (6, 4, 64, 128, 1.0)
+    L = n_windows * s - 1
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(B, L, C, device="cuda", generator=g) * 0.05).cumsum(1)
+    ts0 = make_ts(L)
+    model, _ = create_model("log_ncde", C, logsig_dim(C, 2), 2, make_intervals(ts0, s), 5, H, vf_depth=3, vf_width=width,
+                            dt0=1.0 / n_windows, scale=scale, lambd=1e-3, key=2345, device=torch.device("cuda"))
+    ts = torch.from_numpy(ts0)[None, :].expand(B, -1)
+    y = torch.eye(5, device="cuda")[torch.arange(B, device="cuda") % 5]
+    ls = calc_paths(x, s, 2)
+
+    def step():
+        return T.classification_loss(model, (ts, ls, x[:, 0, :]), y)
+
+    return model, step
+
+
+def k3g_parity():
+    from lncde import _lib
+
+    res = {"cases": 0, "max_rel_diff_grad": 0.0, "max_rel_diff_loss": 0.0}
+    for kind, B, nwin in (("ppg", 3, 40), ("toy", 4, 25), ("ppg", 32, 100)):
+        model, step = _generic_step(kind, B, nwin, seed=B)
+        _lib.set_tuning("k3_stream", 0)
+        l0, g0 = step()
+        _lib.set_tuning("k3_stream", 1)
+        l1, g1 = step()
+        _lib.set_tuning("k3_stream", 0)
+        torch.cuda.synchronize()
+        res["cases"] += 1
+        res["max_rel_diff_loss"] = max(res["max_rel_diff_loss"], abs(float(l1) - float(l0)) / max(abs(float(l0)), 1e-30))
+        res["max_rel_diff_grad"] = max(res["max_rel_diff_grad"],
+                                       float((g1 - g0).abs().max() / g0.abs().max().clamp_min(1e-30)))
+    res["ok"] = bool(res["max_rel_diff_loss"] < 1e-6 and res["max_rel_diff_grad"] < 1e-5)
+    return res
+
+
+def k3g_timing(reps=3):
+    from lncde import _lib
+
+    res = {"shape": "generic-kernel Log-NCDE train step (loss + adjoint), B=32, eager launches: PPG dims with 500 Heun "
+                    "steps (a tenth of the PPG-DaLiA length) and the toy configuration (25 steps)"}
+    for kind, nwin in (("ppg", 500), ("toy", 25)):
+        model, step = _generic_step(kind, 32, nwin)
+        for name, v in (("default", 0), ("stream", 1)):
+            _lib.set_tuning("k3_stream", v)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            res[f"{name}_{kind}"] = {"ms": e0.elapsed_time(e1) / reps}
+    _lib.set_tuning("k3_stream", 0)
+    return res
+
+
 if __name__ == "__main__":
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     skip = sys.argv[sys.argv.index("--skip") + 1].split(",") if "--skip" in sys.argv else []
     out = {}
     for name, par, tim in (("k1", parity, timing), ("k3", k3_parity, k3_timing), ("k2", k2_parity, k2_timing),
-                           ("k2de", k2de_parity, k2de_timing)):
+                           ("k2de", k2de_parity, k2de_timing), ("k3g", k3g_parity, k3g_timing)):
         if only not in (None, name) or name in skip:
             continue
         out[name] = {}

@@ -185,6 +185,44 @@ def test_emu_logncde_forward_and_adjoint(case):
     assert rel_err(gp_r, gp_o) < 5 * TOL
 
 
+STREAM_CASES = [
+    (1, 40, 6, 4, 2, 64, 128, 3, 0.1, 4.0),       # toy dims: last layer in global memory (in_dim 128: all lanes busy)
+    (1, 50, 7, 10, 2, 128, 64, 3, 0.2, 4.0),      # PPG dims, depth 2 (in_dim 64: two row groups per warp)
+    (2, 50, 7, 10, 1, 128, 64, 3, 0.2, 4.0),      # PPG reference config (depth 1)
+    (1, 30, 4, 5, 2, 128, 64, 3, 0.2, 2.0),       # BASELINE's 4-channel PPG variant
+    (1, 24, 3, 4, 2, 36, 200, 2, 0.2, 1.0),       # in_dim 200 > 128: two column chunks per row; H not a power of two
+    (1, 24, 2, 4, 2, 40, 176, 4, 0.3, 1.0),       # several layers in global memory (hidden layers too)
+]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES)
+def test_emu_logncde_stream_variant(case):
+    """lncde_set_tuning("k3_stream", 1): the streamed global-weight mat-vecs of the generic kernels.  The forward
+    sums are formed in the same order (bit-identical states); the transposed products associate differently."""
+    B, L, C, s, depth, H, width, n_hidden, dt0, scale = case
+    logsig, rows, sc, grid, layers, y0 = _setup(B, L, C, s, depth, H, width, n_hidden, dt0, scale)
+    dims = (H, C, width, n_hidden, depth)
+    g_ys = torch.from_numpy(np.random.default_rng(1).normal(size=(B, len(grid), H)))
+    flat = O.flatten_params(layers).numpy()
+    ys_o, gp_o, gy_o = _oracle(layers, logsig, y0, rows, sc, dims, g_ys)
+    ys_d, _, _ = E.logncde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, dims, None, train=False)
+    E.set_tuning("k3_stream", 1)
+    try:
+        ys_s, _, _ = E.logncde_fwd_bwd(flat, logsig, y0.numpy(), rows, sc, dims, None, train=False)
+        gp_s, gy_s = E.logncde_bwd_recompute(flat, logsig, ys_s, rows, sc, dims, g_ys.numpy())
+    finally:
+        E.set_tuning("k3_stream", 0)
+    assert np.array_equal(ys_s, ys_d)
+    assert rel_err(ys_s, ys_o) < TOL
+    assert rel_err(gy_s, gy_o) < 5 * TOL
+    off = 0
+    sizes = O.mlp_sizes(H, C, width, n_hidden)
+    for i, o in zip(sizes[:-1], sizes[1:]):
+        for n in (o * i, o):
+            assert rel_err(gp_s[off : off + n], gp_o[off : off + n]) < 5 * TOL, (case, off)
+            off += n
+
+
 @pytest.mark.parametrize("case", [c for c in SOLVE_CASES if c[5:8] == (128, 32, 2)])
 def test_emu_logncde_fused_variant_bit_identical(case):
     """lncde_set_tuning("k3_fused", 1): the single-warp 32 x 32 phases form the same sums in the same order as

@@ -124,7 +124,7 @@ def test_bench_autotune_decision():
 def test_tuning_api_roundtrip(built_lib):
     from lncde import _lib
 
-    for key in ("k1_tma", "k3_fused", "k2_fused_d", "k2_de_v2"):
+    for key in ("k1_tma", "k3_fused", "k2_fused_d", "k2_de_v2", "k3_stream"):
         old = _lib.get_tuning(key)
         _lib.set_tuning(key, 2)
         assert _lib.get_tuning(key) == 2

@@ -46,3 +46,8 @@ def test_k2_fused_diagonal_variant_parity(built_lib):
 @pytest.mark.xfail(strict=False, reason=REASON)
 def test_k2_dense_v2_variant_parity(built_lib):
     _check("k2de")
+
+
+@pytest.mark.xfail(strict=False, reason=REASON)
+def test_k3_generic_stream_variant_parity(built_lib):
+    _check("k3g")
