@@ -6,10 +6,13 @@ set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/r2_smoke.log 2>&1
 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest.log
-timeout 300 python scripts/variant_check.py > gpurun_out/r2_variants.json 2> gpurun_out/r2_variants.err
+# one process per family (k1 k3 k2 k2de k3g): a fault in one does not lose the others
+for fam in k1 k3 k2 k2de k3g; do
+  timeout 300 python scripts/variant_check.py --only $fam >> gpurun_out/r2_variants.json 2>> gpurun_out/r2_variants.err
+done
 timeout 300 python scripts/phase_timing.py > gpurun_out/r2_phases.txt 2>&1
 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err
-for w in eigenworms_bd eigenworms_d eigenworms_de scp1_bd; do
+for w in eigenworms_bd eigenworms_d eigenworms_de scp1_bd eigenworms_nrde toy_logncde ppg_logncde_d1; do
   python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline >> gpurun_out/r2_bench_others.json 2>> gpurun_out/r2_bench.err
 done
 python scripts/k1_sweep.py > gpurun_out/r2_k1_sweep.txt 2>&1
