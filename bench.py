@@ -330,7 +330,7 @@ def run_ours(args):
             "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WL["desc"], "global_batch": world * B, "parallelism": f"dp{world}",
                        "launch": "one CUDA graph per step" if use_graph else "eager",
@@ -601,12 +601,20 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--workload", default="eigenworms_logncde", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the contract): the workload's batch per GPU; strong: that batch split over the GPUs")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-autotune", action="store_true",
                     help="keep the default kernels (skip the subprocess that checks and times the variants)")
     args = ap.parse_args()
     WL.clear()
     WL.update(WORKLOADS[args.workload])
+    if args.scaling == "strong":  # fixed global batch, B / N samples per GPU (chain-latency bound: expect << N x)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if WL["B"] % world:
+            raise SystemExit(f"--scaling strong needs the batch ({WL['B']}) to divide by the number of GPUs ({world})")
+        WL["B"] //= world
+        WL["desc"] += f" [strong scaling: {WL['B']} samples per GPU]"
     # the default run finishes in ~40 s; never let a stuck collective hold N GPUs for long
     _watchdog(float(os.environ.get("LNCDE_BENCH_TIMEOUT", "600")))
     if args.impl == "reference":

@@ -63,3 +63,17 @@ def batch_calc_paths(data: torch.Tensor, stepsize, depth: int, *, compat: bool =
     whole dataset is ONE launch and the chunk boundary only selects which samples
     have no predecessor for the remainder-window quirk."""
     return calc_paths(data, stepsize, depth, compat=compat, chunk=128)
+
+
+def preprocess_shard(n_samples: int, rank: int, world_size: int, chunk: int = 128) -> slice:
+    """Samples one rank preprocesses when a dataset is split over the GPUs of a node.
+
+    Shards are whole ``chunk``-sample groups of ``batch_calc_paths`` (datasets.py:45): the cross-sample basepoint of
+    the remainder window (quirk B1) only reaches back inside such a group, so no shard needs a halo row of its
+    neighbour and there is no collective - concatenating the ranks' ``batch_calc_paths(data[shard])`` in rank order
+    is bit-for-bit the single-process result.  Ranks beyond the number of groups get an empty slice."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("rank must be in [0, world_size)")
+    n_chunks = -(-int(n_samples) // int(chunk))
+    lo, hi = (n_chunks * rank) // world_size, (n_chunks * (rank + 1)) // world_size
+    return slice(min(n_samples, lo * chunk), min(n_samples, hi * chunk))

@@ -81,3 +81,52 @@ def test_shard_slice_errors():
     assert T.shard_slice(32, 3, 8) == slice(12, 16)
     with pytest.raises(ValueError):
         T.shard_slice(30, 0, 8)
+
+
+def _prep_worker(rank, world, port, out_dir):
+    import sys
+
+    for p in (REPO, os.path.join(REPO, "log-neural-cdes_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lncde.data_dir.generate_paths import preprocess_shard
+    from oracle import paths
+
+    n, L, C, s = 300, 10, 2, 3  # 3 groups of 128 / 128 / 44 samples; stepsize 3 leaves a remainder window (quirk B1)
+    x = np.cumsum(np.round(np.random.default_rng(4).normal(size=(n, L, C))), axis=1)
+    full = paths.batch_calc_paths(x, s, 2, np.float64)
+    sl = preprocess_shard(n, rank, world)
+    mine = paths.batch_calc_paths(x[sl], s, 2, np.float64)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (sl.start, sl.stop, mine))  # test only: the product path needs no collective
+    cat = np.concatenate([g[2] for g in gathered])
+    naive = paths.batch_calc_paths(x[rank * n // world : (rank + 1) * n // world], s, 2, np.float64)
+    naive_ok = np.array_equal(naive, full[rank * n // world : (rank + 1) * n // world])
+    with open(os.path.join(out_dir, f"prep{rank}.txt"), "w") as fh:
+        fh.write(f"{int(np.array_equal(cat, full))} {sl.start} {sl.stop} {int(naive_ok)}\n")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_preprocessing_shards_need_no_halo(tmp_path):
+    """Whole-group shards reproduce the single-process log-signatures exactly; an even split that cuts a 128-sample
+    group does not (rank 1 would start at sample 150 and lose its predecessor's basepoint)."""
+    world = 2
+    mp.spawn(_prep_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = [open(tmp_path / f"prep{r}.txt").read().split() for r in range(world)]
+    assert got[0] == ["1", "0", "128", "1"]
+    assert got[1] == ["1", "128", "300", "0"]
+
+
+def test_preprocess_shard_covers_everything():
+    from lncde.data_dir.generate_paths import preprocess_shard
+
+    for n in (1, 127, 128, 129, 1000, 4096):
+        for world in (1, 2, 4, 8):
+            sl = [preprocess_shard(n, r, world) for r in range(world)]
+            assert sl[0].start == 0 and sl[-1].stop == n
+            assert all(a.stop == b.start for a, b in zip(sl[:-1], sl[1:]))
+            assert all(s.start % 128 == 0 for s in sl)
