@@ -126,9 +126,9 @@ def dataset_generator(name, data, labels, stepsize, depth, include_time, T, inme
     return Dataset(name, raw, None, path, int(tr[0].shape[-1]), int(tr[3].shape[-1]), intervals, label_dim)
 
 
-def create_dataset(name: str, n: int, *, seed: int = 2345, stepsize=None, depth=None, T: float = 1.0,
-                   scale: bool = False, device="cuda", L: int | None = None, n_out: int | None = None,
-                   inmemory: bool = True) -> Dataset:
+def create_synthetic_dataset(name: str, n: int, *, seed: int = 2345, stepsize=None, depth=None, T: float = 1.0,
+                             scale: bool = False, device="cuda", L: int | None = None, n_out: int | None = None,
+                             inmemory: bool = True, paths_fn=None) -> Dataset:
     """Synthetic stand-in for data_dir/datasets.py:create_dataset (the real datasets are not available offline):
     synthetic paths of the named dataset's shape, then ``dataset_generator`` exactly as the reference calls it."""
     cfg = SHAPES[name]
@@ -141,4 +141,102 @@ def create_dataset(name: str, n: int, *, seed: int = 2345, stepsize=None, depth=
     else:
         lab = rng.uniform(-1, 1, size=(n, n_out or 1)).astype(np.float32)
     return dataset_generator(name, torch.from_numpy(x), torch.from_numpy(lab), stepsize, depth, cfg["time"], T,
-                             inmemory=inmemory, key=seed, device=device)
+                             inmemory=inmemory, key=seed, device=device, paths_fn=paths_fn)
+
+
+def _load(path):
+    """One of the reference's processed pickles (data_dir/process_uea.py, process_ppg.py, toy_dataset.py write jax
+    arrays; anything ``np.asarray`` understands is accepted - unpickling a jax array needs jax importable)."""
+    import pickle
+
+    with open(path, "rb") as f:
+        return np.asarray(pickle.load(f))
+
+
+def _with_time(x, T):
+    t = (np.float32(T / x.shape[1]) * np.arange(x.shape[1], dtype=np.float32))[None, :, None]
+    return np.concatenate([np.broadcast_to(t, (x.shape[0], x.shape[1], 1)), x.astype(np.float32)], axis=2)
+
+
+def _onehot(labels):
+    labels = np.asarray(labels).astype(np.int64)
+    return np.eye(len(np.unique(labels)), dtype=np.float32)[labels]
+
+
+def _minmax(x, lo, hi, eps=1e-8):  # datasets.py:236-238
+    return 2.0 * (x - lo) / (hi - lo + eps) - 1.0
+
+
+def create_dataset(data_dir, name, use_idxs, use_presplit, stepsize, depth, include_time, T, scale=False, *, key,
+                   device="cuda", paths_fn=None):
+    """data_dir/datasets.py:406-446 with the reference's signature: the processed UEA / toy / PPG pickles under
+    ``data_dir/processed`` (:241-403), optional time channel, LNCDE min-max scaling (:300-314), then
+    ``dataset_generator``.  ``data_dir = "synthetic"`` or ``"synthetic:<n>"`` builds the named dataset's shape from
+    random walks instead (the real datasets are not available offline)."""
+    import os
+
+    if str(data_dir).startswith("synthetic"):
+        n = int(str(data_dir).split(":")[1]) if ":" in str(data_dir) else 256
+        base = "toy" if name.startswith("signature") else name
+        if base not in SHAPES:
+            raise ValueError(f"Dataset {name} not found in UEA folder and not toy dataset")
+        return create_synthetic_dataset(base, n, seed=int(key) if not isinstance(key, torch.Generator) else 2345,
+                                        stepsize=stepsize, depth=depth, T=T, scale=scale, device=device,
+                                        inmemory=base != "ppg", paths_fn=paths_fn)
+    proc = os.path.join(data_dir, "processed")
+    sub = lambda d: [f.name for f in os.scandir(os.path.join(proc, d)) if f.is_dir()] if os.path.isdir(os.path.join(proc, d)) else []
+    gen = dict(key=key, device=device, paths_fn=paths_fn)
+    if name in sub("UEA"):
+        d = os.path.join(proc, "UEA", name)
+        idxs = None
+        if use_presplit:
+            data = [_load(os.path.join(d, f"X_{s}.pkl")) for s in ("train", "val", "test")]
+            labels = tuple(_load(os.path.join(d, f"y_{s}.pkl")) for s in ("train", "val", "test"))
+            if include_time:
+                data = [_with_time(x, T) for x in data]
+            if scale:
+                allx = np.concatenate(data, axis=0)
+                lo, hi = allx.min(axis=(0, 1), keepdims=True), allx.max(axis=(0, 1), keepdims=True)
+                data = [_minmax(x, lo, hi) for x in data]
+            data = tuple(data)
+        else:
+            data = _load(os.path.join(d, "data.pkl"))
+            labels = _onehot(_load(os.path.join(d, "labels.pkl")))
+            if use_idxs:
+                import pickle
+
+                with open(os.path.join(d, "original_idxs.pkl"), "rb") as f:
+                    idxs = pickle.load(f)
+            if include_time:
+                data = _with_time(data, T)
+            if scale:
+                data = _minmax(data, data.min(axis=(0, 1), keepdims=True), data.max(axis=(0, 1), keepdims=True))
+        return dataset_generator(name, data, labels, stepsize, depth, include_time, T, idxs=idxs,
+                                 use_presplit=use_presplit, **gen)
+    if name[:-1] in sub("toy"):
+        import pickle
+
+        data = _load(os.path.join(proc, "toy", "signature", "data.pkl"))
+        with open(os.path.join(proc, "toy", "signature", "labels.pkl"), "rb") as f:
+            lab = pickle.load(f)
+        pick = {"signature1": lambda l: l[0][:, 2], "signature2": lambda l: l[1][:, 2, 5],
+                "signature3": lambda l: l[2][:, 2, 5, 0], "signature4": lambda l: l[3][:, 2, 5, 0, 3]}
+        if name not in pick:
+            raise ValueError(f"Dataset {name} not found in UEA folder and not toy dataset")
+        labels = ((np.sign(np.asarray(pick[name](lab))) + 1) / 2).astype(int)  # datasets.py:326-333
+        if include_time:
+            data = _with_time(data, T)
+        return dataset_generator("toy", data, _onehot(labels), stepsize, depth, include_time, T, idxs=None, **gen)
+    if name == "ppg":
+        d = os.path.join(proc, "PPG", "ppg")
+        data = [_load(os.path.join(d, f"X_{s}.pkl")) for s in ("train", "val", "test")]
+        labels = [_load(os.path.join(d, f"y_{s}.pkl")) for s in ("train", "val", "test")]
+        if include_time:
+            data = [_with_time(x, T) for x in data]
+        if use_presplit:
+            data, labels = tuple(data), tuple(labels)
+        else:
+            data, labels = np.concatenate(data, axis=0), np.concatenate(labels, axis=0)
+        return dataset_generator("ppg", data, labels, stepsize, depth, include_time, T, inmemory=False,
+                                 use_presplit=use_presplit, **gen)
+    raise ValueError(f"Dataset {name} not found in UEA folder and not toy dataset")

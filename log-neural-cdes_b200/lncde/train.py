@@ -198,6 +198,54 @@ def train_model(model_name, dataset_name, model, metric, filter_spec, state, dat
     return model
 
 
+def experiment_output_dir(model_name, dataset_name, T, include_time, num_steps, lr, stepsize, logsig_depth, model_args,
+                          seed, output_parent_dir=""):
+    """Directory name of one run, exactly as train.py:386-403 composes it."""
+    parent = output_parent_dir + "outputs/" + model_name + "/" + dataset_name
+    out = f"T_{T:.2f}_time_{include_time}_nsteps_{num_steps}_lr_{lr}"
+    if model_name in ("log_ncde", "nrde"):
+        out += f"_stepsize_{stepsize:.2f}_depth_{logsig_depth}"
+    for k, v in model_args.items():
+        name = str(v)
+        if v is not None:
+            if "(" in name:
+                name = name.split("(", 1)[0]
+            if name == "dt0":
+                out += f"_{k}_" + f"{v:.2f}"
+            else:
+                out += f"_{k}_" + name
+            if name == "PIDController":
+                out += f"_rtol_{v.rtol}_atol_{v.atol}"
+    return parent + "/" + out + f"_seed_{seed}"
+
+
+def create_dataset_model_and_train(seed, data_dir, use_presplit, dataset_name, output_step, metric, include_time, T,
+                                   model_name, stepsize, logsig_depth, model_args, num_steps, print_steps,
+                                   early_stopping_steps, lr, lr_scheduler, batch_size, output_parent_dir="", *,
+                                   device="cuda", world_size=1, overwrite=False, log=print, paths_fn=None):
+    """train.py:365-487 with the reference's signature, for the models on the Log-ODE input (``log_ncde``, ``nrde``,
+    ``*_linear_ncde``): dataset -> model -> ``train_model`` on the path dataloaders.  No ``filter_spec`` is needed:
+    ``intervals`` / ``pairs`` / ``hadamard_matrix`` are not part of the flat parameter vector of the mirrors."""
+    from .data_dir.datasets import create_dataset
+    from .models.generate_model import create_model
+
+    if not (model_name in ("log_ncde", "nrde") or model_name.endswith("linear_ncde")):
+        raise NotImplementedError(f"{model_name} does not take the Log-ODE input (SURVEY.md section 8)")
+    output_dir = experiment_output_dir(model_name, dataset_name, T, include_time, num_steps, lr, stepsize, logsig_depth,
+                                       model_args, seed, output_parent_dir)
+    log(f"Creating dataset {dataset_name}")
+    dataset = create_dataset(data_dir, dataset_name, stepsize=stepsize, depth=logsig_depth, include_time=include_time, T=T,
+                             use_idxs=False, use_presplit=use_presplit, scale=model_name.endswith("linear_ncde"),
+                             key=seed, device=device, paths_fn=paths_fn)
+    log(f"Creating model {model_name}")
+    model, state = create_model(model_name, dataset.data_dim, dataset.logsig_dim, logsig_depth, dataset.intervals,
+                                dataset.label_dim, classification=metric == "accuracy", output_step=output_step,
+                                **model_args, key=seed + 1, device=device)
+    return train_model(model_name, dataset_name, model, metric, None, state, dataset.path_dataloaders, num_steps,
+                       print_steps, early_stopping_steps, lr, lr_scheduler, batch_size, seed + 2, output_dir,
+                       world_size=world_size, overwrite=overwrite, log=log)
+
+
 class GraphedStep:
     """One training step captured in a CUDA graph (streams and graphs instead of a tracing compiler):
     the ~100 small launches of a step (K1, solve / scan kernels, read-out + loss autograd, gradient GEMMs,
