@@ -14,6 +14,17 @@ LOG_ODE_MODELS = ("log_ncde", "nrde", "bd_linear_ncde", "diagonal_linear_ncde", 
                   "dense_linear_ncde", "wh_linear_ncde", "sparse_linear_ncde", "dplr_linear_ncde")
 
 
+def _scheduler(src):
+    """The reference's configs hold the schedule as the source of a lambda (``"lambda lr: lr"``, evaluated at
+    run_experiment.py:43); here it is evaluated without builtins, with ``math`` as the only name in scope."""
+    import math
+
+    fn = eval(src, {"__builtins__": {}, "math": math}, {})
+    if not callable(fn):
+        raise ValueError(f"lr_scheduler must be the source of a callable, got {src!r}")
+    return fn
+
+
 def parse_config(model_name, dataset_name, data):
     """(run_args, seeds) from one reference config dict (run_experiment.py:40-150, 199-240)."""
     if model_name not in LOG_ODE_MODELS:
@@ -55,7 +66,7 @@ def parse_config(model_name, dataset_name, data):
         "print_steps": data["print_steps"],
         "early_stopping_steps": data["early_stopping_steps"],
         "lr": float(data["lr"]),
-        "lr_scheduler": eval(data["lr_scheduler"]),  # the reference's configs hold a lambda as a string (:43)
+        "lr_scheduler": _scheduler(data["lr_scheduler"]),
         "batch_size": data["batch_size"],
         "output_parent_dir": data["output_parent_dir"],
     }
