@@ -423,15 +423,22 @@ def decide_tuning(rep, margin=0.98):
     """A variant is used only if ITS parity check passed and it beat the default by the margin."""
     choice = {"k1_tma": 0, "k3_fused": 0}
     k1, k3 = rep.get("k1", {}), rep.get("k3", {})
-    for fam, key, base, var in (("k2", "k2_fused_d", "default_B32", "fused_B32"), ("k2de", "k2_de_v2", "default", "v2"),
-                                ("k3g", "k3_stream", "default_ppg", "stream_ppg")):
+    for fam, key, base, variants in (("k2", "k2_fused_d", "default_B32", ((1, "fused_B32"),)),
+                                     ("k2de", "k2_de_v2", "default", ((1, "v2"), (2, "v2_tc"))),
+                                     ("k3g", "k3_stream", "default_ppg", ((1, "stream_ppg"),))):
         r = rep.get(fam)
         if r is None:
             continue
         choice[key] = 0
         try:
-            if "error" not in r and r.get("parity", {}).get("ok") and r["timing"][var]["ms"] < margin * r["timing"][base]["ms"]:
-                choice[key] = 1
+            if "error" in r or "timing" not in r:
+                continue
+            par = r.get("parity", {})
+            best_ms = margin * r["timing"][base]["ms"]
+            for v, name in variants:
+                ok = par.get("ok_by_variant", {}).get(str(v), par.get("ok")) if "ok_by_variant" in par else par.get("ok")
+                if ok and name in r["timing"] and r["timing"][name]["ms"] < best_ms:
+                    choice[key], best_ms = v, r["timing"][name]["ms"]
         except (KeyError, TypeError):
             pass
     try:

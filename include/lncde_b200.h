@@ -47,7 +47,8 @@ const char* lncde_strerror(int status);
  * fastest on B200 so far.  Keys: "k1_tma" (lncde_logsig_fwd: 1 = TMA bulk-copy staging, same as passing
  * LNCDE_FLAG_K1_TMA; 2 = the same kernel persistent, two-buffer ring, grid sized to the machine), "k3_fused" (lncde_logncde_fwd/bwd, specialised H=128 / width 32 kernels: 1 = the 32 x 32
  * layer phases fused on single warps, 2 = additionally phase Q4 of the adjoint folded into Q5), "k2_fused_d" (host mirror: diagonal LNCDE through lncde_dlncde_* instead
- * of flow build + scan), "k2_de_v2" (lncde_linear_scan_fwd/bwd with block size >= 64: 128 x 128 flow-build tiles with
+ * of flow build + scan), "k2_de_v2" (lncde_linear_scan_fwd/bwd with block size >= 64; 2 = additionally the flow build on the tensor pipe,
+ * 3xTF32 split precision; 1 = 128 x 128 flow-build tiles with
  * 8 x 8 register tiles; the reverse sweep stores lam_t instead of dF_t and the bracket gradient is the triple product
  * sum lam_t (x) y_{t-1} (x) logsig_t - the flows in the workspace are then left intact by the backward call).
  * "k3_stream" (lncde_logncde_fwd/bwd, generic kernels - shapes other than H = 128 / width 32 / 2 hidden layers: layers that

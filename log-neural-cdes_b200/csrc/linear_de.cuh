@@ -12,6 +12,7 @@
 //    operands (lam, y: 24 MB each, ls: 5 MB) - the reverse scan then only has to store lam_t (512 B per step)
 //    instead of the outer product dF_t (64 KB per step), and nothing reads 3.1 GB back.  Same FLOPs as the GEMM it
 //    replaces (the rank-1 factor costs 2 extra multiplies per 56 FMAs), split-K with a deterministic reduce.
+//  * flow_build_tc_kernel ("k2_de_v2" = 2): the flow build on the tensor pipe, 3xTF32 split precision (see below).
 //  * scan_bwd_tma_lam_kernel: the reverse sweep of scan_bwd_tma_kernel (linear_scan.cu) with the in-place dF_t store
 //    replaced by a 512-byte store of lam_t - same ring of TMA bulk copies, same order of the sums, so lam, g_y0 are
 //    bit-identical to the default kernel; the flows in the workspace stay intact.
@@ -90,6 +91,106 @@ __global__ void __launch_bounds__(256) flow_build8_kernel(const float* __restric
       }
     }
   }
+}
+
+// ---------------------------------------------------------------- flow build on the tensor pipe (3xTF32)
+// Same contraction on the warp-level TF32 MMA (mma.sync m16n8k8) with the split-precision scheme
+//   a b ~= a_hi b_hi + a_hi b_lo + a_lo b_hi,   x_hi = tf32(x), x_lo = tf32(x - x_hi)
+// (the dropped a_lo b_lo term and the rounding of x_lo are ~2^-22 relative: fp32-grade flows, inside the 1e-5
+// parity bar; plain TF32 would not be).  CTA tile 128 x 128, 8 warps as 2 (M) x 4 (N), warp tile 64 x 32 =
+// 4 x 4 MMA tiles with fp32 accumulators in registers; the operands are split once while they are staged into
+// shared memory (row stride 36 words: the fragment reads of a warp hit 32 different banks).  K = n_basis is
+// walked in tiles of 32 (zero padded): depth 2 needs one tile, depth 3 (n_basis up to 140) five.  With K this
+// small the kernel is bound by writing the flows (64 KB per CTA), which is the point: the FFMA kernels above
+// are issue-bound at 2-3x the time the bytes need.
+constexpr int kTcTile = 128, kTcK = 32, kTcStride = kTcK + 4;
+constexpr size_t kTcSmemBytes = (size_t)4 * kTcTile * kTcStride * sizeof(uint32_t);
+
+__global__ void __launch_bounds__(256, 2) flow_build_tc_kernel(const float* __restrict__ lie,
+                                                               const float* __restrict__ logsig, float* __restrict__ F,
+                                                               long long Mtot, int N, int D, int n_basis, int bs) {
+  extern __shared__ __align__(16) unsigned char tc_raw[];
+  uint32_t* Ah = reinterpret_cast<uint32_t*>(tc_raw);  // [128][36] logsig tile, hi parts
+  uint32_t* Al = Ah + kTcTile * kTcStride;             // lo parts
+  uint32_t* Bh = Al + kTcTile * kTcStride;             // [128][36] lie tile (row n, column k)
+  uint32_t* Bl = Bh + kTcTile * kTcStride;
+  const long long m0 = (long long)blockIdx.y * kTcTile;
+  const int n0 = blockIdx.x * kTcTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+  float acc[4][4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+  for (int k0 = 0; k0 < n_basis; k0 += kTcK) {
+    // consecutive threads read consecutive k of one row: contiguous in global memory, conflict-free in shared
+    for (int e = threadIdx.x; e < kTcTile * kTcK; e += 256) {
+      const int r = e >> 5, kk = e & 31;
+      const bool kin = k0 + kk < n_basis;
+      const float a = (kin && m0 + r < Mtot) ? __ldg(logsig + (m0 + r) * D + 1 + k0 + kk) : 0.f;
+      const float b = (kin && n0 + r < N) ? __ldg(lie + (size_t)(n0 + r) * n_basis + k0 + kk) : 0.f;
+      const uint32_t ah = cvt_tf32(a), bh = cvt_tf32(b);
+      Ah[r * kTcStride + kk] = ah;
+      Al[r * kTcStride + kk] = cvt_tf32(a - __uint_as_float(ah));
+      Bh[r * kTcStride + kk] = bh;
+      Bl[r * kTcStride + kk] = cvt_tf32(b - __uint_as_float(bh));
+    }
+    __syncthreads();
+    const int ksteps = (min(kTcK, n_basis - k0) + 7) >> 3;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int kc = ks * 8 + t;
+      uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int o = (wn + nt * 8 + g) * kTcStride + kc;
+        bh[nt][0] = Bh[o]; bh[nt][1] = Bh[o + 4];
+        bl[nt][0] = Bl[o]; bl[nt][1] = Bl[o + 4];
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const int o = (wm + mt * 16 + g) * kTcStride + kc;
+        const uint32_t ah[4] = {Ah[o], Ah[o + 8 * kTcStride], Ah[o + 4], Ah[o + 8 * kTcStride + 4]};
+        const uint32_t al[4] = {Al[o], Al[o + 8 * kTcStride], Al[o + 4], Al[o + 8 * kTcStride + 4]};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma_m16n8k8_tf32(acc[mt][nt], al, bh[nt]);  // small terms first
+          mma_m16n8k8_tf32(acc[mt][nt], ah, bl[nt]);
+          mma_m16n8k8_tf32(acc[mt][nt], ah, bh[nt]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int bs2 = bs * bs;
+  const bool vec2 = (N & 1) == 0;  // rows of F 8-byte aligned (the workspace is 16-byte aligned)
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const long long m = m0 + wm + mt * 16 + g + 8 * half;
+      if (m >= Mtot) continue;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int n = n0 + wn + nt * 8 + 2 * t;
+        float v[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int r = (n + j) % bs2;
+          v[j] = acc[mt][nt][2 * half + j] + ((r / bs == r % bs) ? 1.f : 0.f);
+        }
+        float* dst = F + m * N + n;
+        if (vec2 && n + 1 < N) {
+          *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+        } else {
+          if (n < N) dst[0] = v[0];
+          if (n + 1 < N) dst[1] = v[1];
+        }
+      }
+    }
 }
 
 // ---------------------------------------------------------------- bracket gradient without dF

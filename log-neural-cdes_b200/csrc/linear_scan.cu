@@ -578,7 +578,12 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   const int H = nb * bs, N = H * bs;
   const long long Mtot = (long long)B * T;
   // 1. flows
-  if (tuning_value(kTuneK2DeV2) && de_v2_shape(bs, n_basis)) {
+  const int de_v2 = tuning_value(kTuneK2DeV2);
+  if (de_v2 >= 2 && bs >= 64) {  // tensor pipe (3xTF32), any n_basis
+    dim3 grid((N + 127) / 128, (unsigned)((Mtot + 127) / 128));
+    cudaFuncSetAttribute(flow_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    flow_build_tc_kernel<<<grid, 256, kTcSmemBytes, cs>>>(lie, logsig, F, Mtot, N, D, n_basis, bs);
+  } else if (de_v2 && de_v2_shape(bs, n_basis)) {
     dim3 grid((N + 127) / 128, (unsigned)((Mtot + 127) / 128));
     flow_build8_kernel<<<grid, 256, 0, cs>>>(lie, logsig, F, Mtot, N, D, n_basis, bs);
   } else {

@@ -73,4 +73,21 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // order generic-proxy shared-memory writes before later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- TF32 tensor-core MMA (legacy warp-level path; used by the 3xTF32 flow build of K2) ---
+// round-to-nearest (ties away) conversion to TF32 (10-bit mantissa), returned as the fp32 bit pattern
+__device__ __forceinline__ uint32_t cvt_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+// D (16x8, fp32) += A (16x8, row) * B (8x8, col).  Fragments, g = lane / 4, t = lane % 4:
+//   a0 = A[g][t], a1 = A[g+8][t], a2 = A[g][t+4], a3 = A[g+8][t+4];  b0 = B[t][g], b1 = B[t+4][g];
+//   d0 = D[g][2t], d1 = D[g][2t+1], d2 = D[g+8][2t], d3 = D[g+8][2t+1]
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 }  // namespace lncde

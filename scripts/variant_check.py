@@ -283,31 +283,37 @@ def _de_step(B, n_windows, seed=0):
 def k2de_parity():
     from lncde import _lib
 
-    res = {"cases": 0, "max_rel_diff_grad": 0.0, "max_rel_diff_loss": 0.0}
+    res = {"cases": 0, "max_rel_diff_grad": {"1": 0.0, "2": 0.0}, "max_rel_diff_loss": {"1": 0.0, "2": 0.0}}
     for B, nwin in ((3, 40), (8, 1499), (5, 130)):
         model, step = _de_step(B, nwin, seed=B)
         _lib.set_tuning("k2_de_v2", 0)
         l0, g0 = step()
-        _lib.set_tuning("k2_de_v2", 1)
-        l1, g1 = step()
+        for v in (1, 2):
+            _lib.set_tuning("k2_de_v2", v)
+            l1, g1 = step()
+            torch.cuda.synchronize()
+            dl = abs(float(l1) - float(l0)) / max(abs(float(l0)), 1e-30)
+            dg = float((g1 - g0).abs().max() / g0.abs().max().clamp_min(1e-30))
+            res["max_rel_diff_loss"][str(v)] = max(res["max_rel_diff_loss"][str(v)], dl)
+            res["max_rel_diff_grad"][str(v)] = max(res["max_rel_diff_grad"][str(v)], dg)
         _lib.set_tuning("k2_de_v2", 0)
-        torch.cuda.synchronize()
         res["cases"] += 1
-        res["max_rel_diff_loss"] = max(res["max_rel_diff_loss"], abs(float(l1) - float(l0)) / max(abs(float(l0)), 1e-30))
-        res["max_rel_diff_grad"] = max(res["max_rel_diff_grad"],
-                                       float((g1 - g0).abs().max() / g0.abs().max().clamp_min(1e-30)))
         del model, step
         torch.cuda.empty_cache()
-    res["ok"] = bool(res["max_rel_diff_loss"] < 1e-5 and res["max_rel_diff_grad"] < 5e-5)
+    res["ok_by_variant"] = {v: bool(res["max_rel_diff_loss"][v] < 1e-5 and res["max_rel_diff_grad"][v] < 5e-5)
+                            for v in ("1", "2")}
+    res["ok"] = all(res["ok_by_variant"].values())
     return res
 
 
 def k2de_timing(reps=5):
     from lncde import _lib
 
-    res = {"shape": "EigenWorms DE-LNCDE train step (loss + gradient), eager launches, B=32 (flows 3.1 GB)"}
+    res = {"shape": "EigenWorms DE-LNCDE train step (loss + gradient), eager launches, B=32 (flows 3.1 GB); v2 = FFMA 8x8 "
+                    "flow build + lam-only reverse sweep + triple-product gradient, v2_tc = the same with the flow build on "
+                    "the tensor pipe (3xTF32)"}
     model, step = _de_step(32, 1499)
-    for name, v in (("default", 0), ("v2", 1)):
+    for name, v in (("default", 0), ("v2", 1), ("v2_tc", 2)):
         _lib.set_tuning("k2_de_v2", v)
         for _ in range(2):
             step()

@@ -163,6 +163,8 @@ inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __int_as_float(int i) { return emu::unpack<float>(emu::pack(i)); }
 inline int __float_as_int(float f) { return emu::unpack<int>(emu::pack(f)); }
+inline float __uint_as_float(unsigned u) { return emu::unpack<float>(emu::pack(u)); }
+inline unsigned __float_as_uint(float f) { return emu::unpack<unsigned>(emu::pack(f)); }
 inline long long clock64() { return 0; }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }

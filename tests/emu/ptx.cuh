@@ -37,4 +37,39 @@ inline void tma_store_commit() {}
 inline void tma_store_wait_read() {}
 inline void fence_async_proxy() {}
 
+// TF32: keep 10 mantissa bits, round to nearest with ties away from zero (cvt.rna)
+inline uint32_t cvt_tf32(float v) {
+  uint32_t u;
+  std::memcpy(&u, &v, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u += 0x1000u;
+  return u & 0xffffe000u;
+}
+// warp-collective model of mma.sync.m16n8k8 (tf32 x tf32 -> fp32) with the fragment layout documented in csrc/ptx.cuh:
+// every lane deposits its fragments, then forms its four outputs from the gathered 16x8 / 8x8 operand tiles
+inline void mma_m16n8k8_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  uint64_t fa[2][32], fb[32];
+  const uint64_t* s = emu::warp_exchange(0xffffffffu, (uint64_t)a[0] | ((uint64_t)a[1] << 32));
+  std::memcpy(fa[0], s, sizeof(fa[0]));
+  s = emu::warp_exchange(0xffffffffu, (uint64_t)a[2] | ((uint64_t)a[3] << 32));
+  std::memcpy(fa[1], s, sizeof(fa[1]));
+  s = emu::warp_exchange(0xffffffffu, (uint64_t)b[0] | ((uint64_t)b[1] << 32));
+  std::memcpy(fb, s, sizeof(fb));
+  auto as_f = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+  auto A = [&](int m, int k) {  // owner lane (m % 8) * 4 + k % 4, register (m >= 8) + 2 * (k >= 4)
+    const uint64_t w = fa[k >= 4][(m & 7) * 4 + (k & 3)];
+    return as_f((uint32_t)(m >= 8 ? (w >> 32) : w));
+  };
+  auto Bm = [&](int k, int n) {  // owner lane n * 4 + k % 4, register (k >= 4)
+    const uint64_t w = fb[n * 4 + (k & 3)];
+    return as_f((uint32_t)(k >= 4 ? (w >> 32) : w));
+  };
+  const int lane = emu::lane_id(), g = lane >> 2, t = lane & 3;
+  for (int i = 0; i < 4; ++i) {
+    const int m = g + (i >= 2 ? 8 : 0), n = 2 * t + (i & 1);
+    double acc = d[i];
+    for (int k = 0; k < 8; ++k) acc += (double)A(m, k) * (double)Bm(k, n);
+    d[i] = (float)acc;
+  }
+}
+
 }  // namespace lncde

@@ -342,11 +342,15 @@ def test_emu_linear_scan_forward_and_adjoint(nb, bs, T, n_basis):
     assert rel_err(gl_e, lie_t.grad.numpy()) < 5 * TOL
 
 
+@pytest.mark.parametrize("level", [1, 2])
 @pytest.mark.parametrize("nb,bs,T,n_basis,B", [(1, 64, 9, 6, 2), (1, 128, 7, 28, 2), (2, 64, 5, 21, 3), (1, 64, 2, 3, 1),
-                                               (1, 68, 6, 10, 2), (1, 128, 40, 36, 1)])
-def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B):
-    """tuning "k2_de_v2" (linear_de.cuh): 8 x 8 flow build, lam-only reverse sweep, triple-product bracket gradient.
-    ys and g_y0 are bit-identical to the default kernels (same sums in the same order); g_lie to rounding."""
+                                               (1, 68, 6, 10, 2), (1, 128, 40, 36, 1), (1, 64, 5, 40, 2), (1, 72, 4, 70, 1)])
+def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B, level):
+    """tuning "k2_de_v2" (linear_de.cuh).  Level 1: 8 x 8 FFMA flow build, lam-only reverse sweep, triple-product
+    bracket gradient - ys and g_y0 bit-identical to the default kernels (same sums in the same order), g_lie to
+    rounding.  Level 2: the flow build on the tensor pipe (3xTF32 split precision, mma.sync modelled by the emulator
+    with the documented fragment layout) - fp32-grade flows, everything inside the parity tolerance; n_basis > 36
+    (depth-3 sizes, several K tiles) keeps the default reverse path."""
     rng = np.random.default_rng(11)
     H, D = nb * bs, n_basis + 2  # one unused trailing logsig column
     lie = rng.normal(size=(nb, bs, bs, n_basis)) * (0.5 / np.sqrt(bs))
@@ -355,24 +359,49 @@ def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B):
     y0 = rng.normal(size=(B, H))
     g_ys = rng.normal(size=(B, T, H))
     ys0, gl0, gy0 = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
-    E.set_tuning("k2_de_v2", 1)
+    E.set_tuning("k2_de_v2", level)
     try:
         ys1, gl1, gy1 = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
     finally:
         E.set_tuning("k2_de_v2", 0)
-    assert np.array_equal(ys0, ys1)
-    assert np.array_equal(gy0, gy1)
+    if level == 1:
+        assert np.array_equal(ys0, ys1)
+        assert np.array_equal(gy0, gy1)
+    else:
+        assert rel_err(ys1, ys0) < 2e-6 and rel_err(gy1, gy0) < 2e-6
     assert rel_err(gl1, gl0) < 1e-5
     # and against fp64 autograd
     lie_t = torch.from_numpy(lie).requires_grad_(True)
+    y0_t = torch.from_numpy(y0).requires_grad_(True)
     flows = torch.einsum("nijl,btl->btnij", lie_t, torch.from_numpy(ls[..., 1:1 + n_basis])) + torch.eye(bs, dtype=torch.float64)
-    y = torch.from_numpy(y0)
+    y = y0_t
     out = [y]
     for t in range(1, T):
         y = torch.einsum("bnij,bnj->bni", flows[:, t], y.view(B, nb, bs)).reshape(B, H)
         out.append(y)
-    (torch.stack(out, 1) * torch.from_numpy(g_ys)).sum().backward()
+    ys_o = torch.stack(out, 1)
+    (ys_o * torch.from_numpy(g_ys)).sum().backward()
+    assert rel_err(ys1, ys_o.detach().numpy()) < TOL
+    assert rel_err(gy1, y0_t.grad.numpy()) < 5 * TOL
     assert rel_err(gl1, lie_t.grad.numpy()) < 5 * TOL
+
+
+def test_emu_tf32_split_flow_build_accuracy():
+    """3xTF32 flows against fp64: errors at the fp32 rounding level (a single-TF32 product would be ~5e-4 relative)."""
+    rng = np.random.default_rng(2)
+    nb, bs, T, n_basis, B = 1, 128, 3, 28, 2
+    lie = rng.normal(size=(nb, bs, bs, n_basis)) * 0.1
+    ls = rng.normal(size=(B, T, n_basis + 1)) * 0.3
+    y0 = np.zeros((B, bs))
+    y0[:, 5] = 1.0  # ys[:, 1] = column 5 of F_1: reads the flows back through the scan
+    want = np.einsum("ijl,bl->bij", lie[0], ls[:, 1, 1:]) + np.eye(bs)
+    E.set_tuning("k2_de_v2", 2)
+    try:
+        ys, _, _ = E.linear_scan(lie, ls, y0, nb, bs)
+    finally:
+        E.set_tuning("k2_de_v2", 0)
+    err = np.abs(ys[:, 1] - want[:, :, 5]).max()
+    assert err < 3e-7, err
 
 
 # ------------------------------------------------------------------------------------------ K2d

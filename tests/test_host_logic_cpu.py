@@ -114,9 +114,11 @@ def test_bench_autotune_decision():
     assert bench.decide_tuning({"k1": {"error": "x"}, "k3": {"parity": k3ok}}) == {"k1_tma": 0, "k3_fused": 0}
     assert bench.decide_tuning({}) == {"k1_tma": 0, "k3_fused": 0}
     # K2 workloads: one variant per family, same rule
-    de = {"k2de": {"parity": ok, "timing": t(default=10.9, v2=8.0)}}
+    de = {"k2de": {"parity": {"ok": True, "ok_by_variant": {"1": True, "2": True}}, "timing": t(default=10.9, v2=8.0, v2_tc=6.5)}}
+    assert bench.decide_tuning(de)["k2_de_v2"] == 2
+    de["k2de"]["parity"] = {"ok": False, "ok_by_variant": {"1": True, "2": False}}
     assert bench.decide_tuning(de)["k2_de_v2"] == 1
-    de["k2de"]["parity"] = bad
+    de["k2de"]["parity"] = {"ok": False, "ok_by_variant": {"1": False, "2": False}}
     assert bench.decide_tuning(de)["k2_de_v2"] == 0
     assert bench.decide_tuning({"k2": {"parity": ok, "timing": t(default_B32=1.0, fused_B32=0.99)}})["k2_fused_d"] == 0
 
