@@ -286,6 +286,134 @@ __global__ void __launch_bounds__(256) dlie_triple_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------- bracket gradient on the tensor pipe (3xTF32)
+// The same triple product as a GEMM whose left operand is formed on the fly: rows (i, j) of A[(i,j)][k] =
+// lam[k][i] * y[k][j] are built in registers (one multiply, then the hi / lo split), B[k][l] = logsig row k is split
+// once per staged chunk.  CTA tile as above (16 i x 32 j x all l <= 32), 8 warps x (2 i x 32 j) = 4 MMA row tiles of
+// 16 (i fixed, 16 consecutive j) x 4 column tiles of 8 basis elements; per k-step of 8 and warp 48 HMMA against
+// 16 multiplies + 32 conversions - the FFMA kernel above spends 56 FMAs per (i, j, k) instead of 4 ALU operations.
+constexpr int kTcYs = 40, kTcLs = 40;  // row strides (words) of the staged y / logsig chunks: = 8 (mod 32), conflict-free fragments
+
+__global__ void __launch_bounds__(256, 2) dlie_triple_tc_kernel(const float* __restrict__ lam, const float* __restrict__ ys,
+                                                                const float* __restrict__ logsig, float* __restrict__ part,
+                                                                int B, int T, int D, int H, int bs, int n_basis, int ksplit,
+                                                                int i_tiles, int j_tiles) {
+  constexpr int KC = 32, TI = 16, TJ = 32;
+  __shared__ __align__(16) float lam_s[KC][TI];
+  __shared__ __align__(16) float y_s[KC][kTcYs];
+  __shared__ __align__(16) uint32_t lsh[KC][kTcLs];
+  __shared__ __align__(16) uint32_t lsl[KC][kTcLs];
+  int bid = blockIdx.x;
+  const int ks = bid % ksplit; bid /= ksplit;
+  const int jt = bid % j_tiles; bid /= j_tiles;
+  const int it = bid % i_tiles; bid /= i_tiles;
+  const int blk = bid;
+  const int i0 = it * TI, j0 = jt * TJ;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const unsigned Tm1 = (unsigned)(T - 1);
+  const unsigned Ktot = (unsigned)B * Tm1;
+  const unsigned per = (Ktot + ksplit - 1) / ksplit;
+  const unsigned k_lo = min(Ktot, per * ks), k_hi = min(Ktot, k_lo + per);
+  float acc[4][4][4];  // [m-tile = 2 * ii + jh][n-tile][fragment]
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[a][b][r] = 0.f;
+  for (unsigned kc = k_lo; kc < k_hi; kc += KC) {
+    for (int e = threadIdx.x; e < KC * TI; e += 256) {
+      const int kk = e / TI, i = e - kk * TI;
+      const unsigned k = kc + kk;
+      float v = 0.f;
+      if (k < k_hi && i0 + i < bs) {
+        const unsigned b = k / Tm1, tt = 1 + (k - b * Tm1);
+        v = __ldg(lam + ((size_t)b * T + tt) * H + blk * bs + i0 + i);
+      }
+      lam_s[kk][i] = v;
+    }
+    for (int e = threadIdx.x; e < KC * TJ; e += 256) {
+      const int kk = e / TJ, j = e - kk * TJ;
+      const unsigned k = kc + kk;
+      float v = 0.f;
+      if (k < k_hi && j0 + j < bs) {
+        const unsigned b = k / Tm1, tt = 1 + (k - b * Tm1);
+        v = __ldg(ys + ((size_t)b * T + tt - 1) * H + blk * bs + j0 + j);
+      }
+      y_s[kk][j] = v;
+    }
+    for (int e = threadIdx.x; e < KC * 32; e += 256) {
+      const int kk = e >> 5, l = e & 31;
+      const unsigned k = kc + kk;
+      float v = 0.f;
+      if (k < k_hi && l < n_basis) {
+        const unsigned b = k / Tm1, tt = 1 + (k - b * Tm1);
+        v = __ldg(logsig + ((size_t)b * T + tt) * D + 1 + l);
+      }
+      const uint32_t hi = cvt_tf32(v);
+      lsh[kk][l] = hi;
+      lsl[kk][l] = cvt_tf32(v - __uint_as_float(hi));
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int kst = 0; kst < KC / 8; ++kst) {
+      const int ka = kst * 8 + t, kb = ka + 4;
+      uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        bh[nt][0] = lsh[ka][nt * 8 + g]; bh[nt][1] = lsh[kb][nt * 8 + g];
+        bl[nt][0] = lsl[ka][nt * 8 + g]; bl[nt][1] = lsl[kb][nt * 8 + g];
+      }
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        const float y00 = y_s[ka][16 * jh + g], y01 = y_s[ka][16 * jh + g + 8];
+        const float y10 = y_s[kb][16 * jh + g], y11 = y_s[kb][16 * jh + g + 8];
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+          const float la = lam_s[ka][2 * warp + ii], lb = lam_s[kb][2 * warp + ii];
+          const float a[4] = {la * y00, la * y01, lb * y10, lb * y11};
+          uint32_t ah[4], al[4];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            ah[r] = cvt_tf32(a[r]);
+            al[r] = cvt_tf32(a[r] - __uint_as_float(ah[r]));
+          }
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            mma_m16n8k8_tf32(acc[2 * ii + jh][nt], al, bh[nt]);
+            mma_m16n8k8_tf32(acc[2 * ii + jh][nt], ah, bl[nt]);
+            mma_m16n8k8_tf32(acc[2 * ii + jh][nt], ah, bh[nt]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const size_t n_out = (size_t)(H / bs) * bs * bs * n_basis;
+  float* out = part + (size_t)ks * n_out;
+#pragma unroll
+  for (int ii = 0; ii < 2; ++ii) {
+    const int i = i0 + 2 * warp + ii;
+    if (i >= bs) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int j = j0 + 16 * jh + g + 8 * half;
+        if (j >= bs) continue;
+        float* o = out + (((size_t)blk * bs + i) * bs + j) * n_basis;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int l = nt * 8 + 2 * t + c;
+            if (l < n_basis) o[l] = acc[2 * ii + jh][nt][2 * half + c];
+          }
+      }
+  }
+}
+
 template <int NBP>
 static inline void launch_dlie_triple(cudaStream_t st, int grid, const float* lam, const float* ys, const float* ls,
                                       float* part, int B, int T, int D, int H, int bs, int n_basis, int ksplit, int it,
@@ -295,10 +423,14 @@ static inline void launch_dlie_triple(cudaStream_t st, int grid, const float* la
 
 // returns false if n_basis is outside the compiled range
 static inline bool dlie_triple_dispatch(cudaStream_t st, const float* lam, const float* ys, const float* ls, float* part,
-                                        int B, int T, int D, int H, int bs, int n_basis, int ksplit) {
+                                        int B, int T, int D, int H, int bs, int n_basis, int ksplit, bool tensor) {
   if (T < 2 || (long long)B * (T - 1) >= (1ll << 31) - 64) return false;
   const int nb = H / bs, it = (bs + 15) / 16, jt = (bs + 31) / 32;
   const int grid = nb * it * jt * ksplit;
+  if (tensor && n_basis <= 32) {
+    dlie_triple_tc_kernel<<<grid, 256, 0, st>>>(lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt);
+    return true;
+  }
   const int nbp = (n_basis + 3) & ~3;
   switch (nbp) {
     case 4: launch_dlie_triple<4>(st, grid, lam, ys, ls, part, B, T, D, H, bs, n_basis, ksplit, it, jt); return true;

@@ -619,7 +619,8 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
   cudaStream_t cs = (cudaStream_t)stream;
   float* F = (float*)workspace;  // still holds the forward flows of the SAME (lie, logsig)
   const int H = nb * bs, N = H * bs;
-  if (tuning_value(kTuneK2DeV2) && de_v2_shape(bs, n_basis) && T >= 2) {
+  const int de_v2 = tuning_value(kTuneK2DeV2);
+  if (de_v2 && de_v2_shape(bs, n_basis) && T >= 2) {
     // reverse sweep stores lam_t only; dLie = sum lam_t (x) y_{t-1} (x) logsig_t from the small operands
     const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
     const size_t part_n = ((size_t)N * n_basis * kScanKsplit + 3) & ~(size_t)3;
@@ -628,7 +629,8 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
     if (scan_bwd_lam_dispatch(cs, F, g_ys, lam, g_y0, B, T, H, bs)) {
       st = (int)cudaGetLastError();
       if (st != 0) return st;
-      if (!dlie_triple_dispatch(cs, lam, ys, logsig, part, B, T, D, H, bs, n_basis, kScanKsplit)) return LNCDE_ERR_UNSUPPORTED;
+      if (!dlie_triple_dispatch(cs, lam, ys, logsig, part, B, T, D, H, bs, n_basis, kScanKsplit, de_v2 >= 2))
+        return LNCDE_ERR_UNSUPPORTED;
       st = (int)cudaGetLastError();
       if (st != 0) return st;
       reduce_partials_kernel<<<148 * 2, 256, 0, cs>>>(part, g_lie, N * n_basis, kScanKsplit);

@@ -310,8 +310,8 @@ def k2de_timing(reps=5):
     from lncde import _lib
 
     res = {"shape": "EigenWorms DE-LNCDE train step (loss + gradient), eager launches, B=32 (flows 3.1 GB); v2 = FFMA 8x8 "
-                    "flow build + lam-only reverse sweep + triple-product gradient, v2_tc = the same with the flow build on "
-                    "the tensor pipe (3xTF32)"}
+                    "flow build + lam-only reverse sweep + triple-product gradient, v2_tc = the same with the flow build and "
+                    "the bracket gradient on the tensor pipe (3xTF32)"}
     model, step = _de_step(32, 1499)
     for name, v in (("default", 0), ("v2", 1), ("v2_tc", 2)):
         _lib.set_tuning("k2_de_v2", v)
