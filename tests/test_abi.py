@@ -62,3 +62,37 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(_lib.LncdeError):
         calc_paths(torch.zeros(2, 10, 3), 4, 2)
+
+
+def test_new_entry_points_validate_before_launch(built_lib):
+    """K3n / K2d / K2 argument errors are reported by status on the host (no CUDA call is reached)."""
+    import numpy as np
+
+    L = built_lib
+    buf = np.zeros(1 << 16, np.float32)
+    p = ctypes.c_void_p(buf.ctypes.data + (-buf.ctypes.data) % 16)  # a 16-byte aligned non-NULL pointer
+    mis = ctypes.c_void_p(p.value + 4)
+    # lncde_nrde_fwd(stream, params, logsig, y0, rows, scale, ys, B, K, D, H, width, n_vf, n_steps)
+    assert L.lncde_nrde_fwd(None, None, p, p, p, p, p, 1, 4, 4, 8, 8, 2, 3) == -1            # NULL
+    assert L.lncde_nrde_fwd(None, p, p, p, p, p, p, 0, 4, 4, 8, 8, 2, 3) == -2               # B < 1
+    assert L.lncde_nrde_fwd(None, p, p, p, p, p, p, 1, 4, 1, 8, 8, 2, 3) == -2               # D < 2
+    assert L.lncde_nrde_fwd(None, p, p, p, p, p, p, 1, 4, 4, 8, 6, 2, 3) == -3               # width % 4 != 0
+    assert L.lncde_nrde_fwd(None, p, p, p, p, p, p, 1, 4, 4, 8, 8, 5, 3) == -3               # n_vf > 4
+    assert L.lncde_nrde_fwd(None, p, p, p, p, p, p, 1, 4, 4, 600, 8, 2, 3) == -3             # H > 512
+    assert L.lncde_nrde_fwd(None, mis, p, p, p, p, p, 1, 4, 4, 8, 8, 2, 3) == -5             # params not 16-byte aligned
+    assert L.lncde_nrde_param_count(64, 21, 64, 3) == 3 * 64 * 65 + 64 * 21 * 65
+    assert L.lncde_nrde_param_count(64, 21, 64, 0) == -1
+    need = L.lncde_nrde_bwd_workspace_bytes(2, 8, 3, 8, 2, 3)
+    assert need > 0 and L.lncde_nrde_bwd_workspace_bytes(2, 8, 3, 6, 2, 3) == 0
+    # lncde_nrde_bwd(stream, params, logsig, rows, scale, ys, g_ys, g_params, g_y0, B, K, D, H, width, n_vf, n_steps, ws, bytes)
+    assert L.lncde_nrde_bwd(None, p, p, p, p, p, p, p, p, 2, 4, 4, 8, 8, 2, 3, p, need - 1) == -4   # workspace too small
+    assert L.lncde_nrde_bwd(None, p, p, p, p, p, p, p, p, 2, 4, 4, 8, 8, 2, 3, None, need) == -1
+    assert L.lncde_nrde_bwd(None, p, p, p, p, p, p, p, p, 2, 4, 4, 8, 8, 2, 3, mis, need) == -5
+    # K2: shapes, workspace
+    assert L.lncde_linear_scan_fwd(None, p, p, p, p, 1, 4, 4, 2, 4, 9, p, 1 << 20) == -2       # n_basis > D - 1
+    assert L.lncde_linear_scan_fwd(None, p, p, p, p, 1, 4, 4, 2, 4, 3, p, 16) == -4            # workspace too small
+    assert L.lncde_linear_scan_workspace_bytes(2, 5, 1, 128, 28) > L.lncde_linear_scan_workspace_bytes(2, 5, 32, 4, 28)
+    # tuning keys
+    for key in (b"k1_tma", b"k3_fused", b"k2_fused_d", b"k1_grid_cap", b"k2_de_v2", b"k3_stream"):
+        assert L.lncde_get_tuning(key) >= 0
+    assert L.lncde_get_tuning(b"nope") == -3 and L.lncde_set_tuning(None, 1) == -1
