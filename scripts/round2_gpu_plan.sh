@@ -28,4 +28,10 @@ python bench.py --workload eigenworms_de --steps 2 --warmup 3 --no-cpu-baseline 
 ncu --set full --clock-control none --import-source on -k regex:'scan_|flow_build' -s 6 -c 4 \
     -o gpurun_out/r2_prof_k2 python bench.py --workload eigenworms_de --steps 2 --warmup 3 --no-cpu-baseline --no-graph \
     > gpurun_out/r2_ncu3.log 2>&1
+# tensor-pipe variant of the dense LNCDE (k2_de_v2 = 2): one capture of the 3xTF32 flow build and bracket gradient
+LNCDE_TUNE_K2_DE_V2=2 python bench.py --workload eigenworms_de --steps 2 --warmup 3 --no-cpu-baseline --no-graph --no-autotune \
+    > gpurun_out/r2_plain4.log 2>&1 &&
+LNCDE_TUNE_K2_DE_V2=2 ncu --set full --clock-control none --import-source on -k regex:'flow_build_tc|dlie_triple_tc|scan_bwd_tma_lam' \
+    -s 6 -c 3 -o gpurun_out/r2_prof_k2_tc python bench.py --workload eigenworms_de --steps 2 --warmup 3 --no-cpu-baseline \
+    --no-graph --no-autotune > gpurun_out/r2_ncu4.log 2>&1
 tail -3 gpurun_out/r2_pytest.log; head -c 1500 gpurun_out/r2_variants.json; echo; head -c 600 gpurun_out/r2_bench.json
