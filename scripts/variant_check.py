@@ -18,7 +18,7 @@ a fault or hang in a variant that has not been on hardware yet cannot take the c
   k3g: ``set_tuning("k3_stream", 1)`` (generic Log-NCDE kernels with streamed global-weight mat-vecs) - loss and
       gradients against the default generic kernels on PPG / toy dims, timings of both.
 
-    python scripts/variant_check.py [--no-timing] [--no-parity] [--only k1|k2|k3|k2de|k3g]
+    python scripts/variant_check.py [--no-timing] [--no-parity] [--no-oracle] [--only k1|k2|k3|k2de|k3g]
 """
 import json
 import os
@@ -47,7 +47,12 @@ def _persistent(fn):
 
 def parity():
     from lncde.data_dir.generate_paths import calc_paths
-    from oracle import paths
+
+    # --no-oracle (how bench.py's autotune calls this script): the variant is judged against the DEFAULT CUDA kernel
+    # only (bit-identity); the fp64 oracle is test infrastructure and is consulted from tests/ alone
+    use_oracle = "--no-oracle" not in sys.argv
+    if use_oracle:
+        from oracle import paths
 
     res = {"cases": 0, "bit_identical_to_classic": True, "persistent_bit_identical": True,
            "max_rel_err_vs_fp64_oracle": 0.0, "integer_kat_exact": True}
@@ -60,27 +65,29 @@ def parity():
             for s in (1, 4, 7, 12, 16, 100, 102, 500):
                 if s * C > 640:
                     continue
-                want = paths.calc_paths(x, s, depth, np.float64)
                 a = calc_paths(xd, s, depth, kernel="tma").cpu().numpy()
                 b = calc_paths(xd, s, depth, kernel="classic").cpu().numpy()
                 a2 = _persistent(lambda: calc_paths(xd, s, depth)).cpu().numpy()
                 res["cases"] += 1
-                res["integer_kat_exact"] &= bool(np.array_equal(a.astype(np.float64), want))
+                if use_oracle:
+                    want = paths.calc_paths(x, s, depth, np.float64)
+                    res["integer_kat_exact"] &= bool(np.array_equal(a.astype(np.float64), want))
                 res["bit_identical_to_classic"] &= bool(np.array_equal(a, b))
                 res["persistent_bit_identical"] &= bool(np.array_equal(a2, b))
     # float paths at the BASELINE shapes (short batch)
     for C, s, L in [(7, 12, 17984), (6, 12, 17984), (6, 16, 896), (7, 10, 4992), (4, 10, 4992), (7, 16, 896)]:
         x = np.cumsum(rng.normal(scale=0.05, size=(3, L, C)), axis=1).astype(np.float32)
         xd = torch.from_numpy(x).cuda()
-        want = paths.calc_paths(x, s, 2, np.float64)
         a = calc_paths(xd, s, 2, kernel="tma").cpu().numpy()
         b = calc_paths(xd, s, 2, kernel="classic").cpu().numpy()
         a2 = _persistent(lambda: calc_paths(xd, s, 2)).cpu().numpy()
         res["cases"] += 1
         res["bit_identical_to_classic"] &= bool(np.array_equal(a, b))
         res["persistent_bit_identical"] &= bool(np.array_equal(a2, b))
-        err = float(np.abs(a - want).max() / np.abs(want).max())
-        res["max_rel_err_vs_fp64_oracle"] = max(res["max_rel_err_vs_fp64_oracle"], err)
+        if use_oracle:
+            want = paths.calc_paths(x, s, 2, np.float64)
+            err = float(np.abs(a - want).max() / np.abs(want).max())
+            res["max_rel_err_vs_fp64_oracle"] = max(res["max_rel_err_vs_fp64_oracle"], err)
     res["ok"] = bool(res["integer_kat_exact"] and res["bit_identical_to_classic"]
                      and res["max_rel_err_vs_fp64_oracle"] < 1e-5)
     res["ok_by_variant"] = {"1": res["ok"], "2": bool(res["ok"] and res["persistent_bit_identical"])}
