@@ -203,7 +203,7 @@ def run_ours(args):
         families["log_ncde"] = ("k1", "k3g")  # shapes outside the specialised kernels: the generic solve kernels
     if not args.no_autotune and (WL["model"] in families):
         if rank == 0:
-            tuning, tune_report = autotune(families[WL["model"]])
+            tuning, tune_report = cached_autotune(families[WL["model"]], refresh=args.retune)
         if world > 1:
             box = [tuning]
             dist.broadcast_object_list(box, src=0)
@@ -461,6 +461,38 @@ def decide_tuning(rep, margin=0.98):
     return choice
 
 
+TUNE_CACHE = os.path.join(REPO, ".lncde_tune_cache.json")
+
+
+def cached_autotune(families, refresh=False):
+    """autotune() once per (GPU model, library build, kernel families): the 1 / 2 / 4 / 8-GPU runs of one session then
+    use the SAME kernels (scaling efficiency compares like with like) and only the first run pays for the check."""
+    from lncde import _build
+
+    try:
+        key = "|".join([torch.cuda.get_device_name(0), open(_build.STAMP).read().strip()[:16], ",".join(families)])
+    except OSError:
+        key = None
+    cache = {}
+    if key and not refresh and os.path.exists(TUNE_CACHE):
+        try:
+            cache = json.load(open(TUNE_CACHE))
+            if key in cache:
+                return cache[key]["tuning"], {"cached": True, "key": key, "report": cache[key]["report"]}
+        except (OSError, ValueError, KeyError, TypeError):
+            cache = {}
+    tuning, rep = autotune(families)
+    if key and not any("error" in (rep.get(f) or {}) for f in families):  # never pin a decision taken after a failed check
+        try:
+            cache[key] = {"tuning": tuning, "report": rep}
+            with open(TUNE_CACHE + ".tmp", "w") as fh:
+                json.dump(cache, fh)
+            os.replace(TUNE_CACHE + ".tmp", TUNE_CACHE)
+        except OSError:
+            pass
+    return tuning, rep
+
+
 def autotune(families=("k1", "k3")):
     """Pick among kernel variants that compute the same result (lncde.set_tuning): scripts/variant_check.py runs
     each variant in a SUBPROCESS (a variant that has never been on this hardware cannot take the bench down),
@@ -611,6 +643,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the contract): the workload's batch per GPU; strong: that batch split over the GPUs")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
+    ap.add_argument("--retune", action="store_true", help="ignore the cached autotune decision (.lncde_tune_cache.json)")
     ap.add_argument("--no-autotune", action="store_true",
                     help="keep the default kernels (skip the subprocess that checks and times the variants)")
     args = ap.parse_args()

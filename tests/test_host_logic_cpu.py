@@ -165,3 +165,32 @@ def test_nrde_mirror_layout_and_errors(built_lib):
     if not torch.cuda.is_available():
         with pytest.raises(_lib.LncdeError):
             model((torch.zeros(2, 44), torch.zeros(2, 11, 22), torch.zeros(2, 6)))
+
+
+def test_bench_autotune_cache(monkeypatch, tmp_path):
+    """One autotune per (GPU model, library build, families): later runs of a session (N = 2, 4, 8) reuse the decision;
+    a decision taken after a failed variant check is never cached."""
+    import importlib.util
+    import os
+
+    import torch
+
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    calls = []
+    good = ({"k1_tma": 1, "k3_fused": 0}, {"k1": {"parity": {"ok": True}}, "k3": {"parity": {"ok": True}}})
+    monkeypatch.setattr(bench, "autotune", lambda fam: (calls.append(fam) or good))
+    monkeypatch.setattr(torch.cuda, "get_device_name", lambda i=0: "TEST GPU")
+    monkeypatch.setattr(bench, "TUNE_CACHE", str(tmp_path / "cache.json"))
+    t1, r1 = bench.cached_autotune(("k1", "k3"))
+    t2, r2 = bench.cached_autotune(("k1", "k3"))
+    assert t1 == t2 == good[0] and "cached" not in r1 and r2["cached"] and len(calls) == 1
+    bench.cached_autotune(("k1", "k3g"))                      # other families: own entry
+    bench.cached_autotune(("k1", "k3"), refresh=True)         # --retune
+    assert len(calls) == 3
+    os.remove(bench.TUNE_CACHE)
+    monkeypatch.setattr(bench, "autotune", lambda fam: ({"k1_tma": 0, "k3_fused": 0}, {"k1": {"error": "boom"}, "k3": {}}))
+    bench.cached_autotune(("k1", "k3"))
+    assert not os.path.exists(bench.TUNE_CACHE)
