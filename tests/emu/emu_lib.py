@@ -46,6 +46,7 @@ def lib():
         _lib.lncde_nrde_bwd_workspace_bytes.argtypes = [i, i, i, i, i, i]
         _lib.lncde_nrde_bwd_workspace_bytes.restype = sz
         _lib.lncde_nrde_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, sz]
+        _lib.emu_set_schedule.argtypes = [i, u, i]
         _lib.emu_bulk_copies.restype = C.c_long
         _lib.emu_guarded_alloc.restype = C.c_void_p
         _lib.emu_guarded_alloc.argtypes = [C.c_size_t, C.c_int, C.c_int]
@@ -62,6 +63,12 @@ def _with_tuning(key, value, fn):
         return fn()
     finally:
         set_tuning(key, 0)
+
+
+def set_schedule(mode="ascending", seed=1, blocks_reversed=False):
+    """Order in which the emulator runs the threads of a CTA between synchronisation points ("ascending",
+    "descending", "random", "warp_greedy", "warp_greedy_desc" - one warp at a time runs as far as it can) and the CTAs of a grid.  Race-free kernels give identical results under every schedule."""
+    lib().emu_set_schedule({"ascending": 0, "descending": 1, "random": 2, "warp_greedy": 3, "warp_greedy_desc": 4}[mode], int(seed), 1 if blocks_reversed else 0)
 
 
 def bulk_copies():

@@ -87,6 +87,14 @@ struct Block {
 };
 
 Block* g_blk = nullptr;
+// Schedule of the fibers inside a sweep (test hook emu_set_schedule): 0 = ascending thread index, 1 = descending,
+// 2 = a fresh pseudo-random permutation per sweep, 3 / 4 = warp-greedy (warps ascending / descending, each running
+// until none of its lanes can continue).  A kernel that is free of shared-memory races between barriers
+// gives the same result under every schedule; a missing barrier shows up as an order-dependent result.
+int g_sched_mode = 0;
+unsigned g_sched_state = 1;
+bool g_blocks_reversed = false;
+std::vector<int> g_perm;
 char* g_stacks = nullptr;
 size_t g_stack_cap = 0;
 std::map<const void*, int> g_max_dyn_smem;
@@ -159,25 +167,60 @@ void run_block(Block& b) {
     f.sp = sp;
   }
   b.live = b.n;
+  if ((int)g_perm.size() != b.n) {
+    g_perm.resize(b.n);
+    for (int i = 0; i < b.n; ++i) g_perm[i] = i;
+  }
+  // one fiber segment: resume thread t until it blocks or exits
+  auto run_one = [&](int t) {
+    b.fib[t].wait = RUN;
+    set_thread(b, t);
+    emu_switch(&b.sched_sp, b.fib[t].sp);
+    if (b.fib[t].wait == DONE) {
+      b.live--;
+      // exited threads no longer count towards barriers / warp collectives
+      if (b.bar_arrived > 0 && b.bar_arrived == b.live) {
+        b.bar_arrived = 0;
+        b.bar_gen++;
+      }
+      Warp& w = b.warps[t >> 5];
+      const unsigned need = w.mask & live_mask(b, t >> 5);
+      if (w.arrived != 0 && (w.arrived & need) == need) complete_warp(w);
+    }
+  };
   while (b.live > 0) {
     bool progress = false;
-    for (int t = 0; t < b.n; ++t) {
-      if (!runnable(b, t)) continue;
-      b.fib[t].wait = RUN;
-      set_thread(b, t);
-      emu_switch(&b.sched_sp, b.fib[t].sp);
-      progress = true;
-      if (b.fib[t].wait == DONE) {
-        b.live--;
-        // exited threads no longer count towards barriers / warp collectives
-        if (b.bar_arrived > 0 && b.bar_arrived == b.live) {
-          b.bar_arrived = 0;
-          b.bar_gen++;
+    if (g_sched_mode >= 3) {
+      // warp-greedy: each warp in turn runs for as long as any of its lanes can (maximal skew between warps:
+      // a warp reaches the next block barrier before the others have left the previous phase)
+      const int nw = (b.n + 31) / 32;
+      for (int k = 0; k < nw; ++k) {
+        const int w = g_sched_mode == 3 ? k : nw - 1 - k;
+        bool again = true;
+        while (again) {
+          again = false;
+          for (int l = 0; l < 32; ++l) {
+            const int t = w * 32 + l;
+            if (t >= b.n || !runnable(b, t)) continue;
+            run_one(t);
+            again = progress = true;
+          }
         }
-        Warp& w = b.warps[t >> 5];
-        const unsigned need = w.mask & live_mask(b, t >> 5);
-        if (w.arrived != 0 && (w.arrived & need) == need) complete_warp(w);
       }
+      if (!progress) die("deadlock: no runnable thread (mismatched __syncthreads / collective / mbarrier wait)");
+      continue;
+    }
+    if (g_sched_mode == 2) {  // Fisher-Yates with a small LCG: reproducible for a given seed
+      for (int i = b.n - 1; i > 0; --i) {
+        g_sched_state = g_sched_state * 1664525u + 1013904223u;
+        std::swap(g_perm[i], g_perm[(g_sched_state >> 8) % (unsigned)(i + 1)]);
+      }
+    }
+    for (int k = 0; k < b.n; ++k) {
+      const int t = g_sched_mode == 0 ? k : g_sched_mode == 1 ? b.n - 1 - k : g_perm[k];
+      if (!runnable(b, t)) continue;
+      run_one(t);
+      progress = true;
     }
     if (!progress) die("deadlock: no runnable thread (mismatched __syncthreads / collective / mbarrier wait)");
   }
@@ -327,9 +370,11 @@ void launch(const void* func, dim3 grid, dim3 block, size_t smem, const std::fun
   g_gridDim = {grid.x, grid.y, grid.z};
   Block* saved = g_blk;
   g_blk = &b;
-  for (unsigned z = 0; z < grid.z; ++z)
-    for (unsigned y = 0; y < grid.y; ++y)
-      for (unsigned x = 0; x < grid.x; ++x) {
+  for (unsigned zz = 0; zz < grid.z; ++zz)
+    for (unsigned yy = 0; yy < grid.y; ++yy)
+      for (unsigned xx = 0; xx < grid.x; ++xx) {
+        const unsigned x = g_blocks_reversed ? grid.x - 1 - xx : xx, y = g_blocks_reversed ? grid.y - 1 - yy : yy,
+                       z = g_blocks_reversed ? grid.z - 1 - zz : zz;
         g_blockIdx = {x, y, z};
         std::memset(base, kCanaryByte, kCanary);
         std::memset(win, 0xFF, region + span - win);  // uninitialised shared memory reads as NaN
@@ -382,6 +427,26 @@ void* emu_guarded_alloc(size_t bytes, int tight_end, int start_mod16) {
   }
   std::memset(lo, 0xFF, span);
   return p;
+}
+// test hook: order in which the threads of a CTA (mode 0 ascending, 1 descending, 2 random with `seed`) and the CTAs
+// of a grid (reversed != 0: last block first) are run
+void emu_set_schedule(int mode, unsigned seed, int blocks_reversed) {
+  emu::g_sched_mode = mode;
+  emu::g_sched_state = seed ? seed : 1u;
+  emu::g_blocks_reversed = blocks_reversed != 0;
+  emu::g_perm.clear();
+}
+// self-test of the schedule hook: every thread publishes a value in shared memory and reads its neighbour's, with or
+// without the barrier in between - without it the output depends on the order the threads run in
+void emu_selftest_race(float* out, int n, int with_barrier) {
+  const std::function<void()> body = [=]() {
+    float* sm = (float*)emu::dyn_smem();
+    const int t = (int)emu::g_threadIdx.x;
+    sm[t] = (float)(t + 1);
+    if (with_barrier) emu::sync_threads();
+    out[t] = sm[(t + 1) % n];
+  };
+  emu::launch((const void*)&emu_selftest_race, dim3(1), dim3(n), (size_t)n * sizeof(float), body);
 }
 // test hook: number of bulk (TMA) copies issued since the last call
 long emu_bulk_copies(void) {
