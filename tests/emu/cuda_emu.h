@@ -71,6 +71,12 @@ void mbar_expect_tx(void* bar, unsigned bytes);
 void mbar_complete_tx(void* bar, unsigned bytes);
 void mbar_wait(void* bar, unsigned parity);
 void check_bulk(const void* smem_ptr, const void* gptr, unsigned bytes, const char* what);
+// asynchronous copies: delivered at issue (eager) or at the consumer's wait (lazy), see emu_set_async_mode
+void async_load(void* smem_dst, const void* gsrc, unsigned bytes, void* bar);
+void async_store(void* gdst, const void* smem_src, unsigned bytes);
+void async_store_wait();
+void cp_async(void* smem_dst, const void* gsrc, unsigned bytes);
+void cp_async_wait();
 bool in_dyn_smem(const void* p, size_t bytes);
 
 template <class T>

@@ -71,6 +71,11 @@ def set_schedule(mode="ascending", seed=1, blocks_reversed=False):
     lib().emu_set_schedule({"ascending": 0, "descending": 1, "random": 2, "warp_greedy": 3, "warp_greedy_desc": 4}[mode], int(seed), 1 if blocks_reversed else 0)
 
 
+def set_async_mode(lazy: bool):
+    """Asynchronous copies deliver at issue (False, default) or at the wait the programming model requires (True)."""
+    lib().emu_set_async_mode(1 if lazy else 0)
+
+
 def bulk_copies():
     """Bulk (TMA) copies issued by the emulated kernels since the last call."""
     return lib().emu_bulk_copies()

@@ -50,12 +50,21 @@ constexpr unsigned char kCanaryByte = 0xA5;
 
 enum Wait { RUN = 0, BAR, WARP, MBAR, DONE };
 
+struct PendingCopy {
+  void* dst;
+  const void* src;
+  unsigned bytes;
+  void* bar;  // bulk loads: the mbarrier that counts the bytes
+};
+
 struct Fiber {
   void* sp = nullptr;
   Wait wait = RUN;
   long gen = 0;        // generation being waited for (BAR / WARP)
   void* mbar = nullptr;
   unsigned parity = 0;
+  std::vector<PendingCopy> stores;  // lazy mode: bulk stores not yet waited for (cp.async.bulk.wait_group.read)
+  std::vector<PendingCopy> cps;     // lazy mode: cp.async copies not yet waited for (cp.async.wait_group)
 };
 
 struct Warp {
@@ -80,6 +89,7 @@ struct Block {
   int bar_arrived = 0;
   long bar_gen = 0;
   std::map<void*, MBar> mbars;
+  std::vector<PendingCopy> loads;   // lazy mode: bulk loads whose data has not been delivered yet
   unsigned char* smem_raw = nullptr;
   size_t smem_bytes = 0;
   const std::function<void()>* body = nullptr;
@@ -91,6 +101,12 @@ Block* g_blk = nullptr;
 // 2 = a fresh pseudo-random permutation per sweep, 3 / 4 = warp-greedy (warps ascending / descending, each running
 // until none of its lanes can continue).  A kernel that is free of shared-memory races between barriers
 // gives the same result under every schedule; a missing barrier shows up as an order-dependent result.
+// Asynchronous copies (test hook emu_set_async_mode).  Eager (default): the data moves when the copy is issued - the
+// earliest the hardware may do it (exposes a destination or source that is still in use).  Lazy: the data moves when
+// the consumer performs the wait the programming model requires (mbarrier wait for bulk loads, wait_group.read for
+// bulk stores, cp.async.wait_group for cp.async) - the latest the hardware may do it (exposes a missing or misplaced
+// wait: the reader finds the NaN fill of uninitialised shared memory).  A correct kernel is bit-identical under both.
+bool g_lazy_async = false;
 int g_sched_mode = 0;
 unsigned g_sched_state = 1;
 bool g_blocks_reversed = false;
@@ -121,6 +137,10 @@ void yield() {
 void trampoline() {
   Block& b = *g_blk;
   (*b.body)();
+  if (!b.fib[b.cur].stores.empty())
+    die("thread exits with bulk stores it never waited for (cp.async.bulk.wait_group.read): shared memory may be "
+        "released while the copy engine still reads it");
+  if (!b.fib[b.cur].cps.empty()) die("thread exits with cp.async copies it never waited for");
   b.fib[b.cur].wait = DONE;
   emu_switch(&b.fib[b.cur].sp, b.sched_sp);
   std::abort();  // a finished fiber is never resumed
@@ -307,12 +327,51 @@ void mbar_wait(void* bar, unsigned parity) {
   Block& b = *g_blk;
   auto it = b.mbars.find(bar);
   if (it == b.mbars.end()) die("mbarrier.try_wait on an uninitialised barrier");
+  // lazy mode: the bytes counted on this barrier arrive now, at the wait
+  for (size_t i = 0; i < b.loads.size();) {
+    if (b.loads[i].bar == bar) {
+      const PendingCopy c = b.loads[i];
+      b.loads.erase(b.loads.begin() + i);
+      std::memcpy(c.dst, c.src, c.bytes);
+      mbar_complete_tx(bar, c.bytes);
+    } else {
+      ++i;
+    }
+  }
   if (it->second.phase != (parity & 1u)) return;
   Fiber& f = b.fib[b.cur];
   f.wait = MBAR;
   f.mbar = bar;
   f.parity = parity & 1u;
   yield();
+}
+void async_load(void* smem_dst, const void* gsrc, unsigned bytes, void* bar) {
+  bool waited_for = false;  // a consumer already blocked on this barrier: "its wait" is now
+  for (const Fiber& f : g_blk->fib) waited_for = waited_for || (f.wait == MBAR && f.mbar == bar);
+  if (g_lazy_async && !waited_for) {
+    g_blk->loads.push_back({smem_dst, gsrc, bytes, bar});
+  } else {
+    std::memcpy(smem_dst, gsrc, bytes);
+    mbar_complete_tx(bar, bytes);
+  }
+}
+void async_store(void* gdst, const void* smem_src, unsigned bytes) {
+  if (g_lazy_async) g_blk->fib[g_blk->cur].stores.push_back({gdst, smem_src, bytes, nullptr});
+  else std::memcpy(gdst, smem_src, bytes);
+}
+void async_store_wait() {
+  Fiber& f = g_blk->fib[g_blk->cur];
+  for (const PendingCopy& c : f.stores) std::memcpy(c.dst, c.src, c.bytes);
+  f.stores.clear();
+}
+void cp_async(void* smem_dst, const void* gsrc, unsigned bytes) {
+  if (g_lazy_async) g_blk->fib[g_blk->cur].cps.push_back({smem_dst, gsrc, bytes, nullptr});
+  else std::memcpy(smem_dst, gsrc, bytes);
+}
+void cp_async_wait() {
+  Fiber& f = g_blk->fib[g_blk->cur];
+  for (const PendingCopy& c : f.cps) std::memcpy(c.dst, c.src, c.bytes);
+  f.cps.clear();
 }
 long g_bulk_copies = 0;
 void check_bulk(const void* smem_ptr, const void* gptr, unsigned bytes, const char* what) {
@@ -380,6 +439,11 @@ void launch(const void* func, dim3 grid, dim3 block, size_t smem, const std::fun
         std::memset(win, 0xFF, region + span - win);  // uninitialised shared memory reads as NaN
         b.bar_arrived = 0;
         b.mbars.clear();
+        b.loads.clear();
+        for (auto& f : b.fib) {
+          f.stores.clear();
+          f.cps.clear();
+        }
         for (auto& w : b.warps) w = Warp();
         run_block(b);
         for (size_t i = 0; i < kCanary; ++i)
@@ -435,6 +499,22 @@ void emu_set_schedule(int mode, unsigned seed, int blocks_reversed) {
   emu::g_sched_state = seed ? seed : 1u;
   emu::g_blocks_reversed = blocks_reversed != 0;
   emu::g_perm.clear();
+}
+// test hook: 0 = asynchronous copies deliver at issue (default), 1 = at the consumer's wait
+void emu_set_async_mode(int lazy) { emu::g_lazy_async = lazy != 0; }
+// self-test of the lazy mode: one thread bulk-loads 16 bytes and reads them with or without the mbarrier wait
+void emu_selftest_async(const float* src16, float* out, int with_wait) {
+  const std::function<void()> body = [=]() {
+    unsigned char* sm = (unsigned char*)emu::dyn_smem();
+    unsigned long long* bar = (unsigned long long*)sm;
+    float* dst = (float*)(sm + 16);
+    emu::mbar_init(bar, 1);
+    emu::mbar_expect_tx(bar, 16);
+    emu::async_load(dst, src16, 16, bar);
+    if (with_wait) emu::mbar_wait(bar, 0);
+    out[0] = dst[2];
+  };
+  emu::launch((const void*)&emu_selftest_async, dim3(1), dim3(1), 64, body);
 }
 // self-test of the schedule hook: every thread publishes a value in shared memory and reads its neighbour's, with or
 // without the barrier in between - without it the output depends on the order the threads run in

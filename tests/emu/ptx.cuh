@@ -1,5 +1,5 @@
 // Host-emulator counterpart of log-neural-cdes_b200/csrc/ptx.cuh (same names, same contracts).
-// Asynchronous copies complete at issue; the mbarrier bookkeeping (expect_tx / complete_tx / phase
+// Asynchronous copies complete at issue or, in the emulator's lazy mode, at the consumer's wait; the mbarrier bookkeeping (expect_tx / complete_tx / phase
 // parity) and the alignment + size rules of the bulk copies are modelled and checked.
 #pragma once
 #include <cstdint>
@@ -16,9 +16,9 @@ inline float4 ld_stream4(const float4* p) {
   return *p;
 }
 
-inline void cp_async4(float* smem_dst, const float* gsrc) { *smem_dst = *gsrc; }
+inline void cp_async4(float* smem_dst, const float* gsrc) { emu::cp_async(smem_dst, gsrc, 4); }
 inline void cp_async_commit() {}
-inline void cp_async_wait_all() {}
+inline void cp_async_wait_all() { emu::cp_async_wait(); }
 
 inline void mbar_init(unsigned long long* bar, unsigned count) { emu::mbar_init(bar, count); }
 inline void fence_mbar_init() {}
@@ -26,15 +26,14 @@ inline void mbar_expect_tx(unsigned long long* bar, unsigned bytes) { emu::mbar_
 inline void mbar_wait(unsigned long long* bar, unsigned parity) { emu::mbar_wait(bar, parity); }
 inline void tma_load_1d(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
   emu::check_bulk(smem_dst, gsrc, bytes, "cp.async.bulk global->shared");
-  std::memcpy(smem_dst, gsrc, bytes);
-  emu::mbar_complete_tx(bar, bytes);
+  emu::async_load(smem_dst, gsrc, bytes, bar);
 }
 inline void tma_store_1d(void* gdst, const void* smem_src, unsigned bytes) {
   emu::check_bulk(smem_src, gdst, bytes, "cp.async.bulk shared->global");
-  std::memcpy(gdst, smem_src, bytes);
+  emu::async_store(gdst, smem_src, bytes);
 }
 inline void tma_store_commit() {}
-inline void tma_store_wait_read() {}
+inline void tma_store_wait_read() { emu::async_store_wait(); }
 inline void fence_async_proxy() {}
 
 // TF32: keep 10 mantissa bits, round to nearest with ties away from zero (cvt.rna)

@@ -163,3 +163,77 @@ def test_nrde_kernels_schedule_independent(case):
     flat = ON.flatten_params(ON.init_params(H, logsig.shape[2] - 1, width, n_vf, seed=3, dtype=torch.float64)).numpy()
     y0, g_ys = rng.normal(size=(B, H)) * 0.5, rng.normal(size=(B, len(grid), H))
     _under_schedules(lambda: E.nrde_fwd_bwd(flat, logsig, y0, rows, sc, (H, width, n_vf), g_ys))
+
+
+# ---------------------------------------------------------------------------------------------- asynchronous copies
+def test_lazy_async_mode_detects_a_missing_wait():
+    L = E.lib()
+    L.emu_selftest_async.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    src = np.zeros(8, np.float32)
+    off = (-src.ctypes.data) % 16 // 4
+    src[off : off + 4] = [1.0, 2.0, 3.0, 4.0]
+    out = np.zeros(1, np.float32)
+    res = {}
+    try:
+        for lazy in (False, True):
+            E.set_async_mode(lazy)
+            for wait in (1, 0):
+                L.emu_selftest_async(src.ctypes.data + 4 * off, out.ctypes.data, wait)
+                res[(lazy, wait)] = float(out[0])
+    finally:
+        E.set_async_mode(False)
+    assert res[(False, 1)] == res[(True, 1)] == 3.0      # with the wait: right in both modes
+    assert res[(False, 0)] == 3.0 and np.isnan(res[(True, 0)])   # without it: only the lazy mode shows the bug
+
+
+def _under_async_modes(fn):
+    E.set_async_mode(False)
+    ref = fn()
+    try:
+        E.set_async_mode(True)
+        for sched in (("ascending", 1, False), ("descending", 1, False), ("warp_greedy_desc", 1, True)):
+            E.set_schedule(*sched)
+            got = fn()
+            for a, b in zip(ref, got):
+                assert (a is None and b is None) or np.array_equal(a, b, equal_nan=True), sched
+    finally:
+        E.set_async_mode(False)
+        E.set_schedule("ascending")
+
+
+@pytest.mark.parametrize("tma", [True, 2])
+def test_logsig_tma_kernels_late_delivery(tma):
+    """K1 with bulk-copy staging: data delivered only at the mbarrier wait, result rows leaving shared memory only at
+    wait_group.read (persistent form: the staging buffer is reused for the next tile right after that wait)."""
+    rng = np.random.default_rng(0)
+    x = np.cumsum(rng.normal(scale=0.3, size=(3, 400, 7)), axis=1).astype(np.float32)
+    if tma == 2:
+        E.set_tuning("k1_grid_cap", 2)
+    try:
+        _under_async_modes(lambda: (E.calc_paths(x, 12, 2, tma=tma), E.calc_paths(x[:, :, :6], 4, 2, tma=tma)))
+    finally:
+        E.set_tuning("k1_grid_cap", 0)
+
+
+@pytest.mark.parametrize("level", [0, 1])
+def test_dense_scan_tma_rings_late_delivery(level):
+    rng = np.random.default_rng(3)
+    nb, bs, T, n_basis, B = 1, 64, 11, 6, 2
+    lie = rng.normal(size=(nb, bs, bs, n_basis)) * (0.5 / np.sqrt(bs))
+    ls = rng.normal(size=(B, T, n_basis + 1)) * 0.2
+    y0, g_ys = rng.normal(size=(B, bs)), rng.normal(size=(B, T, bs))
+    E.set_tuning("k2_de_v2", level)
+    try:
+        _under_async_modes(lambda: E.linear_scan(lie, ls, y0, nb, bs, g_ys))
+    finally:
+        E.set_tuning("k2_de_v2", 0)
+
+
+@pytest.mark.parametrize("fused", [0, 2])
+def test_saved_adjoint_cp_async_prefetch_late_delivery(fused):
+    flat, logsig, y0, rows, sc, g_ys = _solve_setup(1, 48, 7, 12, 2, 128, 32, 2, 0.26, 3.0)
+    E.set_tuning("k3_fused", fused)
+    try:
+        _under_async_modes(lambda: E.logncde_fwd_bwd(flat, logsig, y0, rows, sc, (128, 7, 32, 2, 2), g_ys))
+    finally:
+        E.set_tuning("k3_fused", 0)
