@@ -77,7 +77,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             units.append(dst)
     units.append(os.path.join(HERE, "emu_runtime.cc"))
     cuda_inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
-    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-w", "-DLNCDE_EMU=1", "-include", os.path.join(HERE, "cuda_emu.h"),
+    # -fsanitize=alignment: every dereference of a float4 / float2 / 64-bit pointer the kernels form by reinterpret_cast
+    # is checked against the type's alignment (a misaligned 128-bit access is a fault on the GPU, silent on x86);
+    # trap-on-error keeps the library free of a sanitizer runtime - emu_runtime.cc turns the trap into a message
+    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-w", "-fsanitize=alignment", "-fsanitize-undefined-trap-on-error",
+             "-DLNCDE_EMU=1", "-include", os.path.join(HERE, "cuda_emu.h"),
              "-I", HERE, "-I", src_dir, "-I", os.path.join(REPO, "include"), "-I", cuda_inc]
     procs, objs = [], []
     for u in units:

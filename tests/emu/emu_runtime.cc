@@ -457,6 +457,16 @@ void launch(const void* func, dim3 grid, dim3 block, size_t smem, const std::fun
 
 // ---- the cudart entry points used by the host wrappers ----------------------------------------
 namespace {
+void on_ill(int) {
+  static const char msg[] = "cuda-emu: misaligned vector access (float2 / float4 / 64-bit dereference of an address that is "
+                            "not a multiple of the type's alignment) - a fault on the GPU\n";
+  ssize_t r = write(2, msg, sizeof(msg) - 1);
+  (void)r;
+  _exit(135);
+}
+struct InstallTrapHandler {
+  InstallTrapHandler() { signal(SIGILL, on_ill); }
+} g_install_trap_handler;
 void on_segv(int) {
   static const char msg[] = "cuda-emu: memory access outside a guarded allocation (out-of-bounds global or shared access)\n";
   ssize_t r = write(2, msg, sizeof(msg) - 1);
@@ -502,6 +512,11 @@ void emu_set_schedule(int mode, unsigned seed, int blocks_reversed) {
 }
 // test hook: 0 = asynchronous copies deliver at issue (default), 1 = at the consumer's wait
 void emu_set_async_mode(int lazy) { emu::g_lazy_async = lazy != 0; }
+// self-test of the alignment check: dereference a float4 at base + offset_floats
+float emu_selftest_align(const float* base, int offset_floats) {
+  const float4 v = *reinterpret_cast<const float4*>(base + offset_floats);
+  return v.x + v.w;
+}
 // self-test of the lazy mode: one thread bulk-loads 16 bytes and reads them with or without the mbarrier wait
 void emu_selftest_async(const float* src16, float* out, int with_wait) {
   const std::function<void()> body = [=]() {

@@ -237,3 +237,29 @@ def test_saved_adjoint_cp_async_prefetch_late_delivery(fused):
         _under_async_modes(lambda: E.logncde_fwd_bwd(flat, logsig, y0, rows, sc, (128, 7, 32, 2, 2), g_ys))
     finally:
         E.set_tuning("k3_fused", 0)
+
+
+# ---------------------------------------------------------------------------------------------- alignment
+def test_emulator_traps_misaligned_vector_access():
+    """The emulated kernels are compiled with -fsanitize=alignment (tests/emu/build_emu.py): a float4 / float2 / 64-bit
+    dereference of a misaligned address - a fault on the GPU, silent on x86 - ends the process.  Checked in a
+    subprocess; every other emulator test in the suite runs under the same check."""
+    import subprocess
+    import textwrap
+
+    code = textwrap.dedent(f'''
+        import sys, ctypes as C, numpy as np
+        sys.path.insert(0, {os.path.join(HERE, "emu")!r})
+        import emu_lib as E
+        L = E.lib()
+        L.emu_selftest_align.argtypes = [C.c_void_p, C.c_int]
+        L.emu_selftest_align.restype = C.c_float
+        a = np.arange(16, dtype=np.float32)
+        off = (-a.ctypes.data) % 16 // 4
+        print("aligned", L.emu_selftest_align(a.ctypes.data, off)); sys.stdout.flush()
+        print("misaligned", L.emu_selftest_align(a.ctypes.data, off + int(sys.argv[1])))
+    ''')
+    ok = subprocess.run([sys.executable, "-c", code, "0"], capture_output=True, text=True, timeout=120)
+    assert ok.returncode == 0 and "misaligned 3.0" in ok.stdout
+    bad = subprocess.run([sys.executable, "-c", code, "1"], capture_output=True, text=True, timeout=120)
+    assert bad.returncode == 135 and "misaligned vector access" in bad.stderr and "aligned 3.0" in bad.stdout
