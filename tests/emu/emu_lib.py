@@ -95,13 +95,29 @@ def _p(a):
 
 
 def _aligned(nbytes, align=256):
-    raw = np.zeros(nbytes + align, np.uint8)
+    """Workspace as torch.empty hands it out on the GPU: aligned, contents undefined - filled with the NaN pattern so
+    that a kernel reading workspace it has not written shows up in the result."""
+    raw = np.full(nbytes + align, 0xFF, np.uint8)
     off = (-raw.ctypes.data) % align
     return raw[off : off + nbytes]
 
 
 def f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _dev(a, dtype=np.float32):
+    """Copy of `a` in a "device" allocation that ENDS at a guard page (reads or writes past the end fault)."""
+    a = np.ascontiguousarray(a, dtype=dtype)
+    g = guarded(a.shape, dtype)
+    g[...] = a
+    return g
+
+
+def _dev_out(shape, dtype=np.float32):
+    g = guarded(shape, dtype)
+    g.view(np.uint8)[...] = 0xFF  # NaN pattern: an element the kernel does not write is visible
+    return g
 
 
 def calc_paths(x, stepsize, depth, compat=True, chunk=None, tma=False, misalign=0, tight_end=True):
@@ -134,43 +150,47 @@ def logncde_fwd_bwd(flat, logsig, y0, rows, scale, dims, g_ys, train=True):
     """lncde_logncde_fwd (+ bwd with the saved-forward workspace when train)."""
     L = lib()
     H, Cn, width, n_hidden, depth = dims
-    flat, logsig, y0, scale = f32(flat), f32(logsig), f32(y0), f32(scale)
-    rows = np.ascontiguousarray(rows, np.int32)
+    flat, logsig, y0, scale = _dev(flat), _dev(logsig), _dev(y0), _dev(scale)
+    rows = _dev(rows, np.int32)
     B, K, D = logsig.shape
     n_steps = rows.shape[0]  # rows / scale are [n_steps, 2]
-    ys = np.full((B, n_steps + 1, H), np.nan, np.float32)
+    ys = _dev_out((B, n_steps + 1, H))
     nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, Cn, width, n_hidden, depth, n_steps) if train else 0
-    ws = _aligned(nbytes) if train else None
+    ws = None
+    if train:
+        ws = guarded((nbytes,), np.uint8)
+        ws[...] = 0xFF
     st = L.lncde_logncde_fwd(None, _p(flat), _p(logsig), _p(y0), _p(rows), _p(scale), _p(ys), B, K, D, H, Cn, width,
                              n_hidden, depth, n_steps, _p(ws), nbytes)
     assert st == 0, st
     if not train:
-        return ys, None, None
-    g_ys = f32(g_ys)
-    g_params = np.full(flat.shape, np.nan, np.float32)
-    g_y0 = np.full((B, H), np.nan, np.float32)
+        return ys.copy(), None, None
+    g_ys = _dev(g_ys)
+    g_params = _dev_out(flat.shape)
+    g_y0 = _dev_out((B, H))
     st = L.lncde_logncde_bwd(None, _p(flat), _p(logsig), _p(rows), _p(scale), _p(ys), _p(g_ys), _p(g_params),
                              _p(g_y0), B, K, D, H, Cn, width, n_hidden, depth, n_steps, _p(ws), nbytes, 2)
     assert st == 0, st
-    return ys, g_params, g_y0
+    return ys.copy(), g_params.copy(), g_y0.copy()
 
 
 def logncde_bwd_recompute(flat, logsig, ys, rows, scale, dims, g_ys):
     """lncde_logncde_bwd without LNCDE_FLAG_SAVED_FWD (recomputing adjoint)."""
     L = lib()
     H, Cn, width, n_hidden, depth = dims
-    flat, logsig, ys, scale, g_ys = f32(flat), f32(logsig), f32(ys), f32(scale), f32(g_ys)
-    rows = np.ascontiguousarray(rows, np.int32)
+    flat, logsig, ys, scale, g_ys = _dev(flat), _dev(logsig), _dev(ys), _dev(scale), _dev(g_ys)
+    rows = _dev(rows, np.int32)
     B, K, D = logsig.shape
     n_steps = rows.shape[0]
     nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, Cn, width, n_hidden, depth, n_steps)
-    ws = _aligned(nbytes)
-    g_params = np.full(flat.shape, np.nan, np.float32)
-    g_y0 = np.full((B, H), np.nan, np.float32)
+    ws = guarded((nbytes,), np.uint8)
+    ws[...] = 0xFF
+    g_params = _dev_out(flat.shape)
+    g_y0 = _dev_out((B, H))
     st = L.lncde_logncde_bwd(None, _p(flat), _p(logsig), _p(rows), _p(scale), _p(ys), _p(g_ys), _p(g_params),
                              _p(g_y0), B, K, D, H, Cn, width, n_hidden, depth, n_steps, _p(ws), nbytes, 0)
     assert st == 0, st
-    return g_params, g_y0
+    return g_params.copy(), g_y0.copy()
 
 
 def nrde_fwd_bwd(flat, logsig, y0, rows, scale, dims, g_ys=None):
@@ -211,24 +231,25 @@ def nrde_fwd_bwd(flat, logsig, y0, rows, scale, dims, g_ys=None):
 def linear_scan(lie, logsig, y0, nb, bs, g_ys=None):
     """lncde_linear_scan_fwd (+ bwd).  lie [nb,bs,bs,n_basis]."""
     L = lib()
-    lie, logsig, y0 = f32(lie), f32(logsig), f32(y0)
+    lie, logsig, y0 = _dev(lie), _dev(logsig), _dev(y0)
     B, T, D = logsig.shape
     n_basis = lie.shape[-1]
     H = nb * bs
     nbytes = L.lncde_linear_scan_workspace_bytes(B, T, nb, bs, n_basis)
-    ws = _aligned(nbytes)
-    ys = np.full((B, T, H), np.nan, np.float32)
+    ws = guarded((nbytes,), np.uint8)
+    ws[...] = 0xFF
+    ys = _dev_out((B, T, H))
     st = L.lncde_linear_scan_fwd(None, _p(lie), _p(logsig), _p(y0), _p(ys), B, T, D, nb, bs, n_basis, _p(ws), nbytes)
     assert st == 0, st
     if g_ys is None:
-        return ys, None, None
-    g_ys = f32(g_ys)
-    g_lie = np.full(lie.shape, np.nan, np.float32)
-    g_y0 = np.full((B, H), np.nan, np.float32)
+        return ys.copy(), None, None
+    g_ys = _dev(g_ys)
+    g_lie = _dev_out(lie.shape)
+    g_y0 = _dev_out((B, H))
     st = L.lncde_linear_scan_bwd(None, _p(lie), _p(logsig), _p(ys), _p(g_ys), _p(g_lie), _p(g_y0), B, T, D, nb, bs,
                                  n_basis, _p(ws), nbytes)
     assert st == 0, st
-    return ys, g_lie, g_y0
+    return ys.copy(), g_lie.copy(), g_y0.copy()
 
 
 def dlncde(vf_At, logsig, y0, g_ys=None):
