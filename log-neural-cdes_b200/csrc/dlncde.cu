@@ -170,6 +170,7 @@ int lncde_dlncde_fwd(void* stream, const float* vf_At, const float* logsig, cons
   int st = dlncde_check(B, T, D, H, C);
   if (st != LNCDE_OK) return st;
   cudaStream_t cs = (cudaStream_t)stream;
+  if (B > 65535) return LNCDE_ERR_UNSUPPORTED;  // samples ride on grid.y
   const dim3 grid((H + kDThreads - 1) / kDThreads, B);
   switch (C) {
     case 1: dlncde_fwd_kernel<1><<<grid, kDThreads, 0, cs>>>(vf_At, logsig, y0, ys, T, D, H); break;
@@ -194,6 +195,7 @@ int lncde_dlncde_bwd(void* stream, const float* vf_At, const float* logsig, cons
   if (workspace_bytes < lncde_dlncde_bwd_workspace_bytes(B, H, C)) return LNCDE_ERR_WORKSPACE;
   cudaStream_t cs = (cudaStream_t)stream;
   float* partial = (float*)workspace;
+  if (B > 65535) return LNCDE_ERR_UNSUPPORTED;  // samples ride on grid.y
   const dim3 grid((H + kDThreads - 1) / kDThreads, B);
   switch (C) {
     case 1: dlncde_bwd_kernel<1><<<grid, kDThreads, 0, cs>>>(vf_At, logsig, ys, g_ys, g_y0, partial, T, D, H); break;

@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(256) flow_build8_kernel(const float* __restric
   constexpr int KT = 32, TS = 128;
   __shared__ __align__(16) float As[KT][TS];  // logsig tile, k-major
   __shared__ __align__(16) float Bs[KT][TS];  // lie tile, k-major
-  const long long m0 = (long long)blockIdx.y * TS;
-  const int n0 = blockIdx.x * TS;
+  const long long m0 = (long long)blockIdx.x * TS;  // row tiles on grid.x: B*T / 128 can exceed the 65 535 limit of grid.y
+  const int n0 = blockIdx.y * TS;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[8][8];
 #pragma unroll
@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(256, 2) flow_build_tc_kernel(const float* __re
   uint32_t* Al = Ah + kTcTile * kTcStride;             // lo parts
   uint32_t* Bh = Al + kTcTile * kTcStride;             // [128][36] lie tile (row n, column k)
   uint32_t* Bl = Bh + kTcTile * kTcStride;
-  const long long m0 = (long long)blockIdx.y * kTcTile;
-  const int n0 = blockIdx.x * kTcTile;
+  const long long m0 = (long long)blockIdx.x * kTcTile;  // row tiles on grid.x (no 65 535 limit)
+  const int n0 = blockIdx.y * kTcTile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;

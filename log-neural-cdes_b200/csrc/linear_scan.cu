@@ -580,14 +580,15 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   // 1. flows
   const int de_v2 = tuning_value(kTuneK2DeV2);
   if (de_v2 >= 2 && bs >= 64) {  // tensor pipe (3xTF32), any n_basis
-    dim3 grid((N + 127) / 128, (unsigned)((Mtot + 127) / 128));
+    dim3 grid((unsigned)((Mtot + 127) / 128), (N + 127) / 128);
     cudaFuncSetAttribute(flow_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     flow_build_tc_kernel<<<grid, 256, kTcSmemBytes, cs>>>(lie, logsig, F, Mtot, N, D, n_basis, bs);
   } else if (de_v2 && de_v2_shape(bs, n_basis)) {
-    dim3 grid((N + 127) / 128, (unsigned)((Mtot + 127) / 128));
+    dim3 grid((unsigned)((Mtot + 127) / 128), (N + 127) / 128);
     flow_build8_kernel<<<grid, 256, 0, cs>>>(lie, logsig, F, Mtot, N, D, n_basis, bs);
   } else {
     const int tm = 4, tn = round_tile(N) > 4 ? 4 : round_tile(N);
+    if ((Mtot + 16 * tm - 1) / (16 * tm) > 65535) return LNCDE_ERR_UNSUPPORTED;  // grid.y limit: B * T <= 4.19 M rows
     dim3 grid((N + 16 * tn - 1) / (16 * tn), (unsigned)((Mtot + 16 * tm - 1) / (16 * tm)));
     launch_build_tn<4>(tn, grid, cs, lie, logsig, F, Mtot, N, D, n_basis, bs);
   }

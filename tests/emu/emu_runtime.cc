@@ -384,7 +384,8 @@ void check_bulk(const void* smem_ptr, const void* gptr, unsigned bytes, const ch
 
 void launch(const void* func, dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   const size_t n = (size_t)block.x * block.y * block.z;
-  if (n == 0 || n > 1024 || (size_t)grid.x * grid.y * grid.z == 0) {
+  if (n == 0 || n > 1024 || (size_t)grid.x * grid.y * grid.z == 0 || grid.y > 65535 || grid.z > 65535 || grid.x > 2147483647u ||
+      block.z > 64) {
     g_last_error = (int)cudaErrorInvalidConfiguration;
     return;
   }
