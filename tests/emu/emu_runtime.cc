@@ -107,6 +107,7 @@ Block* g_blk = nullptr;
 // bulk stores, cp.async.wait_group for cp.async) - the latest the hardware may do it (exposes a missing or misplaced
 // wait: the reader finds the NaN fill of uninitialised shared memory).  A correct kernel is bit-identical under both.
 bool g_lazy_async = false;
+bool g_strict_masks = true;  // warp collectives must not name exited lanes
 int g_sched_mode = 0;
 unsigned g_sched_state = 1;
 bool g_blocks_reversed = false;
@@ -275,13 +276,21 @@ const uint64_t* warp_exchange(unsigned mask, uint64_t v) {
   const int t = b.cur, wi = t >> 5, lane = t & 31;
   Warp& w = b.warps[wi];
   if (!((mask >> lane) & 1u)) die("warp collective: calling lane is not in its own mask");
+  const unsigned lm = live_mask(b, wi);
+  // a collective that names a lane which has already exited is undefined behaviour on the hardware (lanes beyond the
+  // end of a partial last warp do not exist and are ignored, as before)
+  if (g_strict_masks) {
+    const int in_warp = b.n - wi * 32 >= 32 ? 32 : b.n - wi * 32;
+    const unsigned exist = in_warp >= 32 ? 0xffffffffu : ((1u << in_warp) - 1u);
+    if (mask & exist & ~lm) die("warp collective names a lane that has already exited (undefined behaviour on the GPU)");
+  }
   if (w.arrived == 0) w.mask = mask;
   else if (w.mask != mask) die("warp collective: lanes of one warp passed different masks");
   if ((w.arrived >> lane) & 1u) die("warp collective: lane arrived twice");
   w.slot[lane] = v;
   w.arrived |= 1u << lane;
   const long my = w.gen;
-  const unsigned need = mask & live_mask(b, wi);
+  const unsigned need = mask & lm;
   if ((w.arrived & need) == need) {
     complete_warp(w);
   } else {
