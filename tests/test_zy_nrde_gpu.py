@@ -4,19 +4,22 @@ Tolerance: BASELINE north-star 1e-5 relative in fp32 for states, 5e-5 for gradie
 
 These kernels were written after the GPU budget of round 1 was spent (verified on the host emulator against the
 oracle and against the reference-executed fixtures, tests/test_emu_kernels_cpu.py); the file name sorts them behind
-the tests of the hardware-proven kernels so that `pytest -x` reaches those first."""
+the tests of the hardware-proven kernels so that `pytest -x` reaches those first, and every test body runs in a
+child pytest process (conftest.isolated_gpu) so that a fault or a hang of a kernel that has never been on a B200
+cannot poison or stall the session.  Non-strict xfail until a hardware run has been seen: XPASS = correct on the GPU."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, rel_err
+from conftest import GOLDEN, INNER, isolated_gpu, rel_err
 from oracle import log_ncde as O
 from oracle import nrde as ON
 from oracle import paths
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu] + ([] if INNER else [pytest.mark.xfail(
+    strict=False, reason="K3n kernels not yet run on hardware (emulator-verified only); the default path does not use them")])
 
 TOL = 1e-5
 NR = np.load(os.path.join(GOLDEN, "ref_nrde.npz"))
@@ -41,6 +44,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES)
+@isolated_gpu
 def test_nrde_solve_and_adjoint_vs_oracle(built_lib, case):
     from lncde.models.NeuralCDEs import _NRDESolve
 
@@ -79,6 +83,7 @@ def test_nrde_solve_and_adjoint_vs_oracle(built_lib, case):
     assert torch.equal(ys2, ys) and np.array_equal(flat.grad.cpu().numpy(), gp)
 
 
+@isolated_gpu
 def test_nrde_train_step_eigenworms_config(built_lib):
     """One optimiser step of the reference's EigenWorms NRDE configuration (experiment_configs/repeats/nrde/
     EigenWorms.json: H 64, vf 3 x 64, depth 2, stepsize 4, no time channel) on a shortened path: the loss falls."""
@@ -105,6 +110,7 @@ def test_nrde_train_step_eigenworms_config(built_lib):
 
 
 @pytest.mark.parametrize("i", range(int(NR["n"])))
+@isolated_gpu
 def test_nrde_vs_reference_code(built_lib, i):
     """create_model("nrde") over the K3n kernels against the reference's own NeuralRDE: predictions, loss, gradients."""
     from lncde import train as T
