@@ -15,6 +15,8 @@ python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r
 for w in eigenworms_bd eigenworms_d eigenworms_de scp1_bd eigenworms_nrde toy_logncde ppg_logncde_d1; do
   python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline >> gpurun_out/r2_bench_others.json 2>> gpurun_out/r2_bench.err
 done
+# BASELINE configs[4]: DE vs D LNCDE on depth-3 rows, batch / length sweep (quick grid; the full grid and N > 1 later)
+timeout 600 python scripts/lncde_sweep.py --quick --out gpurun_out/r2_lncde_sweep.json > gpurun_out/r2_lncde_sweep.log 2>&1
 python scripts/k1_sweep.py > gpurun_out/r2_k1_sweep.txt 2>&1
 LNCDE_TUNE_K1_TMA=1 python scripts/k1_sweep.py > gpurun_out/r2_k1_sweep_tma.txt 2>&1
 # launch list of the default step (shares only), then one full capture of the K1 TMA kernel and of the K2 kernels

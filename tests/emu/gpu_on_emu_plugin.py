@@ -10,6 +10,7 @@ import contextlib
 import ctypes as C
 import os
 import sys
+import time
 
 import pytest
 import torch
@@ -43,6 +44,20 @@ class _CpuGenerator(torch.Generator):  # stays a class: torch modules use `torch
         return super().__new__(cls, "cpu")
 
 
+class _FakeEvent:
+    def __init__(self, enable_timing=False):
+        self.t = None
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+    def synchronize(self):
+        pass
+
+
 def pytest_configure(config):
     import build_emu
     from lncde import _build, _lib
@@ -63,6 +78,8 @@ def pytest_configure(config):
     torch.cuda.synchronize = lambda *a, **k: None
     torch.cuda.is_available = lambda: True
     torch.cuda.set_device = lambda *a, **k: None
+    torch.cuda.Event = _FakeEvent
+    torch.cuda.empty_cache = lambda: None
     torch.cuda.device = lambda *a, **k: contextlib.nullcontext()
     torch.Generator = _CpuGenerator
     for name in _FACTORIES:
