@@ -73,6 +73,7 @@ WORKLOADS = {
 }
 WL = dict(WORKLOADS["eigenworms_logncde"])
 N_ROT = 16  # distinct input batches rotated through (16 x 16.1 MB = 258 MB > 126 MB L2)
+K1_ROOFLINE_BATCH = 2048  # paths per launch of the K1 roofline leg (1.03 GB read + 0.36 GB written: > L2)
 
 
 def peaks():
@@ -159,6 +160,7 @@ def make_inputs(rank, n_rot):
 
     linear = WL["model"].endswith("linear_ncde")
     x = synthetic_paths(WL["name"], WL["B"] * n_rot, seed=2345 + rank, scale_to_unit=linear)
+    x = x[:, : WL["L"]]
     if x.shape[2] != WL["C"]:  # e.g. EigenWorms without its time channel
         x = np.ascontiguousarray(x[:, :, x.shape[2] - WL["C"]:])
     x = x.reshape(n_rot, WL["B"], WL["L"], WL["C"])
@@ -301,14 +303,13 @@ def run_ours(args):
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
     sync()
-    t0 = time.perf_counter()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
         last_loss = e2e_step(i)
     f1.record()
     sync()
-    e2e_ms = max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3 * 0.0)
+    e2e_ms = f0.elapsed_time(f1)
 
     t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -364,10 +365,15 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     dev = x_dev.device
     L, C, s = WL["L"], WL["C"], WL["stepsize"]
     # ---- K1 roofline leg: B = 2048 EigenWorms paths = 1.03 GB read + 0.36 GB written per launch
-    Bk = 2048
-    big = torch.from_numpy(synthetic_paths("EigenWorms", 64, seed=7)).to(dev).repeat(Bk // 64, 1, 1)
+    from lncde import _lib
+    from lncde.data_dir.generate_paths import logsig_dim
+
+    Bk = K1_ROOFLINE_BATCH
+    K, D = _lib.lib().lncde_logsig_num_windows(L, s), logsig_dim(C, 2)
+    n_src = min(64, Bk)
+    big = torch.from_numpy(synthetic_paths("EigenWorms", n_src, seed=7)[:, :L]).to(dev).repeat(Bk // n_src, 1, 1)
     big += 0.001 * torch.randn(Bk, 1, 1, device=dev)
-    out = torch.empty((Bk, 1499, 29), device=dev)
+    out = torch.empty((Bk, K, D), device=dev)
     for _ in range(3):
         calc_paths(big, s, 2, out=out)
     torch.cuda.synchronize()
@@ -379,7 +385,7 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     e1.record()
     torch.cuda.synchronize()
     k1_ms = e0.elapsed_time(e1) / n_rep
-    alg_bytes = Bk * (4 * L * C + 4 * 1499 * 29)  # 677 436 B per sample
+    alg_bytes = Bk * (4 * L * C + 4 * K * D)  # 677 436 B per sample (EigenWorms, C = 7)
     ach = alg_bytes / (k1_ms * 1e-3) / 1e9
     k1_tma = int(tuning.get("k1_tma", 0))
     res["roofline"] = {"kernel": ("logsig_levy_tma_kernel<7,depth2%s> (K1, TMA staging)" % (",persistent" if k1_tma > 1 else "")
@@ -392,7 +398,8 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
                        "traffic": None if k1_tma else 1.3515e9,
                        "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs (burst copy)",
                        "launch_ms": k1_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                       "shape": f"B={Bk} x EigenWorms (L=17984, C=7, stepsize 12, depth 2): inputs 1.03 GB > L2"}
+                       "shape": f"B={Bk} x EigenWorms (L={L}, C={C}, stepsize {s}, depth 2): inputs "
+                                f"{Bk * L * C * 4 / 1e9:.2f} GB > L2"}
     del big, out
     # ---- per-kernel breakdown of the train step (CUDA events around each phase) -----------------
     res["step_breakdown_ms"] = breakdown(model, opt, x_dev, lab_dev)
@@ -401,7 +408,7 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     # by the latency of ~12 dependent phases per Heun stage, not by HBM or the tensor pipe:
     # its FP32 rate is quoted against the NOMINAL FFMA peak (148 SM x 128 lanes x 2 x 1.965 GHz) for scale.
     macs_stage = 98304                                  # restructured field, SURVEY.md 8d (C = 7)
-    n_stage = 2 * 1499
+    n_stage = 2 * int(model._table[1].shape[0])        # Heun: two stages per step (1 499 steps for EigenWorms)
     flop = 2.0 * (2 * macs_stage) * n_stage * WL["B"]   # transposed mat-vecs + weight-gradient outer products
     t_ms = res["step_breakdown_ms"]["backward_K3b+gemm"]
     ach = flop / (t_ms * 1e-3) / 1e12
@@ -554,7 +561,6 @@ def cpu_baseline(budget_s=20.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     B, s, C = WL["B"], WL["stepsize"], WL["C"]
-    n_full = 1499
     n_sub = 24
     Ls = (n_sub + 1) * s
     from lncde.data_dir.datasets import synthetic_paths
@@ -565,7 +571,9 @@ def cpu_baseline(budget_s=20.0):
     t0 = time.perf_counter()
     ls = OP.calc_paths(x, s, 2, np.float32)
     t_logsig = time.perf_counter() - t0
-    rows, sc, _ = O.stage_table(ts_full, iv, WL["dt0"], 1499)
+    rows, sc, _ = O.stage_table(ts_full, iv, WL["dt0"], len(iv) - 1)
+    n_full = len(rows)  # Heun steps of the full path (1 499 for EigenWorms)
+    n_sub = min(n_sub, n_full)
     rows, sc = rows[:n_sub].copy(), sc[:n_sub].copy()
     rows[rows >= ls.shape[1]] = ls.shape[1] - 1  # quirk B2 row (last row) of the truncated sample
     stepper = LogNCDEStep(WL["H"], C, WL["vf_width"], WL["vf_depth"], WL["label_dim"], 2, WL["scale"], WL["lambd"],
