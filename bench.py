@@ -73,6 +73,7 @@ WORKLOADS = {
 }
 WL = dict(WORKLOADS["eigenworms_logncde"])
 N_ROT = 16  # distinct input batches rotated through (16 x 16.1 MB = 258 MB > 126 MB L2)
+FFMA_PROBE_SHAPE = (148 * 8, 2048)  # CTAs x loop trips of the FP32 probe launch (39.7 GFLOP: ~0.5 ms)
 K1_ROOFLINE_BATCH = 2048  # paths per launch of the K1 roofline leg (1.03 GB read + 0.36 GB written: > L2)
 
 
@@ -339,8 +340,9 @@ def run_ours(args):
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": int(x_pin[0].numel() * 4 + lab_pin[0].numel() * 4),
                     "d2h_bytes_per_step": 4, "last_loss": last_loss},
-            # own kernels in the timed region: K1, K3 fwd, K3b bwd, 3 gradient-GEMM groups, reduce, Adam per step
-            "gpu_launches": 8 * args.steps,
+            # own kernels in the timed region, per step (profiles/r01_launches_final.md): K1, K3 fwd, K3b bwd,
+            # 3 gradient-GEMM groups, gradient reduce, Adam + its step-counter bump
+            "gpu_launches": 9 * args.steps,
             "clocks": clocks,
         }
         if tune_report is not None:
@@ -407,6 +409,10 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     # The kernel that dominates the STEP is the adjoint sweep (+ its deferred gradient GEMMs).  It is bound
     # by the latency of ~12 dependent phases per Heun stage, not by HBM or the tensor pipe:
     # its FP32 rate is quoted against the NOMINAL FFMA peak (148 SM x 128 lanes x 2 x 1.965 GHz) for scale.
+    try:
+        ffma_peak, ffma_src = measured_ffma_tflops(dev), "measured on this device by lncde_probe_ffma (nominal 74.4)"
+    except Exception as e:  # the probe must never cost the bench its line
+        ffma_peak, ffma_src = 74.4, f"nominal FP32 FFMA peak (probe failed: {type(e).__name__})"
     macs_stage = 98304                                  # restructured field, SURVEY.md 8d (C = 7)
     n_stage = 2 * int(model._table[1].shape[0])        # Heun: two stages per step (1 499 steps for EigenWorms)
     flop = 2.0 * (2 * macs_stage) * n_stage * WL["B"]   # transposed mat-vecs + weight-gradient outer products
@@ -415,8 +421,8 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     res["roofline_dominant"] = {"kernel": "logncde_bwd_saved_kernel<7,depth2%s> + outer_gemm_kernel (K3b)"
                                           % (",fused" if tuning.get("k3_fused") else ""),
                                 "bound": "latency (dependent phases), fp32 issue", "achieved": ach,
-                                "peak": 74.4, "unit": "TFLOP/s", "frac": ach / 74.4,
-                                "peak_source": "nominal FP32 FFMA peak (not in MEASURED_PEAKS.json)",
+                                "peak": ffma_peak, "unit": "TFLOP/s", "frac": ach / ffma_peak,
+                                "peak_source": ffma_src,
                                 "share_of_step": t_ms / ms_per_step,
                                 "us_per_stage": 1e3 * t_ms / n_stage,
                                 "algorithmic_flop_per_step": flop}
@@ -424,6 +430,26 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     if not args.no_cpu_baseline:
         res["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     return res
+
+
+def measured_ffma_tflops(dev, reps=5):
+    """FP32 FFMA rate of this device at its current clocks (csrc/probe.cu: 8 independent chains per thread, 8 CTAs of
+    256 threads per SM) - the denominator for the FP32-issue bound solve kernels; MEASURED_PEAKS.json has no FP32 row."""
+    from lncde import _lib
+
+    L = _lib.lib()
+    blocks, iters = FFMA_PROBE_SHAPE
+    out = torch.empty(blocks * 256, device=dev)
+    for _ in range(2):
+        _lib.check(L.lncde_probe_ffma(_lib.stream_ptr(), _lib.ptr(out), blocks, iters), "lncde_probe_ffma")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        _lib.check(L.lncde_probe_ffma(_lib.stream_ptr(), _lib.ptr(out), blocks, iters), "lncde_probe_ffma")
+    e1.record()
+    torch.cuda.synchronize()
+    return L.lncde_probe_ffma_flops(blocks, iters) * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
 
 def decide_tuning(rep, margin=0.98):

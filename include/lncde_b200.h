@@ -204,6 +204,14 @@ int lncde_adam_step(void* stream, float* params, const float* grads, float* m, f
 int lncde_adam_step_dev(void* stream, float* params, const float* grads, float* m, float* v, int64_t n,
                         float lr, float beta1, float beta2, float eps, int* step_counter, float grad_scale);
 
+/* ------------------------------------------------------- measurement ---
+ * FP32 FFMA issue-rate probe (no reference counterpart; SURVEY.md 8d asks for a measured FP32 peak next to the
+ * HBM / tensor peaks of MEASURED_PEAKS.json).  Launches `blocks` CTAs of 256 threads, each thread running 8
+ * independent FFMA chains for 4 * iters rounds; out [blocks * 256] floats.  lncde_probe_ffma_flops returns the
+ * floating-point operations of one such launch (2 per FFMA).                                             */
+int64_t lncde_probe_ffma_flops(int blocks, int iters);
+int lncde_probe_ffma(void* stream, float* out, int blocks, int iters);
+
 #ifdef __cplusplus
 }
 #endif

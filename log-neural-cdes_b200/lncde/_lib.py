@@ -51,6 +51,8 @@ def _declare(lib):
         "lncde_nrde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, sz]),
         "lncde_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, i, f]),
         "lncde_adam_step_dev": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, vp, f]),
+        "lncde_probe_ffma_flops": (i64, [i, i]),
+        "lncde_probe_ffma": (i, [vp, vp, i, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it

@@ -26,7 +26,7 @@ def test_bench_json_contract_over_emulator():
     assert out["metric"] == "train samples/sec EigenWorms Log-NCDE" and out["unit"] == "samples/s"
     assert out["scaling"] == "weak" and out["dtype"] == "f32" and out["data"] == "synthetic"
     assert "workload" in out["config"] and "model" not in out["config"]
-    assert out["gpu_launches"] == 8 * out["steps"]
+    assert out["gpu_launches"] == 9 * out["steps"]
     # value = whole-job samples over the timed region
     assert abs(out["value"] - out["config"]["global_batch"] / (out["ms_per_step"] * 1e-3)) < 1e-6 * out["value"]
     e2e = out["e2e"]
@@ -40,6 +40,8 @@ def test_bench_json_contract_over_emulator():
     assert abs(rf["achieved"] - rf["algorithmic_bytes_per_launch"] / (rf["launch_ms"] * 1e-3) / 1e9) < 1e-9
     cb = out["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and cb["unit"] == "samples/s" and cb["sample"]
+    rd = out["roofline_dominant"]
+    assert rd["peak_source"].startswith("measured") and rd["peak"] > 0 and abs(rd["frac"] - rd["achieved"] / rd["peak"]) < 1e-12
     bd = out["step_breakdown_ms"]
     assert set(bd) == {"logsig_K1", "forward_solve_K3+readout", "backward_K3b+gemm", "adam_K4", "whole_step"}
     # autotune plumbing: K1 variant 1 (verified, 20 % faster) on; K3 variant 1 failed parity, variant 2 within the margin
