@@ -48,6 +48,8 @@ def calc_paths(data: torch.Tensor, stepsize, depth: int, *, compat: bool = True,
         raise _lib.LncdeError("calc_paths: out has the wrong shape")
     if kernel not in (None, "classic", "tma"):
         raise _lib.LncdeError(f"calc_paths: unknown kernel {kernel!r}")
+    if B == 0:  # an empty batch (e.g. the empty shard of preprocess_shard) is an empty result, as under jax.vmap
+        return out
     flags = (1 if compat else 0) | (4 if kernel == "tma" else 0)
     rowptr, cols, vals = _device_t2l(Cn, depth, data.device.index or 0)
     with torch.cuda.device(data.device):

@@ -29,6 +29,24 @@ def test_logsig_edge_shapes(built_lib):
     assert np.all(got[:, 1:] == 0) and np.all(got[:, 0, 4:] == 0)
 
 
+def test_logsig_empty_batch_and_nan_containment(built_lib):
+    """Empty input -> empty output of the right shape (no launch); a NaN sample poisons only the windows that
+    contain it (windows are independent: no cross-window or cross-sample leakage)."""
+    from lncde.data_dir.generate_paths import batch_calc_paths, calc_paths
+
+    for d, D in ((1, 4), (2, 7), (3, 15)):
+        got = calc_paths(torch.zeros(0, 10, 3, device="cuda"), 4, d)
+        assert tuple(got.shape) == (0, 3, D) and got.is_cuda
+    assert tuple(batch_calc_paths(torch.zeros(0, 10, 3, device="cuda"), 4, 2).shape) == (0, 3, 7)
+    x = torch.randn(3, 50, 4, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    clean = calc_paths(x, 5, 2)
+    x[1, 22, 2] = float("nan")  # row 22 lies in window 4 only (zero row prepended: windows cover rows 5k-1 .. 5k+4)
+    got = calc_paths(x, 5, 2)
+    bad = torch.isnan(got).any(-1)
+    assert bad[1, 4] and int(bad.sum()) == 1
+    assert torch.equal(got[~bad], clean[~bad])
+
+
 def test_logsig_argument_errors(built_lib):
     from lncde import _lib
     from lncde.data_dir.generate_paths import calc_paths

@@ -2,6 +2,7 @@
 (tests/emu): same Python code, same ctypes signatures and argument order as on the GPU box, with the three
 device-specific hooks of lncde._lib swapped for the test (library handle, stream, CUDA check).  Test
 infrastructure only - the product has no CPU path.  Results are compared with the reference-executed fixtures."""
+import contextlib
 import ctypes as C
 import os
 import sys
@@ -31,6 +32,12 @@ def emulated(monkeypatch):
     monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
     monkeypatch.setattr(_lib, "require_cuda_device", lambda *a: None)
     monkeypatch.setattr(_lib, "stream_ptr", lambda: C.c_void_p(0))
+    monkeypatch.setattr(torch.cuda, "device", lambda *a, **k: contextlib.nullcontext())  # calc_paths' device guard
+    from lncde.data_dir import generate_paths as GP
+    from lncde.data_dir.hall_set import HallSet
+
+    monkeypatch.setattr(GP, "_device_t2l",  # the K0 tables stay on the host for the emulated library
+                        lambda w, d, idx: tuple(torch.from_numpy(a) for a in HallSet(w, d).t2l_csr()))
     return handle
 
 
@@ -152,3 +159,19 @@ def test_make_step_with_emulated_adam_kernel(emulated):
     big = g.abs() > 1e-6  # elements whose update is not dominated by eps / fp32 rounding of g
     assert rel_err(model.params.detach().double()[big].numpy(), want[big].numpy()) < 1e-4
     assert int(opt.count) == 1
+
+
+def test_calc_paths_empty_batch_and_nan_containment(emulated):
+    """Host twin of tests/test_edge_cases_gpu.py::test_logsig_empty_batch_and_nan_containment."""
+    from lncde.data_dir.generate_paths import batch_calc_paths, calc_paths
+
+    for d, D in ((1, 4), (2, 7), (3, 15)):
+        assert tuple(calc_paths(torch.zeros(0, 10, 3), 4, d).shape) == (0, 3, D)
+    assert tuple(batch_calc_paths(torch.zeros(0, 10, 3), 4, 2).shape) == (0, 3, 7)
+    x = torch.randn(3, 50, 4, generator=torch.Generator().manual_seed(0))
+    clean = calc_paths(x, 5, 2)
+    x[1, 22, 2] = float("nan")
+    got = calc_paths(x, 5, 2)
+    bad = torch.isnan(got).any(-1)
+    assert bad[1, 4] and int(bad.sum()) == 1
+    assert torch.equal(got[~bad], clean[~bad])
