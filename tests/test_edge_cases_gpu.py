@@ -36,7 +36,7 @@ def test_logsig_empty_batch_and_nan_containment(built_lib):
 
     for d, D in ((1, 4), (2, 7), (3, 15)):
         got = calc_paths(torch.zeros(0, 10, 3, device="cuda"), 4, d)
-        assert tuple(got.shape) == (0, 3, D) and got.is_cuda
+        assert tuple(got.shape) == (0, 3, D) and got.device == torch.zeros(0, device="cuda").device
     assert tuple(batch_calc_paths(torch.zeros(0, 10, 3, device="cuda"), 4, 2).shape) == (0, 3, 7)
     x = torch.randn(3, 50, 4, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
     clean = calc_paths(x, 5, 2)
