@@ -457,7 +457,7 @@ def decide_tuning(rep, margin=0.98):
     choice = {"k1_tma": 0, "k3_fused": 0}
     k1, k3 = rep.get("k1", {}), rep.get("k3", {})
     for fam, key, base, variants in (("k2", "k2_fused_d", "default_B32", ((1, "fused_B32"),)),
-                                     ("k2de", "k2_de_v2", "default", ((1, "v2"), (2, "v2_tc"))),
+                                     ("k2de", "k2_de_v2", "default", ((1, "v2"), (2, "v2_tc"), (3, "v2_umma"))),
                                      ("k3g", "k3_stream", "default_ppg", ((1, "stream_ppg"),))):
         r = rep.get(fam)
         if r is None:
@@ -470,7 +470,7 @@ def decide_tuning(rep, margin=0.98):
             best_ms = margin * r["timing"][base]["ms"]
             for v, name in variants:
                 ok = par.get("ok_by_variant", {}).get(str(v), par.get("ok")) if "ok_by_variant" in par else par.get("ok")
-                if ok and name in r["timing"] and r["timing"][name]["ms"] < best_ms:
+                if ok and "ms" in r["timing"].get(name, {}) and r["timing"][name]["ms"] < best_ms:
                     choice[key], best_ms = v, r["timing"][name]["ms"]
         except (KeyError, TypeError):
             pass

@@ -546,6 +546,14 @@ static bool de_v2_shape(int bs, int n_basis) { return bs >= 64 && bs % 4 == 0 &&
 
 }  // namespace lncde
 
+namespace lncde {
+// flow_build_umma.cu: the dense flow build on tcgen05 (9xBF16 split, fp32 accuracy), "k2_de_v2" = 3
+size_t flow_build_umma_scratch_floats(long long Mtot, int N, int n_basis);
+int flow_build_umma(cudaStream_t cs, const float* lie, const float* logsig, float* F, long long Mtot, int N, int D,
+                    int n_basis, int bs, float* scratch, size_t scratch_floats);
+constexpr int kUmmaMinBlock = 64;  // block sizes the tensor-pipe flow build is used for (dense models)
+}  // namespace lncde
+
 extern "C" {
 
 size_t lncde_linear_scan_workspace_bytes(int B, int T, int nb, int bs, int n_basis) {
@@ -554,7 +562,12 @@ size_t lncde_linear_scan_workspace_bytes(int B, int T, int nb, int bs, int n_bas
   const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
   const size_t part = ((size_t)nb * bs * bs * n_basis * kScanKsplit + 3) & ~(size_t)3;
   const size_t lam = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;  // lam_t of the "k2_de_v2" reverse sweep
-  return (flows + part + lam) * 4;
+  // packed operands of the tcgen05 flow build ("k2_de_v2" = 3): a function of the shape only, so that the size does
+  // not depend on the tuning state at the time of the query (< 1 % of the flows)
+  const size_t umma = bs >= kUmmaMinBlock
+                          ? ((flow_build_umma_scratch_floats((long long)B * T, nb * bs * bs, n_basis) + 3) & ~(size_t)3)
+                          : 0;
+  return (flows + part + lam + umma) * 4;
 }
 
 static int check_scan_args(int B, int T, int D, int nb, int bs, int n_basis) {
@@ -579,7 +592,15 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   const long long Mtot = (long long)B * T;
   // 1. flows
   const int de_v2 = tuning_value(kTuneK2DeV2);
-  if (de_v2 >= 2 && bs >= 64) {  // tensor pipe (3xTF32), any n_basis
+  if (de_v2 >= 3 && bs >= kUmmaMinBlock) {  // tcgen05 (9xBF16 split): packed operands behind flows | part | lam
+    const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
+    const size_t part_n = ((size_t)N * n_basis * kScanKsplit + 3) & ~(size_t)3;
+    const size_t lam_n = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;
+    float* scratch = F + flows + part_n + lam_n;
+    st = flow_build_umma(cs, lie, logsig, F, Mtot, N, D, n_basis, bs, scratch,
+                         flow_build_umma_scratch_floats(Mtot, N, n_basis));
+    if (st != 0) return st;
+  } else if (de_v2 >= 2 && bs >= 64) {  // tensor pipe (3xTF32), any n_basis
     dim3 grid((unsigned)((Mtot + 127) / 128), (N + 127) / 128);
     cudaFuncSetAttribute(flow_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     flow_build_tc_kernel<<<grid, 256, kTcSmemBytes, cs>>>(lie, logsig, F, Mtot, N, D, n_basis, bs);

@@ -342,7 +342,7 @@ def test_emu_linear_scan_forward_and_adjoint(nb, bs, T, n_basis):
     assert rel_err(gl_e, lie_t.grad.numpy()) < 5 * TOL
 
 
-@pytest.mark.parametrize("level", [1, 2])
+@pytest.mark.parametrize("level", [1, 2, 3])
 @pytest.mark.parametrize("nb,bs,T,n_basis,B", [(1, 64, 9, 6, 2), (1, 128, 7, 28, 2), (2, 64, 5, 21, 3), (1, 64, 2, 3, 1),
                                                (1, 68, 6, 10, 2), (1, 128, 12, 36, 1), (1, 64, 5, 40, 2), (1, 72, 4, 70, 1)])
 def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B, level):
@@ -350,7 +350,10 @@ def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B, level):
     bracket gradient - ys and g_y0 bit-identical to the default kernels (same sums in the same order), g_lie to
     rounding.  Level 2: the flow build on the tensor pipe (3xTF32 split precision, mma.sync modelled by the emulator
     with the documented fragment layout) - fp32-grade flows, everything inside the parity tolerance; n_basis > 36
-    (depth-3 sizes, several K tiles) keeps the default reverse path."""
+    (depth-3 sizes, several K tiles) keeps the default reverse path.  Level 3: the flow build through
+    flow_build_umma.cu - on the emulator the operand PACKING kernels (16-byte row pitch, identity as one more K column)
+    and the workspace layout are the code under test, the tcgen05 GEMM itself is replaced by a plain fp32 contraction
+    of the packed operands; the rest of the step is level 2."""
     rng = np.random.default_rng(11)
     H, D = nb * bs, n_basis + 2  # one unused trailing logsig column
     lie = rng.normal(size=(nb, bs, bs, n_basis)) * (0.5 / np.sqrt(bs))
