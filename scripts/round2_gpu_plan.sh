@@ -36,4 +36,10 @@ LNCDE_TUNE_K2_DE_V2=2 python bench.py --workload eigenworms_de --steps 2 --warmu
 LNCDE_TUNE_K2_DE_V2=2 ncu --set full --clock-control none --import-source on -k regex:'flow_build_tc|dlie_triple_tc|scan_bwd_tma_lam' \
     -s 6 -c 3 -o gpurun_out/r2_prof_k2_tc python bench.py --workload eigenworms_de --steps 2 --warmup 3 --no-cpu-baseline \
     --no-graph --no-autotune > gpurun_out/r2_ncu4.log 2>&1
+# tcgen05 variant of the dense flow build (k2_de_v2 = 3): bench line, then one capture of the CUTLASS FastFP32 kernel + packing
+LNCDE_TUNE_K2_DE_V2=3 python bench.py --workload eigenworms_de --steps 5 --warmup 3 --no-cpu-baseline --no-graph --no-autotune \
+    > gpurun_out/r2_de_umma.json 2> gpurun_out/r2_de_umma.err &&
+LNCDE_TUNE_K2_DE_V2=3 ncu --set full --clock-control none --import-source on -k regex:'cutlass|umma_pack' -s 6 -c 3 \
+    -o gpurun_out/r2_prof_k2_umma python bench.py --workload eigenworms_de --steps 2 --warmup 3 --no-cpu-baseline \
+    --no-graph --no-autotune > gpurun_out/r2_ncu5.log 2>&1
 tail -3 gpurun_out/r2_pytest.log; head -c 1500 gpurun_out/r2_variants.json; echo; head -c 600 gpurun_out/r2_bench.json
