@@ -532,16 +532,32 @@ def autotune(families=("k1", "k3")):
     checks it against the default kernels and times both; a variant is switched on only if its parity check
     passed there and it was measurably faster.  Returns (choices, raw report)."""
     rep = {}
-    for which in families:  # one process each: a fault or hang in one family does not lose the other
+
+    def run(which, extra=()):
         try:
-            r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "variant_check.py"), "--no-oracle", "--only", which],
-                               capture_output=True, text=True, timeout=150)
+            r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "variant_check.py"), "--no-oracle", "--only",
+                                which, *extra], capture_output=True, text=True, timeout=150)
             if r.returncode != 0:
-                rep[which] = {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
-            else:
-                rep[which] = json.loads(r.stdout.strip().splitlines()[-1]).get(which, {"error": "no result"})
+                return {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
+            return json.loads(r.stdout.strip().splitlines()[-1]).get(which, {"error": "no result"})
         except Exception as e:  # timeout, unparsable output
-            rep[which] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    for which in families:  # one process each: a fault or hang in one family does not lose the other
+        rep[which] = run(which) if which != "k2de" else run(which, ("--levels", "1,2"))
+        if which == "k2de" and "error" not in rep[which]:
+            # the tcgen05 level launches a CUTLASS kernel that has not been on this hardware: a process of its own,
+            # merged into the family's report only if it came back
+            r3 = run(which, ("--levels", "3"))
+            if "error" in r3:
+                rep[which]["level3_error"] = r3["error"]
+            else:
+                for sect in ("parity", "timing"):
+                    for k, v in r3.get(sect, {}).items():
+                        if isinstance(v, dict) and isinstance(rep[which].get(sect, {}).get(k), dict) and k != "default":
+                            rep[which][sect][k].update(v)
+                        elif k not in rep[which].get(sect, {}):
+                            rep[which].setdefault(sect, {})[k] = v
     return decide_tuning(rep), rep
 
 

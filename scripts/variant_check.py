@@ -18,7 +18,10 @@ a fault or hang in a variant that has not been on hardware yet cannot take the c
   k3g: ``set_tuning("k3_stream", 1)`` (generic Log-NCDE kernels with streamed global-weight mat-vecs) - loss and
       gradients against the default generic kernels on PPG / toy dims, timings of both.
 
-    python scripts/variant_check.py [--no-timing] [--no-parity] [--no-oracle] [--only k1|k2|k3|k2de|k3g]
+    python scripts/variant_check.py [--no-timing] [--no-parity] [--no-oracle] [--only k1|k2|k3|k2de|k3g] [--levels 1,2]
+
+``--levels`` restricts the k2de legs to the given ``k2_de_v2`` levels, so that a caller can give the level that launches a
+library kernel it has never seen on hardware (3: tcgen05 / CUTLASS) a process of its own.
 """
 import json
 import os
@@ -287,17 +290,23 @@ def _de_step(B, n_windows, seed=0):
     return model, step
 
 
+def _k2de_levels():
+    if "--levels" in sys.argv:
+        return tuple(v for v in sys.argv[sys.argv.index("--levels") + 1].split(",") if v in ("1", "2", "3"))
+    return ("1", "2", "3")
+
+
 def k2de_parity():
     from lncde import _lib
 
-    levels = ("1", "2", "3")
+    levels = _k2de_levels()
     res = {"cases": 0, "max_rel_diff_grad": {v: 0.0 for v in levels}, "max_rel_diff_loss": {v: 0.0 for v in levels},
            "errors": {}}
     for B, nwin in ((3, 40), (8, 1499), (5, 130)):
         model, step = _de_step(B, nwin, seed=B)
         _lib.set_tuning("k2_de_v2", 0)
         l0, g0 = step()
-        for v in (1, 2, 3):
+        for v in (int(x) for x in levels):
             if str(v) in res["errors"]:
                 continue
             _lib.set_tuning("k2_de_v2", v)
@@ -329,6 +338,8 @@ def k2de_timing(reps=5):
                     "the bracket gradient on the tensor pipe (3xTF32), v2_umma = v2_tc with the flow build on tcgen05 (9xBF16)"}
     model, step = _de_step(32, 1499)
     for name, v in (("default", 0), ("v2", 1), ("v2_tc", 2), ("v2_umma", 3)):
+        if v and str(v) not in _k2de_levels():
+            continue
         _lib.set_tuning("k2_de_v2", v)
         try:
             for _ in range(2):

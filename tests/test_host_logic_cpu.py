@@ -123,6 +123,46 @@ def test_bench_autotune_decision():
     assert bench.decide_tuning({"k2": {"parity": ok, "timing": t(default_B32=1.0, fused_B32=0.99)}})["k2_fused_d"] == 0
 
 
+def test_autotune_runs_the_tcgen05_level_in_its_own_process(monkeypatch):
+    """bench.autotune("k2de"): levels 1, 2 in one subprocess, level 3 (CUTLASS kernel never seen on hardware) in another;
+    the reports are merged, and a level-3 process that dies costs only level 3."""
+    import importlib.util
+    import json
+    import os
+    import types
+
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    calls = []
+    r12 = {"k2de": {"parity": {"cases": 3, "ok": True, "ok_by_variant": {"1": True, "2": True}, "errors": {},
+                               "max_rel_diff_grad": {"1": 1e-7, "2": 2e-6}},
+                    "timing": {"shape": "s", "default": {"ms": 10.9}, "v2": {"ms": 8.0}, "v2_tc": {"ms": 6.5}}}}
+    r3 = {"k2de": {"parity": {"cases": 3, "ok": True, "ok_by_variant": {"3": True}, "errors": {},
+                              "max_rel_diff_grad": {"3": 1e-6}},
+                   "timing": {"shape": "s", "default": {"ms": 11.0}, "v2_umma": {"ms": 5.0}}}}
+    state = {"level3_dies": False}
+
+    def fake_run(cmd, **kw):
+        calls.append(cmd)
+        lv = cmd[cmd.index("--levels") + 1]
+        if lv == "3" and state["level3_dies"]:
+            return types.SimpleNamespace(returncode=-11, stdout="", stderr="Segmentation fault")
+        return types.SimpleNamespace(returncode=0, stdout=json.dumps(r3 if lv == "3" else r12) + "\n", stderr="")
+
+    monkeypatch.setattr(bench.subprocess, "run", fake_run)
+    tuning, rep = bench.autotune(("k2de",))
+    assert [c[c.index("--levels") + 1] for c in calls] == ["1,2", "3"] and all("--no-oracle" in c for c in calls)
+    assert rep["k2de"]["parity"]["ok_by_variant"] == {"1": True, "2": True, "3": True}
+    assert rep["k2de"]["timing"]["default"] == {"ms": 10.9} and rep["k2de"]["timing"]["v2_umma"] == {"ms": 5.0}
+    assert tuning["k2_de_v2"] == 3
+    state["level3_dies"] = True
+    tuning, rep = bench.autotune(("k2de",))
+    assert "level3_error" in rep["k2de"] and "error" not in rep["k2de"]
+    assert tuning["k2_de_v2"] == 2
+
+
 def test_tuning_api_roundtrip(built_lib):
     from lncde import _lib
 
