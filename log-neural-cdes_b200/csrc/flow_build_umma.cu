@@ -16,6 +16,11 @@
 //   B'[n, :] = (lie[n, 0 .. n_basis - 1], I[n], 0 ...)  -> the identity rides along as one more K column, and both
 //   operands get the 16-byte row pitch TMA needs (logsig rows are D = 29 floats: 116 bytes).
 //
+// The bracket gradient of the default reverse sweep, dLie[n, l] = sum_m dF[m, n] logsig[m, 1 + l] (220 GFLOP at depth 3,
+// where n_basis = 140 is beyond the triple-product kernels), runs through the same collective with both operands
+// MN-major: A = dF viewed as [N x B T] (n contiguous), B = the packed logsig rows [B T x K'] (l contiguous), fp32
+// accumulation over all B T rows in TMEM, output [N x K'] into the (then free) packed-lie scratch, copied to g_lie.
+//
 // Under the host emulator (LNCDE_EMU) and where the CUTLASS headers are missing (LNCDE_NO_CUTLASS) the GEMM itself is
 // not available: the emulator runs the packing kernels and a plain host-order fp32 contraction of the PACKED
 // operands (which checks the packing, the identity column and the workspace layout); without CUTLASS the entry point
@@ -74,7 +79,33 @@ __global__ void __launch_bounds__(256) umma_pack_rows_kernel(const float* __rest
   }
 }
 
+// g_lie[n][l] = Dp[n][l] for l < n_basis (the padded columns of the GEMM output are dropped)
+__global__ void __launch_bounds__(256) umma_unpad_kernel(const float* __restrict__ Dp, float* __restrict__ g_lie, int N,
+                                                          int n_basis, int kp) {
+  const long long total = (long long)N * n_basis;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long n = e / n_basis;
+    const int l = (int)(e - n * n_basis);
+    g_lie[e] = Dp[n * kp + l];
+  }
+}
+
 #if defined(LNCDE_EMU)
+// emulator stand-in for the bracket-gradient GEMM: Dp[n][l] = sum_m dF[m][n] A'[m][l], m ascending
+__global__ void __launch_bounds__(256) umma_reference_dlie_kernel(const float* __restrict__ dF, const float* __restrict__ A,
+                                                                   float* __restrict__ Dp, long long Mtot, int N, int kp) {
+  const long long total = (long long)N * kp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long n = e / kp;
+    const int l = (int)(e - n * kp);
+    float acc = 0.f;
+    for (long long m = 0; m < Mtot; ++m) acc = fmaf(dF[m * N + n], A[m * kp + l], acc);
+    Dp[e] = acc;
+  }
+}
+
 // emulator stand-in for the tensor-pipe GEMM: F = A' B'^T in fp32, k ascending (see the header comment)
 __global__ void __launch_bounds__(256) umma_reference_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                                    float* __restrict__ F, long long Mtot, int N, int kp) {
@@ -112,6 +143,17 @@ using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder
     cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32Sm100>::CollectiveOp;
 using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, void>;
 using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
+
+// bracket gradient: both operands MN-major (dF: n contiguous; packed logsig rows: l contiguous), reduction over B T
+using LayoutAg = cutlass::layout::ColumnMajor;
+using LayoutBg = cutlass::layout::RowMajor;
+using MainloopG = typename cutlass::gemm::collective::CollectiveBuilder<
+    cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutAg, kAlign, ElementB, LayoutBg, kAlign,
+    Accumulator, TileShape, ClusterShape,
+    cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
+    cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32Sm100>::CollectiveOp;
+using GemmKernelG = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, MainloopG, CollectiveEpilogue, void>;
+using GemmG = cutlass::gemm::device::GemmUniversalAdapter<GemmKernelG>;
 }  // namespace umma
 #endif
 
@@ -163,6 +205,58 @@ int flow_build_umma(cudaStream_t cs, const float* lie, const float* logsig, floa
   }
   return (int)cudaGetLastError();
 #endif
+#endif
+}
+
+// g_lie[N][n_basis] (fully overwritten) = dF^T logsig[:, 1:] with dF [Mtot][N] (the in-place result of the default reverse
+// sweep) and logsig [Mtot][D]; same scratch as flow_build_umma (the packed-lie region receives the padded output).
+int dlie_umma(cudaStream_t cs, const float* dF, const float* logsig, float* g_lie, long long Mtot, int N, int D,
+              int n_basis, float* scratch, size_t scratch_floats) {
+#if !defined(LNCDE_EMU) && defined(LNCDE_NO_CUTLASS)
+  (void)cs; (void)dF; (void)logsig; (void)g_lie; (void)Mtot; (void)N; (void)D; (void)n_basis; (void)scratch;
+  (void)scratch_floats;
+  return LNCDE_ERR_UNSUPPORTED;
+#else
+  if (Mtot < 1 || N < 1 || n_basis < 1 || Mtot > 0x7fffffffLL) return LNCDE_ERR_SHAPE;
+  if ((N & 3) != 0) return LNCDE_ERR_UNSUPPORTED;
+  if (((uintptr_t)scratch & 15) != 0 || ((uintptr_t)dF & 15) != 0) return LNCDE_ERR_ALIGN;
+  if (scratch_floats < flow_build_umma_scratch_floats(Mtot, N, n_basis)) return LNCDE_ERR_WORKSPACE;
+  const int kp = umma_kpad(n_basis);
+  float* Ap = scratch;                 // packed logsig rows [Mtot][kp] (re-packed: the caller may have changed nothing, but
+  float* Dp = Ap + (size_t)Mtot * kp;  // the call must not depend on what an earlier call left here); output [N][kp]
+  void* gemm_ws = Dp + (size_t)N * kp;
+  const int grid = 148 * 8;
+  umma_pack_rows_kernel<<<grid, 256, 0, cs>>>(logsig, Ap, Mtot, D, 1, n_basis, kp, 0);
+  int st = (int)cudaGetLastError();
+  if (st != 0) return st;
+#if defined(LNCDE_EMU)
+  (void)gemm_ws;
+  umma_reference_dlie_kernel<<<grid, 256, 0, cs>>>(dF, Ap, Dp, Mtot, N, kp);
+#else
+  using namespace umma;
+  using StrideA = typename GemmG::GemmKernel::StrideA;
+  using StrideB = typename GemmG::GemmKernel::StrideB;
+  using StrideC = typename GemmG::GemmKernel::StrideC;
+  using StrideD = typename GemmG::GemmKernel::StrideD;
+  StrideA sA = cute::make_stride(cute::Int<1>{}, (int64_t)N, (int64_t)0);   // A(n, m) = dF[m * N + n]
+  StrideB sB = cute::make_stride(cute::Int<1>{}, (int64_t)kp, (int64_t)0);  // B(l, m) = Ap[m * kp + l]
+  StrideC sC = cute::make_stride((int64_t)kp, cute::Int<1>{}, (int64_t)0);
+  StrideD sD = cute::make_stride((int64_t)kp, cute::Int<1>{}, (int64_t)0);
+  typename GemmG::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm, {N, kp, (int)Mtot, 1}, {dF, sA, Ap, sB},
+                                 {{1.f, 0.f}, Dp, sC, Dp, sD}};
+  GemmG gemm;
+  if (gemm.can_implement(args) != cutlass::Status::kSuccess) return LNCDE_ERR_UNSUPPORTED;
+  if (GemmG::get_workspace_size(args) > kUmmaGemmWorkspaceBytes) return LNCDE_ERR_WORKSPACE;
+  if (gemm.initialize(args, gemm_ws, cs) != cutlass::Status::kSuccess) return LNCDE_ERR_UNSUPPORTED;
+  if (gemm.run(cs) != cutlass::Status::kSuccess) {
+    st = (int)cudaGetLastError();
+    return st != 0 ? st : LNCDE_ERR_UNSUPPORTED;
+  }
+#endif
+  st = (int)cudaGetLastError();
+  if (st != 0) return st;
+  umma_unpad_kernel<<<grid, 256, 0, cs>>>(Dp, g_lie, N, n_basis, kp);
+  return (int)cudaGetLastError();
 #endif
 }
 

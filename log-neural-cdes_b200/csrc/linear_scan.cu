@@ -551,6 +551,8 @@ namespace lncde {
 size_t flow_build_umma_scratch_floats(long long Mtot, int N, int n_basis);
 int flow_build_umma(cudaStream_t cs, const float* lie, const float* logsig, float* F, long long Mtot, int N, int D,
                     int n_basis, int bs, float* scratch, size_t scratch_floats);
+int dlie_umma(cudaStream_t cs, const float* dF, const float* logsig, float* g_lie, long long Mtot, int N, int D,
+              int n_basis, float* scratch, size_t scratch_floats);
 constexpr int kUmmaMinBlock = 64;  // block sizes the tensor-pipe flow build is used for (dense models)
 }  // namespace lncde
 
@@ -668,6 +670,12 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
   if (st != 0) return st;
   // dLie[n][l] = sum_m dF[m][n] * logsig[m][1+l]
   const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
+  if (de_v2 >= 3 && bs >= kUmmaMinBlock) {  // tcgen05 (9xBF16 split), e.g. depth-3 rows: n_basis beyond the triple-product kernels
+    const size_t part_n = ((size_t)N * n_basis * kScanKsplit + 3) & ~(size_t)3;
+    const size_t lam_n = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;
+    return dlie_umma(cs, F, logsig, g_lie, (long long)B * T, N, D, n_basis, F + flows + part_n + lam_n,
+                     flow_build_umma_scratch_floats((long long)B * T, N, n_basis));
+  }
   GemmParams g;
   g.ksplit = kScanKsplit;
   g.part = F + flows;
