@@ -267,8 +267,9 @@ def k2_timing(reps=10):
     return res
 
 
-def _de_step(B, n_windows, seed=0):
-    """EigenWorms DE-LNCDE config (dense_linear_ncde, depth 2, H = 128, one 128 x 128 block): loss + flat gradient."""
+def _de_step(B, n_windows, seed=0, depth=2):
+    """EigenWorms DE-LNCDE config (dense_linear_ncde, depth 2 [3: the sweep's depth], H = 128, one 128 x 128 block):
+    loss + flat gradient."""
     from lncde import train as T
     from lncde.data_dir.generate_paths import calc_paths, logsig_dim
     from lncde.models.generate_model import create_model
@@ -278,11 +279,11 @@ def _de_step(B, n_windows, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = (torch.randn(B, L, C, device="cuda", generator=g) * 0.05).cumsum(1)
     x = 2 * (x - x.amin((0, 1))) / (x.amax((0, 1)) - x.amin((0, 1))) - 1
-    model, _ = create_model("dense_linear_ncde", C, logsig_dim(C, 2), 2, None, 5, H, block_size=H, lambd=1e-3, key=2345,
-                            device=torch.device("cuda"))
+    model, _ = create_model("dense_linear_ncde", C, logsig_dim(C, depth), depth, None, 5, H, block_size=H, lambd=1e-3,
+                            key=2345, device=torch.device("cuda"))
     ts = torch.zeros(B, L)
     y = torch.eye(5, device="cuda")[torch.arange(B, device="cuda") % 5]
-    ls = calc_paths(x, s, 2)
+    ls = calc_paths(x, s, depth)
 
     def step():
         return T.classification_loss(model, (ts, ls, x[:, 0, :]), y)
@@ -302,8 +303,10 @@ def k2de_parity():
     levels = _k2de_levels()
     res = {"cases": 0, "max_rel_diff_grad": {v: 0.0 for v in levels}, "max_rel_diff_loss": {v: 0.0 for v in levels},
            "errors": {}}
-    for B, nwin in ((3, 40), (8, 1499), (5, 130)):
-        model, step = _de_step(B, nwin, seed=B)
+    # the last case has depth-3 rows (n_basis = 140): several K tiles in the flow builds, and the reverse path that
+    # materialises dF - at level 3 its bracket gradient is the second tcgen05 GEMM (dlie_umma)
+    for B, nwin, depth in ((3, 40, 2), (8, 1499, 2), (5, 130, 2), (2, 60, 3)):
+        model, step = _de_step(B, nwin, seed=B, depth=depth)
         _lib.set_tuning("k2_de_v2", 0)
         l0, g0 = step()
         for v in (int(x) for x in levels):
