@@ -200,7 +200,8 @@ def run_ours(args):
 
     # ---- kernel-variant autotune (rank 0 decides, everybody applies the same choice) -------------------
     tuning, tune_report = {"k1_tma": 0, "k3_fused": 0}, None
-    families = {"log_ncde": ("k1", "k3"), "diagonal_linear_ncde": ("k1", "k2"), "dense_linear_ncde": ("k1", "k2de")}
+    families = {"log_ncde": ("k1", "k3"), "diagonal_linear_ncde": ("k1", "k2", "k2p"), "dense_linear_ncde": ("k1", "k2de"),
+                "bd_linear_ncde": ("k1", "k2p")}
     generic = WL["model"] == "log_ncde" and (WL["H"], WL["vf_width"], WL["vf_depth"]) != (128, 32, 2)
     if generic:
         families["log_ncde"] = ("k1", "k3g")  # shapes outside the specialised kernels: the generic solve kernels
@@ -472,6 +473,16 @@ def decide_tuning(rep, margin=0.98):
                 ok = par.get("ok_by_variant", {}).get(str(v), par.get("ok")) if "ok_by_variant" in par else par.get("ok")
                 if ok and "ms" in r["timing"].get(name, {}) and r["timing"][name]["ms"] < best_ms:
                     choice[key], best_ms = v, r["timing"][name]["ms"]
+        except (KeyError, TypeError):
+            pass
+    k2p = rep.get("k2p")
+    if k2p is not None:  # time-parallel scans: judged on the workload's own model (BD or D step)
+        choice["k2_pscan"] = 0
+        try:
+            tag = "d" if WL.get("model") == "diagonal_linear_ncde" else "bd"
+            if "error" not in k2p and k2p.get("parity", {}).get("ok") and \
+                    k2p["timing"][f"pscan_{tag}"]["ms"] < margin * k2p["timing"][f"default_{tag}"]["ms"]:
+                choice["k2_pscan"] = 1
         except (KeyError, TypeError):
             pass
     try:

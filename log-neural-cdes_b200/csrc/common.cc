@@ -10,10 +10,12 @@
 
 namespace lncde {
 namespace {
-const char* const kTuneNames[kTuneCount] = {"k1_tma", "k3_fused", "k2_fused_d", "k1_grid_cap", "k2_de_v2", "k3_stream"};
+const char* const kTuneNames[kTuneCount] = {"k1_tma", "k3_fused", "k2_fused_d", "k1_grid_cap", "k2_de_v2", "k3_stream",
+                                            "k2_pscan"};
 const char* const kTuneEnv[kTuneCount] = {"LNCDE_TUNE_K1_TMA", "LNCDE_TUNE_K3_FUSED", "LNCDE_TUNE_K2_FUSED_D",
-                                          "LNCDE_TUNE_K1_GRID_CAP", "LNCDE_TUNE_K2_DE_V2", "LNCDE_TUNE_K3_STREAM"};
-std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}};  // -1: not set yet -> environment, else 0
+                                          "LNCDE_TUNE_K1_GRID_CAP", "LNCDE_TUNE_K2_DE_V2", "LNCDE_TUNE_K3_STREAM",
+                                          "LNCDE_TUNE_K2_PSCAN"};
+std::atomic<int> g_tune[kTuneCount] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}, {-1}};  // -1: not set yet -> environment, else 0
 }  // namespace
 
 int tuning_value(int key) {

@@ -19,6 +19,7 @@
 
 #include "lncde_b200.h"
 #include "linear_de.cuh"
+#include "linear_pscan.cuh"
 #include "outer_gemm.cuh"
 #include "ptx.cuh"
 #include "tuning.h"
@@ -314,6 +315,41 @@ static bool scan_warp_dispatch(bool bwd, cudaStream_t cs, float* F, const float*
   return false;
 }
 
+// ---------------------------------------------------------------- 2b'. time-parallel scans ("k2_pscan", linear_pscan.cuh)
+template <int BS, int PF>
+static void launch_pscan(bool bwd, cudaStream_t cs, float* F, const float* y0, float* ys, const float* g_ys, float* g_y0,
+                         int B, int T, int H, float* scratch) {
+  const int nc = pscan_chunks(T);
+  float* P = scratch;                                  // [B][nc + 1][H][BS]
+  float* Yb = P + (size_t)B * (nc + 1) * H * BS;       // [B][nc + 1][H]
+  float* Q = Yb + (size_t)B * (nc + 1) * H;            // [B][nc][H]
+  float* Lam = Q + (size_t)B * nc * H;                 // [B][nc + 1][H]
+  const int threads = 256;
+  const int grid_c = (int)(((long long)B * nc * H + threads - 1) / threads);
+  const int grid_b = (int)(((long long)B * H + threads - 1) / threads);
+  pscan_prod_kernel<BS><<<grid_c, threads, 0, cs>>>(F, P, B, T, H, nc);
+  if (!bwd) {
+    scan_fwd_warp_kernel<BS, PF><<<grid_b, threads, 0, cs>>>(P, y0, Yb, B, nc + 1, H);
+    pscan_apply_kernel<BS><<<grid_c, threads, 0, cs>>>(F, Yb, ys, B, T, H, nc);
+  } else {
+    pscan_bwd_local_kernel<BS, false><<<grid_c, threads, 0, cs>>>(F, ys, g_ys, Lam, Q, B, T, H, nc);
+    pscan_bwd_boundary_kernel<BS><<<grid_b, threads, 0, cs>>>(P, Q, g_ys, Lam, g_y0, B, T, H, nc);
+    pscan_bwd_local_kernel<BS, true><<<grid_c, threads, 0, cs>>>(F, ys, g_ys, Lam, Q, B, T, H, nc);
+  }
+}
+static bool pscan_dispatch(bool bwd, cudaStream_t cs, float* F, const float* y0, float* ys, const float* g_ys, float* g_y0,
+                           int B, int T, int H, int bs, float* scratch) {
+  if (!tuning_value(kTuneK2Pscan) || !pscan_shape(T, bs)) return false;
+  if (((long long)B * pscan_chunks(T) * H + 255) / 256 > 0x7fffffffLL) return false;
+  switch (bs) {
+    case 1: launch_pscan<1, 8>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H, scratch); return true;
+    case 2: launch_pscan<2, 8>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H, scratch); return true;
+    case 4: launch_pscan<4, 6>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H, scratch); return true;
+    case 8: launch_pscan<8, 4>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H, scratch); return true;
+  }
+  return false;
+}
+
 // ---------------------------------------------------------------- 2c/3c. big-block scans (DE-LNCDE)
 // One CTA per sample.  The flows do not depend on the state, so they are streamed through a ring
 // of shared-memory stages by 1-D TMA bulk copies (cp.async.bulk + mbarrier, issued NS-1 steps
@@ -544,6 +580,10 @@ static size_t flows_floats(int B, int T, int nb, int bs) { return (size_t)B * T 
 // "k2_de_v2" applies to big blocks only (the warp-shuffle scans of bs | 32 keep their kernels)
 static bool de_v2_shape(int bs, int n_basis) { return bs >= 64 && bs % 4 == 0 && ((n_basis + 3) & ~3) <= 36; }
 
+
+// floats in front of the k2_pscan scratch: flows | split-K partials | lam (dense only) | packed operands (dense only)
+static size_t pscan_scratch_offset(int B, int T, int nb, int bs, int n_basis);
+
 }  // namespace lncde
 
 namespace lncde {
@@ -554,6 +594,16 @@ int flow_build_umma(cudaStream_t cs, const float* lie, const float* logsig, floa
 int dlie_umma(cudaStream_t cs, const float* dF, const float* logsig, float* g_lie, long long Mtot, int N, int D,
               int n_basis, float* scratch, size_t scratch_floats);
 constexpr int kUmmaMinBlock = 64;  // block sizes the tensor-pipe flow build is used for (dense models)
+
+static size_t pscan_scratch_offset(int B, int T, int nb, int bs, int n_basis) {
+  const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
+  const size_t part = ((size_t)nb * bs * bs * n_basis * kScanKsplit + 3) & ~(size_t)3;
+  const size_t lam = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;
+  const size_t umma = bs >= kUmmaMinBlock
+                          ? ((flow_build_umma_scratch_floats((long long)B * T, nb * bs * bs, n_basis) + 3) & ~(size_t)3)
+                          : 0;
+  return flows + part + ((lam + 3) & ~(size_t)3) + umma;
+}
 }  // namespace lncde
 
 extern "C" {
@@ -561,15 +611,11 @@ extern "C" {
 size_t lncde_linear_scan_workspace_bytes(int B, int T, int nb, int bs, int n_basis) {
   using namespace lncde;
   if (B < 1 || T < 1 || nb < 1 || bs < 1 || n_basis < 1) return 0;
-  const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
-  const size_t part = ((size_t)nb * bs * bs * n_basis * kScanKsplit + 3) & ~(size_t)3;
-  const size_t lam = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;  // lam_t of the "k2_de_v2" reverse sweep
-  // packed operands of the tcgen05 flow build ("k2_de_v2" = 3): a function of the shape only, so that the size does
-  // not depend on the tuning state at the time of the query (< 1 % of the flows)
-  const size_t umma = bs >= kUmmaMinBlock
-                          ? ((flow_build_umma_scratch_floats((long long)B * T, nb * bs * bs, n_basis) + 3) & ~(size_t)3)
-                          : 0;
-  return (flows + part + lam + umma) * 4;
+  // flows | split-K partials | lam_t of the "k2_de_v2" reverse sweep | packed operands of the tcgen05 flow build
+  // ("k2_de_v2" = 3) | chunk products and boundary states of the time-parallel scans ("k2_pscan") - every term is a
+  // function of the shape only, so that the size does not depend on the tuning state at the time of the query
+  const size_t pscan = pscan_shape(T, bs) ? ((pscan_floats(B, T, nb * bs, bs) + 3) & ~(size_t)3) : 0;
+  return (pscan_scratch_offset(B, T, nb, bs, n_basis) + pscan) * 4;
 }
 
 static int check_scan_args(int B, int T, int D, int nb, int bs, int n_basis) {
@@ -618,7 +664,9 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   st = (int)cudaGetLastError();
   if (st != 0) return st;
   // 2. scan
-  if (scan_warp_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
+  float* pscan_scratch = F + pscan_scratch_offset(B, T, nb, bs, n_basis);
+  if (pscan_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs, pscan_scratch)) {
+  } else if (scan_warp_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
   } else if (scan_tma_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
   } else if (bs <= 16) {
     int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));
@@ -661,7 +709,9 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
       return (int)cudaGetLastError();
     }
   }
-  if (!scan_warp_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs) &&
+  if (!pscan_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs,
+                      F + pscan_scratch_offset(B, T, nb, bs, n_basis)) &&
+      !scan_warp_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs) &&
       !scan_tma_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs)) {
     int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));
     scan_bwd_kernel<<<B, threads, 3 * H * sizeof(float), cs>>>(F, ys, g_ys, g_y0, T, H, bs);

@@ -14,6 +14,8 @@ enum TuneKey {
                      //             bracket gradient is a triple product of the small operands (linear_de.cuh)
   kTuneK3Stream = 5, // "k3_stream": generic Log-NCDE kernels - layers that do not fit in shared memory are read with the streamed
                      //              (prefetching, all-lanes) mat-vecs of logncde_common.cuh
+  kTuneK2Pscan = 6,  // "k2_pscan": small-block (D / BD) LNCDE scans parallel in time - chunk products, boundary recurrence over the
+                     //             chunks, per-chunk sweeps (linear_pscan.cuh) instead of T - 1 dependent steps per sample
   kTuneCount
 };
 

@@ -18,7 +18,10 @@ a fault or hang in a variant that has not been on hardware yet cannot take the c
   k3g: ``set_tuning("k3_stream", 1)`` (generic Log-NCDE kernels with streamed global-weight mat-vecs) - loss and
       gradients against the default generic kernels on PPG / toy dims, timings of both.
 
-    python scripts/variant_check.py [--no-timing] [--no-parity] [--no-oracle] [--only k1|k2|k3|k2de|k3g] [--levels 1,2]
+  k2p: ``set_tuning("k2_pscan", 1)`` (time-parallel D / BD scans, linear_pscan.cuh) - loss and gradients against the
+      sequential default scans, timings of the EigenWorms BD and D train steps.
+
+    python scripts/variant_check.py [--no-timing] [--no-parity] [--no-oracle] [--only k1|k2|k3|k2de|k3g|k2p] [--levels 1,2]
 
 ``--levels`` restricts the k2de legs to the given ``k2_de_v2`` levels, so that a caller can give the level that launches a
 library kernel it has never seen on hardware (3: tcgen05 / CUTLASS) a process of its own.
@@ -194,6 +197,81 @@ def k3_timing(reps=5):
         torch.cuda.synchronize()
         res[name] = {"ms": e0.elapsed_time(e1) / reps}
     _lib.set_tuning("k3_fused", 0)
+    return res
+
+
+def _bd_step(B, n_windows, seed=0, model_name="bd_linear_ncde", bs=4, depth=2):
+    """EigenWorms BD-LNCDE config (H = 128, 4 x 4 blocks, depth 2) - or the diagonal model on the same rows: loss + flat
+    gradient closure."""
+    from lncde import train as T
+    from lncde.data_dir.generate_paths import calc_paths, logsig_dim
+    from lncde.models.generate_model import create_model
+
+    C, s, H = 7, 12, 128
+    L = n_windows * s - 1
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = (torch.randn(B, L, C, device="cuda", generator=g) * 0.05).cumsum(1)
+    x = 2 * (x - x.amin((0, 1))) / (x.amax((0, 1)) - x.amin((0, 1))) - 1
+    model, _ = create_model(model_name, C, logsig_dim(C, depth), depth, None, 5, H, block_size=bs, lambd=1e-3, key=2345,
+                            device=torch.device("cuda"))
+    ts = torch.zeros(B, L)
+    y = torch.eye(5, device="cuda")[torch.arange(B, device="cuda") % 5]
+    ls = calc_paths(x, s, depth)
+
+    def step():
+        return T.classification_loss(model, (ts, ls, x[:, 0, :]), y)
+
+    return model, step
+
+
+_K2P_CASES = (("bd", "bd_linear_ncde", 4, 2), ("d", "diagonal_linear_ncde", 1, 1))
+
+
+def k2p_parity():
+    """k2_pscan (time-parallel D / BD scans) against the sequential default kernels: loss and flat gradient."""
+    from lncde import _lib
+
+    res = {"cases": 0, "max_rel_diff_grad": 0.0, "max_rel_diff_loss": 0.0}
+    for _, name, bs, depth in _K2P_CASES:
+        for B, nwin in ((3, 70), (32, 1499), (5, 131)):
+            model, step = _bd_step(B, nwin, seed=B, model_name=name, bs=bs, depth=depth)
+            _lib.set_tuning("k2_pscan", 0)
+            l0, g0 = step()
+            _lib.set_tuning("k2_pscan", 1)
+            l1, g1 = step()
+            _lib.set_tuning("k2_pscan", 0)
+            torch.cuda.synchronize()
+            res["cases"] += 1
+            res["max_rel_diff_loss"] = max(res["max_rel_diff_loss"], abs(float(l1) - float(l0)) / max(abs(float(l0)), 1e-30))
+            res["max_rel_diff_grad"] = max(res["max_rel_diff_grad"],
+                                           float((g1 - g0).abs().max() / g0.abs().max().clamp_min(1e-30)))
+            del model, step
+    res["ok"] = bool(res["max_rel_diff_loss"] < 1e-5 and res["max_rel_diff_grad"] < 5e-5)
+    return res
+
+
+def k2p_timing(reps=10):
+    from lncde import _lib
+
+    res = {"shape": "EigenWorms BD-LNCDE (4 x 4 blocks, depth 2) and D-LNCDE (depth 1) train steps (loss + gradient), "
+                    "B=32, eager launches: sequential warp-shuffle scans vs the two-level time-parallel scans"}
+    for tag, name, bs, depth in _K2P_CASES:
+        model, step = _bd_step(32, 1499, model_name=name, bs=bs, depth=depth)
+        for vname, v in (("default", 0), ("pscan", 1)):
+            _lib.set_tuning("k2_pscan", v)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            res[f"{vname}_{tag}"] = {"ms": e0.elapsed_time(e1) / reps}
+        del model, step
+        torch.cuda.empty_cache()
+    _lib.set_tuning("k2_pscan", 0)
     return res
 
 
@@ -436,7 +514,8 @@ if __name__ == "__main__":
     skip = sys.argv[sys.argv.index("--skip") + 1].split(",") if "--skip" in sys.argv else []
     out = {}
     for name, par, tim in (("k1", parity, timing), ("k3", k3_parity, k3_timing), ("k2", k2_parity, k2_timing),
-                           ("k2de", k2de_parity, k2de_timing), ("k3g", k3g_parity, k3g_timing)):
+                           ("k2de", k2de_parity, k2de_timing), ("k3g", k3g_parity, k3g_timing),
+                           ("k2p", k2p_parity, k2p_timing)):
         if only not in (None, name) or name in skip:
             continue
         out[name] = {}

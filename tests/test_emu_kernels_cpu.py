@@ -389,6 +389,47 @@ def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B, level):
     assert rel_err(gl1, lie_t.grad.numpy()) < 5 * TOL
 
 
+@pytest.mark.parametrize("nb,bs,T,n_basis,B", [(32, 4, 200, 6, 2), (5, 4, 66, 3, 1), (128, 1, 131, 5, 2), (8, 2, 97, 4, 3),
+                                               (3, 8, 70, 6, 2), (16, 4, 65, 28, 1), (7, 1, 260, 2, 2)])
+def test_emu_linear_scan_time_parallel(nb, bs, T, n_basis, B):
+    """tuning "k2_pscan" (linear_pscan.cuh): chunk products, boundary recurrence over the chunks, per-chunk sweeps -
+    forward states, g_y0 and the bracket gradient against the sequential default kernels (another association of the
+    same products: agreement to rounding) and against fp64 autograd of the recurrence.  Shapes: H not a multiple of 32
+    (warps straddling chunks), T - 1 not a multiple of the chunk, the shortest T the variant accepts (66), bs 1-8;
+    T = 65 (T - 1 = 2 chunks exactly) stays on the default kernels."""
+    rng = np.random.default_rng(nb * 100 + T)
+    H, D = nb * bs, n_basis + 1
+    lie = rng.normal(size=(nb, bs, bs, n_basis)) * (0.3 / np.sqrt(bs))
+    ls = rng.normal(size=(B, T, D)) * 0.1
+    ls[..., 0] = 0
+    y0 = rng.normal(size=(B, H))
+    g_ys = rng.normal(size=(B, T, H))
+    ys0, gl0, gy0 = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
+    E.set_tuning("k2_pscan", 1)
+    try:
+        ys1, gl1, gy1 = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
+    finally:
+        E.set_tuning("k2_pscan", 0)
+    if T - 1 <= 64:
+        assert np.array_equal(ys0, ys1) and np.array_equal(gl0, gl1) and np.array_equal(gy0, gy1)
+    else:
+        assert not np.array_equal(ys0, ys1)  # the variant really ran
+    assert rel_err(ys1, ys0) < 3e-6 and rel_err(gy1, gy0) < 3e-6 and rel_err(gl1, gl0) < 1e-5
+    lie_t = torch.from_numpy(lie).requires_grad_(True)
+    y0_t = torch.from_numpy(y0).requires_grad_(True)
+    flows = torch.einsum("nijl,btl->btnij", lie_t, torch.from_numpy(ls[..., 1:1 + n_basis])) + torch.eye(bs, dtype=torch.float64)
+    y = y0_t
+    out = [y]
+    for t in range(1, T):
+        y = torch.einsum("bnij,bnj->bni", flows[:, t], y.view(B, nb, bs)).reshape(B, H)
+        out.append(y)
+    ys_o = torch.stack(out, 1)
+    (ys_o * torch.from_numpy(g_ys)).sum().backward()
+    assert rel_err(ys1, ys_o.detach().numpy()) < TOL
+    assert rel_err(gy1, y0_t.grad.numpy()) < 5 * TOL
+    assert rel_err(gl1, lie_t.grad.numpy()) < 5 * TOL
+
+
 def test_emu_tf32_split_flow_build_accuracy():
     """3xTF32 flows against fp64: errors at the fp32 rounding level (a single-TF32 product would be ~5e-4 relative)."""
     rng = np.random.default_rng(2)

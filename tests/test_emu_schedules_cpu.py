@@ -144,6 +144,22 @@ def test_linear_scan_kernels_schedule_independent(nb, bs, T, n_basis, level):
         E.set_tuning("k2_de_v2", 0)
 
 
+@pytest.mark.parametrize("nb,bs,T,n_basis", [(5, 4, 70, 3), (24, 1, 100, 2), (3, 8, 66, 4)])
+def test_time_parallel_scan_schedule_independent(nb, bs, T, n_basis):
+    """k2_pscan: every kernel of the two-level scan is deterministic and free of cross-thread hazards between its
+    collectives (thread / warp / block orders, reversed grid)."""
+    rng = np.random.default_rng(6)
+    B, H = 2, nb * bs
+    lie = rng.normal(size=(nb, bs, bs, n_basis)) * (0.3 / np.sqrt(bs))
+    ls = rng.normal(size=(B, T, n_basis + 1)) * 0.1
+    y0, g_ys = rng.normal(size=(B, H)), rng.normal(size=(B, T, H))
+    E.set_tuning("k2_pscan", 1)
+    try:
+        _under_schedules(lambda: E.linear_scan(lie, ls, y0, nb, bs, g_ys))
+    finally:
+        E.set_tuning("k2_pscan", 0)
+
+
 def test_fused_diagonal_kernels_schedule_independent():
     rng = np.random.default_rng(4)
     B, T, H, Cn, D = 2, 150, 128, 7, 29

@@ -121,6 +121,15 @@ def test_bench_autotune_decision():
     de["k2de"]["parity"] = {"ok": False, "ok_by_variant": {"1": False, "2": False}}
     assert bench.decide_tuning(de)["k2_de_v2"] == 0
     assert bench.decide_tuning({"k2": {"parity": ok, "timing": t(default_B32=1.0, fused_B32=0.99)}})["k2_fused_d"] == 0
+    # time-parallel scans: judged on the timing of the workload's own model
+    p = {"k2p": {"parity": ok, "timing": t(default_bd=1.5, pscan_bd=1.1, default_d=0.9, pscan_d=0.95)}}
+    bench.WL["model"] = "bd_linear_ncde"
+    assert bench.decide_tuning(p)["k2_pscan"] == 1
+    bench.WL["model"] = "diagonal_linear_ncde"
+    assert bench.decide_tuning(p)["k2_pscan"] == 0
+    p["k2p"]["parity"] = bad
+    bench.WL["model"] = "bd_linear_ncde"
+    assert bench.decide_tuning(p)["k2_pscan"] == 0
 
 
 def test_autotune_runs_the_tcgen05_level_in_its_own_process(monkeypatch):
@@ -166,7 +175,7 @@ def test_autotune_runs_the_tcgen05_level_in_its_own_process(monkeypatch):
 def test_tuning_api_roundtrip(built_lib):
     from lncde import _lib
 
-    for key in ("k1_tma", "k3_fused", "k2_fused_d", "k2_de_v2", "k3_stream"):
+    for key in ("k1_tma", "k3_fused", "k2_fused_d", "k2_de_v2", "k3_stream", "k2_pscan"):
         old = _lib.get_tuning(key)
         _lib.set_tuning(key, 2)
         assert _lib.get_tuning(key) == 2

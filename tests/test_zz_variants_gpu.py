@@ -76,3 +76,8 @@ def test_k2_dense_v2_variant_parity(built_lib, level):
 @pytest.mark.xfail(strict=False, reason=REASON)
 def test_k3_generic_stream_variant_parity(built_lib):
     _check("k3g")
+
+
+@pytest.mark.xfail(strict=False, reason=REASON)
+def test_k2_time_parallel_scan_variant_parity(built_lib):
+    _check("k2p")
