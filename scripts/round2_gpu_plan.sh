@@ -6,8 +6,8 @@ set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/r2_smoke.log 2>&1
 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest.log
-# one process per family (k1 k3 k2 k2de k3g): a fault in one does not lose the others
-for fam in k1 k3 k2 k2de k3g; do
+# one process per family (k1 k3 k2 k2de k3g k2p): a fault in one does not lose the others
+for fam in k1 k3 k2 k2de k3g k2p; do
   timeout 300 python scripts/variant_check.py --only $fam >> gpurun_out/r2_variants.json 2>> gpurun_out/r2_variants.err
 done
 timeout 300 python scripts/phase_timing.py > gpurun_out/r2_phases.txt 2>&1
