@@ -341,9 +341,7 @@ def run_ours(args):
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": int(x_pin[0].numel() * 4 + lab_pin[0].numel() * 4),
                     "d2h_bytes_per_step": 4, "last_loss": last_loss},
-            # own kernels in the timed region, per step (profiles/r01_launches_final.md): K1, K3 fwd, K3b bwd,
-            # 3 gradient-GEMM groups, gradient reduce, Adam + its step-counter bump
-            "gpu_launches": 9 * args.steps,
+            "gpu_launches": own_launches_per_step(WL["model"], tuning) * args.steps,
             "clocks": clocks,
         }
         if tune_report is not None:
@@ -355,6 +353,22 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+def own_launches_per_step(model_name, tuning):
+    """Kernels of liblncde_b200.so launched by one train step (counted from the host code of csrc/, confirmed for the
+    default workload by the ncu launch list profiles/r01_launches_final.md)."""
+    adam = 2                                     # adam_dev_kernel + the step-counter bump
+    if model_name in ("log_ncde", "nrde"):
+        return 1 + 1 + 1 + 3 + 1 + adam          # K1, solve fwd, adjoint sweep, 3 gradient-GEMM groups, gradient reduce
+    if model_name == "diagonal_linear_ncde" and tuning.get("k2_fused_d"):
+        return 1 + 1 + 2 + adam                  # K1, dlncde_fwd, dlncde_bwd + its reduce
+    fwd, bwd = 2, 3                              # flow build + scan | reverse scan, bracket GEMM, split-K reduce
+    if tuning.get("k2_pscan") and model_name != "dense_linear_ncde":
+        fwd, bwd = 1 + 3, 4 + 2                  # products / boundary / apply | products / local / boundary / local + GEMM, reduce
+    if model_name == "dense_linear_ncde" and int(tuning.get("k2_de_v2", 0)) >= 3:
+        fwd = 3 + 1                              # two operand packs + the tcgen05 GEMM, scan
+    return 1 + fwd + bwd + adam
 
 
 def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_per_step, tuning):
