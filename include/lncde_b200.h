@@ -43,19 +43,25 @@ const char* lncde_version(void);
 /* Human-readable text for a status returned by any entry point. */
 const char* lncde_strerror(int status);
 
-/* Kernel-variant switches.  Every variant computes the same result; the default is the variant measured
- * fastest on B200 so far.  Keys: "k1_tma" (lncde_logsig_fwd: 1 = TMA bulk-copy staging, same as passing
- * LNCDE_FLAG_K1_TMA; 2 = the same kernel persistent, two-buffer ring, grid sized to the machine), "k3_fused" (lncde_logncde_fwd/bwd, specialised H=128 / width 32 kernels: 1 = the 32 x 32
- * layer phases fused on single warps, 2 = additionally phase Q4 of the adjoint folded into Q5), "k2_fused_d" (host mirror: diagonal LNCDE through lncde_dlncde_* instead
- * of flow build + scan), "k2_de_v2" (lncde_linear_scan_fwd/bwd with block size >= 64; 2 = additionally the flow build on the tensor pipe,
- * 3xTF32 split precision; 1 = 128 x 128 flow-build tiles with
- * 8 x 8 register tiles; the reverse sweep stores lam_t instead of dF_t and the bracket gradient is the triple product
- * sum lam_t (x) y_{t-1} (x) logsig_t - the flows in the workspace are then left intact by the backward call).
- * "k3_stream" (lncde_logncde_fwd/bwd, generic kernels - shapes other than H = 128 / width 32 / 2 hidden layers: layers that
- * do not fit in shared memory are read with prefetching all-lane mat-vecs; forward states bit-identical).
- * Process-wide, thread-safe; initial values come from the environment
- * (LNCDE_TUNE_K1_TMA, LNCDE_TUNE_K3_FUSED, LNCDE_TUNE_K2_FUSED_D, LNCDE_TUNE_K2_DE_V2, LNCDE_TUNE_K3_STREAM).  A forward/backward pair must run under the same
- * setting only in the sense that each call reads the value once at entry; results are interchangeable. */
+/* Kernel-variant switches.  Every variant computes the same result (bit for bit where noted, otherwise to fp32
+ * rounding); 0 = the default, i.e. the kernels measured on B200 so far.  Process-wide, thread-safe; each call reads
+ * the value once at entry; initial values come from the environment (LNCDE_TUNE_<KEY IN CAPITALS>).
+ *   "k1_tma"      lncde_logsig_fwd, C <= 8, depth <= 2: 1 = tiles moved by TMA bulk copies (same as LNCDE_FLAG_K1_TMA),
+ *                 2 = the same kernel persistent with a two-buffer ring, grid sized to the machine.  Bit-identical.
+ *   "k1_grid_cap" upper bound on the grid of the persistent K1 kernel (0 = machine-sized); experiments and tests.
+ *   "k3_fused"    lncde_logncde_fwd/bwd, specialised H = 128 / width 32 kernels: 1 = the 32 x 32 layer phases fused on
+ *                 single warps (bit-identical), 2 = additionally adjoint phase Q4 folded into Q5.
+ *   "k3_stream"   lncde_logncde_fwd/bwd, generic kernels (any other shape): layers that do not fit in shared memory are
+ *                 read with prefetching all-lane mat-vecs; forward states bit-identical.
+ *   "k2_fused_d"  read by the host mirror: diagonal LNCDE through lncde_dlncde_* instead of flow build + scan.
+ *   "k2_de_v2"    lncde_linear_scan_fwd/bwd, block size >= 64: 1 = 128 x 128 flow-build tiles with 8 x 8 register tiles,
+ *                 the reverse sweep stores lam_t instead of dF_t and the bracket gradient is the triple product
+ *                 sum lam_t (x) y_{t-1} (x) logsig_t (the backward call then leaves the flows in the workspace intact);
+ *                 2 = flow build and bracket gradient on the warp-level tensor pipe (3xTF32 split precision);
+ *                 3 = flow build (and the bracket gradient of the dF-materialising reverse path) on tcgen05 through
+ *                 CUTLASS' sm_100 FastFP32 collective (9xBF16 split) - LNCDE_ERR_UNSUPPORTED if built without CUTLASS.
+ *   "k2_pscan"    lncde_linear_scan_fwd/bwd, block size <= 8, T > 65: the scans run parallel in time (chunk products,
+ *                 boundary recurrence over the chunks, per-chunk sweeps). */
 int lncde_set_tuning(const char* key, int value);
 int lncde_get_tuning(const char* key); /* value, or <0 for an unknown key */
 

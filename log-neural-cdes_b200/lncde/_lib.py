@@ -80,7 +80,8 @@ def lib():
 
 
 def set_tuning(key: str, value: int) -> None:
-    """Select a kernel variant ("k1_tma", "k3_fused"); every variant computes the same result."""
+    """Select a kernel variant (keys and levels: include/lncde_b200.h, "Kernel-variant switches"); every variant
+    computes the same result."""
     check(lib().lncde_set_tuning(key.encode(), int(value)), f"lncde_set_tuning({key!r})")
 
 
