@@ -54,3 +54,20 @@ def test_reference_arm_line():
     r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference"], capture_output=True,
                        text=True, timeout=120, cwd=REPO, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""  # ranks other than 0 exit 0 without work
+
+
+def test_lncde_sweep_over_emulator():
+    """scripts/lncde_sweep.py (BASELINE configs[4]: DE vs D LNCDE on depth-3 rows): one JSON line per point + a summary."""
+    r = subprocess.run([sys.executable, os.path.join(REPO, "tests", "emu", "sweep_dryrun.py")], capture_output=True,
+                       text=True, timeout=600, cwd=REPO)
+    assert r.returncode == 0, r.stderr[-3000:]
+    recs = [json.loads(ln) for ln in r.stdout.splitlines() if ln.startswith("{")]
+    points, summary = recs[:-1], recs[-1]
+    assert [(p["model"], p["T"]) for p in points] == [("diagonal_linear_ncde", 9), ("dense_linear_ncde", 9),
+                                                      ("diagonal_linear_ncde", 70), ("dense_linear_ncde", 70)]
+    for p in points:
+        assert "error" not in p and "skipped" not in p and p["depth"] == 3 and p["ms_per_step"] > 0
+        assert abs(p["samples_per_s"] - p["B_per_gpu"] / (p["ms_per_step"] * 1e-3)) < 1e-6 * p["samples_per_s"]
+        assert p["hbm"]["algorithmic_bytes"] > 0 and ("flow_build" in p) == (p["model"] == "dense_linear_ncde")
+    assert points[0]["logsig_dim"] == 15 and points[2]["logsig_dim"] == 6  # Hall dimensions of (3, 3) and (2, 3)
+    assert set(summary["ratio"]) == {"B2_T9_H16_C3", "B2_T70_H8_C2"}
