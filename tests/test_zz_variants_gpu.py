@@ -1,10 +1,12 @@
-"""Kernel variants that exist in the library but are not the default yet.
+"""Kernel variants that exist in the library but are not the default yet (tuning keys of include/lncde_b200.h).
 
-``logsig_levy_tma_kernel`` (calc_paths(kernel="tma"), tuning "k1_tma") and the fused-phase Log-NCDE kernels
-(tuning "k3_fused") and the fused diagonal LNCDE kernels (tuning "k2_fused_d") were written after the GPU budget of round 1 was spent: all are verified against the default kernels
-(the first two bit-for-bit) on the host emulator (tests/test_emu_kernels_cpu.py) but have not run on a B200.
-They are exercised here in a subprocess (scripts/variant_check.py) so that a fault cannot poison this process,
-and the tests are non-strict xfails until a hardware run has been seen: XPASS = correct on the GPU."""
+All of them were written after the GPU budget of round 1 was spent: verified against the default kernels on the host
+emulator (tests/test_emu_kernels_cpu.py, tests/test_emu_schedules_cpu.py; K1 TMA and K3 fused level 1 bit for bit) but not
+yet run on a B200 - "k1_tma" 1 / 2, "k3_fused" 1 / 2, "k2_fused_d", "k2_de_v2" 1 / 2 / 3 (level 3 launches a CUTLASS
+tcgen05 kernel the emulator cannot model at all: a process of its own), "k3_stream", "k2_pscan".
+They are exercised here through scripts/variant_check.py in a subprocess per kernel family, so that a fault or a hang
+cannot poison this process, and the tests are non-strict xfails until a hardware run has been seen: XPASS = correct
+on the GPU (parity against the DEFAULT CUDA kernels and, without --no-oracle, the fp64 oracle)."""
 import json
 import os
 import subprocess
