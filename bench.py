@@ -346,6 +346,19 @@ def run_ours(args):
         }
         if tune_report is not None:
             out["autotune"] = tune_report
+        if WL["model"].endswith("linear_ncde"):
+            # K2 workloads: the whole step against its COMPULSORY bytes (logsig rows in, states out; the
+            # reverse sweep reads the rows, the states and their cotangents) - flows, partials and the bracket GEMM
+            # operands are implementation traffic, not counted.  At B = 32 these steps are launch / chain-latency
+            # bound, so the fraction is small by construction; the HBM-sized measurement is scripts/lncde_sweep.py.
+            T_rows = K
+            alg = world * B * (2 * 4 * T_rows * D + 3 * 4 * T_rows * WL["H"])
+            ach = alg / (ms / args.steps * 1e-3) / 1e9
+            out["roofline"] = {"kernel": f"K2 train step ({WL['model']}: flow build, scans, bracket gradient)", "bound": "hbm",
+                               "achieved": ach, "peak": pk["hbm_gbs"] * world, "unit": "GB/s",
+                               "frac": ach / (pk["hbm_gbs"] * world), "traffic": None,
+                               "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs x {world} GPU(s)",
+                               "algorithmic_bytes_per_step": alg}
         if args.workload == "eigenworms_logncde":
             out.update(extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms / args.steps, tuning))
     if world > 1:
