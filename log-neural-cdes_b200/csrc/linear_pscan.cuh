@@ -56,12 +56,28 @@ __global__ void __launch_bounds__(256) pscan_prod_kernel(const float* __restrict
   for (int t = lo; t < hi; ++t) {
     const float* Ft = Fb + (size_t)t * H * BS;
     float q[BS];
+    if constexpr (BS % 4 == 0) {  // the block is BS * BS contiguous floats at a 16-byte aligned offset: 128-bit loads
 #pragma unroll
-    for (int i = 0; i < BS; ++i) {
-      float acc = 0.f;
+      for (int i = 0; i < BS; ++i) {
+        float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < BS; ++k) acc = fmaf(__ldg(Ft + i * BS + k), p[k], acc);
-      q[i] = acc;
+        for (int k = 0; k < BS; k += 4) {
+          const float4 f = __ldg(reinterpret_cast<const float4*>(Ft + i * BS + k));
+          acc = fmaf(f.x, p[k], acc);
+          acc = fmaf(f.y, p[k + 1], acc);
+          acc = fmaf(f.z, p[k + 2], acc);
+          acc = fmaf(f.w, p[k + 3], acc);
+        }
+        q[i] = acc;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < BS; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < BS; ++k) acc = fmaf(__ldg(Ft + i * BS + k), p[k], acc);
+        q[i] = acc;
+      }
     }
 #pragma unroll
     for (int i = 0; i < BS; ++i) p[i] = q[i];
