@@ -160,4 +160,60 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_nrde_bwd, NrdeBwdImpl,
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::F32>>()
                                   .Ret<ffi::Buffer<ffi::U8>>());
+// ---- K2: D / BD / DE-LNCDE (LinearNeuralCDEs.py:302-386).  lie [nb*bs*bs, n_basis] are the bracket matrices of log_ode
+// (parameters only: stays in JAX), logsig [B, T, D], y0 [B, H]; attrs: nb, bs.  The scratch (flows) is a declared
+// extra result so that XLA owns it.
+static ffi::Error LinearScanFwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> lie, ffi::Buffer<ffi::F32> logsig,
+                                    ffi::Buffer<ffi::F32> y0, int32_t nb, int32_t bs, ffi::ResultBuffer<ffi::F32> ys,
+                                    ffi::ResultBuffer<ffi::U8> scratch) {
+  auto l = logsig.dimensions();
+  const int n_basis = (int)lie.dimensions()[1];
+  return status_to_error(
+      lncde_linear_scan_fwd(stream, lie.typed_data(), logsig.typed_data(), y0.typed_data(), ys->typed_data(), (int)l[0],
+                            (int)l[1], (int)l[2], nb, bs, n_basis, scratch->typed_data(), scratch->size_bytes()),
+      "lncde_linear_scan_fwd");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_linear_scan_fwd, LinearScanFwdImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("nb")
+                                  .Attr<int32_t>("bs")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>());
+
+// (g_lie, g_y0) = linear_scan_bwd(...).  The C entry point needs the flows its forward call left in the workspace; XLA
+// hands inputs over as const buffers, so this handler REBUILDS them (one more forward into its own scratch and a
+// throw-away ys) instead of aliasing the forward's scratch - a maintainer who wants to save that pass registers the
+// call with input_output_aliases on the scratch operand and drops the re-run.
+static ffi::Error LinearScanBwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> lie, ffi::Buffer<ffi::F32> logsig,
+                                    ffi::Buffer<ffi::F32> y0, ffi::Buffer<ffi::F32> g_ys, int32_t nb, int32_t bs,
+                                    ffi::ResultBuffer<ffi::F32> g_lie, ffi::ResultBuffer<ffi::F32> g_y0,
+                                    ffi::ResultBuffer<ffi::F32> ys_scratch, ffi::ResultBuffer<ffi::U8> scratch) {
+  auto l = logsig.dimensions();
+  const int B = (int)l[0], T = (int)l[1], D = (int)l[2], n_basis = (int)lie.dimensions()[1];
+  int st = lncde_linear_scan_fwd(stream, lie.typed_data(), logsig.typed_data(), y0.typed_data(), ys_scratch->typed_data(),
+                                 B, T, D, nb, bs, n_basis, scratch->typed_data(), scratch->size_bytes());
+  if (st != 0) return status_to_error(st, "lncde_linear_scan_fwd (rebuild)");
+  return status_to_error(
+      lncde_linear_scan_bwd(stream, lie.typed_data(), logsig.typed_data(), ys_scratch->typed_data(), g_ys.typed_data(),
+                            g_lie->typed_data(), g_y0->typed_data(), B, T, D, nb, bs, n_basis, scratch->typed_data(),
+                            scratch->size_bytes()),
+      "lncde_linear_scan_bwd");
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_linear_scan_bwd, LinearScanBwdImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int32_t>("nb")
+                                  .Attr<int32_t>("bs")
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>());
 #endif  // LNCDE_HAVE_XLA_FFI
