@@ -17,6 +17,10 @@ for w in eigenworms_bd eigenworms_d eigenworms_de scp1_bd eigenworms_nrde toy_lo
 done
 # BASELINE configs[4]: DE vs D LNCDE on depth-3 rows, batch / length sweep (quick grid; the full grid and N > 1 later)
 timeout 600 python scripts/lncde_sweep.py --quick --out gpurun_out/r2_lncde_sweep.json > gpurun_out/r2_lncde_sweep.log 2>&1
+# the same points with the variants that target these shapes: fused diagonal kernels (HBM path of the D-LNCDE), tcgen05
+# flow build / bracket gradient for the dense model (depth-3 rows: n_basis = 140)
+LNCDE_TUNE_K2_FUSED_D=1 LNCDE_TUNE_K2_DE_V2=3 timeout 600 python scripts/lncde_sweep.py --quick \
+    --out gpurun_out/r2_lncde_sweep_variants.json > gpurun_out/r2_lncde_sweep_variants.log 2>&1
 python scripts/k1_sweep.py > gpurun_out/r2_k1_sweep.txt 2>&1
 LNCDE_TUNE_K1_TMA=1 python scripts/k1_sweep.py > gpurun_out/r2_k1_sweep_tma.txt 2>&1
 # launch list of the default step (shares only), then one full capture of the K1 TMA kernel and of the K2 kernels
