@@ -83,3 +83,19 @@ def test_k3_generic_stream_variant_parity(built_lib):
 @pytest.mark.xfail(strict=False, reason=REASON)
 def test_k2_time_parallel_scan_variant_parity(built_lib):
     _check("k2p")
+
+
+@pytest.mark.xfail(strict=False, reason="measurement helper added after the last hardware run")
+def test_ffma_probe_runs(built_lib):
+    """lncde_probe_ffma (csrc/probe.cu): launches, every chain converges to the fixed point 1 of x -> 0.999 x + 0.001."""
+    import torch
+
+    from lncde import _lib
+
+    blocks, iters = 148, 4096
+    out = torch.full((blocks * 256,), float("nan"), device="cuda")
+    _lib.check(built_lib.lncde_probe_ffma(_lib.stream_ptr(), _lib.ptr(out), blocks, iters), "lncde_probe_ffma")
+    torch.cuda.synchronize()
+    assert built_lib.lncde_probe_ffma_flops(blocks, iters) == blocks * 256 * iters * 4 * 8 * 2
+    assert torch.allclose(out, torch.full_like(out, 8.0), atol=1e-3)  # 8 chains per thread, each at ~1 after 16 384 rounds
+    assert built_lib.lncde_probe_ffma(None, None, 1, 1) == -1 and built_lib.lncde_probe_ffma_flops(0, 1) < 0
