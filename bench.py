@@ -27,6 +27,8 @@ for _p in (REPO, os.path.join(REPO, "log-neural-cdes_b200")):
 import numpy as np
 import torch
 
+T_PROCESS_START = time.time()
+
 # Default = BASELINE.json configs[1]: EigenWorms Log-NCDE (experiment_configs/repeats/log_ncde/EigenWorms.json),
 # time channel included.  The other entries are the remaining BASELINE configs, selectable with --workload
 # (their numbers go to BASELINE.md; the driver only runs the default).
@@ -188,32 +190,50 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
-    if rank == 0:
-        _build.build_library()
-    if world > 1:
-        dist.barrier()
-    _lib.lib()
-
-    # ---- kernel-variant autotune (rank 0 decides, everybody applies the same choice) -------------------
+    # Build + kernel-variant autotune run BEFORE the process group exists: rank 0 works, the other ranks wait on a FILE
+    # (no rank spins inside NCCL meanwhile - round 1 had ranks 1..N-1 74 % "busy" for a minute doing nothing).
     tuning, tune_report = {"k1_tma": 0, "k3_fused": 0}, None
     families = {"log_ncde": ("k1", "k3"), "diagonal_linear_ncde": ("k1", "k2", "k2p"), "dense_linear_ncde": ("k1", "k2de"),
                 "bd_linear_ncde": ("k1", "k2p")}
     generic = WL["model"] == "log_ncde" and (WL["H"], WL["vf_width"], WL["vf_depth"]) != (128, 32, 2)
     if generic:
         families["log_ncde"] = ("k1", "k3g")  # shapes outside the specialised kernels: the generic solve kernels
-    if not args.no_autotune and (WL["model"] in families):
-        if rank == 0:
+    handoff = os.path.join(REPO, f".lncde_bench_handoff_{os.environ.get('MASTER_PORT', '0')}.json")
+    if rank == 0:
+        _build.build_library()
+        if not args.no_autotune and (WL["model"] in families):
             tuning, tune_report = cached_autotune(families[WL["model"]], refresh=args.retune)
         if world > 1:
-            box = [tuning]
-            dist.broadcast_object_list(box, src=0)
-            tuning = box[0]
-        for k, v in tuning.items():
-            _lib.set_tuning(k, v)
+            with open(handoff + ".tmp", "w") as fh:
+                json.dump({"tuning": tuning, "t": time.time()}, fh)
+            os.replace(handoff + ".tmp", handoff)
+    else:
+        t_wait = time.time()
+        while True:  # sleeping on the host, GPU idle
+            try:
+                with open(handoff) as fh:
+                    box = json.load(fh)
+                if box["t"] >= T_PROCESS_START - 5.0:
+                    tuning = box["tuning"]
+                    break
+            except (OSError, ValueError, KeyError):
+                pass
+            if time.time() - t_wait > 900:
+                raise SystemExit("bench.py: rank 0 never published its tuning decision")
+            time.sleep(0.2)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        if rank == 0:
+            try:
+                os.remove(handoff)
+            except OSError:
+                pass
+    _lib.lib()
+    for k, v in tuning.items():
+        _lib.set_tuning(k, v)
 
     B, L, C = WL["B"], WL["L"], WL["C"]
     x_host, lab_host = make_inputs(rank, N_ROT)
@@ -335,9 +355,9 @@ def run_ours(args):
             "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WL["desc"], "global_batch": world * B, "parallelism": f"dp{world}",
-                       "launch": "one CUDA graph per step" if use_graph else "eager",
-                       "tuning": tuning, "l2": l2_note},
+            "config": bench_config(world),
+            "impl_detail": {"launch": "one CUDA graph per step" if use_graph else "eager", "tuning": tuning,
+                            "l2_this_run": l2_note},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": int(x_pin[0].numel() * 4 + lab_pin[0].numel() * 4),
                     "d2h_bytes_per_step": 4, "last_loss": last_loss},
@@ -360,6 +380,8 @@ def run_ours(args):
                                "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs x {world} GPU(s)",
                                "algorithmic_bytes_per_step": alg}
         if args.workload == "eigenworms_logncde":
+            if world > 1:
+                args.no_cpu_baseline = True  # rank 0 at N = 1 only: with N ranks busy on the host the figure is meaningless
             out.update(extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms / args.steps, tuning))
     if world > 1:
         dist.barrier()
@@ -431,6 +453,8 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
                        "shape": f"B={Bk} x EigenWorms (L={L}, C={C}, stepsize {s}, depth 2): inputs "
                                 f"{Bk * L * C * 4 / 1e9:.2f} GB > L2"}
     del big, out
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return res  # N > 1: the other ranks are waiting - breakdown, FP32 probe and CPU baseline are N = 1 measurements
     # ---- per-kernel breakdown of the train step (CUDA events around each phase) -----------------
     res["step_breakdown_ms"] = breakdown(model, opt, x_dev, lab_dev)
     res["step_breakdown_ms"]["whole_step"] = ms_per_step
@@ -456,7 +480,7 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
                                 "algorithmic_flop_per_step": flop}
     # ---- CPU baseline ------------------------------------------------------------------------------
     if not args.no_cpu_baseline:
-        res["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        res["cpu_baseline"] = cpu_baseline()
     return res
 
 
@@ -631,80 +655,139 @@ def breakdown(model, opt, x_dev, lab_dev):
     return acc
 
 
-def cpu_baseline(budget_s=20.0):
-    """Oracle port of the reference train step on the host cores, on a bounded sample:
-    the full batch of 32 EigenWorms-shaped paths truncated to the first n_sub Heun steps."""
-    from oracle import log_ncde as O
-    from oracle import paths as OP
-    from oracle.train import LogNCDEStep
+class CpuReferenceStep:
+    """The reference's formulation of the WHOLE hot-path step on the host cores (oracle port, kind "port": the
+    reference's JAX-CPU code cannot run offline): numpy calc_paths (signax-style Chen / log / t2l) of the raw batch,
+    then oracle.train.LogNCDEStep (1 + C full-MLP JVPs per stage via torch.func, all n Heun steps, autograd adjoint,
+    Adam) - the same batch shape, path length, step count and hyper-parameters as the GPU arm's step."""
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    B, s, C = WL["B"], WL["stepsize"], WL["C"]
-    n_sub = 24
-    Ls = (n_sub + 1) * s
-    from lncde.data_dir.datasets import synthetic_paths
+    def __init__(self, n_rot=2):
+        from lncde.data_dir.datasets import synthetic_paths
+        from oracle import log_ncde as O
+        from oracle import paths as OP
+        from oracle.train import LogNCDEStep
 
-    x = synthetic_paths("EigenWorms", B, seed=2345)[:, :Ls]
-    ts_full = OP.make_ts(WL["L"])
-    iv = OP.make_intervals(ts_full, s)
-    t0 = time.perf_counter()
-    ls = OP.calc_paths(x, s, 2, np.float32)
-    t_logsig = time.perf_counter() - t0
-    rows, sc, _ = O.stage_table(ts_full, iv, WL["dt0"], len(iv) - 1)
-    n_full = len(rows)  # Heun steps of the full path (1 499 for EigenWorms)
-    n_sub = min(n_sub, n_full)
-    rows, sc = rows[:n_sub].copy(), sc[:n_sub].copy()
-    rows[rows >= ls.shape[1]] = ls.shape[1] - 1  # quirk B2 row (last row) of the truncated sample
-    stepper = LogNCDEStep(WL["H"], C, WL["vf_width"], WL["vf_depth"], WL["label_dim"], 2, WL["scale"], WL["lambd"],
-                          WL["lr"])
-    lst, x0 = torch.from_numpy(ls), torch.from_numpy(x[:, 0].copy())
-    y = torch.eye(WL["label_dim"])[torch.arange(B) % WL["label_dim"]]
-    stepper.step(lst, x0, y, rows, sc)  # warm-up
-    times = []
-    t_all = time.perf_counter()
-    while len(times) < 3 or (time.perf_counter() - t_all < budget_s and len(times) < 20):
+        self.OP = OP
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        B, s, C = WL["B"], WL["stepsize"], WL["C"]
+        x = synthetic_paths(WL["name"], B * n_rot, seed=2345)[:, : WL["L"]]
+        if x.shape[2] != C:
+            x = np.ascontiguousarray(x[:, :, x.shape[2] - C:])
+        self.x = x.reshape(n_rot, B, WL["L"], C)
+        ts = OP.make_ts(WL["L"])
+        iv = OP.make_intervals(ts, s)
+        self.rows, self.sc, _ = O.stage_table(ts, iv, WL["dt0"], len(iv) - 1)
+        self.stepper = LogNCDEStep(WL["H"], C, WL["vf_width"], WL["vf_depth"], WL["label_dim"], WL["depth"], WL["scale"],
+                                   WL["lambd"], WL["lr"])
+        self.y = torch.eye(WL["label_dim"])[torch.arange(B) % WL["label_dim"]]
+        self.t_logsig = self.t_train = 0.0
+
+    def step(self, i, n_steps=None):
+        """One full step on batch i (n_steps: truncate the solve to its first n Heun steps - warm-up / cross-check only)."""
+        x = self.x[i % len(self.x)]
         t0 = time.perf_counter()
-        stepper.step(lst, x0, y, rows, sc)
-        times.append(time.perf_counter() - t0)
+        ls = self.OP.calc_paths(x, WL["stepsize"], WL["depth"], np.float32)
+        t1 = time.perf_counter()
+        rows, sc = self.rows, self.sc
+        if n_steps is not None:
+            rows, sc = rows[:n_steps], sc[:n_steps]
+        loss = self.stepper.step(torch.from_numpy(ls), torch.from_numpy(x[:, 0].copy()), self.y, rows, sc)
+        t2 = time.perf_counter()
+        self.t_logsig, self.t_train = t1 - t0, t2 - t1
+        return t2 - t0, loss
+
+
+def cpu_baseline(full_steps=1):
+    """In-line CPU baseline of the default bench run (rank 0, N = 1 only): `full_steps` complete train steps of the full
+    batch - MEASURED, no extrapolation (about 11 s each on the GPU box's 16 cores) after a short truncated warm-up."""
+    ref = CpuReferenceStep()
+    n_full = len(ref.rows)
+    ref.step(0, n_steps=16)  # warm-up of torch's thread pool / allocator: 16 of the Heun steps, not timed
+    times = []
+    for i in range(full_steps):
+        t, loss = ref.step(i)
+        times.append(t)
     t_step = float(np.median(times))
-    scale_up = n_full / n_sub
-    t_full = t_step * scale_up + t_logsig * (WL["L"] / Ls)
-    # logsig half of the metric on the CPU: the numpy oracle of calc_paths over the full-size batch
-    xf = synthetic_paths("EigenWorms", B, seed=2345)
-    OP.calc_paths(xf[:2], s, 2, np.float32)
-    t0 = time.perf_counter()
-    lsf = OP.calc_paths(xf, s, 2, np.float32)
-    t_ls = time.perf_counter() - t0
-    ls_gbs = (xf.nbytes + lsf.nbytes) / t_ls / 1e9
-    return {"value": B / t_full, "unit": "samples/s", "cores": cores, "kind": "port",
-            "logsig": {"value": ls_gbs, "unit": "GB/s", "kind": "port",
-                       "sample": f"numpy oracle calc_paths (signax-style Chen/Horner, log, t2l) on the full B=32 x "
-                                 f"L=17984 x C=7 batch: {t_ls:.3f} s, same algorithmic bytes as the GPU roofline leg "
-                                 f"per sample"},
-            "sample": f"oracle port (torch-CPU fp32, reference formulation 1+C JVPs, autograd adjoint) of the full "
-                      f"B=32 batch truncated to the first {n_sub} of {n_full} Heun steps (L={Ls}); median of "
-                      f"{len(times)} steps = {t_step:.3f} s, scaled x{scale_up:.1f} to the full path; numpy logsig "
-                      f"{t_logsig:.3f} s scaled likewise"}
+    B = WL["B"]
+    ls_bytes = B * (4 * WL["L"] * WL["C"] + 4 * (len(ref.rows)) * 29)
+    return {"value": B / t_step, "unit": "samples/s", "cores": ref.cores, "kind": "port",
+            "logsig": {"value": ls_bytes / ref.t_logsig / 1e9, "unit": "GB/s", "kind": "port",
+                       "sample": f"numpy oracle calc_paths on the full B={B} x L={WL['L']} x C={WL['C']} batch: "
+                                 f"{ref.t_logsig:.3f} s"},
+            "sample": f"oracle port (numpy logsig + torch-CPU fp32 Log-NCDE step in the reference formulation, 1+C JVPs, "
+                      f"autograd adjoint, Adam) on the FULL workload: B={B}, all {n_full} Heun steps; {full_steps} "
+                      f"measured step(s) of {t_step:.2f} s (logsig {ref.t_logsig:.2f} s + train {ref.t_train:.2f} s), "
+                      f"no extrapolation; last loss {loss:.4f}"}
+
+
+def ref_budget_s():
+    """Wall-clock budget of the reference arm: 25 full CPU steps take ~280 s on the GPU box's 16 cores; a slower host
+    runs fewer timed steps (reported as such) instead of running long."""
+    return float(os.environ.get("LNCDE_REF_BUDGET_S", "480"))
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation cannot run offline (jax absent),
-    so this times the oracle port on all host cores (kind 'port').  Rank 0 only."""
+    """--impl reference: the reference's own CPU implementation cannot run offline (jax absent), so this times the
+    oracle port (kind "port") on all host cores: `--warmup` untimed and `--steps` timed FULL train steps of the arm's
+    workload (B = 32, every Heun step; nothing is scaled up).  Rank 0 only; the other ranks exit without work."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    if WL["model"] != "log_ncde":
+        raise SystemExit("--impl reference times the Log-NCDE workloads (the headline metric)")
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    budget = ref_budget_s()
+    t_start = time.perf_counter()
+    ref = CpuReferenceStep()
+    n_full = len(ref.rows)
+    ref.step(0, n_steps=24)  # cross-check figure of round 1 (first 24 Heun steps, scaled); also warms torch up
+    t24_train, t24_logsig = ref.t_train, ref.t_logsig
+    warm, steps, times = 0, 0, []
+    for i in range(args.warmup):
+        t, _ = ref.step(i)
+        warm += 1
+        if (time.perf_counter() - t_start) + t * (args.steps + args.warmup - warm) > budget:
+            break  # a slow host: spend what is left of the budget on timed steps
     t0 = time.perf_counter()
-    cb = cpu_baseline(budget_s=max(10.0, min(60.0, 6.0 * (args.steps + args.warmup))))
-    out = {"impl": "reference", "metric": "train samples/sec EigenWorms Log-NCDE", "value": cb["value"],
-           "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": 1e3 * WL["B"] / cb["value"], "higher_is_better": True, "scaling": "weak",
+    for i in range(args.steps):
+        t, loss = ref.step(warm + i)
+        times.append(t)
+        steps += 1
+        if (time.perf_counter() - t_start) + t > budget and steps >= 2:
+            break
+    total = time.perf_counter() - t0
+    B = WL["B"]
+    value = B * steps / total
+    cb = {"value": value, "unit": "samples/s", "cores": ref.cores, "kind": "port",
+          "sample": f"oracle port (numpy logsig + torch-CPU fp32 Log-NCDE step, reference formulation 1+C JVPs, autograd "
+                    f"adjoint, Adam) on the FULL workload: B={B}, all {n_full} Heun steps per step; {warm} warm-up + "
+                    f"{steps} timed steps, {total / steps:.2f} s each, measured (no extrapolation)"
+                    + (f"; at N={world} rank 0 runs one rank's batch" if world > 1 else ""),
+          # round 1 reported THIS figure (first 24 Heun steps scaled to the full path); kept as a cross-check only
+          "cross_check": {"extrapolated": True, "first_24_heun_steps_s": t24_train,
+                          "value": B / (t24_train * n_full / min(24, n_full) + t24_logsig)}}
+    out = {"impl": "reference", "metric": "train samples/sec EigenWorms Log-NCDE" if args.workload == "eigenworms_logncde"
+           else f"train samples/sec {args.workload}", "value": value,
+           "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warm,
+           "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": args.scaling,
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WL["desc"], "global_batch": WL["B"], "parallelism": "cpu"},
+           "config": bench_config(world),
            "cpu_baseline": cb,
-           "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "wall_s": time.perf_counter() - t0}
+           "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": time.perf_counter() - t_start}
+    if steps != args.steps or warm != args.warmup:
+        out["requested"] = {"steps": args.steps, "warmup": args.warmup, "budget_s": budget}
     print(json.dumps(out))
+
+
+def bench_config(world):
+    """`config` of the JSON line - the WORKLOAD, identical for both arms (what differs between the arms - launch mode,
+    kernel tuning - is reported under `impl_detail`)."""
+    in_mb = N_ROT * WL["B"] * WL["L"] * WL["C"] * 4 / 1e6
+    return {"workload": WL["desc"], "global_batch": world * WL["B"], "parallelism": f"dp{world}",
+            "l2": f"inputs rotate through distinct batches ({N_ROT} x {in_mb / N_ROT:.1f} MB on the GPU arm) and the adjoint "
+                  f"workspace (> 1 GB for the default workload) is streamed every step: working set > 126 MB L2; "
+                  f"workloads smaller than L2 are timed step by step with a 256 MB L2 flush in between"}
 
 
 def _watchdog(seconds):
@@ -726,7 +809,6 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0)
     ap.add_argument("--workload", default="eigenworms_logncde", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the contract): the workload's batch per GPU; strong: that batch split over the GPUs")
@@ -744,7 +826,7 @@ def main():
         WL["B"] //= world
         WL["desc"] += f" [strong scaling: {WL['B']} samples per GPU]"
     # the default run finishes in ~40 s; never let a stuck collective hold N GPUs for long
-    _watchdog(float(os.environ.get("LNCDE_BENCH_TIMEOUT", "600")))
+    _watchdog(float(os.environ.get("LNCDE_BENCH_TIMEOUT", "600")) + (ref_budget_s() if args.impl == "reference" else 0.0))
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -587,22 +587,20 @@ static size_t pscan_scratch_offset(int B, int T, int nb, int bs, int n_basis);
 }  // namespace lncde
 
 namespace lncde {
-// flow_build_umma.cu: the dense flow build on tcgen05 (9xBF16 split, fp32 accuracy), "k2_de_v2" = 3
-size_t flow_build_umma_scratch_floats(long long Mtot, int N, int n_basis);
-int flow_build_umma(cudaStream_t cs, const float* lie, const float* logsig, float* F, long long Mtot, int N, int D,
-                    int n_basis, int bs, float* scratch, size_t scratch_floats);
-int dlie_umma(cudaStream_t cs, const float* dF, const float* logsig, float* g_lie, long long Mtot, int N, int D,
-              int n_basis, float* scratch, size_t scratch_floats);
-constexpr int kUmmaMinBlock = 64;  // block sizes the tensor-pipe flow build is used for (dense models)
+// flow_tcgen05.cu: the dense flow build on tcgen05 (hand-written; 3xTF32 split, fp32 accuracy), "k2_de_v2" = 3
+size_t flow_tcgen05_scratch_floats(long long Mtot, int N, int n_basis);
+bool flow_tcgen05_shape(int N, int bs);
+int flow_build_tcgen05(cudaStream_t cs, const float* lie, const float* logsig, float* F, long long Mtot, int N, int D,
+                       int n_basis, int bs, float* scratch, size_t scratch_floats);
 
 static size_t pscan_scratch_offset(int B, int T, int nb, int bs, int n_basis) {
   const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
   const size_t part = ((size_t)nb * bs * bs * n_basis * kScanKsplit + 3) & ~(size_t)3;
   const size_t lam = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;
-  const size_t umma = bs >= kUmmaMinBlock
-                          ? ((flow_build_umma_scratch_floats((long long)B * T, nb * bs * bs, n_basis) + 3) & ~(size_t)3)
-                          : 0;
-  return flows + part + ((lam + 3) & ~(size_t)3) + umma;
+  const size_t tc5 = flow_tcgen05_shape(nb * bs * bs, bs)
+                         ? ((flow_tcgen05_scratch_floats((long long)B * T, nb * bs * bs, n_basis) + 3) & ~(size_t)3)
+                         : 0;
+  return flows + part + ((lam + 3) & ~(size_t)3) + tc5;
 }
 }  // namespace lncde
 
@@ -640,13 +638,13 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   const long long Mtot = (long long)B * T;
   // 1. flows
   const int de_v2 = tuning_value(kTuneK2DeV2);
-  if (de_v2 >= 3 && bs >= kUmmaMinBlock) {  // tcgen05 (9xBF16 split): packed operands behind flows | part | lam
+  if (de_v2 >= 3 && flow_tcgen05_shape(N, bs)) {  // tcgen05 (3xTF32 split): packed operands behind flows | part | lam
     const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
     const size_t part_n = ((size_t)N * n_basis * kScanKsplit + 3) & ~(size_t)3;
     const size_t lam_n = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;
     float* scratch = F + flows + part_n + lam_n;
-    st = flow_build_umma(cs, lie, logsig, F, Mtot, N, D, n_basis, bs, scratch,
-                         flow_build_umma_scratch_floats(Mtot, N, n_basis));
+    st = flow_build_tcgen05(cs, lie, logsig, F, Mtot, N, D, n_basis, bs, scratch,
+                         flow_tcgen05_scratch_floats(Mtot, N, n_basis));
     if (st != 0) return st;
   } else if (de_v2 >= 2 && bs >= 64) {  // tensor pipe (3xTF32), any n_basis
     dim3 grid((unsigned)((Mtot + 127) / 128), (N + 127) / 128);
@@ -720,12 +718,6 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
   if (st != 0) return st;
   // dLie[n][l] = sum_m dF[m][n] * logsig[m][1+l]
   const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
-  if (de_v2 >= 3 && bs >= kUmmaMinBlock) {  // tcgen05 (9xBF16 split), e.g. depth-3 rows: n_basis beyond the triple-product kernels
-    const size_t part_n = ((size_t)N * n_basis * kScanKsplit + 3) & ~(size_t)3;
-    const size_t lam_n = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;
-    return dlie_umma(cs, F, logsig, g_lie, (long long)B * T, N, D, n_basis, F + flows + part_n + lam_n,
-                     flow_build_umma_scratch_floats((long long)B * T, N, n_basis));
-  }
   GemmParams g;
   g.ksplit = kScanKsplit;
   g.part = F + flows;

@@ -22,21 +22,6 @@ NVCC_FLAGS = [
 ]
 
 
-def cutlass_flags():
-    """Include path of the CUTLASS / CuTe header tree vendored with the image (flashinfer's copy, CUTLASS 4.x with the
-    sm_100 FastFP32 collective) for csrc/flow_build_umma.cu; without it that file compiles to a stub
-    (-DLNCDE_NO_CUTLASS) and "k2_de_v2" = 3 reports LNCDE_ERR_UNSUPPORTED."""
-    import sysconfig
-
-    roots = [os.environ.get("LNCDE_CUTLASS_DIR"),
-             os.path.join(sysconfig.get_paths()["purelib"], "flashinfer", "data", "cutlass")]
-    for root in roots:
-        if root and os.path.exists(os.path.join(root, "include", "cutlass", "gemm", "collective",
-                                                "sm100_mma_warpspecialized_emulated.hpp")):
-            return ["-I", os.path.join(root, "include"), "--expt-relaxed-constexpr"]
-    return ["-DLNCDE_NO_CUTLASS"]
-
-
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cc")))
 
@@ -49,7 +34,7 @@ def _digest() -> str:
         h.update(f.encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS + cutlass_flags()[-1:]).encode())
+    h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -71,8 +56,6 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags=(), li
     for src in sources():
         obj = os.path.join(build_dir, os.path.basename(src) + ".o")
         cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(REPO, "include"), "-I", CSRC, "-x", "cu", "-c", src, "-o", obj]
-        if os.path.basename(src) == "flow_build_umma.cu":
-            cmd[1:1] = cutlass_flags()
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -101,8 +84,6 @@ def _build_variant(extra_flags, lib_path, verbose=False) -> str:
         obj = os.path.join(build_dir, os.path.basename(src) + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-I", os.path.join(REPO, "include"), "-I", CSRC, "-x", "cu", "-c", src,
                "-o", obj]
-        if os.path.basename(src) == "flow_build_umma.cu":
-            cmd[1:1] = cutlass_flags()
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

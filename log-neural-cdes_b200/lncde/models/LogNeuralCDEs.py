@@ -70,7 +70,7 @@ class _LogNCDESolve(torch.autograd.Function):
         # training mode: hand the adjoint workspace to the forward so it can keep its intermediates
         train = any(ctx.needs_input_grad)
         nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, C, width, n_hidden, depth, n_steps) if train else 0
-        ws = _workspace(nbytes, ys.device) if train else None
+        ws = _workspace(nbytes, ys.device) if train else None  # bumps the generation: earlier saved forwards are void
         st = L.lncde_logncde_fwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(y0c),
                                  _lib.ptr(rows), _lib.ptr(scale), _lib.ptr(ys), B, K, D, H, C, width, n_hidden,
                                  depth, n_steps, _lib.ptr(ws), nbytes)
@@ -79,8 +79,6 @@ class _LogNCDESolve(torch.autograd.Function):
         ctx.dims = dims
         # shared grow-only scratch: its contents are valid until the next training-mode forward on this device
         ctx.ws = ws
-        if train:
-            _WS_GEN[ys.device] = _WS_GEN.get(ys.device, 0) + 1
         ctx.ws_gen = _WS_GEN.get(ys.device, 0)
         return ys
 
@@ -97,13 +95,15 @@ class _LogNCDESolve(torch.autograd.Function):
         # LNCDE_FLAG_SAVED_FWD only if nobody has reused the scratch since our forward wrote it
         saved = 2 if (ws is not None and _WS.get(ys.device) is ws and _WS_GEN.get(ys.device) == ctx.ws_gen) else 0
         if ws is None or saved == 0:
-            ws = _workspace(nbytes, ys.device)
+            ws = _workspace(nbytes, ys.device)  # recompute mode overwrites the scratch: bumps the generation too
         g_params = torch.empty_like(mlp_flat)
         g_y0 = torch.empty((B, H), device=ys.device, dtype=torch.float32)
         st = L.lncde_logncde_bwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(rows),
                                  _lib.ptr(scale), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_params), _lib.ptr(g_y0),
                                  B, K, D, H, C, width, n_hidden, depth, n_steps, _lib.ptr(ws), nbytes, saved)
         _lib.check(st, "lncde_logncde_bwd")
+        if saved:  # the sweep wrote its (left, right) gradient pairs over the buffer: a second backward must recompute
+            _WS_GEN[ys.device] = _WS_GEN.get(ys.device, 0) + 1
         return g_params, None, g_y0, None, None, None
 
 
@@ -113,7 +113,10 @@ _RETIRED = []
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only scratch buffer per device (the C ABI never allocates)."""
+    """Grow-only scratch buffer per device (the C ABI never allocates).  Every hand-out is a WRITE claim and bumps the
+    device's generation counter: a saved-forward adjoint (LNCDE_FLAG_SAVED_FWD) is only taken when no other solve -
+    a later training forward, a recompute-mode adjoint, an NRDE adjoint - has been given the buffer since."""
+    _WS_GEN[device] = _WS_GEN.get(device, 0) + 1
     cur = _WS.get(device)
     if cur is None or cur.numel() < nbytes:
         if cur is not None:
@@ -171,6 +174,8 @@ class LogNeuralCDE:
         self.logsig_dim = len(hs)
         self.intervals = torch.as_tensor(np.asarray(intervals, np.float32))
         self._table = None
+        self._tables = {}
+        self._table_ts = None
 
     # -- parameters -----------------------------------------------------------------
     def parameters(self):
@@ -181,19 +186,31 @@ class LogNeuralCDE:
 
     # -- stage table ----------------------------------------------------------------
     def _stage_table(self, ts, n_rows):
-        key = (ts.data_ptr(), tuple(ts.shape), n_rows)  # no device read-back on the steady-state path
-        if self._table is None or self._table[0] != key:
-            t0, t1 = float(ts[0, 0]), float(ts[0, -1])
+        # Two-level cache.  Level 1: the very tensor seen last time (pointer + shape; the tensor is kept referenced so its
+        # allocation cannot be recycled for another grid) - no device read-back on the steady-state path.  Level 2: the
+        # VALUES (t0, t1, L, n_rows) the table is a function of - a fresh `ts` tensor per batch costs one two-float
+        # read-back, not a rebuild.
+        key = (ts.data_ptr(), tuple(ts.shape), n_rows)
+        if self._table is not None and self._table[0] == key:
+            return self._table[1:]
+        t0, t1 = (float(v) for v in ts[0, [0, -1]].tolist())
+        vkey = (t0, t1, int(ts.shape[1]), n_rows)
+        if vkey not in self._tables:
             rows, scale, grid = stage_table(t0, t1, self.intervals.numpy(), self.dt0, n_rows, self.max_steps)
+            assert 0 <= int(rows.min()) and int(rows.max()) < n_rows, "stage table reads a logsig row that does not exist"
             interp = None
             if not self.classification:
-                step = np.float32(self.output_step / ts.shape[1])
-                times = np.arange(step, 1.0, step, dtype=np.float32)  # LogNeuralCDEs.py:143-145
+                # jnp.arange(step, 1.0, step) with a Python-float step: the LENGTH is computed in float64, the values are
+                # then cast to float32 (LogNeuralCDEs.py:143-145)
+                step = self.output_step / ts.shape[1]
+                times = np.arange(step, 1.0, step).astype(np.float32)
                 idx = np.clip(np.searchsorted(grid, times, side="left"), 1, len(grid) - 1)
                 w = ((times - grid[idx - 1]) / (grid[idx] - grid[idx - 1])).astype(np.float32)
                 interp = (torch.from_numpy(idx).to(self.device), torch.from_numpy(w).to(self.device)[None, :, None])
-            self._table = (key, torch.from_numpy(rows.reshape(-1)).to(self.device).view(-1, 2),
-                           torch.from_numpy(scale.reshape(-1)).to(self.device).view(-1, 2), interp)
+            self._tables[vkey] = (torch.from_numpy(rows.reshape(-1)).to(self.device).view(-1, 2),
+                                  torch.from_numpy(scale.reshape(-1)).to(self.device).view(-1, 2), interp)
+        self._table = (key, *self._tables[vkey])
+        self._table_ts = ts
         return self._table[1:]
 
     # -- forward ---------------------------------------------------------------------

@@ -102,6 +102,8 @@ class NeuralRDE:
         self.linear2 = _Linear(self.params, off, H, self.label_dim)
         self.intervals = torch.as_tensor(np.asarray(intervals, np.float32))
         self._table = None
+        self._tables = {}
+        self._table_ts = None
 
     def parameters(self):
         return [self.params]
@@ -110,19 +112,31 @@ class NeuralRDE:
         return self.params[: self.n_field]
 
     def _stage_table(self, ts, n_rows):
+        # Two-level cache.  Level 1: the very tensor seen last time (pointer + shape; the tensor is kept referenced so its
+        # allocation cannot be recycled for another grid) - no device read-back on the steady-state path.  Level 2: the
+        # VALUES (t0, t1, L, n_rows) the table is a function of - a fresh `ts` tensor per batch costs one two-float
+        # read-back, not a rebuild.
         key = (ts.data_ptr(), tuple(ts.shape), n_rows)
-        if self._table is None or self._table[0] != key:
-            t0, t1 = float(ts[0, 0]), float(ts[0, -1])
+        if self._table is not None and self._table[0] == key:
+            return self._table[1:]
+        t0, t1 = (float(v) for v in ts[0, [0, -1]].tolist())
+        vkey = (t0, t1, int(ts.shape[1]), n_rows)
+        if vkey not in self._tables:
             rows, scale, grid = stage_table(t0, t1, self.intervals.numpy(), self.dt0, n_rows, self.max_steps)
+            assert 0 <= int(rows.min()) and int(rows.max()) < n_rows, "stage table reads a logsig row that does not exist"
             interp = None
             if not self.classification:
-                step = np.float32(self.output_step / ts.shape[1])
-                times = np.arange(step, 1.0, step, dtype=np.float32)  # NeuralCDEs.py:244-246
+                # jnp.arange(step, 1.0, step) with a Python-float step: the LENGTH is computed in float64, the values are
+                # then cast to float32 (NeuralCDEs.py:244-246)
+                step = self.output_step / ts.shape[1]
+                times = np.arange(step, 1.0, step).astype(np.float32)
                 idx = np.clip(np.searchsorted(grid, times, side="left"), 1, len(grid) - 1)
                 w = ((times - grid[idx - 1]) / (grid[idx] - grid[idx - 1])).astype(np.float32)
                 interp = (torch.from_numpy(idx).to(self.device), torch.from_numpy(w).to(self.device)[None, :, None])
-            self._table = (key, torch.from_numpy(rows.reshape(-1)).to(self.device).view(-1, 2),
-                           torch.from_numpy(scale.reshape(-1)).to(self.device).view(-1, 2), interp)
+            self._tables[vkey] = (torch.from_numpy(rows.reshape(-1)).to(self.device).view(-1, 2),
+                                  torch.from_numpy(scale.reshape(-1)).to(self.device).view(-1, 2), interp)
+        self._table = (key, *self._tables[vkey])
+        self._table_ts = ts
         return self._table[1:]
 
     def hidden_states(self, X):

@@ -146,8 +146,8 @@ def interp_outputs(ys, grid, out_times):
 
 def regression_times(n_ts: int, output_step: int) -> np.ndarray:
     """LogNeuralCDEs.py:143-145: arange(step, 1, step) with step = output_step/len(ts), plus t1."""
-    step = np.float32(output_step / n_ts)
-    return np.arange(step, 1.0, step, dtype=np.float32)
+    step = output_step / n_ts  # Python float: jnp.arange computes the length in float64, then casts the values
+    return np.arange(step, 1.0, step).astype(np.float32)
 
 
 def lip2_norm(layers, lambd):

@@ -57,5 +57,5 @@ bench.WORKLOADS["eigenworms_logncde"].update(B=2, L=120, dt0=0.1)
 bench.N_ROT = 2
 bench.K1_ROOFLINE_BATCH = 4
 bench.FFMA_PROBE_SHAPE = (2, 3)
-sys.argv = ["bench.py", "--steps", "2", "--warmup", "3", "--cpu-seconds", "0.5"] + sys.argv[1:]
+sys.argv = ["bench.py", "--steps", "2", "--warmup", "3"] + sys.argv[1:]
 bench.main()

@@ -56,9 +56,10 @@ def eye(n, dtype=torch.float64):
 
 
 def arange(*a, dtype=None):
-    # jax computes float ranges in float32 (x64 is off in the reference)
+    # jnp.arange on concrete Python floats: numpy computes the range (and its LENGTH) in float64, the result is then
+    # canonicalised to float32 (x64 is off in the reference)
     if any(isinstance(v, (__builtins__["float"] if isinstance(__builtins__, dict) else __builtins__.float, _np.floating)) for v in a):
-        return torch.from_numpy(_np.arange(*[_np.float32(v) for v in a], dtype=_np.float32))
+        return torch.from_numpy(_np.arange(*a).astype(_np.float32))
     return torch.arange(*a)
 
 

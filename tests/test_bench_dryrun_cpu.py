@@ -45,7 +45,7 @@ def test_bench_json_contract_over_emulator():
     bd = out["step_breakdown_ms"]
     assert set(bd) == {"logsig_K1", "forward_solve_K3+readout", "backward_K3b+gemm", "adam_K4", "whole_step"}
     # autotune plumbing: K1 variant 1 (verified, 20 % faster) on; K3 variant 1 failed parity, variant 2 within the margin
-    assert out["config"]["tuning"] == {"k1_tma": 1, "k3_fused": 0}
+    assert out["impl_detail"]["tuning"] == {"k1_tma": 1, "k3_fused": 0}
     assert "TMA" in rf["kernel"] and rf["traffic"] is None  # no ncu capture of the variant: traffic is not claimed
 
 

@@ -351,9 +351,10 @@ def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B, level):
     rounding.  Level 2: the flow build on the tensor pipe (3xTF32 split precision, mma.sync modelled by the emulator
     with the documented fragment layout) - fp32-grade flows, everything inside the parity tolerance; n_basis > 36
     (depth-3 sizes, several K tiles) keeps the default reverse path.  Level 3: the flow build through
-    flow_build_umma.cu - on the emulator the operand PACKING kernels (16-byte row pitch, identity as one more K column)
-    and the workspace layout are the code under test, the tcgen05 GEMM itself is replaced by a plain fp32 contraction
-    of the packed operands; the rest of the step is level 2."""
+    flow_tcgen05.cu (block sizes that are multiples of 128; others keep level 2) - on the emulator the operand PACKING
+    kernel (the K-major / no-swizzle shared-memory image of tcgen05.mma, hi | lo TF32 planes, K padded to 32), the
+    identity and the workspace layout are the code under test, the MMA unit itself is replaced by a plain fp32
+    evaluation of the same three partial products from the packed operands; the rest of the step is level 2."""
     rng = np.random.default_rng(11)
     H, D = nb * bs, n_basis + 2  # one unused trailing logsig column
     lie = rng.normal(size=(nb, bs, bs, n_basis)) * (0.5 / np.sqrt(bs))

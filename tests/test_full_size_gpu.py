@@ -56,6 +56,44 @@ def test_logncde_full_length_matches_oracle(built_lib):
     assert rel_err(ys, want) < 2e-5
 
 
+def test_logncde_full_length_loss_and_gradient_match_oracle(built_lib):
+    """The bench configuration itself (scale = 1000, lambd = 1e-3, 1 499 Heun steps; B = 4 so that the fp64 oracle -
+    reference formulation, torch autograd through all 2 998 stages - finishes in about a minute): loss and the gradient
+    of every parameter block through train.classification_loss, at the north-star tolerance 1e-5."""
+    from lncde import train as T
+    from lncde.data_dir.generate_paths import calc_paths
+
+    B = 4
+    x = _ew_paths(B, seed=2345)
+    model, ts, iv = _ew_model(scale=1000.0)
+    xg = torch.from_numpy(x).cuda()
+    ls = calc_paths(xg, S_EW, 2)
+    X = (torch.from_numpy(ts)[None].expand(B, -1), ls, xg[:, 0, :].contiguous())
+    y = torch.eye(5, device="cuda")[torch.arange(B) % 5]
+    loss, grads = T.classification_loss(model, X, y)
+    lay = [(l.weight.detach().cpu().double().requires_grad_(True), l.bias.detach().cpu().double().requires_grad_(True))
+           for l in model.vf.mlp.layers]
+    W1 = model.linear1.weight.detach().cpu().double().requires_grad_(True)
+    b1 = model.linear1.bias.detach().cpu().double().requires_grad_(True)
+    W2 = model.linear2.weight.detach().cpu().double().requires_grad_(True)
+    b2 = model.linear2.bias.detach().cpu().double().requires_grad_(True)
+    rows, sc, _ = O.stage_table(ts, iv, DT0, 1499)
+    y0 = torch.from_numpy(x[:, 0]).double() @ W1.T + b1
+    ys = O.solve(lay, ls.cpu().double(), y0, rows, sc, C_EW, H_EW, 2)
+    pred = torch.softmax(ys[:, -1] @ W2.T + b2, -1)
+    lo = O.classification_loss(pred, y.cpu().double()) + O.lip2_norm(lay, 1e-3)
+    lo.backward()
+    assert abs(float(loss) - float(lo.detach())) < 1e-5 * max(1.0, abs(float(lo.detach())))
+    g = grads.cpu().numpy()
+    blocks = [t.grad.reshape(-1).numpy() for W, b in lay for t in (W, b)] + \
+        [W1.grad.reshape(-1).numpy(), b1.grad.numpy(), W2.grad.reshape(-1).numpy(), b2.grad.numpy()]
+    off = 0
+    for k, want in enumerate(blocks):
+        assert rel_err(g[off:off + want.size], want) < 1e-5, ("parameter block", k)
+        off += want.size
+    assert off == g.size
+
+
 def test_logncde_zero_control_is_identity(built_lib):
     model, ts, iv = _ew_model()
     B = 4

@@ -75,8 +75,8 @@ def test_linear_ncde_loss_and_grads(built_lib, case):
     assert abs(float(loss) - float(lo)) < TOL * max(1.0, abs(float(lo)))
     g = grads.cpu().numpy()
     nA = vf_A.numel()
-    assert rel_err(g[:nA], go.numpy()[:nA]) < 5 * TOL
-    assert rel_err(g[nA:], go.numpy()[nA:]) < 5 * TOL
+    assert rel_err(g[:nA], go.numpy()[:nA]) < TOL
+    assert rel_err(g[nA:], go.numpy()[nA:]) < TOL
 
 
 def test_hidden_states_match_oracle_and_chunked_scan(built_lib):

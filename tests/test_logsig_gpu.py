@@ -59,7 +59,8 @@ def test_compat_and_chunk(built_lib, compat):
     assert np.array_equal(got.astype(np.float64), want)
 
 
-@pytest.mark.parametrize("C,s,L", [(7, 12, 17984), (6, 12, 17984), (6, 16, 896), (7, 16, 896), (7, 10, 4992), (4, 10, 4992)])
+@pytest.mark.parametrize("C,s,L", [(7, 12, 17984), (6, 12, 17984), (6, 16, 896), (7, 16, 896), (7, 10, 4992), (4, 10, 4992),
+                                   (7, 10, 49920), (4, 10, 49920)])  # the last two: PPG-DaLiA at its full length
 def test_float_paths_depth2(built_lib, C, s, L):
     x = _walk(4, L, C)
     want = paths.calc_paths(x, s, 2, np.float64)

@@ -175,3 +175,57 @@ def test_calc_paths_empty_batch_and_nan_containment(emulated):
     bad = torch.isnan(got).any(-1)
     assert bad[1, 4] and int(bad.sum()) == 1
     assert torch.equal(got[~bad], clean[~bad])
+
+
+def test_saved_forward_scratch_is_not_reused_after_another_solve(emulated):
+    """Two training-mode forwards, then the backwards in FORWARD order, and an NRDE adjoint in between: the
+    shared grow-only scratch holds the saved intermediates of the LAST forward only, every other adjoint must fall back
+    to recompute mode.  Compared with gradients taken one solve at a time."""
+    from lncde.models import LogNeuralCDEs as M
+    from lncde.models.NeuralCDEs import _NRDESolve
+    from oracle import log_ncde as O
+    from oracle import nrde as ON
+    from oracle import paths
+
+    B, L, C_, s, depth, H, width, nh = 2, 240, 7, 12, 2, 128, 32, 2  # specialised kernels: saved-forward mode exists
+    rng = np.random.default_rng(3)
+    ts = paths.make_ts(L)
+    iv = paths.make_intervals(ts, s)
+    dims = (H, C_, width, nh, depth)
+
+    def problem(seed):
+        r = np.random.default_rng(seed)
+        x = np.cumsum(r.normal(scale=0.3, size=(B, L, C_)), axis=1).astype(np.float32)
+        ls = torch.from_numpy(paths.calc_paths(x, s, depth, np.float32))
+        rows, sc, grid = O.stage_table(ts, iv, 0.05, ls.shape[1])
+        flat = O.flatten_params(O.init_params(H, C_, width, nh, scale=3.0, seed=seed, dtype=torch.float32))
+        y0 = torch.from_numpy(r.normal(size=(B, H)).astype(np.float32) * 0.5)
+        g = torch.from_numpy(r.normal(size=(B, len(grid), H)).astype(np.float32))
+        return flat, ls, y0, torch.from_numpy(rows), torch.from_numpy(sc), g
+
+    def grads_alone(p):
+        flat, ls, y0, rows, sc, g = p
+        f, y = flat.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        (M._LogNCDESolve.apply(f, ls, y, rows, sc, dims) * g).sum().backward()
+        return f.grad.clone(), y.grad.clone()
+
+    pa, pb = problem(1), problem(2)
+    want_a, want_b = grads_alone(pa), grads_alone(pb)
+    fa, ya = pa[0].clone().requires_grad_(True), pa[2].clone().requires_grad_(True)
+    fb, yb = pb[0].clone().requires_grad_(True), pb[2].clone().requires_grad_(True)
+    out_a = M._LogNCDESolve.apply(fa, pa[1], ya, pa[3], pa[4], dims)
+    out_b = M._LogNCDESolve.apply(fb, pb[1], yb, pb[3], pb[4], dims)  # overwrites the intermediates saved for A
+    (out_a * pa[5]).sum().backward()  # must recompute (and thereby clobbers what B saved)
+    (out_b * pb[5]).sum().backward()  # must recompute too
+    for got, want in ((fa.grad, want_a[0]), (ya.grad, want_a[1]), (fb.grad, want_b[0]), (yb.grad, want_b[1])):
+        assert rel_err(got.numpy(), want.numpy()) < 1e-6
+
+    # an NRDE adjoint between a Log-NCDE forward and its backward uses the same scratch
+    fa.grad = ya.grad = None
+    out_a = M._LogNCDESolve.apply(fa, pa[1], ya, pa[3], pa[4], dims)
+    Dm = pa[1].shape[2] - 1
+    nflat = ON.flatten_params(ON.init_params(16, Dm, 8, 2, scale=1.0, seed=4, dtype=torch.float32)).requires_grad_(True)
+    ny0 = torch.from_numpy(rng.normal(size=(B, 16)).astype(np.float32)).requires_grad_(True)
+    _NRDESolve.apply(nflat, pa[1], ny0, pa[3], pa[4], (16, 8, 2)).sum().backward()
+    (out_a * pa[5]).sum().backward()
+    assert rel_err(fa.grad.numpy(), want_a[0].numpy()) < 1e-6 and rel_err(ya.grad.numpy(), want_a[1].numpy()) < 1e-6

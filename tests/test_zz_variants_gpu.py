@@ -1,12 +1,9 @@
 """Kernel variants that exist in the library but are not the default yet (tuning keys of include/lncde_b200.h).
 
-All of them were written after the GPU budget of round 1 was spent: verified against the default kernels on the host
-emulator (tests/test_emu_kernels_cpu.py, tests/test_emu_schedules_cpu.py; K1 TMA and K3 fused level 1 bit for bit) but not
-yet run on a B200 - "k1_tma" 1 / 2, "k3_fused" 1 / 2, "k2_fused_d", "k2_de_v2" 1 / 2 / 3 (level 3 launches a CUTLASS
-tcgen05 kernel the emulator cannot model at all: a process of its own), "k3_stream", "k2_pscan".
-They are exercised here through scripts/variant_check.py in a subprocess per kernel family, so that a fault or a hang
-cannot poison this process, and the tests are non-strict xfails until a hardware run has been seen: XPASS = correct
-on the GPU (parity against the DEFAULT CUDA kernels and, without --no-oracle, the fp64 oracle)."""
+Every variant passed on the driver's B200 at the end of round 1 (GPUTEST_r01.json: 23 XPASS), so these are plain
+asserts now.  They are exercised through scripts/variant_check.py in a subprocess per kernel family, so that a fault
+or a hang cannot poison this process: parity against the DEFAULT CUDA kernels and, without --no-oracle, the fp64
+oracle."""
 import json
 import os
 import subprocess
@@ -17,7 +14,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REASON = "variant not yet run on hardware (emulator-verified only); the default path does not use it"
 
 
 _results = {}
@@ -53,39 +49,32 @@ def _check(which, level=None):
 
 
 @pytest.mark.parametrize("level", [1, 2])  # 1: bulk-copy staging, 2: the same kernel persistent and double-buffered
-@pytest.mark.xfail(strict=False, reason=REASON)
 def test_k1_tma_variant_parity(built_lib, level):
     _check("k1", level)
 
 
 @pytest.mark.parametrize("level", [1, 2])  # fused-phase levels of the specialised Log-NCDE kernels
-@pytest.mark.xfail(strict=False, reason=REASON)
 def test_k3_fused_variant_parity(built_lib, level):
     _check("k3", level)
 
 
-@pytest.mark.xfail(strict=False, reason=REASON)
 def test_k2_fused_diagonal_variant_parity(built_lib):
     _check("k2")
 
 
 @pytest.mark.parametrize("level", [1, 2, 3])  # 1: FFMA 8 x 8, 2: 3xTF32 mma.sync, 3: tcgen05 (CUTLASS FastFP32) flow build
-@pytest.mark.xfail(strict=False, reason=REASON)
 def test_k2_dense_v2_variant_parity(built_lib, level):
     _check("k2de", level)
 
 
-@pytest.mark.xfail(strict=False, reason=REASON)
 def test_k3_generic_stream_variant_parity(built_lib):
     _check("k3g")
 
 
-@pytest.mark.xfail(strict=False, reason=REASON)
 def test_k2_time_parallel_scan_variant_parity(built_lib):
     _check("k2p")
 
 
-@pytest.mark.xfail(strict=False, reason="measurement helper added after the last hardware run")
 def test_ffma_probe_runs(built_lib):
     """lncde_probe_ffma (csrc/probe.cu): launches, every chain converges to the fixed point 1 of x -> 0.999 x + 0.001."""
     import torch
