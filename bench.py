@@ -27,7 +27,6 @@ for _p in (REPO, os.path.join(REPO, "log-neural-cdes_b200")):
 import numpy as np
 import torch
 
-T_PROCESS_START = time.time()
 
 # Default = BASELINE.json configs[1]: EigenWorms Log-NCDE (experiment_configs/repeats/log_ncde/EigenWorms.json),
 # time channel included.  The other entries are the remaining BASELINE configs, selectable with --workload
@@ -77,6 +76,7 @@ WL = dict(WORKLOADS["eigenworms_logncde"])
 N_ROT = 16  # distinct input batches rotated through (16 x 16.1 MB = 258 MB > 126 MB L2)
 FFMA_PROBE_SHAPE = (148 * 8, 2048)  # CTAs x loop trips of the FP32 probe launch (39.7 GFLOP: ~0.5 ms)
 K1_ROOFLINE_BATCH = 2048  # paths per launch of the K1 roofline leg (1.03 GB read + 0.36 GB written: > L2)
+K1_TMA_DRAM_TRAFFIC_BYTES = None  # per launch at that shape, from the committed ncu --set full capture (set when it exists)
 
 
 def peaks():
@@ -190,50 +190,23 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU port")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    # Build + kernel-variant autotune run BEFORE the process group exists: rank 0 works, the other ranks wait on a FILE
-    # (no rank spins inside NCCL meanwhile - round 1 had ranks 1..N-1 74 % "busy" for a minute doing nothing).
-    tuning, tune_report = {"k1_tma": 0, "k3_fused": 0}, None
-    families = {"log_ncde": ("k1", "k3"), "diagonal_linear_ncde": ("k1", "k2", "k2p"), "dense_linear_ncde": ("k1", "k2de"),
-                "bd_linear_ncde": ("k1", "k2p")}
-    generic = WL["model"] == "log_ncde" and (WL["H"], WL["vf_width"], WL["vf_depth"]) != (128, 32, 2)
-    if generic:
-        families["log_ncde"] = ("k1", "k3g")  # shapes outside the specialised kernels: the generic solve kernels
-    handoff = os.path.join(REPO, f".lncde_bench_handoff_{os.environ.get('MASTER_PORT', '0')}.json")
+    # The build runs BEFORE the process group exists: rank 0 compiles (a no-op when the .so is current), the other ranks
+    # wait on its stamp file - nobody spins inside NCCL meanwhile.  Which kernels run is decided by the library from the
+    # shapes (defaults fixed from the round-2 hardware measurements; there is no tuning state and no autotune any more).
     if rank == 0:
         _build.build_library()
-        if not args.no_autotune and (WL["model"] in families):
-            tuning, tune_report = cached_autotune(families[WL["model"]], refresh=args.retune)
-        if world > 1:
-            with open(handoff + ".tmp", "w") as fh:
-                json.dump({"tuning": tuning, "t": time.time()}, fh)
-            os.replace(handoff + ".tmp", handoff)
     else:
         t_wait = time.time()
-        while True:  # sleeping on the host, GPU idle
-            try:
-                with open(handoff) as fh:
-                    box = json.load(fh)
-                if box["t"] >= T_PROCESS_START - 5.0:
-                    tuning = box["tuning"]
-                    break
-            except (OSError, ValueError, KeyError):
-                pass
+        while not (os.path.exists(_build.LIB_PATH) and os.path.exists(_build.STAMP)):
             if time.time() - t_wait > 900:
-                raise SystemExit("bench.py: rank 0 never published its tuning decision")
+                raise SystemExit("bench.py: rank 0 never finished building the library")
             time.sleep(0.2)
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
-        if rank == 0:
-            try:
-                os.remove(handoff)
-            except OSError:
-                pass
     _lib.lib()
-    for k, v in tuning.items():
-        _lib.set_tuning(k, v)
 
     B, L, C = WL["B"], WL["L"], WL["C"]
     x_host, lab_host = make_inputs(rank, N_ROT)
@@ -356,16 +329,14 @@ def run_ours(args):
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": bench_config(world),
-            "impl_detail": {"launch": "one CUDA graph per step" if use_graph else "eager", "tuning": tuning,
-                            "l2_this_run": l2_note},
+            "impl_detail": {"launch": "one CUDA graph per step" if use_graph else "eager", "l2_this_run": l2_note,
+                            "kernels": "library defaults (chosen by shape; include/lncde_b200.h)"},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": int(x_pin[0].numel() * 4 + lab_pin[0].numel() * 4),
                     "d2h_bytes_per_step": 4, "last_loss": last_loss},
-            "gpu_launches": own_launches_per_step(WL["model"], tuning) * args.steps,
+            "gpu_launches": own_launches_per_step(WL["model"], WL) * args.steps,
             "clocks": clocks,
         }
-        if tune_report is not None:
-            out["autotune"] = tune_report
         if WL["model"].endswith("linear_ncde"):
             # K2 workloads: the whole step against its COMPULSORY bytes (logsig rows in, states out; the
             # reverse sweep reads the rows, the states and their cotangents) - flows, partials and the bracket GEMM
@@ -382,7 +353,7 @@ def run_ours(args):
         if args.workload == "eigenworms_logncde":
             if world > 1:
                 args.no_cpu_baseline = True  # rank 0 at N = 1 only: with N ranks busy on the host the figure is meaningless
-            out.update(extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms / args.steps, tuning))
+            out.update(extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms / args.steps))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -390,23 +361,21 @@ def run_ours(args):
         print(json.dumps(out))
 
 
-def own_launches_per_step(model_name, tuning):
-    """Kernels of liblncde_b200.so launched by one train step (counted from the host code of csrc/, confirmed for the
-    default workload by the ncu launch list profiles/r01_launches_final.md)."""
+def own_launches_per_step(model_name, wl):
+    """Kernels of liblncde_b200.so launched by one train step (counted from the host code of csrc/ for the kernels the
+    library picks by default; confirmed for the default workload by the ncu launch list under profiles/)."""
     adam = 2                                     # adam_dev_kernel + the step-counter bump
     if model_name in ("log_ncde", "nrde"):
         return 1 + 1 + 1 + 3 + 1 + adam          # K1, solve fwd, adjoint sweep, 3 gradient-GEMM groups, gradient reduce
-    if model_name == "diagonal_linear_ncde" and tuning.get("k2_fused_d"):
+    if model_name == "diagonal_linear_ncde":
         return 1 + 1 + 2 + adam                  # K1, dlncde_fwd, dlncde_bwd + its reduce
-    fwd, bwd = 2, 3                              # flow build + scan | reverse scan, bracket GEMM, split-K reduce
-    if tuning.get("k2_pscan") and model_name != "dense_linear_ncde":
-        fwd, bwd = 1 + 3, 4 + 2                  # products / boundary / apply | products / local / boundary / local + GEMM, reduce
-    if model_name == "dense_linear_ncde" and int(tuning.get("k2_de_v2", 0)) >= 3:
-        fwd = 3 + 1                              # two operand packs + the tcgen05 GEMM, scan
-    return 1 + fwd + bwd + adam
+    if model_name == "dense_linear_ncde":
+        # two operand packs + tcgen05 flow build + scan | lam-only reverse scan, triple-product gradient, split-K reduce
+        return 1 + (3 + 1) + 3 + adam
+    return 1 + (1 + 3) + (4 + 2) + adam          # time-parallel scans: products / boundary / apply | 4 + GEMM, reduce
 
 
-def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_per_step, tuning):
+def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_per_step):
     """Roofline of the HBM-bound kernel (K1 logsig at a batch larger than L2), per-kernel
     breakdown of the step, and the CPU baseline.  Rank 0 only."""
     from lncde import train as T
@@ -439,15 +408,12 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     k1_ms = e0.elapsed_time(e1) / n_rep
     alg_bytes = Bk * (4 * L * C + 4 * K * D)  # 677 436 B per sample (EigenWorms, C = 7)
     ach = alg_bytes / (k1_ms * 1e-3) / 1e9
-    k1_tma = int(tuning.get("k1_tma", 0))
-    res["roofline"] = {"kernel": ("logsig_levy_tma_kernel<7,depth2%s> (K1, TMA staging)" % (",persistent" if k1_tma > 1 else "")
-                                  if k1_tma else "logsig_levy_kernel<7,depth2> (K1)"),
+    res["roofline"] = {"kernel": "logsig_levy_tma_kernel<7,depth2> (K1, TMA bulk-copy staging)",
                        "bound": "hbm", "achieved": ach,
                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                        # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed
-                       # ncu --set full capture profiles/r01_full_logsig_final.md (1.0525 GB + 0.2990 GB);
-                       # no capture of the TMA variant exists yet
-                       "traffic": None if k1_tma else 1.3515e9,
+                       # ncu --set full capture (profiles/r02_full_k1_tma.md); None until that capture exists
+                       "traffic": K1_TMA_DRAM_TRAFFIC_BYTES,
                        "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs (burst copy)",
                        "launch_ms": k1_ms, "algorithmic_bytes_per_launch": alg_bytes,
                        "shape": f"B={Bk} x EigenWorms (L={L}, C={C}, stepsize {s}, depth 2): inputs "
@@ -470,8 +436,7 @@ def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_p
     flop = 2.0 * (2 * macs_stage) * n_stage * WL["B"]   # transposed mat-vecs + weight-gradient outer products
     t_ms = res["step_breakdown_ms"]["backward_K3b+gemm"]
     ach = flop / (t_ms * 1e-3) / 1e12
-    res["roofline_dominant"] = {"kernel": "logncde_bwd_saved_kernel<7,depth2%s> + outer_gemm_kernel (K3b)"
-                                          % (",fused" if tuning.get("k3_fused") else ""),
+    res["roofline_dominant"] = {"kernel": "logncde_bwd_saved_kernel<7,depth2> + outer_gemm_kernel (K3b)",
                                 "bound": "latency (dependent phases), fp32 issue", "achieved": ach,
                                 "peak": ffma_peak, "unit": "TFLOP/s", "frac": ach / ffma_peak,
                                 "peak_source": ffma_src,
@@ -502,125 +467,6 @@ def measured_ffma_tflops(dev, reps=5):
     e1.record()
     torch.cuda.synchronize()
     return L.lncde_probe_ffma_flops(blocks, iters) * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
-
-
-def decide_tuning(rep, margin=0.98):
-    """A variant is used only if ITS parity check passed and it beat the default by the margin."""
-    choice = {"k1_tma": 0, "k3_fused": 0}
-    k1, k3 = rep.get("k1", {}), rep.get("k3", {})
-    for fam, key, base, variants in (("k2", "k2_fused_d", "default_B32", ((1, "fused_B32"),)),
-                                     ("k2de", "k2_de_v2", "default", ((1, "v2"), (2, "v2_tc"), (3, "v2_umma"))),
-                                     ("k3g", "k3_stream", "default_ppg", ((1, "stream_ppg"),))):
-        r = rep.get(fam)
-        if r is None:
-            continue
-        choice[key] = 0
-        try:
-            if "error" in r or "timing" not in r:
-                continue
-            par = r.get("parity", {})
-            best_ms = margin * r["timing"][base]["ms"]
-            for v, name in variants:
-                ok = par.get("ok_by_variant", {}).get(str(v), par.get("ok")) if "ok_by_variant" in par else par.get("ok")
-                if ok and "ms" in r["timing"].get(name, {}) and r["timing"][name]["ms"] < best_ms:
-                    choice[key], best_ms = v, r["timing"][name]["ms"]
-        except (KeyError, TypeError):
-            pass
-    k2p = rep.get("k2p")
-    if k2p is not None:  # time-parallel scans: judged on the workload's own model (BD or D step)
-        choice["k2_pscan"] = 0
-        try:
-            tag = "d" if WL.get("model") == "diagonal_linear_ncde" else "bd"
-            if "error" not in k2p and k2p.get("parity", {}).get("ok") and \
-                    k2p["timing"][f"pscan_{tag}"]["ms"] < margin * k2p["timing"][f"default_{tag}"]["ms"]:
-                choice["k2_pscan"] = 1
-        except (KeyError, TypeError):
-            pass
-    try:
-        if "error" not in k1 and "timing" in k1:
-            ok = k1.get("parity", {}).get("ok_by_variant", {})
-            best, best_ms = 0, margin * k1["timing"]["classic"]["ms"]
-            for v, name in ((1, "tma"), (2, "tma_persistent")):
-                if ok.get(str(v)) and name in k1["timing"] and k1["timing"][name]["ms"] < best_ms:
-                    best, best_ms = v, k1["timing"][name]["ms"]
-            choice["k1_tma"] = best
-        if "error" not in k3 and "timing" in k3:
-            ok = k3.get("parity", {}).get("ok_by_variant", {})
-            best, best_ms = 0, margin * k3["timing"]["default"]["ms"]
-            for v, name in ((1, "fused"), (2, "fused2")):
-                if ok.get(str(v)) and name in k3["timing"] and k3["timing"][name]["ms"] < best_ms:
-                    best, best_ms = v, k3["timing"][name]["ms"]
-            choice["k3_fused"] = best
-    except (KeyError, TypeError):
-        pass
-    return choice
-
-
-TUNE_CACHE = os.path.join(REPO, ".lncde_tune_cache.json")
-
-
-def cached_autotune(families, refresh=False):
-    """autotune() once per (GPU model, library build, kernel families): the 1 / 2 / 4 / 8-GPU runs of one session then
-    use the SAME kernels (scaling efficiency compares like with like) and only the first run pays for the check."""
-    from lncde import _build
-
-    try:
-        key = "|".join([torch.cuda.get_device_name(0), open(_build.STAMP).read().strip()[:16], ",".join(families)])
-    except OSError:
-        key = None
-    cache = {}
-    if key and not refresh and os.path.exists(TUNE_CACHE):
-        try:
-            cache = json.load(open(TUNE_CACHE))
-            if key in cache:
-                return cache[key]["tuning"], {"cached": True, "key": key, "report": cache[key]["report"]}
-        except (OSError, ValueError, KeyError, TypeError):
-            cache = {}
-    tuning, rep = autotune(families)
-    if key and not any("error" in (rep.get(f) or {}) for f in families):  # never pin a decision taken after a failed check
-        try:
-            cache[key] = {"tuning": tuning, "report": rep}
-            with open(TUNE_CACHE + ".tmp", "w") as fh:
-                json.dump(cache, fh)
-            os.replace(TUNE_CACHE + ".tmp", TUNE_CACHE)
-        except OSError:
-            pass
-    return tuning, rep
-
-
-def autotune(families=("k1", "k3")):
-    """Pick among kernel variants that compute the same result (lncde.set_tuning): scripts/variant_check.py runs
-    each variant in a SUBPROCESS (a variant that has never been on this hardware cannot take the bench down),
-    checks it against the default kernels and times both; a variant is switched on only if its parity check
-    passed there and it was measurably faster.  Returns (choices, raw report)."""
-    rep = {}
-
-    def run(which, extra=()):
-        try:
-            r = subprocess.run([sys.executable, os.path.join(REPO, "scripts", "variant_check.py"), "--no-oracle", "--only",
-                                which, *extra], capture_output=True, text=True, timeout=150)
-            if r.returncode != 0:
-                return {"error": f"exit {r.returncode}: {r.stderr[-300:]}"}
-            return json.loads(r.stdout.strip().splitlines()[-1]).get(which, {"error": "no result"})
-        except Exception as e:  # timeout, unparsable output
-            return {"error": f"{type(e).__name__}: {e}"[:300]}
-
-    for which in families:  # one process each: a fault or hang in one family does not lose the other
-        rep[which] = run(which) if which != "k2de" else run(which, ("--levels", "1,2"))
-        if which == "k2de" and "error" not in rep[which]:
-            # the tcgen05 level launches a CUTLASS kernel that has not been on this hardware: a process of its own,
-            # merged into the family's report only if it came back
-            r3 = run(which, ("--levels", "3"))
-            if "error" in r3:
-                rep[which]["level3_error"] = r3["error"]
-            else:
-                for sect in ("parity", "timing"):
-                    for k, v in r3.get(sect, {}).items():
-                        if isinstance(v, dict) and isinstance(rep[which].get(sect, {}).get(k), dict) and k != "default":
-                            rep[which][sect][k].update(v)
-                        elif k not in rep[which].get(sect, {}):
-                            rep[which].setdefault(sect, {})[k] = v
-    return decide_tuning(rep), rep
 
 
 def breakdown(model, opt, x_dev, lab_dev):
@@ -740,8 +586,7 @@ def run_reference(args):
     t_start = time.perf_counter()
     ref = CpuReferenceStep()
     n_full = len(ref.rows)
-    ref.step(0, n_steps=24)  # cross-check figure of round 1 (first 24 Heun steps, scaled); also warms torch up
-    t24_train, t24_logsig = ref.t_train, ref.t_logsig
+    ref.step(0, n_steps=16)  # torch's first pass (thread pool, functorch set-up), 16 Heun steps: not a measurement
     warm, steps, times = 0, 0, []
     for i in range(args.warmup):
         t, _ = ref.step(i)
@@ -762,10 +607,7 @@ def run_reference(args):
           "sample": f"oracle port (numpy logsig + torch-CPU fp32 Log-NCDE step, reference formulation 1+C JVPs, autograd "
                     f"adjoint, Adam) on the FULL workload: B={B}, all {n_full} Heun steps per step; {warm} warm-up + "
                     f"{steps} timed steps, {total / steps:.2f} s each, measured (no extrapolation)"
-                    + (f"; at N={world} rank 0 runs one rank's batch" if world > 1 else ""),
-          # round 1 reported THIS figure (first 24 Heun steps scaled to the full path); kept as a cross-check only
-          "cross_check": {"extrapolated": True, "first_24_heun_steps_s": t24_train,
-                          "value": B / (t24_train * n_full / min(24, n_full) + t24_logsig)}}
+                    + (f"; at N={world} rank 0 runs one rank's batch" if world > 1 else "")}
     out = {"impl": "reference", "metric": "train samples/sec EigenWorms Log-NCDE" if args.workload == "eigenworms_logncde"
            else f"train samples/sec {args.workload}", "value": value,
            "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warm,
@@ -813,9 +655,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, the contract): the workload's batch per GPU; strong: that batch split over the GPUs")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of as one CUDA graph")
-    ap.add_argument("--retune", action="store_true", help="ignore the cached autotune decision (.lncde_tune_cache.json)")
-    ap.add_argument("--no-autotune", action="store_true",
-                    help="keep the default kernels (skip the subprocess that checks and times the variants)")
+    ap.add_argument("--no-autotune", action="store_true", help="accepted and ignored (there is no autotune any more)")
     args = ap.parse_args()
     WL.clear()
     WL.update(WORKLOADS[args.workload])

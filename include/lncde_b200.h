@@ -15,7 +15,8 @@
  *  - return value: 0 OK; <0 argument errors (checked before any launch);
  *    >0 a cudaError_t from the launch
  *  - re-entrant and thread-safe; the only process-wide state is an immutable,
- *    mutex-guarded host cache of Hall tables keyed by (width, depth)
+ *    mutex-guarded host cache of Hall tables keyed by (width, depth).  Which kernel
+ *    serves a call is a function of its shapes and of its `flags` argument alone.
  */
 #ifndef LNCDE_B200_H_
 #define LNCDE_B200_H_
@@ -34,36 +35,21 @@ extern "C" {
 #define LNCDE_ERR_WORKSPACE (-4)   /* workspace too small                      */
 #define LNCDE_ERR_ALIGN (-5)       /* pointer not 16-byte aligned              */
 
-/* flags */
-#define LNCDE_FLAG_COMPAT 1u    /* reproduce reference quirks */
-#define LNCDE_FLAG_SAVED_FWD 2u /* lncde_logncde_bwd: workspace was filled by lncde_logncde_fwd */
-#define LNCDE_FLAG_K1_TMA 4u    /* lncde_logsig_fwd: closed-form kernel variant that moves its tiles with TMA bulk copies */
+/* flags (per call; entry points ignore bits that do not concern them) */
+#define LNCDE_FLAG_COMPAT 1u      /* reproduce reference quirks */
+#define LNCDE_FLAG_SAVED_FWD 2u   /* lncde_logncde_bwd: workspace was filled by lncde_logncde_fwd */
+#define LNCDE_FLAG_K1_TMA 4u      /* lncde_logsig_fwd: force the TMA bulk-copy kernel (default: chosen by windows per path) */
+#define LNCDE_FLAG_GENERIC 8u     /* baseline kernels only - classic K1 staging, sequential D / BD scans, FFMA dense flow
+                                     build with materialised dF, unstreamed generic Log-NCDE mat-vecs: the kernels every
+                                     specialised one is checked against (tests, scripts/variant_check.py) */
+#define LNCDE_FLAG_K2_MMA_SYNC 16u /* dense LNCDE: flow build on the warp-level tensor pipe (mma.sync, 3xTF32) instead of
+                                      tcgen05 - the path of block sizes that are not multiples of 128 */
+#define LNCDE_FLAG_K3_V3 32u      /* Log-NCDE, H = 128 / width 32 model: six-barrier stage kernels (logncde_v3.cuh); measured
+                                     slower than the default on B200, kept for its clock-trace instrumentation */
 
 const char* lncde_version(void);
 /* Human-readable text for a status returned by any entry point. */
 const char* lncde_strerror(int status);
-
-/* Kernel-variant switches.  Every variant computes the same result (bit for bit where noted, otherwise to fp32
- * rounding); 0 = the default, i.e. the kernels measured on B200 so far.  Process-wide, thread-safe; each call reads
- * the value once at entry; initial values come from the environment (LNCDE_TUNE_<KEY IN CAPITALS>).
- *   "k1_tma"      lncde_logsig_fwd, C <= 8, depth <= 2: 1 = tiles moved by TMA bulk copies (same as LNCDE_FLAG_K1_TMA),
- *                 2 = the same kernel persistent with a two-buffer ring, grid sized to the machine.  Bit-identical.
- *   "k1_grid_cap" upper bound on the grid of the persistent K1 kernel (0 = machine-sized); experiments and tests.
- *   "k3_fused"    lncde_logncde_fwd/bwd, specialised H = 128 / width 32 kernels: 1 = the 32 x 32 layer phases fused on
- *                 single warps (bit-identical), 2 = additionally adjoint phase Q4 folded into Q5.
- *   "k3_stream"   lncde_logncde_fwd/bwd, generic kernels (any other shape): layers that do not fit in shared memory are
- *                 read with prefetching all-lane mat-vecs; forward states bit-identical.
- *   "k2_fused_d"  read by the host mirror: diagonal LNCDE through lncde_dlncde_* instead of flow build + scan.
- *   "k2_de_v2"    lncde_linear_scan_fwd/bwd, block size >= 64: 1 = 128 x 128 flow-build tiles with 8 x 8 register tiles,
- *                 the reverse sweep stores lam_t instead of dF_t and the bracket gradient is the triple product
- *                 sum lam_t (x) y_{t-1} (x) logsig_t (the backward call then leaves the flows in the workspace intact);
- *                 2 = flow build and bracket gradient on the warp-level tensor pipe (3xTF32 split precision);
- *                 3 = flow build (and the bracket gradient of the dF-materialising reverse path) on tcgen05 through
- *                 CUTLASS' sm_100 FastFP32 collective (9xBF16 split) - LNCDE_ERR_UNSUPPORTED if built without CUTLASS.
- *   "k2_pscan"    lncde_linear_scan_fwd/bwd, block size <= 8, T > 65: the scans run parallel in time (chunk products,
- *                 boundary recurrence over the chunks, per-chunk sweeps). */
-int lncde_set_tuning(const char* key, int value);
-int lncde_get_tuning(const char* key); /* value, or <0 for an unknown key */
 
 /* ------------------------------------------------------------------ K0 ---
  * Hall basis and tensor->Lie projection tables (host, cached).
@@ -97,6 +83,8 @@ int lncde_hall_t2l_csr(int width, int depth, int32_t* rowptr, int32_t* cols, flo
  *            datasets.py:43-71 batch_calc_paths).  Ignored without the flag.
  *   t2l_*  : device CSR from lncde_hall_t2l_csr; may be NULL when depth <= 2
  *            and C <= 8 (closed-form Levy-area path).
+ *   flags  : LNCDE_FLAG_COMPAT; LNCDE_FLAG_K1_TMA / LNCDE_FLAG_GENERIC force one of the two closed-form kernels
+ *            (bit-identical results; by default paths of >= 128 windows take the TMA kernel).
  * depth in [1, 4].                                                          */
 int lncde_logsig_num_windows(int L, int stepsize);
 int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int L, int C,
@@ -127,7 +115,7 @@ size_t lncde_logncde_fwd_smem_bytes(int H, int C, int width, int n_hidden);
 int lncde_logncde_fwd(void* stream, const float* params, const float* logsig, const float* y0,
                       const int32_t* stage_row, const float* stage_scale, float* ys, int B, int K,
                       int D, int H, int C, int width, int n_hidden, int depth, int n_steps,
-                      void* workspace, size_t workspace_bytes);
+                      void* workspace, size_t workspace_bytes, unsigned flags);
 
 /* Backward sweep (discretise-then-optimise, what diffrax's default adjoint
  * returns).  g_ys [B, n_steps+1, H] is dLoss/d ys (zero where unused).
@@ -170,18 +158,21 @@ int lncde_nrde_bwd(void* stream, const float* params, const float* logsig, const
  *        for bs == 1 this is vf_A^T laid out [H, n_coeff]
  *   logsig [B, T, D]; uses columns 1 .. n_basis
  *   y0 [B, H];  ys [B, T, H] (ys[:,0] = y0)                                  */
-/* Scratch shared by forward and backward: the flows F [B,T,nb,bs,bs] plus split-K partials (plus lam [B,T,H] for
- * block sizes >= 64, used by the "k2_de_v2" kernels).
- * The backward call must receive the SAME workspace the forward call of the same
- * (lie, logsig) filled, untouched in between (it reads F_t and overwrites it with dF_t).   */
+/* Scratch shared by forward and backward: the flows F [B,T,nb,bs,bs] plus split-K partials (plus lam [B,T,H] and the
+ * packed tensor-core operands for block sizes >= 64, chunk products for the time-parallel scans of block sizes <= 8).
+ * The backward call must receive the SAME workspace the forward call of the same (lie, logsig) filled, untouched in
+ * between, and the same `flags` (it reads F_t; the generic kernels overwrite it with dF_t).
+ * Kernels by block size: bs <= 8 and T > 65: scans parallel in time (chunk products, boundary recurrence over the chunks,
+ * per-chunk sweeps); bs | 32: warp-shuffle scans; bs >= 64: flows from tcgen05 (bs % 128 == 0) or mma.sync tensor
+ * cores with 3xTF32 split precision, TMA-ring scans, lam-only reverse sweep + triple-product bracket gradient.          */
 size_t lncde_linear_scan_workspace_bytes(int B, int T, int nb, int bs, int n_basis);
 int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, const float* y0,
                           float* ys, int B, int T, int D, int nb, int bs, int n_basis,
-                          void* workspace, size_t workspace_bytes);
+                          void* workspace, size_t workspace_bytes, unsigned flags);
 /* g_ys [B,T,H] -> g_lie [nb,bs,bs,n_basis] (summed over batch), g_y0 [B,H].               */
 int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, const float* ys,
                           const float* g_ys, float* g_lie, float* g_y0, int B, int T, int D, int nb,
-                          int bs, int n_basis, void* workspace, size_t workspace_bytes);
+                          int bs, int n_basis, void* workspace, size_t workspace_bytes, unsigned flags);
 
 /* ----------------------------------------------------------------- K2d ---
  * Fused diagonal LNCDE (block size 1): f_t = 1 + sum_c logsig[t, 1 + c] vf_A[c, :], y_t = f_t * y_{t-1},

@@ -1,18 +1,17 @@
-// K2 "dense v2" (tuning "k2_de_v2"): the two kernels that dominate the DE-LNCDE step besides the scans.
+// K2 dense (DE-LNCDE, block size >= 64): the kernels that dominate the step besides the scans.
 //
 // ncu launch list of round 1 (EigenWorms DE, 32 x 1499 x 128 x 128, n_basis 28): flow build 3.8 ms for 44 GFLOP
 // and 3.1 GB of output (16 % of the FP32 peak - its 4 x 4 register tile issues one shared-memory load per two
 // FMAs), bracket-gradient GEMM 1.7 ms reading 3.1 GB of dF that the reverse scan had to write first.
 //
-//  * flow_build8_kernel: same contraction F[m][n] = eye + sum_l ls[m][1+l] lie[n][l] with a 128 x 128 CTA tile and
-//    an 8 x 8 register tile per thread: per k-step 4 conflict-free 128-bit shared loads feed 64 FMAs, every
-//    thread stores rows of 2 x 128 bits (256-byte segments per half-warp).  K = n_basis is 21..36 at depth 2:
-//    one or two k-tiles, so the kernel is FP32-issue bound with the 3.1 GB of output streaming out underneath.
+//  * (an FFMA flow build with 8 x 8 register tiles was measured in round 2 - 7.5 ms per EigenWorms DE step against
+//    7.3 ms with the mma.sync build below and 5.7 ms with the tcgen05 build of flow_tcgen05.cu - and removed.)
 //  * dlie_triple_kernel: dLie[(i,j)][l] = sum_{b,t>=1} lam_t[i] * y_{t-1}[j] * ls[t][1+l] straight from the small
 //    operands (lam, y: 24 MB each, ls: 5 MB) - the reverse scan then only has to store lam_t (512 B per step)
 //    instead of the outer product dF_t (64 KB per step), and nothing reads 3.1 GB back.  Same FLOPs as the GEMM it
 //    replaces (the rank-1 factor costs 2 extra multiplies per 56 FMAs), split-K with a deterministic reduce.
-//  * flow_build_tc_kernel ("k2_de_v2" = 2): the flow build on the tensor pipe, 3xTF32 split precision (see below).
+//  * flow_build_tc_kernel: the flow build on the warp-level tensor pipe (mma.sync, 3xTF32 split precision, see below) -
+//    used for dense block sizes the tcgen05 kernel does not take (not a multiple of 128) or with LNCDE_FLAG_K2_MMA_SYNC.
 //  * scan_bwd_tma_lam_kernel: the reverse sweep of scan_bwd_tma_kernel (linear_scan.cu) with the in-place dF_t store
 //    replaced by a 512-byte store of lam_t - same ring of TMA bulk copies, same order of the sums, so lam, g_y0 are
 //    bit-identical to the default kernel; the flows in the workspace stay intact.
@@ -24,74 +23,6 @@
 #include "ptx.cuh"
 
 namespace lncde {
-
-// ---------------------------------------------------------------- flow build, 8 x 8 register tile
-// thread (tx, ty) of 16 x 16 owns rows ty*4 + {0..3} and 64 + ty*4 + {0..3}, columns tx*4 + {0..3} and
-// 64 + tx*4 + {0..3} of the 128 x 128 tile: every 128-bit operand load of a half-warp covers 256 contiguous bytes.
-__global__ void __launch_bounds__(256) flow_build8_kernel(const float* __restrict__ lie,
-                                                          const float* __restrict__ logsig, float* __restrict__ F,
-                                                          long long Mtot, int N, int D, int n_basis, int bs) {
-  constexpr int KT = 32, TS = 128;
-  __shared__ __align__(16) float As[KT][TS];  // logsig tile, k-major
-  __shared__ __align__(16) float Bs[KT][TS];  // lie tile, k-major
-  const long long m0 = (long long)blockIdx.x * TS;  // row tiles on grid.x: B*T / 128 can exceed the 65 535 limit of grid.y
-  const int n0 = blockIdx.y * TS;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < n_basis; k0 += KT) {
-    // consecutive threads walk the rows (columns) of the tile: conflict-free shared stores
-    for (int e = threadIdx.x; e < KT * TS; e += 256) {
-      const int kk = e >> 7, m = e & (TS - 1);
-      As[kk][m] = (m0 + m < Mtot && k0 + kk < n_basis) ? __ldg(logsig + (m0 + m) * D + 1 + k0 + kk) : 0.f;
-      Bs[kk][m] = (n0 + m < N && k0 + kk < n_basis) ? __ldg(lie + (size_t)(n0 + m) * n_basis + k0 + kk) : 0.f;
-    }
-    __syncthreads();
-    const int kmax = min(KT, n_basis - k0);
-#pragma unroll 4
-    for (int kk = 0; kk < kmax; ++kk) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-  const int bs2 = bs * bs;
-  const bool vec = (N & 3) == 0;  // rows of F are 16-byte aligned (workspace is, N % 4 == 0)
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const long long m = m0 + (i >> 2) * 64 + ty * 4 + (i & 3);
-    if (m >= Mtot) continue;
-#pragma unroll
-    for (int jh = 0; jh < 2; ++jh) {
-      const int n = n0 + jh * 64 + tx * 4;
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = (n + j) % bs2;
-        v[j] = acc[i][jh * 4 + j] + ((r / bs == r % bs) ? 1.f : 0.f);
-      }
-      float* dst = F + m * N + n;
-      if (vec && n + 3 < N) {
-        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (n + j < N) dst[j] = v[j];
-      }
-    }
-  }
-}
 
 // ---------------------------------------------------------------- flow build on the tensor pipe (3xTF32)
 // Same contraction on the warp-level TF32 MMA (mma.sync m16n8k8) with the split-precision scheme

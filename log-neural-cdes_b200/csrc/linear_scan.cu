@@ -22,7 +22,6 @@
 #include "linear_pscan.cuh"
 #include "outer_gemm.cuh"
 #include "ptx.cuh"
-#include "tuning.h"
 
 namespace lncde {
 
@@ -338,8 +337,8 @@ static void launch_pscan(bool bwd, cudaStream_t cs, float* F, const float* y0, f
   }
 }
 static bool pscan_dispatch(bool bwd, cudaStream_t cs, float* F, const float* y0, float* ys, const float* g_ys, float* g_y0,
-                           int B, int T, int H, int bs, float* scratch) {
-  if (!tuning_value(kTuneK2Pscan) || !pscan_shape(T, bs)) return false;
+                           int B, int T, int H, int bs, float* scratch, unsigned flags) {
+  if ((flags & LNCDE_FLAG_GENERIC) || !pscan_shape(T, bs)) return false;
   if (((long long)B * pscan_chunks(T) * H + 255) / 256 > 0x7fffffffLL) return false;
   switch (bs) {
     case 1: launch_pscan<1, 8>(bwd, cs, F, y0, ys, g_ys, g_y0, B, T, H, scratch); return true;
@@ -602,6 +601,15 @@ static size_t pscan_scratch_offset(int B, int T, int nb, int bs, int n_basis) {
                          : 0;
   return flows + part + ((lam + 3) & ~(size_t)3) + tc5;
 }
+// Kernel level of the dense model for this call: 0 = generic FFMA kernels (flows and dF materialised), 2 = warp-level
+// tensor pipe (mma.sync, 3xTF32) flow build + lam-only reverse sweep + triple-product bracket gradient, 3 = the same
+// with the flow build on tcgen05 (flow_tcgen05.cu).  Measured on B200, EigenWorms DE step: 11.0 / 7.3 / 5.7 ms.
+static int dense_level(unsigned flags, int N, int bs) {
+  if ((flags & LNCDE_FLAG_GENERIC) || bs < 64) return 0;
+  if (!(flags & LNCDE_FLAG_K2_MMA_SYNC) && flow_tcgen05_shape(N, bs)) return 3;
+  return 2;
+}
+
 }  // namespace lncde
 
 extern "C" {
@@ -625,7 +633,7 @@ static int check_scan_args(int B, int T, int D, int nb, int bs, int n_basis) {
 
 int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, const float* y0, float* ys,
                           int B, int T, int D, int nb, int bs, int n_basis, void* workspace,
-                          size_t workspace_bytes) {
+                          size_t workspace_bytes, unsigned flags) {
   using namespace lncde;
   if (!lie || !logsig || !y0 || !ys || !workspace) return LNCDE_ERR_NULL;
   int st = check_scan_args(B, T, D, nb, bs, n_basis);
@@ -637,8 +645,8 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   const int H = nb * bs, N = H * bs;
   const long long Mtot = (long long)B * T;
   // 1. flows
-  const int de_v2 = tuning_value(kTuneK2DeV2);
-  if (de_v2 >= 3 && flow_tcgen05_shape(N, bs)) {  // tcgen05 (3xTF32 split): packed operands behind flows | part | lam
+  const int de_v2 = dense_level(flags, N, bs);
+  if (de_v2 >= 3) {  // tcgen05 (3xTF32 split): packed operands behind flows | part | lam
     const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
     const size_t part_n = ((size_t)N * n_basis * kScanKsplit + 3) & ~(size_t)3;
     const size_t lam_n = de_v2_shape(bs, n_basis) ? (size_t)B * T * nb * bs : 0;
@@ -646,13 +654,10 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
     st = flow_build_tcgen05(cs, lie, logsig, F, Mtot, N, D, n_basis, bs, scratch,
                          flow_tcgen05_scratch_floats(Mtot, N, n_basis));
     if (st != 0) return st;
-  } else if (de_v2 >= 2 && bs >= 64) {  // tensor pipe (3xTF32), any n_basis
+  } else if (de_v2 >= 2) {  // warp-level tensor pipe (3xTF32), any n_basis
     dim3 grid((unsigned)((Mtot + 127) / 128), (N + 127) / 128);
     cudaFuncSetAttribute(flow_build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     flow_build_tc_kernel<<<grid, 256, kTcSmemBytes, cs>>>(lie, logsig, F, Mtot, N, D, n_basis, bs);
-  } else if (de_v2 && de_v2_shape(bs, n_basis)) {
-    dim3 grid((unsigned)((Mtot + 127) / 128), (N + 127) / 128);
-    flow_build8_kernel<<<grid, 256, 0, cs>>>(lie, logsig, F, Mtot, N, D, n_basis, bs);
   } else {
     const int tm = 4, tn = round_tile(N) > 4 ? 4 : round_tile(N);
     if ((Mtot + 16 * tm - 1) / (16 * tm) > 65535) return LNCDE_ERR_UNSUPPORTED;  // grid.y limit: B * T <= 4.19 M rows
@@ -663,7 +668,7 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   if (st != 0) return st;
   // 2. scan
   float* pscan_scratch = F + pscan_scratch_offset(B, T, nb, bs, n_basis);
-  if (pscan_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs, pscan_scratch)) {
+  if (pscan_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs, pscan_scratch, flags)) {
   } else if (scan_warp_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
   } else if (scan_tma_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
   } else if (bs <= 16) {
@@ -679,7 +684,7 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
 
 int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, const float* ys,
                           const float* g_ys, float* g_lie, float* g_y0, int B, int T, int D, int nb, int bs,
-                          int n_basis, void* workspace, size_t workspace_bytes) {
+                          int n_basis, void* workspace, size_t workspace_bytes, unsigned flags) {
   using namespace lncde;
   if (!lie || !logsig || !ys || !g_ys || !g_lie || !g_y0 || !workspace) return LNCDE_ERR_NULL;
   int st = check_scan_args(B, T, D, nb, bs, n_basis);
@@ -689,7 +694,7 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
   cudaStream_t cs = (cudaStream_t)stream;
   float* F = (float*)workspace;  // still holds the forward flows of the SAME (lie, logsig)
   const int H = nb * bs, N = H * bs;
-  const int de_v2 = tuning_value(kTuneK2DeV2);
+  const int de_v2 = dense_level(flags, N, bs);
   if (de_v2 && de_v2_shape(bs, n_basis) && T >= 2) {
     // reverse sweep stores lam_t only; dLie = sum lam_t (x) y_{t-1} (x) logsig_t from the small operands
     const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
@@ -708,7 +713,7 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
     }
   }
   if (!pscan_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs,
-                      F + pscan_scratch_offset(B, T, nb, bs, n_basis)) &&
+                      F + pscan_scratch_offset(B, T, nb, bs, n_basis), flags) &&
       !scan_warp_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs) &&
       !scan_tma_dispatch(true, cs, F, nullptr, const_cast<float*>(ys), g_ys, g_y0, B, T, H, bs)) {
     int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));

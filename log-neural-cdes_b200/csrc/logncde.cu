@@ -21,7 +21,6 @@
 #include "lncde_b200.h"
 #include "logncde_common.cuh"
 #include "outer_gemm.cuh"
-#include "tuning.h"
 
 namespace lncde {
 
@@ -241,13 +240,13 @@ struct BwdParams {
 
 }  // namespace lncde
 #include "logncde_fast.cuh"
+#include "logncde_v3.cuh"
 namespace lncde {
 
 static bool use_fast(int H, int C, int width, int n_hidden) {
   static const bool disabled = getenv("LNCDE_DISABLE_FAST") != nullptr;
   return !disabled && fast::shape_supported(H, C, width, n_hidden);
 }
-static int fused_variant() { return tuning_value(kTuneK3Fused); }
 
 struct RevBufs {
   float* g;        // [H] cotangent of G
@@ -518,12 +517,14 @@ static bool any_global_layer(const MlpDesc& d) {
     if (d.gvec[l]) return true;
   return false;
 }
-// tuning "k3_stream": streamed global-weight mat-vecs; only matters when some layer is not resident in shared memory
-static bool stream_variant() { return tuning_value(kTuneK3Stream) != 0; }
+// Streamed global-weight mat-vecs (layers that are not resident in shared memory: PPG / toy shapes).  Round 2 on B200:
+// 84 vs 101 ms (PPG), 5.66 vs 5.94 ms (toy) against the one-L2-round-trip-per-4-rows form, which LNCDE_FLAG_GENERIC keeps
+// reachable for comparison.
+static bool stream_variant(unsigned flags) { return (flags & LNCDE_FLAG_GENERIC) == 0; }
 
 template <int C>
-static int launch_fwd(cudaStream_t st, const FwdParams& p, size_t smem) {
-  const bool pf = stream_variant() && any_global_layer(p.d);
+static int launch_fwd(cudaStream_t st, const FwdParams& p, size_t smem, unsigned flags) {
+  const bool pf = stream_variant(flags) && any_global_layer(p.d);
   auto k = pf ? logncde_fwd_kernel<C, true> : logncde_fwd_kernel<C, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
@@ -546,6 +547,18 @@ static int launch_bwd(cudaStream_t st, const BwdParams& p, size_t smem, bool pf)
 
 #ifdef LNCDE_PHASE_TIMING
 // dev tool only (scripts/phase_timing.py); not part of include/lncde_b200.h
+extern "C" int lncde_debug_v3_trace(long long* host, size_t n, int reset) {
+  using namespace lncde::v3;
+  const size_t total = (size_t)2 * kTrPoints * 16;
+  if (n < total) return LNCDE_ERR_WORKSPACE;
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_v3_trace, total * sizeof(long long));
+  if (e == cudaSuccess && reset) {
+    void* dev = nullptr;
+    e = cudaGetSymbolAddress(&dev, g_v3_trace);
+    if (e == cudaSuccess) e = cudaMemset(dev, 0, total * sizeof(long long));
+  }
+  return (int)e;
+}
 extern "C" int lncde_debug_phase_clocks(long long* host, size_t n, int reset) {
   using namespace lncde::fast;
   const size_t total = (size_t)kPtStages * kPtLines * kPtWarps;
@@ -578,7 +591,7 @@ size_t lncde_logncde_fwd_smem_bytes(int H, int C, int width, int n_hidden) {
 int lncde_logncde_fwd(void* stream, const float* params, const float* logsig, const float* y0,
                       const int32_t* stage_row, const float* stage_scale, float* ys, int B, int K, int D,
                       int H, int C, int width, int n_hidden, int depth, int n_steps, void* workspace,
-                      size_t workspace_bytes) {
+                      size_t workspace_bytes, unsigned flags) {
   using namespace lncde;
   if (!params || !logsig || !y0 || !stage_row || !stage_scale || !ys) return LNCDE_ERR_NULL;
   if (B < 1 || K < 1 || n_steps < 1) return LNCDE_ERR_SHAPE;
@@ -601,21 +614,28 @@ int lncde_logncde_fwd(void* stream, const float* params, const float* logsig, co
       p.wsp = (float*)workspace;
       p.save = 1;
     }
+    if (flags & LNCDE_FLAG_K3_V3) {  // six-barrier stage kernels (logncde_v3.cuh; experimental, not faster on B200)
+      switch (C) {
+        case 4: return v3::launch_fwd_v3<4>(cs, p);
+        case 6: return v3::launch_fwd_v3<6>(cs, p);
+        case 7: return v3::launch_fwd_v3<7>(cs, p);
+      }
+    }
     switch (C) {
-      case 4: return fast::launch_fwd_fast<4>(cs, p, fused_variant() != 0);
-      case 6: return fast::launch_fwd_fast<6>(cs, p, fused_variant() != 0);
-      case 7: return fast::launch_fwd_fast<7>(cs, p, fused_variant() != 0);
+      case 4: return fast::launch_fwd_fast<4>(cs, p);
+      case 6: return fast::launch_fwd_fast<6>(cs, p);
+      case 7: return fast::launch_fwd_fast<7>(cs, p);
     }
   }
   switch (C) {
-    case 1: return launch_fwd<1>(cs, p, smem);
-    case 2: return launch_fwd<2>(cs, p, smem);
-    case 3: return launch_fwd<3>(cs, p, smem);
-    case 4: return launch_fwd<4>(cs, p, smem);
-    case 5: return launch_fwd<5>(cs, p, smem);
-    case 6: return launch_fwd<6>(cs, p, smem);
-    case 7: return launch_fwd<7>(cs, p, smem);
-    case 8: return launch_fwd<8>(cs, p, smem);
+    case 1: return launch_fwd<1>(cs, p, smem, flags);
+    case 2: return launch_fwd<2>(cs, p, smem, flags);
+    case 3: return launch_fwd<3>(cs, p, smem, flags);
+    case 4: return launch_fwd<4>(cs, p, smem, flags);
+    case 5: return launch_fwd<5>(cs, p, smem, flags);
+    case 6: return launch_fwd<6>(cs, p, smem, flags);
+    case 7: return launch_fwd<7>(cs, p, smem, flags);
+    case 8: return launch_fwd<8>(cs, p, smem, flags);
   }
   return LNCDE_ERR_UNSUPPORTED;
 }
@@ -645,7 +665,7 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
   // "k3_stream": if some layer stays in global memory, lay the kernel out again with the larger scratch of the
   // streamed transposed products (which may push another layer out of shared memory: decided on that layout)
   bool pf = false;
-  if (stream_variant() && any_global_layer(p.d) && !use_fast(H, C, width, n_hidden)) {
+  if (stream_variant(flags) && any_global_layer(p.d) && !use_fast(H, C, width, n_hidden)) {
     other = bwd_other_floats(H, C, width, n_hidden, true) * 4;
     st = make_mlp_desc(&p.d, H, C, width, n_hidden, depth, other);
     if (st != LNCDE_OK) return st;
@@ -660,11 +680,17 @@ int lncde_logncde_bwd(void* stream, const float* params, const float* logsig, co
   p.B = B; p.K = K; p.D = D; p.n_steps = n_steps;
   p.saved = (flags & LNCDE_FLAG_SAVED_FWD) ? 1 : 0;
   cudaStream_t cs = (cudaStream_t)stream;
-  if (use_fast(H, C, width, n_hidden)) {
+  if (use_fast(H, C, width, n_hidden) && p.saved && (flags & LNCDE_FLAG_K3_V3)) {  // six-barrier sweep (logncde_v3.cuh)
     switch (C) {
-      case 4: st = fast::launch_bwd_fast<4>(cs, p, fused_variant()); break;
-      case 6: st = fast::launch_bwd_fast<6>(cs, p, fused_variant()); break;
-      case 7: st = fast::launch_bwd_fast<7>(cs, p, fused_variant()); break;
+      case 4: st = v3::launch_bwd_v3<4>(cs, p); break;
+      case 6: st = v3::launch_bwd_v3<6>(cs, p); break;
+      case 7: st = v3::launch_bwd_v3<7>(cs, p); break;
+    }
+  } else if (use_fast(H, C, width, n_hidden)) {
+    switch (C) {
+      case 4: st = fast::launch_bwd_fast<4>(cs, p); break;
+      case 6: st = fast::launch_bwd_fast<6>(cs, p); break;
+      case 7: st = fast::launch_bwd_fast<7>(cs, p); break;
     }
   } else
   switch (C) {

@@ -1,5 +1,5 @@
 // Specialised Log-NCDE solve kernels for the EigenWorms model shape
-// (hidden H = 128, vector-field width 32, 2 hidden layers; C <= 8 channels).
+// (hidden H = 128, vector-field width 32, 2 hidden layers; C in {4, 6, 7} channels).
 //
 // Same algorithm and workspace layout as the generic kernels in logncde.cu, organised so
 // that the instruction count and the shared-memory wavefronts per Heun stage are close to
@@ -104,10 +104,6 @@ struct Smem {
   static constexpr int sb2 = vb + CW, sb1 = sb2 + W, zb2 = sb1 + W, zb1 = zb2 + W;
   static constexpr int bacc = zb1 + W;       // [64] bias accumulators of the two hidden layers
   static constexpr int COMMON_BWD = bacc + 2 * W;
-  // FUSED variant only: W2 in per-thread order [8 K-slices][32 rows][4], appended after the common area
-  static constexpr int W2R_FLOATS = W * W;
-  // M45 variant only (backward): plain copy of W1 [32][128] behind it
-  static constexpr int W1C_FLOATS = W * H;
 };
 
 struct Regs {
@@ -222,16 +218,6 @@ __device__ __forceinline__ void hidden_finish(const float* part, float bias, int
   s_out[lane] = sg * (1.f + z * (1.f - sg));
 }
 
-// SiLU and its derivative from the four running sums of hidden_finish (same order of additions).
-__device__ __forceinline__ void hidden_finish_acc(const float (&acc)[4], int lane, float* z_out, float* a_out,
-                                                  float* s_out) {
-  const float z = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-  const float sg = sigm(z);
-  z_out[lane] = z;
-  a_out[lane] = z * sg;
-  s_out[lane] = sg * (1.f + z * (1.f - sg));
-}
-
 // acc[q % NACC] += dot(Wq[(q*32 + lane)*4 .. +3], x[4q .. 4q+3]), q = 0..7 in order: one 32 x 32 mat-vec (or its
 // transpose, depending on the layout of Wq) done by ONE warp, lane = output index, x read as broadcast
 // 128-bit loads.  The partial products and the order they are summed in are those of the K-sliced path.
@@ -258,13 +244,12 @@ __device__ __forceinline__ void stage_w2r(const MlpDesc& d, const float* __restr
 // last-layer outputs of this lane in o_r / u3_r and, after the trailing barrier, the per-row
 // tangent contributions in cm[dbuf].  The caller finishes
 //   G[h] = sum_i lam1[i] o[i][h] + sum_j dbuf[j][h].
-// FUSED (kernel variant, see lncde_set_tuning "k3_fused"): the 32 x 32 layer and the steps around it run on
-// single warps straight out of shared memory (warp_matvec32) instead of being K-sliced over all warps
-// with a reduce phase each: 8 block barriers per stage instead of 12, same sums in the same order.
-template <int C, bool D2, bool FUSED = false>
+// (Round 2 removed two variants that fused the 32 x 32 layer phases onto single warps - 8 / 7 block barriers per
+// stage instead of 12 / 11: they measured 19.9 / 20.2 ms per step against 19.1 ms on B200.  The clock trace of
+// logncde_v3.cuh shows why: a block barrier costs ~20 cycles here, the time is in the instruction streams.)
+template <int C, bool D2>
 __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& R, float lam_v,
-                                              float (&o_r)[2], float (&u3_r)[2], const float* w2r = nullptr,
-                                              int pt_slot = -1) {
+                                              float (&o_r)[2], float (&u3_r)[2], int pt_slot = -1) {
   using S = Smem<C>;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* part = cm + S::part;
@@ -276,28 +261,16 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     part[warp * 32 + lane] = dot8(R.w1, ya, yb);
   }
   LNCDE_SYNC();
-  if (FUSED) {
-    // F1: warp 0 finishes z1 / a1 / s1 and goes straight on to z2 = W2 a1
-    if (warp == 0) {
-      hidden_finish<16>(part, R.b1, lane, sb + S::z1, sb + S::a1, sb + S::s1);
-      __syncwarp();
-      float acc[4] = {R.b2, 0.f, 0.f, 0.f};
-      warp_matvec32<4>(w2r, sb + S::a1, lane, acc);
-      hidden_finish_acc(acc, lane, sb + S::z2, sb + S::a2, sb + S::s2);
-    }
-    LNCDE_SYNC();
-  } else {
-    if (warp == 0) hidden_finish<16>(part, R.b1, lane, sb + S::z1, sb + S::a1, sb + S::s1);
-    LNCDE_SYNC();
-    // P2: z2 = W2 a1
-    if (warp < 8) {
-      const float4 a = *reinterpret_cast<const float4*>(sb + S::a1 + warp * 4);
-      part[warp * 32 + lane] = dot4(R.w2, a);
-    }
-    LNCDE_SYNC();
-    if (warp == 0) hidden_finish<8>(part, R.b2, lane, sb + S::z2, sb + S::a2, sb + S::s2);
-    LNCDE_SYNC();
+  if (warp == 0) hidden_finish<16>(part, R.b1, lane, sb + S::z1, sb + S::a1, sb + S::s1);
+  LNCDE_SYNC();
+  // P2: z2 = W2 a1
+  if (warp < 8) {
+    const float4 a = *reinterpret_cast<const float4*>(sb + S::a1 + warp * 4);
+    part[warp * 32 + lane] = dot4(R.w2, a);
   }
+  LNCDE_SYNC();
+  if (warp == 0) hidden_finish<8>(part, R.b2, lane, sb + S::z2, sb + S::a2, sb + S::s2);
+  LNCDE_SYNC();
   // P3: o = tanh(W3 a2 + b3)
   const int row0 = lane_row0(tid);
   if (tid < C * 64) {
@@ -331,18 +304,8 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     for (int i = 0; i < C; ++i) u = fmaf(cm[S::lam + i * 8 + warp], cm[S::qv + i * W + lane], u);
     sb[S::u1 + warp * W + lane] = u;
     sb[S::p1 + warp * W + lane] = sb[S::s1 + lane] * u;
-    if (FUSED) {
-      // F2: warp j carries tangent j through the 32 x 32 layer on its own: u2_j = W2 p1_j ; p2_j = s2 * u2_j
-      __syncwarp();
-      float acc[2] = {0.f, 0.f};
-      warp_matvec32<2>(w2r, sb + S::p1 + warp * W, lane, acc);
-      const float u2v = acc[0] + acc[1];
-      sb[S::u2 + warp * W + lane] = u2v;
-      sb[S::p2 + warp * W + lane] = sb[S::s2 + lane] * u2v;
-    }
   }
   LNCDE_SYNC();
-  if (!FUSED) {
   // P6: u2_j = W2 p1_j (8 K-slices x 2 vector halves)
   {
     const int q = warp & 7, j0 = (warp >> 3) * 4;
@@ -365,7 +328,6 @@ __device__ __forceinline__ void stage_forward(float* sb, float* cm, const Regs& 
     sb[S::p2 + warp * W + lane] = sb[S::s2 + lane] * u;
   }
   LNCDE_SYNC();
-  }  // !FUSED
   // P7: u3 = W3[block j] p2_j ; d = (1 - o^2) u3
   if (tid < C * 64) {
     const int j = tid >> 6;
@@ -439,17 +401,15 @@ __device__ __forceinline__ void save_stage(const float* sb, const float (&o_r)[2
   }
 }
 
-template <int C, bool D2, bool SAVE, bool FUSED>
+template <int C, bool D2, bool SAVE>
 __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams p) {
   using S = Smem<C>;
   extern __shared__ __align__(16) float smem[];
   float* sb = smem + S::WEND_FWD;
   float* cm = sb + S::STAGE;
-  float* w2r = cm + S::COMMON_FWD;  // FUSED only
   const int tid = threadIdx.x;
   Regs R;
   load_regs<C>(R, p.params, p.d);
-  if (FUSED) stage_w2r(p.d, p.params, w2r);
   const int b = blockIdx.x;
   const float* ls = p.logsig + (size_t)b * p.K * p.D;
   float* ys = p.ys + (size_t)b * (p.n_steps + 1) * H;
@@ -471,7 +431,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
     const float sc_n = p.stage_scale[nx];
     const float lam_n = lambda_fetch<C>(ls + (size_t)p.stage_row[nx] * p.D, D2);
     const int pt_slot = pt_slot_of(sidx);
-    stage_forward<C, D2, FUSED>(sb, cm, R, lam_c, o_r, u3_r, w2r, pt_slot);
+    stage_forward<C, D2>(sb, cm, R, lam_c, o_r, u3_r, pt_slot);
     if (SAVE) save_stage<C, D2>(sb, o_r, u3_r, p.ws, p.wsp, (size_t)b * n_stage + sidx);
     if (tid < H) {
       const float gk = sc * field_value<C, D2>(sb, cm, tid);
@@ -495,15 +455,11 @@ __global__ void __launch_bounds__(NT, 1) logncde_fwd_fast_kernel(const FwdParams
 // Reverse sweep of one stage.  cm[g] holds dLoss/dG times the stage scale.  On exit (after the
 // trailing barrier) cm[part + ks*128 + h], ks < 4, hold the K-slice partials of
 // dLoss/d(stage input); the caller sums them.
-// M45 (kernel variant, tuning "k3_fused" = 2): phase Q4 (o-bar partials over 4 K-slices, all warps) is folded into
-// Q5 - every row thread forms the full K = 32 sums of ITS two rows from a plain copy of W1 in shared memory
-// (32 conflict-free 64-bit loads + 8 broadcast 128-bit loads), so one block barrier and the partial-sum round
-// trip through shared memory disappear.
-template <int C, bool D2, bool RIGHTS, bool FUSED = false, bool M45 = false>
+template <int C, bool D2, bool RIGHTS>
 __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, float* sb, float* cm, const Regs& R,
                                               const float (&o_r)[2], const float (&u3_r)[2], float (&b3acc)[2],
                                               const WsLayout& ws, float* __restrict__ wsp, size_t slot,
-                                              int pt_slot = -1, const float* w1c = nullptr) {
+                                              int pt_slot = -1) {
   using S = Smem<C>;
   constexpr int CH = C * H, CW = C * W;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -545,23 +501,6 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
   }
   if (D2) {
     LNCDE_SYNC();
-    if (FUSED) {
-      // FQ2: warp j takes tangent j through Q2 (u2-bar), Q3 (p1-bar_j = W2^T u2-bar_j) and Q3r (u1-bar) alone
-      if (warp < C) {
-        const float pb = cm[S::red + (2 * warp) * W + lane] + cm[S::red + (2 * warp + 1) * W + lane];
-        const float ub = sb[S::s2 + lane] * pb;
-        cm[S::ub2 + tid] = ub;
-        cm[S::sp2 + tid] = sb[S::u2 + tid] * pb;
-        wsp[ws.U[1] + slot * CW + tid] = ub;
-        __syncwarp();
-        float acc[2] = {0.f, 0.f};
-        warp_matvec32<2>(sw + S::W2T, cm + S::ub2 + warp * W, lane, acc);
-        const float pb1 = acc[0] + acc[1];
-        cm[S::ub1 + tid] = sb[S::s1 + lane] * pb1;
-        cm[S::sp1 + tid] = sb[S::u1 + tid] * pb1;
-      }
-      LNCDE_SYNC();
-    } else {
     // Q2: u2-bar = s2 * p2-bar ; s2-bar partials
     if (warp < C) {
       const float pb = cm[S::red + (2 * warp) * W + lane] + cm[S::red + (2 * warp + 1) * W + lane];
@@ -602,7 +541,6 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
       cm[S::sp1 + tid] = sb[S::u1 + tid] * pb;
     }
     LNCDE_SYNC();
-    }  // !FUSED
     // v_i = sum_j Lam_ij u1-bar_j ; s1-bar
     if (warp < C) {
       float v = 0.f;
@@ -615,16 +553,10 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
 #pragma unroll
       for (int j = 0; j < C; ++j) s += cm[S::sp1 + j * W + lane];
       cm[S::sb1 + lane] = s;
-      if (FUSED) {  // s2-bar (the unfused path sums it in Q3)
-        float s2s = 0.f;
-#pragma unroll
-        for (int j = 0; j < C; ++j) s2s += cm[S::sp2 + j * W + lane];
-        cm[S::sb2 + lane] = s2s;
-      }
     }
     LNCDE_SYNC();
     // Q4: o-bar_i[h] += sum_c W1[c][h] v_i[c]   (4 K-slices x 4 h-quarters)
-    if (!M45) {
+    {
       const int ks = warp >> 2, h = (warp & 3) * 32 + lane;
       const float4 wa = *reinterpret_cast<const float4*>(sw + S::W1T + ((warp * 2 + 0) * 32 + lane) * 4);
       const float4 wb = *reinterpret_cast<const float4*>(sw + S::W1T + ((warp * 2 + 1) * 32 + lane) * 4);
@@ -641,24 +573,7 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
   // Q5: o-bar complete ; z3-bar = (1 - o^2) o-bar ; a2-bar partials
   if (tid < C * 64) {
     const int j = tid >> 6, h0 = row0 & (H - 1);
-    if (D2 && M45) {
-      const float* wc = w1c + h0;  // W1[c][h0], W1[c][h0 + 1]
-      const float* vj = cm + S::vb + j * W;
-      float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v4 = *reinterpret_cast<const float4*>(vj + 4 * q);
-        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 w2 = *reinterpret_cast<const float2*>(wc + (4 * q + e) * H);
-          a0[e & 1] = fmaf(w2.x, vv[e], a0[e & 1]);
-          a1[e & 1] = fmaf(w2.y, vv[e], a1[e & 1]);
-        }
-      }
-      ob[0] += a0[0] + a0[1];
-      ob[1] += a1[0] + a1[1];
-    } else if (D2) {
+    if (D2) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const float2 pv = *reinterpret_cast<const float2*>(part + (ks * 8 + j) * H + h0);
@@ -676,34 +591,6 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     cm[S::red + warp * W + lane_col(lane)] = pr;
   }
   LNCDE_SYNC();
-  if (FUSED) {
-    // FQ6: warp 0 does Q6 (z2-bar), Q7 (a1-bar = W2^T z2-bar) and Q7r (z1-bar) back to back
-    if (warp == 0) {
-      float acc[2] = {0.f, 0.f};
-#pragma unroll
-      for (int wq = 0; wq < 2 * C; ++wq) acc[wq & 1] += cm[S::red + wq * W + lane];
-      float zb = sb[S::s2 + lane] * (acc[0] + acc[1]);
-      if (D2) {
-        const float z = sb[S::z2 + lane], sg = sigm(z);
-        zb = fmaf(sg * (1.f - sg) * (2.f + z * (1.f - 2.f * sg)), cm[S::sb2 + lane], zb);
-      }
-      cm[S::zb2 + lane] = zb;
-      cm[S::bacc + W + lane] += zb;
-      wsp[ws.Z[1] + slot * W + lane] = zb;
-      __syncwarp();
-      float ac2[2] = {0.f, 0.f};
-      warp_matvec32<2>(sw + S::W2T, cm + S::zb2, lane, ac2);
-      float zb1v = sb[S::s1 + lane] * (ac2[0] + ac2[1]);
-      if (D2) {
-        const float z = sb[S::z1 + lane], sg = sigm(z);
-        zb1v = fmaf(sg * (1.f - sg) * (2.f + z * (1.f - 2.f * sg)), cm[S::sb1 + lane], zb1v);
-      }
-      cm[S::zb1 + lane] = zb1v;
-      cm[S::bacc + lane] += zb1v;
-      wsp[ws.Z[0] + slot * W + lane] = zb1v;
-    }
-    LNCDE_SYNC();
-  } else {
   // Q6: a2-bar ; z2-bar
   if (warp == 0) {
     float acc[2] = {0.f, 0.f};
@@ -741,7 +628,6 @@ __device__ __forceinline__ void stage_reverse(const float* __restrict__ sw, floa
     wsp[ws.Z[0] + slot * W + lane] = zb;
   }
   LNCDE_SYNC();
-  }  // !FUSED
   // Q8: y-bar = W1^T z1-bar, K-slice partials (summed by the caller)
   {
     const int ks = warp >> 2, h = (warp & 3) * 32 + lane;
@@ -762,7 +648,7 @@ __device__ __forceinline__ float yout_value(const float* cm, int h) {
   return (part[h] + part[H + h]) + (part[2 * H + h] + part[3 * H + h]);
 }
 
-template <int C, bool D2, bool FUSED, bool M45 = false>
+template <int C, bool D2>
 __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams p) {
   using S = Smem<C>;
   extern __shared__ __align__(16) float smem[];
@@ -770,15 +656,10 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
   float* sbA = smem + S::WEND_BWD;
   float* sbB = sbA + S::STAGE;
   float* cm = sbB + S::STAGE;
-  float* w2r = cm + S::COMMON_BWD;  // FUSED only
-  float* w1c = w2r + S::W2R_FLOATS; // M45 only
   const int tid = threadIdx.x;
   Regs R;
   load_regs<C>(R, p.params, p.d);
   stage_weights_bwd<C>(p.d, p.params, sw);
-  if (FUSED) stage_w2r(p.d, p.params, w2r);
-  if (M45)
-    for (int t = tid; t < W * H; t += NT) w1c[t] = p.params[p.d.w_off[0] + t];
   const int b = blockIdx.x;
   const float* ls = p.logsig + (size_t)b * p.K * p.D;
   const float* ys = p.ys + (size_t)b * (p.n_steps + 1) * H;
@@ -805,13 +686,13 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
     const float g_nn = tid < H ? gys[(size_t)nn * H + tid] : 0.f;
     if (tid < H) sbA[S::yin + tid] = y_n;
     __syncthreads();
-    stage_forward<C, D2, FUSED>(sbA, cm, R, lam_a, oA, uA, w2r);
+    stage_forward<C, D2>(sbA, cm, R, lam_a, oA, uA);
     if (tid < H) sbB[S::yin + tid] = sbA[S::yin + tid] + s1 * field_value<C, D2>(sbA, cm, tid);
     __syncthreads();
-    stage_forward<C, D2, FUSED>(sbB, cm, R, lam_b, oB, uB, w2r);  // leaves Lambda of row r2
+    stage_forward<C, D2>(sbB, cm, R, lam_b, oB, uB);  // leaves Lambda of row r2
     if (tid < H) cm[S::g + tid] = 0.5f * s2 * cm[S::ybar + tid];
     __syncthreads();
-    stage_reverse<C, D2, true, FUSED, M45>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1, -1, w1c);
+    stage_reverse<C, D2, true>(sw, sbB, cm, R, oB, uB, b3acc, p.ws, p.wsp, slot + 1);
     if (tid < H) {
       const float a = yout_value<C>(cm, tid);
       cm[S::ab + tid] = a;
@@ -821,7 +702,7 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_fast_kernel(const BwdParams
     const float lam_an = lambda_fetch<C>(ls + (size_t)r1n * p.D, D2);
     const float lam_bn = lambda_fetch<C>(ls + (size_t)r2n * p.D, D2);
     __syncthreads();
-    stage_reverse<C, D2, true, FUSED, M45>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot, -1, w1c);
+    stage_reverse<C, D2, true>(sw, sbA, cm, R, oA, uA, b3acc, p.ws, p.wsp, slot);
     if (tid < H) cm[S::ybar + tid] += cm[S::ab + tid] + yout_value<C>(cm, tid) + g_n;
     __syncthreads();
     s1 = s1n; s2 = s2n;
@@ -861,7 +742,7 @@ __device__ __forceinline__ void fetch_saved(float* sb, const WsLayout& ws, const
   cp_async_commit();
 }
 
-template <int C, bool D2, bool FUSED, bool M45 = false>
+template <int C, bool D2>
 __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParams p) {
   using S = Smem<C>;
   constexpr int CH = C * H;
@@ -869,13 +750,10 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
   float* sw = smem;
   float* sbuf[2] = {smem + S::WEND_BWD, smem + S::WEND_BWD + S::STAGE};
   float* cm = sbuf[1] + S::STAGE;
-  float* w1c = cm + S::COMMON_BWD + S::W2R_FLOATS;  // M45 only (same offset as in the recomputing kernel)
   const int tid = threadIdx.x;
   Regs R;
   load_regs<C>(R, p.params, p.d);
   stage_weights_bwd<C>(p.d, p.params, sw);
-  if (M45)
-    for (int t = tid; t < W * H; t += NT) w1c[t] = p.params[p.d.w_off[0] + t];
   const int b = blockIdx.x;
   const float* ls = p.logsig + (size_t)b * p.K * p.D;
   const float* gys = p.g_ys + (size_t)b * (p.n_steps + 1) * H;
@@ -898,13 +776,6 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
   }
   float g_c = tid < H ? gys[(size_t)(p.n_steps - 1) * H + tid] : 0.f;  // cotangent of y_n, n = sidx / 2
   fetch_saved<C, D2>(sbuf[sidx & 1], p.ws, wsp, slot0 + sidx);
-  if (M45) {
-    // M45 also drops one barrier per stage: the cotangent of the NEXT stage's field value and its Lambda are
-    // written at the end of a stage by the threads that just produced their inputs (cm[g] is last read in Q1,
-    // Lambda in Q3m), so the stage starts straight after the closing barrier.  The last stage is a second one.
-    if (tid < H) cm[S::g + tid] = 0.5f * sc_c * cm[S::ybar + tid];
-    lambda_store<C>(cm, lam_c);
-  }
   cp_async_wait_all();
   __syncthreads();
   for (; sidx >= 0; --sidx) {
@@ -922,23 +793,17 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
     // cotangent of this stage's field value
     const bool second = sidx & 1;  // stage 2 of its Heun step
     const int pt_slot = pt_slot_of(n_stage - 1 - sidx);  // slots count stages in sweep order
-    if (!M45) {
-      if (tid < H)
-        cm[S::g + tid] = second ? 0.5f * sc_c * cm[S::ybar + tid] : sc_c * (0.5f * cm[S::ybar + tid] + cm[S::ab + tid]);
-      lambda_store<C>(cm, lam_c);
-      LNCDE_SYNC();
-    }
+    if (tid < H)
+      cm[S::g + tid] = second ? 0.5f * sc_c * cm[S::ybar + tid] : sc_c * (0.5f * cm[S::ybar + tid] + cm[S::ab + tid]);
+    lambda_store<C>(cm, lam_c);
+    LNCDE_SYNC();
     const float oc[2] = {o_c.x, o_c.y}, uc[2] = {u_c.x, u_c.y};
-    stage_reverse<C, D2, false, FUSED, M45>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx, pt_slot,
-                                            w1c);
+    stage_reverse<C, D2, false>(sw, sbuf[sidx & 1], cm, R, oc, uc, b3acc, p.ws, p.wsp, slot0 + sidx, pt_slot);
     if (tid < H) {
       const float yo = yout_value<C>(cm, tid);
       if (second) cm[S::ab + tid] = yo;
       else cm[S::ybar + tid] += cm[S::ab + tid] + yo + g_c;
-      if (M45 && sidx > 0)  // next stage: second iff this one is a first stage
-        cm[S::g + tid] = !second ? 0.5f * sc_n * cm[S::ybar + tid] : sc_n * (0.5f * cm[S::ybar + tid] + cm[S::ab + tid]);
     }
-    if (M45 && sidx > 0) lambda_store<C>(cm, lam_n);
     cp_async_wait_all();
     LNCDE_SYNC();
     lam_c = lam_n; sc_c = sc_n; o_c = o_n; u_c = u_n;
@@ -955,56 +820,45 @@ __global__ void __launch_bounds__(NT, 1) logncde_bwd_saved_kernel(const BwdParam
 }
 
 template <int C>
-constexpr size_t fwd_smem_bytes(bool fused) {
-  return (size_t)(Smem<C>::WEND_FWD + Smem<C>::STAGE + Smem<C>::COMMON_FWD + (fused ? Smem<C>::W2R_FLOATS : 0)) * 4;
+constexpr size_t fwd_smem_bytes() {
+  return (size_t)(Smem<C>::WEND_FWD + Smem<C>::STAGE + Smem<C>::COMMON_FWD) * 4;
 }
 template <int C>
-constexpr size_t bwd_smem_bytes(bool fused, bool m45) {
-  return (size_t)(Smem<C>::WEND_BWD + 2 * Smem<C>::STAGE + Smem<C>::COMMON_BWD +
-                  (fused || m45 ? Smem<C>::W2R_FLOATS : 0) + (m45 ? Smem<C>::W1C_FLOATS : 0)) * 4;
+constexpr size_t bwd_smem_bytes() {
+  return (size_t)(Smem<C>::WEND_BWD + 2 * Smem<C>::STAGE + Smem<C>::COMMON_BWD) * 4;
 }
 
-template <int C, bool FUSED>
-static int launch_fwd_fast_v(cudaStream_t st, const FwdParams& p) {
-  const size_t smem = fwd_smem_bytes<C>(FUSED);
+template <int C>
+static int launch_fwd_fast(cudaStream_t st, const FwdParams& p) {
+  const size_t smem = fwd_smem_bytes<C>();
   auto go = [&](auto k) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<p.B, NT, smem, st>>>(p);
   };
   if (p.d.depth == 2) {
-    if (p.save) go(logncde_fwd_fast_kernel<C, true, true, FUSED>);
-    else go(logncde_fwd_fast_kernel<C, true, false, FUSED>);
+    if (p.save) go(logncde_fwd_fast_kernel<C, true, true>);
+    else go(logncde_fwd_fast_kernel<C, true, false>);
   } else {
-    if (p.save) go(logncde_fwd_fast_kernel<C, false, true, FUSED>);
-    else go(logncde_fwd_fast_kernel<C, false, false, FUSED>);
+    if (p.save) go(logncde_fwd_fast_kernel<C, false, true>);
+    else go(logncde_fwd_fast_kernel<C, false, false>);
   }
   return (int)cudaGetLastError();
 }
 template <int C>
-static int launch_fwd_fast(cudaStream_t st, const FwdParams& p, bool fused) {
-  return fused ? launch_fwd_fast_v<C, true>(st, p) : launch_fwd_fast_v<C, false>(st, p);
-}
-template <int C, bool FUSED, bool M45>
-static int launch_bwd_fast_v(cudaStream_t st, const BwdParams& p) {
-  const size_t smem = bwd_smem_bytes<C>(FUSED, M45);
+static int launch_bwd_fast(cudaStream_t st, const BwdParams& p) {
+  const size_t smem = bwd_smem_bytes<C>();
   auto go = [&](auto k) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<p.B, NT, smem, st>>>(p);
   };
   if (p.d.depth == 2) {
-    if (p.saved) go(logncde_bwd_saved_kernel<C, true, FUSED, M45>);
-    else go(logncde_bwd_fast_kernel<C, true, FUSED, M45>);
-  } else {  // depth 1 has no Q4: M45 is the same kernel as FUSED
-    if (p.saved) go(logncde_bwd_saved_kernel<C, false, FUSED, false>);
-    else go(logncde_bwd_fast_kernel<C, false, FUSED, false>);
+    if (p.saved) go(logncde_bwd_saved_kernel<C, true>);
+    else go(logncde_bwd_fast_kernel<C, true>);
+  } else {
+    if (p.saved) go(logncde_bwd_saved_kernel<C, false>);
+    else go(logncde_bwd_fast_kernel<C, false>);
   }
   return (int)cudaGetLastError();
-}
-// variant: 0 default, 1 fused 32 x 32 phases, 2 fused + Q4 folded into Q5
-template <int C>
-static int launch_bwd_fast(cudaStream_t st, const BwdParams& p, int variant) {
-  if (variant >= 2) return launch_bwd_fast_v<C, true, true>(st, p);
-  return variant == 1 ? launch_bwd_fast_v<C, true, false>(st, p) : launch_bwd_fast_v<C, false, false>(st, p);
 }
 
 inline bool shape_supported(int Hh, int C, int width, int n_hidden) {

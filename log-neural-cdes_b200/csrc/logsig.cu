@@ -22,7 +22,6 @@
 
 #include "lncde_b200.h"
 #include "ptx.cuh"
-#include "tuning.h"
 
 namespace lncde {
 
@@ -330,10 +329,10 @@ __device__ __forceinline__ void levy_issue(const LevyTile& g, float* buf, unsign
   if (lane < g.n_tail) slab[(g.t_lo - g.a0) + lane] = ld_stream(g.t_lo + lane);
 }
 
-// PERSISTENT = false: one CTA per tile.  PERSISTENT = true (tuning "k1_tma" = 2): the grid is sized to the machine,
-// a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... through a two-buffer ring - the bulk copy of the NEXT
-// tile is in flight while the current one is walked and stored - so barrier set-up and CTA launch are paid once.
-template <int C, bool DEPTH2, bool PERSISTENT>
+// One single-warp CTA per tile.  (A persistent two-buffer form of this kernel - grid sized to the machine, the bulk
+// copy of tile k + 1 in flight while tile k is walked - measured 7 % SLOWER on B200, 0.216 vs 0.201 ms at the roofline
+// shape, and was removed in round 2: with ~20 CTAs resident per SM the hardware scheduler already overlaps the phases.)
+template <int C, bool DEPTH2>
 __global__ void __launch_bounds__(32) logsig_levy_tma_kernel(const LevyParams p, int buf_floats) {
   extern __shared__ __align__(128) float smem[];
   constexpr int D = 1 + C + (DEPTH2 ? (C * (C - 1)) / 2 : 0);
@@ -344,32 +343,21 @@ __global__ void __launch_bounds__(32) logsig_levy_tma_kernel(const LevyParams p,
   const long long n_tiles = (long long)p.B * p.tiles;
   if (lane == 0) {
     mbar_init(bars, 1);
-    if (PERSISTENT) mbar_init(bars + 1, 1);
     fence_mbar_init();
   }
   __syncwarp();
   long long t = blockIdx.x;
   if (t >= n_tiles) return;
-  unsigned phase = 0;  // bit s: parity the next wait on buffer s uses
-  bool store_pending = false;
   levy_issue(levy_tile(p, C, t), bufs, bars, lane);
-  for (int k = 0; t < n_tiles; t += gridDim.x, ++k) {
-    const int sb = PERSISTENT ? (k & 1) : 0;
-    float* buf = bufs + (size_t)sb * buf_floats;
-    if (PERSISTENT && t + gridDim.x < n_tiles) {
-      // the other buffer was the source of the previous tile's bulk store: let that finish reading first
-      if (lane == 0 && store_pending) tma_store_wait_read();
-      __syncwarp();
-      levy_issue(levy_tile(p, C, t + gridDim.x), bufs + (size_t)(sb ^ 1) * buf_floats, bars + (sb ^ 1), lane);
-    }
+  {
+    float* buf = bufs;
     const LevyTile g = levy_tile(p, C, t);
     LevyState<C, DEPTH2> st;
     if (g.nw > 0) {
       float* slab = buf + kLevyPad;
       __syncwarp();
       if (g.bytes) {
-        mbar_wait(bars + sb, (phase >> sb) & 1u);
-        phase ^= 1u << sb;
+        mbar_wait(bars, 0u);
       }
       if (lane < g.lead) slab[g.sh0 - g.lead + lane] = 0.f;
       __syncwarp();
@@ -412,7 +400,6 @@ __global__ void __launch_bounds__(32) logsig_levy_tma_kernel(const LevyParams p,
         tma_store_1d(dst + head, stage + head, (unsigned)body * 4);
         tma_store_commit();
       }
-      store_pending = body > 0;
       if (lane < head) dst[lane] = stage[lane];
       const int tail0 = head + body;
       if (lane < n_o - tail0) dst[tail0 + lane] = stage[tail0 + lane];
@@ -449,7 +436,7 @@ __global__ void __launch_bounds__(32) logsig_levy_tma_kernel(const LevyParams p,
       for (int c = 0; c < D; ++c) dst[c] = row[c];
     }
   }
-  if (lane == 0 && store_pending) tma_store_wait_read();  // shared memory must outlive the bulk read
+  if (lane == 0) tma_store_wait_read();  // shared memory must outlive the bulk read (no-op without a pending store)
 }
 
 // ----------------------------------------------------------------------------
@@ -717,38 +704,24 @@ __global__ void __launch_bounds__(128) logsig_tensor_kernel(const TensorParams p
 }
 
 template <int C>
-static int launch_levy_tma(cudaStream_t st, LevyParams p, int depth, bool persistent) {
+static int launch_levy_tma(cudaStream_t st, LevyParams p, int depth) {
   const int D = 1 + C + (depth == 2 ? (C * (C - 1)) / 2 : 0);
   p.WT = 32;
   p.tiles = (p.q + 31) / 32;
   if (p.tiles < 1) p.tiles = 1;
-  // per buffer: [kLevyPad | 32 windows + basepoint row + <= 3 alignment floats | 4 floats of over-read slack], or the
+  // buffer: [kLevyPad | 32 windows + basepoint row + <= 3 alignment floats | 4 floats of over-read slack], or the
   // 32 x D result rows staged in the same place
   const size_t in_f = kLevyPad + (size_t)32 * p.s * C + C + 3 + 4;
   const size_t out_f = 3 + (size_t)32 * D + 4;
   const size_t buf_f = ((in_f > out_f ? in_f : out_f) + 3) & ~(size_t)3;
-  const size_t smem = (4 + buf_f * (persistent ? 2 : 1)) * 4;  // 16 bytes of mbarriers in front
-  const long long n_tiles = (long long)p.B * p.tiles;
-  long long grid = n_tiles;
-  if (persistent) {
-    long long occ = (long long)(220 * 1024) / (long long)smem;  // CTAs per SM that fit in shared memory
-    if (occ > 16) occ = 16;
-    if (occ < 1) occ = 1;
-    if (grid > 148 * occ) grid = 148 * occ;                      // B200: 148 SMs
-    const int cap = tuning_value(kTuneK1GridCap);
-    if (cap > 0 && grid > cap) grid = cap;
-  }
+  const size_t smem = (4 + buf_f) * 4;  // 16 bytes of mbarrier in front
+  const long long grid = (long long)p.B * p.tiles;
   auto go = [&](auto k) {
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<(int)grid, 32, smem, st>>>(p, (int)buf_f);
   };
-  if (persistent) {
-    if (depth == 2) go(logsig_levy_tma_kernel<C, true, true>);
-    else go(logsig_levy_tma_kernel<C, false, true>);
-  } else {
-    if (depth == 2) go(logsig_levy_tma_kernel<C, true, false>);
-    else go(logsig_levy_tma_kernel<C, false, false>);
-  }
+  if (depth == 2) go(logsig_levy_tma_kernel<C, true>);
+  else go(logsig_levy_tma_kernel<C, false>);
   return (int)cudaGetLastError();
 }
 
@@ -807,21 +780,22 @@ int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int 
     p.chunk = compat ? chunk : 1;
     p.stride = (int)(sC | 1);
     p.sc_magic = (uint32_t)((0x100000000ull + sC - 1) / sC);
-    // LNCDE_FLAG_K1_TMA (or the "k1_tma" tuning value, tuning.h) selects the bulk-copy kernel; it
-    // needs a 16-byte aligned `data` so that the 16-byte floor of a tile's first float never precedes
-    // the buffer.  Default: the classic kernel (the one measured on B200 so far).
-    const int tma_mode = tuning_value(kTuneK1Tma) ? tuning_value(kTuneK1Tma) : ((flags & LNCDE_FLAG_K1_TMA) ? 1 : 0);
-    if (tma_mode && ((uintptr_t)data & 15) == 0) {
-      const bool persistent = tma_mode >= 2 && sC <= 1024;
+    // Bulk-copy (TMA) kernel or classic staging.  Measured on B200 (round 2, scripts/k1_sweep.py): TMA 6 903 vs 4 178 GB/s
+    // for EigenWorms (1 499 windows per path), 6 756 vs 4 230 for PPG, but 2 814 vs 3 541 for SCP1 (56 windows per
+    // path: two tiles, the second one three-quarters full) - so the choice is by windows per path.  The TMA kernel
+    // needs a 16-byte aligned `data` (the 16-byte floor of a tile's first float must not precede the buffer).
+    // LNCDE_FLAG_K1_TMA forces it, LNCDE_FLAG_GENERIC forces the classic kernel; both give bit-identical results.
+    const bool want_tma = (flags & LNCDE_FLAG_GENERIC) ? false : ((flags & LNCDE_FLAG_K1_TMA) != 0 || q >= 128);
+    if (want_tma && ((uintptr_t)data & 15) == 0) {
       switch (C) {
-        case 1: return launch_levy_tma<1>(st, p, depth, persistent);
-        case 2: return launch_levy_tma<2>(st, p, depth, persistent);
-        case 3: return launch_levy_tma<3>(st, p, depth, persistent);
-        case 4: return launch_levy_tma<4>(st, p, depth, persistent);
-        case 5: return launch_levy_tma<5>(st, p, depth, persistent);
-        case 6: return launch_levy_tma<6>(st, p, depth, persistent);
-        case 7: return launch_levy_tma<7>(st, p, depth, persistent);
-        case 8: return launch_levy_tma<8>(st, p, depth, persistent);
+        case 1: return launch_levy_tma<1>(st, p, depth);
+        case 2: return launch_levy_tma<2>(st, p, depth);
+        case 3: return launch_levy_tma<3>(st, p, depth);
+        case 4: return launch_levy_tma<4>(st, p, depth);
+        case 5: return launch_levy_tma<5>(st, p, depth);
+        case 6: return launch_levy_tma<6>(st, p, depth);
+        case 7: return launch_levy_tma<7>(st, p, depth);
+        case 8: return launch_levy_tma<8>(st, p, depth);
       }
     }
     static const int wt_env = getenv("LNCDE_LEVY_WT") ? atoi(getenv("LNCDE_LEVY_WT")) : 0;

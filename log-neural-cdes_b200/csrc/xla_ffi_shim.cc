@@ -60,7 +60,7 @@ static ffi::Error SolveFwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params
   return status_to_error(
       lncde_logncde_fwd(stream, params.typed_data(), logsig.typed_data(), y0.typed_data(), rows.typed_data(),
                         scale.typed_data(), ys->typed_data(), (int)l[0], (int)l[1], (int)l[2], (int)y[1], C, width,
-                        n_hidden, depth, n_steps, nullptr, 0),
+                        n_hidden, depth, n_steps, nullptr, 0, 0u),
       "lncde_logncde_fwd");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_logncde_fwd, SolveFwdImpl,
@@ -170,7 +170,7 @@ static ffi::Error LinearScanFwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> l
   const int n_basis = (int)lie.dimensions()[1];
   return status_to_error(
       lncde_linear_scan_fwd(stream, lie.typed_data(), logsig.typed_data(), y0.typed_data(), ys->typed_data(), (int)l[0],
-                            (int)l[1], (int)l[2], nb, bs, n_basis, scratch->typed_data(), scratch->size_bytes()),
+                            (int)l[1], (int)l[2], nb, bs, n_basis, scratch->typed_data(), scratch->size_bytes(), 0u),
       "lncde_linear_scan_fwd");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_linear_scan_fwd, LinearScanFwdImpl,
@@ -195,12 +195,12 @@ static ffi::Error LinearScanBwdImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> l
   auto l = logsig.dimensions();
   const int B = (int)l[0], T = (int)l[1], D = (int)l[2], n_basis = (int)lie.dimensions()[1];
   int st = lncde_linear_scan_fwd(stream, lie.typed_data(), logsig.typed_data(), y0.typed_data(), ys_scratch->typed_data(),
-                                 B, T, D, nb, bs, n_basis, scratch->typed_data(), scratch->size_bytes());
+                                 B, T, D, nb, bs, n_basis, scratch->typed_data(), scratch->size_bytes(), 0u);
   if (st != 0) return status_to_error(st, "lncde_linear_scan_fwd (rebuild)");
   return status_to_error(
       lncde_linear_scan_bwd(stream, lie.typed_data(), logsig.typed_data(), ys_scratch->typed_data(), g_ys.typed_data(),
                             g_lie->typed_data(), g_y0->typed_data(), B, T, D, nb, bs, n_basis, scratch->typed_data(),
-                            scratch->size_bytes()),
+                            scratch->size_bytes(), 0u),
       "lncde_linear_scan_bwd");
 }
 XLA_FFI_DEFINE_HANDLER_SYMBOL(lncde_xla_linear_scan_bwd, LinearScanBwdImpl,

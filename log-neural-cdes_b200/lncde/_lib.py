@@ -25,8 +25,6 @@ def _declare(lib):
     sig = {
         "lncde_version": (C.c_char_p, []),
         "lncde_strerror": (C.c_char_p, [i]),
-        "lncde_set_tuning": (i, [C.c_char_p, i]),
-        "lncde_get_tuning": (i, [C.c_char_p]),
         "lncde_hall_size": (i, [i, i]),
         "lncde_hall_basis": (i, [i, i, vp]),
         "lncde_tensor_dim": (i64, [i, i]),
@@ -36,12 +34,12 @@ def _declare(lib):
         "lncde_logsig_fwd": (i, [vp, vp, vp, i, i, i, i, i, u, i, vp, vp, vp]),
         "lncde_logncde_param_count": (i, [i, i, i, i]),
         "lncde_logncde_fwd_smem_bytes": (sz, [i, i, i, i]),
-        "lncde_logncde_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz]),
+        "lncde_logncde_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz, u]),
         "lncde_logncde_bwd_workspace_bytes": (sz, [i, i, i, i, i, i, i]),
         "lncde_logncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz, u]),
         "lncde_linear_scan_workspace_bytes": (sz, [i, i, i, i, i]),
-        "lncde_linear_scan_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]),
-        "lncde_linear_scan_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]),
+        "lncde_linear_scan_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz, u]),
+        "lncde_linear_scan_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz, u]),
         "lncde_dlncde_bwd_workspace_bytes": (sz, [i, i, i]),
         "lncde_dlncde_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i]),
         "lncde_dlncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]),
@@ -79,17 +77,35 @@ def lib():
     return _lib
 
 
-def set_tuning(key: str, value: int) -> None:
-    """Select a kernel variant (keys and levels: include/lncde_b200.h, "Kernel-variant switches"); every variant
-    computes the same result."""
-    check(lib().lncde_set_tuning(key.encode(), int(value)), f"lncde_set_tuning({key!r})")
+# ---- per-call kernel flags (include/lncde_b200.h) --------------------------------------------------------------
+FLAG_COMPAT, FLAG_SAVED_FWD, FLAG_K1_TMA, FLAG_GENERIC, FLAG_K2_MMA_SYNC, FLAG_K3_V3 = 1, 2, 4, 8, 16, 32
+_VARIANT_BITS = {"k1_tma": FLAG_K1_TMA, "generic": FLAG_GENERIC, "k2_mma_sync": FLAG_K2_MMA_SYNC, "k3_v3": FLAG_K3_V3}
+_call_flags = threading.local()
 
 
-def get_tuning(key: str) -> int:
-    v = lib().lncde_get_tuning(key.encode())
-    if v < 0:
-        check(v, f"lncde_get_tuning({key!r})")
-    return v
+def call_flags() -> int:
+    """Variant bits the host mirrors OR into the `flags` argument of every C-ABI call made from this thread (0 unless
+    inside a `kernel_flags(...)` block).  The library itself keeps no such state: the word travels with each call."""
+    return getattr(_call_flags, "value", 0)
+
+
+class kernel_flags:
+    """``with kernel_flags("generic"):`` - run the enclosed calls on the named kernel variants (tests, benchmarks):
+    "generic" (baseline kernels), "k1_tma", "k2_mma_sync", "k3_v3"; see the LNCDE_FLAG_* comments in the header."""
+
+    def __init__(self, *names):
+        self.bits = 0
+        for n in names:
+            self.bits |= _VARIANT_BITS[n]
+
+    def __enter__(self):
+        self.prev = call_flags()
+        _call_flags.value = self.prev | self.bits
+        return self
+
+    def __exit__(self, *exc):
+        _call_flags.value = self.prev
+        return False
 
 
 def check(status: int, what: str = ""):

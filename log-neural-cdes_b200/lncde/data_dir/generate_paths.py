@@ -30,8 +30,9 @@ def calc_paths(data: torch.Tensor, stepsize, depth: int, *, compat: bool = True,
     remainder-window quirk of generate_paths.py:59 for a batch processed in
     chunks of ``chunk`` samples (default: the whole call, as in calc_paths).
     depth >= 3 (<= 4) extends the reference (which supports 1 and 2 only).
-    ``kernel="tma"`` selects the bulk-copy variant of the closed-form kernel (LNCDE_FLAG_K1_TMA;
-    C <= 8, depth <= 2), ``None`` / ``"classic"`` the default one.
+    ``kernel``: ``None`` lets the library choose between the two closed-form kernels (C <= 8, depth <= 2) by the
+    number of windows per path; ``"tma"`` / ``"classic"`` force the bulk-copy / classic-staging kernel
+    (LNCDE_FLAG_K1_TMA / LNCDE_FLAG_GENERIC) - bit-identical results.
     """
     _lib.require_cuda(data)
     if data.dtype != torch.float32 or data.dim() != 3:
@@ -50,7 +51,11 @@ def calc_paths(data: torch.Tensor, stepsize, depth: int, *, compat: bool = True,
         raise _lib.LncdeError(f"calc_paths: unknown kernel {kernel!r}")
     if B == 0:  # an empty batch (e.g. the empty shard of preprocess_shard) is an empty result, as under jax.vmap
         return out
-    flags = (1 if compat else 0) | (4 if kernel == "tma" else 0)
+    flags = (_lib.FLAG_COMPAT if compat else 0) | _lib.call_flags()
+    if kernel == "tma":
+        flags = (flags | _lib.FLAG_K1_TMA) & ~_lib.FLAG_GENERIC
+    elif kernel == "classic":
+        flags = (flags | _lib.FLAG_GENERIC) & ~_lib.FLAG_K1_TMA
     rowptr, cols, vals = _device_t2l(Cn, depth, data.device.index or 0)
     with torch.cuda.device(data.device):
         st = L.lncde_logsig_fwd(_lib.stream_ptr(), _lib.ptr(data), _lib.ptr(out), B, Ln, Cn, stepsize, depth,

@@ -73,13 +73,14 @@ class _LogNCDESolve(torch.autograd.Function):
         ws = _workspace(nbytes, ys.device) if train else None  # bumps the generation: earlier saved forwards are void
         st = L.lncde_logncde_fwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(y0c),
                                  _lib.ptr(rows), _lib.ptr(scale), _lib.ptr(ys), B, K, D, H, C, width, n_hidden,
-                                 depth, n_steps, _lib.ptr(ws), nbytes)
+                                 depth, n_steps, _lib.ptr(ws), nbytes, _lib.call_flags())
         _lib.check(st, "lncde_logncde_fwd")
         ctx.save_for_backward(mlp_flat, logsig, rows, scale, ys)
         ctx.dims = dims
         # shared grow-only scratch: its contents are valid until the next training-mode forward on this device
         ctx.ws = ws
         ctx.ws_gen = _WS_GEN.get(ys.device, 0)
+        ctx.flags = _lib.call_flags()
         return ys
 
     @staticmethod
@@ -100,7 +101,8 @@ class _LogNCDESolve(torch.autograd.Function):
         g_y0 = torch.empty((B, H), device=ys.device, dtype=torch.float32)
         st = L.lncde_logncde_bwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(rows),
                                  _lib.ptr(scale), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_params), _lib.ptr(g_y0),
-                                 B, K, D, H, C, width, n_hidden, depth, n_steps, _lib.ptr(ws), nbytes, saved)
+                                 B, K, D, H, C, width, n_hidden, depth, n_steps, _lib.ptr(ws), nbytes,
+                                 saved | (ctx.flags & ~_lib.FLAG_SAVED_FWD))
         _lib.check(st, "lncde_logncde_bwd")
         if saved:  # the sweep wrote its (left, right) gradient pairs over the buffer: a second backward must recompute
             _WS_GEN[ys.device] = _WS_GEN.get(ys.device, 0) + 1

@@ -112,6 +112,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--grid", default=None, help='explicit points "B,T,H,C;B,T,H,C;..." instead of the sweep')
     ap.add_argument("--out", default=None)
+    ap.add_argument("--kernels", default="default", choices=["default", "generic", "k2_mma_sync"],
+                    help="default: the kernels the library picks by shape; generic / k2_mma_sync: lncde._lib.kernel_flags")
     args = ap.parse_args()
 
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
@@ -141,6 +143,8 @@ def main():
     hbm, hbm_kind = peaks()
     use_graph = (not args.no_graph) and world == 1  # N > 1 launches eagerly, like bench.py
     results = []
+    if args.kernels != "default":
+        _lib.kernel_flags(args.kernels).__enter__()  # for the whole run (captured CUDA graphs keep the kernels they recorded)
     for (B, T, H, C), name in itertools.product(grid, ("diagonal_linear_ncde", "dense_linear_ncde")):
         rec = {"model": name, "B_per_gpu": B, "T": T, "H": H, "C": C, "depth": args.depth, "n_gpus": world}
         flow_bytes = 4.0 * B * T * H * H if name == "dense_linear_ncde" else 0.0
@@ -178,7 +182,7 @@ def main():
         ratio = {f"B{k[0]}_T{k[1]}_H{k[2]}_C{k[3]}": v["dense_linear_ncde"] / v["diagonal_linear_ncde"]
                  for k, v in pairs.items() if len(v) == 2}
         summary = {"summary": "DE-LNCDE / D-LNCDE step time ratio per point", "depth": args.depth, "n_gpus": world,
-                   "tuning": {k: _lib.get_tuning(k) for k in ("k2_fused_d", "k2_de_v2")}, "ratio": ratio}
+                   "kernels": args.kernels, "ratio": ratio}
         print(json.dumps(summary), flush=True)
         if args.out:
             with open(args.out, "w") as fh:

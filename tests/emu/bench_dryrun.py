@@ -40,19 +40,7 @@ class FakeGraphedStep:
         return self.step_fn(*self.static_in)
 
 
-def fake_autotune(families):
-    """A canned variant_check report: the K1 bulk-copy kernel passes and is faster, the fused K3 level fails parity."""
-    rep = {"k1": {"parity": {"ok": True, "ok_by_variant": {"1": True, "2": True}},
-                  "timing": {"classic": {"ms": 1.0}, "tma": {"ms": 0.8}, "tma_persistent": {"ms": 0.9}}},
-           "k3": {"parity": {"ok": False, "ok_by_variant": {"1": False, "2": True}},
-                  "timing": {"default": {"ms": 2.0}, "fused": {"ms": 1.0}, "fused2": {"ms": 1.99}}}}
-    rep = {k: v for k, v in rep.items() if k in families}
-    return bench.decide_tuning(rep), rep
-
-
 T.GraphedStep = FakeGraphedStep
-bench.autotune = fake_autotune
-bench.TUNE_CACHE = os.path.join(tempfile.mkdtemp(), "tune_cache.json")
 bench.WORKLOADS["eigenworms_logncde"].update(B=2, L=120, dt0=0.1)
 bench.N_ROT = 2
 bench.K1_ROOFLINE_BATCH = 4

@@ -27,14 +27,14 @@ def lib():
         _lib.lncde_hall_t2l_nnz.argtypes = [i, i]
         _lib.lncde_hall_t2l_csr.argtypes = [i, i, vp, vp, vp]
         _lib.lncde_logsig_num_windows.argtypes = [i, i]
-        _lib.lncde_logncde_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz]
+        _lib.lncde_logncde_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz, u]
         _lib.lncde_logncde_bwd_workspace_bytes.argtypes = [i, i, i, i, i, i, i]
         _lib.lncde_logncde_bwd_workspace_bytes.restype = sz
         _lib.lncde_logncde_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, sz, u]
         _lib.lncde_linear_scan_workspace_bytes.argtypes = [i, i, i, i, i]
         _lib.lncde_linear_scan_workspace_bytes.restype = sz
-        _lib.lncde_linear_scan_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]
-        _lib.lncde_linear_scan_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz]
+        _lib.lncde_linear_scan_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz, u]
+        _lib.lncde_linear_scan_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz, u]
         _lib.lncde_adam_step.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, i,
                                          C.c_float]
         _lib.lncde_dlncde_bwd_workspace_bytes.argtypes = [i, i, i]
@@ -53,16 +53,30 @@ def lib():
     return _lib
 
 
+# Kernel selection of the emulated calls.  The library takes a per-call flags word (include/lncde_b200.h); the tests
+# were written as "baseline kernels vs one variant", so this module keeps a small selection state whose ZERO values
+# mean the BASELINE kernels (LNCDE_FLAG_GENERIC) and translates it into the flags of each call:
+#   "k3_v3"     1: six-barrier Log-NCDE kernels (LNCDE_FLAG_K3_V3)
+#   "k3_stream" 1: streamed global-weight mat-vecs of the generic Log-NCDE kernels (the library default)
+#   "k2_pscan"  1: time-parallel D / BD scans (the library default for block sizes <= 8)
+#   "k2_de_v2"  2: dense model on mma.sync tensor cores (LNCDE_FLAG_K2_MMA_SYNC), 3: tcgen05 flow build (library default)
+FLAG_COMPAT, FLAG_SAVED_FWD, FLAG_K1_TMA, FLAG_GENERIC, FLAG_K2_MMA_SYNC, FLAG_K3_V3 = 1, 2, 4, 8, 16, 32
+_sel = {"k3_v3": 0, "k3_stream": 0, "k2_pscan": 0, "k2_de_v2": 0}
+
+
 def set_tuning(key, value):
-    assert lib().lncde_set_tuning(key.encode(), int(value)) == 0
+    assert key in _sel, key
+    _sel[key] = int(value)
 
 
-def _with_tuning(key, value, fn):
-    set_tuning(key, value)
-    try:
-        return fn()
-    finally:
-        set_tuning(key, 0)
+def _k3_flags():
+    return (FLAG_K3_V3 if _sel["k3_v3"] else 0) | (0 if _sel["k3_stream"] else FLAG_GENERIC)
+
+
+def _k2_flags(bs):
+    if bs >= 64:
+        return {0: FLAG_GENERIC, 2: FLAG_K2_MMA_SYNC, 3: 0}[_sel["k2_de_v2"]]
+    return 0 if _sel["k2_pscan"] else FLAG_GENERIC
 
 
 def set_schedule(mode="ascending", seed=1, blocks_reversed=False):
@@ -121,7 +135,7 @@ def _dev_out(shape, dtype=np.float32):
 
 
 def calc_paths(x, stepsize, depth, compat=True, chunk=None, tma=False, misalign=0, tight_end=True):
-    """tma: False (classic kernel), True / 1 (bulk-copy kernel, one CTA per tile), 2 (persistent bulk-copy kernel)."""
+    """tma: False (classic kernel), True (bulk-copy kernel)."""
     L = lib()
     x = f32(x)
     B, Ln, Cn = x.shape
@@ -138,10 +152,8 @@ def calc_paths(x, stepsize, depth, compat=True, chunk=None, tma=False, misalign=
     xin = guarded(x.shape, tight_end=tight_end, start_mod16=4 * (misalign % 4))
     xin[...] = x
     st = L.lncde_logsig_fwd(None, _p(xin), _p(out), B, Ln, Cn, int(stepsize), depth,
-                            (1 if compat else 0) | (4 if tma else 0), int(chunk or B), _p(rowptr), _p(cols), _p(vals)) \
-        if int(tma) < 2 else _with_tuning("k1_tma", 2, lambda: L.lncde_logsig_fwd(
-            None, _p(xin), _p(out), B, Ln, Cn, int(stepsize), depth, 1 if compat else 0, int(chunk or B), _p(rowptr),
-            _p(cols), _p(vals)))
+                            (FLAG_COMPAT if compat else 0) | (FLAG_K1_TMA if tma else FLAG_GENERIC), int(chunk or B),
+                            _p(rowptr), _p(cols), _p(vals))
     assert st == 0, st
     return out.copy()
 
@@ -161,7 +173,7 @@ def logncde_fwd_bwd(flat, logsig, y0, rows, scale, dims, g_ys, train=True):
         ws = guarded((nbytes,), np.uint8)
         ws[...] = 0xFF
     st = L.lncde_logncde_fwd(None, _p(flat), _p(logsig), _p(y0), _p(rows), _p(scale), _p(ys), B, K, D, H, Cn, width,
-                             n_hidden, depth, n_steps, _p(ws), nbytes)
+                             n_hidden, depth, n_steps, _p(ws), nbytes, _k3_flags())
     assert st == 0, st
     if not train:
         return ys.copy(), None, None
@@ -169,7 +181,8 @@ def logncde_fwd_bwd(flat, logsig, y0, rows, scale, dims, g_ys, train=True):
     g_params = _dev_out(flat.shape)
     g_y0 = _dev_out((B, H))
     st = L.lncde_logncde_bwd(None, _p(flat), _p(logsig), _p(rows), _p(scale), _p(ys), _p(g_ys), _p(g_params),
-                             _p(g_y0), B, K, D, H, Cn, width, n_hidden, depth, n_steps, _p(ws), nbytes, 2)
+                             _p(g_y0), B, K, D, H, Cn, width, n_hidden, depth, n_steps, _p(ws), nbytes,
+                             FLAG_SAVED_FWD | _k3_flags())
     assert st == 0, st
     return ys.copy(), g_params.copy(), g_y0.copy()
 
@@ -188,7 +201,7 @@ def logncde_bwd_recompute(flat, logsig, ys, rows, scale, dims, g_ys):
     g_params = _dev_out(flat.shape)
     g_y0 = _dev_out((B, H))
     st = L.lncde_logncde_bwd(None, _p(flat), _p(logsig), _p(rows), _p(scale), _p(ys), _p(g_ys), _p(g_params),
-                             _p(g_y0), B, K, D, H, Cn, width, n_hidden, depth, n_steps, _p(ws), nbytes, 0)
+                             _p(g_y0), B, K, D, H, Cn, width, n_hidden, depth, n_steps, _p(ws), nbytes, _k3_flags())
     assert st == 0, st
     return g_params.copy(), g_y0.copy()
 
@@ -239,7 +252,8 @@ def linear_scan(lie, logsig, y0, nb, bs, g_ys=None):
     ws = guarded((nbytes,), np.uint8)
     ws[...] = 0xFF
     ys = _dev_out((B, T, H))
-    st = L.lncde_linear_scan_fwd(None, _p(lie), _p(logsig), _p(y0), _p(ys), B, T, D, nb, bs, n_basis, _p(ws), nbytes)
+    st = L.lncde_linear_scan_fwd(None, _p(lie), _p(logsig), _p(y0), _p(ys), B, T, D, nb, bs, n_basis, _p(ws), nbytes,
+                                 _k2_flags(bs))
     assert st == 0, st
     if g_ys is None:
         return ys.copy(), None, None
@@ -247,7 +261,7 @@ def linear_scan(lie, logsig, y0, nb, bs, g_ys=None):
     g_lie = _dev_out(lie.shape)
     g_y0 = _dev_out((B, H))
     st = L.lncde_linear_scan_bwd(None, _p(lie), _p(logsig), _p(ys), _p(g_ys), _p(g_lie), _p(g_y0), B, T, D, nb, bs,
-                                 n_basis, _p(ws), nbytes)
+                                 n_basis, _p(ws), nbytes, _k2_flags(bs))
     assert st == 0, st
     return ys.copy(), g_lie.copy(), g_y0.copy()
 

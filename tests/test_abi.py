@@ -89,10 +89,6 @@ def test_new_entry_points_validate_before_launch(built_lib):
     assert L.lncde_nrde_bwd(None, p, p, p, p, p, p, p, p, 2, 4, 4, 8, 8, 2, 3, None, need) == -1
     assert L.lncde_nrde_bwd(None, p, p, p, p, p, p, p, p, 2, 4, 4, 8, 8, 2, 3, mis, need) == -5
     # K2: shapes, workspace
-    assert L.lncde_linear_scan_fwd(None, p, p, p, p, 1, 4, 4, 2, 4, 9, p, 1 << 20) == -2       # n_basis > D - 1
-    assert L.lncde_linear_scan_fwd(None, p, p, p, p, 1, 4, 4, 2, 4, 3, p, 16) == -4            # workspace too small
+    assert L.lncde_linear_scan_fwd(None, p, p, p, p, 1, 4, 4, 2, 4, 9, p, 1 << 20, 0) == -2    # n_basis > D - 1
+    assert L.lncde_linear_scan_fwd(None, p, p, p, p, 1, 4, 4, 2, 4, 3, p, 16, 0) == -4         # workspace too small
     assert L.lncde_linear_scan_workspace_bytes(2, 5, 1, 128, 28) > L.lncde_linear_scan_workspace_bytes(2, 5, 32, 4, 28)
-    # tuning keys
-    for key in (b"k1_tma", b"k3_fused", b"k2_fused_d", b"k1_grid_cap", b"k2_de_v2", b"k3_stream"):
-        assert L.lncde_get_tuning(key) >= 0
-    assert L.lncde_get_tuning(b"nope") == -3 and L.lncde_set_tuning(None, 1) == -1

@@ -44,9 +44,8 @@ def test_bench_json_contract_over_emulator():
     assert rd["peak_source"].startswith("measured") and rd["peak"] > 0 and abs(rd["frac"] - rd["achieved"] / rd["peak"]) < 1e-12
     bd = out["step_breakdown_ms"]
     assert set(bd) == {"logsig_K1", "forward_solve_K3+readout", "backward_K3b+gemm", "adam_K4", "whole_step"}
-    # autotune plumbing: K1 variant 1 (verified, 20 % faster) on; K3 variant 1 failed parity, variant 2 within the margin
-    assert out["impl_detail"]["tuning"] == {"k1_tma": 1, "k3_fused": 0}
-    assert "TMA" in rf["kernel"] and rf["traffic"] is None  # no ncu capture of the variant: traffic is not claimed
+    assert "kernels" in out["impl_detail"] and "autotune" not in out  # kernels are chosen by shape inside the library
+    assert "TMA" in rf["kernel"]
 
 
 def test_reference_arm_line():

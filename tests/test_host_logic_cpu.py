@@ -88,105 +88,6 @@ def test_lncde_error_without_gpu_paths():
         _lib.require_cuda(torch.zeros(1))
 
 
-def test_bench_autotune_decision():
-    """bench.py switches a kernel variant on only if its own parity check passed AND it was measurably faster."""
-    import importlib.util
-    import os
-
-    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(
-        os.path.abspath(__file__))), "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
-    ok, bad = {"ok": True}, {"ok": False}
-    t = lambda **kw: {k: {"ms": v} for k, v in kw.items()}
-    k3ok = {"ok": True, "ok_by_variant": {"1": True, "2": True}}
-    k1ok = {"ok": True, "ok_by_variant": {"1": True, "2": True}}
-    rep = {"k1": {"parity": k1ok, "timing": t(classic=0.33, tma=0.25, tma_persistent=0.26)},
-           "k3": {"parity": k3ok, "timing": t(default=19.0, fused=18.9, fused2=18.8)}}
-    assert bench.decide_tuning(rep) == {"k1_tma": 1, "k3_fused": 0}       # 1 % is inside the noise margin
-    rep["k1"]["timing"] = t(classic=0.33, tma=0.25, tma_persistent=0.22)
-    assert bench.decide_tuning(rep)["k1_tma"] == 2
-    rep["k1"]["parity"] = {"ok": False, "ok_by_variant": {"1": False, "2": False}}
-    rep["k3"]["timing"] = t(default=19.0, fused=15.0, fused2=14.0)
-    assert bench.decide_tuning(rep) == {"k1_tma": 0, "k3_fused": 2}       # faster but wrong is never used; best variant wins
-    rep["k3"]["parity"] = {"ok": False, "ok_by_variant": {"1": True, "2": False}}
-    assert bench.decide_tuning(rep) == {"k1_tma": 0, "k3_fused": 1}       # level 2 failed its check: fall back to level 1
-    assert bench.decide_tuning({"k1": {"error": "x"}, "k3": {"parity": k3ok}}) == {"k1_tma": 0, "k3_fused": 0}
-    assert bench.decide_tuning({}) == {"k1_tma": 0, "k3_fused": 0}
-    # K2 workloads: one variant per family, same rule
-    de = {"k2de": {"parity": {"ok": True, "ok_by_variant": {"1": True, "2": True}}, "timing": t(default=10.9, v2=8.0, v2_tc=6.5)}}
-    assert bench.decide_tuning(de)["k2_de_v2"] == 2
-    de["k2de"]["parity"] = {"ok": False, "ok_by_variant": {"1": True, "2": False}}
-    assert bench.decide_tuning(de)["k2_de_v2"] == 1
-    de["k2de"]["parity"] = {"ok": False, "ok_by_variant": {"1": False, "2": False}}
-    assert bench.decide_tuning(de)["k2_de_v2"] == 0
-    assert bench.decide_tuning({"k2": {"parity": ok, "timing": t(default_B32=1.0, fused_B32=0.99)}})["k2_fused_d"] == 0
-    # time-parallel scans: judged on the timing of the workload's own model
-    p = {"k2p": {"parity": ok, "timing": t(default_bd=1.5, pscan_bd=1.1, default_d=0.9, pscan_d=0.95)}}
-    bench.WL["model"] = "bd_linear_ncde"
-    assert bench.decide_tuning(p)["k2_pscan"] == 1
-    bench.WL["model"] = "diagonal_linear_ncde"
-    assert bench.decide_tuning(p)["k2_pscan"] == 0
-    p["k2p"]["parity"] = bad
-    bench.WL["model"] = "bd_linear_ncde"
-    assert bench.decide_tuning(p)["k2_pscan"] == 0
-
-
-def test_autotune_runs_the_tcgen05_level_in_its_own_process(monkeypatch):
-    """bench.autotune("k2de"): levels 1, 2 in one subprocess, level 3 (CUTLASS kernel never seen on hardware) in another;
-    the reports are merged, and a level-3 process that dies costs only level 3."""
-    import importlib.util
-    import json
-    import os
-    import types
-
-    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(os.path.dirname(os.path.dirname(
-        os.path.abspath(__file__))), "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
-    calls = []
-    r12 = {"k2de": {"parity": {"cases": 3, "ok": True, "ok_by_variant": {"1": True, "2": True}, "errors": {},
-                               "max_rel_diff_grad": {"1": 1e-7, "2": 2e-6}},
-                    "timing": {"shape": "s", "default": {"ms": 10.9}, "v2": {"ms": 8.0}, "v2_tc": {"ms": 6.5}}}}
-    r3 = {"k2de": {"parity": {"cases": 3, "ok": True, "ok_by_variant": {"3": True}, "errors": {},
-                              "max_rel_diff_grad": {"3": 1e-6}},
-                   "timing": {"shape": "s", "default": {"ms": 11.0}, "v2_umma": {"ms": 5.0}}}}
-    state = {"level3_dies": False}
-
-    def fake_run(cmd, **kw):
-        calls.append(cmd)
-        lv = cmd[cmd.index("--levels") + 1]
-        if lv == "3" and state["level3_dies"]:
-            return types.SimpleNamespace(returncode=-11, stdout="", stderr="Segmentation fault")
-        return types.SimpleNamespace(returncode=0, stdout=json.dumps(r3 if lv == "3" else r12) + "\n", stderr="")
-
-    monkeypatch.setattr(bench.subprocess, "run", fake_run)
-    tuning, rep = bench.autotune(("k2de",))
-    assert [c[c.index("--levels") + 1] for c in calls] == ["1,2", "3"] and all("--no-oracle" in c for c in calls)
-    assert rep["k2de"]["parity"]["ok_by_variant"] == {"1": True, "2": True, "3": True}
-    assert rep["k2de"]["timing"]["default"] == {"ms": 10.9} and rep["k2de"]["timing"]["v2_umma"] == {"ms": 5.0}
-    assert tuning["k2_de_v2"] == 3
-    state["level3_dies"] = True
-    tuning, rep = bench.autotune(("k2de",))
-    assert "level3_error" in rep["k2de"] and "error" not in rep["k2de"]
-    assert tuning["k2_de_v2"] == 2
-
-
-def test_tuning_api_roundtrip(built_lib):
-    from lncde import _lib
-
-    for key in ("k1_tma", "k3_fused", "k2_fused_d", "k2_de_v2", "k3_stream", "k2_pscan"):
-        old = _lib.get_tuning(key)
-        _lib.set_tuning(key, 2)
-        assert _lib.get_tuning(key) == 2
-        _lib.set_tuning(key, old)
-        assert _lib.get_tuning(key) == old
-    import pytest
-
-    with pytest.raises(_lib.LncdeError):
-        _lib.set_tuning("no_such_key", 1)
-
-
 def test_nrde_mirror_layout_and_errors(built_lib):
     """create_model("nrde"): same errors as generate_model.py:151-153, reference pytree names, parameter count of
     the C ABI (lncde_nrde_param_count) = [vf | mlp_linear] of the host layout; no CPU fallback."""
@@ -216,30 +117,27 @@ def test_nrde_mirror_layout_and_errors(built_lib):
             model((torch.zeros(2, 44), torch.zeros(2, 11, 22), torch.zeros(2, 6)))
 
 
-def test_bench_autotune_cache(monkeypatch, tmp_path):
-    """One autotune per (GPU model, library build, families): later runs of a session (N = 2, 4, 8) reuse the decision;
-    a decision taken after a failed variant check is never cached."""
-    import importlib.util
-    import os
+def test_kernel_flags_are_per_call_and_thread_local(built_lib):
+    """The C ABI has no tuning state (round 2): variants are named by the `flags` word of each call.  The binding's
+    `kernel_flags` context only decides which bits the host mirrors pass from THIS thread."""
+    import threading
 
-    import torch
+    from lncde import _lib
 
-    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(os.path.dirname(os.path.dirname(
-        os.path.abspath(__file__))), "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bench)
-    calls = []
-    good = ({"k1_tma": 1, "k3_fused": 0}, {"k1": {"parity": {"ok": True}}, "k3": {"parity": {"ok": True}}})
-    monkeypatch.setattr(bench, "autotune", lambda fam: (calls.append(fam) or good))
-    monkeypatch.setattr(torch.cuda, "get_device_name", lambda i=0: "TEST GPU")
-    monkeypatch.setattr(bench, "TUNE_CACHE", str(tmp_path / "cache.json"))
-    t1, r1 = bench.cached_autotune(("k1", "k3"))
-    t2, r2 = bench.cached_autotune(("k1", "k3"))
-    assert t1 == t2 == good[0] and "cached" not in r1 and r2["cached"] and len(calls) == 1
-    bench.cached_autotune(("k1", "k3g"))                      # other families: own entry
-    bench.cached_autotune(("k1", "k3"), refresh=True)         # --retune
-    assert len(calls) == 3
-    os.remove(bench.TUNE_CACHE)
-    monkeypatch.setattr(bench, "autotune", lambda fam: ({"k1_tma": 0, "k3_fused": 0}, {"k1": {"error": "boom"}, "k3": {}}))
-    bench.cached_autotune(("k1", "k3"))
-    assert not os.path.exists(bench.TUNE_CACHE)
+    assert _lib.call_flags() == 0
+    assert not hasattr(built_lib, "lncde_set_tuning_does_not_exist")
+    for gone in ("lncde_set_tuning", "lncde_get_tuning"):
+        with pytest.raises(AttributeError):
+            getattr(built_lib, gone)
+    seen = {}
+    with _lib.kernel_flags("generic"):
+        assert _lib.call_flags() == _lib.FLAG_GENERIC
+        with _lib.kernel_flags("k3_v3", "k2_mma_sync"):
+            assert _lib.call_flags() == _lib.FLAG_GENERIC | _lib.FLAG_K3_V3 | _lib.FLAG_K2_MMA_SYNC
+        t = threading.Thread(target=lambda: seen.setdefault("other", _lib.call_flags()))
+        t.start()
+        t.join()
+        assert _lib.call_flags() == _lib.FLAG_GENERIC
+    assert _lib.call_flags() == 0 and seen["other"] == 0
+    with pytest.raises(KeyError):
+        _lib.kernel_flags("no_such_variant")

@@ -105,13 +105,12 @@ LN = np.load(os.path.join(GOLDEN, "ref_linear.npz"))
 @pytest.mark.parametrize("i", range(int(LN["n"])))
 def test_linear_ncde_mirror_vs_reference_code(emulated, i, fused_d):
     """LogLinearCDE (D / BD / DE, chunked scanner configs) through the product mirror on the emulated K2 kernels;
-    fused_d = 1 routes the diagonal configs through the K2d kernels (tuning "k2_fused_d")."""
+    fused_d = 1: the library's default kernels (the diagonal configs run the fused K2d kernels), 0: the baseline kernels
+    (`kernel_flags("generic")`: flow build + sequential scans)."""
     from lncde import _lib, train as T
     from lncde.models.generate_model import create_model
 
     B, L, C_, s, depth, H, bs, Psteps, cls, ld = (int(v) for v in LN[f"cfg{i}"])
-    if fused_d and bs != 1:
-        pytest.skip("k2_fused_d only changes the diagonal model")
     model, _ = create_model(str(LN[f"name{i}"]), C_, LN[f"logsig{i}"].shape[-1], depth, None, ld, H, block_size=bs,
                             classification=bool(cls), lambd=float(LN[f"lambd{i}"]), parallel_steps=Psteps, key=1,
                             device="cpu")
@@ -121,11 +120,10 @@ def test_linear_ncde_mirror_vs_reference_code(emulated, i, fused_d):
     X = (torch.from_numpy(np.tile(_ts(L), (B, 1))), torch.from_numpy(LN[f"logsig{i}"]).float(),
          torch.from_numpy(LN[f"x{i}"][:, 0, :].copy()).float())
     y = torch.from_numpy(LN[f"y{i}"]).float()
-    _lib.set_tuning("k2_fused_d", fused_d)
-    try:
+    import contextlib
+
+    with (contextlib.nullcontext() if fused_d else _lib.kernel_flags("generic")):
         loss, grads = (T.classification_loss if cls else T.regression_loss)(model, X, y)
-    finally:
-        _lib.set_tuning("k2_fused_d", 0)
     want = float(LN[f"loss{i}"])
     assert abs(float(loss) - want) < TOL * max(1.0, abs(want))
     assert rel_err(grads.numpy(), LN[f"grad{i}"]) < 5 * TOL

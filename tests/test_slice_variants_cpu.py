@@ -37,6 +37,8 @@ def build(i, monkeypatch, device="cpu"):
 
     if device == "cpu":
         monkeypatch.setattr(M, "_LinearScan", TorchScan)
+        monkeypatch.setattr(M, "_diag_scan",  # the diagonal part of diagonal + dense: same contract with 1 x 1 blocks
+                            lambda vf_At, ls, y0: TorchScan.apply(vf_At, ls, y0, (vf_At.shape[0], 1, vf_At.shape[1])))
         monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
     B, L, C, s, depth, H, bs, P, cls, ld = (int(v) for v in S[f"cfg{i}"])
     kind, kw = str(S[f"kind{i}"]), ast.literal_eval(str(S[f"kw{i}"]))
