@@ -201,6 +201,39 @@ int lncde_adam_step(void* stream, float* params, const float* grads, float* m, f
 int lncde_adam_step_dev(void* stream, float* params, const float* grads, float* m, float* v, int64_t n,
                         float lr, float beta1, float beta2, float eps, int* step_counter, float grad_scale);
 
+/* ------------------------------------------------------------------ K5 ---
+ * The classification train step around the solve, as kernels: initial state, read-out + cross-entropy and the Lip(2)
+ * regulariser, each with its gradient (fixed summation orders, no atomics).  Replaces the XLA-lowered bodies of
+ *   y0 = linear1(x0)                          models/LogNeuralCDEs.py:139 (init_layer: models/LinearNeuralCDEs.py:303)
+ *   pred = softmax(linear2(h))                models/LogNeuralCDEs.py:159-160, models/LinearNeuralCDEs.py:388-391
+ *   mean_b(-sum_c y log(pred + 1e-8))         train.py:95 (classification_loss)
+ *   lambd * sum_layers mean(||W_row|| + ||b||) train.py:79-93
+ * and of their reverse-mode derivatives under eqx.filter_value_and_grad (train.py:71-72).                       */
+
+/* y [B, n_out] = x [B, n_in] W^T + b   (eqx.nn.Linear layout W [n_out, n_in]) */
+int lncde_affine_fwd(void* stream, const float* x, const float* W, const float* b, float* y, int B, int n_in, int n_out);
+/* g_W [n_out, n_in] = g_y^T x, g_b [n_out] = sum_b g_y (both fully overwritten) */
+int lncde_affine_bwd(void* stream, const float* x, const float* g_y, float* g_W, float* g_b, int B, int n_in, int n_out);
+
+/* h: B rows of H floats, row s at h + s * h_stride (e.g. the last state of ys [B, n_steps + 1, H]); labels [B, L] one-hot
+ * (or soft); L <= 32.  Outputs, all overwritten: pred [B, L] (may be NULL), loss [1] = mean cross-entropy,
+ * g_h rows (stride g_h_stride) = d loss / d h, g_W [L, H], g_b [L].  workspace: lncde_readout_ce_workspace_bytes.   */
+size_t lncde_readout_ce_workspace_bytes(int B, int L);
+int lncde_readout_ce(void* stream, const float* h, long long h_stride, const float* W, const float* b,
+                     const float* labels, float* pred, float* loss, float* g_h, long long g_h_stride, float* g_W,
+                     float* g_b, int B, int H, int L, void* workspace, size_t workspace_bytes);
+
+/* out [B, H] = mean over t of ys [B, T, H] (the LNCDE read-out, models/LinearNeuralCDEs.py:389) and its gradient
+ * g_ys [B, T, H] = g_mean [B, H] / T (fully overwritten).  H <= 1024.                                                */
+int lncde_time_mean_fwd(void* stream, const float* ys, float* out, int B, int T, int H);
+int lncde_time_mean_bwd(void* stream, const float* g_mean, float* g_ys, int B, int T, int H);
+
+/* loss [1] += lambd * sum_l (mean_rows ||W_l[row, :]|| + ||b_l||), g_params += its gradient.  Layer l: W_l at
+ * params + w_off[l] as [rows[l], cols[l]], b_l at params + b_off[l] as [rows[l]] (b_off[l] < 0: no bias term - the
+ * LNCDE's vf_A); the four index arrays are HOST arrays of n_layers <= 8 entries.                                     */
+int lncde_lip2(void* stream, const float* params, float* loss, float* g_params, int n_layers, const int32_t* w_off,
+               const int32_t* b_off, const int32_t* rows, const int32_t* cols, float lambd);
+
 /* ------------------------------------------------------- measurement ---
  * FP32 FFMA issue-rate probe (no reference counterpart; SURVEY.md 8d asks for a measured FP32 peak next to the
  * HBM / tensor peaks of MEASURED_PEAKS.json).  Launches `blocks` CTAs of 256 threads, each thread running 8

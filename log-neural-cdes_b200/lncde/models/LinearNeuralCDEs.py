@@ -259,6 +259,80 @@ class LogLinearCDE:
         lie = self.log_ode(vfs)
         return _LinearScan.apply(lie, logsigs, y0, (nb, bs, lie.shape[-1]))
 
+    def fused_classification_loss(self, X, y):
+        """One classification train step with the kernels of K2 / K5 only around the scans (initial state, time mean,
+        read-out + cross-entropy, Lip(2) term, init_layer / out_layer gradients) - torch autograd is left with
+        `log_ode` alone (parameters -> bracket matrices; nothing for the diagonal model).  Plain D / BD / DE structures;
+        the other SLiCE parameterisations return None and take the autograd formulation."""
+        if self.diagonal_dense or self._sparse_idx is not None or self.rank > 0 or self.walsh_hadamard:
+            return None
+        ts, logsigs, x0 = X
+        _lib.require_cuda(logsigs)
+        _lib.require_cuda_device(x0, y)
+        L = _lib.lib()
+        C, H, nb, bs, nl = self.data_dim, self.hidden_dim, self.num_blocks, self.block_size, self.label_dim
+        ls, x0c, yc = logsigs.contiguous(), x0.contiguous(), y.contiguous()
+        B, T, D = ls.shape
+        dev = ls.device
+        p = self.params.detach()
+        nA, o2 = self.n_A, self.n_A + H * (C + 1)  # [vf_A | init_layer W, b | out_layer W, b]
+        grads = torch.empty_like(p)
+        s = _lib.stream_ptr()
+        y0 = torch.empty((B, H), device=dev)
+        _lib.check(L.lncde_affine_fwd(s, _lib.ptr(x0c), p.data_ptr() + 4 * nA, p.data_ptr() + 4 * (nA + H * C), _lib.ptr(y0),
+                                      B, C, H), "lncde_affine_fwd")
+        ys = torch.empty((B, T, H), device=dev)
+        diag = bs == 1 and C <= 8
+        flags = _lib.call_flags()
+        if diag:
+            vf_At = p[:nA].view(C, H).t().contiguous()
+            _lib.check(L.lncde_dlncde_fwd(s, _lib.ptr(vf_At), _lib.ptr(ls), _lib.ptr(y0), _lib.ptr(ys), B, T, D, H, C),
+                       "lncde_dlncde_fwd")
+        else:
+            with torch.enable_grad():
+                lie_t = self.log_ode(self.vf_A.view(C, nb, bs, bs))  # the one piece torch autograd still differentiates
+            lie = lie_t.detach().contiguous()
+            n_basis = lie.shape[-1]
+            nbytes = L.lncde_linear_scan_workspace_bytes(B, T, nb, bs, n_basis)
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            _lib.check(L.lncde_linear_scan_fwd(s, _lib.ptr(lie), _lib.ptr(ls), _lib.ptr(y0), _lib.ptr(ys), B, T, D, nb, bs,
+                                               n_basis, _lib.ptr(ws), nbytes, flags), "lncde_linear_scan_fwd")
+        hmean, g_mean = torch.empty((B, H), device=dev), torch.empty((B, H), device=dev)
+        loss = torch.empty(1, device=dev)
+        _lib.check(L.lncde_time_mean_fwd(s, _lib.ptr(ys), _lib.ptr(hmean), B, T, H), "lncde_time_mean_fwd")
+        ce_nb = L.lncde_readout_ce_workspace_bytes(B, nl)
+        ce_ws = torch.empty(max(ce_nb, 1), device=dev, dtype=torch.uint8)
+        _lib.check(L.lncde_readout_ce(s, _lib.ptr(hmean), H, p.data_ptr() + 4 * o2, p.data_ptr() + 4 * (o2 + nl * H),
+                                      _lib.ptr(yc), None, _lib.ptr(loss), _lib.ptr(g_mean), H, grads.data_ptr() + 4 * o2,
+                                      grads.data_ptr() + 4 * (o2 + nl * H), B, H, nl, _lib.ptr(ce_ws), ce_nb),
+                   "lncde_readout_ce")
+        g_ys = torch.empty((B, T, H), device=dev)
+        _lib.check(L.lncde_time_mean_bwd(s, _lib.ptr(g_mean), _lib.ptr(g_ys), B, T, H), "lncde_time_mean_bwd")
+        g_y0 = torch.empty((B, H), device=dev)
+        if diag:
+            nbytes = L.lncde_dlncde_bwd_workspace_bytes(B, H, C)
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            g_At = torch.empty_like(vf_At)
+            _lib.check(L.lncde_dlncde_bwd(s, _lib.ptr(vf_At), _lib.ptr(ls), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_At),
+                                          _lib.ptr(g_y0), B, T, D, H, C, _lib.ptr(ws), nbytes), "lncde_dlncde_bwd")
+            grads[:nA].view(C, H).copy_(g_At.t())
+        else:
+            g_lie = torch.empty_like(lie)
+            _lib.check(L.lncde_linear_scan_bwd(s, _lib.ptr(lie), _lib.ptr(ls), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_lie),
+                                               _lib.ptr(g_y0), B, T, D, nb, bs, n_basis, _lib.ptr(ws), nbytes, flags),
+                       "lncde_linear_scan_bwd")
+            (g_p,) = torch.autograd.grad(lie_t, self.params, g_lie)
+            grads[:nA].copy_(g_p[:nA])
+        _lib.check(L.lncde_affine_bwd(s, _lib.ptr(x0c), _lib.ptr(g_y0), grads.data_ptr() + 4 * nA,
+                                      grads.data_ptr() + 4 * (nA + H * C), B, C, H), "lncde_affine_bwd")
+        if self.lip2 and self.lambd != 0.0:  # lambd * mean_rows ||vf_A[row, :]||  (train.py:87-88)
+            import ctypes
+
+            one = lambda v: (ctypes.c_int32 * 1)(v)
+            _lib.check(L.lncde_lip2(s, _lib.ptr(p), _lib.ptr(loss), _lib.ptr(grads), 1, one(0), one(-1), one(C), one(nA // C),
+                                    float(self.lambd)), "lncde_lip2")
+        return loss[0], grads
+
     def __call__(self, X):
         ys = self.hidden_states(X)
         if self.classification:

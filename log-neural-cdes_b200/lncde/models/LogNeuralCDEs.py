@@ -56,56 +56,66 @@ class VectorField:
         self.mlp = _MLP(layers)
 
 
+def solve_fwd(mlp_flat, logsig, y0, rows, scale, dims, train):
+    """lncde_logncde_fwd on the whole batch.  Returns (ys, token); `token` carries what solve_bwd needs to use the
+    per-stage intermediates the training-mode forward left in the shared scratch."""
+    H, C, width, n_hidden, depth = dims
+    _lib.require_cuda(mlp_flat, logsig, y0, rows, scale)
+    L = _lib.lib()
+    B, K, D = logsig.shape
+    n_steps = rows.shape[0]
+    ys = torch.empty((B, n_steps + 1, H), device=y0.device, dtype=torch.float32)
+    # training mode: hand the adjoint workspace to the forward so it can keep its intermediates
+    nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, C, width, n_hidden, depth, n_steps) if train else 0
+    ws = _workspace(nbytes, ys.device) if train else None  # bumps the generation: earlier saved forwards are void
+    flags = _lib.call_flags()
+    st = L.lncde_logncde_fwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(y0),
+                             _lib.ptr(rows), _lib.ptr(scale), _lib.ptr(ys), B, K, D, H, C, width, n_hidden,
+                             depth, n_steps, _lib.ptr(ws), nbytes, flags)
+    _lib.check(st, "lncde_logncde_fwd")
+    # shared grow-only scratch: its contents are valid until the next hand-out of the buffer on this device
+    return ys, (ws, _WS_GEN.get(ys.device, 0), flags)
+
+
+def solve_bwd(mlp_flat, logsig, rows, scale, ys, g_ys, dims, token, g_params=None):
+    """lncde_logncde_bwd: (g_params of the vector-field MLP [summed over the batch; written into `g_params` if given],
+    g_y0)."""
+    H, C, width, n_hidden, depth = dims
+    L = _lib.lib()
+    B, K, D = logsig.shape
+    n_steps = rows.shape[0]
+    nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, C, width, n_hidden, depth, n_steps)
+    ws, ws_gen, flags = token
+    # LNCDE_FLAG_SAVED_FWD only if nobody has been handed the scratch since our forward wrote it
+    saved = _lib.FLAG_SAVED_FWD if (ws is not None and _WS.get(ys.device) is ws and _WS_GEN.get(ys.device) == ws_gen) else 0
+    if ws is None or saved == 0:
+        ws = _workspace(nbytes, ys.device)  # recompute mode overwrites the scratch: bumps the generation too
+    if g_params is None:
+        g_params = torch.empty_like(mlp_flat)
+    g_y0 = torch.empty((B, H), device=ys.device, dtype=torch.float32)
+    st = L.lncde_logncde_bwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(rows),
+                             _lib.ptr(scale), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_params), _lib.ptr(g_y0),
+                             B, K, D, H, C, width, n_hidden, depth, n_steps, _lib.ptr(ws), nbytes,
+                             saved | (flags & ~_lib.FLAG_SAVED_FWD))
+    _lib.check(st, "lncde_logncde_bwd")
+    if saved:  # the sweep wrote its (left, right) gradient pairs over the buffer: a second backward must recompute
+        _WS_GEN[ys.device] = _WS_GEN.get(ys.device, 0) + 1
+    return g_params, g_y0
+
+
 class _LogNCDESolve(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mlp_flat, logsig, y0, rows, scale, dims):
-        H, C, width, n_hidden, depth = dims
-        _lib.require_cuda(mlp_flat, logsig, y0, rows, scale)
-        L = _lib.lib()
-        B, K, D = logsig.shape
-        n_steps = rows.shape[0]
-        ys = torch.empty((B, n_steps + 1, H), device=y0.device, dtype=torch.float32)
         mlp_flat = mlp_flat.contiguous()
-        y0c = y0.contiguous()
-        # training mode: hand the adjoint workspace to the forward so it can keep its intermediates
-        train = any(ctx.needs_input_grad)
-        nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, C, width, n_hidden, depth, n_steps) if train else 0
-        ws = _workspace(nbytes, ys.device) if train else None  # bumps the generation: earlier saved forwards are void
-        st = L.lncde_logncde_fwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(y0c),
-                                 _lib.ptr(rows), _lib.ptr(scale), _lib.ptr(ys), B, K, D, H, C, width, n_hidden,
-                                 depth, n_steps, _lib.ptr(ws), nbytes, _lib.call_flags())
-        _lib.check(st, "lncde_logncde_fwd")
+        ys, ctx.token = solve_fwd(mlp_flat, logsig, y0.contiguous(), rows, scale, dims, any(ctx.needs_input_grad))
         ctx.save_for_backward(mlp_flat, logsig, rows, scale, ys)
         ctx.dims = dims
-        # shared grow-only scratch: its contents are valid until the next training-mode forward on this device
-        ctx.ws = ws
-        ctx.ws_gen = _WS_GEN.get(ys.device, 0)
-        ctx.flags = _lib.call_flags()
         return ys
 
     @staticmethod
     def backward(ctx, g_ys):
         mlp_flat, logsig, rows, scale, ys = ctx.saved_tensors
-        H, C, width, n_hidden, depth = ctx.dims
-        L = _lib.lib()
-        B, K, D = logsig.shape
-        n_steps = rows.shape[0]
-        g_ys = g_ys.contiguous()
-        nbytes = L.lncde_logncde_bwd_workspace_bytes(B, H, C, width, n_hidden, depth, n_steps)
-        ws = ctx.ws
-        # LNCDE_FLAG_SAVED_FWD only if nobody has reused the scratch since our forward wrote it
-        saved = 2 if (ws is not None and _WS.get(ys.device) is ws and _WS_GEN.get(ys.device) == ctx.ws_gen) else 0
-        if ws is None or saved == 0:
-            ws = _workspace(nbytes, ys.device)  # recompute mode overwrites the scratch: bumps the generation too
-        g_params = torch.empty_like(mlp_flat)
-        g_y0 = torch.empty((B, H), device=ys.device, dtype=torch.float32)
-        st = L.lncde_logncde_bwd(_lib.stream_ptr(), _lib.ptr(mlp_flat), _lib.ptr(logsig), _lib.ptr(rows),
-                                 _lib.ptr(scale), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_params), _lib.ptr(g_y0),
-                                 B, K, D, H, C, width, n_hidden, depth, n_steps, _lib.ptr(ws), nbytes,
-                                 saved | (ctx.flags & ~_lib.FLAG_SAVED_FWD))
-        _lib.check(st, "lncde_logncde_bwd")
-        if saved:  # the sweep wrote its (left, right) gradient pairs over the buffer: a second backward must recompute
-            _WS_GEN[ys.device] = _WS_GEN.get(ys.device, 0) + 1
+        g_params, g_y0 = solve_bwd(mlp_flat, logsig, rows, scale, ys, g_ys.contiguous(), ctx.dims, ctx.token)
         return g_params, None, g_y0, None, None, None
 
 
@@ -225,6 +235,62 @@ class LogNeuralCDE:
         dims = (self.hidden_dim, self.data_dim, self.vf_width, self.vf_depth, self.depth)
         ys = _LogNCDESolve.apply(self.mlp_flat(), logsig.contiguous(), y0, rows, scale, dims)
         return ys, interp
+
+    def fused_classification_loss(self, X, y):
+        """One classification train step WITHOUT torch autograd / eager glue: initial state, solve, read-out +
+        cross-entropy, adjoint sweep, Lip(2) term and the gradients of linear1 / linear2 are all library kernels
+        (K3, K3b, K5) writing into one flat gradient in the layout of ``self.params``.  Same value and gradient as
+        ``train.classification_loss`` through autograd (tests/test_logncde_gpu.py, tests over the emulator)."""
+        ts, logsig, x0 = X
+        _lib.require_cuda(logsig)
+        _lib.require_cuda_device(x0, y)
+        L = _lib.lib()
+        rows, scale, _ = self._stage_table(ts, logsig.shape[1])
+        H, C, nl = self.hidden_dim, self.data_dim, self.label_dim
+        B, n_steps = logsig.shape[0], rows.shape[0]
+        dev = logsig.device
+        p = self.params.detach()
+        x0c, yc, ls = x0.contiguous(), y.contiguous(), logsig.contiguous()
+        o1, o2 = self.n_mlp, self.n_mlp + H * (C + 1)  # [mlp | linear1 W, b | linear2 W, b]
+        W1, b1, W2, b2 = p[o1 : o1 + H * C], p[o1 + H * C : o2], p[o2 : o2 + nl * H], p[o2 + nl * H :]
+        grads = torch.empty_like(p)
+        key = (B, n_steps, dev)
+        if getattr(self, "_fused_buf", (None,))[0] != key:
+            nb = L.lncde_readout_ce_workspace_bytes(B, nl)
+            # g_ys: zero except its last row, which every step overwrites - never cleared again
+            self._fused_buf = (key, torch.zeros((B, n_steps + 1, H), device=dev), torch.empty(max(nb, 1), dtype=torch.uint8,
+                                                                                                device=dev), nb)
+        _, g_ys, ce_ws, ce_nb = self._fused_buf
+        y0 = torch.empty((B, H), device=dev)
+        loss = torch.empty(1, device=dev)
+        s = _lib.stream_ptr()
+        _lib.check(L.lncde_affine_fwd(s, _lib.ptr(x0c), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(y0), B, C, H), "lncde_affine_fwd")
+        dims = (H, C, self.vf_width, self.vf_depth, self.depth)
+        mlp = p[: self.n_mlp]
+        ys, token = solve_fwd(mlp, ls, y0, rows, scale, dims, True)
+        last = n_steps * H  # offset of y(t1) inside a sample's [n_steps + 1, H] block
+        stride = (n_steps + 1) * H
+        _lib.check(L.lncde_readout_ce(s, ys.data_ptr() + 4 * last, stride, _lib.ptr(W2), _lib.ptr(b2), _lib.ptr(yc), None,
+                                      _lib.ptr(loss), g_ys.data_ptr() + 4 * last, stride, _lib.ptr(grads[o2:]),
+                                      grads.data_ptr() + 4 * (o2 + nl * H), B, H, nl, _lib.ptr(ce_ws), ce_nb),
+                   "lncde_readout_ce")
+        _, g_y0 = solve_bwd(mlp, ls, rows, scale, ys, g_ys, dims, token, g_params=grads[: self.n_mlp])
+        _lib.check(L.lncde_affine_bwd(s, _lib.ptr(x0c), _lib.ptr(g_y0), grads.data_ptr() + 4 * o1,
+                                      grads.data_ptr() + 4 * (o1 + H * C), B, C, H), "lncde_affine_bwd")
+        if self.lip2 and self.lambd != 0.0:
+            import ctypes
+
+            lay = self.vf.mlp.layers
+            arr = lambda v: (ctypes.c_int32 * len(v))(*v)
+            w_off, b_off, off = [], [], 0
+            for l in lay:
+                w_off.append(off)
+                b_off.append(off + l.out_features * l.in_features)
+                off += l.numel
+            _lib.check(L.lncde_lip2(s, _lib.ptr(p), _lib.ptr(loss), _lib.ptr(grads), len(lay), arr(w_off), arr(b_off),
+                                    arr([l.out_features for l in lay]), arr([l.in_features for l in lay]),
+                                    float(self.lambd)), "lncde_lip2")
+        return loss[0], grads
 
     def __call__(self, X):
         ys, interp = self.hidden_states(X)

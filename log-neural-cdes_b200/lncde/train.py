@@ -41,7 +41,15 @@ def _value_and_grad(model, loss):
 
 
 def classification_loss(model, X, y, state=None, key=None):
-    """train.py:71-97: mean(-sum(y * log(pred + 1e-8))) + Lip(2) term."""
+    """train.py:71-97: mean(-sum(y * log(pred + 1e-8))) + Lip(2) term.
+
+    Models that bring a kernel-only step (``fused_classification_loss``: LogNeuralCDE) take it - no torch autograd, no
+    eager glue between the solve kernels; ``lncde._lib.kernel_flags("generic")`` keeps the autograd formulation below
+    reachable (it is what the fused step is tested against)."""
+    if model.classification and hasattr(model, "fused_classification_loss") and not (_lib.call_flags() & _lib.FLAG_GENERIC):
+        fused = model.fused_classification_loss(X, y)
+        if fused is not None:  # None: a parameterisation without a kernel-only step (the rarer SLiCE structures)
+            return fused
     pred, _ = calc_output(model, X, state, key, model.stateful, model.nondeterministic)
     loss = torch.mean(-torch.sum(y * torch.log(pred + 1e-8), dim=1)) + _lip2(model)
     return _value_and_grad(model, loss)

@@ -227,3 +227,63 @@ def test_saved_forward_scratch_is_not_reused_after_another_solve(emulated):
     _NRDESolve.apply(nflat, pa[1], ny0, pa[3], pa[4], (16, 8, 2)).sum().backward()
     (out_a * pa[5]).sum().backward()
     assert rel_err(fa.grad.numpy(), want_a[0].numpy()) < 1e-6 and rel_err(ya.grad.numpy(), want_a[1].numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("lambd", [0.0, 0.01])
+@pytest.mark.parametrize("dims", [(3, 64, 3, 4, 2, 16, 8, 2, 3), (2, 96, 7, 12, 2, 128, 32, 2, 5), (5, 40, 2, 4, 1, 8, 8, 1, 2)])
+def test_fused_classification_step_equals_autograd_step(emulated, dims, lambd):
+    """LogNeuralCDE.fused_classification_loss (K5 kernels: initial state, read-out + cross-entropy, Lip(2), linear1 /
+    linear2 gradients around K3 / K3b, no torch autograd) against the autograd formulation of train.classification_loss
+    (`kernel_flags("generic")`) and against the fp64 oracle loss."""
+    from lncde import _lib, train as T
+    from lncde.models.generate_model import create_model
+    from oracle import log_ncde as O
+    from oracle import paths
+
+    B, L, C_, s, depth, H, width, nh, nl = dims
+    rng = np.random.default_rng(B)
+    x = np.cumsum(rng.normal(scale=0.3, size=(B, L, C_)), axis=1).astype(np.float32)
+    logsig = paths.calc_paths(x, s, depth, np.float32)
+    ts = paths.make_ts(L)
+    iv = paths.make_intervals(ts, s)
+    model, _ = create_model("log_ncde", C_, logsig.shape[-1], depth, iv, nl, H, vf_depth=nh, vf_width=width, dt0=0.05,
+                            scale=2.0, lambd=lambd, key=3, device="cpu")
+    X = (torch.from_numpy(np.tile(ts, (B, 1))), torch.from_numpy(logsig), torch.from_numpy(x[:, 0, :].copy()))
+    y = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, nl, size=B)), nl).float()
+    with _lib.kernel_flags("generic"):
+        l0, g0 = T.classification_loss(model, X, y)
+    l1, g1 = T.classification_loss(model, X, y)
+    l2, g2 = T.classification_loss(model, X, y)  # second call: cached buffers (zero g_ys rows) are reused
+    assert abs(float(l1) - float(l0)) < 1e-6 * max(1.0, abs(float(l0)))
+    assert rel_err(g1.numpy(), g0.numpy()) < 2e-6
+    assert torch.equal(l1, l2) and torch.equal(g1, g2)
+    # every parameter block on its own (a wrong small block would hide behind the largest one)
+    n_mlp, o2 = model.n_mlp, model.n_mlp + H * (C_ + 1)
+    for a, b in ((0, n_mlp), (n_mlp, n_mlp + H * C_), (n_mlp + H * C_, o2), (o2, o2 + nl * H), (o2 + nl * H, g0.numel())):
+        assert rel_err(g1[a:b].numpy(), g0[a:b].numpy()) < 1e-5, (a, b)
+
+
+@pytest.mark.parametrize("name,bs,lambd", [("diagonal_linear_ncde", 1, 0.1), ("bd_linear_ncde", 4, 0.1),
+                                            ("dense_linear_ncde", 8, 0.0), ("bd_linear_ncde", 2, 0.0)])
+def test_fused_lncde_classification_step_equals_autograd_step(emulated, name, bs, lambd):
+    """LogLinearCDE.fused_classification_loss (K5 kernels around the K2 scans; autograd only through log_ode) against the
+    autograd formulation under `kernel_flags("generic")` - the generic run also uses the baseline scans, so this covers
+    the default kernels (fused diagonal scan, time-parallel scans need T > 65) against the baseline ones as well."""
+    from lncde import _lib, train as T
+    from lncde.models.generate_model import create_model
+    from oracle import paths
+
+    B, L, C_, s, depth, H, nl = 3, 280, 3, 4, 2, 8, 3
+    rng = np.random.default_rng(7)
+    x = np.cumsum(rng.normal(scale=0.1, size=(B, L, C_)), axis=1).astype(np.float32)
+    logsig = paths.calc_paths(x, s, depth, np.float32)
+    model, _ = create_model(name, C_, logsig.shape[-1], depth, None, nl, H, block_size=bs, lambd=lambd, key=5, device="cpu")
+    X = (None, torch.from_numpy(logsig), torch.from_numpy(x[:, 0, :].copy()))
+    y = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, nl, size=B)), nl).float()
+    with _lib.kernel_flags("generic"):
+        l0, g0 = T.classification_loss(model, X, y)
+    l1, g1 = T.classification_loss(model, X, y)
+    assert abs(float(l1) - float(l0)) < 2e-6 * max(1.0, abs(float(l0)))
+    nA, o2 = model.n_A, model.n_A + H * (C_ + 1)
+    for a, b in ((0, nA), (nA, nA + H * C_), (nA + H * C_, o2), (o2, o2 + nl * H), (o2 + nl * H, g0.numel())):
+        assert rel_err(g1[a:b].numpy(), g0[a:b].numpy()) < 1e-5, (name, a, b)

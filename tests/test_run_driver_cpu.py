@@ -126,6 +126,7 @@ def test_run_experiments_end_to_end(monkeypatch, tmp_path):
 
     monkeypatch.setattr(M, "_LinearScan", TorchScan)
     monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "call_flags", lambda: _lib.FLAG_GENERIC)  # host logic only: the autograd formulation, no library kernels
     monkeypatch.setattr(_lib, "require_cuda_device", lambda *a: None)
 
     class CpuAdam:

@@ -40,6 +40,7 @@ def build(i, monkeypatch, device="cpu"):
         monkeypatch.setattr(M, "_diag_scan",  # the diagonal part of diagonal + dense: same contract with 1 x 1 blocks
                             lambda vf_At, ls, y0: TorchScan.apply(vf_At, ls, y0, (vf_At.shape[0], 1, vf_At.shape[1])))
         monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+        monkeypatch.setattr(_lib, "call_flags", lambda: _lib.FLAG_GENERIC)  # host logic only: the autograd formulation, no library kernels
     B, L, C, s, depth, H, bs, P, cls, ld = (int(v) for v in S[f"cfg{i}"])
     kind, kw = str(S[f"kind{i}"]), ast.literal_eval(str(S[f"kw{i}"]))
     name = {"wh": "wh", "dplr": "dplr", "sparse": "sparse", "diagdense": "diagonal_dense"}[kind] + "_linear_ncde"

@@ -16,6 +16,7 @@ def _setup(monkeypatch, classification=True):
 
     monkeypatch.setattr(M, "_LinearScan", TorchScan)
     monkeypatch.setattr(_lib, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(_lib, "call_flags", lambda: _lib.FLAG_GENERIC)  # host logic only: the autograd formulation, no library kernels
 
     class CpuAdam:  # the fused K4 kernel needs a GPU: same update in torch for this host-logic test
         def __init__(self, model, lr, b1=0.9, b2=0.999, eps=1e-8):
