@@ -76,7 +76,7 @@ WL = dict(WORKLOADS["eigenworms_logncde"])
 N_ROT = 16  # distinct input batches rotated through (16 x 16.1 MB = 258 MB > 126 MB L2)
 FFMA_PROBE_SHAPE = (148 * 8, 2048)  # CTAs x loop trips of the FP32 probe launch (39.7 GFLOP: ~0.5 ms)
 K1_ROOFLINE_BATCH = 2048  # paths per launch of the K1 roofline leg (1.03 GB read + 0.36 GB written: > L2)
-K1_TMA_DRAM_TRAFFIC_BYTES = None  # per launch at that shape, from the committed ncu --set full capture (set when it exists)
+K1_TMA_DRAM_TRAFFIC_BYTES = 1.031656e9 + 0.330286e9  # per launch at that shape: dram__bytes_read.sum + dram__bytes_write.sum (profiles/r02_full_k1_tma.md)
 
 
 def peaks():

@@ -17,6 +17,7 @@ KEYS = [
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
@@ -31,9 +32,10 @@ KEYS = [
 def launches(src, dst):
     with open(src) as fh:
         lines = [l for l in fh if not l.startswith("==")]
+    scale = {"ns": 1.0, "nsecond": 1.0, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6}
     agg = collections.defaultdict(lambda: [0, 0.0])
     for row in csv.DictReader(lines):
-        v = float(row["Metric Value"].replace(",", ""))
+        v = float(row["Metric Value"].replace(",", "")) * scale.get(row.get("Metric Unit", "ns"), 1.0)
         agg[row["Kernel Name"][:90]][0] += 1
         agg[row["Kernel Name"][:90]][1] += v
     tot = sum(v[1] for v in agg.values())
@@ -46,7 +48,13 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """src: a .ncu-rep, or the CSV `ncu -i X.ncu-rep --page raw --csv` wrote on the GPU box (scripts/r2_ncu.sh keeps
+    only that for captures too large to bring back)."""
+    if src.endswith(".csv"):
+        with open(src) as fh:
+            raw = fh.read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(dst, "w") as out:

@@ -111,3 +111,27 @@ def test_diagonal_equals_1x1_blocks(built_lib):
     flows = 1 + ls.cpu().numpy()[:, :, 1:].astype(np.float64) @ lie.cpu().numpy().reshape(H, C).T.astype(np.float64)
     want = np.cumprod(np.concatenate([np.ones((B, 1, H)), flows[:, 1:]], 1), axis=1) * y0.cpu().numpy()[:, None, :]
     assert rel_err(ys, want) < TOL
+
+
+@pytest.mark.parametrize("name,bs", [("diagonal_linear_ncde", 1), ("bd_linear_ncde", 4), ("dense_linear_ncde", 128)])
+def test_fused_lncde_classification_step_equals_autograd_step(built_lib, name, bs):
+    """LogLinearCDE.fused_classification_loss (the library's default kernels + K5) against the autograd formulation on the
+    baseline kernels (`kernel_flags("generic")`), EigenWorms model dims, T > 65 so the time-parallel scans run."""
+    from lncde import _lib, train as T
+    from lncde.models.generate_model import create_model
+
+    B, L, C, s, H, nl = 4, 1200, 7, 12, 128, 5
+    rng = np.random.default_rng(4)
+    x = np.cumsum(rng.normal(scale=0.02, size=(B, L, C)), axis=1).astype(np.float32)
+    logsig = paths.calc_paths(x, s, 2, np.float32)
+    model, _ = create_model(name, C, logsig.shape[-1], 2, None, nl, H, block_size=bs, lambd=1e-3, key=5)
+    X = (None, torch.from_numpy(logsig).cuda(), torch.from_numpy(x[:, 0, :].copy()).cuda())
+    y = torch.eye(nl, device="cuda")[torch.arange(B, device="cuda") % nl]
+    with _lib.kernel_flags("generic"):
+        l0, g0 = T.classification_loss(model, X, y)
+    l1, g1 = T.classification_loss(model, X, y)
+    assert abs(float(l1) - float(l0)) < 2e-6 * max(1.0, abs(float(l0)))
+    nA, o2 = model.n_A, model.n_A + H * (C + 1)
+    g0, g1 = g0.cpu().numpy(), g1.cpu().numpy()
+    for a, b in ((0, nA), (nA, nA + H * C), (nA + H * C, o2), (o2, o2 + nl * H), (o2 + nl * H, g0.size)):
+        assert rel_err(g1[a:b], g0[a:b]) < TOL, (name, a, b)

@@ -146,3 +146,29 @@ def test_model_loss_and_grads(built_lib, classification):
     assert abs(float(loss) - float(lo)) < TOL * max(1.0, abs(float(lo)))
     assert rel_err(grads.cpu().numpy(), go.numpy()) < TOL
     assert len(p) == len(go)
+
+
+@pytest.mark.parametrize("lambd", [0.0, 1e-3])
+def test_fused_classification_step_equals_autograd_step(built_lib, lambd):
+    """The kernel-only train step (K5 around K3 / K3b: LogNeuralCDE.fused_classification_loss, the path bench.py times)
+    against the torch-autograd formulation of the same loss (`kernel_flags("generic")`) at the EigenWorms model dims."""
+    from lncde import _lib, train as T
+    from lncde.models.generate_model import create_model
+
+    B, L, C, s, H = 6, 480, 7, 12, 128
+    rng = np.random.default_rng(2)
+    x = np.cumsum(rng.normal(scale=0.05, size=(B, L, C)), axis=1).astype(np.float32)
+    logsig = paths.calc_paths(x, s, 2, np.float32)
+    ts = paths.make_ts(L)
+    model, _ = create_model("log_ncde", C, logsig.shape[-1], 2, paths.make_intervals(ts, s), 5, H, vf_depth=2, vf_width=32,
+                            dt0=1.0 / 40, scale=10.0, lambd=lambd, key=7)
+    X = (torch.from_numpy(np.tile(ts, (B, 1))).cuda(), torch.from_numpy(logsig).cuda(), torch.from_numpy(x[:, 0, :].copy()).cuda())
+    y = torch.eye(5, device="cuda")[torch.arange(B, device="cuda") % 5]
+    with _lib.kernel_flags("generic"):
+        l0, g0 = T.classification_loss(model, X, y)
+    l1, g1 = T.classification_loss(model, X, y)
+    assert abs(float(l1) - float(l0)) < 1e-6 * max(1.0, abs(float(l0)))
+    n_mlp, o2 = model.n_mlp, model.n_mlp + H * (C + 1)
+    g0, g1 = g0.cpu().numpy(), g1.cpu().numpy()
+    for a, b in ((0, n_mlp), (n_mlp, n_mlp + H * C), (n_mlp + H * C, o2), (o2, o2 + 5 * H), (o2 + 5 * H, g0.size)):
+        assert rel_err(g1[a:b], g0[a:b]) < TOL, (a, b)

@@ -106,7 +106,7 @@ def test_slice_variants_vs_reference_code(built_lib, monkeypatch, i):
     import test_slice_variants_cpu as V
 
     model, X, y, cls, kind = V.build(i, monkeypatch, device="cuda")
-    V.check(i, model, X, y, cls, kind, 2e-5)
+    V.check(i, model, X, y, cls, kind, TOL, grad_tol=TOL)  # measured on B200: 4.8e-7 (profiles/r02_parity_errors.md)
 
 
 @pytest.mark.parametrize("inmemory", [True, False])

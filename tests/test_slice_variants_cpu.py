@@ -66,7 +66,7 @@ def build(i, monkeypatch, device="cpu"):
     return model, X, y, bool(cls), kind
 
 
-def check(i, model, X, y, cls, kind, tol):
+def check(i, model, X, y, cls, kind, tol, grad_tol=None):
     from lncde import train as T
 
     pred = model(X)
@@ -79,8 +79,9 @@ def check(i, model, X, y, cls, kind, tol):
     vfgrad = S[f"vfgrad{i}"]
     if kind == "sparse":
         vfgrad = vfgrad[model._sparse_idx.cpu().numpy()]  # gradient of the dense tensor at the pattern
-    assert rel_err(g[:n_vf], vfgrad) < 5 * tol
-    assert rel_err(g[n_vf:], S[f"iograd{i}"]) < 5 * tol
+    grad_tol = 5 * tol if grad_tol is None else grad_tol
+    assert rel_err(g[:n_vf], vfgrad) < grad_tol
+    assert rel_err(g[n_vf:], S[f"iograd{i}"]) < grad_tol
 
 
 @pytest.mark.parametrize("i", range(int(S["n"])))
