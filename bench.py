@@ -240,10 +240,10 @@ def run_ours(args):
         _, _, _, value = T.make_step(model, None, X, lab, loss_fn, None, opt, None, None, world_size=world)
         return value
 
-    # 1 GPU: the whole step (K1 .. Adam) replays as ONE CUDA graph launch.  N > 1: the step is launched
-    # eagerly - capturing the NCCL all-reduce inside the graph hung an 8-GPU run in round 1 (the eager
-    # N = 2 path is the one validated on hardware); the glue it leaves is ~0.5 ms of a 19 ms step.
-    use_graph = (not args.no_graph) and world == 1
+    # 1 GPU: the whole step (K1 .. Adam) replays as ONE CUDA graph launch.  N > 1: launched eagerly by default - with the
+    # kernel-only step (K5) that is ~15 launches + one ncclAllReduce, no longer ~110; capturing the all-reduce inside the
+    # graph hung an 8-GPU run in round 1 and stays opt-in (LNCDE_BENCH_GRAPH_NCCL=1) until it has been seen to work.
+    use_graph = (not args.no_graph) and (world == 1 or os.environ.get("LNCDE_BENCH_GRAPH_NCCL") == "1")
     step = T.GraphedStep(eager_step, [x_dev[0], lab_dev[0]]) if use_graph else eager_step
 
     # workloads whose per-step working set is smaller than L2 get an explicit L2 flush between steps

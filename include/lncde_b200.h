@@ -212,16 +212,21 @@ int lncde_adam_step_dev(void* stream, float* params, const float* grads, float* 
 
 /* y [B, n_out] = x [B, n_in] W^T + b   (eqx.nn.Linear layout W [n_out, n_in]) */
 int lncde_affine_fwd(void* stream, const float* x, const float* W, const float* b, float* y, int B, int n_in, int n_out);
-/* g_W [n_out, n_in] = g_y^T x, g_b [n_out] = sum_b g_y (both fully overwritten) */
-int lncde_affine_bwd(void* stream, const float* x, const float* g_y, float* g_W, float* g_b, int B, int n_in, int n_out);
+/* g_Wb = [g_W (n_out x n_in) | g_b (n_out)], the layout of an eqx.nn.Linear inside the flat parameter vector:
+ * g_W = g_y^T x, g_b = sum_b g_y (fully overwritten).  Sums over the batch run in chunks of 32 samples, combined in a
+ * fixed order; workspace: lncde_affine_bwd_workspace_bytes (0 bytes / may be NULL for B <= 32).                    */
+size_t lncde_affine_bwd_workspace_bytes(int B, int n_in, int n_out);
+int lncde_affine_bwd(void* stream, const float* x, const float* g_y, float* g_Wb, int B, int n_in, int n_out,
+                     void* workspace, size_t workspace_bytes);
 
 /* h: B rows of H floats, row s at h + s * h_stride (e.g. the last state of ys [B, n_steps + 1, H]); labels [B, L] one-hot
- * (or soft); L <= 32.  Outputs, all overwritten: pred [B, L] (may be NULL), loss [1] = mean cross-entropy,
- * g_h rows (stride g_h_stride) = d loss / d h, g_W [L, H], g_b [L].  workspace: lncde_readout_ce_workspace_bytes.   */
-size_t lncde_readout_ce_workspace_bytes(int B, int L);
+ * (or soft); L <= 32.  Outputs, all overwritten: pred [B, L] (may be NULL), g_h rows (stride g_h_stride) = d loss / d h,
+ * g_Wb_loss = [g_W (L x H) | g_b (L) | loss (1)] - the linear layer's gradient in flat-parameter layout followed by the
+ * mean cross-entropy.  workspace: lncde_readout_ce_workspace_bytes.                                                 */
+size_t lncde_readout_ce_workspace_bytes(int B, int H, int L);
 int lncde_readout_ce(void* stream, const float* h, long long h_stride, const float* W, const float* b,
-                     const float* labels, float* pred, float* loss, float* g_h, long long g_h_stride, float* g_W,
-                     float* g_b, int B, int H, int L, void* workspace, size_t workspace_bytes);
+                     const float* labels, float* pred, float* g_h, long long g_h_stride, float* g_Wb_loss, int B, int H,
+                     int L, void* workspace, size_t workspace_bytes);
 
 /* out [B, H] = mean over t of ys [B, T, H] (the LNCDE read-out, models/LinearNeuralCDEs.py:389) and its gradient
  * g_ys [B, T, H] = g_mean [B, H] / T (fully overwritten).  H <= 1024.                                                */

@@ -30,22 +30,37 @@ __global__ void __launch_bounds__(256) affine_fwd_kernel(const float* __restrict
   }
 }
 
-// g_W[o][c] = sum_b g_y[b][o] x[b][c], g_b[o] = sum_b g_y[b][o]; one thread per (o, c) entry (+ one per bias), b ascending
+// Sums over the batch are split into chunks of kChunk samples (grid.y), each chunk summed in ascending sample order into
+// its own partial, the partials added in ascending chunk order by chunk_reduce_kernel: deterministic for any B, and a
+// batch of 2 048 does not leave one thread with 2 048 dependent loads.  A single chunk writes its result directly.
+constexpr int kChunk = 32;
+
+__global__ void __launch_bounds__(256) chunk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, int n,
+                                                            int stride, int chunks, float scale) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < chunks; ++c) acc += part[(size_t)c * stride + e];
+    out[e] = acc * scale;
+  }
+}
+
+// g_W[o][c] = sum_b g_y[b][o] x[b][c], g_b[o] = sum_b g_y[b][o]; one thread per (o, c) entry (+ one per bias) and chunk.
+// dst: [chunks][n_out * n_in + n_out] partials, or (one chunk) g_W directly followed by g_b at dst + n_out * n_in.
 __global__ void __launch_bounds__(256) affine_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g_y,
-                                                          float* __restrict__ g_W, float* __restrict__ g_b, int B, int n_in,
-                                                          int n_out) {
-  const int nW = n_out * n_in;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nW + n_out; e += gridDim.x * blockDim.x) {
+                                                          float* __restrict__ dst, int B, int n_in, int n_out) {
+  const int nW = n_out * n_in, nE = nW + n_out;
+  const int s0 = blockIdx.y * kChunk, s1 = min(B, s0 + kChunk);
+  float* out = dst + (size_t)blockIdx.y * nE;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
     float acc = 0.f;
     if (e < nW) {
       const int o = e / n_in, c = e - o * n_in;
-      for (int s = 0; s < B; ++s) acc = fmaf(g_y[(size_t)s * n_out + o], x[(size_t)s * n_in + c], acc);
-      g_W[e] = acc;
+      for (int s = s0; s < s1; ++s) acc = fmaf(g_y[(size_t)s * n_out + o], x[(size_t)s * n_in + c], acc);
     } else {
       const int o = e - nW;
-      for (int s = 0; s < B; ++s) acc += g_y[(size_t)s * n_out + o];
-      g_b[o] = acc;
+      for (int s = s0; s < s1; ++s) acc += g_y[(size_t)s * n_out + o];
     }
+    out[e] = acc;
   }
 }
 
@@ -105,27 +120,27 @@ __global__ void __launch_bounds__(128) readout_ce_sample_kernel(const float* __r
   }
 }
 
-// one CTA: loss = mean_b loss_b (b ascending), g_W = g_z^T h, g_b = sum_b g_z
+// per chunk of samples: [g_W (L x H) | g_b (L) | sum of loss_b] partials (or, one chunk, the results themselves with the
+// loss divided by B): g_W = g_z^T h, g_b = sum_b g_z, sample order ascending
 __global__ void __launch_bounds__(256) readout_ce_reduce_kernel(const float* __restrict__ h, long long h_stride,
                                                                  const float* __restrict__ g_z, const float* __restrict__ loss_b,
-                                                                 float* __restrict__ loss, float* __restrict__ g_W,
-                                                                 float* __restrict__ g_b, int B, int H, int L) {
-  for (int e = threadIdx.x; e < L * H + L; e += blockDim.x) {
+                                                                 float* __restrict__ dst, int B, int H, int L, float loss_scale) {
+  const int nE = L * H + L + 1;
+  const int s0 = blockIdx.y * kChunk, s1 = min(B, s0 + kChunk);
+  float* out = dst + (size_t)blockIdx.y * nE;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nE; e += gridDim.x * blockDim.x) {
     float acc = 0.f;
     if (e < L * H) {
       const int l = e / H, k = e - l * H;
-      for (int s = 0; s < B; ++s) acc = fmaf(g_z[(size_t)s * L + l], h[(size_t)s * h_stride + k], acc);
-      g_W[e] = acc;
-    } else {
+      for (int s = s0; s < s1; ++s) acc = fmaf(g_z[(size_t)s * L + l], h[(size_t)s * h_stride + k], acc);
+    } else if (e < L * H + L) {
       const int l = e - L * H;
-      for (int s = 0; s < B; ++s) acc += g_z[(size_t)s * L + l];
-      g_b[l] = acc;
+      for (int s = s0; s < s1; ++s) acc += g_z[(size_t)s * L + l];
+    } else {
+      for (int s = s0; s < s1; ++s) acc += loss_b[s];
+      acc *= loss_scale;
     }
-  }
-  if (threadIdx.x == 0) {
-    float acc = 0.f;
-    for (int s = 0; s < B; ++s) acc += loss_b[s];
-    *loss = acc / (float)B;
+    out[e] = acc;
   }
 }
 
@@ -254,32 +269,57 @@ int lncde_affine_fwd(void* stream, const float* x, const float* W, const float* 
   return (int)cudaGetLastError();
 }
 
-int lncde_affine_bwd(void* stream, const float* x, const float* g_y, float* g_W, float* g_b, int B, int n_in, int n_out) {
+size_t lncde_affine_bwd_workspace_bytes(int B, int n_in, int n_out) {
+  if (B < 1 || n_in < 1 || n_out < 1) return 0;
+  const size_t chunks = ((size_t)B + lncde::kChunk - 1) / lncde::kChunk;
+  return chunks > 1 ? chunks * (size_t)n_out * (n_in + 1) * sizeof(float) : 0;
+}
+
+int lncde_affine_bwd(void* stream, const float* x, const float* g_y, float* g_Wb, int B, int n_in, int n_out,
+                     void* workspace, size_t workspace_bytes) {
   using namespace lncde;
-  if (!x || !g_y || !g_W || !g_b) return LNCDE_ERR_NULL;
+  if (!x || !g_y || !g_Wb) return LNCDE_ERR_NULL;
   if (B < 1 || n_in < 1 || n_out < 1) return LNCDE_ERR_SHAPE;
-  const int total = n_out * (n_in + 1);
-  affine_bwd_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, g_y, g_W, g_b, B, n_in, n_out);
+  const int nE = n_out * (n_in + 1), chunks = (B + kChunk - 1) / kChunk;
+  if (chunks > 1 && (!workspace || workspace_bytes < lncde_affine_bwd_workspace_bytes(B, n_in, n_out))) return LNCDE_ERR_WORKSPACE;
+  cudaStream_t cs = (cudaStream_t)stream;
+  float* dst = chunks > 1 ? (float*)workspace : g_Wb;
+  affine_bwd_kernel<<<dim3((nE + 255) / 256, chunks), 256, 0, cs>>>(x, g_y, dst, B, n_in, n_out);
+  int st = (int)cudaGetLastError();
+  if (st != 0 || chunks == 1) return st;
+  chunk_reduce_kernel<<<(nE + 255) / 256, 256, 0, cs>>>(dst, g_Wb, nE, nE, chunks, 1.f);
   return (int)cudaGetLastError();
 }
 
-size_t lncde_readout_ce_workspace_bytes(int B, int L) { return B < 1 || L < 1 ? 0 : ((size_t)B * L + B) * sizeof(float); }
+size_t lncde_readout_ce_workspace_bytes(int B, int H, int L) {
+  if (B < 1 || H < 1 || L < 1) return 0;
+  const size_t chunks = ((size_t)B + lncde::kChunk - 1) / lncde::kChunk;
+  return ((size_t)B * L + B + (chunks > 1 ? chunks * ((size_t)L * H + L + 1) : 0)) * sizeof(float);
+}
 
 int lncde_readout_ce(void* stream, const float* h, long long h_stride, const float* W, const float* b,
-                     const float* labels, float* pred, float* loss, float* g_h, long long g_h_stride, float* g_W,
-                     float* g_b, int B, int H, int L, void* workspace, size_t workspace_bytes) {
+                     const float* labels, float* pred, float* g_h, long long g_h_stride, float* g_Wb_loss, int B, int H,
+                     int L, void* workspace, size_t workspace_bytes) {
   using namespace lncde;
-  if (!h || !W || !b || !labels || !loss || !g_h || !g_W || !g_b || !workspace) return LNCDE_ERR_NULL;
+  if (!h || !W || !b || !labels || !g_h || !g_Wb_loss || !workspace) return LNCDE_ERR_NULL;
   if (B < 1 || H < 1 || L < 1 || h_stride < H || g_h_stride < H) return LNCDE_ERR_SHAPE;
   if (L > kMaxLabels) return LNCDE_ERR_UNSUPPORTED;
-  if (workspace_bytes < lncde_readout_ce_workspace_bytes(B, L)) return LNCDE_ERR_WORKSPACE;
+  if (workspace_bytes < lncde_readout_ce_workspace_bytes(B, H, L)) return LNCDE_ERR_WORKSPACE;
   float* g_z = (float*)workspace;
   float* loss_b = g_z + (size_t)B * L;
   cudaStream_t cs = (cudaStream_t)stream;
   readout_ce_sample_kernel<<<(B + 3) / 4, 128, 0, cs>>>(h, h_stride, W, b, labels, pred, g_h, g_h_stride, g_z, loss_b, B, H, L);
   int st = (int)cudaGetLastError();
   if (st != 0) return st;
-  readout_ce_reduce_kernel<<<1, 256, 0, cs>>>(h, h_stride, g_z, loss_b, loss, g_W, g_b, B, H, L);
+  const int nE = L * H + L + 1, chunks = (B + kChunk - 1) / kChunk;
+  float* dst = chunks > 1 ? loss_b + B : g_Wb_loss;
+  readout_ce_reduce_kernel<<<dim3((nE + 255) / 256, chunks), 256, 0, cs>>>(h, h_stride, g_z, loss_b, dst, B, H, L,
+                                                                            chunks > 1 ? 1.f : 1.f / (float)B);
+  st = (int)cudaGetLastError();
+  if (st != 0 || chunks == 1) return st;
+  // the loss entry (last) is a plain sum of the chunk sums: scale it by 1 / B in a second, single-element pass
+  chunk_reduce_kernel<<<(nE - 1 + 255) / 256, 256, 0, cs>>>(dst, g_Wb_loss, nE - 1, nE, chunks, 1.f);
+  chunk_reduce_kernel<<<1, 32, 0, cs>>>(dst + (nE - 1), g_Wb_loss + (nE - 1), 1, nE, chunks, 1.f / (float)B);
   return (int)cudaGetLastError();
 }
 

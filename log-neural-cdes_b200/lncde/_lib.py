@@ -50,9 +50,10 @@ def _declare(lib):
         "lncde_adam_step": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, i, f]),
         "lncde_adam_step_dev": (i, [vp, vp, vp, vp, vp, i64, f, f, f, f, vp, f]),
         "lncde_affine_fwd": (i, [vp, vp, vp, vp, vp, i, i, i]),
-        "lncde_affine_bwd": (i, [vp, vp, vp, vp, vp, i, i, i]),
-        "lncde_readout_ce_workspace_bytes": (sz, [i, i]),
-        "lncde_readout_ce": (i, [vp, vp, C.c_longlong, vp, vp, vp, vp, vp, vp, C.c_longlong, vp, vp, i, i, i, vp, sz]),
+        "lncde_affine_bwd_workspace_bytes": (sz, [i, i, i]),
+        "lncde_affine_bwd": (i, [vp, vp, vp, vp, i, i, i, vp, sz]),
+        "lncde_readout_ce_workspace_bytes": (sz, [i, i, i]),
+        "lncde_readout_ce": (i, [vp, vp, C.c_longlong, vp, vp, vp, vp, vp, C.c_longlong, vp, i, i, i, vp, sz]),
         "lncde_lip2": (i, [vp, vp, vp, vp, i, vp, vp, vp, vp, f]),
         "lncde_time_mean_fwd": (i, [vp, vp, vp, i, i, i]),
         "lncde_time_mean_bwd": (i, [vp, vp, vp, i, i, i]),

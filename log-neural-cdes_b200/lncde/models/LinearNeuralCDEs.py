@@ -276,7 +276,9 @@ class LogLinearCDE:
         dev = ls.device
         p = self.params.detach()
         nA, o2 = self.n_A, self.n_A + H * (C + 1)  # [vf_A | init_layer W, b | out_layer W, b]
-        grads = torch.empty_like(p)
+        n_par = p.numel()
+        out = torch.empty(n_par + 1, device=dev)  # flat gradient, then the loss (where the read-out kernel puts it)
+        grads = out[:n_par]
         s = _lib.stream_ptr()
         y0 = torch.empty((B, H), device=dev)
         _lib.check(L.lncde_affine_fwd(s, _lib.ptr(x0c), p.data_ptr() + 4 * nA, p.data_ptr() + 4 * (nA + H * C), _lib.ptr(y0),
@@ -298,14 +300,12 @@ class LogLinearCDE:
             _lib.check(L.lncde_linear_scan_fwd(s, _lib.ptr(lie), _lib.ptr(ls), _lib.ptr(y0), _lib.ptr(ys), B, T, D, nb, bs,
                                                n_basis, _lib.ptr(ws), nbytes, flags), "lncde_linear_scan_fwd")
         hmean, g_mean = torch.empty((B, H), device=dev), torch.empty((B, H), device=dev)
-        loss = torch.empty(1, device=dev)
         _lib.check(L.lncde_time_mean_fwd(s, _lib.ptr(ys), _lib.ptr(hmean), B, T, H), "lncde_time_mean_fwd")
-        ce_nb = L.lncde_readout_ce_workspace_bytes(B, nl)
-        ce_ws = torch.empty(max(ce_nb, 1), device=dev, dtype=torch.uint8)
+        nb5 = max(L.lncde_readout_ce_workspace_bytes(B, H, nl), L.lncde_affine_bwd_workspace_bytes(B, C, H), 16)
+        ws5 = torch.empty(nb5, device=dev, dtype=torch.uint8)
         _lib.check(L.lncde_readout_ce(s, _lib.ptr(hmean), H, p.data_ptr() + 4 * o2, p.data_ptr() + 4 * (o2 + nl * H),
-                                      _lib.ptr(yc), None, _lib.ptr(loss), _lib.ptr(g_mean), H, grads.data_ptr() + 4 * o2,
-                                      grads.data_ptr() + 4 * (o2 + nl * H), B, H, nl, _lib.ptr(ce_ws), ce_nb),
-                   "lncde_readout_ce")
+                                      _lib.ptr(yc), None, _lib.ptr(g_mean), H, out.data_ptr() + 4 * o2, B, H, nl,
+                                      _lib.ptr(ws5), nb5), "lncde_readout_ce")
         g_ys = torch.empty((B, T, H), device=dev)
         _lib.check(L.lncde_time_mean_bwd(s, _lib.ptr(g_mean), _lib.ptr(g_ys), B, T, H), "lncde_time_mean_bwd")
         g_y0 = torch.empty((B, H), device=dev)
@@ -323,15 +323,15 @@ class LogLinearCDE:
                        "lncde_linear_scan_bwd")
             (g_p,) = torch.autograd.grad(lie_t, self.params, g_lie)
             grads[:nA].copy_(g_p[:nA])
-        _lib.check(L.lncde_affine_bwd(s, _lib.ptr(x0c), _lib.ptr(g_y0), grads.data_ptr() + 4 * nA,
-                                      grads.data_ptr() + 4 * (nA + H * C), B, C, H), "lncde_affine_bwd")
+        _lib.check(L.lncde_affine_bwd(s, _lib.ptr(x0c), _lib.ptr(g_y0), out.data_ptr() + 4 * nA, B, C, H, _lib.ptr(ws5), nb5),
+                   "lncde_affine_bwd")
         if self.lip2 and self.lambd != 0.0:  # lambd * mean_rows ||vf_A[row, :]||  (train.py:87-88)
             import ctypes
 
             one = lambda v: (ctypes.c_int32 * 1)(v)
-            _lib.check(L.lncde_lip2(s, _lib.ptr(p), _lib.ptr(loss), _lib.ptr(grads), 1, one(0), one(-1), one(C), one(nA // C),
-                                    float(self.lambd)), "lncde_lip2")
-        return loss[0], grads
+            _lib.check(L.lncde_lip2(s, _lib.ptr(p), out.data_ptr() + 4 * n_par, _lib.ptr(grads), 1, one(0), one(-1), one(C),
+                                    one(nA // C), float(self.lambd)), "lncde_lip2")
+        return out[n_par], grads
 
     def __call__(self, X):
         ys = self.hidden_states(X)

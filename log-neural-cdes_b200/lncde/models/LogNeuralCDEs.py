@@ -253,16 +253,17 @@ class LogNeuralCDE:
         x0c, yc, ls = x0.contiguous(), y.contiguous(), logsig.contiguous()
         o1, o2 = self.n_mlp, self.n_mlp + H * (C + 1)  # [mlp | linear1 W, b | linear2 W, b]
         W1, b1, W2, b2 = p[o1 : o1 + H * C], p[o1 + H * C : o2], p[o2 : o2 + nl * H], p[o2 + nl * H :]
-        grads = torch.empty_like(p)
+        n_par = p.numel()
+        out = torch.empty(n_par + 1, device=dev)  # flat gradient, then the loss (where the read-out kernel puts it)
+        grads = out[:n_par]
         key = (B, n_steps, dev)
         if getattr(self, "_fused_buf", (None,))[0] != key:
-            nb = L.lncde_readout_ce_workspace_bytes(B, nl)
+            nb = max(L.lncde_readout_ce_workspace_bytes(B, H, nl), L.lncde_affine_bwd_workspace_bytes(B, C, H), 16)
             # g_ys: zero except its last row, which every step overwrites - never cleared again
-            self._fused_buf = (key, torch.zeros((B, n_steps + 1, H), device=dev), torch.empty(max(nb, 1), dtype=torch.uint8,
-                                                                                                device=dev), nb)
-        _, g_ys, ce_ws, ce_nb = self._fused_buf
+            self._fused_buf = (key, torch.zeros((B, n_steps + 1, H), device=dev), torch.empty(nb, dtype=torch.uint8, device=dev),
+                               nb)
+        _, g_ys, ws5, nb5 = self._fused_buf
         y0 = torch.empty((B, H), device=dev)
-        loss = torch.empty(1, device=dev)
         s = _lib.stream_ptr()
         _lib.check(L.lncde_affine_fwd(s, _lib.ptr(x0c), _lib.ptr(W1), _lib.ptr(b1), _lib.ptr(y0), B, C, H), "lncde_affine_fwd")
         dims = (H, C, self.vf_width, self.vf_depth, self.depth)
@@ -271,12 +272,11 @@ class LogNeuralCDE:
         last = n_steps * H  # offset of y(t1) inside a sample's [n_steps + 1, H] block
         stride = (n_steps + 1) * H
         _lib.check(L.lncde_readout_ce(s, ys.data_ptr() + 4 * last, stride, _lib.ptr(W2), _lib.ptr(b2), _lib.ptr(yc), None,
-                                      _lib.ptr(loss), g_ys.data_ptr() + 4 * last, stride, _lib.ptr(grads[o2:]),
-                                      grads.data_ptr() + 4 * (o2 + nl * H), B, H, nl, _lib.ptr(ce_ws), ce_nb),
-                   "lncde_readout_ce")
+                                      g_ys.data_ptr() + 4 * last, stride, out.data_ptr() + 4 * o2, B, H, nl, _lib.ptr(ws5),
+                                      nb5), "lncde_readout_ce")
         _, g_y0 = solve_bwd(mlp, ls, rows, scale, ys, g_ys, dims, token, g_params=grads[: self.n_mlp])
-        _lib.check(L.lncde_affine_bwd(s, _lib.ptr(x0c), _lib.ptr(g_y0), grads.data_ptr() + 4 * o1,
-                                      grads.data_ptr() + 4 * (o1 + H * C), B, C, H), "lncde_affine_bwd")
+        _lib.check(L.lncde_affine_bwd(s, _lib.ptr(x0c), _lib.ptr(g_y0), out.data_ptr() + 4 * o1, B, C, H, _lib.ptr(ws5), nb5),
+                   "lncde_affine_bwd")
         if self.lip2 and self.lambd != 0.0:
             import ctypes
 
@@ -287,10 +287,10 @@ class LogNeuralCDE:
                 w_off.append(off)
                 b_off.append(off + l.out_features * l.in_features)
                 off += l.numel
-            _lib.check(L.lncde_lip2(s, _lib.ptr(p), _lib.ptr(loss), _lib.ptr(grads), len(lay), arr(w_off), arr(b_off),
-                                    arr([l.out_features for l in lay]), arr([l.in_features for l in lay]),
+            _lib.check(L.lncde_lip2(s, _lib.ptr(p), out.data_ptr() + 4 * n_par, _lib.ptr(grads), len(lay), arr(w_off),
+                                    arr(b_off), arr([l.out_features for l in lay]), arr([l.in_features for l in lay]),
                                     float(self.lambd)), "lncde_lip2")
-        return loss[0], grads
+        return out[n_par], grads
 
     def __call__(self, X):
         ys, interp = self.hidden_states(X)

@@ -230,7 +230,8 @@ def test_saved_forward_scratch_is_not_reused_after_another_solve(emulated):
 
 
 @pytest.mark.parametrize("lambd", [0.0, 0.01])
-@pytest.mark.parametrize("dims", [(3, 64, 3, 4, 2, 16, 8, 2, 3), (2, 96, 7, 12, 2, 128, 32, 2, 5), (5, 40, 2, 4, 1, 8, 8, 1, 2)])
+@pytest.mark.parametrize("dims", [(3, 64, 3, 4, 2, 16, 8, 2, 3), (2, 96, 7, 12, 2, 128, 32, 2, 5), (5, 40, 2, 4, 1, 8, 8, 1, 2),
+                                  (70, 24, 2, 4, 1, 8, 8, 1, 2)])  # the last: batch sums in three chunks of 32 samples
 def test_fused_classification_step_equals_autograd_step(emulated, dims, lambd):
     """LogNeuralCDE.fused_classification_loss (K5 kernels: initial state, read-out + cross-entropy, Lip(2), linear1 /
     linear2 gradients around K3 / K3b, no torch autograd) against the autograd formulation of train.classification_loss
