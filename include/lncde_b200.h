@@ -174,6 +174,23 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
                           const float* g_ys, float* g_lie, float* g_y0, int B, int T, int D, int nb,
                           int bs, int n_basis, void* workspace, size_t workspace_bytes, unsigned flags);
 
+/* ----------------------------------------------------------------- K2a ---
+ * Bracket matrices of the structured linear CDE and their gradient.  Replaces LogLinearCDE.log_ode,
+ * models/LinearNeuralCDEs.py:192-232 (A_[u,v] = A_v A_u - A_u A_v level by level, stacked on the last axis) and its
+ * reverse-mode derivative.
+ *   vf    [C, nb, bs, bs]          the letters' matrices (vf_A reshaped, :318)
+ *   pairs [n_basis][2]  HOST int32: HallSet(C, depth).data[1:] - (left, right) element numbers, 1-based, left == 0
+ *                       for the letters (data_dir/hall_set.py:60-119; the order roughpy's lie_basis enumerates, :111-116)
+ *   lie   [nb, bs, bs, n_basis]    what lncde_linear_scan_fwd takes
+ * n_basis <= 160, degree <= 6.  workspace: lncde_lie_brackets_workspace_bytes bytes; the forward call leaves every A_k
+ * there ([n_basis, nb, bs, bs]) and the backward call reads it (`workspace`) next to a scratch of the same size
+ * (`workspace_g`).  g_vf [C, nb, bs, bs] is fully overwritten; deterministic (gather per parent, no atomics).       */
+size_t lncde_lie_brackets_workspace_bytes(int n_basis, int nb, int bs);
+int lncde_lie_brackets_fwd(void* stream, const float* vf, const int32_t* pairs, float* lie, int C, int n_basis, int nb,
+                           int bs, void* workspace, size_t workspace_bytes);
+int lncde_lie_brackets_bwd(void* stream, const float* g_lie, const int32_t* pairs, float* g_vf, int C, int n_basis, int nb,
+                           int bs, const void* workspace, void* workspace_g, size_t workspace_bytes);
+
 /* ----------------------------------------------------------------- K2d ---
  * Fused diagonal LNCDE (block size 1): f_t = 1 + sum_c logsig[t, 1 + c] vf_A[c, :], y_t = f_t * y_{t-1},
  * t = 1..T-1, WITHOUT materialising the flows (models/LinearNeuralCDEs.py:302-316 + scanner :355-386).

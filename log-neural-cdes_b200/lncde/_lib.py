@@ -40,6 +40,9 @@ def _declare(lib):
         "lncde_linear_scan_workspace_bytes": (sz, [i, i, i, i, i]),
         "lncde_linear_scan_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz, u]),
         "lncde_linear_scan_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, vp, sz, u]),
+        "lncde_lie_brackets_workspace_bytes": (sz, [i, i, i]),
+        "lncde_lie_brackets_fwd": (i, [vp, vp, vp, vp, i, i, i, i, vp, sz]),
+        "lncde_lie_brackets_bwd": (i, [vp, vp, vp, vp, i, i, i, i, vp, vp, sz]),
         "lncde_dlncde_bwd_workspace_bytes": (sz, [i, i, i]),
         "lncde_dlncde_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i]),
         "lncde_dlncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]),

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
 
 from .. import _lib
@@ -91,6 +92,40 @@ class _DiagScan(torch.autograd.Function):
         return g_A, None, g_y0
 
 
+class _LieBrackets(torch.autograd.Function):
+    """log_ode as kernels (K2a, lncde_lie_brackets_*): vfs [C, nb, bs, bs] -> lie [nb, bs, bs, n_basis]."""
+
+    @staticmethod
+    def forward(ctx, vfs, pairs):
+        _lib.require_cuda(vfs)
+        L = _lib.lib()
+        C, nb, bs, _ = vfs.shape
+        n_basis = pairs.shape[0]
+        vfs = vfs.contiguous()
+        nbytes = L.lncde_lie_brackets_workspace_bytes(n_basis, nb, bs)
+        ws = torch.empty(nbytes, device=vfs.device, dtype=torch.uint8)  # every A_k: kept for the backward pass
+        lie = torch.empty((nb, bs, bs, n_basis), device=vfs.device, dtype=torch.float32)
+        st = L.lncde_lie_brackets_fwd(_lib.stream_ptr(), _lib.ptr(vfs), pairs.ctypes.data, _lib.ptr(lie), C, n_basis, nb, bs,
+                                      _lib.ptr(ws), nbytes)
+        _lib.check(st, "lncde_lie_brackets_fwd")
+        ctx.save_for_backward(ws)
+        ctx.meta = (pairs, C, n_basis, nb, bs, nbytes)
+        return lie
+
+    @staticmethod
+    def backward(ctx, g_lie):
+        (ws,) = ctx.saved_tensors
+        pairs, C, n_basis, nb, bs, nbytes = ctx.meta
+        L = _lib.lib()
+        g_lie = g_lie.contiguous()
+        wsg = torch.empty(nbytes, device=g_lie.device, dtype=torch.uint8)
+        g_vf = torch.empty((C, nb, bs, bs), device=g_lie.device, dtype=torch.float32)
+        st = L.lncde_lie_brackets_bwd(_lib.stream_ptr(), _lib.ptr(g_lie), pairs.ctypes.data, _lib.ptr(g_vf), C, n_basis, nb, bs,
+                                      _lib.ptr(ws), _lib.ptr(wsg), nbytes)
+        _lib.check(st, "lncde_lie_brackets_bwd")
+        return g_vf, None
+
+
 def _diag_scan(vf_At, logsigs, y0):
     """Diagonal scan: the fused K2d kernels (no flows in HBM; measured on B200: as fast as flow build + scan at B = 32,
     2.2x faster at B = 2048), or flow build + scan under ``kernel_flags("generic")`` / for more than 8 channels."""
@@ -125,6 +160,7 @@ class LogLinearCDE:
         self.basis_list = hs.basis_list()  # what roughpy's lie_basis enumerates (:111-116)
         self._basis_pairs = hs.data
         self._levels = None
+        self._pairs_np = None
         C, H, bs, nb = self.data_dim, self.hidden_dim, self.block_size, self.num_blocks
         gen = torch.Generator().manual_seed(int(key))
         randn = lambda n: torch.randn(n, generator=gen)
@@ -214,6 +250,10 @@ class LogLinearCDE:
         """vfs [C, nb, bs, bs] -> bracket matrices [nb, bs, bs, n_basis] (:192-232), batched over blocks.
         Level by level, every bracket of a level in ONE batched matmul pair:
         A_[u,v] = A_v A_u - A_u A_v  (:225-227)."""
+        if not (_lib.call_flags() & _lib.FLAG_GENERIC) and len(self._basis_pairs) - 1 <= 160:
+            if self._pairs_np is None:  # HallSet.data[1:], 1-based (left, right), left = 0 for the letters
+                self._pairs_np = np.ascontiguousarray(np.asarray(self._basis_pairs[1:], np.int32).reshape(-1, 2))
+            return _LieBrackets.apply(vfs, self._pairs_np)
         if self._levels is None:
             n = len(self._basis_pairs)
             deg = [0] * n
@@ -261,8 +301,8 @@ class LogLinearCDE:
 
     def fused_classification_loss(self, X, y):
         """One classification train step with the kernels of K2 / K5 only around the scans (initial state, time mean,
-        read-out + cross-entropy, Lip(2) term, init_layer / out_layer gradients) - torch autograd is left with
-        `log_ode` alone (parameters -> bracket matrices; nothing for the diagonal model).  Plain D / BD / DE structures;
+        read-out + cross-entropy, Lip(2) term, init_layer / out_layer gradients, bracket matrices K2a) - no torch
+        autograd on the step (beyond 160 basis elements `log_ode` falls back to it).  Plain D / BD / DE structures;
         the other SLiCE parameterisations return None and take the autograd formulation."""
         if self.diagonal_dense or self._sparse_idx is not None or self.rank > 0 or self.walsh_hadamard:
             return None
@@ -291,10 +331,20 @@ class LogLinearCDE:
             _lib.check(L.lncde_dlncde_fwd(s, _lib.ptr(vf_At), _lib.ptr(ls), _lib.ptr(y0), _lib.ptr(ys), B, T, D, H, C),
                        "lncde_dlncde_fwd")
         else:
-            with torch.enable_grad():
-                lie_t = self.log_ode(self.vf_A.view(C, nb, bs, bs))  # the one piece torch autograd still differentiates
-            lie = lie_t.detach().contiguous()
-            n_basis = lie.shape[-1]
+            n_basis = len(self._basis_pairs) - 1
+            br_kernels = n_basis <= 160
+            if br_kernels:  # K2a: bracket matrices straight from the flat parameters, every A_k kept for the gradient
+                if self._pairs_np is None:
+                    self._pairs_np = np.ascontiguousarray(np.asarray(self._basis_pairs[1:], np.int32).reshape(-1, 2))
+                br_nb = L.lncde_lie_brackets_workspace_bytes(n_basis, nb, bs)
+                br_ws = torch.empty(2 * br_nb, device=dev, dtype=torch.uint8)
+                lie = torch.empty((nb, bs, bs, n_basis), device=dev)
+                _lib.check(L.lncde_lie_brackets_fwd(s, _lib.ptr(p), self._pairs_np.ctypes.data, _lib.ptr(lie), C, n_basis, nb, bs,
+                                                    _lib.ptr(br_ws), br_nb), "lncde_lie_brackets_fwd")
+            else:
+                with torch.enable_grad():
+                    lie_t = self.log_ode(self.vf_A.view(C, nb, bs, bs))
+                lie = lie_t.detach().contiguous()
             nbytes = L.lncde_linear_scan_workspace_bytes(B, T, nb, bs, n_basis)
             ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             _lib.check(L.lncde_linear_scan_fwd(s, _lib.ptr(lie), _lib.ptr(ls), _lib.ptr(y0), _lib.ptr(ys), B, T, D, nb, bs,
@@ -321,8 +371,12 @@ class LogLinearCDE:
             _lib.check(L.lncde_linear_scan_bwd(s, _lib.ptr(lie), _lib.ptr(ls), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_lie),
                                                _lib.ptr(g_y0), B, T, D, nb, bs, n_basis, _lib.ptr(ws), nbytes, flags),
                        "lncde_linear_scan_bwd")
-            (g_p,) = torch.autograd.grad(lie_t, self.params, g_lie)
-            grads[:nA].copy_(g_p[:nA])
+            if br_kernels:
+                _lib.check(L.lncde_lie_brackets_bwd(s, _lib.ptr(g_lie), self._pairs_np.ctypes.data, _lib.ptr(grads), C, n_basis, nb,
+                                                    bs, _lib.ptr(br_ws), br_ws.data_ptr() + br_nb, br_nb), "lncde_lie_brackets_bwd")
+            else:
+                (g_p,) = torch.autograd.grad(lie_t, self.params, g_lie)
+                grads[:nA].copy_(g_p[:nA])
         _lib.check(L.lncde_affine_bwd(s, _lib.ptr(x0c), _lib.ptr(g_y0), out.data_ptr() + 4 * nA, B, C, H, _lib.ptr(ws5), nb5),
                    "lncde_affine_bwd")
         if self.lip2 and self.lambd != 0.0:  # lambd * mean_rows ||vf_A[row, :]||  (train.py:87-88)

@@ -135,3 +135,24 @@ def test_fused_lncde_classification_step_equals_autograd_step(built_lib, name, b
     g0, g1 = g0.cpu().numpy(), g1.cpu().numpy()
     for a, b in ((0, nA), (nA, nA + H * C), (nA + H * C, o2), (o2, o2 + nl * H), (o2 + nl * H, g0.size)):
         assert rel_err(g1[a:b], g0[a:b]) < TOL, (name, a, b)
+
+
+@pytest.mark.parametrize("C,depth,nb,bs", [(7, 2, 1, 128), (7, 3, 1, 128), (7, 2, 32, 4), (6, 3, 8, 16), (3, 4, 1, 64)])
+def test_lie_bracket_kernels_equal_torch_log_ode(built_lib, C, depth, nb, bs):
+    """K2a behind LogLinearCDE.log_ode (values and gradient) against the batched torch.matmul formulation
+    (`kernel_flags("generic")`) at the dense / block-diagonal EigenWorms shapes, depth 2 - 4."""
+    from lncde import _lib
+    from lncde.models.generate_model import create_model
+
+    model, _ = create_model("bd_linear_ncde", C, 1, depth, None, 2, nb * bs, block_size=bs, lambd=0.0, key=2)
+    g = torch.Generator().manual_seed(C * 10 + depth)
+    vfs = (torch.randn(C, nb, bs, bs, generator=g) / bs ** 0.5).cuda().requires_grad_(True)
+    with _lib.kernel_flags("generic"):
+        want = model.log_ode(vfs)
+    got = model.log_ode(vfs)
+    assert got.shape == want.shape
+    assert rel_err(got.detach().cpu().numpy(), want.detach().cpu().numpy()) < 2e-6
+    w = torch.randn(want.shape, generator=g).cuda()
+    (g_want,) = torch.autograd.grad(want, vfs, w)
+    (g_got,) = torch.autograd.grad(got, vfs, w)
+    assert rel_err(g_got.cpu().numpy(), g_want.cpu().numpy()) < TOL

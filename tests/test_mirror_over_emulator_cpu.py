@@ -288,3 +288,26 @@ def test_fused_lncde_classification_step_equals_autograd_step(emulated, name, bs
     nA, o2 = model.n_A, model.n_A + H * (C_ + 1)
     for a, b in ((0, nA), (nA, nA + H * C_), (nA + H * C_, o2), (o2, o2 + nl * H), (o2 + nl * H, g0.numel())):
         assert rel_err(g1[a:b].numpy(), g0[a:b].numpy()) < 1e-5, (name, a, b)
+
+
+@pytest.mark.parametrize("C_,depth,nb,bs", [(3, 2, 2, 4), (3, 3, 1, 8), (2, 4, 3, 5), (7, 2, 1, 40), (2, 3, 1, 33)])
+def test_lie_bracket_kernels_equal_torch_log_ode(emulated, C_, depth, nb, bs):
+    """K2a (lncde_lie_brackets_fwd / bwd) behind LogLinearCDE.log_ode against the batched-matmul formulation it replaces
+    (`kernel_flags("generic")`) and torch autograd through it: all degrees up to 4, several blocks, block sizes below,
+    at and above the 32 x 32 tile, parents with children on several levels (gather order of the reverse pass)."""
+    from lncde import _lib
+    from lncde.models.generate_model import create_model
+
+    H = nb * bs
+    model, _ = create_model("bd_linear_ncde", C_, 1, depth, None, 2, H, block_size=bs, lambd=0.0, key=2, device="cpu")
+    g = torch.Generator().manual_seed(C_ * 10 + depth)
+    vfs = (torch.randn(C_, nb, bs, bs, generator=g) / bs ** 0.5).requires_grad_(True)
+    with _lib.kernel_flags("generic"):
+        want = model.log_ode(vfs)
+    got = model.log_ode(vfs)
+    assert got.shape == want.shape == (nb, bs, bs, len(model._basis_pairs) - 1)
+    assert rel_err(got.detach().numpy(), want.detach().numpy()) < 2e-6
+    w = torch.randn(want.shape, generator=g)
+    (g_want,) = torch.autograd.grad(want, vfs, w)
+    (g_got,) = torch.autograd.grad(got, vfs, w)
+    assert rel_err(g_got.numpy(), g_want.numpy()) < 5e-6
