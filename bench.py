@@ -362,17 +362,27 @@ def run_ours(args):
 
 
 def own_launches_per_step(model_name, wl):
-    """Kernels of liblncde_b200.so launched by one train step (counted from the host code of csrc/ for the kernels the
-    library picks by default; confirmed for the default workload by the ncu launch list under profiles/)."""
+    """Kernels of liblncde_b200.so launched by one train step (counted from the host code of csrc/ and the kernel-only
+    step of the host mirrors, for the kernels the library picks by default; the ncu launch lists under profiles/ show the
+    same kernels).  Since round 2 a classification step launches nothing else (no torch / cuBLAS kernels)."""
     adam = 2                                     # adam_dev_kernel + the step-counter bump
-    if model_name in ("log_ncde", "nrde"):
-        return 1 + 1 + 1 + 3 + 1 + adam          # K1, solve fwd, adjoint sweep, 3 gradient-GEMM groups, gradient reduce
+    lip = 1 if wl.get("lambd", 0.0) else 0       # lip2_kernel
+    k5 = 1 + 2 + 1 + lip                         # affine_fwd, read-out (per-sample + reduce), affine_bwd, Lip(2)
+    if model_name == "nrde":                     # autograd glue around the kernels: K1, solve, sweep, 3 GEMM groups, reduce
+        return 1 + 1 + 1 + 3 + 1 + adam
+    if model_name == "log_ncde":
+        if not wl.get("classification", True):   # regression read-out stays in torch
+            return 1 + 1 + 1 + 3 + 1 + adam
+        return 1 + k5 + 1 + (1 + 3 + 1) + adam   # K1, K5, solve, sweep + 3 gradient-GEMM groups + gradient reduce, Adam
+    mean = 2                                     # time_mean_fwd / _bwd
     if model_name == "diagonal_linear_ncde":
-        return 1 + 1 + 2 + adam                  # K1, dlncde_fwd, dlncde_bwd + its reduce
+        return 1 + k5 + mean + 1 + 2 + adam      # dlncde_fwd, dlncde_bwd + its reduce
+    brackets = 2 * (1 + (wl.get("depth", 2) - 1))  # K2a forward and reverse: one launch per degree >= 2 + the transpose
     if model_name == "dense_linear_ncde":
         # two operand packs + tcgen05 flow build + scan | lam-only reverse scan, triple-product gradient, split-K reduce
-        return 1 + (3 + 1) + 3 + adam
-    return 1 + (1 + 3) + (4 + 2) + adam          # time-parallel scans: products / boundary / apply | 4 + GEMM, reduce
+        return 1 + k5 + mean + brackets + (3 + 1) + 3 + adam
+    # block-diagonal: flow build + time-parallel scans (products / boundary / apply | products / local / boundary / local) + GEMM, reduce
+    return 1 + k5 + mean + brackets + (1 + 3) + (4 + 2) + adam
 
 
 def extra_measurements(args, model, opt, x_dev, lab_dev, step, pk, pk_kind, ms_per_step):

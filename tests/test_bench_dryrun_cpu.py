@@ -26,7 +26,7 @@ def test_bench_json_contract_over_emulator():
     assert out["metric"] == "train samples/sec EigenWorms Log-NCDE" and out["unit"] == "samples/s"
     assert out["scaling"] == "weak" and out["dtype"] == "f32" and out["data"] == "synthetic"
     assert "workload" in out["config"] and "model" not in out["config"]
-    assert out["gpu_launches"] == 9 * out["steps"]
+    assert out["gpu_launches"] == 14 * out["steps"]  # K1, K5 (5), solve, sweep + 3 GEMM groups + reduce, Adam (2)
     # value = whole-job samples over the timed region
     assert abs(out["value"] - out["config"]["global_batch"] / (out["ms_per_step"] * 1e-3)) < 1e-6 * out["value"]
     e2e = out["e2e"]
