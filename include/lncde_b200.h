@@ -46,6 +46,8 @@ extern "C" {
                                       tcgen05 - the path of block sizes that are not multiples of 128 */
 #define LNCDE_FLAG_K3_V3 32u      /* Log-NCDE, H = 128 / width 32 model: six-barrier stage kernels (logncde_v3.cuh); measured
                                      slower than the default on B200, kept for its clock-trace instrumentation */
+#define LNCDE_FLAG_K2_ONE_CTA 64u /* dense LNCDE: one CTA per series for the two sweeps instead of a thread-block cluster
+                                     per series (linear_cluster.cuh) - the path of batches that fill the SMs anyway */
 
 const char* lncde_version(void);
 /* Human-readable text for a status returned by any entry point. */

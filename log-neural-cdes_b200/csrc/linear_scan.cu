@@ -18,6 +18,7 @@
 #include <cstdint>
 
 #include "lncde_b200.h"
+#include "linear_cluster.cuh"
 #include "linear_de.cuh"
 #include "linear_pscan.cuh"
 #include "outer_gemm.cuh"
@@ -610,6 +611,11 @@ static int dense_level(unsigned flags, int N, int bs) {
   return 2;
 }
 
+// the sweeps of the dense model run on thread-block clusters (linear_cluster.cuh) unless the caller asks for one CTA per series
+static bool cluster_sweeps(unsigned flags, int bs) {
+  return !(flags & (LNCDE_FLAG_GENERIC | LNCDE_FLAG_K2_ONE_CTA)) && bs >= 64;
+}
+
 }  // namespace lncde
 
 extern "C" {
@@ -670,6 +676,7 @@ int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, c
   float* pscan_scratch = F + pscan_scratch_offset(B, T, nb, bs, n_basis);
   if (pscan_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs, pscan_scratch, flags)) {
   } else if (scan_warp_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
+  } else if (cluster_sweeps(flags, bs) && scan_cluster_dispatch(false, cs, F, y0, ys, nullptr, B, T, H, bs)) {
   } else if (scan_tma_dispatch(false, cs, F, y0, ys, nullptr, nullptr, B, T, H, bs)) {
   } else if (bs <= 16) {
     int threads = H < 32 ? 32 : (H > 1024 ? 1024 : ((H + 31) & ~31));
@@ -701,7 +708,8 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
     const size_t part_n = ((size_t)N * n_basis * kScanKsplit + 3) & ~(size_t)3;
     float* part = F + flows;
     float* lam = part + part_n;
-    if (scan_bwd_lam_dispatch(cs, F, g_ys, lam, g_y0, B, T, H, bs)) {
+    if ((cluster_sweeps(flags, bs) && scan_cluster_dispatch(true, cs, F, g_ys, lam, g_y0, B, T, H, bs)) ||
+        scan_bwd_lam_dispatch(cs, F, g_ys, lam, g_y0, B, T, H, bs)) {
       st = (int)cudaGetLastError();
       if (st != 0) return st;
       if (!dlie_triple_dispatch(cs, lam, ys, logsig, part, B, T, D, H, bs, n_basis, kScanKsplit, de_v2 >= 2))

@@ -107,7 +107,7 @@ struct Smem {
 };
 
 struct Regs {
-  float Wt[8][8];  // last-layer tile: rows r0..r0+7, inputs cg*8..cg*8+7
+  float2 Wt[8][4];  // last-layer tile: rows r0..r0+7, inputs cg*8..cg*8+7 as (even, odd) pairs for FFMA2
   float b3[2];     // bias of the two rows this lane finishes
   float w1[8];     // W1[lane][warp*8 .. +7]
   float w2[4];     // W2[lane][(warp&7)*4 .. +3]
@@ -133,20 +133,32 @@ __device__ __forceinline__ void load_regs(Regs& R, const float* __restrict__ par
 #pragma unroll
     for (int e = 0; e < 8; ++e)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) R.Wt[e][k] = params[d.w_off[2] + (size_t)(r0 + e) * W + cg * 8 + k];
+      for (int q = 0; q < 4; ++q)
+        R.Wt[e][q] = *reinterpret_cast<const float2*>(params + d.w_off[2] + (size_t)(r0 + e) * W + cg * 8 + 2 * q);
     const int row0 = lane_row0(tid);
     R.b3[0] = params[d.b_off[2] + row0];
     R.b3[1] = params[d.b_off[2] + row0 + 1];
   }
 }
 
+// The 8x8 register tile runs on packed fp32 pairs (FFMA2: two fused multiply-adds per issue slot, each half rounded
+// like a scalar FFMA).  tile_rows pairs the inputs (even, odd) and adds the two halves at the end; tile_cols pairs
+// the outputs and needs the input duplicated into both halves.
 __device__ __forceinline__ void tile_rows(const Regs& R, const float* __restrict__ x8, int lane, float& r_a,
                                           float& r_b) {
   const float4 x0 = *reinterpret_cast<const float4*>(x8);
   const float4 x1 = *reinterpret_cast<const float4*>(x8 + 4);
+  const float2 xa = make_float2(x0.x, x0.y), xb = make_float2(x0.z, x0.w);
+  const float2 xc = make_float2(x1.x, x1.y), xd = make_float2(x1.z, x1.w);
   float v[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) v[e] = dot8(R.Wt[e], x0, x1);
+  for (int e = 0; e < 8; ++e) {
+    float2 s = __fmul2_rn(R.Wt[e][0], xa);
+    s = __ffma2_rn(R.Wt[e][1], xb, s);
+    s = __ffma2_rn(R.Wt[e][2], xc, s);
+    s = __ffma2_rn(R.Wt[e][3], xd, s);
+    v[e] = s.x + s.y;
+  }
   xstep<4>(v, lane & 1, 1);
   xstep<2>(v, lane & 2, 2);
   r_a = v[0];
@@ -156,18 +168,21 @@ __device__ __forceinline__ void tile_rows(const Regs& R, const float* __restrict
 __device__ __forceinline__ float tile_cols(const Regs& R, const float* __restrict__ x8, int lane) {
   const float4 x0 = *reinterpret_cast<const float4*>(x8);
   const float4 x1 = *reinterpret_cast<const float4*>(x8 + 4);
+  const float xe[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  float2 s[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) s[q] = __fmul2_rn(R.Wt[0][q], make_float2(xe[0], xe[0]));
+#pragma unroll
+  for (int e = 1; e < 8; ++e) {
+    const float2 xx = make_float2(xe[e], xe[e]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s[q] = __ffma2_rn(R.Wt[e][q], xx, s[q]);
+  }
   float v[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float s = R.Wt[0][k] * x0.x;
-    s = fmaf(R.Wt[1][k], x0.y, s);
-    s = fmaf(R.Wt[2][k], x0.z, s);
-    s = fmaf(R.Wt[3][k], x0.w, s);
-    s = fmaf(R.Wt[4][k], x1.x, s);
-    s = fmaf(R.Wt[5][k], x1.y, s);
-    s = fmaf(R.Wt[6][k], x1.z, s);
-    s = fmaf(R.Wt[7][k], x1.w, s);
-    v[k] = s;
+  for (int q = 0; q < 4; ++q) {
+    v[2 * q] = s[q].x;
+    v[2 * q + 1] = s[q].y;
   }
   xstep<4>(v, lane & 4, 4);
   xstep<2>(v, lane & 8, 8);

@@ -89,8 +89,9 @@ def lib():
 
 
 # ---- per-call kernel flags (include/lncde_b200.h) --------------------------------------------------------------
-FLAG_COMPAT, FLAG_SAVED_FWD, FLAG_K1_TMA, FLAG_GENERIC, FLAG_K2_MMA_SYNC, FLAG_K3_V3 = 1, 2, 4, 8, 16, 32
-_VARIANT_BITS = {"k1_tma": FLAG_K1_TMA, "generic": FLAG_GENERIC, "k2_mma_sync": FLAG_K2_MMA_SYNC, "k3_v3": FLAG_K3_V3}
+FLAG_COMPAT, FLAG_SAVED_FWD, FLAG_K1_TMA, FLAG_GENERIC, FLAG_K2_MMA_SYNC, FLAG_K3_V3, FLAG_K2_ONE_CTA = 1, 2, 4, 8, 16, 32, 64
+_VARIANT_BITS = {"k1_tma": FLAG_K1_TMA, "generic": FLAG_GENERIC, "k2_mma_sync": FLAG_K2_MMA_SYNC, "k3_v3": FLAG_K3_V3,
+                 "k2_one_cta": FLAG_K2_ONE_CTA}
 _call_flags = threading.local()
 
 
@@ -102,7 +103,7 @@ def call_flags() -> int:
 
 class kernel_flags:
     """``with kernel_flags("generic"):`` - run the enclosed calls on the named kernel variants (tests, benchmarks):
-    "generic" (baseline kernels), "k1_tma", "k2_mma_sync", "k3_v3"; see the LNCDE_FLAG_* comments in the header."""
+    "generic" (baseline kernels), "k1_tma", "k2_mma_sync", "k2_one_cta", "k3_v3"; see the LNCDE_FLAG_* comments in the header."""
 
     def __init__(self, *names):
         self.bits = 0

@@ -229,7 +229,7 @@ def k2_timing(reps=10):
     return res
 
 
-_DE_VARIANTS = {"mma_sync": ("k2_mma_sync",), "tcgen05": ()}
+_DE_VARIANTS = {"mma_sync": ("k2_mma_sync",), "one_cta": ("k2_one_cta",), "tcgen05": ()}
 
 
 def k2de_parity():

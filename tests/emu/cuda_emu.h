@@ -78,6 +78,7 @@ void async_store_wait();
 void cp_async(void* smem_dst, const void* gsrc, unsigned bytes);
 void cp_async_wait();
 bool in_dyn_smem(const void* p, size_t bytes);
+void count_peer_store();
 
 template <class T>
 inline uint64_t pack(T v) {
@@ -167,6 +168,10 @@ inline float __logf(float x) { return ::logf(x); }
 inline float __fmaf_rn(float a, float b, float c) { return ::fmaf(a, b, c); }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
+// packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100): each half rounds like the scalar instruction
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(::fmaf(a.x, b.x, c.x), ::fmaf(a.y, b.y, c.y)); }
+inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 inline float __int_as_float(int i) { return emu::unpack<float>(emu::pack(i)); }
 inline int __float_as_int(float f) { return emu::unpack<int>(emu::pack(f)); }
 inline float __uint_as_float(unsigned u) { return emu::unpack<float>(emu::pack(u)); }

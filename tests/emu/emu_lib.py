@@ -48,6 +48,7 @@ def lib():
         _lib.lncde_nrde_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, vp, sz]
         _lib.emu_set_schedule.argtypes = [i, u, i]
         _lib.emu_bulk_copies.restype = C.c_long
+        _lib.emu_peer_stores.restype = C.c_long
         _lib.emu_guarded_alloc.restype = C.c_void_p
         _lib.emu_guarded_alloc.argtypes = [C.c_size_t, C.c_int, C.c_int]
     return _lib
@@ -60,8 +61,9 @@ def lib():
 #   "k3_stream" 1: streamed global-weight mat-vecs of the generic Log-NCDE kernels (the library default)
 #   "k2_pscan"  1: time-parallel D / BD scans (the library default for block sizes <= 8)
 #   "k2_de_v2"  2: dense model on mma.sync tensor cores (LNCDE_FLAG_K2_MMA_SYNC), 3: tcgen05 flow build (library default)
-FLAG_COMPAT, FLAG_SAVED_FWD, FLAG_K1_TMA, FLAG_GENERIC, FLAG_K2_MMA_SYNC, FLAG_K3_V3 = 1, 2, 4, 8, 16, 32
-_sel = {"k3_v3": 0, "k3_stream": 0, "k2_pscan": 0, "k2_de_v2": 0}
+#   "k2_cluster" 1: sweeps of the dense model on the cluster kernels (library default; a cluster of one CTA here)
+FLAG_COMPAT, FLAG_SAVED_FWD, FLAG_K1_TMA, FLAG_GENERIC, FLAG_K2_MMA_SYNC, FLAG_K3_V3, FLAG_K2_ONE_CTA = 1, 2, 4, 8, 16, 32, 64
+_sel = {"k3_v3": 0, "k3_stream": 0, "k2_pscan": 0, "k2_de_v2": 0, "k2_cluster": 0}
 
 
 def set_tuning(key, value):
@@ -75,7 +77,7 @@ def _k3_flags():
 
 def _k2_flags(bs):
     if bs >= 64:
-        return {0: FLAG_GENERIC, 2: FLAG_K2_MMA_SYNC, 3: 0}[_sel["k2_de_v2"]]
+        return {0: FLAG_GENERIC, 2: FLAG_K2_MMA_SYNC, 3: 0}[_sel["k2_de_v2"]] | (0 if _sel["k2_cluster"] else FLAG_K2_ONE_CTA)
     return 0 if _sel["k2_pscan"] else FLAG_GENERIC
 
 
@@ -93,6 +95,11 @@ def set_async_mode(lazy: bool):
 def bulk_copies():
     """Bulk (TMA) copies issued by the emulated kernels since the last call."""
     return lib().emu_bulk_copies()
+
+
+def peer_stores():
+    """One-sided cluster stores (st.async) issued by the emulated kernels since the last call."""
+    return lib().emu_peer_stores()
 
 
 def guarded(shape, dtype=np.float32, tight_end=True, start_mod16=0):

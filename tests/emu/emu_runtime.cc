@@ -383,6 +383,8 @@ void cp_async_wait() {
   f.cps.clear();
 }
 long g_bulk_copies = 0;
+long g_peer_stores = 0;
+void count_peer_store() { ++g_peer_stores; }
 void check_bulk(const void* smem_ptr, const void* gptr, unsigned bytes, const char* what) {
   ++g_bulk_copies;
   if (bytes == 0 || (bytes & 15u)) die((std::string(what) + ": size is not a positive multiple of 16 bytes").c_str());
@@ -552,6 +554,12 @@ void emu_selftest_race(float* out, int n, int with_barrier) {
     out[t] = sm[(t + 1) % n];
   };
   emu::launch((const void*)&emu_selftest_race, dim3(1), dim3(n), (size_t)n * sizeof(float), body);
+}
+// test hook: number of one-sided cluster stores (st.async) issued since the last call
+long emu_peer_stores(void) {
+  const long n = emu::g_peer_stores;
+  emu::g_peer_stores = 0;
+  return n;
 }
 // test hook: number of bulk (TMA) copies issued since the last call
 long emu_bulk_copies(void) {

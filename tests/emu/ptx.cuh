@@ -36,6 +36,21 @@ inline void tma_store_commit() {}
 inline void tma_store_wait_read() { emu::async_store_wait(); }
 inline void fence_async_proxy() {}
 
+// clusters: the emulator runs a cluster of ONE CTA (csrc/linear_cluster.cuh launches CS = 1 under LNCDE_EMU), so the only
+// peer is the CTA itself; the byte counting on the mbarrier is the real protocol
+inline unsigned cluster_ctarank() { return 0; }
+inline void cluster_sync_all() { emu::sync_threads(); }
+inline void st_async_f32(float* dst, float v, unsigned long long* bar, unsigned rank) {
+  if (rank != 0 || !emu::in_dyn_smem(dst, 4)) {
+    std::fprintf(stderr, "cuda-emu: st.async to a peer that does not exist / outside shared memory\n");
+    std::abort();
+  }
+  *dst = v;
+  emu::count_peer_store();
+  emu::mbar_complete_tx(bar, 4);
+}
+inline void mbar_wait_cluster(unsigned long long* bar, unsigned parity) { emu::mbar_wait(bar, parity); }
+
 // TF32: keep 10 mantissa bits, round to nearest with ties away from zero (cvt.rna)
 inline uint32_t cvt_tf32(float v) {
   uint32_t u;

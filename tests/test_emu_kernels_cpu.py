@@ -301,6 +301,34 @@ def test_emu_linear_scan_forward_and_adjoint(nb, bs, T, n_basis):
     assert rel_err(gl_e, lie_t.grad.numpy()) < 5 * TOL
 
 
+@pytest.mark.parametrize("bs,T,B", [(64, 1, 1), (64, 2, 2), (64, 3, 1), (64, 27, 2), (128, 4, 1), (128, 11, 2)])
+def test_emu_dense_cluster_sweeps(bs, T, B):
+    """linear_cluster.cuh: the forward and the lam-only reverse sweep of the dense model with the series spread over a
+    thread-block cluster.  The emulator runs a cluster of ONE CTA: row slicing, the ring of flow stages (deeper than
+    T, equal to, and wrapped several times), the st.async + byte-counted mbarrier exchange with its arming order and
+    parities, and the exit protocol are the code under test; the peer addressing (mapa) is covered on the GPU."""
+    rng = np.random.default_rng(5)
+    nb, n_basis = 1, 6
+    lie = rng.normal(size=(nb, bs, bs, n_basis)) * (0.5 / np.sqrt(bs))
+    ls = rng.normal(size=(B, T, n_basis + 1)) * 0.2
+    y0, g_ys = rng.normal(size=(B, bs)), rng.normal(size=(B, T, bs))
+    ys0, gl0, gy0 = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
+    E.set_tuning("k2_de_v2", 2)
+    try:
+        ys1, gl1, gy1 = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
+        E.set_tuning("k2_cluster", 1)
+        E.peer_stores()
+        ys2, gl2, gy2 = E.linear_scan(lie, ls, y0, nb, bs, g_ys)
+        sent = E.peer_stores()
+    finally:
+        E.set_tuning("k2_de_v2", 0)
+        E.set_tuning("k2_cluster", 0)
+    assert sent == B * (T - 1) * (bs + 256)  # forward: one store per row and step; reverse: one per thread and step
+    assert rel_err(ys2, ys0) < 2e-6 and rel_err(gy2, gy0) < 2e-6 and rel_err(gl2, gl0) < 1e-5
+    assert np.array_equal(ys2, ys1)  # same row arithmetic as the one-CTA sweep
+    assert rel_err(gy2, gy1) < 1e-6
+
+
 @pytest.mark.parametrize("level", [2, 3])
 @pytest.mark.parametrize("nb,bs,T,n_basis,B", [(1, 64, 9, 6, 2), (1, 128, 7, 28, 2), (2, 64, 5, 21, 3), (1, 64, 2, 3, 1),
                                                (1, 68, 6, 10, 2), (1, 128, 12, 36, 1), (1, 64, 5, 40, 2), (1, 72, 4, 70, 1)])

@@ -139,6 +139,24 @@ def test_linear_scan_kernels_schedule_independent(nb, bs, T, n_basis, level):
         E.set_tuning("k2_de_v2", 0)
 
 
+@pytest.mark.parametrize("bs,T", [(64, 12), (128, 5)])
+def test_dense_cluster_sweeps_schedule_and_delivery_independent(bs, T):
+    """linear_cluster.cuh has no block barrier in the forward loop: warps may be a whole step apart."""
+    rng = np.random.default_rng(4)
+    B, n_basis = 2, 5
+    lie = rng.normal(size=(1, bs, bs, n_basis)) * (0.5 / np.sqrt(bs))
+    ls = rng.normal(size=(B, T, n_basis + 1)) * 0.2
+    y0, g_ys = rng.normal(size=(B, bs)), rng.normal(size=(B, T, bs))
+    E.set_tuning("k2_de_v2", 2)
+    E.set_tuning("k2_cluster", 1)
+    try:
+        _under_schedules(lambda: E.linear_scan(lie, ls, y0, 1, bs, g_ys))
+        _under_async_modes(lambda: E.linear_scan(lie, ls, y0, 1, bs, g_ys))
+    finally:
+        E.set_tuning("k2_de_v2", 0)
+        E.set_tuning("k2_cluster", 0)
+
+
 @pytest.mark.parametrize("nb,bs,T,n_basis", [(5, 4, 70, 3), (24, 1, 100, 2), (3, 8, 66, 4)])
 def test_time_parallel_scan_schedule_independent(nb, bs, T, n_basis):
     """k2_pscan: every kernel of the two-level scan is deterministic and free of cross-thread hazards between its

@@ -79,6 +79,31 @@ def test_linear_ncde_loss_and_grads(built_lib, case):
     assert rel_err(g[nA:], go.numpy()[nA:]) < TOL
 
 
+@pytest.mark.parametrize("B,H,bs", [(3, 128, 128), (20, 128, 128), (40, 128, 128), (5, 128, 64), (30, 256, 64)])
+def test_dense_cluster_sweeps_equal_one_cta_sweeps(built_lib, B, H, bs):
+    """linear_cluster.cuh (8 / 4 / 2 CTAs per series, by batch size) against the one-CTA sweeps (LNCDE_FLAG_K2_ONE_CTA):
+    same flows, same row arithmetic forward (bit-equal states), same gradient up to summation order."""
+    from lncde import _lib, train as T
+    from lncde.models.generate_model import create_model
+
+    C, s, depth, L = 7, 12, 2, 12 * 41
+    x, logsig = _data(B, L, C, s, depth)
+    name = "dense_linear_ncde" if bs == H else "bd_linear_ncde"
+    model, _ = create_model(name, C, logsig.shape[-1], depth, None, 3, H, block_size=bs, classification=True,
+                            lambd=0.01, w_init_std=0.25, parallel_steps=128, key=3)
+    X = (None, torch.from_numpy(logsig).cuda(), torch.from_numpy(x[:, 0].copy()).cuda())
+    y = torch.nn.functional.one_hot(torch.from_numpy(np.random.default_rng(1).integers(0, 3, B)), 3).float().cuda()
+    ys_c = model.hidden_states(X).detach().cpu().numpy()
+    loss_c, g_c = T.classification_loss(model, X, y)
+    loss_c, g_c = float(loss_c), g_c.cpu().numpy().copy()
+    with _lib.kernel_flags("k2_one_cta"):
+        ys_1 = model.hidden_states(X).detach().cpu().numpy()
+        loss_1, g_1 = T.classification_loss(model, X, y)
+    assert np.array_equal(ys_c, ys_1)
+    assert abs(loss_c - float(loss_1)) < 1e-6 * max(1.0, abs(loss_c))
+    assert rel_err(g_c, g_1.cpu().numpy()) < TOL
+
+
 def test_hidden_states_match_oracle_and_chunked_scan(built_lib):
     from lncde.models.generate_model import create_model
 
