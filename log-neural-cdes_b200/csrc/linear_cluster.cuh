@@ -75,31 +75,34 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
   }
   __syncthreads();
   cluster_sync_all();  // every peer's barriers exist before the first remote store
+  // the slice lies inside one block (RH | bs): its state columns start here
+  const int ycol0 = ((rank * RH) / bs) * bs;
+  int s = 0, sprev = NS - 1;      // stage of this step / of the previous one
+  unsigned fphase = 0;            // parity of the current pass over the ring
   for (int t = 1; t < T; ++t) {
-    const int it = t - 1, s = it % NS;
     if (t >= 2) {
-      // y_{t-1} complete here <=> every warp of every CTA has finished step t-1
-      mbar_wait_cluster(ybar + ((t - 1) & 1), (unsigned)(((t - 2) >> 1) & 1));
+      // y_{t-1} complete here <=> every warp of every CTA has finished step t-1.  (Plain wait: the payload is shared
+      // memory written through the async proxy and counted on this barrier, as for a TMA load; an acquire at cluster
+      // scope would add an L1 invalidate per step.)
+      mbar_wait(ybar + ((t - 1) & 1), (unsigned)(((t - 2) >> 1) & 1));
       if (tid == 0) {
         if (t + 1 < T) mbar_expect_tx(ybar + ((t + 1) & 1), y_bytes);
         const int tn = t - 1 + NS;  // the stage of step t-1 is free: refill it NS steps ahead
         if (tn < T) {
-          const int sn = (it - 1) % NS;
           fence_async_proxy();
-          mbar_expect_tx(fbar + sn, slice_bytes);
-          tma_load_1d(tiles + (size_t)sn * SN, Fb + (size_t)tn * N, slice_bytes, fbar + sn);
+          mbar_expect_tx(fbar + sprev, slice_bytes);
+          tma_load_1d(tiles + (size_t)sprev * SN, Fb + (size_t)tn * N, slice_bytes, fbar + sprev);
         }
       }
     }
-    mbar_wait(fbar + s, (unsigned)((it / NS) & 1));
+    mbar_wait(fbar + s, fphase);
     const float* Ft = tiles + (size_t)s * SN;
-    const float* yc = ybuf + ((t - 1) & 1) * H;
+    const float* yv = ybuf + ((t - 1) & 1) * H + ycol0;
     float* yn = ybuf + (t & 1) * H;
     // warp per group of 4 rows, lanes across the columns
     for (int r0 = warp * 4; r0 < RH; r0 += nw * 4) {
       const int h0 = rank * RH + r0;
       float v[4] = {0.f, 0.f, 0.f, 0.f};
-      const float* yv = yc + (h0 / bs) * bs;
       for (int j4 = lane; j4 < bs / 4; j4 += 32) {
         const float4 y4 = *reinterpret_cast<const float4*>(yv + j4 * 4);
 #pragma unroll
@@ -131,9 +134,14 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
       for (int dst = sub; dst < CS; dst += 8) st_async_f32(yn + h, v[0], ybar + (t & 1), (unsigned)dst);
       if (sub == 7) yb[(size_t)t * H + h] = v[0];
     }
+    sprev = s;
+    if (++s == NS) {
+      s = 0;
+      fphase ^= 1u;
+    }
   }
   // nothing may be in flight towards a CTA that has exited: take delivery of the last state, then leave together
-  if (T > 1) mbar_wait_cluster(ybar + ((T - 1) & 1), (unsigned)(((T - 2) >> 1) & 1));
+  if (T > 1) mbar_wait(ybar + ((T - 1) & 1), (unsigned)(((T - 2) >> 1) & 1));
   cluster_sync_all();
 }
 
@@ -149,8 +157,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
   const int RH = H / CS, SN = RH * bs, NP = kClusterThreads / RH;  // NP partials per owned column
   const unsigned slice_bytes = (unsigned)SN * 4, rx_bytes = (unsigned)kClusterThreads * 4;
   float* tiles = reinterpret_cast<float*>(smraw);  // [NS][SN]
-  float* lamb = tiles + (size_t)NS * SN;           // [RH]
-  float* rx = lamb + RH;                           // [2][NP][RH]  partials of step t in half t & 1
+  float* lamb = tiles + (size_t)NS * SN;           // [2][RH]
+  float* rx = lamb + 2 * RH;                          // [2][NP][RH]  partials of step t in half t & 1
   unsigned long long* fbar = reinterpret_cast<unsigned long long*>(rx + 2 * kClusterThreads);  // [NS]
   unsigned long long* rbar = fbar + NS;                                                        // [2]
   const int tid = threadIdx.x;
@@ -180,23 +188,28 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
   const int col = blk * bs + jj;                            // global column
   const int owner = col / RH, oc = col - owner * RH;        // owning CTA, its local index
   const int src = (rank - blk * (bs / RH)) * RQ + rq;       // which of the owner's NP partials this is
+  int s = 0, cur = 0;   // ring stage, half of lamb that holds lam_t
+  unsigned fphase = 0;
   for (int t = T - 1; t >= 1; --t) {
-    const int it = T - 1 - t, s = it % NS;
+    const int it = T - 1 - t;
+    const float* lam = lamb + cur * RH;
     const float g_prev = tid < RH ? gb[(size_t)(t - 1) * H + tid] : 0.f;
-    if (tid < RH) lo[(size_t)t * H + tid] = lamb[tid];
-    mbar_wait(fbar + s, (unsigned)((it / NS) & 1));
+    if (tid < RH) lo[(size_t)t * H + tid] = lam[tid];
+    mbar_wait(fbar + s, fphase);
     const float* Ft = tiles + (size_t)s * SN + jj;
     float acc = 0.f;
-    for (int i = rq; i < RH; i += RQ) acc = fmaf(Ft[(size_t)i * bs], lamb[i], acc);
+    for (int i = rq; i < RH; i += RQ) acc = fmaf(Ft[(size_t)i * bs], lam[i], acc);
     st_async_f32(rx + ((t & 1) * NP + src) * RH + oc, acc, rbar + (t & 1), (unsigned)owner);
-    mbar_wait_cluster(rbar + (t & 1), (unsigned)((it >> 1) & 1));
-    float sum = g_prev;
-    if (tid < RH)
+    // all partials of step t are here <=> every thread of every CTA sharing this block has read lam_t and its stage
+    mbar_wait(rbar + (t & 1), (unsigned)((it >> 1) & 1));
+    if (tid < RH) {
+      float sum = g_prev;
       for (int q = 0; q < NP; ++q) sum += rx[((t & 1) * NP + q) * RH + tid];
-    __syncthreads();  // every thread has read lam_t and the stage
-    if (tid < RH) lamb[tid] = sum;
+      lamb[(cur ^ 1) * RH + tid] = sum;  // the other half: lam_t may still be read by a slower warp's `lo` store
+    }
+    if (tid == 0 && t - 2 >= 1) mbar_expect_tx(rbar + (t & 1), rx_bytes);
+    __syncthreads();  // lam_{t-1} visible; every thread of THIS CTA is past its reads of the stage
     if (tid == 0) {
-      if (t - 2 >= 1) mbar_expect_tx(rbar + (t & 1), rx_bytes);
       const int tn = t - NS;
       if (tn >= 1) {
         fence_async_proxy();
@@ -204,15 +217,20 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
         tma_load_1d(tiles + (size_t)s * SN, Fb + (size_t)tn * N, slice_bytes, fbar + s);
       }
     }
-    __syncthreads();
+    cur ^= 1;
+    if (++s == NS) {
+      s = 0;
+      fphase ^= 1u;
+    }
   }
-  if (tid < RH) g_y0[(size_t)b * H + rank * RH + tid] = lamb[tid];
+  const float* lamb_end = lamb + cur * RH;
+  if (tid < RH) g_y0[(size_t)b * H + rank * RH + tid] = lamb_end[tid];
   cluster_sync_all();
 }
 
 inline size_t cluster_smem_bytes(bool bwd, int H, int bs, int cs, int ns) {
   const size_t slice = (size_t)(H / cs) * bs * 4;
-  const size_t vec = bwd ? (size_t)(H / cs + 2 * kClusterThreads) * 4 : (size_t)2 * H * 4;
+  const size_t vec = bwd ? (size_t)(2 * (H / cs) + 2 * kClusterThreads) * 4 : (size_t)2 * H * 4;
   return ns * slice + vec + (size_t)(ns + 2) * 8 + 64;
 }
 

@@ -84,7 +84,8 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n"
                "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
-// store `v` at the address `dst` has in CTA `rank` of the cluster and count 4 bytes on that CTA's copy of `bar`
+// store `v` at the address `dst` has in CTA `rank` of the cluster and count 4 bytes on that CTA's copy of `bar`; the
+// receiver waits with mbar_wait, as for a TMA load (the data is in its shared memory when the phase completes)
 // (both pointers are this CTA's own shared-memory addresses; the layouts of the CTAs are identical)
 __device__ __forceinline__ void st_async_f32(float* dst, float v, unsigned long long* bar, unsigned rank) {
   unsigned rdst, rbar;
@@ -94,21 +95,6 @@ __device__ __forceinline__ void st_async_f32(float* dst, float v, unsigned long 
                "r"(__float_as_uint(v)), "r"(rbar)
                : "memory");
 }
-// wait for a phase completed by peers' st_async_f32 (acquire at cluster scope)
-__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAITC_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni WAITC_DONE;\n"
-      "bra.uni WAITC_LOOP;\n"
-      "WAITC_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
 // ---- TF32 tensor-core MMA (legacy warp-level path; used by the 3xTF32 flow build of K2) ---
 // round-to-nearest (ties away) conversion to TF32 (10-bit mantissa), returned as the fp32 bit pattern
 __device__ __forceinline__ uint32_t cvt_tf32(float v) {

@@ -157,7 +157,7 @@ struct LipParams {
 __global__ void __launch_bounds__(1024) lip2_kernel(const float* __restrict__ params, float* __restrict__ loss,
                                                     float* __restrict__ g_params, const LipParams p) {
   __shared__ float warp_sum[32];
-  __shared__ float total_s;
+  __shared__ float total_s, row_norm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (threadIdx.x == 0) total_s = 0.f;
   __syncthreads();
@@ -166,6 +166,33 @@ __global__ void __launch_bounds__(1024) lip2_kernel(const float* __restrict__ pa
     float* gW = g_params + p.w_off[l];
     const int R = p.rows[l], Cn = p.cols[l];
     float mine = 0.f;  // sum of the row norms this warp handled
+    if (Cn >= 1024) {
+      // few long rows (the LNCDE generators: C rows of nb * bs * bs entries): the whole CTA per row, partials added in
+      // warp order - a warp per row would leave all but R warps idle
+      for (int r = 0; r < R; ++r) {
+        const float* row = Wl + (size_t)r * Cn;
+        float ss = 0.f;
+#pragma unroll 4
+        for (int c = threadIdx.x; c < Cn; c += blockDim.x) ss = fmaf(row[c], row[c], ss);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+        __syncthreads();  // warp_sum / row_norm of the previous row have been read
+        if (lane == 0) warp_sum[warp] = ss;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          float t = 0.f;
+          for (int w = 0; w < nw; ++w) t += warp_sum[w];
+          row_norm = sqrtf(t);
+        }
+        __syncthreads();
+        const float nrm = row_norm;
+        if (threadIdx.x == 0) mine += nrm;
+        const float sc = nrm > 0.f ? p.lambd / ((float)R * nrm) : 0.f;
+#pragma unroll 4
+        for (int c = threadIdx.x; c < Cn; c += blockDim.x) gW[(size_t)r * Cn + c] += sc * row[c];
+      }
+      __syncthreads();
+    } else
     for (int r = warp; r < R; r += nw) {
       float ss = 0.f;
       for (int c = lane; c < Cn; c += 32) ss = fmaf(Wl[(size_t)r * Cn + c], Wl[(size_t)r * Cn + c], ss);

@@ -49,7 +49,6 @@ inline void st_async_f32(float* dst, float v, unsigned long long* bar, unsigned 
   emu::count_peer_store();
   emu::mbar_complete_tx(bar, 4);
 }
-inline void mbar_wait_cluster(unsigned long long* bar, unsigned parity) { emu::mbar_wait(bar, parity); }
 
 // TF32: keep 10 mantissa bits, round to nearest with ties away from zero (cvt.rna)
 inline uint32_t cvt_tf32(float v) {

@@ -265,7 +265,8 @@ def test_fused_classification_step_equals_autograd_step(emulated, dims, lambd):
 
 
 @pytest.mark.parametrize("name,bs,lambd", [("diagonal_linear_ncde", 1, 0.1), ("bd_linear_ncde", 4, 0.1),
-                                            ("dense_linear_ncde", 8, 0.0), ("bd_linear_ncde", 2, 0.0)])
+                                            ("dense_linear_ncde", 8, 0.0), ("bd_linear_ncde", 2, 0.0),
+                                            ("dense_linear_ncde", 32, 0.1)])  # rows of 1024 entries: CTA-wide Lip(2) path
 def test_fused_lncde_classification_step_equals_autograd_step(emulated, name, bs, lambd):
     """LogLinearCDE.fused_classification_loss (K5 kernels around the K2 scans; autograd only through log_ode) against the
     autograd formulation under `kernel_flags("generic")` - the generic run also uses the baseline scans, so this covers
@@ -274,7 +275,7 @@ def test_fused_lncde_classification_step_equals_autograd_step(emulated, name, bs
     from lncde.models.generate_model import create_model
     from oracle import paths
 
-    B, L, C_, s, depth, H, nl = 3, 280, 3, 4, 2, 8, 3
+    B, L, C_, s, depth, H, nl = 3, 280, 3, 4, 2, max(8, bs), 3
     rng = np.random.default_rng(7)
     x = np.cumsum(rng.normal(scale=0.1, size=(B, L, C_)), axis=1).astype(np.float32)
     logsig = paths.calc_paths(x, s, depth, np.float32)
