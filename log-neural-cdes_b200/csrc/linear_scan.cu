@@ -590,6 +590,9 @@ namespace lncde {
 // flow_tcgen05.cu: the dense flow build on tcgen05 (hand-written; 3xTF32 split, fp32 accuracy), "k2_de_v2" = 3
 size_t flow_tcgen05_scratch_floats(long long Mtot, int N, int n_basis);
 bool flow_tcgen05_shape(int N, int bs);
+bool dlie_tcgen05_shape(int bs, int n_basis);
+int dlie_tcgen05(cudaStream_t cs, const float* lam, const float* ys, const float* logsig, float* part, int B, int T,
+                 int D, int H, int bs, int n_basis, int max_ksplit, int* err, int* ksplit_out);
 int flow_build_tcgen05(cudaStream_t cs, const float* lie, const float* logsig, float* F, long long Mtot, int N, int D,
                        int n_basis, int bs, float* scratch, size_t scratch_floats);
 
@@ -712,11 +715,21 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
         scan_bwd_lam_dispatch(cs, F, g_ys, lam, g_y0, B, T, H, bs)) {
       st = (int)cudaGetLastError();
       if (st != 0) return st;
-      if (!dlie_triple_dispatch(cs, lam, ys, logsig, part, B, T, D, H, bs, n_basis, kScanKsplit, de_v2 >= 2))
-        return LNCDE_ERR_UNSUPPORTED;
-      st = (int)cudaGetLastError();
-      if (st != 0) return st;
-      reduce_partials_kernel<<<148 * 2, 256, 0, cs>>>(part, g_lie, N * n_basis, kScanKsplit);
+      int ksplit = kScanKsplit;
+      if (de_v2 >= 3 && dlie_tcgen05_shape(bs, n_basis)) {
+        // tcgen05 (3xTF32 split); its error word is the tail of the flow build's scratch (same shape rule)
+        const size_t lam_n = (size_t)B * T * nb * bs;
+        float* tc5_scratch = F + flows + part_n + lam_n;
+        int* err = reinterpret_cast<int*>(tc5_scratch + flow_tcgen05_scratch_floats((long long)B * T, N, n_basis) - 4);
+        st = dlie_tcgen05(cs, lam, ys, logsig, part, B, T, D, H, bs, n_basis, kScanKsplit, err, &ksplit);
+        if (st != 0) return st;
+      } else {
+        if (!dlie_triple_dispatch(cs, lam, ys, logsig, part, B, T, D, H, bs, n_basis, kScanKsplit, de_v2 >= 2))
+          return LNCDE_ERR_UNSUPPORTED;
+        st = (int)cudaGetLastError();
+        if (st != 0) return st;
+      }
+      reduce_partials_kernel<<<148 * 2, 256, 0, cs>>>(part, g_lie, N * n_basis, ksplit);
       return (int)cudaGetLastError();
     }
   }

@@ -8,7 +8,7 @@ B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph --workload 
 $B > $O/r2d_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2b_launches_eigenworms_de.csv $B > $O/r2d_l.log 2>&1
 $B > $O/r2d_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'scan_fwd_cluster|scan_lam_cluster|dlie_triple' -s 6 -c 3 \
+ncu --set full --clock-control none --import-source on -k regex:'scan_fwd_cluster|scan_lam_cluster|dlie_t' -s 6 -c 3 \
     -o $O/r2b_full_k2_de $B > $O/r2d_c.log 2>&1
 ncu -i $O/r2b_full_k2_de.ncu-rep --page raw --csv > $O/r2b_full_k2_de.raw.csv 2> /dev/null
 ncu -i $O/r2b_full_k2_de.ncu-rep --page source --csv -k regex:scan_fwd_cluster > $O/r2b_src_fwd_cluster.csv 2> /dev/null
