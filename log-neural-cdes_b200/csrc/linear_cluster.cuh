@@ -39,11 +39,14 @@ __host__ __device__ inline bool cluster_rows_ok(int H, int bs, int cs) {
   return rh <= bs && bs % rh == 0 && kClusterThreads % rh == 0;
 }
 
-template <int CS>
+// HH / BS: the state and block size at compile time (0 = take the run-time arguments): with the EigenWorms sizes fixed
+// the row and column loops have one trip and the step is a straight line of ~70 instructions per warp.
+template <int CS, int HH, int BS>
 __global__ void __launch_bounds__(kClusterThreads, 1)
     scan_fwd_cluster_kernel(const float* __restrict__ F, const float* __restrict__ y0, float* __restrict__ ys, int T,
-                            int H, int bs, int NS) {
+                            int H_rt, int bs_rt, int NS) {
   extern __shared__ __align__(128) unsigned char smraw[];
+  const int H = HH ? HH : H_rt, bs = BS ? BS : bs_rt;
   const int RH = H / CS, SN = RH * bs;
   const unsigned slice_bytes = (unsigned)SN * 4, y_bytes = (unsigned)H * 4;
   float* tiles = reinterpret_cast<float*>(smraw);  // [NS][SN]
@@ -149,11 +152,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
 // (same contract as scan_bwd_tma_lam_kernel).  CTA `rank` keeps lam[rank * RH .. +RH) and forms, for each of the bs
 // columns of its block, the partial sum over its RH rows - split over RQ = 256 / bs thread groups - and sends it to
 // the owner of the column; an owner receives 256 / RH partials per column.
-template <int CS>
+template <int CS, int HH, int BS>
 __global__ void __launch_bounds__(kClusterThreads, 1)
     scan_lam_cluster_kernel(const float* __restrict__ F, const float* __restrict__ g_ys, float* __restrict__ lam_out,
-                            float* __restrict__ g_y0, int T, int H, int bs, int NS) {
+                            float* __restrict__ g_y0, int T, int H_rt, int bs_rt, int NS) {
   extern __shared__ __align__(128) unsigned char smraw[];
+  const int H = HH ? HH : H_rt, bs = BS ? BS : bs_rt;
   const int RH = H / CS, SN = RH * bs, NP = kClusterThreads / RH;  // NP partials per owned column
   const unsigned slice_bytes = (unsigned)SN * 4, rx_bytes = (unsigned)kClusterThreads * 4;
   float* tiles = reinterpret_cast<float*>(smraw);  // [NS][SN]
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
     mbar_wait(fbar + s, fphase);
     const float* Ft = tiles + (size_t)s * SN + jj;
     float acc = 0.f;
+#pragma unroll 16
     for (int i = rq; i < RH; i += RQ) acc = fmaf(Ft[(size_t)i * bs], lam[i], acc);
     st_async_f32(rx + ((t & 1) * NP + src) * RH + oc, acc, rbar + (t & 1), (unsigned)owner);
     // all partials of step t are here <=> every thread of every CTA sharing this block has read lam_t and its stage
@@ -240,18 +245,18 @@ static inline int cluster_fail() {
   return 0;
 }
 
-template <int CS>
+template <int CS, int HH, int BS>
 static int launch_cluster_scan(bool bwd, cudaStream_t cs, const float* F, const float* a, float* out, float* g_y0, int B,
                                int T, int H, int bs, int ns, size_t smem, bool probe_only) {
 #if LNCDE_EMU
   // the host emulator runs CTAs one at a time: it executes the kernels as clusters of one CTA (CS = 1)
   if (probe_only) return 1 << 30;
   if (!bwd) {
-    cudaFuncSetAttribute(scan_fwd_cluster_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_fwd_cluster_kernel<CS><<<B * CS, kClusterThreads, smem, cs>>>(F, a, out, T, H, bs, ns);
+    cudaFuncSetAttribute(scan_fwd_cluster_kernel<CS, HH, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_fwd_cluster_kernel<CS, HH, BS><<<B * CS, kClusterThreads, smem, cs>>>(F, a, out, T, H, bs, ns);
   } else {
-    cudaFuncSetAttribute(scan_lam_cluster_kernel<CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    scan_lam_cluster_kernel<CS><<<B * CS, kClusterThreads, smem, cs>>>(F, a, out, g_y0, T, H, bs, ns);
+    cudaFuncSetAttribute(scan_lam_cluster_kernel<CS, HH, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_lam_cluster_kernel<CS, HH, BS><<<B * CS, kClusterThreads, smem, cs>>>(F, a, out, g_y0, T, H, bs, ns);
   }
   return 1 << 30;
 #else
@@ -269,13 +274,13 @@ static int launch_cluster_scan(bool bwd, cudaStream_t cs, const float* F, const 
   cfg.numAttrs = 1;
   int resident = 0;
   if (!bwd) {
-    auto k = scan_fwd_cluster_kernel<CS>;
+    auto k = scan_fwd_cluster_kernel<CS, HH, BS>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cluster_fail();
     if (CS > 8 && cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return cluster_fail();
     if (cudaOccupancyMaxActiveClusters(&resident, k, &cfg) != cudaSuccess) return cluster_fail();
     if (!probe_only && cudaLaunchKernelEx(&cfg, k, F, a, out, T, H, bs, ns) != cudaSuccess) return cluster_fail();
   } else {
-    auto k = scan_lam_cluster_kernel<CS>;
+    auto k = scan_lam_cluster_kernel<CS, HH, BS>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return cluster_fail();
     if (CS > 8 && cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) return cluster_fail();
     if (cudaOccupancyMaxActiveClusters(&resident, k, &cfg) != cudaSuccess) return cluster_fail();
@@ -312,14 +317,16 @@ static int cluster_try(bool bwd, cudaStream_t cs, const float* F, const float* a
     std::lock_guard<std::mutex> lock(mu);
     auto it = seen[bwd].find(sh.smem);
     if (it == seen[bwd].end()) {
-      resident = launch_cluster_scan<CS>(bwd, cs, F, a, out, g_y0, B, T, H, bs, sh.ns, sh.smem, true);
+      resident = launch_cluster_scan<CS, 0, 0>(bwd, cs, F, a, out, g_y0, B, T, H, bs, sh.ns, sh.smem, true);
       seen[bwd][sh.smem] = resident;
     } else {
       resident = it->second;
     }
   }
   if (resident < B) return 0;  // a second wave would double the sweep: a narrower cluster (or one CTA) is better
-  return launch_cluster_scan<CS>(bwd, cs, F, a, out, g_y0, B, T, H, bs, sh.ns, sh.smem, false);
+  if (H == 128 && bs == 128)  // the EigenWorms dense model: sizes folded at compile time
+    return launch_cluster_scan<CS, 128, 128>(bwd, cs, F, a, out, g_y0, B, T, H, bs, sh.ns, sh.smem, false);
+  return launch_cluster_scan<CS, 0, 0>(bwd, cs, F, a, out, g_y0, B, T, H, bs, sh.ns, sh.smem, false);
 }
 
 // true if the sweep was launched on clusters: the widest of 8 / 4 / 2 CTAs per series whose clusters are all resident
