@@ -88,15 +88,6 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
       // memory written through the async proxy and counted on this barrier, as for a TMA load; an acquire at cluster
       // scope would add an L1 invalidate per step.)
       mbar_wait(ybar + ((t - 1) & 1), (unsigned)(((t - 2) >> 1) & 1));
-      if (tid == 0) {
-        if (t + 1 < T) mbar_expect_tx(ybar + ((t + 1) & 1), y_bytes);
-        const int tn = t - 1 + NS;  // the stage of step t-1 is free: refill it NS steps ahead
-        if (tn < T) {
-          fence_async_proxy();
-          mbar_expect_tx(fbar + sprev, slice_bytes);
-          tma_load_1d(tiles + (size_t)sprev * SN, Fb + (size_t)tn * N, slice_bytes, fbar + sprev);
-        }
-      }
     }
     mbar_wait(fbar + s, fphase);
     const float* Ft = tiles + (size_t)s * SN;
@@ -136,6 +127,18 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
       // lane `sub` of the group delivers the value to CTA `sub` (its own CTA included); 4 bytes counted per delivery
       for (int dst = sub; dst < CS; dst += 8) st_async_f32(yn + h, v[0], ybar + (t & 1), (unsigned)dst);
       if (sub == 7) yb[(size_t)t * H + h] = v[0];
+    }
+    // housekeeping AFTER the send - every peer waits on this warp's rows, nobody on this.  y_{t-1} was complete at the
+    // top of the step, so the stage of step t-1 is free (refilled NS steps ahead) and the half of y_{t+1} can be armed
+    // (bytes that arrive before the arming are counted all the same).
+    if (tid == 0 && t >= 2) {
+      if (t + 1 < T) mbar_expect_tx(ybar + ((t + 1) & 1), y_bytes);
+      const int tn = t - 1 + NS;
+      if (tn < T) {
+        fence_async_proxy();
+        mbar_expect_tx(fbar + sprev, slice_bytes);
+        tma_load_1d(tiles + (size_t)sprev * SN, Fb + (size_t)tn * N, slice_bytes, fbar + sprev);
+      }
     }
     sprev = s;
     if (++s == NS) {
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
   const int col = blk * bs + jj;                            // global column
   const int owner = col / RH, oc = col - owner * RH;        // owning CTA, its local index
   const int src = (rank - blk * (bs / RH)) * RQ + rq;       // which of the owner's NP partials this is
-  int s = 0, cur = 0;   // ring stage, half of lamb that holds lam_t
+  int s = 0, sprev = 0, cur = 0;   // ring stage of this step / the previous one, half of lamb that holds lam_t
   unsigned fphase = 0;
   for (int t = T - 1; t >= 1; --t) {
     const int it = T - 1 - t;
@@ -205,6 +208,12 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
 #pragma unroll 16
     for (int i = rq; i < RH; i += RQ) acc = fmaf(Ft[(size_t)i * bs], lam[i], acc);
     st_async_f32(rx + ((t & 1) * NP + src) * RH + oc, acc, rbar + (t & 1), (unsigned)owner);
+    if (tid == 0 && t + 1 - NS >= 1 && t + 1 <= T - 1) {
+      // housekeeping after the send: the stage of step t+1 was released by the block barrier that closed it
+      fence_async_proxy();
+      mbar_expect_tx(fbar + sprev, slice_bytes);
+      tma_load_1d(tiles + (size_t)sprev * SN, Fb + (size_t)(t + 1 - NS) * N, slice_bytes, fbar + sprev);
+    }
     // all partials of step t are here <=> every thread of every CTA sharing this block has read lam_t and its stage
     mbar_wait(rbar + (t & 1), (unsigned)((it >> 1) & 1));
     if (tid < RH) {
@@ -214,15 +223,8 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
     }
     if (tid == 0 && t - 2 >= 1) mbar_expect_tx(rbar + (t & 1), rx_bytes);
     __syncthreads();  // lam_{t-1} visible; every thread of THIS CTA is past its reads of the stage
-    if (tid == 0) {
-      const int tn = t - NS;
-      if (tn >= 1) {
-        fence_async_proxy();
-        mbar_expect_tx(fbar + s, slice_bytes);
-        tma_load_1d(tiles + (size_t)s * SN, Fb + (size_t)tn * N, slice_bytes, fbar + s);
-      }
-    }
     cur ^= 1;
+    sprev = s;
     if (++s == NS) {
       s = 0;
       fphase ^= 1u;
