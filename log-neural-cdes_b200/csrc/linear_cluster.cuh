@@ -197,10 +197,13 @@ __global__ void __launch_bounds__(kClusterThreads, 1)
   const int src = (rank - blk * (bs / RH)) * RQ + rq;       // which of the owner's NP partials this is
   int s = 0, sprev = 0, cur = 0;   // ring stage of this step / the previous one, half of lamb that holds lam_t
   unsigned fphase = 0;
+  float g_ahead = (tid < RH && T >= 2) ? gb[(size_t)(T - 2) * H + tid] : 0.f;
   for (int t = T - 1; t >= 1; --t) {
     const int it = T - 1 - t;
     const float* lam = lamb + cur * RH;
-    const float g_prev = tid < RH ? gb[(size_t)(t - 1) * H + tid] : 0.f;
+    // g_{t-1} is needed after the exchange: loaded one step ahead (its L2 latency is about a whole step)
+    const float g_prev = g_ahead;
+    g_ahead = (tid < RH && t >= 2) ? gb[(size_t)(t - 2) * H + tid] : 0.f;
     if (tid < RH) lo[(size_t)t * H + tid] = lam[tid];
     mbar_wait(fbar + s, fphase);
     const float* Ft = tiles + (size_t)s * SN + jj;
