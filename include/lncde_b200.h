@@ -42,8 +42,8 @@ extern "C" {
 #define LNCDE_FLAG_GENERIC 8u     /* baseline kernels only - classic K1 staging, sequential D / BD scans, FFMA dense flow
                                      build with materialised dF, unstreamed generic Log-NCDE mat-vecs: the kernels every
                                      specialised one is checked against (tests, scripts/variant_check.py) */
-#define LNCDE_FLAG_K2_MMA_SYNC 16u /* dense LNCDE: flow build on the warp-level tensor pipe (mma.sync, 3xTF32) instead of
-                                      tcgen05 - the path of block sizes that are not multiples of 128 */
+#define LNCDE_FLAG_K2_MMA_SYNC 16u /* dense LNCDE: flow build and bracket gradient on the warp-level tensor pipe (mma.sync,
+                                      3xTF32) instead of tcgen05 - the path of block sizes that are not multiples of 128 */
 #define LNCDE_FLAG_K3_V3 32u      /* Log-NCDE, H = 128 / width 32 model: six-barrier stage kernels (logncde_v3.cuh); measured
                                      slower than the default on B200, kept for its clock-trace instrumentation */
 #define LNCDE_FLAG_K2_ONE_CTA 64u /* dense LNCDE: one CTA per series for the two sweeps instead of a thread-block cluster

@@ -11,7 +11,7 @@ $B > $O/r2d_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'scan_fwd_cluster|scan_lam_cluster|dlie_t' -s 6 -c 3 \
     -o $O/r2b_full_k2_de $B > $O/r2d_c.log 2>&1
 ncu -i $O/r2b_full_k2_de.ncu-rep --page raw --csv > $O/r2b_full_k2_de.raw.csv 2> /dev/null
-ncu -i $O/r2b_full_k2_de.ncu-rep --page source --csv -k regex:scan_fwd_cluster > $O/r2b_src_fwd_cluster.csv 2> /dev/null
+ncu -i $O/r2b_full_k2_de.ncu-rep --page source --csv -k regex:scan_lam_cluster > $O/r2b_src_lam_cluster.csv 2> /dev/null
 sz=$(stat -c %s $O/r2b_full_k2_de.ncu-rep 2> /dev/null || echo 0)
 if [ "$sz" -gt 6000000 ]; then rm -f $O/r2b_full_k2_de.ncu-rep; fi
 ls -la $O | grep r2b

@@ -1,10 +1,11 @@
 """Static SASS / resource table of the kernels in liblncde_b200.so (no GPU needed): registers, shared memory, stack,
 instruction count and mix (FP32 arithmetic, shared / global memory, block barriers, shuffles) and the Blackwell-specific
 mnemonics (UBLKCP = 1-D TMA bulk copy, UTMALDG = tensor-map TMA load, UTCHMMA = tcgen05.mma, HMMA = warp-level MMA,
-LDGSTS = cp.async, SYNCS = mbarrier).  Counts are STATIC (whole kernel, every instantiated path once), so they compare
+LDGSTS = cp.async, SYNCS = mbarrier, LDTM = tcgen05.ld, STAS = st.async into a peer CTA's shared memory, UCGABAR = cluster
+barrier, FFMA2 = packed fp32 pair).  Counts are STATIC (whole kernel, every instantiated path once), so they compare
 variants of the same kernel - e.g. block barriers of the default and the fused-phase Log-NCDE kernels - not run times.
 
-    python scripts/sass_stats.py [regex] > profiles/r01_static_sass.md
+    python scripts/sass_stats.py [regex] > profiles/r02_static_sass.md
 """
 import os
 import re
@@ -16,9 +17,9 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(R, "log-neural-cdes_b200", "liblncde_b200.so")
 CLASSES = (("fp32", r"^(FFMA|FMUL|FADD|FMNMX|MUFU|FSEL|FSET|FSETP)"), ("lds", r"^LDS"), ("sts", r"^STS"),
            ("ldg", r"^(LDG|LD\.)"), ("stg", r"^(STG|ST\.)"), ("bar", r"^BAR"), ("shfl", r"^SHFL"))
-SPECIAL = ("UBLKCP", "UTMALDG", "UTMASTG", "UTCHMMA", "UTCBAR", "HMMA", "LDGSTS", "SYNCS")
+SPECIAL = ("UBLKCP", "UTMALDG", "UTMASTG", "UTCHMMA", "UTCBAR", "LDTM", "HMMA", "LDGSTS", "SYNCS", "STAS", "UCGABAR", "FFMA2")
 DEFAULT_PICK = (r"logsig_levy(_tma)?_kernel<7, ?(true|1)|logsig_d3_kernel<7>|logncde_(fwd_fast|bwd_saved)_kernel<7|"
-                r"outer_gemm_kernel|flow_build|dlie_triple|scan_(fwd|bwd)_(warp_kernel<4|tma)|pscan_\w+<4|dlncde_\w+<7>|"
+                r"outer_gemm_kernel|flow_build|dlie_t|scan_(fwd|bwd|lam)_(warp_kernel<4|tma|cluster_kernel<4)|pscan_\w+<4|dlncde_\w+<7>|"
                 r"nrde_(fwd|bwd)_kernel|umma_|cutlass|adam_dev|ffma_probe")
 
 
