@@ -5,13 +5,13 @@
 //    models/LinearNeuralCDEs.py:318-329; dF_t = lam_t y_{t-1}^T is never materialised)
 //
 // As a GEMM:  D[i, (j, l)] = sum_m A[i, m] * Bm[(j, l), m]   with A = lam^T and Bm[(j, l), m] = y_prev[m, j] * logsig[m, 1 + l]
-// formed on the fly: M = 128 rows i (the TMEM lanes), N = 16 j x 32 l (l padded to 32) = 512 fp32 accumulator columns =
-// all of TMEM, K = the (sample, step) pairs, split over CTAs (split-K partials, reduced by reduce_partials_kernel).
+// formed on the fly: M = 128 rows i (the TMEM lanes), N = 16 j x 32 l (tiles of 32 basis elements, the last one padded) =
+// 512 fp32 accumulator columns = all of TMEM, K = the (sample, step) pairs, split over CTAs (split-K partials, reduced by reduce_partials_kernel).
 // 44 GFLOP x 3 for EigenWorms against 0.1 GB of operands: tensor-pipe work.  3xTF32 as in flow_tcgen05.cu: both operands
 // are split into hi = tf32(x), lo = tf32(x - hi) on their way into shared memory and
 // a b ~= a_lo b_hi + a_hi b_lo + a_hi b_hi, accumulated in fp32 in TMEM.
 //
-// Kernel (one CTA per (block, 128-row i tile, 16-column j group, K split), 9 warps):
+// Kernel (one CTA per (block, 128-row i tile, 16-column j group, 32-element basis tile, K split), 9 warps):
 //   warps 0-7  producers: per stage of 16 m's read lam / y_prev / logsig rows straight from global memory (L2 resident,
 //              one stage ahead in registers), form the products, split, and write the K-major / no-swizzle operand
 //              image tcgen05.mma reads (core matrix = 8 rows x 16 B; hi and lo planes): 16 KB of A + 64 KB of B per stage,
@@ -56,19 +56,20 @@ struct DlieParams {
   const float* ys;   // [B][T][H]
   const float* ls;   // [B][T][D]
   float* part;       // [ksplit][nb][bs][bs][n_basis]
-  int T, D, H, bs, n_basis, ksplit, i_tiles, j_tiles;
+  int T, D, H, bs, n_basis, ksplit, i_tiles, j_tiles, l_tiles;
   unsigned Ktot, per;  // B (T - 1) pairs, pairs per K split (multiple of kStageK)
   size_t n_out;
   int* err;
 };
 
 struct Tile {
-  int ks, blk, i0, j0;
+  int ks, blk, i0, j0, l0;  // l0: first of the (at most) 32 basis elements of this tile
   unsigned k_lo, k_hi;
 };
 __device__ __forceinline__ Tile tile_of(const DlieParams& p, int bid) {
   Tile t;
   t.ks = bid % p.ksplit; bid /= p.ksplit;
+  t.l0 = (bid % p.l_tiles) * kL; bid /= p.l_tiles;
   t.j0 = (bid % p.j_tiles) * kJ; bid /= p.j_tiles;
   t.i0 = (bid % p.i_tiles) * kM; bid /= p.i_tiles;
   t.blk = bid;
@@ -96,8 +97,8 @@ __device__ __forceinline__ void load_stage(StageRegs& r, const DlieParams& p, co
   const unsigned Tm1 = (unsigned)p.T - 1u;
   const float* lam = p.lam + (size_t)t.blk * p.bs + t.i0 + (tid & 127);
   const float* ya = p.ys + (size_t)t.blk * p.bs + t.j0 + warp;
-  const float* ls = p.ls + 1 + lane;
-  const bool l_ok = lane < p.n_basis;
+  const float* ls = p.ls + 1 + t.l0 + lane;
+  const bool l_ok = t.l0 + lane < p.n_basis;
 #pragma unroll
   for (int kk = 0; kk < kStageK; ++kk) {
     const unsigned k = k0 + kk;
@@ -158,10 +159,11 @@ __device__ __forceinline__ void advance_pairs(unsigned n, unsigned Tm1, unsigned
   }
 }
 
-// part[ks][blk][i][j][l]
+// part[ks][blk][i][j][l0 ..]: the tile's basis elements of pair (i, j); n_l of them exist
 __device__ __forceinline__ float* out_row(const DlieParams& p, const Tile& t, int i, int jl) {
-  return p.part + (size_t)t.ks * p.n_out + (((size_t)t.blk * p.bs + t.i0 + i) * p.bs + t.j0 + jl) * p.n_basis;
+  return p.part + (size_t)t.ks * p.n_out + (((size_t)t.blk * p.bs + t.i0 + i) * p.bs + t.j0 + jl) * p.n_basis + t.l0;
 }
+__device__ __forceinline__ int tile_basis(const DlieParams& p, const Tile& t) { return min(kL, p.n_basis - t.l0); }
 
 #if defined(LNCDE_EMU)
 // emulator stand-in for the tensor pipe: the same stage images, the three partial products in plain fp32
@@ -170,8 +172,9 @@ __global__ void __launch_bounds__(kProducers) dlie_tc5_reference_kernel(const Dl
   float* stage = reinterpret_cast<float*>(smem_raw);
   const int tid = threadIdx.x;
   const Tile t = tile_of(p, blockIdx.x);
+  const int n_l = tile_basis(p, t);
   for (int e = tid; e < kM * kJ; e += kProducers)
-    for (int l = 0; l < p.n_basis; ++l) out_row(p, t, e / kJ, e % kJ)[l] = 0.f;
+    for (int l = 0; l < n_l; ++l) out_row(p, t, e / kJ, e % kJ)[l] = 0.f;
   unsigned b, rem;
   pair_of(t.k_lo, (unsigned)p.T - 1u, b, rem);
   for (unsigned k0 = t.k_lo; k0 < t.k_hi; k0 += kStageK) {
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(kProducers) dlie_tc5_reference_kernel(const Dl
     for (int e = tid; e < kM * kJ; e += kProducers) {
       const int i = e / kJ, jl = e % kJ;
       float* o = out_row(p, t, i, jl);
-      for (int l = 0; l < p.n_basis; ++l) {
+      for (int l = 0; l < n_l; ++l) {
         float acc = o[l];
         for (int k = 0; k < kStageK; ++k) {
           const int ia = ((k >> 2) * kM + i) * 4 + (k & 3), ib = ((k >> 2) * kN + jl * kL + l) * 4 + (k & 3);
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) dlie_tcgen05_kernel(const DliePar
     if (ok) {
       fence_after_thread_sync();
       const int quarter = warp & 3, i = quarter * 32 + lane, jbase = (warp >> 2) * (kJ / 2);
+      const int n_l = tile_basis(p, t);
       for (int jj = 0; jj < kJ / 2; ++jj) {
         float v[32];
         if (n_stages > 0) {
@@ -267,14 +271,14 @@ __global__ void __launch_bounds__(kThreads, 1) dlie_tcgen05_kernel(const DliePar
           for (int l = 0; l < 32; ++l) v[l] = 0.f;
         }
         float* o = out_row(p, t, i, jbase + jj);
-        if ((p.n_basis & 3) == 0) {
+        if ((p.n_basis & 3) == 0) {  // rows of the partial buffer are 16-byte aligned, n_l is a multiple of 4
 #pragma unroll
           for (int l = 0; l < 32; l += 4)
-            if (l < p.n_basis) *reinterpret_cast<float4*>(o + l) = make_float4(v[l], v[l + 1], v[l + 2], v[l + 3]);
+            if (l < n_l) *reinterpret_cast<float4*>(o + l) = make_float4(v[l], v[l + 1], v[l + 2], v[l + 3]);
         } else {
 #pragma unroll
           for (int l = 0; l < 32; ++l)
-            if (l < p.n_basis) o[l] = v[l];
+            if (l < n_l) o[l] = v[l];
         }
       }
     }
@@ -321,12 +325,13 @@ __global__ void __launch_bounds__(kThreads, 1) dlie_tcgen05_kernel(const DliePar
 
 }  // namespace tc5d
 
-// shapes the kernel takes: whole 128-row i tiles and 16-column j groups inside a block, at most 32 basis elements
-bool dlie_tcgen05_shape(int bs, int n_basis) { return bs >= tc5d::kM && bs % tc5d::kM == 0 && n_basis >= 1 && n_basis <= tc5d::kL; }
+// shapes the kernel takes: whole 128-row i tiles and 16-column j groups inside a block; any number of basis elements
+// (tiles of 32: depth 3 of 7 channels has 140)
+bool dlie_tcgen05_shape(int bs, int n_basis) { return bs >= tc5d::kM && bs % tc5d::kM == 0 && n_basis >= 1; }
 
 // K splits used for this shape (<= max_ksplit, the size of the caller's partial buffer)
-int dlie_tcgen05_ksplit(int B, int T, int H, int bs, int max_ksplit) {
-  const long long tiles = (long long)(H / bs) * (bs / tc5d::kM) * (bs / tc5d::kJ);
+int dlie_tcgen05_ksplit(int B, int T, int H, int bs, int n_basis, int max_ksplit) {
+  const long long tiles = (long long)(H / bs) * (bs / tc5d::kM) * (bs / tc5d::kJ) * ((n_basis + tc5d::kL - 1) / tc5d::kL);
   const long long stages = ((long long)B * (T - 1) + tc5d::kStageK - 1) / tc5d::kStageK;
   long long ks = 148 / (tiles < 1 ? 1 : tiles);
   if (ks > stages) ks = stages;
@@ -344,15 +349,17 @@ int dlie_tcgen05(cudaStream_t cs, const float* lam, const float* ys, const float
   DlieParams p;
   p.lam = lam; p.ys = ys; p.ls = logsig; p.part = part;
   p.T = T; p.D = D; p.H = H; p.bs = bs; p.n_basis = n_basis;
-  p.ksplit = dlie_tcgen05_ksplit(B, T, H, bs, max_ksplit);
-  p.i_tiles = bs / kM; p.j_tiles = bs / kJ;
+  p.ksplit = dlie_tcgen05_ksplit(B, T, H, bs, n_basis, max_ksplit);
+  p.i_tiles = bs / kM; p.j_tiles = bs / kJ; p.l_tiles = (n_basis + kL - 1) / kL;
   p.Ktot = (unsigned)B * (unsigned)(T - 1);
   const unsigned per = (p.Ktot + p.ksplit - 1) / p.ksplit;
   p.per = (per + kStageK - 1) / kStageK * kStageK;
   p.n_out = (size_t)H * bs * n_basis;
   p.err = err;
   *ksplit_out = p.ksplit;
-  const int grid = (H / bs) * p.i_tiles * p.j_tiles * p.ksplit;
+  const long long grid_ll = (long long)(H / bs) * p.i_tiles * p.j_tiles * p.l_tiles * p.ksplit;
+  if (grid_ll > 0x7fffffffLL) return LNCDE_ERR_UNSUPPORTED;
+  const int grid = (int)grid_ll;
 #if defined(LNCDE_EMU)
   const size_t smem = (size_t)kStageFloats * 4;
   cudaFuncSetAttribute(dlie_tc5_reference_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -578,7 +578,18 @@ constexpr int kScanKsplit = 64;
 static size_t flows_floats(int B, int T, int nb, int bs) { return (size_t)B * T * nb * bs * bs; }
 
 // "k2_de_v2" applies to big blocks only (the warp-shuffle scans of bs | 32 keep their kernels)
-static bool de_v2_shape(int bs, int n_basis) { return bs >= 64 && bs % 4 == 0 && ((n_basis + 3) & ~3) <= 36; }
+bool dlie_tcgen05_shape(int bs, int n_basis);
+// shapes for which SOME kernel level runs the reverse sweep that stores lam_t only (sizes the workspace: shape-only)
+static bool de_v2_shape(int bs, int n_basis) {
+  return bs >= 64 && bs % 4 == 0 && (((n_basis + 3) & ~3) <= 36 || dlie_tcgen05_shape(bs, n_basis));
+}
+// ... and whether this call's level has a bracket-gradient kernel for it: the mma.sync / FFMA triple products are
+// compiled for n_basis <= 36, the tcgen05 kernel (level 3) takes any n_basis
+static bool lam_path(int level, int bs, int n_basis) {
+  if (level < 2 || bs < 64 || bs % 4 != 0) return false;
+  if (((n_basis + 3) & ~3) <= 36) return true;
+  return level >= 3 && dlie_tcgen05_shape(bs, n_basis);
+}
 
 
 // floats in front of the k2_pscan scratch: flows | split-K partials | lam (dense only) | packed operands (dense only)
@@ -590,7 +601,6 @@ namespace lncde {
 // flow_tcgen05.cu: the dense flow build on tcgen05 (hand-written; 3xTF32 split, fp32 accuracy), "k2_de_v2" = 3
 size_t flow_tcgen05_scratch_floats(long long Mtot, int N, int n_basis);
 bool flow_tcgen05_shape(int N, int bs);
-bool dlie_tcgen05_shape(int bs, int n_basis);
 int dlie_tcgen05(cudaStream_t cs, const float* lam, const float* ys, const float* logsig, float* part, int B, int T,
                  int D, int H, int bs, int n_basis, int max_ksplit, int* err, int* ksplit_out);
 int flow_build_tcgen05(cudaStream_t cs, const float* lie, const float* logsig, float* F, long long Mtot, int N, int D,
@@ -705,7 +715,7 @@ int lncde_linear_scan_bwd(void* stream, const float* lie, const float* logsig, c
   float* F = (float*)workspace;  // still holds the forward flows of the SAME (lie, logsig)
   const int H = nb * bs, N = H * bs;
   const int de_v2 = dense_level(flags, N, bs);
-  if (de_v2 && de_v2_shape(bs, n_basis) && T >= 2) {
+  if (lam_path(de_v2, bs, n_basis) && T >= 2) {
     // reverse sweep stores lam_t only; dLie = sum lam_t (x) y_{t-1} (x) logsig_t from the small operands
     const size_t flows = (flows_floats(B, T, nb, bs) + 3) & ~(size_t)3;
     const size_t part_n = ((size_t)N * n_basis * kScanKsplit + 3) & ~(size_t)3;

@@ -332,7 +332,7 @@ def test_emu_dense_cluster_sweeps(bs, T, B):
 @pytest.mark.parametrize("level", [2, 3])
 @pytest.mark.parametrize("nb,bs,T,n_basis,B", [(1, 64, 9, 6, 2), (1, 128, 7, 28, 2), (2, 64, 5, 21, 3), (1, 64, 2, 3, 1),
                                                (1, 68, 6, 10, 2), (1, 128, 12, 36, 1), (1, 64, 5, 40, 2), (1, 72, 4, 70, 1),
-                                               (1, 128, 14, 5, 3), (1, 128, 2, 4, 5)])
+                                               (1, 128, 14, 5, 3), (1, 128, 2, 4, 5), (1, 128, 6, 70, 2)])
 def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B, level):
     """Dense-model kernels (linear_de.cuh) against the baseline kernels (LNCDE_FLAG_GENERIC).  Level 2
     (LNCDE_FLAG_K2_MMA_SYNC): lam-only reverse sweep, triple-product bracket gradient, the flow build on the tensor pipe (3xTF32 split precision, mma.sync modelled by the emulator
@@ -342,7 +342,8 @@ def test_emu_linear_scan_dense_v2_variant(nb, bs, T, n_basis, B, level):
     kernel (the K-major / no-swizzle shared-memory image of tcgen05.mma, hi | lo TF32 planes, K padded to 32), the
     identity and the workspace layout are the code under test, the MMA unit itself is replaced by a plain fp32
     evaluation of the same three partial products from the packed operands; with n_basis <= 32 the bracket gradient
-    runs through dlie_tcgen05.cu the same way (operand-forming code shared with the tcgen05 kernel: pair -> row
+    runs through dlie_tcgen05.cu the same way (any n_basis at level 3, in tiles of 32 basis elements: 36 and 70 have a
+    partial last tile, 70 takes the scalar stores) (operand-forming code shared with the tcgen05 kernel: pair -> row
     bookkeeping across samples, including T = 2 where every pair starts a new sample, K splits, zero fill, hi | lo
     image; the MMA unit replaced by plain fp32); the rest of the step is level 2."""
     rng = np.random.default_rng(11)
