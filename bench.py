@@ -376,10 +376,11 @@ def own_launches_per_step(model_name, wl):
         return 1 + k5 + 1 + (1 + 3 + 1) + adam   # K1, K5, solve, sweep + 3 gradient-GEMM groups + gradient reduce, Adam
     mean = 2                                     # time_mean_fwd / _bwd
     if model_name == "diagonal_linear_ncde":
-        return 1 + k5 + mean + 1 + 2 + adam      # dlncde_fwd, dlncde_bwd + its reduce
+        # dlncde_fwd (forms the time mean), dlncde_bwd (takes its cotangent) + its batch reduce (two levels beyond 32 samples)
+        return 1 + k5 + 1 + 2 + (1 if wl.get("B", 32) > 32 else 0) + adam
     brackets = 2 * (1 + (wl.get("depth", 2) - 1))  # K2a forward and reverse: one launch per degree >= 2 + the transpose
     if model_name == "dense_linear_ncde":
-        # two operand packs + tcgen05 flow build + scan | lam-only reverse scan, triple-product gradient, split-K reduce
+        # two operand packs + tcgen05 flow build + cluster sweep | lam-only reverse cluster sweep, tcgen05 bracket gradient, split-K reduce
         return 1 + k5 + mean + brackets + (3 + 1) + 3 + adam
     # block-diagonal: flow build + time-parallel scans (products / boundary / apply | products / local / boundary / local) + GEMM, reduce
     return 1 + k5 + mean + brackets + (1 + 3) + (4 + 2) + adam

@@ -207,6 +207,14 @@ int lncde_dlncde_fwd(void* stream, const float* vf_At, const float* logsig, cons
 int lncde_dlncde_bwd(void* stream, const float* vf_At, const float* logsig, const float* ys,
                      const float* g_ys, float* g_vf_At, float* g_y0, int B, int T, int D, int H, int C,
                      void* workspace, size_t workspace_bytes);
+/* The same pair for the classification read-out, which only sees the mean of the states over time
+ * (LinearNeuralCDEs.py:389): the forward also returns y_mean [B, H] = mean_t ys, the backward takes g_mean [B, H] =
+ * dLoss/dy_mean and uses g_ys[b, t, :] = g_mean[b, :] / T for every t - no [B, T, H] cotangent is written or read. */
+int lncde_dlncde_fwd_mean(void* stream, const float* vf_At, const float* logsig, const float* y0, float* ys,
+                          float* y_mean, int B, int T, int D, int H, int C);
+int lncde_dlncde_bwd_mean(void* stream, const float* vf_At, const float* logsig, const float* ys,
+                          const float* g_mean, float* g_vf_At, float* g_y0, int B, int T, int D, int H, int C,
+                          void* workspace, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------ K4 ---
  * Fused Adam update on a flat parameter buffer (optax.adam defaults,

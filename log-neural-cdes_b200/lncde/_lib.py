@@ -46,6 +46,8 @@ def _declare(lib):
         "lncde_dlncde_bwd_workspace_bytes": (sz, [i, i, i]),
         "lncde_dlncde_fwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, i]),
         "lncde_dlncde_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]),
+        "lncde_dlncde_fwd_mean": (i, [vp, vp, vp, vp, vp, vp, i, i, i, i, i]),
+        "lncde_dlncde_bwd_mean": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]),
         "lncde_nrde_param_count": (i, [i, i, i, i]),
         "lncde_nrde_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i]),
         "lncde_nrde_bwd_workspace_bytes": (sz, [i, i, i, i, i, i]),

@@ -326,10 +326,11 @@ class LogLinearCDE:
         ys = torch.empty((B, T, H), device=dev)
         diag = bs == 1 and C <= 8
         flags = _lib.call_flags()
-        if diag:
+        hmean, g_mean = torch.empty((B, H), device=dev), torch.empty((B, H), device=dev)
+        if diag:  # the read-out only sees the time mean: the fused kernels form it / take its cotangent directly
             vf_At = p[:nA].view(C, H).t().contiguous()
-            _lib.check(L.lncde_dlncde_fwd(s, _lib.ptr(vf_At), _lib.ptr(ls), _lib.ptr(y0), _lib.ptr(ys), B, T, D, H, C),
-                       "lncde_dlncde_fwd")
+            _lib.check(L.lncde_dlncde_fwd_mean(s, _lib.ptr(vf_At), _lib.ptr(ls), _lib.ptr(y0), _lib.ptr(ys), _lib.ptr(hmean),
+                                               B, T, D, H, C), "lncde_dlncde_fwd_mean")
         else:
             n_basis = len(self._basis_pairs) - 1
             br_kernels = n_basis <= 160
@@ -349,24 +350,25 @@ class LogLinearCDE:
             ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             _lib.check(L.lncde_linear_scan_fwd(s, _lib.ptr(lie), _lib.ptr(ls), _lib.ptr(y0), _lib.ptr(ys), B, T, D, nb, bs,
                                                n_basis, _lib.ptr(ws), nbytes, flags), "lncde_linear_scan_fwd")
-        hmean, g_mean = torch.empty((B, H), device=dev), torch.empty((B, H), device=dev)
-        _lib.check(L.lncde_time_mean_fwd(s, _lib.ptr(ys), _lib.ptr(hmean), B, T, H), "lncde_time_mean_fwd")
+        if not diag:
+            _lib.check(L.lncde_time_mean_fwd(s, _lib.ptr(ys), _lib.ptr(hmean), B, T, H), "lncde_time_mean_fwd")
         nb5 = max(L.lncde_readout_ce_workspace_bytes(B, H, nl), L.lncde_affine_bwd_workspace_bytes(B, C, H), 16)
         ws5 = torch.empty(nb5, device=dev, dtype=torch.uint8)
         _lib.check(L.lncde_readout_ce(s, _lib.ptr(hmean), H, p.data_ptr() + 4 * o2, p.data_ptr() + 4 * (o2 + nl * H),
                                       _lib.ptr(yc), None, _lib.ptr(g_mean), H, out.data_ptr() + 4 * o2, B, H, nl,
                                       _lib.ptr(ws5), nb5), "lncde_readout_ce")
-        g_ys = torch.empty((B, T, H), device=dev)
-        _lib.check(L.lncde_time_mean_bwd(s, _lib.ptr(g_mean), _lib.ptr(g_ys), B, T, H), "lncde_time_mean_bwd")
         g_y0 = torch.empty((B, H), device=dev)
         if diag:
             nbytes = L.lncde_dlncde_bwd_workspace_bytes(B, H, C)
             ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             g_At = torch.empty_like(vf_At)
-            _lib.check(L.lncde_dlncde_bwd(s, _lib.ptr(vf_At), _lib.ptr(ls), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_At),
-                                          _lib.ptr(g_y0), B, T, D, H, C, _lib.ptr(ws), nbytes), "lncde_dlncde_bwd")
+            _lib.check(L.lncde_dlncde_bwd_mean(s, _lib.ptr(vf_At), _lib.ptr(ls), _lib.ptr(ys), _lib.ptr(g_mean),
+                                               _lib.ptr(g_At), _lib.ptr(g_y0), B, T, D, H, C, _lib.ptr(ws), nbytes),
+                       "lncde_dlncde_bwd_mean")
             grads[:nA].view(C, H).copy_(g_At.t())
         else:
+            g_ys = torch.empty((B, T, H), device=dev)
+            _lib.check(L.lncde_time_mean_bwd(s, _lib.ptr(g_mean), _lib.ptr(g_ys), B, T, H), "lncde_time_mean_bwd")
             g_lie = torch.empty_like(lie)
             _lib.check(L.lncde_linear_scan_bwd(s, _lib.ptr(lie), _lib.ptr(ls), _lib.ptr(ys), _lib.ptr(g_ys), _lib.ptr(g_lie),
                                                _lib.ptr(g_y0), B, T, D, nb, bs, n_basis, _lib.ptr(ws), nbytes, flags),

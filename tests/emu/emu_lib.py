@@ -41,6 +41,8 @@ def lib():
         _lib.lncde_dlncde_bwd_workspace_bytes.restype = sz
         _lib.lncde_dlncde_fwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i]
         _lib.lncde_dlncde_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]
+        _lib.lncde_dlncde_fwd_mean.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, i, i]
+        _lib.lncde_dlncde_bwd_mean.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, vp, sz]
         _lib.lncde_nrde_param_count.argtypes = [i, i, i, i]
         _lib.lncde_nrde_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i]
         _lib.lncde_nrde_bwd_workspace_bytes.argtypes = [i, i, i, i, i, i]
@@ -271,6 +273,33 @@ def linear_scan(lie, logsig, y0, nb, bs, g_ys=None):
                                  n_basis, _p(ws), nbytes, _k2_flags(bs))
     assert st == 0, st
     return ys.copy(), g_lie.copy(), g_y0.copy()
+
+
+def dlncde_mean(vf_At, logsig, y0, g_mean):
+    """lncde_dlncde_fwd_mean + lncde_dlncde_bwd_mean: the fused diagonal LNCDE behind a mean-over-time read-out."""
+    L = lib()
+    H, Cn = vf_At.shape
+    B, T, D = logsig.shape
+
+    def dev(a):
+        g = guarded(a.shape)
+        g[...] = a
+        return g
+
+    A, ls, y0d, gm = dev(f32(vf_At)), dev(f32(logsig)), dev(f32(y0)), dev(f32(g_mean))
+    ys, ym = guarded((B, T, H)), guarded((B, H))
+    ys[...] = np.nan
+    ym[...] = np.nan
+    st = L.lncde_dlncde_fwd_mean(None, _p(A), _p(ls), _p(y0d), _p(ys), _p(ym), B, T, D, H, Cn)
+    assert st == 0, st
+    nbytes = L.lncde_dlncde_bwd_workspace_bytes(B, H, Cn)
+    ws = guarded((nbytes // 4,))
+    g_A, g_y0 = guarded((H, Cn)), guarded((B, H))
+    g_A[...] = np.nan
+    g_y0[...] = np.nan
+    st = L.lncde_dlncde_bwd_mean(None, _p(A), _p(ls), _p(ys), _p(gm), _p(g_A), _p(g_y0), B, T, D, H, Cn, _p(ws), nbytes)
+    assert st == 0, st
+    return ys.copy(), ym.copy(), g_A.copy(), g_y0.copy()
 
 
 def dlncde(vf_At, logsig, y0, g_ys=None):

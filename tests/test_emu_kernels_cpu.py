@@ -465,6 +465,36 @@ def test_emu_fused_diagonal_scan(B, T, H, C, D):
     assert rel_err(ys_e, ys_g) < 1e-5 and rel_err(gy_e, gy_g) < 5e-5 and rel_err(gA_e, gl_g.reshape(H, C)) < 5e-5
 
 
+@pytest.mark.parametrize("B,T,H,C,D", [(2, 40, 16, 3, 4), (3, 131, 128, 7, 29), (2, 1, 8, 2, 4), (70, 66, 40, 5, 9),
+                                       (33, 3, 130, 8, 12)])
+def test_emu_fused_diagonal_scan_mean_readout(B, T, H, C, D):
+    """lncde_dlncde_fwd_mean / _bwd_mean (the time mean formed by the scan kernel, its cotangent taken as one [B, H]
+    array) against the plain pair fed with the broadcast cotangent g_mean / T: same states, the mean within fp32
+    rounding of numpy's, bit-equal gradients per sample; B > 32 exercises the two-level batch reduction."""
+    rng = np.random.default_rng(B * 77 + T)
+    A = (rng.normal(size=(H, C)) * 0.3).astype(np.float32)
+    ls = (rng.normal(size=(B, T, D)) * 0.2).astype(np.float32)
+    ls[..., 0] = 0
+    y0 = rng.normal(size=(B, H)).astype(np.float32)
+    gm = rng.normal(size=(B, H)).astype(np.float32)
+    ys_m, ym, gA_m, gy_m = E.dlncde_mean(A, ls, y0, gm)
+    g_ys = np.broadcast_to((gm / np.float32(T))[:, None, :], (B, T, H)).copy()
+    ys_p, gA_p, gy_p = E.dlncde(A, ls, y0, g_ys)
+    assert np.array_equal(ys_m, ys_p)
+    assert rel_err(ym, ys_p.astype(np.float64).mean(1)) < 2e-6
+    assert np.array_equal(gy_m, gy_p)
+    assert rel_err(gA_m, gA_p) < 1e-6  # same per-sample partials; B > 32 adds them in chunks of 32
+    # fp64 recurrence (checks the batch reduction itself)
+    f = 1.0 + ls[..., 1:1 + C].astype(np.float64) @ A.astype(np.float64).T  # [B, T, H]
+    g = gm.astype(np.float64) / T
+    lam, gA = g.copy(), np.zeros((H, C))
+    ys64 = ys_p.astype(np.float64)
+    for t in range(T - 1, 0, -1):
+        gA += np.einsum("bh,bc->hc", lam * ys64[:, t - 1], ls[:, t, 1:1 + C].astype(np.float64))
+        lam = f[:, t] * lam + g
+    assert rel_err(gA_m, gA) < 5 * TOL and rel_err(gy_m, lam) < 5 * TOL
+
+
 # ------------------------------------------------------------------------------------------ reference-executed fixtures
 # tests/golden/ref_*.npz hold outputs of the reference's OWN code (tests/golden/make_golden_ref.py): the emulated
 # kernels are compared with them directly, the oracle only supplies the glue the reference does in its host code.
