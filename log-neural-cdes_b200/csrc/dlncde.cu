@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(kDThreads) dlncde_fwd_kernel(const float* __re
 // lam_{t-1} = f_t * lam_t + g_{t-1};  g_y0 = lam_0.  partial[b][h][c] is summed over b afterwards.
 // MEAN: g_ys[b][t][h] = g_mean[b][h] / T for every t (the cotangent of the mean over time): `g_ys` then points at the
 // [B][H] array and nothing of size [B][T][H] is written or read for it.
+// (Capping the kernel at 32 registers for 16 CTAs per SM - one wave at B = 2048 - was measured SLOWER, 1.30 vs 0.98 ms
+// per step: the unrolled loop needs its registers to keep four steps' loads in flight.)
 template <int C, bool MEAN>
 __global__ void __launch_bounds__(kDThreads) dlncde_bwd_kernel(const float* __restrict__ vf_At,
                                                                const float* __restrict__ logsig,
