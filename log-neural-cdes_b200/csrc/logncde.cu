@@ -243,10 +243,7 @@ struct BwdParams {
 #include "logncde_v3.cuh"
 namespace lncde {
 
-static bool use_fast(int H, int C, int width, int n_hidden) {
-  static const bool disabled = getenv("LNCDE_DISABLE_FAST") != nullptr;
-  return !disabled && fast::shape_supported(H, C, width, n_hidden);
-}
+static bool use_fast(int H, int C, int width, int n_hidden) { return fast::shape_supported(H, C, width, n_hidden); }
 
 struct RevBufs {
   float* g;        // [H] cotangent of G

@@ -798,10 +798,9 @@ int lncde_logsig_fwd(void* stream, const float* data, float* logsig, int B, int 
         case 8: return launch_levy_tma<8>(st, p, depth);
       }
     }
-    static const int wt_env = getenv("LNCDE_LEVY_WT") ? atoi(getenv("LNCDE_LEVY_WT")) : 0;
     // measured on B200 (scripts/k1_sweep.py): 32-window, single-warp CTAs give the best overlap of
     // the load / walk / store phases across the ~21 CTAs resident per SM (63.8 % vs 59.7 % at 128)
-    int WT = wt_env > 0 ? wt_env : 32;
+    int WT = 32;
     while (WT > 32 && (size_t)(C + (size_t)WT * p.stride) * 4 > 80 * 1024) WT >>= 1;
     if (WT > 128) WT = 128;
     p.WT = WT;
