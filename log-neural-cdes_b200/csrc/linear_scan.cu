@@ -617,7 +617,8 @@ static size_t pscan_scratch_offset(int B, int T, int nb, int bs, int n_basis) {
 }
 // Kernel level of the dense model for this call: 0 = generic FFMA kernels (flows and dF materialised), 2 = warp-level
 // tensor pipe (mma.sync, 3xTF32) flow build + lam-only reverse sweep + triple-product bracket gradient, 3 = the same
-// with the flow build on tcgen05 (flow_tcgen05.cu).  Measured on B200, EigenWorms DE step: 11.0 / 7.3 / 5.7 ms.
+// with the flow build and the bracket gradient on tcgen05 (flow_tcgen05.cu, dlie_tcgen05.cu).  Measured on B200,
+// EigenWorms DE step with the cluster sweeps: 11.0 / 5.3 / 2.7 ms.
 static int dense_level(unsigned flags, int N, int bs) {
   if ((flags & LNCDE_FLAG_GENERIC) || bs < 64) return 0;
   if (!(flags & LNCDE_FLAG_K2_MMA_SYNC) && flow_tcgen05_shape(N, bs)) return 3;
