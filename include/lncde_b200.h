@@ -166,7 +166,10 @@ int lncde_nrde_bwd(void* stream, const float* params, const float* logsig, const
  * between, and the same `flags` (it reads F_t; the generic kernels overwrite it with dF_t).
  * Kernels by block size: bs <= 8 and T > 65: scans parallel in time (chunk products, boundary recurrence over the chunks,
  * per-chunk sweeps); bs | 32: warp-shuffle scans; bs >= 64: flows from tcgen05 (bs % 128 == 0) or mma.sync tensor
- * cores with 3xTF32 split precision, TMA-ring scans, lam-only reverse sweep + triple-product bracket gradient.          */
+ * cores with 3xTF32 split precision; the two sequential sweeps on thread-block clusters of 8 / 4 / 2 CTAs per series
+ * (batches of fewer than 75 series; TMA ring of flow slices, state exchanged with st.async onto the peers' mbarriers) or
+ * one CTA per series; lam-only reverse sweep + triple-product bracket gradient on tcgen05 (any n_basis) or mma.sync
+ * (n_basis <= 36).                                                                                                     */
 size_t lncde_linear_scan_workspace_bytes(int B, int T, int nb, int bs, int n_basis);
 int lncde_linear_scan_fwd(void* stream, const float* lie, const float* logsig, const float* y0,
                           float* ys, int B, int T, int D, int nb, int bs, int n_basis,
