@@ -27,7 +27,7 @@ python scripts/variant_check.py --no-oracle --no-parity --only k2 > $O/r2n_plain
 ncu --set full --clock-control none -k regex:'dlncde_' -s 8 -c 2 -o $O/r2_full_k2d python scripts/variant_check.py --no-oracle --no-parity --only k2 > $O/r2n_c2.log 2>&1
 keep r2_full_k2d
 $B --workload eigenworms_de > $O/r2n_plain4.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'flow_build_tcgen05|de_pack|scan_fwd_tma|scan_bwd_tma_lam|dlie_triple' -s 10 -c 6 \
+ncu --set full --clock-control none --import-source on -k regex:'flow_build_tcgen05|de_pack|scan_fwd_cluster|scan_lam_cluster|dlie_t' -s 10 -c 6 \
     -o $O/r2_full_k2_de $B --workload eigenworms_de > $O/r2n_c3.log 2>&1
 keep r2_full_k2_de
 $B --workload eigenworms_bd > $O/r2n_plain5.log 2>&1 &&
